@@ -1,0 +1,292 @@
+"""TenNetLib sweep drivers on the CPU (oracle; test infrastructure only).
+
+Line-by-line restatement (not a copy) of the control flow of
+  /root/reference/src/mps/state_envs.jl:18-27,364-378   StateEnvs, position!, product
+  /root/reference/src/base/solver.jl:23-43              eig_solver defaults
+  /root/reference/src/mps/update_site.jl:13-90,231-277  halfsweep_done, _update_two_site!, update_position!
+  /root/reference/src/mps/sweep.jl:26-196               SweepData, fullsweep!
+  /root/reference/src/mps/dmrg.jl:26-227                DMRGParams, dmrg!
+plus ITensorMPS `replacebond!` / `orthogonalize!` (third-party, restated from their published
+behaviour: factorize(phi, inds(M[b]); ortho, which_decomp=nothing, eigen_perturbation), then
+`M[b+1] ./= norm` (ortho left) or `M[b] ./= norm` (ortho right) when normalize).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+
+from .blocksparse import BSTensor, contract, factorize, inner
+from .krylov import eigsolve_lanczos
+from .projmpo import ProjMPO, drho_matrices
+
+FLOAT64_THRESHOLD = 1e-15          # src/base/global_variables.jl:10-26
+
+
+class MPS:
+    """Tensors + orthogonality limits (ITensorMPS `MPS`: llim/rlim)."""
+
+    def __init__(self, tensors: Sequence[BSTensor], llim: int = 0, rlim: int | None = None):
+        self.t: List[BSTensor] = list(tensors)
+        self.llim = llim
+        self.rlim = len(self.t) + 1 if rlim is None else rlim
+
+    def __len__(self):
+        return len(self.t)
+
+    def __getitem__(self, j):          # 1-based like the reference
+        return self.t[j - 1]
+
+    def __setitem__(self, j, v):
+        self.t[j - 1] = v
+
+    def isortho(self):
+        return self.llim + 2 == self.rlim
+
+    def orthocenter(self):
+        assert self.isortho()
+        return self.llim + 1
+
+    def copy(self):
+        return MPS([x.copy() for x in self.t], self.llim, self.rlim)
+
+
+def orthogonalize(psi: MPS, j: int) -> MPS:
+    """ITensorMPS `orthogonalize!(psi, j)`: gauge moves without truncation."""
+    N = len(psi)
+    while psi.llim < j - 1:
+        b = psi.llim + 1
+        A = psi[b]
+        L, R, _, _ = factorize(A, A.inds[:2], ortho="left", which_decomp="svd", cutoff=None, maxdim=None)
+        psi[b] = L
+        psi[b + 1] = contract(R, psi[b + 1])
+        psi.llim = b
+        if psi.rlim < b + 2:
+            psi.rlim = b + 2
+    while psi.rlim > j + 1:
+        b = psi.rlim - 1
+        A = psi[b]
+        L, R, _, _ = factorize(A, A.inds[:1], ortho="right", which_decomp="svd", cutoff=None, maxdim=None)
+        psi[b] = R
+        psi[b - 1] = contract(psi[b - 1], L)
+        psi.rlim = b
+        if psi.llim > b - 2:
+            psi.llim = b - 2
+    return psi
+
+
+def replacebond(psi: MPS, b: int, phi: BSTensor, *, maxdim, mindim, cutoff, eigen_perturbation, ortho,
+                normalize, which_decomp=None, svd_alg="divide_and_conquer"):
+    left = [ix for ix in psi[b].inds if ix in phi.inds]
+    tags = psi[b].inds[2].tags
+    L, R, spec, _ = factorize(phi, left, ortho=ortho, maxdim=maxdim, mindim=mindim, cutoff=cutoff,
+                              eigen_perturbation=eigen_perturbation, which_decomp=which_decomp, tags=tags)
+    psi[b] = L
+    psi[b + 1] = R
+    if ortho == "left":
+        if psi.llim == b - 1:
+            psi.llim += 1
+        if psi.rlim == b + 1:
+            psi.rlim += 1
+        if normalize:
+            psi[b + 1] = psi[b + 1].scale(1.0 / psi[b + 1].norm())
+    elif ortho == "right":
+        if psi.llim == b:
+            psi.llim -= 1
+        if psi.rlim == b + 2:
+            psi.rlim -= 1
+        if normalize:
+            psi[b] = psi[b].scale(1.0 / psi[b].norm())
+    else:
+        raise ValueError(ortho)
+    return spec
+
+
+class StateEnvs:
+    """src/mps/state_envs.jl:18-27 with PH = ProjMPO (constructor :54-60 copies psi)."""
+
+    def __init__(self, psi: MPS, H: Sequence[BSTensor]):
+        self.psi = psi.copy()
+        self.PH = ProjMPO(H)
+
+    def __len__(self):
+        return len(self.psi)
+
+    def nsite(self):
+        return self.PH.nsite
+
+    def set_nsite(self, n):
+        self.PH.set_nsite(n)
+
+    def position(self, pos):
+        self.PH.position(self.psi.t, pos)
+
+    def product(self, v):
+        return self.PH.product(v)
+
+    __call__ = product
+
+
+def eig_solver(env, phi0, time_step=None, **kw):
+    """src/base/solver.jl:23-43."""
+    val, vec, info = eigsolve_lanczos(env, phi0,
+                                      tol=kw.get("solver_tol", 1e-14),
+                                      krylovdim=kw.get("solver_krylovdim", 5),
+                                      maxiter=kw.get("solver_maxiter", 2),
+                                      eager=kw.get("solver_eager", False),
+                                      which=kw.get("solver_which_eigenvalue", "SR"))
+    if kw.get("solver_check_convergence", False) and info["converged"] < 1:
+        raise RuntimeError("`eig_solver()` not converged !!")
+    return val, vec
+
+
+def halfsweep_done(N, pos, nsite, ortho):
+    if pos == 1 and ortho == "right":
+        return True
+    if pos == N and ortho == "left" and nsite == 1:
+        return True
+    if pos == N - 1 and ortho == "left" and nsite == 2:
+        return True
+    return False
+
+
+def _update_two_site(sysenv: StateEnvs, solver, pos, ortho, time_step, normalize, maxdim, mindim, cutoff,
+                     svd_alg, noise, reverse_step, **kw):
+    psi = sysenv.psi
+    assert 0 < pos < len(sysenv)
+    assert (psi.orthocenter() == pos and ortho == "left") or (psi.orthocenter() == pos + 1 and ortho == "right")
+    sysenv.set_nsite(2)
+    phi = contract(psi[pos], psi[pos + 1])
+    sysenv.position(pos)
+    energy, phi = solver(sysenv, phi, time_step, **kw)
+    if normalize:
+        phi = phi.scale(1.0 / phi.norm())
+    if np.isnan(energy):
+        energy = float(np.real(inner(phi, sysenv.PH(phi))))
+    drho = None
+    if abs(noise) > FLOAT64_THRESHOLD:
+        d = drho_matrices(sysenv.PH.noiseterm(phi, ortho), noise)
+        drho = d if ortho == "left" else {tuple(-x for x in q): M for q, M in d.items()}
+    spec = replacebond(psi, pos, phi, maxdim=maxdim, mindim=mindim, cutoff=cutoff, eigen_perturbation=drho,
+                       ortho=ortho, normalize=normalize, which_decomp=None, svd_alg=svd_alg)
+    if reverse_step and not halfsweep_done(len(sysenv), pos, 2, ortho):
+        raise NotImplementedError("TDVP reverse step: SURVEY.md section 8(f) next row")
+    return energy, spec.truncerr, spec.eigs
+
+
+def update_position(sysenv: StateEnvs, solver, pos, nsite, ortho, **kw):
+    """src/mps/update_site.jl:231-277 (two-site branch; one-site is a section 8(f) 'next' row)."""
+    time_step = kw.get("time_step", None)
+    normalize = kw.get("normalize", True)
+    maxdim = kw.get("maxdim", None)
+    mindim = kw.get("mindim", 1)
+    cutoff = kw.get("cutoff", FLOAT64_THRESHOLD)
+    svd_alg = kw.get("svd_alg", "divide_and_conquer")
+    noise = kw.get("noise", 0.0)
+    reverse_step = kw.get("reverse_step", time_step is not None)
+    if noise > 0 and reverse_step:
+        raise RuntimeError(f"`updatePosition()` :: `noise={noise}` cannot be greater than zero "
+                           f"for `reverse_step={reverse_step}` !!")
+    kw2 = {k: v for k, v in kw.items() if k not in ("time_step", "normalize", "maxdim", "mindim", "cutoff",
+                                                   "svd_alg", "noise", "reverse_step")}
+    if nsite == 2:
+        return _update_two_site(sysenv, solver, pos, ortho, time_step, normalize, maxdim, mindim, cutoff,
+                                svd_alg, noise, reverse_step, **kw2)
+    raise NotImplementedError(f"`update_position()` with `nsite={nsite}` not implemented !!")
+
+
+class SweepData:
+    def __init__(self):
+        self.sweepcount = 0
+        self.maxchi: List[int] = []
+        self.energy: List[float] = []
+        self.entropy: List[float] = []
+        self.maxtruncerr: List[float] = []
+        self.lasteigs: List[np.ndarray] = []
+
+
+def _entropy(p):
+    """src/mps/measure.jl:4-20 (von Neumann entropy of a normalised spectrum)."""
+    p = np.asarray(p, dtype=np.float64)
+    p = p[p > 0]
+    return float(-np.sum(p * np.log(p)))
+
+
+def fullsweep(sysenv: StateEnvs, solver, nsite: int, swdata: SweepData, **kw):
+    """src/mps/sweep.jl:94-196."""
+    psi = sysenv.psi
+    if (not psi.isortho()) or psi.orthocenter() != 1:
+        orthogonalize(psi, 1)
+    energy = np.nan
+    maxtruncerr = 0.0
+    swdata.sweepcount += 1
+    N = len(sysenv)
+    lasteigs = [None] * (N - 1)
+    for bond in range(1, N):
+        energy, err, _ = update_position(sysenv, solver, bond, nsite, "left", **kw)
+        maxtruncerr = max(err, maxtruncerr)
+    for bond in range(N - 1, 0, -1):
+        energy, err, eigs = update_position(sysenv, solver, bond, nsite, "right", **kw)
+        lasteigs[bond - 1] = eigs
+        maxtruncerr = max(err, maxtruncerr)
+    swdata.lasteigs = lasteigs
+    swdata.maxchi.append(max(A.inds[2].dim for A in psi.t[:-1]))
+    swdata.energy.append(energy)
+    mideigs = lasteigs[N // 2 - 1]
+    swdata.entropy.append(_entropy(mideigs / np.sum(mideigs)))
+    swdata.maxtruncerr.append(maxtruncerr)
+    if swdata.sweepcount > 1:
+        return swdata.energy[-1] - swdata.energy[-2], swdata.entropy[-1] - swdata.entropy[-2]
+    return np.nan, np.nan
+
+
+class DMRGParams:
+    """src/mps/dmrg.jl:26-33,72-102."""
+
+    def __init__(self, *, maxdim, nsweeps, cutoff=FLOAT64_THRESHOLD, noise=0.0, noisedecay=1.0,
+                 disable_noise_after=-1):
+        n = len(nsweeps)
+        vec = lambda x, T: [T(v) for v in x] if isinstance(x, (list, tuple)) else [T(x)] * n
+        self.maxdim = list(maxdim)
+        self.nsweeps = list(nsweeps)
+        self.cutoff = vec(cutoff, float)
+        self.noise = vec(noise, float)
+        self.noisedecay = vec(noisedecay, float)
+        self.disable_noise_after = vec(disable_noise_after, int)
+        if not (len(self.maxdim) == n == len(self.cutoff) == len(self.noise) == len(self.noisedecay)
+                == len(self.disable_noise_after)):
+            raise ValueError("`DMRGParams()` :: Size mismatch in input vectors !!")
+
+
+def dmrg_(sysenv: StateEnvs, params: DMRGParams, nsite: int, **kw) -> SweepData:
+    """`dmrg!` src/mps/dmrg.jl:148-227 (stage / sweep loop, noise decay; error goals included)."""
+    enerrgoal = kw.pop("energyErrGoal", None)
+    enterrgoal = kw.pop("entropyErrGoal", None)
+    kw.pop("outputlevel", None)
+    swdata = SweepData()
+    for ii in range(len(params.nsweeps)):
+        errGoalMet = False
+        maxdim, cutoff, noise = params.maxdim[ii], params.cutoff[ii], params.noise[ii]
+        noisedecay, disable_after = params.noisedecay[ii], params.disable_noise_after[ii]
+        for jj in range(1, params.nsweeps[ii] + 1):
+            enerr, enterr = fullsweep(sysenv, eig_solver, nsite, swdata, maxdim=maxdim, cutoff=cutoff,
+                                      noise=noise, **kw)
+            if enerrgoal is not None and enterrgoal is not None:
+                errGoalMet = abs(enerr) < abs(enerrgoal) and abs(enterr) < abs(enterrgoal)
+            elif enerrgoal is not None:
+                errGoalMet = abs(enerr) < abs(enerrgoal)
+            # (entropy-only goal: result discarded by the reference, dmrg.jl:191)
+            if errGoalMet and abs(noise) < FLOAT64_THRESHOLD:
+                break
+            if jj == disable_after:
+                noise = 0.0
+            noise /= noisedecay
+            if noise < 100 * FLOAT64_THRESHOLD:
+                noise = 0.0
+    return swdata
+
+
+def dmrg2(psi0: MPS, H, params: DMRGParams, **kw):
+    sysenv = StateEnvs(psi0, H)
+    sw = dmrg_(sysenv, params, 2, **kw)
+    return sw.energy[-1], sysenv.psi, sw

@@ -1,0 +1,134 @@
+"""Projected-MPO environments on the CPU (oracle; test infrastructure only).
+
+Restates ITensorMPS `ProjMPO` (third-party, not vendored; reached from `StateEnvs{ProjMPO}`
+at /root/reference/src/mps/state_envs.jl:54-60,364-378) in the exact contraction order the
+reference executes:
+
+* `product(v)`   = noprime(v * L * W_j [* W_{j+1}] * R)                 
+* `_makeL!`      : L_j = L_{j-1} * psi[j] * H[j] * dag(prime(psi[j]))    
+* `_makeR!`      : mirror image;  watermarks lpos / rpos as in
+                   src/mps/projcouplingmodel.jl:123-129,212-218 (same contract as ProjMPO)
+* `noiseterm`    : nt = L*W_j*phi (ortho left) | phi*W_{j+1}*R (right); nt * dag(noprime(nt)).
+
+The same pattern is visible in-tree in `ProjMPS2.contract` (src/mps/projmps2.jl:159-173).
+Boundary environments are explicit 1x1x1 tensors on the dim-1 boundary links (oracle/models.py)
+instead of ITensors' `OneITensor`, which changes no arithmetic.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+
+from .blocksparse import BSTensor, Index, contract, matricize
+
+
+def _edge(A: BSTensor, W: BSTensor, left: bool) -> BSTensor:
+    """1x1x1 boundary environment facing tensor A / MPO tensor W on their outer links."""
+    k = 0 if left else -1
+    a, w = A.inds[k], W.inds[k]
+    inds = [a.prime().copy(dir=a.dir), w.copy(dir=-w.dir), a.copy(dir=-a.dir)]
+    return BSTensor(inds, {(0, 0, 0): np.ones((1, 1, 1))})
+
+
+class ProjMPO:
+    def __init__(self, H: Sequence[BSTensor]):
+        self.H = list(H)
+        self.N = len(H)
+        self.lpos = 0
+        self.rpos = self.N + 1
+        self.nsite = 2
+        self.LR: List[BSTensor | None] = [None] * self.N     # LR[j-1] holds L_j or R_j (1-based j)
+        self._Ledge = None
+        self._Redge = None
+
+    # -- accessors (1-based positions as in the reference)
+    def site_range(self):
+        return range(self.lpos + 1, self.rpos)
+
+    def lproj(self):
+        return self._Ledge if self.lpos <= 0 else self.LR[self.lpos - 1]
+
+    def rproj(self):
+        return self._Redge if self.rpos >= self.N + 1 else self.LR[self.rpos - 1]
+
+    def set_nsite(self, n: int):
+        self.nsite = n
+
+    # -- environment update
+    def _ensure_edges(self, psi):
+        if self._Ledge is None or self._Ledge.inds[2] != psi[0].inds[0]:
+            self._Ledge = _edge(psi[0], self.H[0], True)
+        if self._Redge is None or self._Redge.inds[2] != psi[-1].inds[-1]:
+            self._Redge = _edge(psi[-1], self.H[-1], False)
+
+    def makeL(self, psi, k: int):
+        self._ensure_edges(psi)
+        ll = self.lpos
+        if ll >= k:
+            self.lpos = k
+            return
+        ll = max(ll, 0)
+        L = self.lproj()
+        while ll < k:
+            A = psi[ll]
+            L = contract(contract(contract(L, A), self.H[ll]), A.prime().dag())
+            self.LR[ll] = L
+            ll += 1
+        self.lpos = k
+
+    def makeR(self, psi, k: int):
+        self._ensure_edges(psi)
+        rl = self.rpos
+        if rl <= k:
+            self.rpos = k
+            return
+        rl = min(rl, self.N + 1)
+        R = self.rproj()
+        while rl > k:
+            A = psi[rl - 2]
+            R = contract(contract(contract(R, A), self.H[rl - 2]), A.prime().dag())
+            self.LR[rl - 2] = R
+            rl -= 1
+        self.rpos = k
+
+    def position(self, psi, pos: int):
+        self.makeL(psi, pos - 1)
+        self.makeR(psi, pos + self.nsite)
+
+    # -- H_eff apply
+    def contract_v(self, v: BSTensor) -> BSTensor:
+        Hv = contract(v, self.lproj())
+        for j in self.site_range():
+            Hv = contract(Hv, self.H[j - 1])
+        return contract(Hv, self.rproj())
+
+    def product(self, v: BSTensor) -> BSTensor:
+        Pv = self.contract_v(v)
+        if Pv.rank != v.rank:
+            raise RuntimeError("The order of the ProjMPO-ITensor product P*v is not equal to the order of v")
+        return Pv.noprime()
+
+    __call__ = product
+
+    # -- noise term (density-matrix perturbation), returned per charge group of the kept side
+    def noiseterm(self, phi: BSTensor, ortho: str) -> BSTensor:
+        if self.nsite != 2:
+            raise RuntimeError("noise term only defined for 2-site ProjMPO")
+        sr = list(self.site_range())
+        if ortho == "left":
+            AL = contract(self.lproj(), self.H[sr[0] - 1])
+            nt = contract(AL, phi)
+        elif ortho == "right":
+            AR = contract(self.H[sr[-1] - 1], self.rproj())
+            nt = contract(phi, AR)
+        else:
+            raise ValueError(f"In noiseterm, got ortho = {ortho}, only supports `left` and `right`")
+        return contract(nt, nt.noprime().dag())
+
+
+def drho_matrices(drho: BSTensor, scale: float):
+    """Per-charge matrices of scale*drho, rows = primed index group (layout of `matricize`)."""
+    primed = [ix for ix in drho.inds if ix.plev > 0]
+    _, groups, _, _, _ = matricize(drho, primed)
+    return {q: scale * M for q, (M, _, _) in groups.items()}
