@@ -1,0 +1,100 @@
+/* tnl_b200 -- C ABI of the B200-native DMRG hot path (drop-in boundary for TenNetLib.jl).
+ *
+ * Every entry point returns 0 on success, non-zero on error (2 = invalid argument / index
+ * mismatch, 3 = CUDA, 4 = cuSOLVER, 1 = other); tnl_last_error() gives the message, which the
+ * Julia shim rethrows as `error(msg)` (reference convention: src/mps/update_site.jl:39-41,247-250,
+ * src/mps/projcouplingmodel.jl:367-381).  Handles are opaque pointers owned by the library; host
+ * buffers passed in are only read/written during the call.  Plain pointers and sizes only -- no
+ * torch / CUDA types.  Positions are 1-based like the reference.
+ *
+ * Host tensor format = NDTensors BlockSparse: flat `data`, per block the
+ * 0-based sector number of every index (`coords`, block-major) and the 0-based element `offset`;
+ * each block is dense column-major.  QN indices are described by tnl_index_t.
+ */
+#ifndef TNL_B200_H
+#define TNL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tnl_ctx_s* tnl_ctx_t;
+typedef struct tnl_tensor_s* tnl_tensor_t;
+typedef struct tnl_env_s* tnl_env_t;
+
+/* One QN index: ITensors `Index{Vector{Pair{QN,Int}}}` -- sector dims, nq charges per sector, arrow. */
+typedef struct {
+  int32_t nsect;
+  int32_t dir;          /* +1 = Out, -1 = In */
+  const int32_t* dims;  /* [nsect] */
+  const int32_t* qns;   /* [nsect * nq] */
+} tnl_index_t;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int tnl_ctx_create(int device, tnl_ctx_t* ctx);
+int tnl_ctx_destroy(tnl_ctx_t ctx);
+const char* tnl_last_error(tnl_ctx_t ctx); /* ctx may be NULL: last error of the calling thread */
+/* out[0..7] = gemm_flops, transform_flops, vec_bytes, transform_bytes, kernel launches, gemm launches,
+ * H_eff applies, reserved.  Algorithmic counts. */
+int tnl_get_counters(tnl_ctx_t ctx, double* out8);
+int tnl_reset_counters(tnl_ctx_t ctx);
+int tnl_ctx_sync(tnl_ctx_t ctx);
+/* CUDA-event timing on the library's own stream (bench.py times kernels here, not on torch's stream). */
+int tnl_timer_start(tnl_ctx_t ctx);
+int tnl_timer_stop(tnl_ctx_t ctx, double* milliseconds);
+
+/* ---- tensors: ITensor <-> device (replaces nothing in the reference; it is the marshalling the shim needs) */
+int tnl_tensor_import(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t* inds, int64_t nblocks,
+                      const int32_t* coords, const int64_t* offsets, const double* data, int32_t nrow,
+                      tnl_tensor_t* out);
+int tnl_tensor_create(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t* inds, int32_t nrow,
+                      tnl_tensor_t* out); /* all symmetry-allowed blocks, zero */
+int tnl_tensor_free(tnl_tensor_t t);
+int tnl_tensor_copy(tnl_tensor_t t, tnl_tensor_t* out);
+int tnl_tensor_rank(tnl_tensor_t t, int32_t* rank, int32_t* nq);
+int tnl_tensor_index(tnl_tensor_t t, int32_t which, int32_t* nsect, int32_t* dir, int32_t* dims, int32_t* qns,
+                     int32_t cap);
+int tnl_tensor_export_size(tnl_tensor_t t, int64_t* nblocks, int64_t* nelem);
+int tnl_tensor_export(tnl_tensor_t t, int32_t* coords, int64_t* offsets, double* data);
+int tnl_tensor_fill_random(tnl_tensor_t t, uint64_t seed); /* uniform [-1,1), counter based */
+
+/* ---- Krylov vector interface (VectorInterface inner / norm / scale!! / add!! on ITensors) ---- */
+int tnl_vec_dot(tnl_tensor_t x, tnl_tensor_t y, double* out);
+int tnl_vec_norm(tnl_tensor_t x, double* out);
+int tnl_vec_scale(tnl_tensor_t x, double a);
+int tnl_vec_axpy(tnl_tensor_t y, tnl_tensor_t x, double a); /* y += a*x */
+
+/* ---- StateEnvs{ProjMPO}: src/mps/state_envs.jl:18-27,54-60 ---------------------------------- */
+int tnl_env_create(tnl_ctx_t ctx, int32_t nsites, tnl_env_t* env);
+int tnl_env_destroy(tnl_env_t env);
+/* MPO tensor W_site(wl, s', s, wr) in host format (StateEnvs(psi, H::MPO), state_envs.jl:54-60) */
+int tnl_env_set_site_op(tnl_env_t env, int32_t site, int32_t nq, const tnl_index_t* inds4, int64_t nblocks,
+                        const int32_t* coords, const int64_t* offsets, const double* data);
+/* MPS tensor A_site(l, s, r); the env shares the tensor (no copy) */
+int tnl_env_set_state(tnl_env_t env, int32_t site, tnl_tensor_t a);
+int tnl_env_get_state(tnl_env_t env, int32_t site, tnl_tensor_t* out); /* getpsi, state_envs.jl:36 */
+int tnl_env_set_nsite(tnl_env_t env, int32_t nsite);                   /* set_nsite!, state_envs.jl:352-355 */
+int tnl_env_position(tnl_env_t env, int32_t pos);                      /* position!, state_envs.jl:364-367 */
+int tnl_env_orthogonalize(tnl_env_t env); /* orthogonalize!(psi, 1) of a fresh MPS, sweep.jl:100-102 */
+int tnl_env_make_phi(tnl_env_t env, int32_t pos, tnl_tensor_t* phi); /* psi[pos]*psi[pos+1], update_site.jl:46 */
+int tnl_env_apply_flops(tnl_env_t env, double* flops); /* algorithmic flops of one apply at this position */
+
+/* product(sysenv, v) = H_eff v : state_envs.jl:376-378 -> ProjMPO.product */
+int tnl_heff_apply(tnl_env_t env, tnl_tensor_t v, tnl_tensor_t* out);
+/* eig_solver: src/base/solver.jl:23-43 -> KrylovKit.eigsolve(env, phi, 1, :SR; Lanczos).  phi is updated in place. */
+int tnl_eigsolve_lanczos(tnl_env_t env, tnl_tensor_t phi, double tol, int32_t krylovdim, int32_t maxiter,
+                         int32_t eager, double* eval, int32_t* converged, int32_t* numops, int32_t* numiter,
+                         double* normres);
+/* real(scalar(dag(phi) * PH(phi))) : src/mps/update_site.jl:51-57 */
+int tnl_expectation(tnl_env_t env, tnl_tensor_t phi, double* e);
+/* noiseterm + replacebond! : src/mps/update_site.jl:59-76.  which_decomp: 0 = reference rule, 1 = svd, 2 = eigen.
+ * eigs receives spec.eigs (kept spectrum, descending), at most `cap` values; *neigs = number kept. */
+int tnl_replacebond(tnl_env_t env, int32_t pos, tnl_tensor_t phi, int32_t ortho_left, int64_t maxdim, int64_t mindim,
+                    double cutoff, double noise, int32_t normalize, int32_t which_decomp, double* truncerr,
+                    double* eigs, int64_t cap, int64_t* neigs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,96 @@
+"""ctypes binding of libtnl_b200.so (include/tnl_b200.h).  There is no CPU fallback: if the library is
+missing it is built with nvcc; if no GPU is visible `Context()` raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libtnl_b200.so")
+
+
+class TnlError(RuntimeError):
+    pass
+
+
+class tnl_index_t(C.Structure):
+    _fields_ = [("nsect", C.c_int32), ("dir", C.c_int32), ("dims", C.POINTER(C.c_int32)), ("qns", C.POINTER(C.c_int32))]
+
+
+_lib = None
+
+# name -> argtypes (restype is always int except tnl_last_error)
+_P = C.c_void_p
+_SIGS = {
+    "tnl_ctx_create": [C.c_int, C.POINTER(_P)],
+    "tnl_ctx_destroy": [_P],
+    "tnl_get_counters": [_P, C.POINTER(C.c_double)],
+    "tnl_reset_counters": [_P],
+    "tnl_ctx_sync": [_P],
+    "tnl_timer_start": [_P],
+    "tnl_timer_stop": [_P, C.POINTER(C.c_double)],
+    "tnl_tensor_import": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int64, _P, _P, _P, C.c_int32, C.POINTER(_P)],
+    "tnl_tensor_create": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int32, C.POINTER(_P)],
+    "tnl_tensor_free": [_P],
+    "tnl_tensor_copy": [_P, C.POINTER(_P)],
+    "tnl_tensor_rank": [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+    "tnl_tensor_index": [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, _P, C.c_int32],
+    "tnl_tensor_export_size": [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+    "tnl_tensor_export": [_P, _P, _P, _P],
+    "tnl_tensor_fill_random": [_P, C.c_uint64],
+    "tnl_vec_dot": [_P, _P, C.POINTER(C.c_double)],
+    "tnl_vec_norm": [_P, C.POINTER(C.c_double)],
+    "tnl_vec_scale": [_P, C.c_double],
+    "tnl_vec_axpy": [_P, _P, C.c_double],
+    "tnl_env_create": [_P, C.c_int32, C.POINTER(_P)],
+    "tnl_env_destroy": [_P],
+    "tnl_env_set_site_op": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int64, _P, _P, _P],
+    "tnl_env_set_state": [_P, C.c_int32, _P],
+    "tnl_env_get_state": [_P, C.c_int32, C.POINTER(_P)],
+    "tnl_env_set_nsite": [_P, C.c_int32],
+    "tnl_env_position": [_P, C.c_int32],
+    "tnl_env_orthogonalize": [_P],
+    "tnl_env_make_phi": [_P, C.c_int32, C.POINTER(_P)],
+    "tnl_env_apply_flops": [_P, C.POINTER(C.c_double)],
+    "tnl_heff_apply": [_P, _P, C.POINTER(_P)],
+    "tnl_eigsolve_lanczos": [_P, _P, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double),
+                             C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)],
+    "tnl_expectation": [_P, _P, C.POINTER(C.c_double)],
+    "tnl_replacebond": [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int32,
+                        C.c_int32, C.POINTER(C.c_double), _P, C.c_int64, C.POINTER(C.c_int64)],
+}
+EXPORTED = sorted(list(_SIGS) + ["tnl_last_error"])
+
+
+def so_path() -> str:
+    return _SO
+
+
+def load(build_if_missing: bool = True):
+    """Load the CUDA library.  Raises if it cannot be built/loaded -- never falls back to the CPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_tnl_build", os.path.join(_HERE, "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    if not os.path.exists(_SO):
+        raise TnlError(f"{_SO} is missing: the CUDA extension is required (no CPU fallback)")
+    lib = C.CDLL(_SO, mode=C.RTLD_LOCAL)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.tnl_last_error.argtypes = [_P]
+    lib.tnl_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc: int, ctx=None):
+    if rc != 0:
+        msg = load().tnl_last_error(ctx)
+        raise TnlError(f"tnl_b200 error {rc}: {msg.decode() if msg else '?'}")

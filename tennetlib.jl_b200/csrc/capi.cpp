@@ -1,0 +1,292 @@
+// extern "C" boundary of libtnl_b200.so -- see include/tnl_b200.h for the contract and the
+// reference interfaces each entry point replaces.
+#include "../../include/tnl_b200.h"
+
+#include <cmath>
+#include <cstring>
+
+#include "env.hpp"
+
+using namespace tnl;
+
+struct tnl_ctx_s { Ctx ctx; cudaEvent_t e0 = nullptr, e1 = nullptr; explicit tnl_ctx_s(int dev) : ctx(dev) {} };
+struct tnl_tensor_s { TensorP t; };
+struct tnl_env_s { Env env; tnl_env_s(Ctx* c, int n) : env(c, n) {} };
+
+static thread_local std::string g_last_error;
+
+template <class F>
+static int guard(Ctx* ctx, F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    if (ctx) ctx->last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    if (ctx) ctx->last_error = e.what();
+    return 1;
+  }
+}
+
+static std::vector<Index> make_inds(int rank, int nq, const tnl_index_t* inds) {
+  TNL_CHECK(rank >= 1 && rank <= MAXR, "rank out of range");
+  TNL_CHECK(nq >= 1 && nq <= MAXQ, "number of conserved charges out of range");
+  std::vector<Index> out(rank);
+  for (int k = 0; k < rank; k++) {
+    TNL_CHECK(inds[k].nsect >= 1 && inds[k].nsect < 1024, "sector count out of range");
+    TNL_CHECK(inds[k].dir == 1 || inds[k].dir == -1, "arrow must be +1 or -1");
+    out[k].nq = nq;
+    out[k].dir = inds[k].dir;
+    for (int s = 0; s < inds[k].nsect; s++) {
+      TNL_CHECK(inds[k].dims[s] >= 1, "sector dims must be positive");
+      out[k].dims.push_back(inds[k].dims[s]);
+      Charge q = charge_zero();
+      for (int a = 0; a < nq; a++) q[a] = inds[k].qns[s * nq + a];
+      out[k].qns.push_back(q);
+    }
+  }
+  return out;
+}
+
+static HostBlocks make_host(int rank, int nq, const tnl_index_t* inds, int64_t nblocks, const int32_t* coords,
+                            const int64_t* offsets, const double* data) {
+  HostBlocks hb;
+  hb.rank = rank;
+  hb.inds = make_inds(rank, nq, inds);
+  for (int64_t n = 0; n < nblocks; n++) {
+    std::vector<int> c(rank);
+    for (int k = 0; k < rank; k++) c[k] = coords[n * rank + k];
+    hb.coords.push_back(c);
+    hb.offsets.push_back(offsets[n]);
+  }
+  hb.data = data;
+  return hb;
+}
+
+extern "C" {
+
+int tnl_ctx_create(int device, tnl_ctx_t* out) {
+  return guard(nullptr, [&] {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw Error(3, "tnl_b200 needs a CUDA device: no GPU visible (there is no CPU fallback)");
+    *out = new tnl_ctx_s(device);
+  });
+}
+int tnl_ctx_destroy(tnl_ctx_t c) {
+  return guard(nullptr, [&] {
+    if (c->e0) { cudaEventDestroy(c->e0); cudaEventDestroy(c->e1); }
+    delete c;
+  });
+}
+const char* tnl_last_error(tnl_ctx_t c) { return c ? c->ctx.last_error.c_str() : g_last_error.c_str(); }
+int tnl_get_counters(tnl_ctx_t c, double* o) {
+  return guard(&c->ctx, [&] {
+    const Counters& k = c->ctx.cnt;
+    o[0] = k.gemm_flops; o[1] = k.xf_flops; o[2] = k.vec_bytes; o[3] = k.xf_bytes;
+    o[4] = (double)k.launches; o[5] = (double)k.gemm_launches; o[6] = k.apply_count; o[7] = 0;
+  });
+}
+int tnl_reset_counters(tnl_ctx_t c) { return guard(&c->ctx, [&] { c->ctx.cnt = Counters(); }); }
+int tnl_ctx_sync(tnl_ctx_t c) { return guard(&c->ctx, [&] { c->ctx.sync(); }); }
+int tnl_timer_start(tnl_ctx_t c) {
+  return guard(&c->ctx, [&] {
+    if (!c->e0) { CUDA_OK(cudaEventCreate(&c->e0)); CUDA_OK(cudaEventCreate(&c->e1)); }
+    CUDA_OK(cudaEventRecord(c->e0, c->ctx.stream));
+  });
+}
+int tnl_timer_stop(tnl_ctx_t c, double* ms) {
+  return guard(&c->ctx, [&] {
+    TNL_CHECK(c->e0, "timer not started");
+    CUDA_OK(cudaEventRecord(c->e1, c->ctx.stream));
+    CUDA_OK(cudaEventSynchronize(c->e1));
+    float f = 0;
+    CUDA_OK(cudaEventElapsedTime(&f, c->e0, c->e1));
+    *ms = f;
+  });
+}
+
+int tnl_tensor_import(tnl_ctx_t c, int32_t rank, int32_t nq, const tnl_index_t* inds, int64_t nblocks,
+                      const int32_t* coords, const int64_t* offsets, const double* data, int32_t nrow,
+                      tnl_tensor_t* out) {
+  return guard(&c->ctx, [&] {
+    HostBlocks hb = make_host(rank, nq, inds, nblocks, coords, offsets, data);
+    *out = new tnl_tensor_s{import_tensor(&c->ctx, hb, nrow)};
+  });
+}
+int tnl_tensor_create(tnl_ctx_t c, int32_t rank, int32_t nq, const tnl_index_t* inds, int32_t nrow, tnl_tensor_t* out) {
+  return guard(&c->ctx, [&] {
+    *out = new tnl_tensor_s{std::make_shared<Tensor>(&c->ctx, make_inds(rank, nq, inds), nrow)};
+  });
+}
+int tnl_tensor_free(tnl_tensor_t t) {
+  return guard(nullptr, [&] { delete t; });
+}
+int tnl_tensor_copy(tnl_tensor_t t, tnl_tensor_t* out) {
+  return guard(t->t->ctx, [&] {
+    auto n = std::make_shared<Tensor>(t->t->ctx, t->t->inds, t->t->nrow);
+    vec_copy(t->t->ctx, n->d, t->t->d, t->t->nelem);
+    n->present = t->t->present;
+    *out = new tnl_tensor_s{n};
+  });
+}
+int tnl_tensor_rank(tnl_tensor_t t, int32_t* rank, int32_t* nq) {
+  return guard(t->t->ctx, [&] { *rank = t->t->rank(); *nq = t->t->inds[0].nq; });
+}
+int tnl_tensor_index(tnl_tensor_t t, int32_t which, int32_t* nsect, int32_t* dir, int32_t* dims, int32_t* qns, int32_t cap) {
+  return guard(t->t->ctx, [&] {
+    TNL_CHECK(which >= 0 && which < t->t->rank(), "index number out of range");
+    const Index& ix = t->t->inds[which];
+    *nsect = ix.nsect();
+    *dir = ix.dir;
+    if (dims && qns) {
+      TNL_CHECK(cap >= ix.nsect(), "index buffer too small");
+      for (int s = 0; s < ix.nsect(); s++) {
+        dims[s] = ix.dims[s];
+        for (int a = 0; a < ix.nq; a++) qns[s * ix.nq + a] = ix.qns[s][a];
+      }
+    }
+  });
+}
+int tnl_tensor_export_size(tnl_tensor_t t, int64_t* nblocks, int64_t* nelem) {
+  return guard(t->t->ctx, [&] {
+    *nblocks = (int64_t)t->t->blocks.size();
+    *nelem = t->t->logical_elems();
+  });
+}
+int tnl_tensor_export(tnl_tensor_t t, int32_t* coords, int64_t* offsets, double* data) {
+  return guard(t->t->ctx, [&] {
+    Ctx* ctx = t->t->ctx;
+    TensorP nat = to_natural(ctx, *t->t);      // contiguous column-major blocks, column-major block order
+    const int r = nat->rank();
+    for (size_t b = 0; b < nat->blocks.size(); b++) {
+      for (int k = 0; k < r; k++) coords[b * r + k] = nat->blocks[b].c[k];
+      offsets[b] = nat->blocks[b].off;
+    }
+    int64_t n = nat->logical_elems();
+    if (n) CUDA_OK(cudaMemcpyAsync(data, nat->d, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+  });
+}
+int tnl_tensor_fill_random(tnl_tensor_t t, uint64_t seed) {
+  return guard(t->t->ctx, [&] { fill_random(t->t->ctx, *t->t, seed); t->t->ctx->sync(); });
+}
+
+static void same_layout(const Tensor& a, const Tensor& b) {
+  TNL_CHECK(a.nelem == b.nelem && a.nrow == b.nrow && a.rank() == b.rank(), "vectors have different layouts");
+}
+int tnl_vec_dot(tnl_tensor_t x, tnl_tensor_t y, double* out) {
+  return guard(x->t->ctx, [&] {
+    same_layout(*x->t, *y->t);
+    Ctx* ctx = x->t->ctx;
+    vec_dot(ctx, x->t->d, y->t->d, x->t->nelem, 0);
+    fetch_scalars(ctx, 1);
+    *out = ctx->h_scalars[0];
+  });
+}
+int tnl_vec_norm(tnl_tensor_t x, double* out) {
+  double d = 0;
+  int rc = tnl_vec_dot(x, x, &d);
+  *out = std::sqrt(d);
+  return rc;
+}
+int tnl_vec_scale(tnl_tensor_t x, double a) {
+  return guard(x->t->ctx, [&] { vec_scale(x->t->ctx, x->t->d, x->t->nelem, a); });
+}
+int tnl_vec_axpy(tnl_tensor_t y, tnl_tensor_t x, double a) {
+  return guard(x->t->ctx, [&] {
+    same_layout(*x->t, *y->t);
+    vec_axpy(x->t->ctx, y->t->d, x->t->d, x->t->nelem, a);
+  });
+}
+
+int tnl_env_create(tnl_ctx_t c, int32_t nsites, tnl_env_t* env) {
+  return guard(&c->ctx, [&] {
+    TNL_CHECK(nsites >= 2, "need at least two sites");
+    *env = new tnl_env_s(&c->ctx, nsites);
+  });
+}
+int tnl_env_destroy(tnl_env_t e) {
+  return guard(nullptr, [&] { delete e; });
+}
+int tnl_env_set_site_op(tnl_env_t e, int32_t site, int32_t nq, const tnl_index_t* inds4, int64_t nblocks,
+                        const int32_t* coords, const int64_t* offsets, const double* data) {
+  return guard(e->env.ctx, [&] {
+    HostBlocks hb = make_host(4, nq, inds4, nblocks, coords, offsets, data);
+    e->env.set_site_op(site, hb);
+  });
+}
+int tnl_env_set_state(tnl_env_t e, int32_t site, tnl_tensor_t a) {
+  return guard(e->env.ctx, [&] { e->env.set_state(site, a->t); });
+}
+int tnl_env_get_state(tnl_env_t e, int32_t site, tnl_tensor_t* out) {
+  return guard(e->env.ctx, [&] {
+    TNL_CHECK(site >= 1 && site <= e->env.N && e->env.A[site - 1], "site out of range or unset");
+    *out = new tnl_tensor_s{e->env.A[site - 1]};
+  });
+}
+int tnl_env_set_nsite(tnl_env_t e, int32_t nsite) {
+  return guard(e->env.ctx, [&] {
+    TNL_CHECK(nsite >= 0 && nsite <= 2, "nsite must be 0, 1 or 2");
+    e->env.nsite = nsite;
+  });
+}
+int tnl_env_position(tnl_env_t e, int32_t pos) {
+  return guard(e->env.ctx, [&] { e->env.position(pos); });
+}
+int tnl_env_orthogonalize(tnl_env_t e) {
+  return guard(e->env.ctx, [&] { e->env.orthogonalize_all_right(); });
+}
+int tnl_env_make_phi(tnl_env_t e, int32_t pos, tnl_tensor_t* phi) {
+  return guard(e->env.ctx, [&] { *phi = new tnl_tensor_s{e->env.make_phi(pos)}; });
+}
+int tnl_env_apply_flops(tnl_env_t e, double* flops) {
+  return guard(e->env.ctx, [&] { *flops = e->env.apply_flops(); });
+}
+int tnl_heff_apply(tnl_env_t e, tnl_tensor_t v, tnl_tensor_t* out) {
+  return guard(e->env.ctx, [&] {
+    TensorP vq = v->t->nrow == 1 ? v->t : relayout(e->env.ctx, *v->t, 1);
+    auto o = std::make_shared<Tensor>(e->env.ctx, vq->inds, 1);
+    e->env.apply(*vq, *o);
+    e->env.ctx->sync();
+    *out = new tnl_tensor_s{o};
+  });
+}
+int tnl_eigsolve_lanczos(tnl_env_t e, tnl_tensor_t phi, double tol, int32_t krylovdim, int32_t maxiter, int32_t eager,
+                         double* eval, int32_t* converged, int32_t* numops, int32_t* numiter, double* normres) {
+  return guard(e->env.ctx, [&] {
+    if (phi->t->nrow != 1) phi->t = relayout(e->env.ctx, *phi->t, 1);
+    LanczosResult r = e->env.eigsolve(*phi->t, tol, krylovdim, maxiter, eager != 0);
+    *eval = r.eval; *converged = r.converged; *numops = r.numops; *numiter = r.numiter; *normres = r.normres;
+  });
+}
+int tnl_expectation(tnl_env_t e, tnl_tensor_t phi, double* out) {
+  return guard(e->env.ctx, [&] {
+    TensorP vq = phi->t->nrow == 1 ? phi->t : relayout(e->env.ctx, *phi->t, 1);
+    *out = e->env.expectation(*vq);
+  });
+}
+int tnl_replacebond(tnl_env_t e, int32_t pos, tnl_tensor_t phi, int32_t ortho_left, int64_t maxdim, int64_t mindim,
+                    double cutoff, double noise, int32_t normalize, int32_t which_decomp, double* truncerr,
+                    double* eigs, int64_t cap, int64_t* neigs) {
+  return guard(e->env.ctx, [&] {
+    FactorizeParams prm;
+    prm.ortho_left = ortho_left;
+    prm.maxdim = maxdim <= 0 ? INT64_MAX : maxdim;
+    prm.mindim = mindim;
+    prm.cutoff = cutoff;
+    prm.noise = noise;
+    prm.which = which_decomp;
+    TensorP vq = phi->t->nrow == 1 ? phi->t : relayout(e->env.ctx, *phi->t, 1);
+    FactorizeResult f = e->env.replacebond(pos, *vq, prm, normalize != 0);
+    *truncerr = f.truncerr;
+    *neigs = (int64_t)f.eigs.size();
+    for (int64_t i = 0; i < std::min<int64_t>(cap, *neigs); i++) eigs[i] = f.eigs[i];
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+// Host-side planner of tnl_b200: charge-fused layouts, grouped-GEMM plans and transform plans.
+// See core.hpp for the data model.  The block-matching rule restated here is NDTensors'
+// `contract_blockoffsets` (blocks pair when their contracted sector numbers agree), specialised to
+// the fused layout where all pairs of one charge sector collapse into a single dense GEMM.
+#include "core.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <functional>
+
+namespace tnl {
+
+// ------------------------------------------------------------------------------------------ Ctx
+Ctx::Ctx(int dev) : device(dev) {
+  CUDA_OK(cudaSetDevice(dev));
+  CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  num_sms = prop.multiProcessorCount;
+  cudaMemPool_t pool;
+  CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t thr = UINT64_MAX;
+  CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  CUDA_OK(cudaMalloc(&d_scalars, 256 * sizeof(double)));
+  CUDA_OK(cudaMallocHost(&h_scalars, 256 * sizeof(double)));
+  CUDA_OK(cudaMalloc(&d_sync, sizeof(unsigned int)));
+  CUDA_OK(cudaMemset(d_sync, 0, sizeof(unsigned int)));
+  CUDA_OK(cudaMalloc(&d_partials, 4096 * sizeof(double)));
+  CUDA_OK(cudaMalloc(&d_info, 16 * sizeof(int)));
+}
+Ctx::~Ctx() {
+  cudaStreamSynchronize(stream);
+  if (solver_work) cudaFree(solver_work);
+  cudaFree(d_scalars);
+  cudaFreeHost(h_scalars);
+  cudaFree(d_sync);
+  cudaFree(d_partials);
+  cudaFree(d_info);
+  cudaStreamDestroy(stream);
+}
+void* Ctx::alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  CUDA_OK(cudaMallocAsync(&p, bytes, stream));
+  return p;
+}
+void Ctx::free(void* p) {
+  if (p) cudaFreeAsync(p, stream);
+}
+
+GemmPlan::~GemmPlan() {
+  if (ctx) { ctx->free(d_probs); ctx->free(d_tiles_big); ctx->free(d_tiles_small); }
+}
+TransformPlan::~TransformPlan() {
+  if (ctx) { ctx->free(d_blocks); ctx->free(d_contribs); }
+}
+
+// --------------------------------------------------------------------------------------- Tensor
+static void enumerate_combos(const std::vector<Index>& inds, int lo, int hi,
+                             std::map<Charge, std::vector<Combo>>& out) {
+  // product sectors of inds[lo..hi), first index fastest, grouped by charge sum_i dir_i*qn_i
+  int n = hi - lo;
+  std::vector<int> c(n, 0);
+  if (n == 0) {
+    Combo cb{};
+    cb.dim = 1; cb.off = 0;
+    out[charge_zero()].push_back(cb);
+    return;
+  }
+  for (int i = lo; i < hi; i++)
+    if (inds[i].nsect() == 0) return;
+  while (true) {
+    Combo cb{};
+    Charge q = charge_zero();
+    cb.dim = 1;
+    for (int k = 0; k < n; k++) {
+      const Index& ix = inds[lo + k];
+      cb.c[k] = c[k];
+      cb.d[k] = ix.dims[c[k]];
+      cb.dim *= cb.d[k];
+      for (int a = 0; a < ix.nq; a++) q[a] += ix.dir * ix.qns[c[k]][a];
+    }
+    out[q].push_back(cb);
+    int k = 0;
+    while (k < n) {
+      if (++c[k] < inds[lo + k].nsect()) break;
+      c[k] = 0;
+      k++;
+    }
+    if (k == n) break;
+  }
+}
+
+void build_layout(Tensor& t) {
+  const int r = t.rank();
+  TNL_CHECK(r <= MAXR, "tensor rank too large");
+  TNL_CHECK(t.nrow >= 0 && t.nrow <= r, "bad nrow");
+  std::map<Charge, std::vector<Combo>> rows, cols;
+  enumerate_combos(t.inds, 0, t.nrow, rows);
+  enumerate_combos(t.inds, t.nrow, r, cols);
+  t.groups.clear(); t.blocks.clear(); t.lut.clear();
+  int64_t base = 0;
+  for (auto& kv : rows) {                              // std::map: ascending charge
+    auto it = cols.find(charge_neg(kv.first));
+    if (it == cols.end()) continue;
+    Group g;
+    g.q = kv.first;
+    g.rows = kv.second;
+    g.cols = it->second;
+    for (auto& cb : g.rows) { cb.off = g.R; g.R += cb.dim; }
+    for (auto& cb : g.cols) { cb.off = g.C; g.C += cb.dim; }
+    g.ld = (g.R + 1) & ~int64_t(1);
+    g.base = base;
+    base += g.ld * g.C;
+    base = (base + 1) & ~int64_t(1);
+    int gi = (int)t.groups.size();
+    for (auto& cc : g.cols)
+      for (auto& rc : g.rows) {
+        Block b{};
+        int64_t st = 1;
+        for (int k = 0; k < t.nrow; k++) { b.c[k] = rc.c[k]; b.d[k] = rc.d[k]; b.st[k] = st; st *= rc.d[k]; }
+        st = g.ld;
+        for (int k = t.nrow; k < r; k++) { b.c[k] = cc.c[k - t.nrow]; b.d[k] = cc.d[k - t.nrow]; b.st[k] = st; st *= b.d[k]; }
+        b.off = g.base + rc.off + g.ld * cc.off;
+        b.group = gi;
+        t.lut[Tensor::key(b.c, r)] = (int)t.blocks.size();
+        t.blocks.push_back(b);
+      }
+    t.groups.push_back(std::move(g));
+  }
+  t.nelem = std::max<int64_t>(base, 2);
+}
+
+Tensor::Tensor(Ctx* c, std::vector<Index> ii, int nr, bool alloc) : ctx(c), inds(std::move(ii)), nrow(nr) {
+  build_layout(*this);
+  if (alloc) {
+    d = (double*)ctx->alloc(nelem * sizeof(double));
+    CUDA_OK(cudaMemsetAsync(d, 0, nelem * sizeof(double), ctx->stream));
+  }
+}
+Tensor::~Tensor() {
+  if (d && ctx) ctx->free(d);
+}
+void Tensor::zero() { CUDA_OK(cudaMemsetAsync(d, 0, nelem * sizeof(double), ctx->stream)); }
+
+// ------------------------------------------------------------------------------------ GEMM plan
+static bool combos_equal(const std::vector<Combo>& a, int na, const std::vector<Combo>& b, int nb) {
+  if (a.size() != b.size() || na != nb) return false;
+  for (size_t i = 0; i < a.size(); i++) {
+    if (a[i].dim != b[i].dim) return false;
+    for (int k = 0; k < na; k++)
+      if (a[i].c[k] != b[i].c[k] || a[i].d[k] != b[i].d[k]) return false;
+  }
+  return true;
+}
+
+static void make_tiles(GemmPlan& plan) {
+  // biggest problems first; tiles of one problem are emitted m-fastest so that concurrently resident
+  // CTAs share the B panel and stream A through L2
+  std::vector<int> order(plan.probs.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    const auto &x = plan.probs[a], &y = plan.probs[b];
+    return (double)x.M * x.N * x.K > (double)y.M * y.N * y.K;
+  });
+  for (int pi : order) {
+    const auto& p = plan.probs[pi];
+    bool big = p.M > 64 && p.N > 64;
+    int bm = big ? 128 : 64, bn = big ? 128 : 64;
+    auto& tl = big ? plan.tiles_big : plan.tiles_small;
+    for (int n0 = 0; n0 < p.N; n0 += bn)
+      for (int m0 = 0; m0 < p.M; m0 += bm) tl.push_back(GemmTile{pi, m0, n0});
+  }
+  plan.d_probs = plan.ctx->upload(plan.probs);
+  plan.d_tiles_big = plan.ctx->upload(plan.tiles_big);
+  plan.d_tiles_small = plan.ctx->upload(plan.tiles_small);
+}
+
+std::unique_ptr<GemmPlan> plan_gemm_raw(Ctx* ctx, bool transA, bool transB, const std::vector<GemmProblem>& probs) {
+  auto plan = std::make_unique<GemmPlan>();
+  plan->ctx = ctx;
+  plan->transA = transA;
+  plan->transB = transB;
+  for (auto& p : probs) {
+    if (p.M == 0 || p.N == 0) continue;
+    if (p.K == 0) {
+      for (int n = 0; n < p.N; n++) plan->zero_fill.emplace_back(p.c + (int64_t)n * p.ldc, (int64_t)p.M);
+      continue;
+    }
+    plan->flops += 2.0 * p.M * (double)p.N * p.K;
+    plan->probs.push_back(p);
+  }
+  make_tiles(*plan);
+  return plan;
+}
+
+std::unique_ptr<GemmPlan> plan_gemm(const Tensor& A, bool transA, const Tensor& B, bool transB, Tensor& C,
+                                    bool dagA, bool dagB) {
+  auto sgnA = [&](Charge q) { return dagA ? charge_neg(q) : q; };
+  auto sgnB = [&](Charge q) { return dagB ? charge_neg(q) : q; };
+  auto plan = std::make_unique<GemmPlan>();
+  plan->ctx = C.ctx;
+  plan->transA = transA;
+  plan->transB = transB;
+  const int nMa = transA ? A.rank() - A.nrow : A.nrow;
+  const int nKa = A.rank() - nMa;
+  const int nNb = transB ? B.nrow : B.rank() - B.nrow;
+  const int nKb = B.rank() - nNb;
+  TNL_CHECK(nKa == nKb, "contracted index groups differ in size");
+  TNL_CHECK(C.nrow == nMa && C.rank() - C.nrow == nNb, "output bipartition mismatch");
+  for (size_t gc = 0; gc < C.groups.size(); gc++) {
+    Group& G = C.groups[gc];
+    // A group whose M side has charge q
+    int ga = A.find_group(sgnA(transA ? charge_neg(G.q) : G.q));
+    bool ok = ga >= 0;
+    int gb = -1;
+    if (ok) {
+      const Group& GA = A.groups[ga];
+      // charge of the K combos as seen from A
+      Charge kA = transA ? sgnA(GA.q) : charge_neg(sgnA(GA.q));
+      // seen from B the same sectors carry the opposite arrows
+      Charge kB = charge_neg(kA);
+      gb = B.find_group(sgnB(transB ? charge_neg(kB) : kB));
+      ok = gb >= 0;
+    }
+    if (!ok) {
+      plan->zero_fill.emplace_back(G.base, G.ld * G.C);
+      continue;
+    }
+    const Group& GA = A.groups[ga];
+    const Group& GB = B.groups[gb];
+    const auto& Mc = transA ? GA.cols : GA.rows;
+    const auto& Ka = transA ? GA.rows : GA.cols;
+    const auto& Kb = transB ? GB.cols : GB.rows;
+    const auto& Nc = transB ? GB.rows : GB.cols;
+    TNL_CHECK(combos_equal(Ka, nKa, Kb, nKb), "contracted sectors of A and B do not line up");
+    TNL_CHECK(combos_equal(Mc, nMa, G.rows, C.nrow), "row sectors of A and C do not line up");
+    TNL_CHECK(combos_equal(Nc, nNb, G.cols, C.rank() - C.nrow), "column sectors of B and C do not line up");
+    GemmProblem p;
+    p.a = GA.base;
+    p.b = GB.base;
+    p.c = G.base;
+    p.M = (int)G.R;
+    p.N = (int)G.C;
+    p.K = (int)(transA ? GA.R : GA.C);
+    p.lda = (int)GA.ld;
+    p.ldb = (int)GB.ld;
+    p.ldc = (int)G.ld;
+    if (p.M == 0 || p.N == 0) continue;
+    if (p.K == 0) { plan->zero_fill.emplace_back(G.base, G.ld * G.C); continue; }
+    plan->flops += 2.0 * p.M * (double)p.N * p.K;
+    plan->probs.push_back(p);
+  }
+  make_tiles(*plan);
+  return plan;
+}
+
+// ------------------------------------------------------------------------------- transform plan
+std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const std::vector<int>& xmap,
+                                              const Tensor* W, const std::vector<int>& kpos) {
+  auto plan = std::make_unique<TransformPlan>();
+  plan->ctx = Y.ctx;
+  const int ry = Y.rank(), rx = X.rank();
+  TNL_CHECK((int)xmap.size() == ry, "xmap size");
+  TNL_CHECK(xmap[0] == 0, "leading index must be shared and leading in both tensors");
+  std::vector<int> newpos, passY;          // Y positions of new / passive (non-leading) indices
+  for (int j = 1; j < ry; j++) (xmap[j] < 0 ? newpos : passY).push_back(j);
+  const int nk = (int)kpos.size(), nn = (int)newpos.size();
+  TNL_CHECK(nk <= 2 && nn <= 2, "at most two contracted / new indices");
+  TNL_CHECK((int)passY.size() <= MAXP, "too many passive indices");
+  TNL_CHECK((W == nullptr) == (nk == 0 && nn == 0), "W must be given iff indices are contracted");
+  TNL_CHECK(rx == 1 + (int)passY.size() + nk, "index bookkeeping mismatch");
+  if (W) TNL_CHECK(W->rank() == nk + nn && W->nrow == W->rank(), "W must be (contracted..., new...) in natural layout");
+  // W blocks grouped by their new-sector coordinates
+  int64_t col = 0;
+  for (const Block& yb : Y.blocks) {
+    XfBlock xb{};
+    xb.yoff = yb.off;
+    xb.I = yb.d[0];
+    xb.nd0 = xb.nd1 = 1;
+    xb.yns[0] = xb.yns[1] = 0;
+    if (nn > 0) { xb.nd0 = yb.d[newpos[0]]; xb.yns[0] = yb.st[newpos[0]]; }
+    if (nn > 1) { xb.nd1 = yb.d[newpos[1]]; xb.yns[1] = yb.st[newpos[1]]; }
+    int64_t ncol = (int64_t)xb.nd0 * xb.nd1;
+    for (int k = 0; k < MAXP; k++) { xb.pd[k] = 1; xb.yps[k] = 0; }
+    for (size_t k = 0; k < passY.size(); k++) {
+      xb.pd[k] = yb.d[passY[k]];
+      xb.yps[k] = yb.st[passY[k]];
+      ncol *= xb.pd[k];
+    }
+    xb.cbeg = (int)plan->contribs.size();
+    // candidate contributions: every W block whose new sectors match (or the single identity one)
+    int xc[MAXR];
+    xc[0] = yb.c[0];
+    for (size_t k = 0; k < passY.size(); k++) xc[xmap[passY[k]]] = yb.c[passY[k]];
+    auto add = [&](const Block* wb) {
+      for (int k = 0; k < nk; k++) xc[kpos[k]] = wb->c[k];
+      int bi = X.find(xc);
+      if (bi < 0) return;
+      const Block& sb = X.blocks[bi];
+      XfContrib c{};
+      c.xoff = sb.off;
+      for (int k = 0; k < MAXP; k++) c.xps[k] = 0;
+      for (size_t k = 0; k < passY.size(); k++) c.xps[k] = sb.st[xmap[passY[k]]];
+      c.kd0 = c.kd1 = 1; c.ks0 = c.ks1 = 0;
+      if (nk > 0) { c.kd0 = sb.d[kpos[0]]; c.ks0 = sb.st[kpos[0]]; }
+      if (nk > 1) { c.kd1 = sb.d[kpos[1]]; c.ks1 = sb.st[kpos[1]]; }
+      c.woff = wb ? wb->off : 0;
+      plan->contribs.push_back(c);
+      plan->flops += 2.0 * xb.I * (double)ncol * c.kd0 * c.kd1;
+    };
+    if (!W) {
+      add(nullptr);
+    } else {
+      for (size_t wi = 0; wi < W->blocks.size(); wi++) {
+        const Block& wb = W->blocks[wi];
+        if (!W->present.empty() && !W->present[wi]) continue;
+        bool match = true;
+        for (int k = 0; k < nn; k++) match = match && (wb.c[nk + k] == yb.c[newpos[k]]);
+        if (match) add(&wb);
+      }
+    }
+    xb.cnum = (int)plan->contribs.size() - xb.cbeg;
+    xb.colstart = col;
+    col += ncol;
+    plan->blocks.push_back(xb);
+  }
+  plan->ncols = col;
+  plan->bytes = 8.0 * ((double)X.logical_elems() + (double)Y.logical_elems());
+  plan->d_blocks = Y.ctx->upload(plan->blocks);
+  plan->d_contribs = Y.ctx->upload(plan->contribs);
+  return plan;
+}
+
+}  // namespace tnl

@@ -1,0 +1,257 @@
+// tnl_b200 core data model: QN indices and charge-fused block-sparse tensors in HBM.
+//
+// Design: a block-sparse tensor with flux 0 and a bipartition
+// (first `nrow` indices | remaining indices) is block diagonal in the fused charge of the
+// row group.  We store every charge group as ONE dense column-major "super-matrix"
+// [R_q x C_q] (leading dimension padded to 16 B) whose sub-blocks are the NDTensors blocks.
+// Consequences:
+//   * contracting two tensors over a whole row/column group is a plain dense DGEMM per charge
+//     sector (grouped_gemm.cu) -- no per-block-pair GEMMs, no ragged tiny tiles;
+//   * regrouping indices (and applying the skinny MPO site operators on the way) is one
+//     HBM-bound pass (transform.cu);
+//   * the flat buffer of a Krylov vector has no holes except zero padding, so inner products /
+//     axpys are flat BLAS-1 kernels (vecops.cu).
+// Semantics follow NDTensors' BlockSparse storage as consumed by the reference at
+// src/mps/projcouplingmodel.jl:315-356, src/mps/update_site.jl:46-76.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <array>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace tnl {
+
+constexpr int MAXR = 6;   // max tensor rank on the hot path (T1/T2/T3 of the two-site apply are rank 5)
+constexpr int MAXQ = 2;   // U(1) or U(1)xU(1)
+using Charge = std::array<int, MAXQ>;
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+#define TNL_CHECK(cond, msg)                                                         \
+  do {                                                                               \
+    if (!(cond)) throw ::tnl::Error(2, std::string(msg) + " [" #cond "] at " __FILE__ ":" + std::to_string(__LINE__)); \
+  } while (0)
+#define CUDA_OK(call)                                                                \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess)                                                          \
+      throw ::tnl::Error(3, std::string("CUDA error: ") + cudaGetErrorString(e__) + " in " #call " at " __FILE__ ":" + \
+                                std::to_string(__LINE__));                           \
+  } while (0)
+
+struct Index {
+  std::vector<int> dims;      // sector dims
+  std::vector<Charge> qns;    // sector charges
+  int dir = +1;               // arrow
+  int nq = 1;
+  int nsect() const { return (int)dims.size(); }
+  int64_t dim() const { int64_t d = 0; for (int x : dims) d += x; return d; }
+  bool same_space(const Index& o) const { return dims == o.dims && qns == o.qns && nq == o.nq; }
+  Index dag() const { Index r = *this; r.dir = -dir; return r; }
+};
+
+inline Charge charge_zero() { Charge c; c.fill(0); return c; }
+inline Charge charge_neg(Charge c) { for (auto& x : c) x = -x; return c; }
+
+// one product of sectors of an index group
+struct Combo {
+  int c[MAXR];       // sector number per index of the group
+  int d[MAXR];       // sector dims
+  int64_t dim;       // product of dims
+  int64_t off;       // offset inside the group's row (or column) range
+};
+
+struct Group {
+  Charge q;                 // charge of the ROW group: sum_i dir_i * qn_i
+  int64_t R = 0, C = 0;     // logical rows / cols
+  int64_t ld = 0;           // padded leading dimension (>= R, even)
+  int64_t base = 0;         // element offset of the super-matrix in the tensor buffer
+  std::vector<Combo> rows, cols;
+};
+
+struct Block {
+  int c[MAXR];
+  int d[MAXR];
+  int64_t st[MAXR];         // element strides
+  int64_t off;              // element offset of element (0,..,0)
+  int group;
+};
+
+class Ctx;
+
+// Block-sparse tensor, flux 0, fused layout with the first `nrow` indices as row group.
+class Tensor {
+ public:
+  Ctx* ctx = nullptr;
+  std::vector<Index> inds;
+  int nrow = 0;
+  std::vector<Group> groups;
+  std::vector<Block> blocks;                       // all symmetry-allowed blocks
+  std::unordered_map<uint64_t, int> lut;           // packed coords -> block number
+  std::vector<uint8_t> present;                    // imported tensors: which blocks the host supplied (empty = all)
+  double* d = nullptr;
+  int64_t nelem = 0;                               // padded element count of the buffer
+
+  Tensor(Ctx* ctx, std::vector<Index> inds, int nrow, bool alloc = true);
+  ~Tensor();
+  Tensor(const Tensor&) = delete;
+  Tensor& operator=(const Tensor&) = delete;
+
+  int rank() const { return (int)inds.size(); }
+  static uint64_t key(const int* c, int r) {
+    uint64_t k = 0;
+    for (int i = 0; i < r; i++) k = (k << 10) | (uint64_t)(c[i] & 1023);
+    return k;
+  }
+  int find(const int* c) const {
+    auto it = lut.find(key(c, rank()));
+    return it == lut.end() ? -1 : it->second;
+  }
+  int find_group(const Charge& q) const {
+    for (size_t g = 0; g < groups.size(); g++)
+      if (groups[g].q == q) return (int)g;
+    return -1;
+  }
+  int64_t logical_elems() const { int64_t n = 0; for (auto& g : groups) n += g.R * g.C; return n; }
+  void zero();
+};
+using TensorP = std::shared_ptr<Tensor>;
+
+// ---- device work descriptors ---------------------------------------------------------------
+struct GemmProblem {          // C[M x N] = op(A)[M x K] * op(B)[K x N], column-major
+  int64_t a, b, c;            // element offsets relative to the base pointers given at launch
+  int M, N, K;
+  int lda, ldb, ldc;
+};
+struct GemmTile { int prob; int m0; int n0; };
+
+struct GemmPlan {
+  bool transA = false, transB = false;
+  std::vector<GemmProblem> probs;
+  std::vector<GemmTile> tiles_big, tiles_small;
+  GemmProblem* d_probs = nullptr;
+  GemmTile* d_tiles_big = nullptr;
+  GemmTile* d_tiles_small = nullptr;
+  std::vector<std::pair<int64_t, int64_t>> zero_fill;   // (offset, count) of C ranges with no contribution
+  double flops = 0;
+  Ctx* ctx = nullptr;
+  ~GemmPlan();
+};
+
+// transform: Y(i, n..., p...) = sum_contrib sum_k X(i, k..., p...) * W(k, n)
+constexpr int MAXP = 4;
+struct XfContrib {
+  int64_t xoff;              // X element offset of (i=0, k=0, p=0)
+  int64_t xps[MAXP];         // X strides of the passive dims
+  int64_t ks0, ks1;          // X strides of the (up to two) contracted dims
+  int kd0, kd1;              // their dims (Ka = kd0*kd1)
+  int64_t woff;              // W element offset; W block is [Ka x Na] column-major
+};
+struct XfBlock {
+  int64_t yoff;              // Y element offset of (i=0, n=0, p=0)
+  int64_t yns[2];            // Y strides of the (up to two) new dims
+  int nd0, nd1;              // their dims (Na = nd0*nd1)
+  int64_t yps[MAXP];         // Y strides of the passive dims
+  int pd[MAXP];              // passive dims
+  int I;                     // leading (stride-1) dim
+  int cbeg, cnum;            // contribution range
+  int64_t colstart;          // first global column of this block (columns = Na * prod(pd))
+};
+struct TransformPlan {
+  std::vector<XfBlock> blocks;
+  std::vector<XfContrib> contribs;
+  XfBlock* d_blocks = nullptr;
+  XfContrib* d_contribs = nullptr;
+  int64_t ncols = 0;
+  double bytes = 0;          // algorithmic bytes moved (read X once + write Y once)
+  double flops = 0;
+  Ctx* ctx = nullptr;
+  ~TransformPlan();
+};
+
+// ---- context --------------------------------------------------------------------------------
+struct Counters {
+  double gemm_flops = 0;          // algorithmic 2mnk summed over executed GEMM problems
+  double xf_flops = 0;
+  double vec_bytes = 0;           // algorithmic bytes of Krylov vector kernels
+  double xf_bytes = 0;
+  long long launches = 0;         // kernels of THIS library launched
+  long long gemm_launches = 0;
+  double apply_count = 0;
+};
+
+class Ctx {
+ public:
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  Counters cnt;
+  double* d_scalars = nullptr;      // device scratch for reductions
+  double* h_scalars = nullptr;      // pinned mirror
+  unsigned int* d_sync = nullptr;   // "last block" counters
+  double* d_partials = nullptr;
+  int num_sms = 148;
+  // NCCL sharding (multi-GPU apply); rank 0 / world 1 when unused
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;
+  // cuSOLVER (opaque here; factorize.cu owns the type)
+  void* cusolver = nullptr;
+  void* solver_work = nullptr; size_t solver_work_bytes = 0;
+  int* d_info = nullptr;
+
+  explicit Ctx(int device);
+  ~Ctx();
+  void* alloc(size_t bytes);
+  void free(void* p);
+  void sync() { CUDA_OK(cudaStreamSynchronize(stream)); }
+  template <class T> T* upload(const std::vector<T>& v) {
+    if (v.empty()) return nullptr;
+    T* p = (T*)alloc(v.size() * sizeof(T));
+    CUDA_OK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));   // source vector may die right after
+    return p;
+  }
+};
+
+// ---- kernels / planners (implemented in the .cu / .cpp files) --------------------------------
+void build_layout(Tensor& t);
+
+// dagA / dagB: the operand enters with reversed arrows (ITensor `dag`); data is real so only the charge
+// bookkeeping changes.
+std::unique_ptr<GemmPlan> plan_gemm(const Tensor& A, bool transA, const Tensor& B, bool transB, Tensor& C,
+                                    bool dagA = false, bool dagB = false);
+void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C);
+// ad-hoc problems (factorisation internals); builds tiles and uploads
+std::unique_ptr<GemmPlan> plan_gemm_raw(Ctx* ctx, bool transA, bool transB, const std::vector<GemmProblem>& probs);
+void transpose(Ctx* ctx, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t R, int64_t C);  // dst[C x R] = src[R x C]^T
+void copy2d(Ctx* ctx, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t R, int64_t C);
+
+// W == nullptr: pure relayout / index permutation.  `xmap[j]` = position in X of Y's index j, or -1 for a
+// new index (coming from W); `kpos` lists the X positions that are contracted with W (in W's row order);
+// W's indices are ordered (contracted..., new...).
+std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const std::vector<int>& xmap,
+                                              const Tensor* W, const std::vector<int>& kpos);
+void run_transform(Ctx* ctx, TransformPlan& p, const double* X, double* Y, const double* W);
+
+// flat vector kernels on padded buffers of equal layout
+void vec_dot(Ctx* ctx, const double* x, const double* y, int64_t n, int slot);       // d_scalars[slot] = <x,y>
+void vec_axpy_dev(Ctx* ctx, double* y, const double* x, int64_t n, int slot, double sign);  // y += sign*s[slot]*x
+void vec_axpy(Ctx* ctx, double* y, const double* x, int64_t n, double a);
+void vec_scale(Ctx* ctx, double* y, int64_t n, double a);
+void vec_scale_to(Ctx* ctx, double* y, const double* x, int64_t n, double a);         // y = a*x
+void vec_copy(Ctx* ctx, double* y, const double* x, int64_t n);
+void vec_lincomb(Ctx* ctx, double* y, const double* const* xs, const double* coef, int k, int64_t n);
+void fetch_scalars(Ctx* ctx, int n);                                                  // d_scalars -> h_scalars, sync
+void fill_random(Ctx* ctx, Tensor& t, uint64_t seed);
+void scale_rows_or_cols(Ctx* ctx, double* A, int64_t ld, int64_t R, int64_t C, const double* s, bool rows);
+
+}  // namespace tnl

@@ -1,0 +1,633 @@
+// Device StateEnvs{ProjMPO}: environments, H_eff apply, Lanczos.  Reference call sites:
+//   position!            src/mps/state_envs.jl:364-367  -> ITensorMPS ProjMPO makeL!/makeR!
+//   product / callable   src/mps/state_envs.jl:376-378  -> ProjMPO.product: noprime(v*L*W_j*W_{j+1}*R)
+//   eig_solver           src/base/solver.jl:23-43       -> KrylovKit.eigsolve (Lanczos)
+//   phi = psi[j]*psi[j+1]  src/mps/update_site.jl:46
+// Contraction order follows the reference (L first, then the site operators, then R); in the
+// charge-fused layout each big step is a grouped DGEMM over charge sectors and each site-operator
+// step is one transform pass.
+#include "env.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace tnl {
+
+// ------------------------------------------------------------------------------ tensor helpers
+static TensorP mk(Ctx* ctx, std::vector<Index> inds, int nrow) { return std::make_shared<Tensor>(ctx, std::move(inds), nrow); }
+
+static Index with_dir(Index ix, int dir) { ix.dir = dir; return ix; }
+
+TensorP import_tensor(Ctx* ctx, const HostBlocks& hb, int nrow) {
+  TNL_CHECK(hb.rank >= 1 && hb.rank <= MAXR, "import: bad rank");
+  auto Y = mk(ctx, hb.inds, nrow);
+  Tensor X(ctx, hb.inds, hb.rank, false);
+  X.blocks.clear();
+  X.lut.clear();
+  X.groups.clear();
+  int64_t total = 0;
+  for (size_t n = 0; n < hb.coords.size(); n++) {
+    Block b{};
+    int64_t st = 1;
+    for (int k = 0; k < hb.rank; k++) {
+      int c = hb.coords[n][k];
+      TNL_CHECK(c >= 0 && c < hb.inds[k].nsect(), "import: block coordinate out of range");
+      b.c[k] = c; b.d[k] = hb.inds[k].dims[c]; b.st[k] = st; st *= b.d[k];
+    }
+    b.off = hb.offsets[n];
+    b.group = 0;
+    TNL_CHECK(Y->find(b.c) >= 0, "import: block violates flux 0 for the given arrows");
+    X.lut[Tensor::key(b.c, hb.rank)] = (int)X.blocks.size();
+    X.blocks.push_back(b);
+    total = std::max(total, b.off + st);
+  }
+  double* tmp = (double*)ctx->alloc(std::max<int64_t>(total, 1) * sizeof(double));
+  if (total) CUDA_OK(cudaMemcpyAsync(tmp, hb.data, total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<int> xmap(hb.rank);
+  std::iota(xmap.begin(), xmap.end(), 0);
+  auto plan = plan_transform(X, *Y, xmap, nullptr, {});
+  run_transform(ctx, *plan, tmp, Y->d, nullptr);
+  Y->present.resize(Y->blocks.size());
+  for (size_t i = 0; i < Y->blocks.size(); i++) Y->present[i] = X.find(Y->blocks[i].c) >= 0;
+  ctx->sync();
+  ctx->free(tmp);
+  return Y;
+}
+
+TensorP relayout(Ctx* ctx, const Tensor& t, int nrow) {
+  auto Y = mk(ctx, t.inds, nrow);
+  std::vector<int> xmap(t.rank());
+  std::iota(xmap.begin(), xmap.end(), 0);
+  auto plan = plan_transform(t, *Y, xmap, nullptr, {});
+  run_transform(ctx, *plan, t.d, Y->d, nullptr);
+  ctx->sync();   // the plan's device arrays die with `plan`
+  return Y;
+}
+TensorP to_natural(Ctx* ctx, const Tensor& t) { return relayout(ctx, t, t.rank()); }
+
+static TensorP as_nrow(Ctx* ctx, const TensorP& t, int nrow) { return t->nrow == nrow ? t : relayout(ctx, *t, nrow); }
+
+// host permutation of a tiny tensor (MPO site operators)
+struct OwnedHost { HostBlocks hb; std::vector<double> data; };
+static OwnedHost permute_host(const HostBlocks& h, const std::vector<int>& perm) {
+  OwnedHost o;
+  o.hb.rank = h.rank;
+  for (int k = 0; k < h.rank; k++) o.hb.inds.push_back(h.inds[perm[k]]);
+  int64_t off = 0;
+  for (size_t n = 0; n < h.coords.size(); n++) {
+    std::vector<int> c(h.rank), d(h.rank), dn(h.rank);
+    int64_t sz = 1;
+    for (int k = 0; k < h.rank; k++) { d[k] = h.inds[k].dims[h.coords[n][k]]; sz *= d[k]; }
+    for (int k = 0; k < h.rank; k++) { c[k] = h.coords[n][perm[k]]; dn[k] = d[perm[k]]; }
+    o.hb.coords.push_back(c);
+    o.hb.offsets.push_back(off);
+    o.data.resize(off + sz);
+    std::vector<int64_t> sst(h.rank);
+    int64_t st = 1;
+    for (int k = 0; k < h.rank; k++) { sst[k] = st; st *= d[k]; }
+    std::vector<int> idx(h.rank, 0);
+    for (int64_t e = 0; e < sz; e++) {
+      int64_t src = 0;
+      for (int k = 0; k < h.rank; k++) src += idx[k] * sst[perm[k]];
+      o.data[off + e] = h.data[h.offsets[n] + src];
+      for (int k = 0; k < h.rank; k++) { if (++idx[k] < dn[k]) break; idx[k] = 0; }
+    }
+    off += sz;
+  }
+  o.hb.data = o.data.data();
+  return o;
+}
+
+// -------------------------------------------------------------------------------------- Env
+void Env::set_site_op(int site, const HostBlocks& hb) {
+  TNL_CHECK(site >= 1 && site <= N, "site out of range");
+  TNL_CHECK(hb.rank == 4, "MPO tensor must be (wl, s', s, wr)");
+  auto lr = permute_host(hb, {0, 2, 1, 3});     // (wl, s | s', wr)
+  auto rl = permute_host(hb, {1, 3, 0, 2});     // (s', wr | wl, s)
+  Wlr[site - 1] = import_tensor(ctx, lr.hb, 4);
+  Wrl[site - 1] = import_tensor(ctx, rl.hb, 4);
+  auto nr = permute_host(hb, {2, 3, 0, 1});     // (s, wr | wl, s')
+  Wnr[site - 1] = import_tensor(ctx, nr.hb, 4);
+  Wl[site - 1] = hb.inds[0];
+  Wr[site - 1] = hb.inds[3];
+  lpos = 0; rpos = N + 1; ap.reset(); Ledge.reset(); Redge.reset();
+}
+
+void Env::set_state(int site, TensorP a) {
+  TNL_CHECK(site >= 1 && site <= N, "site out of range");
+  TNL_CHECK(a->rank() == 3, "site tensor must be (l, s, r)");
+  A[site - 1] = std::move(a);
+  lpos = std::min(lpos, site - 1);
+  rpos = std::max(rpos, site + 1);
+  ap.reset();
+}
+
+static void set_one(Ctx* ctx, Tensor& t) {
+  TNL_CHECK(t.blocks.size() == 1, "boundary environment must be a single 1x1x1 block");
+  double one = 1.0;
+  CUDA_OK(cudaMemcpyAsync(t.d + t.blocks[0].off, &one, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->sync();
+}
+
+void Env::ensure_edges() {
+  if (!Ledge) {
+    const Index& l = A[0]->inds[0];
+    TNL_CHECK(l.dim() == 1 && Wl[0].dim() == 1, "boundary links must have dimension 1");
+    Ledge = mk(ctx, {with_dir(l, l.dir), with_dir(Wl[0], -Wl[0].dir), with_dir(l, -l.dir)}, 2);
+    set_one(ctx, *Ledge);
+  }
+  if (!Redge) {
+    const Index& r = A[N - 1]->inds[2];
+    TNL_CHECK(r.dim() == 1 && Wr[N - 1].dim() == 1, "boundary links must have dimension 1");
+    Redge = mk(ctx, {with_dir(r, r.dir), with_dir(Wr[N - 1], -Wr[N - 1].dir), with_dir(r, -r.dir)}, 1);
+    set_one(ctx, *Redge);
+  }
+}
+
+TensorP Env::lproj() { return lpos <= 0 ? Ledge : LR[lpos - 1]; }
+TensorP Env::rproj() { return rpos >= N + 1 ? Redge : LR[rpos - 1]; }
+
+// L_j = L_{j-1} * A_j * W_j * dag(prime(A_j))      (ITensorMPS ProjMPO._makeL!)
+void Env::makeL(int k) {
+  ensure_edges();
+  int ll = lpos;
+  if (ll >= k) { lpos = k; return; }
+  ll = std::max(ll, 0);
+  TensorP L = lproj();
+  while (ll < k) {
+    TensorP Aq = as_nrow(ctx, A[ll], 1);            // [l | s r]
+    TensorP As = as_nrow(ctx, A[ll], 2);            // [l s | r]
+    const TensorP& W = Wlr[ll];
+    auto X1 = mk(ctx, {L->inds[0], L->inds[1], Aq->inds[1], Aq->inds[2]}, 2);
+    auto g1 = plan_gemm(*L, false, *Aq, false, *X1);
+    run_gemm(ctx, *g1, L->d, Aq->d, X1->d);
+    auto Y1 = mk(ctx, {X1->inds[0], W->inds[2], W->inds[3], X1->inds[3]}, 2);
+    auto x1 = plan_transform(*X1, *Y1, {0, -1, -1, 3}, W.get(), {1, 2});
+    run_transform(ctx, *x1, X1->d, Y1->d, W->d);
+    const Index& r = As->inds[2];
+    auto Ln = mk(ctx, {with_dir(r, -r.dir), Y1->inds[2], Y1->inds[3]}, 1);
+    auto g2 = plan_gemm(*As, true, *Y1, false, *Ln, /*dagA=*/true);
+    run_gemm(ctx, *g2, As->d, Y1->d, Ln->d);
+    ctx->sync();
+    L = relayout(ctx, *Ln, 2);
+    LR[ll] = L;
+    ll++;
+  }
+  lpos = k;
+}
+
+// R_j = dag(prime(A_j)) * R_{j+1} * W_j * A_j  (mirror image; same sum, bra contracted first)
+void Env::makeR(int k) {
+  ensure_edges();
+  int rl = rpos;
+  if (rl <= k) { rpos = k; return; }
+  rl = std::min(rl, N + 1);
+  TensorP R = rproj();
+  while (rl > k) {
+    int j = rl - 2;
+    TensorP Aq = as_nrow(ctx, A[j], 1);
+    TensorP As = as_nrow(ctx, A[j], 2);
+    const TensorP& W = Wrl[j];
+    const Index &l = As->inds[0], &s = As->inds[1];
+    auto Z = mk(ctx, {with_dir(l, -l.dir), with_dir(s, -s.dir), R->inds[1], R->inds[2]}, 2);
+    auto g1 = plan_gemm(*As, false, *R, false, *Z, /*dagA=*/true);
+    run_gemm(ctx, *g1, As->d, R->d, Z->d);
+    auto Z2 = mk(ctx, {Z->inds[0], W->inds[2], W->inds[3], Z->inds[3]}, 2);
+    auto x1 = plan_transform(*Z, *Z2, {0, -1, -1, 3}, W.get(), {1, 2});
+    run_transform(ctx, *x1, Z->d, Z2->d, W->d);
+    auto Rn = mk(ctx, {Z2->inds[0], Z2->inds[1], Aq->inds[0]}, 2);
+    auto g2 = plan_gemm(*Z2, false, *Aq, true, *Rn);
+    run_gemm(ctx, *g2, Z2->d, Aq->d, Rn->d);
+    ctx->sync();
+    R = relayout(ctx, *Rn, 1);
+    LR[j] = R;
+    rl--;
+  }
+  rpos = k;
+}
+
+void Env::position(int pos) {
+  int lp = lpos, rp = rpos;
+  makeL(pos - 1);
+  makeR(pos + nsite);
+  if (lp != lpos || rp != rpos) ap.reset();
+}
+
+TensorP Env::make_phi(int pos) {
+  TNL_CHECK(pos >= 1 && pos < N, "bond out of range");
+  TensorP A1 = as_nrow(ctx, A[pos - 1], 2);
+  TensorP A2 = as_nrow(ctx, A[pos], 1);
+  auto S = mk(ctx, {A1->inds[0], A1->inds[1], A2->inds[1], A2->inds[2]}, 2);
+  auto g = plan_gemm(*A1, false, *A2, false, *S);
+  run_gemm(ctx, *g, A1->d, A2->d, S->d);
+  ctx->sync();
+  return relayout(ctx, *S, 1);
+}
+
+// ---------------------------------------------------------------------------------- H_eff apply
+struct Env::ApplyPlan {
+  int nsite;
+  TensorP L, R, W1, W2;
+  TensorP T1, T2, T3, P;
+  std::unique_ptr<GemmPlan> g1, g4;
+  std::unique_ptr<TransformPlan> x2, x3, x5;
+  int64_t nelem;
+  double flops;
+};
+
+void Env::build_apply_plan(const Tensor& v) {
+  auto p = std::make_shared<ApplyPlan>();
+  p->nsite = nsite;
+  p->L = lproj();
+  p->R = rproj();
+  TNL_CHECK(p->L && p->R, "environments not positioned");
+  TNL_CHECK(v.nrow == 1, "Krylov vectors use the [l | rest] layout");
+  const int first = lpos + 1;      // 1-based first site of the range
+  if (nsite == 2) {
+    TNL_CHECK(v.rank() == 4 && rpos - lpos == 3, "two-site apply needs a (l,s1,s2,r) vector and nsite=2 position");
+    p->W1 = Wlr[first - 1];
+    p->W2 = Wlr[first];
+    const Tensor &L = *p->L, &R = *p->R, &W1 = *p->W1, &W2 = *p->W2;
+    p->T1 = mk(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2], v.inds[3]}, 2);
+    p->g1 = plan_gemm(L, false, v, false, *p->T1);
+    p->T2 = mk(ctx, {L.inds[0], W1.inds[2], W1.inds[3], v.inds[2], v.inds[3]}, 5);
+    p->x2 = plan_transform(*p->T1, *p->T2, {0, -1, -1, 3, 4}, &W1, {1, 2});
+    p->T3 = mk(ctx, {L.inds[0], W1.inds[2], W2.inds[2], W2.inds[3], v.inds[3]}, 3);
+    p->x3 = plan_transform(*p->T2, *p->T3, {0, 1, -1, -1, 4}, &W2, {2, 3});
+    p->P = mk(ctx, {L.inds[0], W1.inds[2], W2.inds[2], R.inds[0]}, 3);
+    p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
+    Tensor Q(ctx, p->P->inds, 1, false);
+    TNL_CHECK(Q.nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
+    p->x5 = plan_transform(*p->P, Q, {0, 1, 2, 3}, nullptr, {});
+    p->flops = p->g1->flops + p->x2->flops + p->x3->flops + p->g4->flops;
+  } else if (nsite == 1) {
+    TNL_CHECK(v.rank() == 3 && rpos - lpos == 2, "one-site apply needs a (l,s,r) vector and nsite=1 position");
+    p->W1 = Wlr[first - 1];
+    const Tensor &L = *p->L, &R = *p->R, &W1 = *p->W1;
+    p->T1 = mk(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2]}, 2);
+    p->g1 = plan_gemm(L, false, v, false, *p->T1);
+    p->T3 = mk(ctx, {L.inds[0], W1.inds[2], W1.inds[3], v.inds[2]}, 2);
+    p->x2 = plan_transform(*p->T1, *p->T3, {0, -1, -1, 3}, &W1, {1, 2});
+    p->P = mk(ctx, {L.inds[0], W1.inds[2], R.inds[0]}, 2);
+    p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
+    Tensor Q(ctx, p->P->inds, 1, false);
+    TNL_CHECK(Q.nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
+    p->x5 = plan_transform(*p->P, Q, {0, 1, 2}, nullptr, {});
+    p->flops = p->g1->flops + p->x2->flops + p->g4->flops;
+  } else if (nsite == 0) {
+    TNL_CHECK(v.rank() == 2 && rpos - lpos == 1, "zero-site apply needs a (l,r) bond matrix and nsite=0 position");
+    const Tensor &L = *p->L, &R = *p->R;
+    p->T1 = mk(ctx, {L.inds[0], L.inds[1], v.inds[1]}, 2);            // [(l' w) | r]
+    p->g1 = plan_gemm(L, false, v, false, *p->T1);
+    p->T3 = mk(ctx, p->T1->inds, 1);                                  // [l' | (w r)]
+    p->x2 = plan_transform(*p->T1, *p->T3, {0, 1, 2}, nullptr, {});
+    p->P = mk(ctx, {L.inds[0], R.inds[0]}, 1);
+    p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
+    TNL_CHECK(p->P->nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
+    p->flops = p->g1->flops + p->g4->flops;
+  } else {
+    throw Error(2, "nsite must be 0, 1 or 2");
+  }
+  p->nelem = v.nelem;
+  ap = p;
+}
+
+double Env::apply_flops() const { return ap ? ap->flops : 0.0; }
+
+void Env::apply(const Tensor& v, Tensor& out) {
+  TNL_CHECK(out.nelem == v.nelem && out.nrow == 1, "output vector layout mismatch");
+  apply_ptr(v, v.d, out.d);
+}
+
+void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
+  if (!ap || ap->nsite != nsite || ap->nelem != proto.nelem) build_apply_plan(proto);
+  ApplyPlan& p = *ap;
+  struct { const double* d; } v{vin};
+  struct { double* d; } out{vout};
+  run_gemm(ctx, *p.g1, p.L->d, v.d, p.T1->d);
+  if (p.nsite == 2) {
+    run_transform(ctx, *p.x2, p.T1->d, p.T2->d, p.W1->d);
+    run_transform(ctx, *p.x3, p.T2->d, p.T3->d, p.W2->d);
+    run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
+    run_transform(ctx, *p.x5, p.P->d, out.d, nullptr);
+  } else if (p.nsite == 1) {
+    run_transform(ctx, *p.x2, p.T1->d, p.T3->d, p.W1->d);
+    run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
+    run_transform(ctx, *p.x5, p.P->d, out.d, nullptr);
+  } else {
+    run_transform(ctx, *p.x2, p.T1->d, p.T3->d, nullptr);
+    run_gemm(ctx, *p.g4, p.T3->d, p.R->d, out.d);
+  }
+  ctx->cnt.apply_count += 1;
+}
+
+double Env::expectation(const Tensor& phi) {
+  Tensor tmp(ctx, phi.inds, 1);
+  apply(phi, tmp);
+  vec_dot(ctx, phi.d, tmp.d, phi.nelem, 0);
+  fetch_scalars(ctx, 1);
+  return ctx->h_scalars[0];
+}
+
+// ------------------------------------------------------------------------------------ Lanczos
+// small dense symmetric eigenproblem (cyclic Jacobi); eigenvalues ascending, eigenvectors in columns
+static void sym_eig(int n, std::vector<double>& Amat, std::vector<double>& D, std::vector<double>& U) {
+  U.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) U[i * n + i] = 1.0;
+  auto a = [&](int i, int j) -> double& { return Amat[(size_t)i * n + j]; };
+  auto u = [&](int i, int j) -> double& { return U[(size_t)i * n + j]; };
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0, dia = 0;
+    for (int i = 0; i < n; i++) {
+      dia += a(i, i) * a(i, i);
+      for (int j = i + 1; j < n; j++) off += a(i, j) * a(i, j);
+    }
+    if (off <= 1e-32 * dia || off == 0.0) break;
+    for (int p = 0; p < n - 1; p++)
+      for (int q = p + 1; q < n; q++) {
+        double apq = a(p, q);
+        if (apq == 0.0) continue;
+        double theta = (a(q, q) - a(p, p)) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; k++) {
+          double akp = a(k, p), akq = a(k, q);
+          a(k, p) = c * akp - s * akq;
+          a(k, q) = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; k++) {
+          double apk = a(p, k), aqk = a(q, k);
+          a(p, k) = c * apk - s * aqk;
+          a(q, k) = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; k++) {
+          double ukp = u(k, p), ukq = u(k, q);
+          u(k, p) = c * ukp - s * ukq;
+          u(k, q) = s * ukp + c * ukq;
+        }
+      }
+  }
+  std::vector<int> perm(n);
+  std::iota(perm.begin(), perm.end(), 0);
+  std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return a(x, x) < a(y, y); });
+  D.resize(n);
+  std::vector<double> U2((size_t)n * n);
+  for (int j = 0; j < n; j++) {
+    D[j] = a(perm[j], perm[j]);
+    // sign convention: largest-magnitude component positive (makes results reproducible across backends)
+    int im = 0;
+    for (int i = 1; i < n; i++)
+      if (std::fabs(u(i, perm[j])) > std::fabs(u(im, perm[j]))) im = i;
+    double sg = u(im, perm[j]) < 0 ? -1.0 : 1.0;
+    for (int i = 0; i < n; i++) U2[(size_t)i * n + j] = sg * u(i, perm[j]);
+  }
+  U.swap(U2);
+}
+
+// KrylovKit `_householder!` for a real vector: H = I - beta v v^T, H x = nu e_i, nu >= 0
+static void householder(const std::vector<double>& x, int i, double& beta, std::vector<double>& v, double& nu) {
+  v = x;
+  double sigma = 0;
+  for (int k = 0; k < (int)x.size(); k++)
+    if (k != i) sigma += x[k] * x[k];
+  double vi = x[i];
+  nu = std::sqrt(vi * vi + sigma);
+  if (sigma == 0.0 && vi == nu) { beta = 0.0; return; }
+  if (vi < 0) vi = vi - nu; else vi = -sigma / (vi + nu);
+  for (auto& e : v) e /= vi;
+  v[i] = 1.0;
+  beta = -vi / nu;
+}
+
+// Restatement of KrylovKit.eigsolve(A, x0, 1, :SR, Lanczos(krylovdim, maxiter, tol, eager; orth = MGS2)).
+// The same algorithm is restated independently in oracle/krylov.py.
+LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter, bool eager) {
+  TNL_CHECK(krylovdim >= 1 && krylovdim < 200, "krylovdim out of range");
+  const int64_t n = phi.nelem;
+  const int howmany = 1;
+  std::vector<double*> V;                  // Krylov basis (device buffers)
+  auto newvec = [&]() { return (double*)ctx->alloc(n * sizeof(double)); };
+  double* r = newvec();
+  auto applyraw = [&](double* vin, double* vout) { apply_ptr(phi, vin, vout); };
+  // ---- initialize
+  vec_dot(ctx, phi.d, phi.d, n, 0);
+  fetch_scalars(ctx, 1);
+  double beta0 = std::sqrt(ctx->h_scalars[0]);
+  TNL_CHECK(beta0 > 0, "initial vector should not have norm zero");
+  applyraw(phi.d, r);                                   // Ax0
+  vec_dot(ctx, phi.d, r, n, 0);
+  fetch_scalars(ctx, 1);
+  double alpha = ctx->h_scalars[0] / (beta0 * beta0);
+  double* v0 = newvec();
+  vec_scale_to(ctx, v0, phi.d, n, 1.0 / beta0);
+  vec_scale(ctx, r, n, 1.0 / beta0);
+  vec_axpy(ctx, r, v0, n, -alpha);
+  vec_dot(ctx, v0, r, n, 0);                            // MGS2 correction
+  vec_axpy_dev(ctx, r, v0, n, 0, -1.0);
+  vec_dot(ctx, r, r, n, 1);
+  fetch_scalars(ctx, 2);
+  alpha += ctx->h_scalars[0];
+  double beta = std::sqrt(ctx->h_scalars[1]);
+  V.push_back(v0);
+  std::vector<double> alphas{alpha}, betas{beta};
+  LanczosResult res;
+  res.numops = 1;
+  res.numiter = 1;
+  int converged = 0;
+  std::vector<double> D, U, f;
+  int Klast = 0;
+  while (true) {
+    beta = betas.back();
+    const int K = (int)alphas.size();
+    if (K == krylovdim || beta <= tol || (eager && K >= howmany)) {
+      Klast = K;
+      if (K == 1) {
+        D = {alphas[0]}; U = {1.0}; f = {beta};
+        converged = beta <= tol ? 1 : 0;
+      } else {
+        std::vector<double> T((size_t)K * K, 0.0);
+        for (int j = 0; j < K; j++) T[(size_t)j * K + j] = alphas[j];
+        for (int j = 0; j + 1 < K; j++) T[(size_t)j * K + j + 1] = T[(size_t)(j + 1) * K + j] = betas[j];
+        sym_eig(K, T, D, U);
+        f.resize(K);
+        for (int j = 0; j < K; j++) f[j] = U[(size_t)(K - 1) * K + j] * beta;
+        converged = 0;
+        while (converged < K && std::fabs(f[converged]) <= tol) converged++;
+      }
+      if (converged >= howmany) break;
+    }
+    if (K < krylovdim) {
+      // expand! + lanczosrecurrence (ModifiedGramSchmidt2)
+      double bold = betas.back();
+      double* vnew = r;
+      vec_scale(ctx, vnew, n, 1.0 / bold);
+      V.push_back(vnew);
+      double* w = newvec();
+      applyraw(vnew, w);
+      res.numops++;
+      const int m = (int)V.size();
+      vec_axpy(ctx, w, V[m - 2], n, -bold);
+      vec_dot(ctx, vnew, w, n, 0);
+      vec_axpy_dev(ctx, w, vnew, n, 0, -1.0);
+      for (int q = 0; q < m; q++) {
+        vec_dot(ctx, V[q], w, n, 1 + q);
+        vec_axpy_dev(ctx, w, V[q], n, 1 + q, -1.0);
+      }
+      vec_dot(ctx, w, w, n, 1 + m);
+      fetch_scalars(ctx, 2 + m);
+      double a = ctx->h_scalars[0] + ctx->h_scalars[m];       // alpha + last correction (against vnew)
+      double b = std::sqrt(ctx->h_scalars[1 + m]);
+      alphas.push_back(a);
+      betas.push_back(b);
+      r = w;
+    } else {
+      if (res.numiter == maxiter) break;
+      const int keep = (3 * krylovdim + 2 * converged) / 5;
+      // restore tridiagonal form of [diag(D[:keep]); f[:keep]^T] with Householder reflections
+      std::vector<double> H((size_t)(keep + 1) * keep, 0.0);
+      auto h = [&](int i, int j) -> double& { return H[(size_t)i * keep + j]; };
+      for (int j = 0; j < keep; j++) { h(j, j) = D[j]; h(keep, j) = f[j]; }
+      std::vector<double> U2 = U;      // K x K row-major
+      for (int j = keep - 1; j >= 0; j--) {
+        std::vector<double> x(j + 1), hv;
+        for (int c = 0; c <= j; c++) x[c] = h(j + 1, c);
+        double hb, nu;
+        householder(x, j, hb, hv, nu);
+        h(j + 1, j) = nu;
+        for (int c = 0; c < j; c++) h(j + 1, c) = 0.0;
+        if (hb != 0.0) {
+          for (int c = 0; c < keep; c++) {            // rows 0..j from the left
+            double s = 0;
+            for (int i = 0; i <= j; i++) s += hv[i] * h(i, c);
+            for (int i = 0; i <= j; i++) h(i, c) -= hb * hv[i] * s;
+          }
+          for (int i = 0; i <= j; i++) {              // columns 0..j of rows 0..j from the right
+            double s = 0;
+            for (int c = 0; c <= j; c++) s += h(i, c) * hv[c];
+            for (int c = 0; c <= j; c++) h(i, c) -= hb * s * hv[c];
+          }
+          for (int i = 0; i < K; i++) {               // accumulate into U
+            double s = 0;
+            for (int c = 0; c <= j; c++) s += U2[(size_t)i * K + c] * hv[c];
+            for (int c = 0; c <= j; c++) U2[(size_t)i * K + c] -= hb * s * hv[c];
+          }
+        }
+      }
+      // basistransform!: B_new[j] = sum_i B[i] U2[i, j]
+      std::vector<double*> newV;
+      for (int j = 0; j < keep; j++) {
+        double* y = newvec();
+        std::vector<double> coef(K);
+        for (int i = 0; i < K; i++) coef[i] = U2[(size_t)i * K + j];
+        vec_lincomb(ctx, y, V.data(), coef.data(), K, n);
+        newV.push_back(y);
+      }
+      for (double* p : V) ctx->free(p);
+      V = newV;
+      alphas.resize(keep);
+      betas.resize(keep);
+      for (int j = 0; j < keep; j++) { alphas[j] = h(j, j); betas[j] = h(j + 1, j); }
+      vec_scale(ctx, r, n, betas.back() / beta);      // B[keep+1] = r/beta ; shrink!: r <- that * normres
+      res.numiter++;
+    }
+  }
+  // eigenvector = B * U[:, 0]
+  {
+    const int K = Klast;
+    std::vector<double> coef(K);
+    for (int i = 0; i < K; i++) coef[i] = U[(size_t)i * K + 0];
+    TNL_CHECK((int)V.size() >= K, "Krylov basis bookkeeping");
+    vec_lincomb(ctx, phi.d, V.data(), coef.data(), K, n);
+  }
+  ctx->sync();
+  for (double* p : V) ctx->free(p);
+  if (std::find(V.begin(), V.end(), r) == V.end()) ctx->free(r);
+  res.eval = D[0];
+  res.converged = converged;
+  res.normres = std::fabs(f[0]);
+  return res;
+}
+
+}  // namespace tnl
+
+namespace tnl {
+
+// ------------------------------------------------------------------------------- noise term
+// ITensorMPS `noiseterm(::ProjMPO, phi, ortho)`: nt = L*W_j*phi (left) | phi*W_{j+1}*R (right); the density
+// perturbation nt*dag(noprime(nt)) is formed inside factorize() as X X^T / X^T X per charge group.
+TensorP Env::noise_tensor(const Tensor& phi, bool left) {
+  TNL_CHECK(nsite == 2 && phi.rank() == 4, "noise term only defined for 2-site ProjMPO");
+  const int first = lpos + 1;
+  if (left) {
+    TensorP L = lproj();
+    const TensorP& W1 = Wlr[first - 1];
+    auto T1 = std::make_shared<Tensor>(ctx, std::vector<Index>{L->inds[0], L->inds[1], phi.inds[1], phi.inds[2], phi.inds[3]}, 2);
+    auto g1 = plan_gemm(*L, false, phi, false, *T1);
+    run_gemm(ctx, *g1, L->d, phi.d, T1->d);
+    auto X = std::make_shared<Tensor>(ctx, std::vector<Index>{L->inds[0], W1->inds[2], W1->inds[3], phi.inds[2], phi.inds[3]}, 2);
+    auto x = plan_transform(*T1, *X, {0, -1, -1, 3, 4}, W1.get(), {1, 2});
+    run_transform(ctx, *x, T1->d, X->d, W1->d);
+    ctx->sync();
+    return X;
+  }
+  TensorP R = relayout(ctx, *rproj(), 2);                       // [(r' w) | r]
+  TensorP P3 = relayout(ctx, phi, 3);                           // [(l s1 s2) | r]
+  const TensorP& W2 = Wnr[first];                               // (s, wr | wl, s')
+  auto Xa = std::make_shared<Tensor>(ctx, std::vector<Index>{phi.inds[0], phi.inds[1], phi.inds[2], R->inds[0], R->inds[1]}, 3);
+  auto g1 = plan_gemm(*P3, false, *R, true, *Xa);
+  run_gemm(ctx, *g1, P3->d, R->d, Xa->d);
+  auto X = std::make_shared<Tensor>(ctx, std::vector<Index>{phi.inds[0], phi.inds[1], W2->inds[2], W2->inds[3], R->inds[0]}, 3);
+  auto x = plan_transform(*Xa, *X, {0, 1, -1, -1, 3}, W2.get(), {2, 4});
+  run_transform(ctx, *x, Xa->d, X->d, W2->d);
+  ctx->sync();
+  return X;
+}
+
+// ITensorMPS `replacebond!(psi, pos, phi; ortho, maxdim, mindim, cutoff, eigen_perturbation, normalize)`
+FactorizeResult Env::replacebond(int pos, const Tensor& phi, FactorizeParams prm, bool normalize) {
+  TNL_CHECK(pos >= 1 && pos < N && phi.rank() == 4, "replacebond: bad bond / tensor");
+  TensorP X;
+  if (prm.noise != 0.0) {
+    X = noise_tensor(phi, prm.ortho_left != 0);
+    prm.noiseX = X.get();
+  }
+  TensorP S = relayout(ctx, phi, 2);
+  FactorizeResult f = factorize(ctx, *S, prm);
+  if (normalize) {
+    Tensor& t = prm.ortho_left ? *f.R : *f.L;
+    vec_dot(ctx, t.d, t.d, t.nelem, 0);
+    fetch_scalars(ctx, 1);
+    double nrm = std::sqrt(ctx->h_scalars[0]);
+    TNL_CHECK(nrm > 0, "replacebond: zero norm");
+    vec_scale(ctx, t.d, t.nelem, 1.0 / nrm);
+  }
+  A[pos - 1] = f.L;
+  A[pos] = f.R;
+  ap.reset();
+  return f;
+}
+
+// ITensorMPS `orthogonalize!(psi, 1)` for a fresh MPS: right-canonicalise sites N..2 without truncation
+void Env::orthogonalize_all_right() {
+  for (int j = N - 1; j >= 1; j--) {
+    TensorP Aq = as_nrow(ctx, A[j], 1);            // [l | s r]
+    FactorizeParams prm;
+    prm.ortho_left = 0;
+    prm.which = 1;
+    prm.cutoff = 0.0;
+    FactorizeResult f = factorize(ctx, *Aq, prm);  // L = U*S (l, m) ; R = V (m, s, r)
+    A[j] = f.R;
+    TensorP Ap = as_nrow(ctx, A[j - 1], 2);        // [(l0 s0) | l]
+    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{Ap->inds[0], Ap->inds[1], f.L->inds[1]}, 2);
+    TensorP C = as_nrow(ctx, f.L, 1);
+    auto g = plan_gemm(*Ap, false, *C, false, *An);
+    run_gemm(ctx, *g, Ap->d, C->d, An->d);
+    ctx->sync();
+    A[j - 1] = An;
+  }
+  lpos = 0; rpos = N + 1; ap.reset();
+}
+
+}  // namespace tnl

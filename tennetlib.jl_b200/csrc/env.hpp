@@ -1,0 +1,88 @@
+// Device-resident mirror of the reference's StateEnvs{ProjMPO} (src/mps/state_envs.jl:18-27,54-60):
+// the MPS, the MPO, the cached left/right environments with lpos/rpos watermarks
+// (same contract as src/mps/projcouplingmodel.jl:123-129,212-218), the H_eff apply, the Lanczos
+// eigensolver around it and the bond factorisation.
+#pragma once
+#include "core.hpp"
+
+namespace tnl {
+
+struct HostBlocks {             // NDTensors-style flat host tensor (column-major blocks)
+  int rank = 0;
+  std::vector<Index> inds;
+  std::vector<std::vector<int>> coords;
+  std::vector<int64_t> offsets;
+  const double* data = nullptr;
+};
+
+TensorP import_tensor(Ctx* ctx, const HostBlocks& hb, int nrow);
+// natural-layout copy: blocks contiguous column-major, column-major block order
+TensorP to_natural(Ctx* ctx, const Tensor& t);
+TensorP relayout(Ctx* ctx, const Tensor& t, int nrow);
+
+struct FactorizeParams {
+  int ortho_left = 1;           // 1: L isometry ("left"), 0: R isometry ("right")
+  int64_t maxdim = INT64_MAX;
+  int64_t mindim = 1;
+  double cutoff = 0.0;
+  int which = 0;                // 0 = automatic (reference rule), 1 = svd, 2 = eigen
+  double noise = 0.0;           // scale of the density-matrix perturbation
+  const Tensor* noiseX = nullptr;   // see factorize.cu
+  int new_dir_on_L = -1;        // arrow of the new index on the left factor
+};
+struct FactorizeResult {
+  TensorP L, R;                 // L: (rows..., m) nrow = split ; R: (m, cols...) nrow = 1
+  std::vector<double> eigs;     // kept spectrum, descending
+  double truncerr = 0.0;
+  std::string path;
+};
+// T must be laid out with nrow = split.
+FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm);
+
+struct LanczosResult {
+  double eval = 0;
+  int converged = 0;
+  int numops = 0;
+  int numiter = 0;
+  double normres = 0;
+};
+
+class Env {
+ public:
+  Ctx* ctx;
+  int N;
+  int nsite = 2;
+  int lpos, rpos;
+  std::vector<TensorP> Wlr, Wrl, Wnr; // MPO tensors as transform operands: (wl,s | s',wr), (s',wr | wl,s), (s,wr | wl,s')
+  std::vector<Index> Wl, Wr;         // MPO link indices per site
+  std::vector<TensorP> A;            // site tensors (l, s, r), any nrow
+  std::vector<TensorP> LR;           // LR[j] = L_{j+1} (nrow 2) or R_{j+1} (nrow 1), 0-based slot j = site j+1
+  TensorP Ledge, Redge;
+
+  Env(Ctx* c, int n) : ctx(c), N(n), lpos(0), rpos(n + 1), Wlr(n), Wrl(n), Wnr(n), Wl(n), Wr(n), A(n), LR(n) {}
+
+  void set_site_op(int site, const HostBlocks& hb);     // W(wl, s', s, wr), 1-based site
+  void set_state(int site, TensorP a);
+  void position(int pos);                               // makeL!(pos-1), makeR!(pos+nsite)
+  TensorP make_phi(int pos);                            // two-site tensor (l,s1,s2,r) in Krylov layout (nrow 1)
+  void apply(const Tensor& v, Tensor& out);             // out = H_eff v, both in Krylov layout
+  void apply_ptr(const Tensor& proto, const double* vin, double* vout);
+  LanczosResult eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter, bool eager);
+  double expectation(const Tensor& phi);
+  FactorizeResult replacebond(int pos, const Tensor& phi, FactorizeParams prm, bool normalize);
+  void orthogonalize_all_right();                       // gauge the whole MPS right-canonical (centre at site 1)
+  double apply_flops() const;                           // algorithmic flops of one H_eff apply at the current position
+
+ private:
+  struct ApplyPlan;
+  std::shared_ptr<ApplyPlan> ap;
+  void build_apply_plan(const Tensor& v);
+  TensorP lproj();
+  TensorP rproj();
+  void ensure_edges();
+  void makeL(int k);
+  void makeR(int k);
+  TensorP noise_tensor(const Tensor& phi, bool left);
+};
+
+}  // namespace tnl

@@ -1,0 +1,476 @@
+// Hand-written sm_100a kernels of the tnl_b200 hot path.
+//
+//  * gemm_kernel      : grouped FP64 GEMM over charge sectors.  Blackwell has no tcgen05/UMMA kind for
+//                       FP64; the FP64 tensor op is the warp-level DMMA.8x8x4 (mma.sync.m8n8k4.f64).
+//                       128x128x16 CTA tiles, 8 warps x (64x32) register tiles, 4-stage cp.async (LDGSTS.128)
+//                       pipeline into bank-conflict-free padded shared memory.  Replaces the per-block-pair
+//                       `permutedims + BLAS.gemm!` loop NDTensors runs for every ITensor `*` on the reference
+//                       hot path (src/mps/projcouplingmodel.jl:145-147,342-343; ITensorMPS ProjMPO.product).
+//  * transform_kernel : HBM-bound regrouping pass that also applies the skinny MPO site operators
+//                       (the `* W_j` steps of ProjMPO.product / `_makeL!`), one warp per output column.
+//  * vec kernels      : flat Krylov-vector kernels (VectorInterface inner/add!!/scale!!/norm as used by
+//                       KrylovKit.eigsolve from src/base/solver.jl:36) with warp-shuffle reductions.
+#include "core.hpp"
+
+#include <algorithm>
+
+namespace tnl {
+
+// =================================================================================================
+// helpers
+// =================================================================================================
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// =================================================================================================
+// grouped DGEMM
+// =================================================================================================
+// operand tile in shared memory.  KFAST = the operand is contiguous along k in global memory.
+//   !KFAST : smem[k][x]  row stride BX+4      (x = m or n)
+//    KFAST : smem[x][k]  row stride BK+4
+// Both strides are == 4 (mod 16) doubles, which makes the DMMA fragment loads (8 x-values x 4 k-values per
+// warp, 64-bit each) hit 16 distinct 8-byte bank pairs per half-warp: conflict free.
+template <int BX, int BK, bool KFAST>
+struct OpTile {
+  static constexpr int LD = KFAST ? (BK + 4) : (BX + 4);
+  static constexpr int ELEMS = KFAST ? BX * LD : BK * LD;
+  // global element (x, k) lives at  g + x*sx + k*sk ; exactly one of sx/sk is 1
+  template <int NT>
+  __device__ static __forceinline__ void load(double* s, const double* g, int ld, int x0, int k0, int X, int K, int tid) {
+    constexpr int CH = BX * BK / 2;   // 16-byte chunks
+    if (KFAST) {
+      constexpr int CPR = BK / 2;
+#pragma unroll
+      for (int c = tid; c < CH; c += NT) {
+        int xx = c / CPR, kc = c % CPR;
+        int x = x0 + xx, k = k0 + 2 * kc;
+        int v = (x < X) ? max(0, min(2, K - k)) : 0;
+        const double* src = v ? (g + (int64_t)x * ld + k) : g;
+        cp_async16(s + xx * LD + 2 * kc, src, v * 8);
+      }
+    } else {
+      constexpr int CPR = BX / 2;
+#pragma unroll
+      for (int c = tid; c < CH; c += NT) {
+        int kk = c / CPR, xc = c % CPR;
+        int x = x0 + 2 * xc, k = k0 + kk;
+        int v = (k < K) ? max(0, min(2, X - x)) : 0;
+        const double* src = v ? (g + (int64_t)k * ld + x) : g;
+        cp_async16(s + kk * LD + 2 * xc, src, v * 8);
+      }
+    }
+  }
+  __device__ static __forceinline__ double frag(const double* s, int x, int k) {
+    return KFAST ? s[x * LD + k] : s[k * LD + x];
+  }
+};
+
+template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+gemm_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles,
+            const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase) {
+  constexpr int NT = (BM / WM) * (BN / WN) * 32;
+  using TileA = OpTile<BM, BK, TA>;     // A is k-fast when transposed (stored [k, m])
+  using TileB = OpTile<BN, BK, !TB>;    // B is k-fast when NOT transposed (stored [k, n])
+  constexpr int STAGE_ELEMS = TileA::ELEMS + TileB::ELEMS;
+  extern __shared__ __align__(16) double smem[];
+
+  const GemmTile tile = tiles[blockIdx.x];
+  const GemmProblem p = probs[tile.prob];
+  const double* pA = Abase + p.a;
+  const double* pB = Bbase + p.b;
+  double* pC = Cbase + p.c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp % (BM / WM)) * WM, wn0 = (warp / (BM / WM)) * WN;
+  const int m0 = tile.m0, n0 = tile.n0;
+  const int ktiles = (p.K + BK - 1) / BK;
+
+  double acc[WM / 8][WN / 8][2];
+#pragma unroll
+  for (int i = 0; i < WM / 8; i++)
+#pragma unroll
+    for (int j = 0; j < WN / 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto issue = [&](int kt) {
+    double* sa = smem + (kt % STAGES) * STAGE_ELEMS;
+    double* sb = sa + TileA::ELEMS;
+    TileA::template load<NT>(sa, pA, p.lda, m0, kt * BK, p.M, p.K, tid);
+    TileB::template load<NT>(sb, pB, p.ldb, n0, kt * BK, p.N, p.K, tid);
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < ktiles) issue(s);
+    cp_async_commit();
+  }
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int kt = 0; kt < ktiles; kt++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (kt + STAGES - 1 < ktiles) issue(kt + STAGES - 1);
+    cp_async_commit();
+    const double* sa = smem + (kt % STAGES) * STAGE_ELEMS;
+    const double* sb = sa + TileA::ELEMS;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; kk++) {
+      double a[WM / 8], b[WN / 8];
+#pragma unroll
+      for (int i = 0; i < WM / 8; i++) a[i] = TileA::frag(sa, wm0 + i * 8 + lr, kk * 4 + lc);
+#pragma unroll
+      for (int j = 0; j < WN / 8; j++) b[j] = TileB::frag(sb, wn0 + j * 8 + lr, kk * 4 + lc);
+#pragma unroll
+      for (int i = 0; i < WM / 8; i++)
+#pragma unroll
+        for (int j = 0; j < WN / 8; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+  // epilogue: C fragment = rows lane>>2, cols 2*(lane&3)+{0,1}
+#pragma unroll
+  for (int i = 0; i < WM / 8; i++) {
+    int m = m0 + wm0 + i * 8 + lr;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < WN / 8; j++) {
+      int n = n0 + wn0 + j * 8 + 2 * lc;
+      double* c = pC + (int64_t)n * p.ldc + m;
+      if (n < p.N) c[0] = acc[i][j][0];
+      if (n + 1 < p.N) c[p.ldc] = acc[i][j][1];
+    }
+  }
+}
+
+template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
+static void launch_gemm_one(Ctx* ctx, const GemmProblem* probs, const GemmTile* tiles, int ntiles,
+                            const double* A, const double* B, double* C) {
+  constexpr int NT = (BM / WM) * (BN / WN) * 32;
+  constexpr size_t SMEM = sizeof(double) * STAGES * (OpTile<BM, BK, TA>::ELEMS + OpTile<BN, BK, !TB>::ELEMS);
+  auto kern = gemm_kernel<BM, BN, BK, WM, WN, TA, TB, STAGES>;
+  static bool configured = false;   // one static per template instantiation
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    configured = true;
+  }
+  kern<<<ntiles, NT, SMEM, ctx->stream>>>(probs, tiles, A, B, C);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.gemm_launches++;
+}
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES>
+static void launch_gemm_cfg(Ctx* ctx, bool ta, bool tb, const GemmProblem* probs, const GemmTile* tiles, int ntiles,
+                            const double* A, const double* B, double* C) {
+  if (ntiles == 0) return;
+  if (!ta && !tb) launch_gemm_one<BM, BN, BK, WM, WN, false, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
+  else if (!ta && tb) launch_gemm_one<BM, BN, BK, WM, WN, false, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
+  else if (ta && !tb) launch_gemm_one<BM, BN, BK, WM, WN, true, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
+  else launch_gemm_one<BM, BN, BK, WM, WN, true, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
+}
+
+void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C) {
+  for (auto& z : p.zero_fill) CUDA_OK(cudaMemsetAsync(C + z.first, 0, z.second * sizeof(double), ctx->stream));
+  launch_gemm_cfg<128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, (int)p.tiles_big.size(), A, B, C);
+  launch_gemm_cfg<64, 64, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_small, (int)p.tiles_small.size(), A, B, C);
+  ctx->cnt.gemm_flops += p.flops;
+}
+
+// =================================================================================================
+// transform: Y(i, n.., p..) = sum_c sum_k X_c(i, k.., p..) * W_c(k, n)      one warp per output column
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+transform_kernel(const XfBlock* __restrict__ blocks, int nblocks, const XfContrib* __restrict__ contribs,
+                 const double* __restrict__ X, double* __restrict__ Y, const double* __restrict__ W, int64_t ncols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; col < ncols; col += nwarps) {
+    int lo = 0, hi = nblocks - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (blocks[mid].colstart <= col) lo = mid; else hi = mid - 1;
+    }
+    const XfBlock& b = blocks[lo];
+    int64_t t = col - b.colstart;
+    int n0 = (int)(t % b.nd0); t /= b.nd0;
+    int n1 = (int)(t % b.nd1); t /= b.nd1;
+    int64_t ybase = b.yoff + n0 * b.yns[0] + n1 * b.yns[1];
+    int pidx[MAXP];
+#pragma unroll
+    for (int k = 0; k < MAXP; k++) {
+      pidx[k] = (int)(t % b.pd[k]); t /= b.pd[k];
+      ybase += pidx[k] * b.yps[k];
+    }
+    const int na = n0 + b.nd0 * n1;
+    const int I = b.I;
+    for (int i0 = 0; i0 < I; i0 += 128) {
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int c = b.cbeg; c < b.cbeg + b.cnum; c++) {
+        const XfContrib& cc = contribs[c];
+        int64_t xb = cc.xoff;
+#pragma unroll
+        for (int k = 0; k < MAXP; k++) xb += pidx[k] * cc.xps[k];
+        const int Ka = cc.kd0 * cc.kd1;
+        for (int a1 = 0; a1 < cc.kd1; a1++)
+          for (int a0 = 0; a0 < cc.kd0; a0++) {
+            const double w = W ? W[cc.woff + a0 + cc.kd0 * a1 + (int64_t)Ka * na] : 1.0;
+            const double* xp = X + xb + a0 * cc.ks0 + a1 * cc.ks1;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              int i = i0 + lane + 32 * u;
+              if (i < I) acc[u] = fma(xp[i], w, acc[u]);
+            }
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        int i = i0 + lane + 32 * u;
+        if (i < I) Y[ybase + i] = acc[u];
+      }
+    }
+  }
+}
+
+void run_transform(Ctx* ctx, TransformPlan& p, const double* X, double* Y, const double* W) {
+  if (p.ncols == 0) return;
+  int64_t warps_needed = p.ncols;
+  int64_t blocks = std::min<int64_t>((warps_needed + 7) / 8, (int64_t)ctx->num_sms * 32);
+  transform_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_contribs, X, Y, W, p.ncols);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.xf_bytes += p.bytes;
+  ctx->cnt.xf_flops += p.flops;
+}
+
+// =================================================================================================
+// flat vector kernels
+// =================================================================================================
+constexpr int VT = 256;        // threads
+constexpr int VMAXB = 148 * 8; // partial slots
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// deterministic two-level reduction: per-block partials, the last block to finish sums them in order
+__global__ void __launch_bounds__(VT)
+dot_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n2, double* __restrict__ partials,
+           unsigned int* __restrict__ sync, double* __restrict__ out) {
+  const double2* x2 = reinterpret_cast<const double2*>(x);
+  const double2* y2 = reinterpret_cast<const double2*>(y);
+  double s0 = 0.0, s1 = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * VT;
+  int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x;
+  for (; i + stride < n2; i += 2 * stride) {       // two independent loads in flight
+    double2 a = x2[i], b = y2[i];
+    double2 c = x2[i + stride], d = y2[i + stride];
+    s0 = fma(a.x, b.x, s0); s0 = fma(a.y, b.y, s0);
+    s1 = fma(c.x, d.x, s1); s1 = fma(c.y, d.y, s1);
+  }
+  if (i < n2) { double2 a = x2[i], b = y2[i]; s0 = fma(a.x, b.x, s0); s0 = fma(a.y, b.y, s0); }
+  double s = warp_sum(s0 + s1);
+  __shared__ double ws[VT / 32];
+  __shared__ bool last;
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < VT / 32; w++) t += ws[w];
+    partials[blockIdx.x] = t;
+    __threadfence();
+    unsigned int done = atomicAdd(sync, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double t = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += VT) t += partials[b];   // fixed assignment
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r = 0.0;
+      for (int w = 0; w < VT / 32; w++) r += ws[w];
+      *out = r;
+      *sync = 0u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(VT)
+axpy_kernel(double* __restrict__ y, const double* __restrict__ x, int64_t n2, const double* __restrict__ sdev, double a) {
+  const double s = sdev ? a * (*sdev) : a;
+  double2* y2 = reinterpret_cast<double2*>(y);
+  const double2* x2 = reinterpret_cast<const double2*>(x);
+  const int64_t stride = (int64_t)gridDim.x * VT;
+  for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += stride) {
+    double2 a2 = x2[i], b2 = y2[i];
+    b2.x = fma(s, a2.x, b2.x); b2.y = fma(s, a2.y, b2.y);
+    y2[i] = b2;
+  }
+}
+
+__global__ void __launch_bounds__(VT)
+scale_kernel(double* __restrict__ y, const double* __restrict__ x, int64_t n2, double a) {
+  double2* y2 = reinterpret_cast<double2*>(y);
+  const double2* x2 = reinterpret_cast<const double2*>(x);
+  const int64_t stride = (int64_t)gridDim.x * VT;
+  for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += stride) {
+    double2 v = x2[i];
+    v.x *= a; v.y *= a;
+    y2[i] = v;
+  }
+}
+
+constexpr int LC_MAX = 32;
+struct LincombArgs { const double* x[LC_MAX]; double c[LC_MAX]; int k; };
+__global__ void __launch_bounds__(VT)
+lincomb_kernel(double* __restrict__ y, LincombArgs a, int64_t n2) {
+  double2* y2 = reinterpret_cast<double2*>(y);
+  const int64_t stride = (int64_t)gridDim.x * VT;
+  for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += stride) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int j = 0; j < a.k; j++) {
+      double2 v = reinterpret_cast<const double2*>(a.x[j])[i];
+      acc.x = fma(a.c[j], v.x, acc.x); acc.y = fma(a.c[j], v.y, acc.y);
+    }
+    y2[i] = acc;
+  }
+}
+
+static inline int vec_grid(Ctx* ctx, int64_t n2) {
+  int64_t b = (n2 + VT - 1) / VT;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)ctx->num_sms * 8));
+}
+
+void vec_dot(Ctx* ctx, const double* x, const double* y, int64_t n, int slot) {
+  TNL_CHECK(n % 2 == 0, "padded vector length must be even");
+  dot_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(x, y, n / 2, ctx->d_partials, ctx->d_sync, ctx->d_scalars + slot);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.vec_bytes += (x == y ? 1.0 : 2.0) * n * 8.0;
+}
+void vec_axpy_dev(Ctx* ctx, double* y, const double* x, int64_t n, int slot, double sign) {
+  axpy_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(y, x, n / 2, ctx->d_scalars + slot, sign);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.vec_bytes += 3.0 * n * 8.0;
+}
+void vec_axpy(Ctx* ctx, double* y, const double* x, int64_t n, double a) {
+  axpy_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(y, x, n / 2, nullptr, a);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.vec_bytes += 3.0 * n * 8.0;
+}
+void vec_scale(Ctx* ctx, double* y, int64_t n, double a) { vec_scale_to(ctx, y, y, n, a); }
+void vec_scale_to(Ctx* ctx, double* y, const double* x, int64_t n, double a) {
+  scale_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(y, x, n / 2, a);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.vec_bytes += 2.0 * n * 8.0;
+}
+void vec_copy(Ctx* ctx, double* y, const double* x, int64_t n) {
+  CUDA_OK(cudaMemcpyAsync(y, x, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+}
+void vec_lincomb(Ctx* ctx, double* y, const double* const* xs, const double* coef, int k, int64_t n) {
+  TNL_CHECK(k <= LC_MAX, "too many vectors in linear combination");
+  LincombArgs a;
+  a.k = k;
+  for (int j = 0; j < k; j++) { a.x[j] = xs[j]; a.c[j] = coef[j]; }
+  lincomb_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(y, a, n / 2);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.vec_bytes += (k + 1.0) * n * 8.0;
+}
+void fetch_scalars(Ctx* ctx, int n) {
+  CUDA_OK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+}
+
+// =================================================================================================
+// misc elementwise kernels
+// =================================================================================================
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+struct BlkDesc { int64_t off; int64_t st[MAXR]; int d[MAXR]; int r; uint64_t key; };
+__global__ void fill_random_kernel(double* __restrict__ data, BlkDesc b, int64_t n, uint64_t seed) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = e, addr = b.off;
+    for (int k = 0; k < b.r; k++) { addr += (t % b.d[k]) * b.st[k]; t /= b.d[k]; }
+    uint64_t u = splitmix64(splitmix64(seed ^ (b.key * 0xD1342543DE82EF95ull)) + (uint64_t)e);
+    data[addr] = (double)(u >> 11) * (2.0 / 9007199254740992.0) - 1.0;   // uniform [-1, 1), 53 bits
+  }
+}
+void fill_random(Ctx* ctx, Tensor& t, uint64_t seed) {
+  for (auto& b : t.blocks) {
+    BlkDesc d;
+    d.off = b.off; d.r = t.rank(); d.key = Tensor::key(b.c, t.rank());
+    int64_t n = 1;
+    for (int k = 0; k < t.rank(); k++) { d.st[k] = b.st[k]; d.d[k] = b.d[k]; n *= b.d[k]; }
+    int grid = (int)std::min<int64_t>((n + 255) / 256, 1184);
+    fill_random_kernel<<<grid, 256, 0, ctx->stream>>>(t.d, d, n, seed);
+    CUDA_OK(cudaGetLastError());
+    ctx->cnt.launches++;
+  }
+}
+
+__global__ void scale_rc_kernel(double* __restrict__ A, int64_t ld, int64_t R, int64_t C, const double* __restrict__ s, bool rows) {
+  int64_t n = R * C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = e % R, c = e / R;
+    A[c * ld + r] *= rows ? s[r] : s[c];
+  }
+}
+void scale_rows_or_cols(Ctx* ctx, double* A, int64_t ld, int64_t R, int64_t C, const double* s, bool rows) {
+  if (R * C == 0) return;
+  int grid = (int)std::min<int64_t>((R * C + 255) / 256, 1184);
+  scale_rc_kernel<<<grid, 256, 0, ctx->stream>>>(A, ld, R, C, s, rows);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+}
+
+}  // namespace tnl
+
+namespace tnl {
+__global__ void transpose_kernel(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds, int64_t R, int64_t C) {
+  __shared__ double tile[32][33];
+  int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t r = r0 + threadIdx.x, c = c0 + j;
+    if (r < R && c < C) tile[j][threadIdx.x] = src[c * lds + r];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t c = c0 + threadIdx.x, r = r0 + j;
+    if (r < R && c < C) dst[r * ldd + c] = tile[threadIdx.x][j];
+  }
+}
+void transpose(Ctx* ctx, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t R, int64_t C) {
+  if (R * C == 0) return;
+  dim3 grid((unsigned)((R + 31) / 32), (unsigned)((C + 31) / 32)), block(32, 8);
+  transpose_kernel<<<grid, block, 0, ctx->stream>>>(dst, ldd, src, lds, R, C);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+}
+void copy2d(Ctx* ctx, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t R, int64_t C) {
+  if (R * C == 0) return;
+  CUDA_OK(cudaMemcpy2DAsync(dst, ldd * sizeof(double), src, lds * sizeof(double), R * sizeof(double), C,
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+}
+}  // namespace tnl

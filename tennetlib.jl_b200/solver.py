@@ -1,0 +1,32 @@
+"""`eig_solver` -- mirror of /root/reference/src/base/solver.jl:23-43: same keyword names and defaults; the
+KrylovKit Lanczos loop runs on the device behind `tnl_eigsolve_lanczos`."""
+from __future__ import annotations
+
+import ctypes as C
+
+from ._lib import check
+
+
+def eig_solver(env, phi0, time_step=None, **kwargs):
+    if time_step is not None:
+        raise TypeError("`eig_solver()` is only defined with `time_step=nothing`")
+    which = kwargs.get("solver_which_eigenvalue", "SR")
+    if which != "SR" or not kwargs.get("ishermitian", True):
+        raise NotImplementedError("device eig_solver supports which=:SR, ishermitian=true")
+    tol = kwargs.get("solver_tol", 1e-14)
+    krylovdim = kwargs.get("solver_krylovdim", 5)
+    maxiter = kwargs.get("solver_maxiter", 2)
+    eager = kwargs.get("solver_eager", False)
+    ev, conv, nops, nit, nres = C.c_double(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
+    check(env.ctx.lib.tnl_eigsolve_lanczos(env.h, phi0.h, float(tol), int(krylovdim), int(maxiter), 1 if eager else 0,
+                                           C.byref(ev), C.byref(conv), C.byref(nops), C.byref(nit), C.byref(nres)),
+          env.ctx.h)
+    env.last_solver_info = dict(converged=conv.value, numops=nops.value, numiter=nit.value, normres=nres.value)
+    if kwargs.get("solver_check_convergence", False) and conv.value < 1:
+        raise RuntimeError("`eig_solver()` not converged !!")
+    return ev.value, phi0
+
+
+def exp_solver(env, phi0, time_step, **kwargs):
+    """src/base/solver.jl:66-88 -- TDVP exponentiation: SURVEY.md section 8 row a7, not built yet."""
+    raise NotImplementedError("exp_solver (KrylovKit.exponentiate) is a later row of the scope table")

@@ -1,0 +1,135 @@
+"""`StateEnvs` on the GPU -- host-side mirror of /root/reference/src/mps/state_envs.jl:18-27,54-60,
+352-378 for PH = ProjMPO.  The MPS, the MPO and all environments live in HBM behind a `tnl_env_t`."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence
+
+import numpy as np
+
+from ._lib import check
+from .tensor import Context, DeviceTensor, HostTensor, _index_array, flatten_blocks
+
+
+class StateEnvs:
+    """StateEnvs(psi::MPS, H::MPO).  `psi`: sequence of site tensors A_j(l, s, r) (host tensors or
+    DeviceTensors); `H`: sequence of MPO tensors W_j(wl, s', s, wr) (host).  As in the reference the state is
+    copied on construction (state_envs.jl:59)."""
+
+    def __init__(self, ctx: Context, psi: Sequence, H: Sequence, llim: int = 0, rlim: int | None = None):
+        self.ctx = ctx
+        self.N = len(psi)
+        if len(H) != self.N:
+            raise ValueError("MPS and MPO lengths differ")
+        h = C.c_void_p()
+        check(ctx.lib.tnl_env_create(ctx.h, self.N, C.byref(h)), ctx.h)
+        self.h = h
+        for j, W in enumerate(H):
+            arr, nq, keep = _index_array(W.inds)
+            coords, offsets, data, nb = flatten_blocks(W)
+            check(ctx.lib.tnl_env_set_site_op(self.h, j + 1, nq, arr, nb, coords.ctypes.data, offsets.ctypes.data,
+                                              data.ctypes.data), ctx.h)
+        for j, A in enumerate(psi):
+            dt = A.copy() if isinstance(A, DeviceTensor) else DeviceTensor.from_host(ctx, A, nrow=2)
+            check(ctx.lib.tnl_env_set_state(self.h, j + 1, dt.h), ctx.h)
+        # orthogonality limits of the MPS (ITensorMPS llim / rlim)
+        self.llim = llim
+        self.rlim = self.N + 1 if rlim is None else rlim
+        self._nsite = 2
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.tnl_env_destroy(self.h)
+        except Exception:
+            pass
+        self.h = None
+
+    def __len__(self):
+        return self.N
+
+    # ---- MPS bookkeeping
+    def isortho(self) -> bool:
+        return self.llim + 2 == self.rlim
+
+    def orthocenter(self) -> int:
+        if not self.isortho():
+            raise RuntimeError("MPS has no well-defined orthogonality centre")
+        return self.llim + 1
+
+    def orthogonalize1(self):
+        """orthogonalize!(psi, 1) (sweep.jl:100-102)."""
+        check(self.ctx.lib.tnl_env_orthogonalize(self.h), self.ctx.h)
+        self.llim, self.rlim = 0, 2
+
+    def site_tensor(self, j: int) -> DeviceTensor:
+        h = C.c_void_p()
+        check(self.ctx.lib.tnl_env_get_state(self.h, j, C.byref(h)), self.ctx.h)
+        return DeviceTensor(self.ctx, h)
+
+    def getpsi(self) -> List[HostTensor]:
+        """getpsi (state_envs.jl:36): host copy of the MPS."""
+        return [self.site_tensor(j).to_host() for j in range(1, self.N + 1)]
+
+    def linkdims(self) -> List[int]:
+        return [self.site_tensor(j).inds[2].dim for j in range(1, self.N)]
+
+    # ---- environment interface
+    def nsite(self) -> int:
+        return self._nsite
+
+    def set_nsite(self, n: int):
+        check(self.ctx.lib.tnl_env_set_nsite(self.h, n), self.ctx.h)
+        self._nsite = n
+        return self
+
+    def position(self, pos: int):
+        check(self.ctx.lib.tnl_env_position(self.h, pos), self.ctx.h)
+        return self
+
+    def make_phi(self, pos: int) -> DeviceTensor:
+        h = C.c_void_p()
+        check(self.ctx.lib.tnl_env_make_phi(self.h, pos, C.byref(h)), self.ctx.h)
+        return DeviceTensor(self.ctx, h)
+
+    def product(self, v: DeviceTensor) -> DeviceTensor:
+        h = C.c_void_p()
+        check(self.ctx.lib.tnl_heff_apply(self.h, v.h, C.byref(h)), self.ctx.h)
+        return DeviceTensor(self.ctx, h, v._inds)
+
+    __call__ = product
+
+    def apply_flops(self) -> float:
+        out = C.c_double()
+        check(self.ctx.lib.tnl_env_apply_flops(self.h, C.byref(out)), self.ctx.h)
+        return out.value
+
+    def expectation(self, phi: DeviceTensor) -> float:
+        out = C.c_double()
+        check(self.ctx.lib.tnl_expectation(self.h, phi.h, C.byref(out)), self.ctx.h)
+        return out.value
+
+    def replacebond(self, pos: int, phi: DeviceTensor, *, maxdim, mindim, cutoff, noise, ortho, normalize,
+                    which_decomp=None, svd_alg="divide_and_conquer"):
+        """noiseterm + replacebond! (update_site.jl:59-76).  Returns (truncerr, eigs)."""
+        N = self.N
+        cap = 1 << 16
+        eigs = np.zeros(cap)
+        truncerr = C.c_double()
+        neigs = C.c_int64()
+        which = {None: 0, "svd": 1, "eigen": 2}[which_decomp]
+        md = 0 if maxdim is None or maxdim >= (1 << 62) else int(maxdim)
+        check(self.ctx.lib.tnl_replacebond(self.h, pos, phi.h, 1 if ortho == "left" else 0, md, int(mindim),
+                                           float(cutoff), float(noise), 1 if normalize else 0, which,
+                                           C.byref(truncerr), eigs.ctypes.data, cap, C.byref(neigs)), self.ctx.h)
+        if ortho == "left":
+            if self.llim == pos - 1:
+                self.llim += 1
+            if self.rlim == pos + 1:
+                self.rlim += 1
+        else:
+            if self.llim == pos:
+                self.llim -= 1
+            if self.rlim == pos + 2:
+                self.rlim -= 1
+        return truncerr.value, eigs[:min(neigs.value, cap)].copy()

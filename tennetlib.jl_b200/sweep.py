@@ -1,0 +1,67 @@
+"""Sweep driver -- mirror of /root/reference/src/mps/sweep.jl:26-196 (`SweepData`, `fullsweep!`)."""
+from __future__ import annotations
+
+import time
+from typing import List
+
+import numpy as np
+
+from .update_site import update_position
+
+
+class SweepData:
+    def __init__(self):
+        self.sweepcount = 0
+        self.maxchi: List[int] = []
+        self.energy: List[float] = []
+        self.entropy: List[float] = []
+        self.maxtruncerr: List[float] = []
+        self.lasteigs: List[np.ndarray] = []
+
+
+def _entropy(p) -> float:
+    p = np.asarray(p, dtype=np.float64)
+    p = p[p > 0]
+    return float(-np.sum(p * np.log(p)))
+
+
+def fullsweep(sysenv, solver, nsite: int, swdata: SweepData, **kwargs):
+    outputlevel = kwargs.pop("outputlevel", 1)
+    noise = kwargs.get("noise", 0.0)
+    if (not sysenv.isortho()) or sysenv.orthocenter() != 1:
+        sysenv.orthogonalize1()
+    energy = float("nan")
+    maxtruncerr = 0.0
+    swdata.sweepcount += 1
+    N = len(sysenv)
+    lasteigs = [None] * (N - 1)
+    t0 = time.time()
+    for bond in range(1, N):
+        energy, err, _ = update_position(sysenv, solver, bond, nsite, "left", **kwargs)
+        maxtruncerr = max(err, maxtruncerr)
+        if outputlevel > 1:
+            print(f"At left sweep {swdata.sweepcount} bond {bond} => Energy {energy}, Err {err:.2g}", flush=True)
+    for bond in range(N - 1, 0, -1):
+        energy, err, eigs = update_position(sysenv, solver, bond, nsite, "right", **kwargs)
+        lasteigs[bond - 1] = eigs
+        maxtruncerr = max(err, maxtruncerr)
+        if outputlevel > 1:
+            print(f"At right sweep {swdata.sweepcount} bond {bond} => Energy {energy}, Err {err:.2g}", flush=True)
+    sw_time = time.time() - t0
+    swdata.lasteigs = lasteigs
+    swdata.maxchi.append(max(sysenv.linkdims()))
+    swdata.energy.append(energy)
+    mideigs = lasteigs[N // 2 - 1]
+    swdata.entropy.append(_entropy(mideigs / np.sum(mideigs)))
+    swdata.maxtruncerr.append(maxtruncerr)
+    if swdata.sweepcount > 1:
+        enerr = swdata.energy[-1] - swdata.energy[-2]
+        enterr = swdata.entropy[-1] - swdata.entropy[-2]
+    else:
+        enerr = enterr = float("nan")
+    if outputlevel > 0:
+        print(f"At sweep {swdata.sweepcount} => E={swdata.energy[-1]}, S={swdata.entropy[-1]}, "
+              f"MaxLinkDim={swdata.maxchi[-1]}, Noise={noise:.2g}")
+        print(f"At sweep {swdata.sweepcount} => dE={enerr}, dS={enterr}, MaxErr={maxtruncerr:.2g}, Time={sw_time:.3f}",
+              flush=True)
+    return enerr, enterr

@@ -1,0 +1,239 @@
+"""Host-side index / tensor types and device handles.
+
+`Index` and `HostTensor` mirror what the Julia shim extracts from an ITensor:
+per index the (QN, dim) sectors and arrow; per tensor a dict {0-based sector coords -> dense block}.
+`DeviceTensor` wraps a `tnl_tensor_t` living in HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, tnl_index_t
+
+_ids = itertools.count(1)
+
+
+class Index:
+    __slots__ = ("id", "qns", "dims", "dir", "tags", "plev")
+
+    def __init__(self, qns, dims, dir=+1, tags="", plev=0, id=None):
+        self.qns = tuple(tuple(int(x) for x in q) for q in qns)
+        self.dims = tuple(int(d) for d in dims)
+        self.dir = int(dir)
+        self.tags = tags
+        self.plev = plev
+        self.id = next(_ids) if id is None else id
+
+    @property
+    def dim(self):
+        return sum(self.dims)
+
+    @property
+    def nsect(self):
+        return len(self.dims)
+
+    def copy(self, **kw):
+        d = dict(qns=self.qns, dims=self.dims, dir=self.dir, tags=self.tags, plev=self.plev, id=self.id)
+        d.update(kw)
+        return Index(**d)
+
+    def dag(self):
+        return self.copy(dir=-self.dir)
+
+    def prime(self, n=1):
+        return self.copy(plev=self.plev + n)
+
+    def __repr__(self):
+        return f"Index({self.tags}|dir={self.dir:+d}|" + ",".join(f"{q}:{d}" for q, d in zip(self.qns, self.dims)) + ")"
+
+
+class HostTensor:
+    """Block-sparse host tensor (any object with `.inds` and `.blocks` is accepted wherever this is)."""
+
+    def __init__(self, inds: Sequence[Index], blocks: Dict[Tuple[int, ...], np.ndarray] | None = None):
+        self.inds = list(inds)
+        self.blocks = {} if blocks is None else blocks
+
+    def to_dense(self):
+        out = np.zeros([ix.dim for ix in self.inds])
+        offs = [np.concatenate([[0], np.cumsum(ix.dims)]) for ix in self.inds]
+        for c, b in self.blocks.items():
+            out[tuple(slice(o[k], o[k + 1]) for o, k in zip(offs, c))] = b
+        return out
+
+
+def _index_array(inds):
+    """ctypes array of tnl_index_t (+ keep-alive list)."""
+    nq = len(inds[0].qns[0])
+    arr = (tnl_index_t * len(inds))()
+    keep = []
+    for k, ix in enumerate(inds):
+        dims = np.ascontiguousarray(ix.dims, dtype=np.int32)
+        qns = np.ascontiguousarray(np.array(ix.qns, dtype=np.int32).reshape(-1))
+        keep += [dims, qns]
+        arr[k].nsect = len(ix.dims)
+        arr[k].dir = ix.dir
+        arr[k].dims = dims.ctypes.data_as(C.POINTER(C.c_int32))
+        arr[k].qns = qns.ctypes.data_as(C.POINTER(C.c_int32))
+    return arr, nq, keep
+
+
+def flatten_blocks(t):
+    """NDTensors flat layout: (coords[nb,rank] i32, offsets[nb] i64, data f64), blocks column-major."""
+    keys = list(t.blocks.keys())
+    rank = len(t.inds)
+    coords = np.zeros((max(len(keys), 1), rank), dtype=np.int32)
+    offsets = np.zeros(max(len(keys), 1), dtype=np.int64)
+    chunks, off = [], 0
+    for n, c in enumerate(keys):
+        coords[n] = c
+        offsets[n] = off
+        b = np.asarray(t.blocks[c], dtype=np.float64)
+        chunks.append(b.reshape(-1, order="F"))
+        off += b.size
+    data = np.ascontiguousarray(np.concatenate(chunks)) if chunks else np.zeros(1)
+    return coords[:len(keys)] if keys else coords[:0], offsets[:len(keys)], data, len(keys)
+
+
+class Context:
+    """One CUDA context/stream of the library (`tnl_ctx_t`)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        check(self.lib.tnl_ctx_create(device, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.tnl_ctx_destroy(self.h)
+            self.h = None
+
+    def counters(self):
+        out = (C.c_double * 8)()
+        check(self.lib.tnl_get_counters(self.h, out), self.h)
+        k = ("gemm_flops", "transform_flops", "vec_bytes", "transform_bytes", "launches", "gemm_launches", "applies", "_")
+        return dict(zip(k, list(out)))
+
+    def reset_counters(self):
+        check(self.lib.tnl_reset_counters(self.h), self.h)
+
+    def sync(self):
+        check(self.lib.tnl_ctx_sync(self.h), self.h)
+
+    def timer_start(self):
+        check(self.lib.tnl_timer_start(self.h), self.h)
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        check(self.lib.tnl_timer_stop(self.h, C.byref(ms)), self.h)
+        return ms.value
+
+
+class DeviceTensor:
+    def __init__(self, ctx: Context, handle, inds: Sequence[Index] | None = None):
+        self.ctx = ctx
+        self.h = handle
+        self._inds = list(inds) if inds is not None else None
+
+    # ---- construction
+    @staticmethod
+    def from_host(ctx: Context, t, nrow: int = 1) -> "DeviceTensor":
+        arr, nq, keep = _index_array(t.inds)
+        coords, offsets, data, nb = flatten_blocks(t)
+        h = C.c_void_p()
+        check(ctx.lib.tnl_tensor_import(ctx.h, len(t.inds), nq, arr, nb, coords.ctypes.data, offsets.ctypes.data,
+                                        data.ctypes.data, nrow, C.byref(h)), ctx.h)
+        return DeviceTensor(ctx, h, t.inds)
+
+    @staticmethod
+    def zeros(ctx: Context, inds, nrow: int = 1) -> "DeviceTensor":
+        arr, nq, keep = _index_array(inds)
+        h = C.c_void_p()
+        check(ctx.lib.tnl_tensor_create(ctx.h, len(inds), nq, arr, nrow, C.byref(h)), ctx.h)
+        return DeviceTensor(ctx, h, inds)
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.tnl_tensor_free(self.h)
+        except Exception:
+            pass
+        self.h = None
+
+    # ---- queries
+    @property
+    def inds(self) -> List[Index]:
+        """Index structure as the device sees it (ids are host-side only and regenerated when unknown)."""
+        lib = self.ctx.lib
+        rank, nq = C.c_int32(), C.c_int32()
+        check(lib.tnl_tensor_rank(self.h, C.byref(rank), C.byref(nq)), self.ctx.h)
+        out = []
+        for k in range(rank.value):
+            ns, dr = C.c_int32(), C.c_int32()
+            check(lib.tnl_tensor_index(self.h, k, C.byref(ns), C.byref(dr), None, None, 0), self.ctx.h)
+            dims = np.zeros(ns.value, dtype=np.int32)
+            qns = np.zeros(ns.value * nq.value, dtype=np.int32)
+            check(lib.tnl_tensor_index(self.h, k, C.byref(ns), C.byref(dr), dims.ctypes.data, qns.ctypes.data, ns.value),
+                  self.ctx.h)
+            qn = [tuple(int(x) for x in qns[s * nq.value:(s + 1) * nq.value]) for s in range(ns.value)]
+            known = self._inds[k] if self._inds is not None and k < len(self._inds) else None
+            if known is not None and known.qns == tuple(qn) and known.dims == tuple(int(d) for d in dims):
+                out.append(known.copy(dir=dr.value))
+            else:
+                out.append(Index(qn, dims, dir=dr.value))
+        return out
+
+    def to_host(self, drop_zero_blocks: bool = False) -> HostTensor:
+        lib = self.ctx.lib
+        nb, ne = C.c_int64(), C.c_int64()
+        check(lib.tnl_tensor_export_size(self.h, C.byref(nb), C.byref(ne)), self.ctx.h)
+        inds = self.inds
+        rank = len(inds)
+        coords = np.zeros((max(nb.value, 1), rank), dtype=np.int32)
+        offsets = np.zeros(max(nb.value, 1), dtype=np.int64)
+        data = np.zeros(max(ne.value, 1), dtype=np.float64)
+        check(lib.tnl_tensor_export(self.h, coords.ctypes.data, offsets.ctypes.data, data.ctypes.data), self.ctx.h)
+        t = HostTensor(inds)
+        for n in range(nb.value):
+            c = tuple(int(x) for x in coords[n])
+            shp = tuple(ix.dims[k] for ix, k in zip(inds, c))
+            sz = int(np.prod(shp))
+            blk = data[offsets[n]:offsets[n] + sz].reshape(shp, order="F").copy()
+            if drop_zero_blocks and not blk.any():
+                continue
+            t.blocks[c] = blk
+        return t
+
+    def copy(self) -> "DeviceTensor":
+        h = C.c_void_p()
+        check(self.ctx.lib.tnl_tensor_copy(self.h, C.byref(h)), self.ctx.h)
+        return DeviceTensor(self.ctx, h, self._inds)
+
+    def fill_random(self, seed: int):
+        check(self.ctx.lib.tnl_tensor_fill_random(self.h, C.c_uint64(seed)), self.ctx.h)
+        return self
+
+    # ---- VectorInterface
+    def norm(self) -> float:
+        out = C.c_double()
+        check(self.ctx.lib.tnl_vec_norm(self.h, C.byref(out)), self.ctx.h)
+        return out.value
+
+    def dot(self, other: "DeviceTensor") -> float:
+        out = C.c_double()
+        check(self.ctx.lib.tnl_vec_dot(self.h, other.h, C.byref(out)), self.ctx.h)
+        return out.value
+
+    def scale_(self, a: float):
+        check(self.ctx.lib.tnl_vec_scale(self.h, float(a)), self.ctx.h)
+        return self
+
+    def axpy_(self, x: "DeviceTensor", a: float):
+        check(self.ctx.lib.tnl_vec_axpy(self.h, x.h, float(a)), self.ctx.h)
+        return self

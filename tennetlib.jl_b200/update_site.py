@@ -1,0 +1,58 @@
+"""Local updates -- mirror of /root/reference/src/mps/update_site.jl:13-90,231-277 (two-site branch)."""
+from __future__ import annotations
+
+import math
+
+FLOAT64_THRESHOLD = 1e-15      # src/base/global_variables.jl:10-26
+
+
+def halfsweep_done(N: int, pos: int, nsite: int, ortho: str) -> bool:
+    if pos == 1 and ortho == "right":
+        return True
+    if pos == N and ortho == "left" and nsite == 1:
+        return True
+    if pos == N - 1 and ortho == "left" and nsite == 2:
+        return True
+    return False
+
+
+def _update_two_site(sysenv, solver, pos, ortho, time_step, normalize, maxdim, mindim, cutoff, svd_alg, noise,
+                     reverse_step, **kwargs):
+    assert 0 < pos < len(sysenv)
+    assert (sysenv.orthocenter() == pos and ortho == "left") or (sysenv.orthocenter() == pos + 1 and ortho == "right")
+    nsite = 2
+    sysenv.set_nsite(nsite)
+    phi = sysenv.make_phi(pos)                       # psi[pos] * psi[pos+1]
+    sysenv.position(pos)
+    energy, phi = solver(sysenv, phi, time_step, **kwargs)
+    if normalize:
+        phi.scale_(1.0 / phi.norm())
+    if isinstance(energy, float) and math.isnan(energy):
+        energy = sysenv.expectation(phi)
+    drho_noise = noise if abs(noise) > FLOAT64_THRESHOLD else 0.0
+    truncerr, eigs = sysenv.replacebond(pos, phi, maxdim=maxdim, mindim=mindim, cutoff=cutoff, noise=drho_noise,
+                                        ortho=ortho, normalize=normalize, which_decomp=kwargs.get("which_decomp"),
+                                        svd_alg=svd_alg)
+    if reverse_step and not halfsweep_done(len(sysenv), pos, nsite, ortho):
+        raise NotImplementedError("TDVP reverse step needs exp_solver (later row of the scope table)")
+    return energy, truncerr, eigs
+
+
+def update_position(sysenv, solver, pos: int, nsite: int, ortho: str, **kwargs):
+    time_step = kwargs.get("time_step", None)
+    normalize = kwargs.get("normalize", True)
+    maxdim = kwargs.get("maxdim", None)
+    mindim = kwargs.get("mindim", 1)
+    cutoff = kwargs.get("cutoff", FLOAT64_THRESHOLD)
+    svd_alg = kwargs.get("svd_alg", "divide_and_conquer")
+    noise = kwargs.get("noise", 0.0)
+    reverse_step = kwargs.get("reverse_step", time_step is not None)
+    if noise > 0 and reverse_step:
+        raise RuntimeError(f"`updatePosition()` :: `noise={noise}` cannot be greater than zero"
+                           f" for `reverse_step={reverse_step}` !!")
+    rest = {k: v for k, v in kwargs.items() if k not in ("time_step", "normalize", "maxdim", "mindim", "cutoff",
+                                                          "svd_alg", "noise", "reverse_step")}
+    if nsite == 2:
+        return _update_two_site(sysenv, solver, pos, ortho, time_step, normalize, maxdim, mindim, cutoff, svd_alg,
+                                noise, reverse_step, **rest)
+    raise NotImplementedError(f"`update_position()` with `nsite={nsite}` not implemented !!")
