@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- DMRG hot path at chi=4096 on B200 (BASELINE.json metric: "DMRG sweep time (s) and H_eff-apply
+FP64 TFLOP/s at chi=4096").
+
+Workload (config[1] of BASELINE.json): S=1 Heisenberg chain, N=100, U(1) QN, two-site DMRG, maxdim 4096.
+The MPS is a random QN MPS with the Gaussian link-sector profile of SURVEY.md section 8d (sigma = 1.3 in Sz),
+generated on the device, right-canonicalised with QR, centre moved to mid-chain, all environments built.
+
+A STEP is one pass of the hot path = one two-site bond update through the public API
+(`update_position(sysenv, eig_solver, bond, 2, "left")`): phi = A_j A_{j+1}, environment update, Lanczos
+eig_solver (<= 7 H_eff applies + Krylov vector ops), noise-free truncation (replacebond!).
+
+  value / metric : H_eff-apply FP64 TFLOP/s = algorithmic apply flops (reference contraction order, 2mnk per
+                   block GEMM) / device time of the eig_solver phase (applies + Krylov vector kernels)
+  ms_per_step    : one full bond update;   sweep_time_s_est = 198 * ms_per_step (upper bound: edge bonds are cheaper)
+  e2e            : same metric through the C ABI with HOST buffers: host phi -> tnl_tensor_import (H2D) ->
+                   tnl_eigsolve_lanczos -> tnl_tensor_export (D2H), copies inside the timed region
+  roofline       : grouped DGEMM kernel (dominant), achieved algorithmic TFLOP/s per launch (CUDA events on the
+                   library stream) vs the cuBLAS DGEMM 8192^3 peak measured on this pool (profiles/r01_peaks_fp64.json)
+  cpu_baseline   : oracle (NumPy restatement of the ITensors CPU path) timed on the host cores for one H_eff
+                   apply at the same bond ("port")
+`--impl reference` times that oracle apply alone on synthetic tensors of the same sector structure.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+FP64_PEAK_TFLOPS_FALLBACK = 35.46     # cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_peaks_fp64.json)
+SIGMA_SZ = 1.3
+QMAX = 6
+
+
+def fp64_peak():
+    p = os.path.join(HERE, "profiles", "r01_peaks_fp64.json")
+    try:
+        return float(json.load(open(p))["dgemm_8192_sustained_tflops"]), "measured cuBLAS DGEMM 8192^3 (profiles/r01_peaks_fp64.json)"
+    except Exception:
+        return FP64_PEAK_TFLOPS_FALLBACK, "fallback (earlier cuBLAS DGEMM measurement on this pool)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def workload_config(args):
+    return {"workload": "S=1 Heisenberg chain N=%d U(1) QN two-site DMRG chi=%d (BASELINE.json configs[1])" % (args.nsites, args.chi),
+            "nsites": args.nsites, "chi": args.chi, "site": "S=1", "mpo_bond_dim": 5,
+            "link_sector_profile": "gaussian sigma=%.1f (Sz units), |Sz|<=%d" % (SIGMA_SZ, QMAX),
+            "step": "one two-site bond update at a mid-chain bond (phi, env update, Lanczos eig_solver "
+                    "krylovdim=5 maxiter=2 tol=1e-14, truncation maxdim=chi cutoff=%g via %s)" % (args.cutoff, args.decomp),
+            "l2_policy": "inputs larger than L2 (per-apply working set > 3 GB at chi=4096)",
+            "cutoff": args.cutoff, "decomp": args.decomp}
+
+
+def oracle_apply_inputs(sector_qns, sector_dims, rng):
+    """Synthetic mid-chain bond for the CPU arm: phi, L, R with every symmetry-allowed block N(0,1)
+     and the exact S=1 Heisenberg MPO tensors."""
+    from oracle import blocksparse as ob, models as om
+    sites = om.siteinds("S=1", 4)
+    H = om.heisenberg_mpo(sites)
+    W1, W2 = H[1], H[2]
+    link = ob.Index(sector_qns, sector_dims, dir=+1, tags="Link")
+    l, r = link.sim(), link.sim()
+    s1, s2 = W1.inds[2], W2.inds[2]
+    phi = ob.BSTensor.random([l.copy(dir=+1), s1.copy(dir=+1), s2.copy(dir=+1), r.copy(dir=-1)], rng)
+    phi = phi.scale(1.0 / phi.norm())
+    wl, wr = W1.inds[0], W2.inds[3]
+    L = ob.BSTensor.random([l.prime().copy(dir=+1), wl.copy(dir=-1), l.copy(dir=-1)], rng)
+    R = ob.BSTensor.random([r.prime().copy(dir=-1), wr.copy(dir=+1), r.copy(dir=+1)], rng)
+    return phi, L, W1, W2, R
+
+
+def oracle_apply(phi, L, W1, W2, R):
+    from oracle.blocksparse import contract
+    return contract(contract(contract(contract(phi, L), W1), W2), R).noprime()
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def time_oracle_apply(sector_qns, sector_dims, reps: int, seed: int = 20262):
+    from oracle import blocksparse as ob
+    rng = np.random.default_rng(seed)
+    t0 = time.time()
+    phi, L, W1, W2, R = oracle_apply_inputs(sector_qns, sector_dims, rng)
+    gen_s = time.time() - t0
+    times, flops = [], 0
+    for _ in range(reps):
+        ob.reset_flops()
+        t0 = time.time()
+        oracle_apply(phi, L, W1, W2, R)
+        times.append(time.time() - t0)
+        flops = ob.get_flops()
+    return times, flops, gen_s
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference CPU path (Julia is not installed)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tennetlib.jl_b200 import models as pm          # host-only helper (sector profile); no CUDA involved
+    qns, dims = pm.gaussian_link_sectors(args.chi, SIGMA_SZ, QMAX, 0, 2)
+    reps = args.warmup + args.steps
+    times, flops, gen_s = time_oracle_apply(qns, dims, reps)
+    timed = times[args.warmup:]
+    tf = flops / np.mean(timed) / 1e12
+    cores = blas_threads()
+    line = {"impl": "reference", "metric": "heff_apply_fp64_tflops", "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(timed)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                             "sample": "one H_eff apply per step (reference contraction order, NumPy/BLAS per block pair) "
+                                       "on a synthetic mid-chain bond with the bench sector profile"},
+            "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "apply_gflop": flops / 1e9, "note": "oracle port of the ITensors CPU path, not Julia (reference cannot run here)"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import tennetlib.jl_b200 as T
+    from tennetlib.jl_b200 import models as pm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ctx = T.Context(local)
+    N, chi = args.nsites, args.chi
+    sites = pm.siteinds("S=1", N)
+    H = pm.heisenberg_mpo(sites)
+    qns, dims = pm.gaussian_link_sectors(chi, SIGMA_SZ, QMAX, 0, 2)
+    links = pm.random_mps_links(sites, qns, dims, 0)
+    t_setup = time.time()
+    psi = []
+    for j in range(N):
+        A = T.DeviceTensor.zeros(ctx, [links[j].copy(dir=+1), sites[j].copy(dir=+1), links[j + 1].copy(dir=-1)], nrow=2)
+        A.fill_random(20262 + 1000 * rank + j)
+        psi.append(A)
+    sysenv = T.StateEnvs(ctx, psi, H, llim=0, rlim=N + 1, copy=False)
+    del psi
+    b0 = max(1, N // 2 - (args.warmup + args.steps) // 2)
+    sysenv.orthogonalize(1)
+    sysenv.orthogonalize(b0)
+    sysenv.set_nsite(2)
+    sysenv.position(b0)
+    ctx.sync()
+    t_setup = time.time() - t_setup
+
+    kw = dict(maxdim=chi, cutoff=args.cutoff, noise=0.0, normalize=True, svd_alg=args.svd_alg,
+              which_decomp=None if args.decomp == "auto" else args.decomp)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    energies = []
+    bond = b0
+    for _ in range(args.warmup):
+        e, err, eigs = T.update_position(sysenv, T.eig_solver, bond, 2, "left", **kw)
+        bond += 1
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.reset_counters()
+    sysenv.profile = True
+    sysenv.phase_ms = {}
+    phases0 = None
+    ctx.profile_gemm(True)
+    ctx.profile_read()
+    apply_flops_total, numops_total = 0.0, 0
+    ctx.timer_start(1)              # CUDA events on the library's stream (slot 0 is used by the phase timers)
+    for _ in range(args.steps):
+        e, err, eigs = T.update_position(sysenv, T.eig_solver, bond, 2, "left", **kw)
+        energies.append(e)
+        numops_total += sysenv.last_solver_info["numops"]
+        apply_flops_total += sysenv.last_solver_info["apply_flops"] * sysenv.last_solver_info["numops"]
+        bond += 1
+    total_s = ctx.timer_stop(1) * 1e-3
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    cnt = ctx.counters()
+    prof = ctx.profile_read()
+    ctx.profile_gemm(False)
+    sysenv.profile = False
+    phases = dict(sysenv.phase_ms)
+
+    sysenv.set_nsite(2)
+    bond_e2e = bond
+    phi = sysenv.make_phi(bond_e2e)
+    sysenv.position(bond_e2e)
+    _ = sysenv.product(phi)
+    flops_per_apply = sysenv.apply_flops()
+    solver_s = phases.get("solver", 0.0) * 1e-3
+    tf_apply = apply_flops_total / solver_s / 1e12 if solver_s > 0 else 0.0
+
+    # ---- e2e through the C ABI with host buffers (eig_solver call: host phi in, host phi out)
+    phi_host = phi.to_host()
+    nbytes = sum(b.nbytes for b in phi_host.blocks.values())
+    e2e_ops = 0
+    for _ in range(1):
+        d = T.DeviceTensor.from_host(ctx, phi_host, nrow=1)
+        T.eig_solver(sysenv, d)
+        d.to_host()
+    barrier()
+    t1 = time.time()
+    for _ in range(max(1, min(args.steps, 3))):
+        d = T.DeviceTensor.from_host(ctx, phi_host, nrow=1)
+        T.eig_solver(sysenv, d)
+        e2e_ops += sysenv.last_solver_info["numops"]
+        d.to_host()
+    ctx.sync()
+    e2e_s = time.time() - t1
+    tf_e2e = flops_per_apply * e2e_ops / e2e_s / 1e12
+
+    # ---- aggregate over ranks (replicas: no data-path collective; time = max over ranks)
+    ms_per_step = 1e3 * total_s / args.steps
+    if world > 1:
+        t = torch.tensor([ms_per_step, solver_s, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step, solver_s_max, e2e_s_max = t.tolist()
+        s = torch.tensor([apply_flops_total, flops_per_apply * e2e_ops], device="cuda", dtype=torch.float64)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        tf_apply = s[0].item() / solver_s_max / 1e12
+        tf_e2e = s[1].item() / e2e_s_max / 1e12
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = fp64_peak()
+    gemm_tf = prof["flops"] / (prof["total_ms"] * 1e-3) / 1e12 if prof["total_ms"] > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "tnl::gemm_kernel<128,128,16,64,32> (FP64 DMMA grouped GEMM)",
+                "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": None,
+                "peak_source": peak_src, "launches": prof["launches"],
+                "avg_launch_ms": prof["total_ms"] / max(1, prof["launches"]),
+                "algorithmic_gflop_per_launch": prof["flops"] / max(1, prof["launches"]) / 1e9,
+                "best_launch_tflops": prof["max_tflops"]}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        # bounded sample: ONE oracle apply on a synthetic bond with the same sector profile
+        li = sysenv.site_tensor(bond_e2e).inds[0]
+        times, fl, gen_s = time_oracle_apply(list(li.qns), list(li.dims), 1)
+        cpu = {"value": fl / times[0] / 1e12, "unit": "TFLOP/s", "cores": blas_threads(), "kind": "port",
+               "sample": "one H_eff apply (%.1f GFLOP algorithmic) by the NumPy oracle on a synthetic bond with the "
+                         "left-link sectors of the timed bond; %.1f s" % (fl / 1e9, times[0])}
+
+    line = {"metric": "heff_apply_fp64_tflops", "value": tf_apply, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args), parallelism="replicas x%d" % world if world > 1 else "single GPU",
+                           first_timed_bond=b0 + args.warmup),
+            "sweep_time_s_est": 198 * ms_per_step * 1e-3,
+            "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+            "apply_gflop": apply_flops_total / max(1, numops_total) / 1e9, "applies_per_step": numops_total / args.steps,
+            "energies": energies[-2:], "setup_s": t_setup,
+            "krylov_vec": {"algorithmic_gb_per_step": cnt["vec_bytes"] / args.steps / 1e9},
+            "transform": {"algorithmic_gb_per_step": cnt["transform_bytes"] / args.steps / 1e9},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": tf_e2e, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                    "call": "tnl_tensor_import -> tnl_eigsolve_lanczos -> tnl_tensor_export"},
+            "gpu_launches": int(cnt["launches"]), "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chi", type=int, default=4096)
+    ap.add_argument("--nsites", type=int, default=100)
+    ap.add_argument("--cutoff", type=float, default=1e-15)
+    ap.add_argument("--decomp", default="auto", choices=["auto", "svd", "eigen"])
+    ap.add_argument("--svd-alg", dest="svd_alg", default="polar", choices=["divide_and_conquer", "qr_iteration", "polar"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

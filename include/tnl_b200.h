@@ -41,8 +41,12 @@ int tnl_get_counters(tnl_ctx_t ctx, double* out8);
 int tnl_reset_counters(tnl_ctx_t ctx);
 int tnl_ctx_sync(tnl_ctx_t ctx);
 /* CUDA-event timing on the library's own stream (bench.py times kernels here, not on torch's stream). */
-int tnl_timer_start(tnl_ctx_t ctx);
-int tnl_timer_stop(tnl_ctx_t ctx, double* milliseconds);
+int tnl_timer_start(tnl_ctx_t ctx, int32_t slot); /* slot 0..3 */
+int tnl_timer_stop(tnl_ctx_t ctx, int32_t slot, double* milliseconds);
+/* per-launch CUDA-event profile of the grouped DGEMM launches (those with 128x128 tiles): enable, run, read
+ * (read synchronises, sums the launch durations and algorithmic flops, and clears the records) */
+int tnl_profile_gemm(tnl_ctx_t ctx, int32_t enable);
+int tnl_profile_read(tnl_ctx_t ctx, double* total_ms, int64_t* launches, double* flops, double* max_tflops);
 
 /* ---- tensors: ITensor <-> device (replaces nothing in the reference; it is the marshalling the shim needs) */
 int tnl_tensor_import(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t* inds, int64_t nblocks,
@@ -76,7 +80,9 @@ int tnl_env_set_state(tnl_env_t env, int32_t site, tnl_tensor_t a);
 int tnl_env_get_state(tnl_env_t env, int32_t site, tnl_tensor_t* out); /* getpsi, state_envs.jl:36 */
 int tnl_env_set_nsite(tnl_env_t env, int32_t nsite);                   /* set_nsite!, state_envs.jl:352-355 */
 int tnl_env_position(tnl_env_t env, int32_t pos);                      /* position!, state_envs.jl:364-367 */
-int tnl_env_orthogonalize(tnl_env_t env); /* orthogonalize!(psi, 1) of a fresh MPS, sweep.jl:100-102 */
+/* orthogonalize!: QR gauge moves of the orthogonality centre from site `from` to site `to`;
+ * (N, 1) right-canonicalises an arbitrary MPS (sweep.jl:100-102) */
+int tnl_env_move_center(tnl_env_t env, int32_t from, int32_t to);
 int tnl_env_make_phi(tnl_env_t env, int32_t pos, tnl_tensor_t* phi); /* psi[pos]*psi[pos+1], update_site.jl:46 */
 int tnl_env_apply_flops(tnl_env_t env, double* flops); /* algorithmic flops of one apply at this position */
 
@@ -88,7 +94,8 @@ int tnl_eigsolve_lanczos(tnl_env_t env, tnl_tensor_t phi, double tol, int32_t kr
                          double* normres);
 /* real(scalar(dag(phi) * PH(phi))) : src/mps/update_site.jl:51-57 */
 int tnl_expectation(tnl_env_t env, tnl_tensor_t phi, double* e);
-/* noiseterm + replacebond! : src/mps/update_site.jl:59-76.  which_decomp: 0 = reference rule, 1 = svd, 2 = eigen.
+/* noiseterm + replacebond! : src/mps/update_site.jl:59-76.  which_decomp low 4 bits: 0 = reference rule,
+ * 1 = svd, 2 = eigen; bits 4.. select the SVD driver (0 = gesvd `qr_iteration`, 1 = gesvdp polar).
  * eigs receives spec.eigs (kept spectrum, descending), at most `cap` values; *neigs = number kept. */
 int tnl_replacebond(tnl_env_t env, int32_t pos, tnl_tensor_t phi, int32_t ortho_left, int64_t maxdim, int64_t mindim,
                     double cutoff, double noise, int32_t normalize, int32_t which_decomp, double* truncerr,

@@ -27,8 +27,10 @@ _SIGS = {
     "tnl_get_counters": [_P, C.POINTER(C.c_double)],
     "tnl_reset_counters": [_P],
     "tnl_ctx_sync": [_P],
-    "tnl_timer_start": [_P],
-    "tnl_timer_stop": [_P, C.POINTER(C.c_double)],
+    "tnl_timer_start": [_P, C.c_int32],
+    "tnl_timer_stop": [_P, C.c_int32, C.POINTER(C.c_double)],
+    "tnl_profile_gemm": [_P, C.c_int32],
+    "tnl_profile_read": [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "tnl_tensor_import": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int64, _P, _P, _P, C.c_int32, C.POINTER(_P)],
     "tnl_tensor_create": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int32, C.POINTER(_P)],
     "tnl_tensor_free": [_P],
@@ -49,7 +51,7 @@ _SIGS = {
     "tnl_env_get_state": [_P, C.c_int32, C.POINTER(_P)],
     "tnl_env_set_nsite": [_P, C.c_int32],
     "tnl_env_position": [_P, C.c_int32],
-    "tnl_env_orthogonalize": [_P],
+    "tnl_env_move_center": [_P, C.c_int32, C.c_int32],
     "tnl_env_make_phi": [_P, C.c_int32, C.POINTER(_P)],
     "tnl_env_apply_flops": [_P, C.POINTER(C.c_double)],
     "tnl_heff_apply": [_P, _P, C.POINTER(_P)],

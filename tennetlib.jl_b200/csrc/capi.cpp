@@ -9,7 +9,7 @@
 
 using namespace tnl;
 
-struct tnl_ctx_s { Ctx ctx; cudaEvent_t e0 = nullptr, e1 = nullptr; explicit tnl_ctx_s(int dev) : ctx(dev) {} };
+struct tnl_ctx_s { Ctx ctx; cudaEvent_t ev[8] = {}; explicit tnl_ctx_s(int dev) : ctx(dev) {} };
 struct tnl_tensor_s { TensorP t; };
 struct tnl_env_s { Env env; tnl_env_s(Ctx* c, int n) : env(c, n) {} };
 
@@ -79,7 +79,7 @@ int tnl_ctx_create(int device, tnl_ctx_t* out) {
 }
 int tnl_ctx_destroy(tnl_ctx_t c) {
   return guard(nullptr, [&] {
-    if (c->e0) { cudaEventDestroy(c->e0); cudaEventDestroy(c->e1); }
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
   });
 }
@@ -93,20 +93,39 @@ int tnl_get_counters(tnl_ctx_t c, double* o) {
 }
 int tnl_reset_counters(tnl_ctx_t c) { return guard(&c->ctx, [&] { c->ctx.cnt = Counters(); }); }
 int tnl_ctx_sync(tnl_ctx_t c) { return guard(&c->ctx, [&] { c->ctx.sync(); }); }
-int tnl_timer_start(tnl_ctx_t c) {
+int tnl_timer_start(tnl_ctx_t c, int32_t slot) {
   return guard(&c->ctx, [&] {
-    if (!c->e0) { CUDA_OK(cudaEventCreate(&c->e0)); CUDA_OK(cudaEventCreate(&c->e1)); }
-    CUDA_OK(cudaEventRecord(c->e0, c->ctx.stream));
+    TNL_CHECK(slot >= 0 && slot < 4, "timer slot out of range");
+    if (!c->ev[2 * slot]) { CUDA_OK(cudaEventCreate(&c->ev[2 * slot])); CUDA_OK(cudaEventCreate(&c->ev[2 * slot + 1])); }
+    CUDA_OK(cudaEventRecord(c->ev[2 * slot], c->ctx.stream));
   });
 }
-int tnl_timer_stop(tnl_ctx_t c, double* ms) {
+int tnl_timer_stop(tnl_ctx_t c, int32_t slot, double* ms) {
   return guard(&c->ctx, [&] {
-    TNL_CHECK(c->e0, "timer not started");
-    CUDA_OK(cudaEventRecord(c->e1, c->ctx.stream));
-    CUDA_OK(cudaEventSynchronize(c->e1));
+    TNL_CHECK(slot >= 0 && slot < 4 && c->ev[2 * slot], "timer not started");
+    CUDA_OK(cudaEventRecord(c->ev[2 * slot + 1], c->ctx.stream));
+    CUDA_OK(cudaEventSynchronize(c->ev[2 * slot + 1]));
     float f = 0;
-    CUDA_OK(cudaEventElapsedTime(&f, c->e0, c->e1));
+    CUDA_OK(cudaEventElapsedTime(&f, c->ev[2 * slot], c->ev[2 * slot + 1]));
     *ms = f;
+  });
+}
+
+int tnl_profile_gemm(tnl_ctx_t c, int32_t enable) {
+  return guard(&c->ctx, [&] { c->ctx.prof_gemm = enable != 0; });
+}
+int tnl_profile_read(tnl_ctx_t c, double* total_ms, int64_t* launches, double* flops, double* max_tflops) {
+  return guard(&c->ctx, [&] {
+    c->ctx.sync();
+    *total_ms = 0; *launches = 0; *flops = 0; *max_tflops = 0;
+    for (auto& r : c->ctx.prof_recs) {
+      float ms = 0;
+      CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+      *total_ms += ms; *launches += 1; *flops += r.flops;
+      if (ms > 0 && r.flops > 1e9) *max_tflops = std::max(*max_tflops, r.flops / (ms * 1e-3) / 1e12);
+      cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    c->ctx.prof_recs.clear();
   });
 }
 
@@ -238,8 +257,8 @@ int tnl_env_set_nsite(tnl_env_t e, int32_t nsite) {
 int tnl_env_position(tnl_env_t e, int32_t pos) {
   return guard(e->env.ctx, [&] { e->env.position(pos); });
 }
-int tnl_env_orthogonalize(tnl_env_t e) {
-  return guard(e->env.ctx, [&] { e->env.orthogonalize_all_right(); });
+int tnl_env_move_center(tnl_env_t e, int32_t from, int32_t to) {
+  return guard(e->env.ctx, [&] { e->env.move_center(from, to); });
 }
 int tnl_env_make_phi(tnl_env_t e, int32_t pos, tnl_tensor_t* phi) {
   return guard(e->env.ctx, [&] { *phi = new tnl_tensor_s{e->env.make_phi(pos)}; });
@@ -280,7 +299,8 @@ int tnl_replacebond(tnl_env_t e, int32_t pos, tnl_tensor_t phi, int32_t ortho_le
     prm.mindim = mindim;
     prm.cutoff = cutoff;
     prm.noise = noise;
-    prm.which = which_decomp;
+    prm.which = which_decomp & 15;
+    prm.svd_alg = which_decomp >> 4;
     TensorP vq = phi->t->nrow == 1 ? phi->t : relayout(e->env.ctx, *phi->t, 1);
     FactorizeResult f = e->env.replacebond(pos, *vq, prm, normalize != 0);
     *truncerr = f.truncerr;

@@ -200,6 +200,10 @@ class Ctx {
   unsigned int* d_sync = nullptr;   // "last block" counters
   double* d_partials = nullptr;
   int num_sms = 148;
+  // optional per-launch CUDA-event profile of the grouped GEMM kernel (bench.py roofline)
+  struct ProfRec { cudaEvent_t a, b; double flops; int tiles; };
+  bool prof_gemm = false;
+  std::vector<ProfRec> prof_recs;
   // NCCL sharding (multi-GPU apply); rank 0 / world 1 when unused
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;

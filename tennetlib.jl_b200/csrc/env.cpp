@@ -609,25 +609,41 @@ FactorizeResult Env::replacebond(int pos, const Tensor& phi, FactorizeParams prm
   return f;
 }
 
-// ITensorMPS `orthogonalize!(psi, 1)` for a fresh MPS: right-canonicalise sites N..2 without truncation
-void Env::orthogonalize_all_right() {
-  for (int j = N - 1; j >= 1; j--) {
-    TensorP Aq = as_nrow(ctx, A[j], 1);            // [l | s r]
-    FactorizeParams prm;
+// ITensorMPS `orthogonalize!`: QR gauge moves of the centre from site `from` to site `to` (no truncation).
+// move_center(N, 1) right-canonicalises an arbitrary MPS (sweep.jl:100-102).
+void Env::move_center(int from, int to) {
+  TNL_CHECK(from >= 1 && from <= N && to >= 1 && to <= N, "site out of range");
+  FactorizeParams prm;
+  prm.which = 3;
+  for (int j = from; j > to; j--) {                // right-orthonormalise site j, push the rest into j-1
+    TensorP Aq = as_nrow(ctx, A[j - 1], 1);        // [l | s r]
     prm.ortho_left = 0;
-    prm.which = 1;
-    prm.cutoff = 0.0;
-    FactorizeResult f = factorize(ctx, *Aq, prm);  // L = U*S (l, m) ; R = V (m, s, r)
-    A[j] = f.R;
-    TensorP Ap = as_nrow(ctx, A[j - 1], 2);        // [(l0 s0) | l]
+    FactorizeResult f = factorize(ctx, *Aq, prm);  // L (l, m) ; R = Q (m, s, r)
+    A[j - 1] = f.R;
+    TensorP Ap = as_nrow(ctx, A[j - 2], 2);        // [(l0 s0) | l]
     auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{Ap->inds[0], Ap->inds[1], f.L->inds[1]}, 2);
-    TensorP C = as_nrow(ctx, f.L, 1);
-    auto g = plan_gemm(*Ap, false, *C, false, *An);
-    run_gemm(ctx, *g, Ap->d, C->d, An->d);
+    TensorP Cm = as_nrow(ctx, f.L, 1);
+    auto g = plan_gemm(*Ap, false, *Cm, false, *An);
+    run_gemm(ctx, *g, Ap->d, Cm->d, An->d);
     ctx->sync();
-    A[j - 1] = An;
+    A[j - 2] = An;
   }
-  lpos = 0; rpos = N + 1; ap.reset();
+  for (int j = from; j < to; j++) {                // left-orthonormalise site j, push the rest into j+1
+    TensorP As = as_nrow(ctx, A[j - 1], 2);        // [l s | r]
+    prm.ortho_left = 1;
+    FactorizeResult f = factorize(ctx, *As, prm);  // L = Q (l, s, m) ; R (m, r)
+    A[j - 1] = f.L;
+    TensorP An1 = as_nrow(ctx, A[j], 1);           // [r | s2 r2]
+    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{f.R->inds[0], An1->inds[1], An1->inds[2]}, 1);
+    auto g = plan_gemm(*f.R, false, *An1, false, *An);
+    run_gemm(ctx, *g, f.R->d, An1->d, An->d);
+    ctx->sync();
+    A[j] = An;
+  }
+  int lo = std::min(from, to), hi = std::max(from, to);
+  lpos = std::min(lpos, lo - 1);
+  rpos = std::max(rpos, hi + 1);
+  ap.reset();
 }
 
 }  // namespace tnl

@@ -25,7 +25,8 @@ struct FactorizeParams {
   int64_t maxdim = INT64_MAX;
   int64_t mindim = 1;
   double cutoff = 0.0;
-  int which = 0;                // 0 = automatic (reference rule), 1 = svd, 2 = eigen
+  int which = 0;                // 0 = automatic (reference rule), 1 = svd, 2 = eigen, 3 = qr (no truncation)
+  int svd_alg = 0;              // svd path: 0 = cusolverDnDgesvd (QR iteration), 1 = cusolverDnXgesvdp (polar)
   double noise = 0.0;           // scale of the density-matrix perturbation
   const Tensor* noiseX = nullptr;   // see factorize.cu
   int new_dir_on_L = -1;        // arrow of the new index on the left factor
@@ -70,7 +71,7 @@ class Env {
   LanczosResult eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter, bool eager);
   double expectation(const Tensor& phi);
   FactorizeResult replacebond(int pos, const Tensor& phi, FactorizeParams prm, bool normalize);
-  void orthogonalize_all_right();                       // gauge the whole MPS right-canonical (centre at site 1)
+  void move_center(int from, int to);                   // QR gauge moves, ITensorMPS orthogonalize!
   double apply_flops() const;                           // algorithmic flops of one H_eff apply at the current position
 
  private:

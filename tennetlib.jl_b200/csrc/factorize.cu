@@ -116,6 +116,78 @@ struct FG {                     // one charge group of the factorisation
   std::vector<int> keep;                          // kept columns, descending weight
 };
 
+// ---------------------------------------------------------------------------------------------
+// QR / LQ gauge move without truncation (ITensors `factorize(...; which_decomp = "qr")`, what
+// `orthogonalize!` needs): ortho left  M = Q R  -> L = Q [R x k], R = R [k x C];
+//                          ortho right M = L Q  -> via QR of M^T.                k = min(R, C).
+__global__ void triu_kernel(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds,
+                            int64_t k, int64_t n, bool transpose_out) {
+  // dst = triu(src[0:k, 0:n])  (or its transpose [n x k])
+  int64_t tot = k * n;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = e % k, j = e / k;
+    double v = (i <= j) ? src[j * lds + i] : 0.0;
+    if (transpose_out) dst[i * ldd + j] = v; else dst[j * ldd + i] = v;
+  }
+}
+
+static FactorizeResult factorize_qr(Ctx* ctx, const Tensor& T, bool left, int new_dir_on_L) {
+  cusolverDnHandle_t H = solver(ctx);
+  const int split = T.nrow;
+  Index m;
+  m.nq = T.inds[0].nq;
+  m.dir = new_dir_on_L;
+  for (const Group& g : T.groups) {
+    int64_t k = std::min(g.R, g.C);
+    if (k == 0) continue;
+    m.dims.push_back((int)k);
+    m.qns.push_back(g.q);
+  }
+  std::vector<Index> li(T.inds.begin(), T.inds.begin() + split), ri;
+  li.push_back(m);
+  ri.push_back(m.dag());
+  ri.insert(ri.end(), T.inds.begin() + split, T.inds.end());
+  FactorizeResult res;
+  res.path = "qr";
+  res.L = std::make_shared<Tensor>(ctx, li, split);
+  res.R = std::make_shared<Tensor>(ctx, ri, 1);
+  std::vector<void*> temps;
+  for (const Group& g : T.groups) {
+    const int64_t R = g.R, C = g.C, k = std::min(R, C);
+    if (k == 0) continue;
+    const Group& GL = res.L->groups[res.L->find_group(g.q)];
+    const Group& GR = res.R->groups[res.R->find_group(g.q)];
+    const int64_t mm = left ? R : C, nn = left ? C : R;          // QR of the [mm x nn] matrix
+    double* Aw = (double*)ctx->alloc(mm * nn * sizeof(double));
+    temps.push_back(Aw);
+    if (left) copy2d(ctx, Aw, mm, T.d + g.base, g.ld, R, C);
+    else transpose(ctx, Aw, mm, T.d + g.base, g.ld, R, C);       // M^T
+    double* tau = (double*)ctx->alloc(k * sizeof(double));
+    temps.push_back(tau);
+    int lw1 = 0, lw2 = 0;
+    CUSOLVER_OK(cusolverDnDgeqrf_bufferSize(H, (int)mm, (int)nn, Aw, (int)mm, &lw1));
+    CUSOLVER_OK(cusolverDnDorgqr_bufferSize(H, (int)mm, (int)k, (int)k, Aw, (int)mm, tau, &lw2));
+    double* work = solver_ws(ctx, (size_t)std::max(lw1, lw2));
+    CUSOLVER_OK(cusolverDnDgeqrf(H, (int)mm, (int)nn, Aw, (int)mm, tau, work, lw1, ctx->d_info));
+    // triangular factor [k x nn]
+    int grid = (int)std::min<int64_t>((k * nn + 255) / 256, 1184);
+    if (left) triu_kernel<<<grid, 256, 0, ctx->stream>>>(res.R->d + GR.base, GR.ld, Aw, mm, k, nn, false);   // R [k x C]
+    else triu_kernel<<<grid, 256, 0, ctx->stream>>>(res.L->d + GL.base, GL.ld, Aw, mm, k, nn, true);          // (R')^T [R x k]
+    CUDA_OK(cudaGetLastError());
+    ctx->cnt.launches++;
+    CUSOLVER_OK(cusolverDnDorgqr(H, (int)mm, (int)k, (int)k, Aw, (int)mm, tau, work, lw2, ctx->d_info));
+    if (left) copy2d(ctx, res.L->d + GL.base, GL.ld, Aw, mm, R, k);                                           // Q [R x k]
+    else transpose(ctx, res.R->d + GR.base, GR.ld, Aw, mm, C, k);                                              // Q^T [k x C]
+    int info = 0;
+    CUDA_OK(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    TNL_CHECK(info == 0, "cuSOLVER QR failed");
+  }
+  ctx->sync();
+  for (void* p : temps) ctx->free(p);
+  return res;
+}
+
 FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm) {
   const int split = T.nrow, rank = T.rank();
   TNL_CHECK(split >= 1 && split < rank, "factorize needs a proper bipartition");
@@ -124,6 +196,9 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
   if (which == 0) which = noisy ? 2 : (prm.cutoff <= 1e-12 ? 1 : 2);
   const bool left = prm.ortho_left != 0;
   cusolverDnHandle_t H = solver(ctx);
+  int svd_alg = prm.svd_alg;
+  if (const char* e = getenv("TNL_SVD_ALG")) svd_alg = atoi(e);
+  if (which == 3) return factorize_qr(ctx, T, left, prm.new_dir_on_L);
 
   // ---- collect charge groups (union of T's and, on the kept side, the noise operand's)
   std::vector<FG> fg;
@@ -173,17 +248,35 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
       double* S = talloc(n);
       double* Uw = talloc(m * n);
       double* Vw = talloc(n * n);
-      int lwork = 0;
-      CUSOLVER_OK(cusolverDnDgesvd_bufferSize(H, (int)m, (int)n, &lwork));
-      double* work = solver_ws(ctx, (size_t)lwork + 2 * n);
-      CUSOLVER_OK(cusolverDnDgesvd(H, 'S', 'S', (int)m, (int)n, Awork, (int)m, S, Uw, (int)m, Vw, (int)n, work, lwork,
-                                   work + lwork, ctx->d_info));
+      const int alg = (n >= 64) ? svd_alg : 0;
+      if (alg == 1) {
+        // polar-decomposition SVD (QDWH + syevd inside cuSOLVER): same absolute accuracy as gesvd, GEMM-rich
+        static cusolverDnParams_t params = nullptr;
+        if (!params) CUSOLVER_OK(cusolverDnCreateParams(&params));
+        size_t wd = 0, wh = 0;
+        double* Vfull = talloc(n * n);
+        CUSOLVER_OK(cusolverDnXgesvdp_bufferSize(H, params, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, CUDA_R_64F, Awork, m,
+                                                 CUDA_R_64F, S, CUDA_R_64F, Uw, m, CUDA_R_64F, Vfull, n, CUDA_R_64F, &wd, &wh));
+        double* work = solver_ws(ctx, wd / sizeof(double) + 2);
+        std::vector<char> hbuf(wh + 8);
+        double herr = 0;
+        CUSOLVER_OK(cusolverDnXgesvdp(H, params, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, CUDA_R_64F, Awork, m, CUDA_R_64F, S,
+                                      CUDA_R_64F, Uw, m, CUDA_R_64F, Vfull, n, CUDA_R_64F, work, wd, hbuf.data(), wh,
+                                      ctx->d_info, &herr));
+        transpose(ctx, Vw, n, Vfull, n, n, n);    // Vw = V^T
+      } else {
+        int lwork = 0;
+        CUSOLVER_OK(cusolverDnDgesvd_bufferSize(H, (int)m, (int)n, &lwork));
+        double* work = solver_ws(ctx, (size_t)lwork + 2 * n);
+        CUSOLVER_OK(cusolverDnDgesvd(H, 'S', 'S', (int)m, (int)n, Awork, (int)m, S, Uw, (int)m, Vw, (int)n, work, lwork,
+                                     work + lwork, ctx->d_info));
+      }
       f.vals.resize(n);
       CUDA_OK(cudaMemcpyAsync(f.vals.data(), S, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
       int info = 0;
       CUDA_OK(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       ctx->sync();
-      TNL_CHECK(info == 0, "cusolverDnDgesvd did not converge");
+      TNL_CHECK(info == 0, "cuSOLVER SVD did not converge");
       if (!tr) {
         f.U = Uw; f.ldu = m; f.Vt = Vw; f.ldv = n;
       } else {                                      // M^T = Uw S Vw  =>  M = Vw^T S Uw^T
@@ -296,10 +389,12 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
     const int nk = (int)f.keep.size();
     int gl = res.L->find_group(f.q);
     int gr = res.R->find_group(f.q);
-    TNL_CHECK(gl >= 0, "new link sector missing on the left factor");
-    const Group& GL = res.L->groups[gl];
-    TNL_CHECK(GL.R == f.R && GL.C == nk, "left factor group shape");
-    double* Ld = res.L->d + GL.base;
+    // a sector opened by the noise term alone exists only on the factor that carries the eigenvectors
+    TNL_CHECK(gl >= 0 || (which == 2 && !left), "new link sector missing on the left factor");
+    static const Group kNoGroup{};
+    const Group& GL = gl >= 0 ? res.L->groups[gl] : kNoGroup;
+    if (gl >= 0) TNL_CHECK(GL.R == f.R && GL.C == nk, "left factor group shape");
+    double* Ld = gl >= 0 ? res.L->d + GL.base : nullptr;
     if (which == 1) {
       TNL_CHECK(gr >= 0, "new link sector missing on the right factor");
       const Group& GR = res.R->groups[gr];
@@ -337,7 +432,7 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
       double* Vk = talloc(ldk * nk);
       gather_cols(ctx, Vk, ldk, f.E, f.C, f.C, f.keep, nullptr);
       transpose(ctx, res.R->d + GR.base, GR.ld, Vk, ldk, f.C, nk);
-      if (f.M) {                                  // L = M V
+      if (f.M && gl >= 0) {                       // L = M V
         GemmProblem p{};
         p.M = (int)f.R; p.N = nk; p.K = (int)f.C;
         p.a = off(f.M); p.lda = (int)f.ldm; p.b = off(Vk); p.ldb = (int)ldk;

@@ -180,8 +180,21 @@ static void launch_gemm_cfg(Ctx* ctx, bool ta, bool tb, const GemmProblem* probs
 
 void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C) {
   for (auto& z : p.zero_fill) CUDA_OK(cudaMemsetAsync(C + z.first, 0, z.second * sizeof(double), ctx->stream));
+  Ctx::ProfRec rec{};
+  const bool prof = ctx->prof_gemm && !p.tiles_big.empty();
+  if (prof) {
+    CUDA_OK(cudaEventCreate(&rec.a));
+    CUDA_OK(cudaEventCreate(&rec.b));
+    CUDA_OK(cudaEventRecord(rec.a, ctx->stream));
+  }
   launch_gemm_cfg<128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, (int)p.tiles_big.size(), A, B, C);
   launch_gemm_cfg<64, 64, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_small, (int)p.tiles_small.size(), A, B, C);
+  if (prof) {
+    CUDA_OK(cudaEventRecord(rec.b, ctx->stream));
+    rec.flops = p.flops;
+    rec.tiles = (int)(p.tiles_big.size() + p.tiles_small.size());
+    ctx->prof_recs.push_back(rec);
+  }
   ctx->cnt.gemm_flops += p.flops;
 }
 

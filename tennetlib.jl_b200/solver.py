@@ -21,7 +21,8 @@ def eig_solver(env, phi0, time_step=None, **kwargs):
     check(env.ctx.lib.tnl_eigsolve_lanczos(env.h, phi0.h, float(tol), int(krylovdim), int(maxiter), 1 if eager else 0,
                                            C.byref(ev), C.byref(conv), C.byref(nops), C.byref(nit), C.byref(nres)),
           env.ctx.h)
-    env.last_solver_info = dict(converged=conv.value, numops=nops.value, numiter=nit.value, normres=nres.value)
+    env.last_solver_info = dict(converged=conv.value, numops=nops.value, numiter=nit.value, normres=nres.value,
+                                apply_flops=env.apply_flops())
     if kwargs.get("solver_check_convergence", False) and conv.value < 1:
         raise RuntimeError("`eig_solver()` not converged !!")
     return ev.value, phi0

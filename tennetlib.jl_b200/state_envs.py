@@ -16,8 +16,12 @@ class StateEnvs:
     DeviceTensors); `H`: sequence of MPO tensors W_j(wl, s', s, wr) (host).  As in the reference the state is
     copied on construction (state_envs.jl:59)."""
 
-    def __init__(self, ctx: Context, psi: Sequence, H: Sequence, llim: int = 0, rlim: int | None = None):
+    def __init__(self, ctx: Context, psi: Sequence, H: Sequence, llim: int = 0, rlim: int | None = None,
+                 copy: bool = True):
         self.ctx = ctx
+        self.profile = False           # when True, per-phase device times are accumulated in phase_ms
+        self.phase_ms = {}
+        self.last_solver_info = {}
         self.N = len(psi)
         if len(H) != self.N:
             raise ValueError("MPS and MPO lengths differ")
@@ -30,7 +34,7 @@ class StateEnvs:
             check(ctx.lib.tnl_env_set_site_op(self.h, j + 1, nq, arr, nb, coords.ctypes.data, offsets.ctypes.data,
                                               data.ctypes.data), ctx.h)
         for j, A in enumerate(psi):
-            dt = A.copy() if isinstance(A, DeviceTensor) else DeviceTensor.from_host(ctx, A, nrow=2)
+            dt = (A.copy() if copy else A) if isinstance(A, DeviceTensor) else DeviceTensor.from_host(ctx, A, nrow=2)
             check(ctx.lib.tnl_env_set_state(self.h, j + 1, dt.h), ctx.h)
         # orthogonality limits of the MPS (ITensorMPS llim / rlim)
         self.llim = llim
@@ -48,6 +52,21 @@ class StateEnvs:
     def __len__(self):
         return self.N
 
+    def phase(self, name: str):
+        """Context manager: CUDA-event time of a phase on the library stream (only when self.profile)."""
+        env = self
+
+        class _P:
+            def __enter__(self_p):
+                if env.profile:
+                    env.ctx.timer_start()
+
+            def __exit__(self_p, *exc):
+                if env.profile and exc[0] is None:
+                    env.phase_ms[name] = env.phase_ms.get(name, 0.0) + env.ctx.timer_stop()
+                return False
+        return _P()
+
     # ---- MPS bookkeeping
     def isortho(self) -> bool:
         return self.llim + 2 == self.rlim
@@ -57,10 +76,16 @@ class StateEnvs:
             raise RuntimeError("MPS has no well-defined orthogonality centre")
         return self.llim + 1
 
+    def orthogonalize(self, j: int):
+        """orthogonalize!(psi, j) (sweep.jl:100-102): QR gauge moves on the device."""
+        if self.llim < j - 1:
+            check(self.ctx.lib.tnl_env_move_center(self.h, self.llim + 1, j), self.ctx.h)
+        if self.rlim > j + 1:
+            check(self.ctx.lib.tnl_env_move_center(self.h, self.rlim - 1, j), self.ctx.h)
+        self.llim, self.rlim = j - 1, j + 1
+
     def orthogonalize1(self):
-        """orthogonalize!(psi, 1) (sweep.jl:100-102)."""
-        check(self.ctx.lib.tnl_env_orthogonalize(self.h), self.ctx.h)
-        self.llim, self.rlim = 0, 2
+        self.orthogonalize(1)
 
     def site_tensor(self, j: int) -> DeviceTensor:
         h = C.c_void_p()
@@ -118,6 +143,7 @@ class StateEnvs:
         truncerr = C.c_double()
         neigs = C.c_int64()
         which = {None: 0, "svd": 1, "eigen": 2}[which_decomp]
+        which |= {"divide_and_conquer": 0, "qr_iteration": 0, "recursive": 0, "polar": 1}[svd_alg] << 4
         md = 0 if maxdim is None or maxdim >= (1 << 62) else int(maxdim)
         check(self.ctx.lib.tnl_replacebond(self.h, pos, phi.h, 1 if ortho == "left" else 0, md, int(mindim),
                                            float(cutoff), float(noise), 1 if normalize else 0, which,

@@ -126,12 +126,21 @@ class Context:
     def sync(self):
         check(self.lib.tnl_ctx_sync(self.h), self.h)
 
-    def timer_start(self):
-        check(self.lib.tnl_timer_start(self.h), self.h)
+    def profile_gemm(self, enable: bool):
+        check(self.lib.tnl_profile_gemm(self.h, 1 if enable else 0), self.h)
 
-    def timer_stop(self) -> float:
+    def profile_read(self):
+        ms, n, fl, mx = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+        check(self.lib.tnl_profile_read(self.h, C.byref(ms), C.byref(n), C.byref(fl), C.byref(mx)), self.h)
+        return dict(total_ms=ms.value, launches=n.value, flops=fl.value, max_tflops=mx.value)
+
+    def timer_start(self, slot: int = 0):
+        check(self.lib.tnl_timer_start(self.h, slot), self.h)
+
+    def timer_stop(self, slot: int = 0) -> float:
+        """CUDA-event milliseconds since timer_start(slot) on the library stream (synchronises)."""
         ms = C.c_double()
-        check(self.lib.tnl_timer_stop(self.h, C.byref(ms)), self.h)
+        check(self.lib.tnl_timer_stop(self.h, slot, C.byref(ms)), self.h)
         return ms.value
 
 

@@ -22,17 +22,21 @@ def _update_two_site(sysenv, solver, pos, ortho, time_step, normalize, maxdim, m
     assert (sysenv.orthocenter() == pos and ortho == "left") or (sysenv.orthocenter() == pos + 1 and ortho == "right")
     nsite = 2
     sysenv.set_nsite(nsite)
-    phi = sysenv.make_phi(pos)                       # psi[pos] * psi[pos+1]
-    sysenv.position(pos)
-    energy, phi = solver(sysenv, phi, time_step, **kwargs)
+    with sysenv.phase("make_phi"):
+        phi = sysenv.make_phi(pos)                   # psi[pos] * psi[pos+1]
+    with sysenv.phase("position"):
+        sysenv.position(pos)
+    with sysenv.phase("solver"):
+        energy, phi = solver(sysenv, phi, time_step, **kwargs)
     if normalize:
         phi.scale_(1.0 / phi.norm())
     if isinstance(energy, float) and math.isnan(energy):
         energy = sysenv.expectation(phi)
     drho_noise = noise if abs(noise) > FLOAT64_THRESHOLD else 0.0
-    truncerr, eigs = sysenv.replacebond(pos, phi, maxdim=maxdim, mindim=mindim, cutoff=cutoff, noise=drho_noise,
-                                        ortho=ortho, normalize=normalize, which_decomp=kwargs.get("which_decomp"),
-                                        svd_alg=svd_alg)
+    with sysenv.phase("replacebond"):
+        truncerr, eigs = sysenv.replacebond(pos, phi, maxdim=maxdim, mindim=mindim, cutoff=cutoff, noise=drho_noise,
+                                            ortho=ortho, normalize=normalize, which_decomp=kwargs.get("which_decomp"),
+                                            svd_alg=svd_alg)
     if reverse_step and not halfsweep_done(len(sysenv), pos, nsite, ortho):
         raise NotImplementedError("TDVP reverse step needs exp_solver (later row of the scope table)")
     return energy, truncerr, eigs

@@ -127,7 +127,7 @@ def t_replacebond():
                   "eig err", rel(eigs, spec.eigs) if len(eigs) == len(spec.eigs) else None,
                   "link", m_d.qns == m_o.qns and m_d.dims == m_o.dims, "two-site err", rel(two_d, two_o))
             assert len(eigs) == len(spec.eigs) and (m_d.qns, m_d.dims) == (m_o.qns, m_o.dims)
-            assert abs(terr - spec.truncerr) <= 1e-10 * max(spec.truncerr, 1e-30) + 1e-18
+            assert abs(terr - spec.truncerr) <= 1e-10 * spec.truncerr + 1e-14
             assert rel(two_d, two_o) < 1e-9
 
 
