@@ -408,7 +408,12 @@ LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter,
   const int64_t n = phi.nelem;
   const int howmany = 1;
   std::vector<double*> V;                  // Krylov basis (device buffers)
-  auto newvec = [&]() { return (double*)ctx->alloc(n * sizeof(double)); };
+  // pads between charge groups must stay zero: the flat BLAS-1 kernels run over the padded buffer
+  auto newvec = [&]() {
+    double* p = (double*)ctx->alloc(n * sizeof(double));
+    CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(double), ctx->stream));
+    return p;
+  };
   double* r = newvec();
   auto applyraw = [&](double* vin, double* vout) { apply_ptr(phi, vin, vout); };
   // ---- initialize

