@@ -235,6 +235,8 @@ def run_ours(args):
     ctx.profile_gemm(True)
     ctx.profile_read()
     apply_flops_total, numops_total = 0.0, 0
+    if args.profile_region:
+        torch.cuda.profiler.start()     # ncu --profile-from-start off: only the timed region is captured
     ctx.timer_start(1)              # CUDA events on the library's stream (slot 0 is used by the phase timers)
     for _ in range(args.steps):
         e, err, eigs = T.update_position(sysenv, T.eig_solver, bond, 2, "left", **kw)
@@ -243,6 +245,8 @@ def run_ours(args):
         apply_flops_total += sysenv.last_solver_info["apply_flops"] * sysenv.last_solver_info["numops"]
         bond += 1
     total_s = ctx.timer_stop(1) * 1e-3
+    if args.profile_region:
+        torch.cuda.profiler.stop()
     torch.cuda.synchronize()
     clocks = sampler.stop()
     cnt = ctx.counters()
@@ -279,16 +283,12 @@ def run_ours(args):
     e2e_s = time.time() - t1
     tf_e2e = flops_per_apply * e2e_ops / e2e_s / 1e12
 
-    # ---- aggregate over ranks (replicas: no data-path collective; time = max over ranks)
+    # ---- aggregate over ranks (replicas: no data-path collective; time = max over ranks, work = sum)
+    from tools.rank_agg import aggregate
     ms_per_step = 1e3 * total_s / args.steps
-    if world > 1:
-        t = torch.tensor([ms_per_step, solver_s, e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_per_step, solver_s_max, e2e_s_max = t.tolist()
-        s = torch.tensor([apply_flops_total, flops_per_apply * e2e_ops], device="cuda", dtype=torch.float64)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        tf_apply = s[0].item() / solver_s_max / 1e12
-        tf_e2e = s[1].item() / e2e_s_max / 1e12
+    agg = aggregate(ms_per_step, solver_s, apply_flops_total)
+    ms_per_step, tf_apply = agg["ms_per_step"], agg["tflops"]
+    tf_e2e = aggregate(0.0, e2e_s, flops_per_apply * e2e_ops)["tflops"]
 
     if rank != 0:
         if world > 1:
@@ -345,6 +345,7 @@ def main():
     ap.add_argument("--decomp", default="auto", choices=["auto", "svd", "eigen"])
     ap.add_argument("--svd-alg", dest="svd_alg", default="polar", choices=["divide_and_conquer", "qr_iteration", "polar"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

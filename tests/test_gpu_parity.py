@@ -1,0 +1,276 @@
+"""CUDA path vs CPU oracle through the C ABI (ctypes) -- the parity gate.  Run on the B200 with `-m gpu`.
+
+Tolerances: block structure / bond dimensions / work counts exact; FP64 data 1e-12 relative (different but
+equivalent summation orders); energies 1e-10 relative as required by BASELINE.json north_star."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.json")))
+
+
+def _imports():
+    import tennetlib.jl_b200 as T
+    from oracle import blocksparse as ob, dmrg as od, krylov as ok, models as om, projmpo as op
+    return T, ob, od, ok, om, op
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(1e-300, np.abs(b).max()))
+
+
+def _setup(om, od, kind, N, chi, seed, center):
+    sites = om.siteinds(kind, N)
+    H = om.heisenberg_mpo(sites)
+    qn, dm = om.gaussian_link_sectors(chi, 1.3, 4, step=2 if kind == "S=1" else 1)
+    mps = od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(seed)))
+    od.orthogonalize(mps, center)
+    return sites, H, mps
+
+
+@pytest.mark.parametrize("nrow", [1, 2, 3])
+def test_import_export_roundtrip_is_bit_exact(ctx, nrow):
+    T, ob, od, ok, om, op = _imports()
+    _, _, mps = _setup(om, od, "S=1", 8, 24, 3, 1)
+    A = mps[4]
+    d = T.DeviceTensor.from_host(ctx, A, nrow=nrow)
+    B = d.to_host()
+    assert np.array_equal(B.to_dense(), A.to_dense())
+    assert [(ix.qns, ix.dims, ix.dir) for ix in B.inds] == [(ix.qns, ix.dims, ix.dir) for ix in A.inds]
+    assert abs(d.norm() - A.norm()) < 1e-13 * A.norm()
+
+
+def test_empty_and_single_block_tensors(ctx):
+    T, ob, od, ok, om, op = _imports()
+    sites = om.siteinds("S=1/2", 4)
+    psi = om.neel_mps(sites)                       # product state: one 1x1x1 block per site, most blocks absent
+    for A in psi:
+        d = T.DeviceTensor.from_host(ctx, A, nrow=2)
+        assert np.array_equal(d.to_host().to_dense(), A.to_dense())
+    z = T.DeviceTensor.zeros(ctx, psi[1].inds, nrow=1)
+    assert z.norm() == 0.0
+
+
+def test_vector_interface(ctx):
+    T, ob, od, ok, om, op = _imports()
+    _, _, mps = _setup(om, od, "S=1", 8, 40, 11, 1)
+    A, B = mps[4], mps[4].scale(0.5).add(mps[4], 0.25)
+    x, y = T.DeviceTensor.from_host(ctx, A, 1), T.DeviceTensor.from_host(ctx, B, 1)
+    assert abs(x.dot(y) - ob.inner(A, B)) < 1e-13 * abs(ob.inner(A, B))
+    y.axpy_(x, -0.3).scale_(2.0)
+    ref = B.add(A, -0.3).scale(2.0)
+    assert rel(y.to_host().to_dense(), ref.to_dense()) < 1e-15
+
+
+@pytest.mark.parametrize("kind,N,chi", [("S=1", 8, 24), ("S=1/2", 10, 16), ("S=1", 6, 200)])
+def test_heff_apply_and_environments_match_oracle(ctx, kind, N, chi):
+    T, ob, od, ok, om, op = _imports()
+    sites, H, mps = _setup(om, od, kind, N, chi, 3, 1)
+    env_o = od.StateEnvs(mps, H)
+    env_d = T.StateEnvs(ctx, mps.t, H, llim=0, rlim=2)
+    for pos in (1, N // 2, N - 1):
+        env_o.set_nsite(2); env_o.position(pos)
+        phi_o = ob.contract(env_o.psi[pos], env_o.psi[pos + 1])
+        env_d.set_nsite(2)
+        phi_d = env_d.make_phi(pos)
+        assert rel(phi_d.to_host().to_dense(), phi_o.to_dense()) < 1e-13
+        env_d.position(pos)
+        Hv_o = env_o.product(phi_o)
+        Hv_d = env_d.product(phi_d)
+        assert rel(Hv_d.to_host().to_dense(), Hv_o.to_dense()) < 1e-12
+        assert abs(env_d.expectation(phi_d) - ob.inner(phi_o, Hv_o)) < 1e-12 * abs(ob.inner(phi_o, Hv_o))
+        # linearity and symmetry of the projected Hamiltonian
+        w = phi_d.copy().fill_random(99)
+        a = w.dot(env_d.product(phi_d)); b = env_d.product(w).dot(phi_d)
+        assert abs(a - b) < 1e-10 * max(1.0, abs(a))
+
+
+def test_one_site_and_zero_site_apply_match_oracle(ctx):
+    T, ob, od, ok, om, op = _imports()
+    sites, H, mps = _setup(om, od, "S=1", 8, 24, 3, 4)
+    env_o = od.StateEnvs(mps, H)
+    env_d = T.StateEnvs(ctx, mps.t, H, llim=3, rlim=5)
+    env_o.set_nsite(1); env_o.position(4)
+    env_d.set_nsite(1); env_d.position(4)
+    v_o = env_o.psi[4]
+    v_d = env_d.site_tensor(4)
+    assert rel(env_d.product(v_d).to_host().to_dense(), env_o.product(v_o).to_dense()) < 1e-12
+    # zero-site: bond matrix between sites 4 and 5
+    L, R, spec, u = ob.factorize(v_o, v_o.inds[:2], ortho="left", which_decomp="svd", cutoff=0.0)
+    env_o.psi[4] = L
+    env_o.psi[5] = ob.contract(R, env_o.psi[5])
+    env_o.psi.llim, env_o.psi.rlim = 4, 6
+    env_d2 = T.StateEnvs(ctx, env_o.psi.t, H, llim=4, rlim=6)
+    env_o.PH.lpos, env_o.PH.rpos = 0, 9
+    env_o.set_nsite(0); env_o.position(5)
+    env_d2.set_nsite(0); env_d2.position(5)
+    C = R                                             # (u, r) bond matrix
+    Cd = T.DeviceTensor.from_host(ctx, C, 1)
+    ref = env_o.product(C)
+    assert rel(env_d2.product(Cd).to_host().to_dense(), ref.permute(C.inds).to_dense()) < 1e-12
+
+
+@pytest.mark.parametrize("k", [0, 1])
+def test_bond_fixture_lanczos_and_truncation(ctx, k):
+    """Golden fixture + oracle: eig_solver energy, applies count, truncation error, kept spectrum, new link sectors."""
+    T, ob, od, ok, om, op = _imports()
+    g = G["bond"][k]
+    sites, H, mps = _setup(om, od, g["kind"], g["N"], g["chi"], g["seed"], g["pos"])
+    pos = g["pos"]
+    for t in g["trunc"]:
+        c = pos if t["ortho"] == "left" else pos       # centre already at pos: two-site tensor is the same
+        env_d = T.StateEnvs(ctx, mps.t, H, llim=pos - 1, rlim=pos + 1)
+        env_d.set_nsite(2)
+        phi = env_d.make_phi(pos)
+        env_d.position(pos)
+        phi.scale_(1 / phi.norm())
+        assert abs(env_d.expectation(phi) - g["expectation"]) < 1e-11 * abs(g["expectation"])
+        assert abs(env_d.product(phi).norm() - g["Hv_norm"]) < 1e-11 * g["Hv_norm"]
+        e, phi = T.eig_solver(env_d, phi)
+        assert abs(e - g["lanczos_energy"]) < 1e-10 * abs(g["lanczos_energy"])
+        assert env_d.last_solver_info["numops"] == g["lanczos_numops"]
+        phi.scale_(1 / phi.norm())
+        # the fixture truncates with ortho=left bookkeeping for both directions of the same centre
+        env_d.llim, env_d.rlim = (pos - 1, pos + 1) if t["ortho"] == "left" else (pos, pos + 2)
+        terr, eigs = env_d.replacebond(pos, phi, maxdim=t["maxdim"], mindim=1, cutoff=t["cutoff"], noise=0.0,
+                                       ortho=t["ortho"], normalize=True)
+        link = env_d.site_tensor(pos).inds[2]
+        assert [list(q) for q in link.qns] == t["link_qns"] and list(link.dims) == t["link_dims"]
+        assert len(eigs) == len(t["eigs"])
+        assert abs(terr - t["truncerr"]) < 1e-10 * t["truncerr"] + 1e-14
+        assert np.abs(eigs - np.array(t["eigs"])).max() < 1e-12
+
+
+@pytest.mark.parametrize("ortho", ["left", "right"])
+@pytest.mark.parametrize("kw", [dict(maxdim=12, cutoff=1e-14, noise=0.0), dict(maxdim=40, cutoff=1e-8, noise=0.0),
+                                dict(maxdim=14, cutoff=1e-14, noise=1e-3)])
+def test_replacebond_matches_oracle(ctx, ortho, kw):
+    T, ob, od, ok, om, op = _imports()
+    pos = 4
+    c = pos if ortho == "left" else pos + 1
+    sites, H, mps = _setup(om, od, "S=1", 8, 30, 3, c)
+    env_o = od.StateEnvs(mps, H)
+    env_d = T.StateEnvs(ctx, mps.t, H, llim=c - 1, rlim=c + 1)
+    env_o.set_nsite(2); env_o.position(pos)
+    phi_o = ob.contract(env_o.psi[pos], env_o.psi[pos + 1])
+    phi_o = phi_o.scale(1 / phi_o.norm())
+    drho = None
+    if kw["noise"]:
+        d = op.drho_matrices(env_o.PH.noiseterm(phi_o, ortho), kw["noise"])
+        drho = d if ortho == "left" else {tuple(-x for x in q): M for q, M in d.items()}
+    spec = od.replacebond(env_o.psi, pos, phi_o, maxdim=kw["maxdim"], mindim=1, cutoff=kw["cutoff"],
+                          eigen_perturbation=drho, ortho=ortho, normalize=True)
+    env_d.set_nsite(2); phi_d = env_d.make_phi(pos); env_d.position(pos)
+    phi_d.scale_(1 / phi_d.norm())
+    terr, eigs = env_d.replacebond(pos, phi_d, maxdim=kw["maxdim"], mindim=1, cutoff=kw["cutoff"], noise=kw["noise"],
+                                   ortho=ortho, normalize=True)
+    A1 = env_d.site_tensor(pos).to_host(); A2 = env_d.site_tensor(pos + 1).to_host()
+    two_d = np.tensordot(A1.to_dense(), A2.to_dense(), axes=([2], [0]))
+    two_o = ob.contract(env_o.psi[pos], env_o.psi[pos + 1]).to_dense()
+    m_d, m_o = A1.inds[2], env_o.psi[pos].inds[2]
+    assert (m_d.qns, m_d.dims) == (m_o.qns, m_o.dims)
+    assert len(eigs) == len(spec.eigs) and np.abs(eigs - spec.eigs).max() < 1e-12
+    assert abs(terr - spec.truncerr) <= 1e-10 * spec.truncerr + 1e-14
+    assert rel(two_d, two_o) < 1e-9
+    # the isometric factor is an isometry
+    iso = A1.to_dense() if ortho == "left" else A2.to_dense()
+    M = iso.reshape(-1, iso.shape[2]) if ortho == "left" else iso.reshape(iso.shape[0], -1).T
+    assert np.abs(M.T @ M - np.eye(M.shape[1])).max() < 1e-10
+
+
+def test_qr_gauge_moves_preserve_the_state(ctx):
+    T, ob, od, ok, om, op = _imports()
+    sites, H, mps = _setup(om, od, "S=1/2", 10, 16, 5, 1)
+    raw = od.MPS(om.random_mps(sites, *om.gaussian_link_sectors(16, 1.3, 4, step=1), np.random.default_rng(5)))
+    env = T.StateEnvs(ctx, raw.t, H, llim=0, rlim=11)
+    v0 = om.mps_to_dense(raw.t)
+    env.orthogonalize(1)
+    env.orthogonalize(6)
+    psi = env.getpsi()
+    v1 = om.mps_to_dense(psi)
+    assert rel(v1, v0) < 1e-12
+    for j in range(0, 5):                 # left-canonical
+        M = psi[j].to_dense(); M = M.reshape(-1, M.shape[2])
+        assert np.abs(M.T @ M - np.eye(M.shape[1])).max() < 1e-12
+    for j in range(6, 10):                # right-canonical
+        M = psi[j].to_dense(); M = M.reshape(M.shape[0], -1)
+        assert np.abs(M @ M.T - np.eye(M.shape[0])).max() < 1e-12
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_dmrg_matches_oracle_fixture_and_ed(ctx, k):
+    """configs[0]-scale end-to-end parity: per-sweep energies, bond dimensions and truncation errors."""
+    T, ob, od, ok, om, op = _imports()
+    g = G["dmrg"][k]
+    sites = om.siteinds(g["kind"], g["N"])
+    H = om.heisenberg_mpo(sites)
+    psi0 = om.neel_mps(sites)
+    e, env, sw = T.dmrg2(ctx, psi0, H, T.DMRGParams(**g["params"]), outputlevel=0)
+    assert sw.maxchi == g["maxchi"]
+    assert env.linkdims() == g["linkdims"]
+    noisy = np.array([n > 0 for n in _noise_per_sweep(g["params"])])
+    de = np.abs(np.array(sw.energy) - np.array(g["energy"]))
+    assert de[~noisy].max() < 1e-10 * abs(g["energy"][-1])
+    assert de.max() < 1e-7 * abs(g["energy"][-1])
+    te = np.abs(np.array(sw.maxtruncerr) - np.array(g["maxtruncerr"]))
+    assert te[~noisy].max() < 1e-12 and te.max() < 1e-8
+    ed = G["ed"]["S12_N12"] if g["kind"] == "S=1/2" else G["ed"]["S1_N8"]
+    assert e > ed - 1e-11 and e - ed < 1e-8
+
+
+def _noise_per_sweep(p):
+    out = []
+    n = len(p["nsweeps"])
+    vec = lambda x: x if isinstance(x, list) else [x] * n
+    for ii in range(n):
+        noise = vec(p.get("noise", 0.0))[ii]
+        decay = vec(p.get("noisedecay", 1.0))[ii]
+        off = vec(p.get("disable_noise_after", -1))[ii]
+        for jj in range(1, p["nsweeps"][ii] + 1):
+            out.append(noise)
+            if jj == off:
+                noise = 0.0
+            noise /= decay
+            if noise < 1e-13:
+                noise = 0.0
+    # a sweep right after noisy ones still starts from the noisy state: count it as noisy as well
+    return [a if a > 0 else (out[i - 1] if i > 0 else 0.0) for i, a in enumerate(out)]
+
+
+def test_large_block_properties_chi512(ctx):
+    """Size-independent properties at a size where the 128x128 DMMA tiles, K tails and odd leading dimensions
+    are all exercised: symmetry and linearity of H_eff, Lanczos lowers the energy, truncation bookkeeping."""
+    import tennetlib.jl_b200 as T
+    from tennetlib.jl_b200 import models as pm
+    N, chi = 12, 512
+    sites = pm.siteinds("S=1", N)
+    H = pm.heisenberg_mpo(sites)
+    qn, dm = pm.gaussian_link_sectors(chi, 1.3, 5)
+    links = pm.random_mps_links(sites, qn, dm)
+    psi = [T.DeviceTensor.zeros(ctx, [links[j].copy(dir=+1), sites[j].copy(dir=+1), links[j + 1].copy(dir=-1)], 2).fill_random(7 + j)
+           for j in range(N)]
+    env = T.StateEnvs(ctx, psi, H, llim=0, rlim=N + 1, copy=False)
+    env.orthogonalize(1)
+    env.orthogonalize(6)
+    env.set_nsite(2)
+    phi = env.make_phi(6)
+    env.position(6)
+    phi.scale_(1 / phi.norm())
+    x = phi.copy().fill_random(1); y = phi.copy().fill_random(2)
+    Hx, Hy = env.product(x), env.product(y)
+    assert abs(y.dot(Hx) - Hy.dot(x)) < 1e-11 * abs(y.dot(Hx))
+    z = x.copy().axpy_(y, 0.7)
+    Hz = env.product(z)
+    Hz.axpy_(Hx, -1.0).axpy_(Hy, -0.7)
+    assert Hz.norm() < 1e-12 * Hx.norm()
+    e0 = env.expectation(phi)
+    e1, phi = T.eig_solver(env, phi)
+    assert e1 < e0 and abs(phi.norm() - 1) < 1e-12
+    assert abs(env.expectation(phi) - e1) < 1e-9 * abs(e1)
+    terr, eigs = env.replacebond(6, phi, maxdim=300, mindim=1, cutoff=0.0, noise=0.0, ortho="left", normalize=True)
+    assert len(eigs) == 300 and abs(eigs.sum() + terr - 1.0) < 1e-12 and np.all(np.diff(eigs) <= 0)
+    assert sum(env.site_tensor(6).inds[2].dims) <= 300
