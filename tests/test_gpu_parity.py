@@ -101,9 +101,7 @@ def test_one_site_and_zero_site_apply_match_oracle(ctx):
     assert rel(env_d.product(v_d).to_host().to_dense(), env_o.product(v_o).to_dense()) < 1e-12
     # zero-site: bond matrix between sites 4 and 5
     L, R, spec, u = ob.factorize(v_o, v_o.inds[:2], ortho="left", which_decomp="svd", cutoff=0.0)
-    env_o.psi[4] = L
-    env_o.psi[5] = ob.contract(R, env_o.psi[5])
-    env_o.psi.llim, env_o.psi.rlim = 4, 6
+    env_o.psi[4] = L                                  # psi[pos] = U ; C = S*V lives on the bond (update_site.jl:170-186)
     env_d2 = T.StateEnvs(ctx, env_o.psi.t, H, llim=4, rlim=6)
     env_o.PH.lpos, env_o.PH.rpos = 0, 9
     env_o.set_nsite(0); env_o.position(5)
