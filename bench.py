@@ -101,7 +101,7 @@ def workload_config(args):
             "step": "one two-site bond update at a mid-chain bond (phi, env update, Lanczos eig_solver "
                     "krylovdim=5 maxiter=2 tol=1e-14, truncation maxdim=chi cutoff=%g via %s)" % (args.cutoff, args.decomp),
             "l2_policy": "inputs larger than L2 (per-apply working set > 3 GB at chi=4096)",
-            "cutoff": args.cutoff, "decomp": args.decomp}
+            "cutoff": args.cutoff, "decomp": args.decomp, "svd_alg": args.svd_alg}
 
 
 def oracle_apply_inputs(sector_qns, sector_dims, rng):
@@ -343,7 +343,8 @@ def main():
     ap.add_argument("--nsites", type=int, default=100)
     ap.add_argument("--cutoff", type=float, default=1e-15)
     ap.add_argument("--decomp", default="auto", choices=["auto", "svd", "eigen"])
-    ap.add_argument("--svd-alg", dest="svd_alg", default="polar", choices=["divide_and_conquer", "qr_iteration", "polar"])
+    ap.add_argument("--svd-alg", dest="svd_alg", default="gram", choices=["divide_and_conquer", "qr_iteration", "polar", "gram"],
+                    help="SVD driver of the truncation: gesvd, gesvdp (polar) or Gram-eigh with accuracy guard + gesvdp fallback")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu)")
     args = ap.parse_args()

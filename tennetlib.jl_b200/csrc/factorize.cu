@@ -35,6 +35,23 @@ static cusolverDnHandle_t solver(Ctx* ctx) {
   }
   return (cusolverDnHandle_t)ctx->cusolver;
 }
+struct SideSolver { cudaStream_t s = nullptr; cusolverDnHandle_t h = nullptr; double* work = nullptr; size_t bytes = 0; int* info = nullptr; };
+static std::vector<SideSolver>& side_solvers(Ctx* ctx) {
+  static std::map<Ctx*, std::vector<SideSolver>> all;
+  auto& v = all[ctx];
+  if (v.empty()) {
+    int ns = 4;
+    if (const char* e = getenv("TNL_SIDE_STREAMS")) ns = std::max(1, atoi(e));
+    v.resize(ns);
+    for (auto& sv : v) {
+      CUDA_OK(cudaStreamCreateWithFlags(&sv.s, cudaStreamNonBlocking));
+      CUSOLVER_OK(cusolverDnCreate(&sv.h));
+      CUSOLVER_OK(cusolverDnSetStream(sv.h, sv.s));
+      CUDA_OK(cudaMalloc(&sv.info, 64 * sizeof(int)));
+    }
+  }
+  return v;
+}
 static double* solver_ws(Ctx* ctx, size_t doubles) {
   size_t bytes = doubles * sizeof(double);
   if (bytes > ctx->solver_work_bytes) {
@@ -197,8 +214,12 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
   const bool left = prm.ortho_left != 0;
   cusolverDnHandle_t H = solver(ctx);
   int svd_alg = prm.svd_alg;
-  if (const char* e = getenv("TNL_SVD_ALG")) svd_alg = atoi(e);
   if (which == 3) return factorize_qr(ctx, T, left, prm.new_dir_on_L);
+  // svd_alg 2 ("gram"): singular vectors from the Hermitian eigenproblem of M M^T / M^T M (three DGEMM-rich
+  // steps instead of a latency-bound vendor SVD).  sigma^2 is then accurate to eps*sigma_max^2 ABSOLUTE, so the
+  // result is accepted only if every kept weight is >= 1e-10 of the largest; otherwise fall back to gesvdp.
+  const bool gram = (which == 1 && svd_alg == 2);
+  if (gram) which = 2;
 
   // ---- collect charge groups (union of T's and, on the kept side, the noise operand's)
   std::vector<FG> fg;
@@ -331,33 +352,77 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
       }
       ctx->sync();
     }
-    ctx->sync();
-    g.reset();
+    // Hermitian eigendecompositions, one per charge group, spread over side streams so that the
+    // host-latency-bound phases of cusolverDnDsyevd of different groups overlap
+    std::vector<FG*> todo;
+    std::vector<double*> Wvs;
     for (FG& f : fg) {
       const int64_t n = left ? f.R : f.C;
       if (n == 0) continue;
-      double* Wv = talloc(n);
-      int lwork = 0;
-      CUSOLVER_OK(cusolverDnDsyevd_bufferSize(H, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, f.E, (int)n, Wv, &lwork));
-      double* work = solver_ws(ctx, (size_t)lwork);
-      CUSOLVER_OK(cusolverDnDsyevd(H, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, f.E, (int)n, Wv, work, lwork, ctx->d_info));
-      f.vals.resize(n);
-      CUDA_OK(cudaMemcpyAsync(f.vals.data(), Wv, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-      int info = 0;
-      CUDA_OK(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      ctx->sync();
-      TNL_CHECK(info == 0, "cusolverDnDsyevd did not converge");
-      for (double w : f.vals) pool.push_back(std::fabs(w));
+      todo.push_back(&f);
+      Wvs.push_back(talloc(n));
     }
+    ctx->sync();
+    g.reset();
+    std::vector<size_t> order(todo.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+      return (left ? todo[a]->R : todo[a]->C) > (left ? todo[b]->R : todo[b]->C);
+    });
+    auto& sides = side_solvers(ctx);
+    std::vector<int> slot_of(todo.size());
+    std::vector<int> used(sides.size(), 0);
+    for (size_t k = 0; k < order.size(); k++) {
+      FG& f = *todo[order[k]];
+      const int64_t n = left ? f.R : f.C;
+      SideSolver& sv = sides[k % sides.size()];
+      int lwork = 0;
+      CUSOLVER_OK(cusolverDnDsyevd_bufferSize(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, f.E, (int)n,
+                                              Wvs[order[k]], &lwork));
+      if ((size_t)lwork * sizeof(double) > sv.bytes) {
+        CUDA_OK(cudaStreamSynchronize(sv.s));
+        if (sv.work) cudaFree(sv.work);
+        sv.bytes = (size_t)lwork * sizeof(double) * 5 / 4;
+        CUDA_OK(cudaMalloc(&sv.work, sv.bytes));
+      }
+      TNL_CHECK(used[k % sides.size()] < 64, "too many charge groups per side stream");
+      slot_of[order[k]] = used[k % sides.size()]++;
+      CUSOLVER_OK(cusolverDnDsyevd(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, f.E, (int)n,
+                                   Wvs[order[k]], sv.work, lwork, sv.info + slot_of[order[k]]));
+    }
+    for (auto& sv : sides) CUDA_OK(cudaStreamSynchronize(sv.s));
+    for (size_t k = 0; k < order.size(); k++) {
+      FG& f = *todo[order[k]];
+      const int64_t n = left ? f.R : f.C;
+      SideSolver& sv = sides[k % sides.size()];
+      f.vals.resize(n);
+      CUDA_OK(cudaMemcpy(f.vals.data(), Wvs[order[k]], n * sizeof(double), cudaMemcpyDeviceToHost));
+      int info = 0;
+      CUDA_OK(cudaMemcpy(&info, sv.info + slot_of[order[k]], sizeof(int), cudaMemcpyDeviceToHost));
+      TNL_CHECK(info == 0, "cusolverDnDsyevd did not converge");
+    }
+    for (FG& f : fg)
+      for (double w : f.vals) pool.push_back(std::fabs(w));
   }
 
   // ---- pooled truncation
   std::sort(pool.begin(), pool.end(), std::greater<double>());
   FactorizeResult res;
-  res.path = which == 1 ? "svd" : "eigen";
+  res.path = which == 1 ? "svd" : (gram ? "svd(gram)" : "eigen");
   double docut = 0.0;
+  const double wmax = pool.empty() ? 0.0 : pool[0];
   truncate_spectrum(pool, prm.maxdim, prm.mindim, prm.cutoff, res.truncerr, docut);
   res.eigs = pool;
+  if (gram && !pool.empty() && pool.back() < 1e-10 * wmax) {
+    ctx->sync();
+    for (void* p : temps) ctx->free(p);
+    FactorizeParams p2 = prm;
+    p2.which = 1;
+    p2.svd_alg = 1;
+    FactorizeResult r2 = factorize(ctx, T, p2);
+    r2.path = "svd(polar, gram guard tripped)";
+    return r2;
+  }
   Index m;
   m.nq = T.inds[0].nq;
   std::vector<FG*> kept;

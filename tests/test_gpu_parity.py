@@ -272,3 +272,33 @@ def test_large_block_properties_chi512(ctx):
     terr, eigs = env.replacebond(6, phi, maxdim=300, mindim=1, cutoff=0.0, noise=0.0, ortho="left", normalize=True)
     assert len(eigs) == 300 and abs(eigs.sum() + terr - 1.0) < 1e-12 and np.all(np.diff(eigs) <= 0)
     assert sum(env.site_tensor(6).inds[2].dims) <= 300
+
+
+@pytest.mark.parametrize("svd_alg", ["qr_iteration", "polar", "gram"])
+def test_svd_drivers_agree(ctx, svd_alg):
+    """All SVD drivers of the truncation give the same spectrum / truncation error / bond dimension; the Gram
+    driver trips its accuracy guard (and falls back) when the kept spectrum spans more than 1e-10."""
+    T, ob, od, ok, om, op = _imports()
+    pos = 4
+    sites, H, mps = _setup(om, od, "S=1", 8, 100, 3, pos)
+    env_o = od.StateEnvs(mps, H)
+    env_o.set_nsite(2); env_o.position(pos)
+    phi_o = ob.contract(env_o.psi[pos], env_o.psi[pos + 1])
+    phi_o = phi_o.scale(1 / phi_o.norm())
+    for maxdim, cutoff in ((60, 1e-14), (10000, 0.0)):
+        mo = env_o.psi.copy()
+        spec = od.replacebond(mo, pos, phi_o, maxdim=maxdim, mindim=1, cutoff=cutoff, eigen_perturbation=None,
+                              ortho="left", normalize=True)
+        env_d = T.StateEnvs(ctx, mps.t, H, llim=pos - 1, rlim=pos + 1)
+        env_d.set_nsite(2); phi_d = env_d.make_phi(pos); env_d.position(pos)
+        phi_d.scale_(1 / phi_d.norm())
+        terr, eigs = env_d.replacebond(pos, phi_d, maxdim=maxdim, mindim=1, cutoff=cutoff, noise=0.0, ortho="left",
+                                       normalize=True, svd_alg=svd_alg)
+        assert len(eigs) == len(spec.eigs)
+        assert np.abs(eigs - spec.eigs).max() < 1e-12 and abs(terr - spec.truncerr) < 1e-12
+        A1 = env_d.site_tensor(pos).to_host().to_dense(); A2 = env_d.site_tensor(pos + 1).to_host().to_dense()
+        two_d = np.tensordot(A1, A2, axes=([2], [0]))
+        two_o = ob.contract(mo[pos], mo[pos + 1]).to_dense()
+        assert rel(two_d, two_o) < 1e-9
+        M = A1.reshape(-1, A1.shape[2])
+        assert np.abs(M.T @ M - np.eye(M.shape[1])).max() < 1e-10
