@@ -36,17 +36,32 @@ int tnl_ctx_create(int device, tnl_ctx_t* ctx);
 int tnl_ctx_destroy(tnl_ctx_t ctx);
 const char* tnl_last_error(tnl_ctx_t ctx); /* ctx may be NULL: last error of the calling thread */
 /* out[0..7] = gemm_flops, transform_flops, vec_bytes, transform_bytes, kernel launches, gemm launches,
- * H_eff applies, reserved.  Algorithmic counts. */
+ * H_eff applies, all-reduce bytes.  Algorithmic counts. */
 int tnl_get_counters(tnl_ctx_t ctx, double* out8);
 int tnl_reset_counters(tnl_ctx_t ctx);
 int tnl_ctx_sync(tnl_ctx_t ctx);
 /* CUDA-event timing on the library's own stream (bench.py times kernels here, not on torch's stream). */
 int tnl_timer_start(tnl_ctx_t ctx, int32_t slot); /* slot 0..3 */
 int tnl_timer_stop(tnl_ctx_t ctx, int32_t slot, double* milliseconds);
+/* kernel self test / micro-benchmark: random C = op(A) op(B) with the grouped DGEMM kernel; returns the average
+ * launch time and (verify != 0) the max abs deviation from a naive FP64 reference kernel */
+int tnl_gemm_selftest(tnl_ctx_t ctx, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB, int32_t variant,
+                      int32_t reps, int32_t verify, double* ms, double* maxerr);
+int tnl_set_gemm_variant(tnl_ctx_t ctx, int32_t variant); /* tuning knob: main-loop variant of the DGEMM kernel */
 /* per-launch CUDA-event profile of the grouped DGEMM launches (those with 128x128 tiles): enable, run, read
  * (read synchronises, sums the launch durations and algorithmic flops, and clears the records) */
 int tnl_profile_gemm(tnl_ctx_t ctx, int32_t enable);
 int tnl_profile_read(tnl_ctx_t ctx, double* total_ms, int64_t* launches, double* flops, double* max_tflops);
+
+/* ---- multi-GPU: one process per GPU, sharded H_eff apply ----------------
+ * rank 0 calls tnl_comm_unique_id, the 128 bytes are broadcast by the host (torch.distributed / MPI), every rank
+ * calls tnl_comm_init.  Afterwards tnl_heff_apply / tnl_eigsolve_lanczos shard the two-site apply over the right
+ * link (each rank owns tnl_shard_range of every sector) and combine the partial results with ncclAllReduce.
+ * All ranks must hold identical replicated state and issue the same calls. */
+int tnl_comm_unique_id(char* out128);
+int tnl_comm_init(tnl_ctx_t ctx, const char* uid128, int32_t rank, int32_t world);
+int tnl_comm_destroy(tnl_ctx_t ctx);
+int tnl_shard_range(int32_t dim, int32_t world, int32_t sector, int32_t rank, int32_t* start, int32_t* count);
 
 /* ---- tensors: ITensor <-> device (replaces nothing in the reference; it is the marshalling the shim needs) */
 int tnl_tensor_import(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t* inds, int64_t nblocks,

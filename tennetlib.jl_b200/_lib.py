@@ -29,6 +29,13 @@ _SIGS = {
     "tnl_ctx_sync": [_P],
     "tnl_timer_start": [_P, C.c_int32],
     "tnl_timer_stop": [_P, C.c_int32, C.POINTER(C.c_double)],
+    "tnl_comm_unique_id": [C.c_char_p],
+    "tnl_comm_init": [_P, C.c_char_p, C.c_int32, C.c_int32],
+    "tnl_comm_destroy": [_P],
+    "tnl_shard_range": [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+    "tnl_gemm_selftest": [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                          C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    "tnl_set_gemm_variant": [_P, C.c_int32],
     "tnl_profile_gemm": [_P, C.c_int32],
     "tnl_profile_read": [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "tnl_tensor_import": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int64, _P, _P, _P, C.c_int32, C.POINTER(_P)],

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libtnl_b200.so")
-SOURCES = ["kernels.cu", "core.cpp", "env.cpp", "factorize.cu", "capi.cpp"]
+SOURCES = ["kernels.cu", "core.cpp", "env.cpp", "factorize.cu", "comm.cpp", "capi.cpp"]
 HEADERS = ["core.hpp", "env.hpp", os.path.join("..", "..", "include", "tnl_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {s}")
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-L/usr/local/cuda/lib64", "-lcusolver", "-lcudart",
+    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-L/usr/local/cuda/lib64", "-lcusolver", "-lcudart", "-ldl",
                                                   "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
     return OUT

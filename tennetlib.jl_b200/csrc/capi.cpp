@@ -88,7 +88,7 @@ int tnl_get_counters(tnl_ctx_t c, double* o) {
   return guard(&c->ctx, [&] {
     const Counters& k = c->ctx.cnt;
     o[0] = k.gemm_flops; o[1] = k.xf_flops; o[2] = k.vec_bytes; o[3] = k.xf_bytes;
-    o[4] = (double)k.launches; o[5] = (double)k.gemm_launches; o[6] = k.apply_count; o[7] = 0;
+    o[4] = (double)k.launches; o[5] = (double)k.gemm_launches; o[6] = k.apply_count; o[7] = k.allreduce_bytes;
   });
 }
 int tnl_reset_counters(tnl_ctx_t c) { return guard(&c->ctx, [&] { c->ctx.cnt = Counters(); }); }
@@ -111,6 +111,35 @@ int tnl_timer_stop(tnl_ctx_t c, int32_t slot, double* ms) {
   });
 }
 
+int tnl_comm_unique_id(char* out128) {
+  return guard(nullptr, [&] { comm_unique_id(out128); });
+}
+int tnl_comm_init(tnl_ctx_t c, const char* uid128, int32_t rank, int32_t world) {
+  return guard(&c->ctx, [&] { comm_init(&c->ctx, uid128, rank, world); });
+}
+int tnl_comm_destroy(tnl_ctx_t c) {
+  return guard(&c->ctx, [&] { comm_destroy(&c->ctx); });
+}
+int tnl_shard_range(int32_t dim, int32_t world, int32_t sector, int32_t rank, int32_t* start, int32_t* count) {
+  return guard(nullptr, [&] {
+    TNL_CHECK(world >= 1 && rank >= 0 && rank < world && dim >= 0, "bad shard query");
+    int s, n;
+    shard_range(dim, world, sector, rank, &s, &n);
+    *start = s; *count = n;
+  });
+}
+int tnl_gemm_selftest(tnl_ctx_t c, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB, int32_t variant,
+                      int32_t reps, int32_t verify, double* ms, double* maxerr) {
+  return guard(&c->ctx, [&] {
+    int old = c->ctx.gemm_variant;
+    if (variant > 0) c->ctx.gemm_variant = variant;
+    gemm_selftest(&c->ctx, M, N, K, transA != 0, transB != 0, reps, verify != 0, ms, maxerr);
+    c->ctx.gemm_variant = old;
+  });
+}
+int tnl_set_gemm_variant(tnl_ctx_t c, int32_t variant) {
+  return guard(&c->ctx, [&] { c->ctx.gemm_variant = variant; });
+}
 int tnl_profile_gemm(tnl_ctx_t c, int32_t enable) {
   return guard(&c->ctx, [&] { c->ctx.prof_gemm = enable != 0; });
 }

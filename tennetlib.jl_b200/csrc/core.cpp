@@ -257,7 +257,7 @@ std::unique_ptr<GemmPlan> plan_gemm(const Tensor& A, bool transA, const Tensor& 
 
 // ------------------------------------------------------------------------------- transform plan
 std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const std::vector<int>& xmap,
-                                              const Tensor* W, const std::vector<int>& kpos) {
+                                              const Tensor* W, const std::vector<int>& kpos, const SliceMap* slice) {
   auto plan = std::make_unique<TransformPlan>();
   plan->ctx = Y.ctx;
   const int ry = Y.rank(), rx = X.rank();
@@ -293,13 +293,19 @@ std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const 
     int xc[MAXR];
     xc[0] = yb.c[0];
     for (size_t k = 0; k < passY.size(); k++) xc[xmap[passY[k]]] = yb.c[passY[k]];
+    int64_t slice_start = 0;
+    if (slice) {
+      TNL_CHECK(slice->ypos > 0 && xmap[slice->ypos] >= 0, "sliced index must be passive and non-leading");
+      xc[xmap[slice->ypos]] = slice->orig[yb.c[slice->ypos]];
+      slice_start = slice->start[yb.c[slice->ypos]];
+    }
     auto add = [&](const Block* wb) {
       for (int k = 0; k < nk; k++) xc[kpos[k]] = wb->c[k];
       int bi = X.find(xc);
       if (bi < 0) return;
       const Block& sb = X.blocks[bi];
       XfContrib c{};
-      c.xoff = sb.off;
+      c.xoff = sb.off + (slice ? slice_start * sb.st[xmap[slice->ypos]] : 0);
       for (int k = 0; k < MAXP; k++) c.xps[k] = 0;
       for (size_t k = 0; k < passY.size(); k++) c.xps[k] = sb.st[xmap[passY[k]]];
       c.kd0 = c.kd1 = 1; c.ks0 = c.ks1 = 0;

@@ -187,6 +187,7 @@ struct Counters {
   long long launches = 0;         // kernels of THIS library launched
   long long gemm_launches = 0;
   double apply_count = 0;
+  double allreduce_bytes = 0;
 };
 
 class Ctx {
@@ -200,6 +201,7 @@ class Ctx {
   unsigned int* d_sync = nullptr;   // "last block" counters
   double* d_partials = nullptr;
   int num_sms = 148;
+  int gemm_variant = 3;             // grouped DGEMM main-loop variant (3 = v2 loop, BK=32, 3 stages; see kernels.cu)
   // optional per-launch CUDA-event profile of the grouped GEMM kernel (bench.py roofline)
   struct ProfRec { cudaEvent_t a, b; double flops; int tiles; };
   bool prof_gemm = false;
@@ -236,14 +238,24 @@ std::unique_ptr<GemmPlan> plan_gemm(const Tensor& A, bool transA, const Tensor& 
 void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C);
 // ad-hoc problems (factorisation internals); builds tiles and uploads
 std::unique_ptr<GemmPlan> plan_gemm_raw(Ctx* ctx, bool transA, bool transB, const std::vector<GemmProblem>& probs);
+void gemm_selftest(Ctx* ctx, int M, int N, int K, bool ta, bool tb, int reps, bool verify, double* ms, double* maxerr);
+void comm_unique_id(char* out128);
+void comm_init(Ctx* ctx, const char* uid128, int rank, int world);
+void comm_destroy(Ctx* ctx);
+void comm_allreduce_sum(Ctx* ctx, double* buf, int64_t n);
+void shard_range(int d, int world, int sector, int rank, int* start, int* count);
 void transpose(Ctx* ctx, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t R, int64_t C);  // dst[C x R] = src[R x C]^T
 void copy2d(Ctx* ctx, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t R, int64_t C);
 
 // W == nullptr: pure relayout / index permutation.  `xmap[j]` = position in X of Y's index j, or -1 for a
 // new index (coming from W); `kpos` lists the X positions that are contracted with W (in W's row order);
 // W's indices are ordered (contracted..., new...).
+// Optional slicing of one PASSIVE index: Y's index `ypos` is a sub-range of X's index xmap[ypos];
+// Y sector k corresponds to X sector orig[k], elements [start[k], start[k] + dim_Y(k)).
+struct SliceMap { int ypos = -1; std::vector<int> orig; std::vector<int64_t> start; };
 std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const std::vector<int>& xmap,
-                                              const Tensor* W, const std::vector<int>& kpos);
+                                              const Tensor* W, const std::vector<int>& kpos,
+                                              const SliceMap* slice = nullptr);
 void run_transform(Ctx* ctx, TransformPlan& p, const double* X, double* Y, const double* W);
 
 // flat vector kernels on padded buffers of equal layout

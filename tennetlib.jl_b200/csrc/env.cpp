@@ -229,6 +229,9 @@ TensorP Env::make_phi(int pos) {
 // ---------------------------------------------------------------------------------- H_eff apply
 struct Env::ApplyPlan {
   int nsite;
+  bool sharded = false;              // multi-GPU: this rank handles a slice of the right link r
+  TensorP vloc;                      // v restricted to the local r range
+  std::unique_ptr<TransformPlan> xs; // v -> vloc
   TensorP L, R, W1, W2;
   TensorP T1, T2, T3, P;
   std::unique_ptr<GemmPlan> g1, g4;
@@ -237,7 +240,8 @@ struct Env::ApplyPlan {
   double flops;
 };
 
-void Env::build_apply_plan(const Tensor& v) {
+void Env::build_apply_plan(const Tensor& vfull) {
+  const Tensor& v = vfull;
   auto p = std::make_shared<ApplyPlan>();
   p->nsite = nsite;
   p->L = lproj();
@@ -249,6 +253,37 @@ void Env::build_apply_plan(const Tensor& v) {
     TNL_CHECK(v.rank() == 4 && rpos - lpos == 3, "two-site apply needs a (l,s1,s2,r) vector and nsite=2 position");
     p->W1 = Wlr[first - 1];
     p->W2 = Wlr[first];
+    const Tensor* vin = &v;
+    if (ctx->world > 1) {
+      // Sharded apply: every rank owns a contiguous share of each sector of the right
+      // link r.  It contracts L with its slice of v, carries the slice through the site operators and contracts
+      // with its slice of R over (w, r_local): a partial H_eff v of full size, summed by one NCCL all-reduce.
+      const Index& r = v.inds[3];
+      Index rl = r;
+      rl.dims.clear(); rl.qns.clear();
+      SliceMap sm;
+      sm.ypos = 3;
+      for (int s = 0; s < r.nsect(); s++) {
+        int st, cnt;
+        shard_range(r.dims[s], ctx->world, s, ctx->rank, &st, &cnt);
+        if (cnt > 0) { rl.dims.push_back(cnt); rl.qns.push_back(r.qns[s]); sm.orig.push_back(s); sm.start.push_back(st); }
+      }
+      p->sharded = true;
+      p->vloc = mk(ctx, {v.inds[0], v.inds[1], v.inds[2], rl}, 1);
+      p->xs = plan_transform(v, *p->vloc, {0, 1, 2, 3}, nullptr, {}, &sm);
+      const Tensor& Rf = *p->R;
+      Index rlR = rl;
+      rlR.dir = Rf.inds[2].dir;
+      SliceMap sr = sm;
+      sr.ypos = 2;
+      auto Rloc = mk(ctx, {Rf.inds[0], Rf.inds[1], rlR}, 1);
+      auto xr = plan_transform(Rf, *Rloc, {0, 1, 2}, nullptr, {}, &sr);
+      run_transform(ctx, *xr, Rf.d, Rloc->d, nullptr);
+      ctx->sync();
+      p->R = Rloc;
+      vin = p->vloc.get();
+    }
+    const Tensor& v = *vin;     // from here on: the (possibly sliced) input structure
     const Tensor &L = *p->L, &R = *p->R, &W1 = *p->W1, &W2 = *p->W2;
     p->T1 = mk(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2], v.inds[3]}, 2);
     p->g1 = plan_gemm(L, false, v, false, *p->T1);
@@ -259,7 +294,7 @@ void Env::build_apply_plan(const Tensor& v) {
     p->P = mk(ctx, {L.inds[0], W1.inds[2], W2.inds[2], R.inds[0]}, 3);
     p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
     Tensor Q(ctx, p->P->inds, 1, false);
-    TNL_CHECK(Q.nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
+    TNL_CHECK(Q.nelem == vfull.nelem, "H_eff output layout differs from the input layout (index mismatch)");
     p->x5 = plan_transform(*p->P, Q, {0, 1, 2, 3}, nullptr, {});
     p->flops = p->g1->flops + p->x2->flops + p->x3->flops + p->g4->flops;
   } else if (nsite == 1) {
@@ -290,7 +325,7 @@ void Env::build_apply_plan(const Tensor& v) {
   } else {
     throw Error(2, "nsite must be 0, 1 or 2");
   }
-  p->nelem = v.nelem;
+  p->nelem = vfull.nelem;
   ap = p;
 }
 
@@ -306,12 +341,17 @@ void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
   ApplyPlan& p = *ap;
   struct { const double* d; } v{vin};
   struct { double* d; } out{vout};
+  if (p.sharded) {
+    run_transform(ctx, *p.xs, v.d, p.vloc->d, nullptr);
+    v.d = p.vloc->d;
+  }
   run_gemm(ctx, *p.g1, p.L->d, v.d, p.T1->d);
   if (p.nsite == 2) {
     run_transform(ctx, *p.x2, p.T1->d, p.T2->d, p.W1->d);
     run_transform(ctx, *p.x3, p.T2->d, p.T3->d, p.W2->d);
     run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
     run_transform(ctx, *p.x5, p.P->d, out.d, nullptr);
+    if (p.sharded) comm_allreduce_sum(ctx, out.d, p.nelem);
   } else if (p.nsite == 1) {
     run_transform(ctx, *p.x2, p.T1->d, p.T3->d, p.W1->d);
     run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);

@@ -151,12 +151,167 @@ gemm_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ 
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// v2 of the grouped DGEMM main loop.  Differences to gemm_kernel:
+//   * every thread precomputes, once per tile, the source offset / validity of its 16-byte chunks: inside the
+//     k loop a load is "offset += step" + one predicate (no 64-bit multiplies, no branches);
+//   * DMMA fragments are double buffered in registers: the LDS of k-step kk+1 are issued before the 32 DMMAs
+//     of k-step kk, and the cp.async of the next stage are issued after the first fragments are in flight.
+// -------------------------------------------------------------------------------------------------
+template <int BX, int BK, bool KFAST, int NT>
+struct Loader {
+  static constexpr int LD = OpTile<BX, BK, KFAST>::LD;
+  static constexpr int CH = BX * BK / 2;
+  static constexpr int NCH = CH / NT;          // chunks per thread
+  static_assert(CH % NT == 0, "tile must split evenly over the threads");
+  int goff[NCH];      // element offset of the chunk at k-tile 0 (relative to the operand base)
+  int soff[NCH];      // shared-memory element offset inside a stage
+  int kq[NCH];        // k position of the chunk inside a k-tile
+  int xv[NCH];        // valid doubles along x (!KFAST: 0..2 ; KFAST: 0 or 2 meaning the row is valid)
+  int kstep;          // offset advance per k-tile
+  __device__ __forceinline__ void init(int ld, int x0, int X, int tid) {
+#pragma unroll
+    for (int i = 0; i < NCH; i++) {
+      int c = tid + i * NT;
+      if (KFAST) {
+        constexpr int CPR = BK / 2;
+        int xx = c / CPR, kc = c % CPR;
+        int x = x0 + xx;
+        kq[i] = 2 * kc;
+        xv[i] = (x < X) ? 2 : 0;
+        goff[i] = (x < X) ? x * ld + 2 * kc : 0;
+        soff[i] = xx * LD + 2 * kc;
+      } else {
+        constexpr int CPR = BX / 2;
+        int kk = c / CPR, xc = c % CPR;
+        int x = x0 + 2 * xc;
+        kq[i] = kk;
+        xv[i] = max(0, min(2, X - x));
+        goff[i] = xv[i] ? kk * ld + x : 0;
+        soff[i] = kk * LD + 2 * xc;
+      }
+    }
+    kstep = KFAST ? BK : BK * ld;
+  }
+  __device__ __forceinline__ void issue(double* s, const double* g, int kt, int K) const {
+#pragma unroll
+    for (int i = 0; i < NCH; i++) {
+      int k = kt * BK + kq[i];
+      int v;
+      if (KFAST) v = xv[i] ? max(0, min(2, K - k)) : 0;
+      else v = (k < K) ? xv[i] : 0;
+      const double* src = g + (v ? (int64_t)goff[i] + (int64_t)kt * kstep : 0);
+      cp_async16(s + soff[i], src, v * 8);
+    }
+  }
+};
+
 template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+gemm_kernel_v2(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles,
+               const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase) {
+  constexpr int NT = (BM / WM) * (BN / WN) * 32;
+  using TileA = OpTile<BM, BK, TA>;
+  using TileB = OpTile<BN, BK, !TB>;
+  constexpr int STAGE_ELEMS = TileA::ELEMS + TileB::ELEMS;
+  constexpr int MI = WM / 8, NI = WN / 8, KK = BK / 4;
+  extern __shared__ __align__(16) double smem[];
+
+  const GemmTile tile = tiles[blockIdx.x];
+  const GemmProblem p = probs[tile.prob];
+  const double* pA = Abase + p.a;
+  const double* pB = Bbase + p.b;
+  double* pC = Cbase + p.c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp % (BM / WM)) * WM, wn0 = (warp / (BM / WM)) * WN;
+  const int m0 = tile.m0, n0 = tile.n0;
+  const int ktiles = (p.K + BK - 1) / BK;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  Loader<BM, BK, TA, NT> la;
+  Loader<BN, BK, !TB, NT> lb;
+  la.init(p.lda, m0, p.M, tid);
+  lb.init(p.ldb, n0, p.N, tid);
+
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int i = 0; i < MI; i++)
+#pragma unroll
+    for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < ktiles) {
+      double* sa = smem + s * STAGE_ELEMS;
+      la.issue(sa, pA, s, p.K);
+      lb.issue(sa + TileA::ELEMS, pB, s, p.K);
+    }
+    cp_async_commit();
+  }
+  // fragment element offsets of this lane inside a stage
+  const int fa = TA ? (wm0 + lr) * TileA::LD + lc : lc * TileA::LD + wm0 + lr;
+  const int fb = (!TB) ? (wn0 + lr) * TileB::LD + lc : lc * TileB::LD + wn0 + lr;
+  constexpr int FA_I = TA ? 8 * TileA::LD : 8;            // +8 rows of m
+  constexpr int FA_K = TA ? 4 : 4 * TileA::LD;            // +4 in k
+  constexpr int FB_J = (!TB) ? 8 * TileB::LD : 8;
+  constexpr int FB_K = (!TB) ? 4 : 4 * TileB::LD;
+
+  double a[2][MI], b[2][NI];
+  for (int kt = 0; kt < ktiles; kt++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    const double* sa = smem + (kt % STAGES) * STAGE_ELEMS + fa;
+    const double* sb = smem + (kt % STAGES) * STAGE_ELEMS + TileA::ELEMS + fb;
+#pragma unroll
+    for (int i = 0; i < MI; i++) a[0][i] = sa[i * FA_I];
+#pragma unroll
+    for (int j = 0; j < NI; j++) b[0][j] = sb[j * FB_J];
+    {
+      const int nk = kt + STAGES - 1;
+      if (nk < ktiles) {
+        double* st = smem + (nk % STAGES) * STAGE_ELEMS;
+        la.issue(st, pA, nk, p.K);
+        lb.issue(st + TileA::ELEMS, pB, nk, p.K);
+      }
+      cp_async_commit();
+    }
+#pragma unroll
+    for (int kk = 0; kk < KK; kk++) {
+      const int cur = kk & 1, nxt = cur ^ 1;
+      if (kk + 1 < KK) {
+#pragma unroll
+        for (int i = 0; i < MI; i++) a[nxt][i] = sa[i * FA_I + (kk + 1) * FA_K];
+#pragma unroll
+        for (int j = 0; j < NI; j++) b[nxt][j] = sb[j * FB_J + (kk + 1) * FB_K];
+      }
+#pragma unroll
+      for (int i = 0; i < MI; i++)
+#pragma unroll
+        for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < MI; i++) {
+    int m = m0 + wm0 + i * 8 + lr;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < NI; j++) {
+      int n = n0 + wn0 + j * 8 + 2 * lc;
+      double* c = pC + (int64_t)n * p.ldc + m;
+      if (n < p.N) c[0] = acc[i][j][0];
+      if (n + 1 < p.N) c[p.ldc] = acc[i][j][1];
+    }
+  }
+}
+
+template <int VER, int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
 static void launch_gemm_one(Ctx* ctx, const GemmProblem* probs, const GemmTile* tiles, int ntiles,
                             const double* A, const double* B, double* C) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr size_t SMEM = sizeof(double) * STAGES * (OpTile<BM, BK, TA>::ELEMS + OpTile<BN, BK, !TB>::ELEMS);
-  auto kern = gemm_kernel<BM, BN, BK, WM, WN, TA, TB, STAGES>;
+  auto kern = VER == 2 ? gemm_kernel_v2<BM, BN, BK, WM, WN, TA, TB, STAGES> : gemm_kernel<BM, BN, BK, WM, WN, TA, TB, STAGES>;
   static bool configured = false;   // one static per template instantiation
   if (!configured) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -168,14 +323,14 @@ static void launch_gemm_one(Ctx* ctx, const GemmProblem* probs, const GemmTile* 
   ctx->cnt.gemm_launches++;
 }
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES>
+template <int VER, int BM, int BN, int BK, int WM, int WN, int STAGES>
 static void launch_gemm_cfg(Ctx* ctx, bool ta, bool tb, const GemmProblem* probs, const GemmTile* tiles, int ntiles,
                             const double* A, const double* B, double* C) {
   if (ntiles == 0) return;
-  if (!ta && !tb) launch_gemm_one<BM, BN, BK, WM, WN, false, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
-  else if (!ta && tb) launch_gemm_one<BM, BN, BK, WM, WN, false, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
-  else if (ta && !tb) launch_gemm_one<BM, BN, BK, WM, WN, true, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
-  else launch_gemm_one<BM, BN, BK, WM, WN, true, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
+  if (!ta && !tb) launch_gemm_one<VER, BM, BN, BK, WM, WN, false, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
+  else if (!ta && tb) launch_gemm_one<VER, BM, BN, BK, WM, WN, false, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
+  else if (ta && !tb) launch_gemm_one<VER, BM, BN, BK, WM, WN, true, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
+  else launch_gemm_one<VER, BM, BN, BK, WM, WN, true, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
 }
 
 void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C) {
@@ -187,8 +342,17 @@ void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C
     CUDA_OK(cudaEventCreate(&rec.b));
     CUDA_OK(cudaEventRecord(rec.a, ctx->stream));
   }
-  launch_gemm_cfg<128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, (int)p.tiles_big.size(), A, B, C);
-  launch_gemm_cfg<64, 64, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_small, (int)p.tiles_small.size(), A, B, C);
+  const int nb = (int)p.tiles_big.size();
+  switch (ctx->gemm_variant) {
+    case 1: launch_gemm_cfg<1, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    case 4: launch_gemm_cfg<2, 128, 128, 16, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    case 5: launch_gemm_cfg<2, 128, 128, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    case 6: launch_gemm_cfg<2, 128, 128, 32, 32, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    case 7: launch_gemm_cfg<2, 128, 128, 32, 32, 64, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    case 2: launch_gemm_cfg<2, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    default: launch_gemm_cfg<2, 128, 128, 32, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+  }
+  launch_gemm_cfg<1, 64, 64, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_small, (int)p.tiles_small.size(), A, B, C);
   if (prof) {
     CUDA_OK(cudaEventRecord(rec.b, ctx->stream));
     rec.flops = p.flops;
@@ -196,6 +360,82 @@ void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C
     ctx->prof_recs.push_back(rec);
   }
   ctx->cnt.gemm_flops += p.flops;
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+struct BlkDesc { int64_t off; int64_t st[MAXR]; int d[MAXR]; int r; uint64_t key; };
+__global__ void fill_random_kernel(double* __restrict__ data, BlkDesc b, int64_t n, uint64_t seed) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = e, addr = b.off;
+    for (int k = 0; k < b.r; k++) { addr += (t % b.d[k]) * b.st[k]; t /= b.d[k]; }
+    uint64_t u = splitmix64(splitmix64(seed ^ (b.key * 0xD1342543DE82EF95ull)) + (uint64_t)e);
+    data[addr] = (double)(u >> 11) * (2.0 / 9007199254740992.0) - 1.0;   // uniform [-1, 1), 53 bits
+  }
+}
+// reference kernel + self test (also the GEMM micro-benchmark used while tuning)
+__global__ void ref_gemm_kernel(const double* A, const double* B, double* C, int M, int N, int K, int lda, int ldb, int ldc,
+                                bool ta, bool tb) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+  if (m >= M || n >= N) return;
+  double s = 0.0;
+  for (int k = 0; k < K; k++) {
+    double a = ta ? A[(int64_t)m * lda + k] : A[(int64_t)k * lda + m];
+    double b = tb ? B[(int64_t)k * ldb + n] : B[(int64_t)n * ldb + k];
+    s = fma(a, b, s);
+  }
+  C[(int64_t)n * ldc + m] = s;
+}
+
+void gemm_selftest(Ctx* ctx, int M, int N, int K, bool ta, bool tb, int reps, bool verify, double* ms, double* maxerr) {
+  auto ev = [](int64_t x) { return (x + 1) & ~int64_t(1); };
+  const int lda = (int)ev(ta ? K : M), ldb = (int)ev(tb ? N : K), ldc = (int)ev(M);
+  const int64_t na = (int64_t)lda * (ta ? M : K), nb = (int64_t)ldb * (tb ? K : N), nc = (int64_t)ldc * N;
+  double* A = (double*)ctx->alloc(na * 8);
+  double* B = (double*)ctx->alloc(nb * 8);
+  double* C = (double*)ctx->alloc(nc * 8);
+  double* R = (double*)ctx->alloc(nc * 8);
+  BlkDesc d{};
+  d.r = 1; d.st[0] = 1; d.key = 1;
+  d.off = 0; d.d[0] = (int)std::min<int64_t>(na, INT32_MAX);
+  fill_random_kernel<<<1184, 256, 0, ctx->stream>>>(A, d, na, 11);
+  d.key = 2; d.d[0] = (int)std::min<int64_t>(nb, INT32_MAX);
+  fill_random_kernel<<<1184, 256, 0, ctx->stream>>>(B, d, nb, 12);
+  CUDA_OK(cudaMemsetAsync(C, 0, nc * 8, ctx->stream));
+  GemmProblem p{};
+  p.a = p.b = p.c = 0; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+  auto plan = plan_gemm_raw(ctx, ta, tb, {p});
+  run_gemm(ctx, *plan, A, B, C);
+  ctx->sync();
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+  CUDA_OK(cudaEventRecord(e0, ctx->stream));
+  for (int r = 0; r < reps; r++) run_gemm(ctx, *plan, A, B, C);
+  CUDA_OK(cudaEventRecord(e1, ctx->stream));
+  CUDA_OK(cudaEventSynchronize(e1));
+  float f = 0;
+  CUDA_OK(cudaEventElapsedTime(&f, e0, e1));
+  *ms = f / std::max(1, reps);
+  *maxerr = -1.0;
+  if (verify) {
+    dim3 grid((M + 127) / 128, N);
+    ref_gemm_kernel<<<grid, 128, 0, ctx->stream>>>(A, B, R, M, N, K, lda, ldb, ldc, ta, tb);
+    CUDA_OK(cudaGetLastError());
+    std::vector<double> hc(nc), hr(nc);
+    CUDA_OK(cudaMemcpyAsync(hc.data(), C, nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(hr.data(), R, nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    double e = 0;
+    for (int n = 0; n < N; n++)
+      for (int m = 0; m < M; m++) e = std::max(e, std::fabs(hc[(int64_t)n * ldc + m] - hr[(int64_t)n * ldc + m]));
+    *maxerr = e;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  ctx->free(A); ctx->free(B); ctx->free(C); ctx->free(R);
 }
 
 // =================================================================================================
@@ -415,21 +655,6 @@ void fetch_scalars(Ctx* ctx, int n) {
 // =================================================================================================
 // misc elementwise kernels
 // =================================================================================================
-__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-struct BlkDesc { int64_t off; int64_t st[MAXR]; int d[MAXR]; int r; uint64_t key; };
-__global__ void fill_random_kernel(double* __restrict__ data, BlkDesc b, int64_t n, uint64_t seed) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = e, addr = b.off;
-    for (int k = 0; k < b.r; k++) { addr += (t % b.d[k]) * b.st[k]; t /= b.d[k]; }
-    uint64_t u = splitmix64(splitmix64(seed ^ (b.key * 0xD1342543DE82EF95ull)) + (uint64_t)e);
-    data[addr] = (double)(u >> 11) * (2.0 / 9007199254740992.0) - 1.0;   // uniform [-1, 1), 53 bits
-  }
-}
 void fill_random(Ctx* ctx, Tensor& t, uint64_t seed) {
   for (auto& b : t.blocks) {
     BlkDesc d;

@@ -126,6 +126,27 @@ class Context:
     def sync(self):
         check(self.lib.tnl_ctx_sync(self.h), self.h)
 
+    # ---- multi-GPU (one process per GPU)
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        check(self.lib.tnl_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        check(self.lib.tnl_comm_init(self.h, uid, rank, world), self.h)
+
+    def comm_destroy(self):
+        check(self.lib.tnl_comm_destroy(self.h), self.h)
+
+    def gemm_selftest(self, M, N, K, transA=False, transB=False, variant=0, reps=1, verify=True):
+        ms, err = C.c_double(), C.c_double()
+        check(self.lib.tnl_gemm_selftest(self.h, M, N, K, int(transA), int(transB), variant, reps, int(verify),
+                                         C.byref(ms), C.byref(err)), self.h)
+        return ms.value, err.value
+
+    def set_gemm_variant(self, v: int):
+        check(self.lib.tnl_set_gemm_variant(self.h, v), self.h)
+
     def profile_gemm(self, enable: bool):
         check(self.lib.tnl_profile_gemm(self.h, 1 if enable else 0), self.h)
 

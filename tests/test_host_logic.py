@@ -88,3 +88,34 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".hpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_shard_ranges_tile_every_sector_exactly():
+    """Multi-GPU partition of the right link (tnl_shard_range): for every (dim, world) the per-rank ranges are
+    contiguous, disjoint and cover [0, dim); remainders rotate with the sector number so small sectors spread."""
+    import ctypes as C
+    lib = T.load()
+    for world in (1, 2, 3, 4, 8):
+        for dim in (0, 1, 2, 7, 8, 11, 88, 385, 935, 1254):
+            for sector in range(5):
+                seen = []
+                for rank in range(world):
+                    st, cnt = C.c_int32(), C.c_int32()
+                    assert lib.tnl_shard_range(dim, world, sector, rank, C.byref(st), C.byref(cnt)) == 0
+                    assert abs(cnt.value - dim / world) < 1
+                    seen.append((st.value, cnt.value))
+                seen.sort()
+                pos = 0
+                for st, cnt in seen:
+                    assert st == pos
+                    pos += cnt
+                assert pos == dim
+        # dim-1 sectors land on different ranks for different sector numbers
+        owners = set()
+        for sector in range(world):
+            for rank in range(world):
+                st, cnt = C.c_int32(), C.c_int32()
+                lib.tnl_shard_range(1, world, sector, rank, C.byref(st), C.byref(cnt))
+                if cnt.value:
+                    owners.add(rank)
+        assert len(owners) == world

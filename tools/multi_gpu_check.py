@@ -1,0 +1,54 @@
+"""Sharded H_eff apply / Lanczos across ranks vs the CPU oracle.  Launch:
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, ".")
+import tennetlib.jl_b200 as T
+from oracle import blocksparse as ob, dmrg as od, krylov as ok, models as om
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ctx = T.Context(local)
+uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    uid.copy_(torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8))
+dist.broadcast(uid, 0)
+ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+ok_all = True
+for kind, N, chi, pos in (("S=1", 8, 40, 4), ("S=1/2", 10, 24, 1), ("S=1", 6, 300, 3)):
+    sites = om.siteinds(kind, N)
+    H = om.heisenberg_mpo(sites)
+    qn, dm = om.gaussian_link_sectors(chi, 1.3, 4, step=2 if kind == "S=1" else 1)
+    mps = od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(3)))
+    od.orthogonalize(mps, pos)
+    env_o = od.StateEnvs(mps, H)
+    env_o.set_nsite(2); env_o.position(pos)
+    phi_o = ob.contract(env_o.psi[pos], env_o.psi[pos + 1])
+    phi_o = phi_o.scale(1 / phi_o.norm())
+    Hv_o = env_o.product(phi_o)
+    e_o, v_o, info = ok.eigsolve_lanczos(env_o, phi_o)
+    env_d = T.StateEnvs(ctx, mps.t, H, llim=pos - 1, rlim=pos + 1)
+    env_d.set_nsite(2)
+    phi_d = env_d.make_phi(pos); env_d.position(pos)
+    phi_d.scale_(1 / phi_d.norm())
+    Hv_d = env_d.product(phi_d)
+    err = np.abs(Hv_d.to_host().to_dense() - Hv_o.to_dense()).max() / np.abs(Hv_o.to_dense()).max()
+    e_d, _ = T.eig_solver(env_d, phi_d)
+    good = err < 1e-12 and abs(e_d - e_o) < 1e-10 * abs(e_o)
+    ok_all &= good
+    print(f"rank {rank}/{world} {kind} N={N} chi={chi} pos={pos}: apply err {err:.2e}  E dev {e_d:.12f} oracle {e_o:.12f} "
+          f"local flops {env_d.apply_flops():.0f} {'OK' if good else 'FAIL'}", flush=True)
+t = torch.tensor([1.0 if ok_all else 0.0], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("MULTI-GPU CHECK", "PASSED" if t.item() == 1.0 else "FAILED", flush=True)
+ctx.comm_destroy()
+dist.destroy_process_group()
+sys.exit(0 if t.item() == 1.0 else 1)
