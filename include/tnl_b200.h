@@ -116,6 +116,13 @@ int tnl_replacebond(tnl_env_t env, int32_t pos, tnl_tensor_t phi, int32_t ortho_
                     double cutoff, double noise, int32_t normalize, int32_t which_decomp, double* truncerr,
                     double* eigs, int64_t cap, int64_t* neigs);
 
+/* one-site update tail, src/mps/update_site.jl:158-186: U,S,V = svd(phi, uinds; maxdim, mindim, cutoff);
+ * normalize!(S); psi[pos] = U; psi[posnext] = (S*V)*psi[posnext]  (posnext = pos+1 for ortho left, pos-1 for right).
+ * svd_alg: 0 = gesvd, 1 = gesvdp, 2 = guarded Gram-eigh. */
+int tnl_svd_split(tnl_env_t env, int32_t pos, tnl_tensor_t phi, int32_t ortho_left, int64_t maxdim, int64_t mindim,
+                  double cutoff, int32_t normalize, int32_t svd_alg, double* truncerr, double* eigs, int64_t cap,
+                  int64_t* neigs);
+
 #ifdef __cplusplus
 }
 #endif

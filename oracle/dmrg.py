@@ -174,8 +174,64 @@ def _update_two_site(sysenv: StateEnvs, solver, pos, ortho, time_step, normalize
     return energy, spec.truncerr, spec.eigs
 
 
+def _update_one_site(sysenv: StateEnvs, solver, pos, ortho, time_step, normalize, maxdim, mindim, cutoff,
+                     svd_alg, noise, reverse_step, **kw):
+    """src/mps/update_site.jl:94-190 (DMRG branch; the TDVP reverse step is not restated)."""
+    psi = sysenv.psi
+    assert 0 < pos <= len(sysenv)
+    assert psi.orthocenter() == pos
+    nsite = 1
+    sysenv.set_nsite(nsite)
+    phi = psi[pos]
+    sysenv.position(pos)
+    energy, phi = solver(sysenv, phi, time_step, **kw)
+    if normalize:
+        phi = phi.scale(1.0 / phi.norm())
+    if np.isnan(energy):
+        energy = float(np.real(inner(phi, sysenv.PH(phi))))
+    truncerr, eigs = 0.0, np.zeros(0)
+    if halfsweep_done(len(sysenv), pos, nsite, ortho):
+        psi[pos] = phi
+        return energy, truncerr, eigs
+    posnext = pos + 1 if ortho == "left" else pos - 1
+    pos0 = pos if ortho == "left" else pos - 1
+    if abs(noise) > FLOAT64_THRESHOLD:
+        phi2 = contract(phi, psi[posnext]) if ortho == "left" else contract(psi[posnext], phi)
+        psi[pos] = phi                               # keeps the index bookkeeping of psi[pos0] for replacebond
+        sysenv.set_nsite(2)
+        sysenv.position(pos0)
+        d = drho_matrices(sysenv.PH.noiseterm(phi2, ortho), noise)
+        drho = d if ortho == "left" else {tuple(-x for x in q): M for q, M in d.items()}
+        spec = replacebond(psi, pos0, phi2, maxdim=maxdim, mindim=mindim, cutoff=cutoff, eigen_perturbation=drho,
+                           ortho=ortho, normalize=normalize, which_decomp=None, svd_alg=svd_alg)
+        sysenv.set_nsite(1)
+        return energy, spec.truncerr, spec.eigs
+    if reverse_step:
+        raise NotImplementedError("TDVP reverse step: SURVEY.md section 8 row a7")
+    nxt = psi[posnext]
+    uinds = [ix for ix in phi.inds if ix not in nxt.inds]
+    if ortho == "left":
+        U, R, spec, u = factorize(phi, uinds, ortho="left", maxdim=maxdim, mindim=mindim, cutoff=cutoff,
+                                  which_decomp="svd", tags=psi[pos].inds[2].tags)           # U, S*V
+        if normalize:
+            R = R.scale(1.0 / R.norm())                                                    # normalize!(S)
+        psi[pos] = U
+        psi[posnext] = contract(R, nxt)
+        psi.llim, psi.rlim = pos, pos + 2
+    else:
+        left = [ix for ix in phi.inds if ix not in uinds]
+        L, V, spec, u = factorize(phi, left, ortho="right", maxdim=maxdim, mindim=mindim, cutoff=cutoff,
+                                  which_decomp="svd", tags=psi[pos].inds[0].tags)           # U*S, V
+        if normalize:
+            L = L.scale(1.0 / L.norm())
+        psi[pos] = V
+        psi[posnext] = contract(nxt, L)
+        psi.llim, psi.rlim = pos - 2, pos
+    return energy, spec.truncerr, spec.eigs
+
+
 def update_position(sysenv: StateEnvs, solver, pos, nsite, ortho, **kw):
-    """src/mps/update_site.jl:231-277 (two-site branch; one-site is a section 8(f) 'next' row)."""
+    """src/mps/update_site.jl:231-277."""
     time_step = kw.get("time_step", None)
     normalize = kw.get("normalize", True)
     maxdim = kw.get("maxdim", None)
@@ -191,6 +247,9 @@ def update_position(sysenv: StateEnvs, solver, pos, nsite, ortho, **kw):
                                                    "svd_alg", "noise", "reverse_step")}
     if nsite == 2:
         return _update_two_site(sysenv, solver, pos, ortho, time_step, normalize, maxdim, mindim, cutoff,
+                                svd_alg, noise, reverse_step, **kw2)
+    if nsite == 1:
+        return _update_one_site(sysenv, solver, pos, ortho, time_step, normalize, maxdim, mindim, cutoff,
                                 svd_alg, noise, reverse_step, **kw2)
     raise NotImplementedError(f"`update_position()` with `nsite={nsite}` not implemented !!")
 
@@ -225,10 +284,15 @@ def fullsweep(sysenv: StateEnvs, solver, nsite: int, swdata: SweepData, **kw):
     for bond in range(1, N):
         energy, err, _ = update_position(sysenv, solver, bond, nsite, "left", **kw)
         maxtruncerr = max(err, maxtruncerr)
+        if nsite == 1 and bond == N - 1:
+            energy, _, _ = update_position(sysenv, solver, bond + 1, nsite, "left", **kw)
     for bond in range(N - 1, 0, -1):
-        energy, err, eigs = update_position(sysenv, solver, bond, nsite, "right", **kw)
+        site = bond + 1 if nsite == 1 else bond
+        energy, err, eigs = update_position(sysenv, solver, site, nsite, "right", **kw)
         lasteigs[bond - 1] = eigs
         maxtruncerr = max(err, maxtruncerr)
+        if nsite == 1 and bond == 1:
+            energy, _, _ = update_position(sysenv, solver, bond, nsite, "right", **kw)
     swdata.lasteigs = lasteigs
     swdata.maxchi.append(max(A.inds[2].dim for A in psi.t[:-1]))
     swdata.energy.append(energy)
@@ -289,4 +353,10 @@ def dmrg_(sysenv: StateEnvs, params: DMRGParams, nsite: int, **kw) -> SweepData:
 def dmrg2(psi0: MPS, H, params: DMRGParams, **kw):
     sysenv = StateEnvs(psi0, H)
     sw = dmrg_(sysenv, params, 2, **kw)
+    return sw.energy[-1], sysenv.psi, sw
+
+
+def dmrg1(psi0: MPS, H, params: DMRGParams, **kw):
+    sysenv = StateEnvs(psi0, H)
+    sw = dmrg_(sysenv, params, 1, **kw)
     return sw.energy[-1], sysenv.psi, sw

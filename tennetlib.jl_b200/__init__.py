@@ -4,7 +4,7 @@ Product code only: CUDA kernels + C ABI in `csrc/` (libtnl_b200.so) and the host
 interface (`StateEnvs`, `eig_solver`, `update_position`, `fullsweep`, `DMRGParams`, `dmrg_`/`dmrg2`).
 Nothing here imports `oracle/`; there is no CPU fallback."""
 from ._lib import EXPORTED, TnlError, load, so_path
-from .dmrg import DMRGParams, dmrg, dmrg2, dmrg_
+from .dmrg import DMRGParams, dmrg, dmrg1, dmrg2, dmrg_
 from .solver import eig_solver, exp_solver
 from .state_envs import StateEnvs
 from .sweep import SweepData, fullsweep
@@ -12,5 +12,5 @@ from .tensor import Context, DeviceTensor, HostTensor, Index
 from .update_site import halfsweep_done, update_position
 
 __all__ = ["Context", "DeviceTensor", "HostTensor", "Index", "StateEnvs", "eig_solver", "exp_solver",
-           "update_position", "halfsweep_done", "fullsweep", "SweepData", "DMRGParams", "dmrg_", "dmrg", "dmrg2",
+           "update_position", "halfsweep_done", "fullsweep", "SweepData", "DMRGParams", "dmrg_", "dmrg", "dmrg1", "dmrg2",
            "load", "so_path", "TnlError", "EXPORTED"]

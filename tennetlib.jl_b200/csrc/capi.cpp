@@ -338,4 +338,21 @@ int tnl_replacebond(tnl_env_t e, int32_t pos, tnl_tensor_t phi, int32_t ortho_le
   });
 }
 
+int tnl_svd_split(tnl_env_t e, int32_t pos, tnl_tensor_t phi, int32_t ortho_left, int64_t maxdim, int64_t mindim,
+                  double cutoff, int32_t normalize, int32_t svd_alg, double* truncerr, double* eigs, int64_t cap,
+                  int64_t* neigs) {
+  return guard(e->env.ctx, [&] {
+    FactorizeParams prm;
+    prm.ortho_left = ortho_left;
+    prm.maxdim = maxdim <= 0 ? INT64_MAX : maxdim;
+    prm.mindim = mindim;
+    prm.cutoff = cutoff;
+    prm.svd_alg = svd_alg;
+    FactorizeResult f = e->env.svd_split(pos, *phi->t, prm, normalize != 0);
+    *truncerr = f.truncerr;
+    *neigs = (int64_t)f.eigs.size();
+    for (int64_t i = 0; i < std::min<int64_t>(cap, *neigs); i++) eigs[i] = f.eigs[i];
+  });
+}
+
 }  // extern "C"

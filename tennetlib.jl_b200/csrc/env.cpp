@@ -654,6 +654,50 @@ FactorizeResult Env::replacebond(int pos, const Tensor& phi, FactorizeParams prm
   return f;
 }
 
+// One-site split (src/mps/update_site.jl:158-186 without the TDVP reverse step):
+//   U, S, V = svd(phi, uinds; maxdim, mindim, cutoff); normalize!(S); psi[pos] = U; psi[posnext] = (S*V) * psi[posnext]
+FactorizeResult Env::svd_split(int pos, const Tensor& phi, FactorizeParams prm, bool normalize) {
+  TNL_CHECK(pos >= 1 && pos <= N && phi.rank() == 3, "svd_split: bad site / tensor");
+  prm.which = 1;                                    // `svd`, not `factorize`: always the SVD path
+  prm.noise = 0.0;
+  const bool left = prm.ortho_left != 0;
+  TNL_CHECK(left ? pos < N : pos > 1, "svd_split: no neighbour in that direction");
+  TensorP T = relayout(ctx, phi, left ? 2 : 1);
+  FactorizeResult f = factorize(ctx, *T, prm);
+  Tensor& carry = left ? *f.R : *f.L;               // S*V (m, r)  or  U*S (l, m)
+  if (normalize) {
+    vec_dot(ctx, carry.d, carry.d, carry.nelem, 0);
+    fetch_scalars(ctx, 1);
+    double nrm = std::sqrt(ctx->h_scalars[0]);
+    TNL_CHECK(nrm > 0, "svd_split: zero norm");
+    vec_scale(ctx, carry.d, carry.nelem, 1.0 / nrm);
+  }
+  if (left) {
+    A[pos - 1] = f.L;
+    TensorP nx = as_nrow(ctx, A[pos], 1);
+    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{f.R->inds[0], nx->inds[1], nx->inds[2]}, 1);
+    auto g = plan_gemm(*f.R, false, *nx, false, *An);
+    run_gemm(ctx, *g, f.R->d, nx->d, An->d);
+    ctx->sync();
+    A[pos] = An;
+    lpos = std::min(lpos, pos - 1);
+    rpos = std::max(rpos, pos + 2);
+  } else {
+    A[pos - 1] = f.R;
+    TensorP pv = as_nrow(ctx, A[pos - 2], 2);
+    TensorP Cm = as_nrow(ctx, f.L, 1);
+    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{pv->inds[0], pv->inds[1], f.L->inds[1]}, 2);
+    auto g = plan_gemm(*pv, false, *Cm, false, *An);
+    run_gemm(ctx, *g, pv->d, Cm->d, An->d);
+    ctx->sync();
+    A[pos - 2] = An;
+    lpos = std::min(lpos, pos - 2);
+    rpos = std::max(rpos, pos + 1);
+  }
+  ap.reset();
+  return f;
+}
+
 // ITensorMPS `orthogonalize!`: QR gauge moves of the centre from site `from` to site `to` (no truncation).
 // move_center(N, 1) right-canonicalises an arbitrary MPS (sweep.jl:100-102).
 void Env::move_center(int from, int to) {

@@ -71,6 +71,7 @@ class Env {
   LanczosResult eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter, bool eager);
   double expectation(const Tensor& phi);
   FactorizeResult replacebond(int pos, const Tensor& phi, FactorizeParams prm, bool normalize);
+  FactorizeResult svd_split(int pos, const Tensor& phi, FactorizeParams prm, bool normalize);
   void move_center(int from, int to);                   // QR gauge moves, ITensorMPS orthogonalize!
   double apply_flops() const;                           // algorithmic flops of one H_eff apply at the current position
 

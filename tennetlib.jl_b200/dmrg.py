@@ -64,3 +64,7 @@ def dmrg(ctx, psi0, H, params: DMRGParams, nsite: int, **kwargs):
 
 def dmrg2(ctx, psi0, H, params: DMRGParams, **kwargs):
     return dmrg(ctx, psi0, H, params, 2, **kwargs)
+
+
+def dmrg1(ctx, psi0, H, params: DMRGParams, **kwargs):
+    return dmrg(ctx, psi0, H, params, 1, **kwargs)

@@ -92,6 +92,28 @@ class StateEnvs:
         check(self.ctx.lib.tnl_env_get_state(self.h, j, C.byref(h)), self.ctx.h)
         return DeviceTensor(self.ctx, h)
 
+    def set_site_tensor(self, j: int, t: DeviceTensor):
+        """sysenv.psi[j] = t (shares the device tensor; environments that contain site j are invalidated)."""
+        check(self.ctx.lib.tnl_env_set_state(self.h, j, t.h), self.ctx.h)
+
+    def svd_split(self, pos: int, phi: DeviceTensor, *, maxdim, mindim, cutoff, ortho, normalize,
+                  svd_alg="divide_and_conquer"):
+        """One-site tail (update_site.jl:158-186): psi[pos] = U, psi[posnext] = (S*V)*psi[posnext]."""
+        cap = 1 << 16
+        eigs = np.zeros(cap)
+        truncerr = C.c_double()
+        neigs = C.c_int64()
+        md = 0 if maxdim is None or maxdim >= (1 << 62) else int(maxdim)
+        alg = {"divide_and_conquer": 0, "qr_iteration": 0, "recursive": 0, "polar": 1, "gram": 2}[svd_alg]
+        check(self.ctx.lib.tnl_svd_split(self.h, pos, phi.h, 1 if ortho == "left" else 0, md, int(mindim), float(cutoff),
+                                         1 if normalize else 0, alg, C.byref(truncerr), eigs.ctypes.data, cap,
+                                         C.byref(neigs)), self.ctx.h)
+        if ortho == "left":
+            self.llim, self.rlim = pos, pos + 2                  # setleftlim!(psi, pos)
+        else:
+            self.llim, self.rlim = pos - 2, pos                  # setrightlim!(psi, pos)
+        return truncerr.value, eigs[:min(neigs.value, cap)].copy()
+
     def getpsi(self) -> List[HostTensor]:
         """getpsi (state_envs.jl:36): host copy of the MPS."""
         return [self.site_tensor(j).to_host() for j in range(1, self.N + 1)]

@@ -41,12 +41,17 @@ def fullsweep(sysenv, solver, nsite: int, swdata: SweepData, **kwargs):
         maxtruncerr = max(err, maxtruncerr)
         if outputlevel > 1:
             print(f"At left sweep {swdata.sweepcount} bond {bond} => Energy {energy}, Err {err:.2g}", flush=True)
+        if nsite == 1 and bond == N - 1:
+            energy, _, _ = update_position(sysenv, solver, bond + 1, nsite, "left", **kwargs)
     for bond in range(N - 1, 0, -1):
-        energy, err, eigs = update_position(sysenv, solver, bond, nsite, "right", **kwargs)
+        site = bond + 1 if nsite == 1 else bond
+        energy, err, eigs = update_position(sysenv, solver, site, nsite, "right", **kwargs)
         lasteigs[bond - 1] = eigs
         maxtruncerr = max(err, maxtruncerr)
         if outputlevel > 1:
             print(f"At right sweep {swdata.sweepcount} bond {bond} => Energy {energy}, Err {err:.2g}", flush=True)
+        if nsite == 1 and bond == 1:
+            energy, _, _ = update_position(sysenv, solver, bond, nsite, "right", **kwargs)
     sw_time = time.time() - t0
     swdata.lasteigs = lasteigs
     swdata.maxchi.append(max(sysenv.linkdims()))

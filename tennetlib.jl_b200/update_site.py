@@ -3,6 +3,8 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
+
 FLOAT64_THRESHOLD = 1e-15      # src/base/global_variables.jl:10-26
 
 
@@ -42,6 +44,45 @@ def _update_two_site(sysenv, solver, pos, ortho, time_step, normalize, maxdim, m
     return energy, truncerr, eigs
 
 
+def _update_one_site(sysenv, solver, pos, ortho, time_step, normalize, maxdim, mindim, cutoff, svd_alg, noise,
+                     reverse_step, **kwargs):
+    """src/mps/update_site.jl:94-190 (DMRG branches: noise -> two-site replacebond!, else svd split)."""
+    assert 0 < pos <= len(sysenv)
+    assert sysenv.orthocenter() == pos
+    nsite = 1
+    sysenv.set_nsite(nsite)
+    phi = sysenv.site_tensor(pos).copy()
+    with sysenv.phase("position"):
+        sysenv.position(pos)
+    with sysenv.phase("solver"):
+        energy, phi = solver(sysenv, phi, time_step, **kwargs)
+    if normalize:
+        phi.scale_(1.0 / phi.norm())
+    if isinstance(energy, float) and math.isnan(energy):
+        energy = sysenv.expectation(phi)
+    truncerr, eigs = 0.0, np.zeros(0)
+    if halfsweep_done(len(sysenv), pos, nsite, ortho):
+        sysenv.set_site_tensor(pos, phi)
+        return energy, truncerr, eigs
+    pos0 = pos if ortho == "left" else pos - 1
+    if abs(noise) > FLOAT64_THRESHOLD:
+        sysenv.set_site_tensor(pos, phi)             # phi *= psi[posnext]  is formed on the device below
+        sysenv.set_nsite(nsite + 1)
+        phi2 = sysenv.make_phi(pos0)
+        sysenv.position(pos0)
+        with sysenv.phase("replacebond"):
+            truncerr, eigs = sysenv.replacebond(pos0, phi2, maxdim=maxdim, mindim=mindim, cutoff=cutoff, noise=noise,
+                                                ortho=ortho, normalize=normalize, which_decomp=None, svd_alg=svd_alg)
+        sysenv.set_nsite(nsite)
+        return energy, truncerr, eigs
+    if reverse_step:
+        raise NotImplementedError("TDVP reverse step needs exp_solver (later row of the scope table)")
+    with sysenv.phase("replacebond"):
+        truncerr, eigs = sysenv.svd_split(pos, phi, maxdim=maxdim, mindim=mindim, cutoff=cutoff, ortho=ortho,
+                                          normalize=normalize, svd_alg=svd_alg)
+    return energy, truncerr, eigs
+
+
 def update_position(sysenv, solver, pos: int, nsite: int, ortho: str, **kwargs):
     time_step = kwargs.get("time_step", None)
     normalize = kwargs.get("normalize", True)
@@ -58,5 +99,8 @@ def update_position(sysenv, solver, pos: int, nsite: int, ortho: str, **kwargs):
                                                           "svd_alg", "noise", "reverse_step")}
     if nsite == 2:
         return _update_two_site(sysenv, solver, pos, ortho, time_step, normalize, maxdim, mindim, cutoff, svd_alg,
+                                noise, reverse_step, **rest)
+    if nsite == 1:
+        return _update_one_site(sysenv, solver, pos, ortho, time_step, normalize, maxdim, mindim, cutoff, svd_alg,
                                 noise, reverse_step, **rest)
     raise NotImplementedError(f"`update_position()` with `nsite={nsite}` not implemented !!")

@@ -15,11 +15,11 @@ from oracle import blocksparse as ob, dmrg as od, krylov as ok, models as om  # 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
-def case_dmrg(kind, N, params, name):
+def case_dmrg(kind, N, params, name, nsite=2):
     sites = om.siteinds(kind, N)
     H = om.heisenberg_mpo(sites)
     psi0 = od.MPS(om.neel_mps(sites))
-    e, psi, sw = od.dmrg2(psi0, H, od.DMRGParams(**params))
+    e, psi, sw = (od.dmrg2 if nsite == 2 else od.dmrg1)(psi0, H, od.DMRGParams(**params))
     return dict(name=name, kind=kind, N=N, params=params, energy=sw.energy, maxchi=sw.maxchi,
                 maxtruncerr=sw.maxtruncerr, entropy=sw.entropy,
                 linkdims=[A.inds[2].dim for A in psi.t[:-1]])
@@ -62,6 +62,9 @@ if __name__ == "__main__":
         dmrg=[case_dmrg("S=1/2", 12, ref, "reference test_MPS_DMRG.jl parameters"),
               case_dmrg("S=1/2", 12, dict(nsweeps=[6], maxdim=[64], cutoff=1e-14), "noise-free, exact bond dimension"),
               case_dmrg("S=1", 8, dict(nsweeps=[3, 4], maxdim=[30, 200], cutoff=1e-14, noise=[1e-4, 0.0]), "S=1 N=8")],
+        dmrg1=[case_dmrg("S=1/2", 12, ref, "one-site DMRG, reference test parameters (dmrg_1, nsite=1)", nsite=1),
+               case_dmrg("S=1", 8, dict(nsweeps=[4, 3], maxdim=[40, 40], cutoff=[1e-14, 0.0], noise=[1e-3, 0.0]),
+                         "one-site S=1 N=8, noise then noise-free svd split", nsite=1)],
         bond=[case_bond("S=1", 8, 30, 3, 4), case_bond("S=1/2", 10, 24, 5, 5)],
         ed=dict(S12_N12=-5.1420906328405, S1_N8=-10.1246372223589, S12_N20=-8.6824733343990))
     json.dump(g, open(os.path.join(OUT, "oracle_golden.json"), "w"), indent=1)

@@ -220,6 +220,20 @@ def test_dmrg_matches_oracle_fixture_and_ed(ctx, k):
     assert e > ed - 1e-11 and e - ed < 1e-8
 
 
+@pytest.mark.parametrize("k", [0, 1])
+def test_one_site_dmrg_matches_oracle_fixture(ctx, k):
+    """`dmrg1` (src/mps/dmrg.jl:311-320 -> _update_one_site!): noise branch (two-site replacebond!) and svd split."""
+    T, ob, od, ok, om, op = _imports()
+    g = G["dmrg1"][k]
+    sites = om.siteinds(g["kind"], g["N"])
+    H = om.heisenberg_mpo(sites)
+    e, env, sw = T.dmrg1(ctx, om.neel_mps(sites), H, T.DMRGParams(**g["params"]), outputlevel=0)
+    assert sw.maxchi == g["maxchi"] and env.linkdims() == g["linkdims"]
+    noisy = np.array([n > 0 for n in _noise_per_sweep(g["params"])])
+    de = np.abs(np.array(sw.energy) - np.array(g["energy"]))
+    assert de[~noisy].max() < 1e-10 * abs(g["energy"][-1]) and de.max() < 1e-7 * abs(g["energy"][-1])
+
+
 def _noise_per_sweep(p):
     out = []
     n = len(p["nsweeps"])
