@@ -93,6 +93,9 @@ int tnl_env_set_site_op(tnl_env_t env, int32_t site, int32_t nq, const tnl_index
 /* MPS tensor A_site(l, s, r); the env shares the tensor (no copy) */
 int tnl_env_set_state(tnl_env_t env, int32_t site, tnl_tensor_t a);
 int tnl_env_get_state(tnl_env_t env, int32_t site, tnl_tensor_t* out); /* getpsi, state_envs.jl:36 */
+/* StateEnvs(psi, H, Ms; weight): add weight*|M><M| for one fixed MPS M (ProjMPO_MPS2 / ProjMPS2,
+ * src/mps/state_envs.jl:86-103, src/mps/projmpo_mps2.jl:94-101, src/mps/projmps2.jl:77-224); call once per M */
+int tnl_env_add_penalty(tnl_env_t env, double weight, int32_t nsites, const tnl_tensor_t* tensors);
 int tnl_env_set_nsite(tnl_env_t env, int32_t nsite);                   /* set_nsite!, state_envs.jl:352-355 */
 int tnl_env_position(tnl_env_t env, int32_t pos);                      /* position!, state_envs.jl:364-367 */
 /* orthogonalize!: QR gauge moves of the orthogonality centre from site `from` to site `to`;

@@ -18,7 +18,7 @@ import numpy as np
 
 from .blocksparse import BSTensor, contract, factorize, inner
 from .krylov import eigsolve_lanczos
-from .projmpo import ProjMPO, drho_matrices
+from .projmpo import ProjMPO, ProjMPO_MPS2, drho_matrices
 
 FLOAT64_THRESHOLD = 1e-15          # src/base/global_variables.jl:10-26
 
@@ -105,9 +105,10 @@ def replacebond(psi: MPS, b: int, phi: BSTensor, *, maxdim, mindim, cutoff, eige
 class StateEnvs:
     """src/mps/state_envs.jl:18-27 with PH = ProjMPO (constructor :54-60 copies psi)."""
 
-    def __init__(self, psi: MPS, H: Sequence[BSTensor]):
+    def __init__(self, psi: MPS, H: Sequence[BSTensor], Ms=None, weight: float = -1.0):
         self.psi = psi.copy()
-        self.PH = ProjMPO(H)
+        # StateEnvs(psi, H, Ms; weight)  (src/mps/state_envs.jl:86-103) when penalised states are given
+        self.PH = ProjMPO(H) if not Ms else ProjMPO_MPS2(H, [m.t if isinstance(m, MPS) else m for m in Ms], weight)
 
     def __len__(self):
         return len(self.psi)
@@ -350,8 +351,8 @@ def dmrg_(sysenv: StateEnvs, params: DMRGParams, nsite: int, **kw) -> SweepData:
     return swdata
 
 
-def dmrg2(psi0: MPS, H, params: DMRGParams, **kw):
-    sysenv = StateEnvs(psi0, H)
+def dmrg2(psi0: MPS, H, params: DMRGParams, Ms=None, **kw):
+    sysenv = StateEnvs(psi0, H, Ms, kw.pop("weight", -1.0))
     sw = dmrg_(sysenv, params, 2, **kw)
     return sw.energy[-1], sysenv.psi, sw
 

@@ -132,3 +132,115 @@ def drho_matrices(drho: BSTensor, scale: float):
     primed = [ix for ix in drho.inds if ix.plev > 0]
     _, groups, _, _, _ = matricize(drho, primed)
     return {q: scale * M for q, (M, _, _) in groups.items()}
+
+
+class ProjMPS2:
+    """Overlap environments of a fixed MPS `M` with the optimised state (src/mps/projmps2.jl:26-32,77-224):
+    L_j = L_{j-1} * psi[j] * dag(prime(M[j], "Link")); product(v) = <m|v> |m> with
+    dag(m) = L * dag(M_j') * dag(M_{j+1}') * R  (`proj_mps`, :182-196)."""
+
+    def __init__(self, M: Sequence[BSTensor]):
+        self.M = list(M)
+        self.N = len(M)
+        self.lpos, self.rpos, self.nsite = 0, self.N + 1, 2
+        self.LR: List[BSTensor | None] = [None] * self.N
+        self._Ledge = self._Redge = None
+
+    def set_nsite(self, n):
+        self.nsite = n
+
+    def site_range(self):
+        return range(self.lpos + 1, self.rpos)
+
+    def _mdag(self, j):          # dag(prime(M[j], "Link")) : links primed, site index untouched
+        Mj = self.M[j]
+        return Mj.prime(1, [Mj.inds[0], Mj.inds[2]]).dag()
+
+    def _edges(self, psi):
+        def edge(a, m):
+            return BSTensor([a.copy(dir=-a.dir), m.prime().copy(dir=m.dir)], {(0, 0): np.ones((1, 1))})
+        if self._Ledge is None:
+            self._Ledge = edge(psi[0].inds[0], self.M[0].inds[0])
+            self._Redge = edge(psi[-1].inds[2], self.M[-1].inds[2])
+
+    def lproj(self):
+        return self._Ledge if self.lpos <= 0 else self.LR[self.lpos - 1]
+
+    def rproj(self):
+        return self._Redge if self.rpos >= self.N + 1 else self.LR[self.rpos - 1]
+
+    def position(self, psi, pos):
+        self._edges(psi)
+        k = pos - 1
+        if self.lpos >= k:
+            self.lpos = k
+        else:
+            ll, L = max(self.lpos, 0), self.lproj()
+            while ll < k:
+                L = contract(contract(L, psi[ll]), self._mdag(ll))
+                self.LR[ll] = L
+                ll += 1
+            self.lpos = k
+        k = pos + self.nsite
+        if self.rpos <= k:
+            self.rpos = k
+        else:
+            rl, R = min(self.rpos, self.N + 1), self.rproj()
+            while rl > k:
+                R = contract(contract(R, psi[rl - 2]), self._mdag(rl - 2))
+                self.LR[rl - 2] = R
+                rl -= 1
+            self.rpos = k
+
+    def proj_mps(self) -> BSTensor:
+        m = self.lproj()
+        for j in self.site_range():
+            m = contract(m, self._mdag(j - 1))
+        return contract(m, self.rproj())
+
+    def contract_v(self, v):
+        Mv = contract(v, self.lproj())
+        for j in self.site_range():
+            Mv = contract(Mv, self._mdag(j - 1))
+        return contract(Mv, self.rproj())
+
+    def product(self, v):
+        ov = self.contract_v(v).scalar()
+        return self.proj_mps().dag().scale(ov)
+
+
+class ProjMPO_MPS2:
+    """PH + weight * sum_M |M><M| (src/mps/projmpo_mps2.jl:94-134); noiseterm forwards to PH."""
+
+    def __init__(self, H, Ms, weight: float):
+        if weight <= 0.0:
+            raise ValueError(f"`weight` parameter should be > 0.0 (value passed was `weight={weight}`)")
+        self.PH = ProjMPO(H)
+        self.pm = [ProjMPS2(M) for M in Ms]
+        self.weight = weight
+        self.N = self.PH.N
+
+    @property
+    def nsite(self):
+        return self.PH.nsite
+
+    def set_nsite(self, n):
+        self.PH.set_nsite(n)
+        for p in self.pm:
+            p.set_nsite(n)
+
+    def position(self, psi, pos):
+        self.PH.position(psi, pos)
+        for p in self.pm:
+            p.position(psi, pos)
+
+    def product(self, v):
+        Pv = self.PH.product(v)
+        for p in self.pm:
+            Pv = Pv.add(p.product(v), self.weight)
+        return Pv
+
+    __call__ = product
+
+    def noiseterm(self, phi, ortho):
+        return self.PH.noiseterm(phi, ortho)

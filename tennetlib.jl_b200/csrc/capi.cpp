@@ -268,6 +268,16 @@ int tnl_env_set_site_op(tnl_env_t e, int32_t site, int32_t nq, const tnl_index_t
     e->env.set_site_op(site, hb);
   });
 }
+int tnl_env_add_penalty(tnl_env_t e, double weight, int32_t nsites, const tnl_tensor_t* tensors) {
+  return guard(e->env.ctx, [&] {
+    std::vector<TensorP> M;
+    for (int j = 0; j < nsites; j++) {
+      TNL_CHECK(tensors[j] && tensors[j]->t->rank() == 3, "penalised MPS tensors must be (l, s, r)");
+      M.push_back(tensors[j]->t);
+    }
+    e->env.add_penalty(M, weight);
+  });
+}
 int tnl_env_set_state(tnl_env_t e, int32_t site, tnl_tensor_t a) {
   return guard(e->env.ctx, [&] { e->env.set_state(site, a->t); });
 }

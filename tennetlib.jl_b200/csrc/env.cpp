@@ -119,8 +119,19 @@ void Env::set_state(int site, TensorP a) {
   TNL_CHECK(site >= 1 && site <= N, "site out of range");
   TNL_CHECK(a->rank() == 3, "site tensor must be (l, s, r)");
   A[site - 1] = std::move(a);
-  lpos = std::min(lpos, site - 1);
-  rpos = std::max(rpos, site + 1);
+  invalidate(site, site);
+}
+
+// sites lo..hi of the state changed: environments containing them are stale (watermark semantics of
+// src/mps/projcouplingmodel.jl:123-129,212-218)
+void Env::invalidate(int lo, int hi) {
+  lpos = std::min(lpos, lo - 1);
+  rpos = std::max(rpos, hi + 1);
+  for (auto& p : pens) {
+    p.lpos = std::min(p.lpos, lo - 1);
+    p.rpos = std::max(p.rpos, hi + 1);
+    p.m.reset();
+  }
   ap.reset();
 }
 
@@ -213,6 +224,128 @@ void Env::position(int pos) {
   makeL(pos - 1);
   makeR(pos + nsite);
   if (lp != lpos || rp != rpos) ap.reset();
+  for (auto& p : pens) position_penalty(p, pos);
+}
+
+// ------------------------------------------------------------------------ excited-state penalty
+// ProjMPS2 (src/mps/projmps2.jl:77-124): L_j = L_{j-1} * psi[j] * dag(prime(M[j], "Link")), mirror for R.
+void Env::add_penalty(const std::vector<TensorP>& M, double w) {
+  TNL_CHECK((int)M.size() == N, "penalised MPS has the wrong length");
+  TNL_CHECK(w > 0.0, "`weight` parameter should be > 0.0");
+  Penalty p;
+  p.M = M;
+  p.LR.resize(N);
+  p.rpos = N + 1;
+  pens.push_back(std::move(p));
+  weight = w;
+  ap.reset();
+}
+
+void Env::position_penalty(Penalty& p, int pos) {
+  if (p.dead) return;
+  if (!p.Ledge) {
+    const Index &a0 = A[0]->inds[0], &m0 = p.M[0]->inds[0], &aN = A[N - 1]->inds[2], &mN = p.M[N - 1]->inds[2];
+    p.Ledge = mk(ctx, {with_dir(a0, -a0.dir), with_dir(m0, m0.dir)}, 1);
+    p.Redge = mk(ctx, {with_dir(aN, -aN.dir), with_dir(mN, mN.dir)}, 1);
+    if (p.Ledge->blocks.size() != 1 || p.Redge->blocks.size() != 1) { p.dead = true; return; }
+    set_one(ctx, *p.Ledge);
+    set_one(ctx, *p.Redge);
+  }
+  const int kl = pos - 1, kr = pos + nsite;
+  // left overlap environments
+  if (p.lpos >= kl) {
+    p.lpos = kl;
+  } else {
+    int ll = std::max(p.lpos, 0);
+    TensorP L = ll <= 0 ? p.Ledge : p.LR[ll - 1];
+    while (ll < kl) {
+      TensorP Aq = as_nrow(ctx, A[ll], 1);
+      TensorP Ms = as_nrow(ctx, p.M[ll], 2);
+      auto X = mk(ctx, {L->inds[1], Aq->inds[1], Aq->inds[2]}, 1);                 // (lM, s, r)
+      auto g1 = plan_gemm(*L, true, *Aq, false, *X);
+      run_gemm(ctx, *g1, L->d, Aq->d, X->d);
+      ctx->sync();
+      TensorP X2 = relayout(ctx, *X, 2);
+      const Index& rm = Ms->inds[2];
+      auto Ln = mk(ctx, {X->inds[2], with_dir(rm, -rm.dir)}, 1);                   // (r, rM)
+      auto g2 = plan_gemm(*X2, true, *Ms, false, *Ln, false, /*dagB=*/true);
+      run_gemm(ctx, *g2, X2->d, Ms->d, Ln->d);
+      ctx->sync();
+      p.LR[ll] = Ln;
+      L = Ln;
+      ll++;
+    }
+    p.lpos = kl;
+  }
+  if (p.rpos <= kr) {
+    p.rpos = kr;
+  } else {
+    int rl = std::min(p.rpos, N + 1);
+    TensorP R = rl >= N + 1 ? p.Redge : p.LR[rl - 1];
+    while (rl > kr) {
+      const int j = rl - 2;
+      TensorP As = as_nrow(ctx, A[j], 2);
+      TensorP Mq = as_nrow(ctx, p.M[j], 1);
+      auto Y = mk(ctx, {As->inds[0], As->inds[1], R->inds[1]}, 2);                 // (l, s, rM)
+      auto g1 = plan_gemm(*As, false, *R, false, *Y);
+      run_gemm(ctx, *g1, As->d, R->d, Y->d);
+      ctx->sync();
+      TensorP Y1 = relayout(ctx, *Y, 1);
+      const Index& lm = Mq->inds[0];
+      auto Rn = mk(ctx, {Y->inds[0], with_dir(lm, -lm.dir)}, 1);                   // (l, lM)
+      auto g2 = plan_gemm(*Y1, false, *Mq, true, *Rn, false, /*dagB=*/true);
+      run_gemm(ctx, *g2, Y1->d, Mq->d, Rn->d);
+      ctx->sync();
+      p.LR[j] = Rn;
+      R = Rn;
+      rl--;
+    }
+    p.rpos = kr;
+  }
+  p.m.reset();
+}
+
+// |m> = dag(proj_mps) = dag(L) * M_j * M_{j+1} * dag(R)   (src/mps/projmps2.jl:182-196)
+void Env::build_penalty_vector(Penalty& p, const Tensor& proto) {
+  if (p.dead || p.m) return;
+  TensorP L = p.lpos <= 0 ? p.Ledge : p.LR[p.lpos - 1];
+  TensorP R = p.rpos >= N + 1 ? p.Redge : p.LR[p.rpos - 1];
+  TNL_CHECK(L && R, "penalty environments not positioned");
+  TensorP cur;           // running tensor with indices (l, sites..., link_M) , bipartition before the last index
+  const int first = p.lpos + 1;
+  if (nsite == 0) {
+    auto m = mk(ctx, {with_dir(L->inds[0], -L->inds[0].dir), with_dir(R->inds[0], -R->inds[0].dir)}, 1);
+    auto g = plan_gemm(*L, false, *R, true, *m, true, true);
+    run_gemm(ctx, *g, L->d, R->d, m->d);
+    ctx->sync();
+    p.m = m;
+  } else {
+    TensorP M1 = as_nrow(ctx, p.M[first - 1], 1);
+    auto P1 = mk(ctx, {with_dir(L->inds[0], -L->inds[0].dir), M1->inds[1], M1->inds[2]}, 1);   // (l, s1, mM)
+    auto g1 = plan_gemm(*L, false, *M1, false, *P1, /*dagA=*/true);
+    run_gemm(ctx, *g1, L->d, M1->d, P1->d);
+    ctx->sync();
+    cur = P1;
+    if (nsite == 2) {
+      TensorP P1s = relayout(ctx, *P1, 2);
+      TensorP M2 = as_nrow(ctx, p.M[first], 1);
+      auto P2 = mk(ctx, {P1->inds[0], P1->inds[1], M2->inds[1], M2->inds[2]}, 2);              // (l, s1, s2, rM)
+      auto g2 = plan_gemm(*P1s, false, *M2, false, *P2);
+      run_gemm(ctx, *g2, P1s->d, M2->d, P2->d);
+      ctx->sync();
+      cur = P2;
+    }
+    const int r = cur->rank();
+    TensorP C3 = relayout(ctx, *cur, r - 1);
+    std::vector<Index> mi(cur->inds.begin(), cur->inds.end() - 1);
+    mi.push_back(with_dir(R->inds[0], -R->inds[0].dir));
+    auto m = mk(ctx, mi, r - 1);
+    auto g3 = plan_gemm(*C3, false, *R, true, *m, false, /*dagB=*/true);
+    run_gemm(ctx, *g3, C3->d, R->d, m->d);
+    ctx->sync();
+    p.m = relayout(ctx, *m, 1);
+  }
+  TNL_CHECK(p.m->nelem == proto.nelem, "penalty projector layout differs from the Krylov vector layout");
 }
 
 TensorP Env::make_phi(int pos) {
@@ -359,6 +492,13 @@ void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
   } else {
     run_transform(ctx, *p.x2, p.T1->d, p.T3->d, nullptr);
     run_gemm(ctx, *p.g4, p.T3->d, p.R->d, out.d);
+  }
+  // + weight * sum_M <m|v> |m>   (ProjMPO_MPS2.product)
+  for (auto& pen : pens) {
+    if (pen.dead) continue;
+    build_penalty_vector(pen, proto);
+    vec_dot(ctx, pen.m->d, vin, proto.nelem, 200);
+    vec_axpy_dev(ctx, vout, pen.m->d, proto.nelem, 200, weight);
   }
   ctx->cnt.apply_count += 1;
 }
@@ -650,7 +790,7 @@ FactorizeResult Env::replacebond(int pos, const Tensor& phi, FactorizeParams prm
   }
   A[pos - 1] = f.L;
   A[pos] = f.R;
-  ap.reset();
+  invalidate(pos, pos + 1);
   return f;
 }
 
@@ -680,8 +820,7 @@ FactorizeResult Env::svd_split(int pos, const Tensor& phi, FactorizeParams prm, 
     run_gemm(ctx, *g, f.R->d, nx->d, An->d);
     ctx->sync();
     A[pos] = An;
-    lpos = std::min(lpos, pos - 1);
-    rpos = std::max(rpos, pos + 2);
+    invalidate(pos, pos + 1);
   } else {
     A[pos - 1] = f.R;
     TensorP pv = as_nrow(ctx, A[pos - 2], 2);
@@ -691,10 +830,8 @@ FactorizeResult Env::svd_split(int pos, const Tensor& phi, FactorizeParams prm, 
     run_gemm(ctx, *g, pv->d, Cm->d, An->d);
     ctx->sync();
     A[pos - 2] = An;
-    lpos = std::min(lpos, pos - 2);
-    rpos = std::max(rpos, pos + 1);
+    invalidate(pos - 1, pos);
   }
-  ap.reset();
   return f;
 }
 
@@ -729,10 +866,7 @@ void Env::move_center(int from, int to) {
     ctx->sync();
     A[j] = An;
   }
-  int lo = std::min(from, to), hi = std::max(from, to);
-  lpos = std::min(lpos, lo - 1);
-  rpos = std::max(rpos, hi + 1);
-  ap.reset();
+  invalidate(std::min(from, to), std::max(from, to));
 }
 
 }  // namespace tnl

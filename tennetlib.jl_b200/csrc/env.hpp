@@ -59,6 +59,19 @@ class Env {
   std::vector<TensorP> A;            // site tensors (l, s, r), any nrow
   std::vector<TensorP> LR;           // LR[j] = L_{j+1} (nrow 2) or R_{j+1} (nrow 1), 0-based slot j = site j+1
   TensorP Ledge, Redge;
+  // excited-state penalty  weight * sum_M |M><M|  (ProjMPO_MPS2, src/mps/projmpo_mps2.jl:94-134)
+  struct Penalty {
+    std::vector<TensorP> M;          // fixed MPS tensors (l, s, r)
+    std::vector<TensorP> LR;         // overlap environments (psi link, M link), nrow 1
+    TensorP Ledge, Redge;
+    int lpos = 0, rpos = 0;
+    bool dead = false;               // different total charge: overlap vanishes identically
+    TensorP m;                       // |m> = dag(proj_mps) at the current position, Krylov layout
+  };
+  std::vector<Penalty> pens;
+  double weight = 0.0;
+  void add_penalty(const std::vector<TensorP>& M, double w);
+  void invalidate(int lo, int hi);
 
   Env(Ctx* c, int n) : ctx(c), N(n), lpos(0), rpos(n + 1), Wlr(n), Wrl(n), Wnr(n), Wl(n), Wr(n), A(n), LR(n) {}
 
@@ -85,6 +98,8 @@ class Env {
   void makeL(int k);
   void makeR(int k);
   TensorP noise_tensor(const Tensor& phi, bool left);
+  void position_penalty(Penalty& p, int pos);
+  void build_penalty_vector(Penalty& p, const Tensor& proto);
 };
 
 }  // namespace tnl

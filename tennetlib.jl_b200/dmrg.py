@@ -56,15 +56,17 @@ def dmrg_(sysenv: StateEnvs, params: DMRGParams, nsite: int, **kwargs) -> SweepD
     return swdata
 
 
-def dmrg(ctx, psi0, H, params: DMRGParams, nsite: int, **kwargs):
-    sysenv = StateEnvs(ctx, psi0, H, llim=kwargs.pop("llim", 0), rlim=kwargs.pop("rlim", 2))
+def dmrg(ctx, psi0, H, params: DMRGParams, nsite: int, Ms=None, **kwargs):
+    """dmrg(psi0, H, params, nsite) and dmrg(psi0, H, Ms, params, nsite; weight) (src/mps/dmrg.jl:231-246)."""
+    sysenv = StateEnvs(ctx, psi0, H, llim=kwargs.pop("llim", 0), rlim=kwargs.pop("rlim", 2), Ms=Ms,
+                       weight=kwargs.pop("weight", -1.0))
     swdata = dmrg_(sysenv, params, nsite, **kwargs)
     return swdata.energy[-1], sysenv, swdata
 
 
-def dmrg2(ctx, psi0, H, params: DMRGParams, **kwargs):
-    return dmrg(ctx, psi0, H, params, 2, **kwargs)
+def dmrg2(ctx, psi0, H, params: DMRGParams, Ms=None, **kwargs):
+    return dmrg(ctx, psi0, H, params, 2, Ms=Ms, **kwargs)
 
 
-def dmrg1(ctx, psi0, H, params: DMRGParams, **kwargs):
-    return dmrg(ctx, psi0, H, params, 1, **kwargs)
+def dmrg1(ctx, psi0, H, params: DMRGParams, Ms=None, **kwargs):
+    return dmrg(ctx, psi0, H, params, 1, Ms=Ms, **kwargs)

@@ -17,7 +17,7 @@ class StateEnvs:
     copied on construction (state_envs.jl:59)."""
 
     def __init__(self, ctx: Context, psi: Sequence, H: Sequence, llim: int = 0, rlim: int | None = None,
-                 copy: bool = True):
+                 copy: bool = True, Ms: Sequence | None = None, weight: float = -1.0):
         self.ctx = ctx
         self.profile = False           # when True, per-phase device times are accumulated in phase_ms
         self.phase_ms = {}
@@ -36,6 +36,16 @@ class StateEnvs:
         for j, A in enumerate(psi):
             dt = (A.copy() if copy else A) if isinstance(A, DeviceTensor) else DeviceTensor.from_host(ctx, A, nrow=2)
             check(ctx.lib.tnl_env_set_state(self.h, j + 1, dt.h), ctx.h)
+        # StateEnvs(psi, H, Ms; weight) (state_envs.jl:86-103): penalised states for excited-state DMRG
+        if Ms:
+            if weight <= 0.0:
+                raise ValueError(f"`weight` parameter should be > 0.0 (value passed was `weight={weight}`)")
+            for M in Ms:
+                if len(M) != self.N:
+                    raise ValueError("penalised MPS has the wrong length")
+                dts = [m if isinstance(m, DeviceTensor) else DeviceTensor.from_host(ctx, m, nrow=2) for m in M]
+                arr = (C.c_void_p * self.N)(*[d.h for d in dts])
+                check(ctx.lib.tnl_env_add_penalty(self.h, float(weight), self.N, arr), ctx.h)
         # orthogonality limits of the MPS (ITensorMPS llim / rlim)
         self.llim = llim
         self.rlim = self.N + 1 if rlim is None else rlim

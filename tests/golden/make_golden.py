@@ -25,6 +25,17 @@ def case_dmrg(kind, N, params, name, nsite=2):
                 linkdims=[A.inds[2].dim for A in psi.t[:-1]])
 
 
+def case_excited(kind, N, params, weight):
+    """Reference dmrg_ex test (test/test_MPS_DMRG.jl:68-97): ground state, then first excited state with the
+    penalty weight*|gs><gs| (StateEnvs(psi0, H, [psi_gr]; weight))."""
+    sites = om.siteinds(kind, N)
+    H = om.heisenberg_mpo(sites)
+    psi0 = od.MPS(om.neel_mps(sites))
+    e0, gs, sw0 = od.dmrg2(psi0, H, od.DMRGParams(**params))
+    e1, ex, sw1 = od.dmrg2(psi0, H, od.DMRGParams(**params), Ms=[gs], weight=weight)
+    return dict(kind=kind, N=N, params=params, weight=weight, e0=e0, energy=sw1.energy, maxchi=sw1.maxchi)
+
+
 def case_bond(kind, N, chi, seed, pos):
     """One bond of a seeded random MPS: H_eff apply, Lanczos and truncation invariants."""
     sites = om.siteinds(kind, N)
@@ -65,7 +76,9 @@ if __name__ == "__main__":
         dmrg1=[case_dmrg("S=1/2", 12, ref, "one-site DMRG, reference test parameters (dmrg_1, nsite=1)", nsite=1),
                case_dmrg("S=1", 8, dict(nsweeps=[4, 3], maxdim=[40, 40], cutoff=[1e-14, 0.0], noise=[1e-3, 0.0]),
                          "one-site S=1 N=8, noise then noise-free svd split", nsite=1)],
+        excited=[case_excited("S=1/2", 12, ref, 10.0)],
         bond=[case_bond("S=1", 8, 30, 3, 4), case_bond("S=1/2", 10, 24, 5, 5)],
-        ed=dict(S12_N12=-5.1420906328405, S1_N8=-10.1246372223589, S12_N20=-8.6824733343990))
+        ed=dict(S12_N12=-5.1420906328405, S1_N8=-10.1246372223589, S12_N20=-8.6824733343990,
+                S12_N12_E1=-4.8611479370364))
     json.dump(g, open(os.path.join(OUT, "oracle_golden.json"), "w"), indent=1)
     print("wrote", os.path.join(OUT, "oracle_golden.json"))

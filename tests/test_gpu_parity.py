@@ -234,6 +234,24 @@ def test_one_site_dmrg_matches_oracle_fixture(ctx, k):
     assert de[~noisy].max() < 1e-10 * abs(g["energy"][-1]) and de.max() < 1e-7 * abs(g["energy"][-1])
 
 
+def test_excited_state_dmrg_with_penalty(ctx):
+    """StateEnvs(psi0, H, [psi_gr]; weight=10) (test/test_MPS_DMRG.jl:68-97): ProjMPO_MPS2 on the device."""
+    T, ob, od, ok, om, op = _imports()
+    g = G["excited"][0]
+    sites = om.siteinds(g["kind"], g["N"])
+    H = om.heisenberg_mpo(sites)
+    psi0 = om.neel_mps(sites)
+    e0, env0, sw0 = T.dmrg2(ctx, psi0, H, T.DMRGParams(**g["params"]), outputlevel=0)
+    gs = env0.getpsi()
+    e1, env1, sw1 = T.dmrg2(ctx, psi0, H, T.DMRGParams(**g["params"]), Ms=[gs], weight=g["weight"], outputlevel=0)
+    assert abs(e0 - g["e0"]) < 1e-10 * abs(e0)
+    assert sw1.maxchi == g["maxchi"]
+    assert abs(e1 - g["energy"][-1]) < 1e-8                         # oracle fixture (its own ground state as penalty)
+    assert e1 > G["ed"]["S12_N12_E1"] - 1e-9 and e1 - G["ed"]["S12_N12_E1"] < 1e-6      # exact first excited level
+    with pytest.raises(ValueError):
+        T.StateEnvs(ctx, psi0, H, Ms=[gs], weight=-1.0)
+
+
 def _noise_per_sweep(p):
     out = []
     n = len(p["nsweeps"])

@@ -153,3 +153,27 @@ def test_dmrg_spin1_matches_ed():
     p = od.DMRGParams(nsweeps=[3, 4], maxdim=[30, 200], cutoff=1e-14, noise=[1e-4, 0.0])
     e, psi, sw = od.dmrg2(psi0, H, p)
     assert abs(e - E0_S1_N8) < 1e-10
+
+
+def test_excited_state_penalty_matches_ed():
+    """dmrg_ex of the reference test (weight = 10): converges to E1 of the Sz=0 sector."""
+    e = lowest_energies(12, 1, 2)
+    assert abs(e[1] - (-4.8611479370364)) < 1e-10
+    N = 12
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites)
+    psi0 = od.MPS(om.neel_mps(sites))
+    p = od.DMRGParams(nsweeps=[5], maxdim=[20], cutoff=1e-14, noise=1e-3, noisedecay=2, disable_noise_after=2)
+    e0, gs, _ = od.dmrg2(psi0, H, p)
+    e1, ex, sw = od.dmrg2(psi0, H, p, Ms=[gs], weight=10.0)
+    assert e1 > e[1] - 1e-9 and e1 - e[1] < 1e-6
+
+
+def test_one_site_dmrg_matches_ed():
+    N = 12
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites)
+    env = od.StateEnvs(od.MPS(om.neel_mps(sites)), H)
+    od.dmrg_(env, od.DMRGParams(nsweeps=[4], maxdim=[64], cutoff=1e-14, noise=1e-3, noisedecay=2, disable_noise_after=2), 2)
+    sw = od.dmrg_(env, od.DMRGParams(nsweeps=[2], maxdim=[64], cutoff=0.0), 1)       # docs/src/mps/example_dmrg.md:62-71
+    assert abs(sw.energy[-1] - E0_S12_N12) < 1e-10
