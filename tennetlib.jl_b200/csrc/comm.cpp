@@ -22,6 +22,8 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -40,6 +42,8 @@ static NcclApi& nccl() {
     api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
     api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
     api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.ReduceScatter = (decltype(api.ReduceScatter))sym("ncclReduceScatter");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
   }
   return api;
@@ -83,6 +87,19 @@ void comm_allreduce_sum(Ctx* ctx, double* buf, int64_t n) {
   TNL_CHECK(ctx->nccl_comm, "communicator not initialised");
   NCCL_OK(nccl().AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
   ctx->cnt.allreduce_bytes += 8.0 * n;
+}
+
+// recv[0..n) = sum over ranks of send[rank*n .. rank*n+n)
+void comm_reduce_scatter_sum(Ctx* ctx, const double* send, double* recv, int64_t n) {
+  TNL_CHECK(ctx->nccl_comm, "communicator not initialised");
+  NCCL_OK(nccl().ReduceScatter(send, recv, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  ctx->cnt.allreduce_bytes += 8.0 * n * ctx->world;
+}
+// recv[k*n .. k*n+n) = send of rank k
+void comm_allgather(Ctx* ctx, const double* send, double* recv, int64_t n) {
+  TNL_CHECK(ctx->nccl_comm, "communicator not initialised");
+  NCCL_OK(nccl().AllGather(send, recv, (size_t)n, ncclFloat64, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  ctx->cnt.allreduce_bytes += 8.0 * n * ctx->world;
 }
 
 // contiguous share of a sector of dimension d for `rank` out of `world`; remainders rotate with the sector number

@@ -338,4 +338,47 @@ std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const 
   return plan;
 }
 
+std::unique_ptr<TransformPlan> plan_scatter(const Tensor& X, Tensor& Y, const SliceMap& slice) {
+  auto plan = std::make_unique<TransformPlan>();
+  plan->ctx = Y.ctx;
+  const int r = X.rank(), pos = slice.ypos;
+  TNL_CHECK(r == Y.rank() && pos > 0 && pos < r && r - 1 <= MAXP, "plan_scatter: bad ranks / slice position");
+  int64_t col = 0;
+  for (const Block& xb : X.blocks) {
+    int yc[MAXR];
+    for (int k = 0; k < r; k++) yc[k] = xb.c[k];
+    yc[pos] = slice.orig[xb.c[pos]];
+    int bi = Y.find(yc);
+    TNL_CHECK(bi >= 0, "plan_scatter: block missing in the full tensor");
+    const Block& yb = Y.blocks[bi];
+    XfBlock b{};
+    b.yoff = yb.off + slice.start[xb.c[pos]] * yb.st[pos];
+    b.I = xb.d[0];
+    b.nd0 = b.nd1 = 1;
+    b.yns[0] = b.yns[1] = 0;
+    int64_t ncol = 1;
+    XfContrib c{};
+    c.xoff = xb.off;
+    c.kd0 = c.kd1 = 1; c.ks0 = c.ks1 = 0; c.woff = 0;
+    for (int k = 0; k < MAXP; k++) { b.pd[k] = 1; b.yps[k] = 0; c.xps[k] = 0; }
+    for (int k = 1; k < r; k++) {
+      b.pd[k - 1] = xb.d[k];
+      b.yps[k - 1] = yb.st[k];
+      c.xps[k - 1] = xb.st[k];
+      ncol *= xb.d[k];
+    }
+    b.cbeg = (int)plan->contribs.size();
+    b.cnum = 1;
+    plan->contribs.push_back(c);
+    b.colstart = col;
+    col += ncol;
+    plan->blocks.push_back(b);
+  }
+  plan->ncols = col;
+  plan->bytes = 16.0 * (double)X.logical_elems();
+  plan->d_blocks = Y.ctx->upload(plan->blocks);
+  plan->d_contribs = Y.ctx->upload(plan->contribs);
+  return plan;
+}
+
 }  // namespace tnl

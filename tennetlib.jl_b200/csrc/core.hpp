@@ -243,6 +243,8 @@ void comm_unique_id(char* out128);
 void comm_init(Ctx* ctx, const char* uid128, int rank, int world);
 void comm_destroy(Ctx* ctx);
 void comm_allreduce_sum(Ctx* ctx, double* buf, int64_t n);
+void comm_reduce_scatter_sum(Ctx* ctx, const double* send, double* recv, int64_t n);
+void comm_allgather(Ctx* ctx, const double* send, double* recv, int64_t n);
 void shard_range(int d, int world, int sector, int rank, int* start, int* count);
 void transpose(Ctx* ctx, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t R, int64_t C);  // dst[C x R] = src[R x C]^T
 void copy2d(Ctx* ctx, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t R, int64_t C);
@@ -256,6 +258,9 @@ struct SliceMap { int ypos = -1; std::vector<int> orig; std::vector<int64_t> sta
 std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const std::vector<int>& xmap,
                                               const Tensor* W, const std::vector<int>& kpos,
                                               const SliceMap* slice = nullptr);
+// inverse of a sliced transform: every block of the LOCAL tensor X is written into the sub-range of the matching
+// block of the full tensor Y (index `slice.ypos`, Y sector slice.orig[k], elements from slice.start[k])
+std::unique_ptr<TransformPlan> plan_scatter(const Tensor& X, Tensor& Y, const SliceMap& slice);
 void run_transform(Ctx* ctx, TransformPlan& p, const double* X, double* Y, const double* W);
 
 // flat vector kernels on padded buffers of equal layout

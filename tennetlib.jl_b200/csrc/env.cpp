@@ -131,6 +131,7 @@ void Env::invalidate(int lo, int hi) {
     p.lpos = std::min(p.lpos, lo - 1);
     p.rpos = std::max(p.rpos, hi + 1);
     p.m.reset();
+    p.mloc.reset();
   }
   ap.reset();
 }
@@ -303,6 +304,7 @@ void Env::position_penalty(Penalty& p, int pos) {
     p.rpos = kr;
   }
   p.m.reset();
+  p.mloc.reset();
 }
 
 // |m> = dag(proj_mps) = dag(L) * M_j * M_{j+1} * dag(R)   (src/mps/projmps2.jl:182-196)
@@ -363,8 +365,18 @@ TensorP Env::make_phi(int pos) {
 struct Env::ApplyPlan {
   int nsite;
   bool sharded = false;              // multi-GPU: this rank handles a slice of the right link r
-  TensorP vloc;                      // v restricted to the local r range
-  std::unique_ptr<TransformPlan> xs; // v -> vloc
+  TensorP vloc;                      // structure of a Krylov vector restricted to the local r range (no data)
+  std::unique_ptr<TransformPlan> xs; // full Krylov layout -> local slice
+  int64_t nloc = 0;                  // padded length of a local Krylov vector (same on every rank)
+  std::vector<std::unique_ptr<TransformPlan>> pack;    // P -> packed + k*nloc : the slice of rank k
+  std::vector<std::unique_ptr<TransformPlan>> unpack;  // packed + k*nloc -> full Krylov layout
+  double* packed = nullptr;          // world * nloc doubles
+  double* loc_in = nullptr;          // scratch local vectors for the full-vector entry points
+  double* loc_out = nullptr;
+  std::vector<SliceMap> pack_maps;
+  std::vector<TensorP> qloc;
+  Ctx* ctx = nullptr;
+  ~ApplyPlan() { if (ctx) { ctx->free(packed); ctx->free(loc_in); ctx->free(loc_out); } }
   TensorP L, R, W1, W2;
   TensorP T1, T2, T3, P;
   std::unique_ptr<GemmPlan> g1, g4;
@@ -392,20 +404,38 @@ void Env::build_apply_plan(const Tensor& vfull) {
       // link r.  It contracts L with its slice of v, carries the slice through the site operators and contracts
       // with its slice of R over (w, r_local): a partial H_eff v of full size, summed by one NCCL all-reduce.
       const Index& r = v.inds[3];
-      Index rl = r;
-      rl.dims.clear(); rl.qns.clear();
-      SliceMap sm;
-      sm.ypos = 3;
-      for (int s = 0; s < r.nsect(); s++) {
-        int st, cnt;
-        shard_range(r.dims[s], ctx->world, s, ctx->rank, &st, &cnt);
-        if (cnt > 0) { rl.dims.push_back(cnt); rl.qns.push_back(r.qns[s]); sm.orig.push_back(s); sm.start.push_back(st); }
-      }
-      p->sharded = true;
-      p->vloc = mk(ctx, {v.inds[0], v.inds[1], v.inds[2], rl}, 1);
-      p->xs = plan_transform(v, *p->vloc, {0, 1, 2, 3}, nullptr, {}, &sm);
       const Tensor& Rf = *p->R;
-      Index rlR = rl;
+      p->sharded = true;
+      p->ctx = ctx;
+      Tensor Qfull(ctx, v.inds, 1, false);
+      std::vector<SliceMap> sms(ctx->world);
+      std::vector<TensorP> qloc(ctx->world);
+      for (int k = 0; k < ctx->world; k++) {
+        Index rl = r;
+        rl.dims.clear(); rl.qns.clear();
+        sms[k].ypos = 3;
+        for (int s = 0; s < r.nsect(); s++) {
+          int st, cnt;
+          shard_range(r.dims[s], ctx->world, s, k, &st, &cnt);
+          if (cnt > 0) { rl.dims.push_back(cnt); rl.qns.push_back(r.qns[s]); sms[k].orig.push_back(s); sms[k].start.push_back(st); }
+        }
+        qloc[k] = std::make_shared<Tensor>(ctx, std::vector<Index>{v.inds[0], v.inds[1], v.inds[2], rl}, 1, false);
+        p->nloc = std::max(p->nloc, qloc[k]->nelem);
+      }
+      const SliceMap& sm = sms[ctx->rank];
+      p->vloc = qloc[ctx->rank];
+      p->xs = plan_transform(v, *p->vloc, {0, 1, 2, 3}, nullptr, {}, &sm);
+      p->packed = (double*)ctx->alloc((size_t)p->nloc * ctx->world * sizeof(double));
+      CUDA_OK(cudaMemsetAsync(p->packed, 0, (size_t)p->nloc * ctx->world * sizeof(double), ctx->stream));
+      p->loc_in = (double*)ctx->alloc((size_t)p->nloc * sizeof(double));
+      p->loc_out = (double*)ctx->alloc((size_t)p->nloc * sizeof(double));
+      CUDA_OK(cudaMemsetAsync(p->loc_in, 0, (size_t)p->nloc * sizeof(double), ctx->stream));
+      CUDA_OK(cudaMemsetAsync(p->loc_out, 0, (size_t)p->nloc * sizeof(double), ctx->stream));
+      for (int k = 0; k < ctx->world; k++) p->unpack.push_back(plan_scatter(*qloc[k], Qfull, sms[k]));
+      // pack plans need P: built below once P exists (same slice maps on P's last index)
+      p->pack_maps = sms;
+      p->qloc = qloc;
+      Index rlR = p->vloc->inds[3];
       rlR.dir = Rf.inds[2].dir;
       SliceMap sr = sm;
       sr.ypos = 2;
@@ -429,6 +459,9 @@ void Env::build_apply_plan(const Tensor& vfull) {
     Tensor Q(ctx, p->P->inds, 1, false);
     TNL_CHECK(Q.nelem == vfull.nelem, "H_eff output layout differs from the input layout (index mismatch)");
     p->x5 = plan_transform(*p->P, Q, {0, 1, 2, 3}, nullptr, {});
+    if (p->sharded)
+      for (int k = 0; k < ctx->world; k++)
+        p->pack.push_back(plan_transform(*p->P, *p->qloc[k], {0, 1, 2, 3}, nullptr, {}, &p->pack_maps[k]));
     p->flops = p->g1->flops + p->x2->flops + p->x3->flops + p->g4->flops;
   } else if (nsite == 1) {
     TNL_CHECK(v.rank() == 3 && rpos - lpos == 2, "one-site apply needs a (l,s,r) vector and nsite=1 position");
@@ -469,22 +502,55 @@ void Env::apply(const Tensor& v, Tensor& out) {
   apply_ptr(v, v.d, out.d);
 }
 
-void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
-  if (!ap || ap->nsite != nsite || ap->nelem != proto.nelem) build_apply_plan(proto);
+// Sharded core: local slice in, local slice of H_eff v out (sum over ranks by reduce-scatter).
+void Env::apply_local(const double* vloc, double* outloc) {
   ApplyPlan& p = *ap;
+  run_gemm(ctx, *p.g1, p.L->d, vloc, p.T1->d);
+  run_transform(ctx, *p.x2, p.T1->d, p.T2->d, p.W1->d);
+  run_transform(ctx, *p.x3, p.T2->d, p.T3->d, p.W2->d);
+  run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
+  for (int k = 0; k < ctx->world; k++) run_transform(ctx, *p.pack[k], p.P->d, p.packed + (int64_t)k * p.nloc, nullptr);
+  comm_reduce_scatter_sum(ctx, p.packed, outloc, p.nloc);
+  for (auto& pen : pens) {
+    if (pen.dead) continue;
+    if (!pen.mloc) {
+      pen.mloc = std::make_shared<Tensor>(ctx, p.vloc->inds, 1, false);
+      pen.mloc->d = (double*)ctx->alloc((size_t)p.nloc * sizeof(double));
+      CUDA_OK(cudaMemsetAsync(pen.mloc->d, 0, (size_t)p.nloc * sizeof(double), ctx->stream));
+      run_transform(ctx, *p.xs, pen.m->d, pen.mloc->d, nullptr);
+    }
+    vec_dot(ctx, pen.mloc->d, vloc, p.nloc, 200);
+    comm_allreduce_sum(ctx, ctx->d_scalars + 200, 1);
+    vec_axpy_dev(ctx, outloc, pen.mloc->d, p.nloc, 200, weight);
+  }
+  ctx->cnt.apply_count += 1;
+}
+
+void Env::ensure_plan(const Tensor& proto) {
+  if (!ap || ap->nsite != nsite || ap->nelem != proto.nelem) build_apply_plan(proto);
+  if (ap->sharded)
+    for (auto& pen : pens)
+      if (!pen.dead) build_penalty_vector(pen, proto);
+}
+
+void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
+  ensure_plan(proto);
+  ApplyPlan& p = *ap;
+  if (p.sharded) {
+    run_transform(ctx, *p.xs, vin, p.loc_in, nullptr);
+    apply_local(p.loc_in, p.loc_out);
+    comm_allgather(ctx, p.loc_out, p.packed, p.nloc);
+    for (int k = 0; k < ctx->world; k++) run_transform(ctx, *p.unpack[k], p.packed + (int64_t)k * p.nloc, vout, nullptr);
+    return;
+  }
   struct { const double* d; } v{vin};
   struct { double* d; } out{vout};
-  if (p.sharded) {
-    run_transform(ctx, *p.xs, v.d, p.vloc->d, nullptr);
-    v.d = p.vloc->d;
-  }
   run_gemm(ctx, *p.g1, p.L->d, v.d, p.T1->d);
   if (p.nsite == 2) {
     run_transform(ctx, *p.x2, p.T1->d, p.T2->d, p.W1->d);
     run_transform(ctx, *p.x3, p.T2->d, p.T3->d, p.W2->d);
     run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
     run_transform(ctx, *p.x5, p.P->d, out.d, nullptr);
-    if (p.sharded) comm_allreduce_sum(ctx, out.d, p.nelem);
   } else if (p.nsite == 1) {
     run_transform(ctx, *p.x2, p.T1->d, p.T3->d, p.W1->d);
     run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
@@ -585,7 +651,9 @@ static void householder(const std::vector<double>& x, int i, double& beta, std::
 // The same algorithm is restated independently in oracle/krylov.py.
 LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter, bool eager) {
   TNL_CHECK(krylovdim >= 1 && krylovdim < 200, "krylovdim out of range");
-  const int64_t n = phi.nelem;
+  ensure_plan(phi);
+  const bool sh = ap->sharded;                       // Krylov vectors live as r-slices, one per rank
+  const int64_t n = sh ? ap->nloc : phi.nelem;
   const int howmany = 1;
   std::vector<double*> V;                  // Krylov basis (device buffers)
   // pads between charge groups must stay zero: the flat BLAS-1 kernels run over the padded buffer
@@ -595,7 +663,20 @@ LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter,
     return p;
   };
   double* r = newvec();
-  auto applyraw = [&](double* vin, double* vout) { apply_ptr(phi, vin, vout); };
+  auto applyraw = [&](double* vin, double* vout) { if (sh) apply_local(vin, vout); else apply_ptr(phi, vin, vout); };
+  // inner products: local partial sum, then a one-double all-reduce on the stream (no host round trip)
+  auto vec_dot = [&](Ctx* c, const double* x, const double* y, int64_t len, int slot) {
+    tnl::vec_dot(c, x, y, len, slot);
+    if (sh) comm_allreduce_sum(c, c->d_scalars + slot, 1);
+  };
+  double* phi_full = phi.d;
+  double* phi_loc = nullptr;
+  if (sh) {
+    phi_loc = newvec();
+    run_transform(ctx, *ap->xs, phi.d, phi_loc, nullptr);
+  }
+  struct { double* d; } phiv{sh ? phi_loc : phi.d};
+#define phi phiv
   // ---- initialize
   vec_dot(ctx, phi.d, phi.d, n, 0);
   fetch_scalars(ctx, 1);
@@ -725,6 +806,13 @@ LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter,
     for (int i = 0; i < K; i++) coef[i] = U[(size_t)i * K + 0];
     TNL_CHECK((int)V.size() >= K, "Krylov basis bookkeeping");
     vec_lincomb(ctx, phi.d, V.data(), coef.data(), K, n);
+  }
+#undef phi
+  if (sh) {
+    comm_allgather(ctx, phi_loc, ap->packed, ap->nloc);
+    for (int k = 0; k < ctx->world; k++)
+      run_transform(ctx, *ap->unpack[k], ap->packed + (int64_t)k * ap->nloc, phi_full, nullptr);
+    ctx->free(phi_loc);
   }
   ctx->sync();
   for (double* p : V) ctx->free(p);

@@ -67,6 +67,7 @@ class Env {
     int lpos = 0, rpos = 0;
     bool dead = false;               // different total charge: overlap vanishes identically
     TensorP m;                       // |m> = dag(proj_mps) at the current position, Krylov layout
+    TensorP mloc;                    // its local slice (sharded apply)
   };
   std::vector<Penalty> pens;
   double weight = 0.0;
@@ -81,6 +82,8 @@ class Env {
   TensorP make_phi(int pos);                            // two-site tensor (l,s1,s2,r) in Krylov layout (nrow 1)
   void apply(const Tensor& v, Tensor& out);             // out = H_eff v, both in Krylov layout
   void apply_ptr(const Tensor& proto, const double* vin, double* vout);
+  void apply_local(const double* vloc, double* outloc);   // sharded core (multi-GPU)
+  void ensure_plan(const Tensor& proto);
   LanczosResult eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter, bool eager);
   double expectation(const Tensor& phi);
   FactorizeResult replacebond(int pos, const Tensor& phi, FactorizeParams prm, bool normalize);
