@@ -52,6 +52,9 @@ int tnl_set_gemm_variant(tnl_ctx_t ctx, int32_t variant); /* tuning knob: main-l
  * (read synchronises, sums the launch durations and algorithmic flops, and clears the records) */
 int tnl_profile_gemm(tnl_ctx_t ctx, int32_t enable);
 int tnl_profile_read(tnl_ctx_t ctx, double* total_ms, int64_t* launches, double* flops, double* max_tflops);
+/* by-category device time of the records consumed by the last tnl_profile_read: out[0..3] = ms of grouped DGEMM,
+ * transform, Krylov-vector and collective launches, out[4..7] = their launch counts */
+int tnl_profile_categories(tnl_ctx_t ctx, double* out8);
 
 /* ---- multi-GPU: one process per GPU, sharded H_eff apply ----------------
  * rank 0 calls tnl_comm_unique_id, the 128 bytes are broadcast by the host (torch.distributed / MPI), every rank

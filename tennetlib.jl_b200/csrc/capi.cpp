@@ -9,7 +9,7 @@
 
 using namespace tnl;
 
-struct tnl_ctx_s { Ctx ctx; cudaEvent_t ev[8] = {}; explicit tnl_ctx_s(int dev) : ctx(dev) {} };
+struct tnl_ctx_s { Ctx ctx; cudaEvent_t ev[8] = {}; double cat_ms[8] = {}; explicit tnl_ctx_s(int dev) : ctx(dev) {} };
 struct tnl_tensor_s { TensorP t; };
 struct tnl_env_s { Env env; tnl_env_s(Ctx* c, int n) : env(c, n) {} };
 
@@ -147,15 +147,24 @@ int tnl_profile_read(tnl_ctx_t c, double* total_ms, int64_t* launches, double* f
   return guard(&c->ctx, [&] {
     c->ctx.sync();
     *total_ms = 0; *launches = 0; *flops = 0; *max_tflops = 0;
+    for (int k = 0; k < 8; k++) c->cat_ms[k] = 0;
     for (auto& r : c->ctx.prof_recs) {
       float ms = 0;
       CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
-      *total_ms += ms; *launches += 1; *flops += r.flops;
-      if (ms > 0 && r.flops > 1e9) *max_tflops = std::max(*max_tflops, r.flops / (ms * 1e-3) / 1e12);
+      if (r.cat == 0) {
+        *total_ms += ms; *launches += 1; *flops += r.flops;
+        if (ms > 0 && r.flops > 1e9) *max_tflops = std::max(*max_tflops, r.flops / (ms * 1e-3) / 1e12);
+      }
+      if (r.cat >= 0 && r.cat < 4) { c->cat_ms[r.cat] += ms; c->cat_ms[4 + r.cat] += 1; }
       cudaEventDestroy(r.a); cudaEventDestroy(r.b);
     }
     c->ctx.prof_recs.clear();
   });
+}
+/* out[0..3] = device ms of the last tnl_profile_read by category (gemm, transform, vector, collective),
+ * out[4..7] = launch counts */
+int tnl_profile_categories(tnl_ctx_t c, double* out8) {
+  return guard(&c->ctx, [&] { for (int k = 0; k < 8; k++) out8[k] = c->cat_ms[k]; out8[7] = c->ctx.cnt.host_plan_ms; });
 }
 
 int tnl_tensor_import(tnl_ctx_t c, int32_t rank, int32_t nq, const tnl_index_t* inds, int64_t nblocks,

@@ -84,6 +84,7 @@ void comm_destroy(Ctx* ctx) {
 }
 
 void comm_allreduce_sum(Ctx* ctx, double* buf, int64_t n) {
+  Ctx::Scope prof_scope(ctx, 3);
   TNL_CHECK(ctx->nccl_comm, "communicator not initialised");
   NCCL_OK(nccl().AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
   ctx->cnt.allreduce_bytes += 8.0 * n;
@@ -91,12 +92,14 @@ void comm_allreduce_sum(Ctx* ctx, double* buf, int64_t n) {
 
 // recv[0..n) = sum over ranks of send[rank*n .. rank*n+n)
 void comm_reduce_scatter_sum(Ctx* ctx, const double* send, double* recv, int64_t n) {
+  Ctx::Scope prof_scope(ctx, 3);
   TNL_CHECK(ctx->nccl_comm, "communicator not initialised");
   NCCL_OK(nccl().ReduceScatter(send, recv, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
   ctx->cnt.allreduce_bytes += 8.0 * n * ctx->world;
 }
 // recv[k*n .. k*n+n) = send of rank k
 void comm_allgather(Ctx* ctx, const double* send, double* recv, int64_t n) {
+  Ctx::Scope prof_scope(ctx, 3);
   TNL_CHECK(ctx->nccl_comm, "communicator not initialised");
   NCCL_OK(nccl().AllGather(send, recv, (size_t)n, ncclFloat64, (ncclComm_t)ctx->nccl_comm, ctx->stream));
   ctx->cnt.allreduce_bytes += 8.0 * n * ctx->world;

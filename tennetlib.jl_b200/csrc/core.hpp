@@ -188,6 +188,7 @@ struct Counters {
   long long gemm_launches = 0;
   double apply_count = 0;
   double allreduce_bytes = 0;
+  double host_plan_ms = 0;        // host wall time spent building apply plans (planner + uploads)
 };
 
 class Ctx {
@@ -203,9 +204,21 @@ class Ctx {
   int num_sms = 148;
   int gemm_variant = 3;             // grouped DGEMM main-loop variant (3 = v2 loop, BK=32, 3 stages; see kernels.cu)
   // optional per-launch CUDA-event profile of the grouped GEMM kernel (bench.py roofline)
-  struct ProfRec { cudaEvent_t a, b; double flops; int tiles; };
+  struct ProfRec { cudaEvent_t a, b; double flops; int tiles; int cat; };   // cat: 0 gemm, 1 transform, 2 vec, 3 comm
   bool prof_gemm = false;
   std::vector<ProfRec> prof_recs;
+  // scoped CUDA-event timer for the non-GEMM categories (active only while prof_gemm is on)
+  struct Scope {
+    Ctx* c; ProfRec r; bool on;
+    Scope(Ctx* ctx, int cat) : c(ctx), on(ctx->prof_gemm) {
+      if (!on) return;
+      r = ProfRec{};
+      r.cat = cat;
+      cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+      cudaEventRecord(r.a, c->stream);
+    }
+    ~Scope() { if (on) { cudaEventRecord(r.b, c->stream); c->prof_recs.push_back(r); } }
+  };
   // NCCL sharding (multi-GPU apply); rank 0 / world 1 when unused
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;

@@ -9,6 +9,7 @@
 #include "env.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -386,6 +387,10 @@ struct Env::ApplyPlan {
 };
 
 void Env::build_apply_plan(const Tensor& vfull) {
+  struct Timer {
+    Ctx* c; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~Timer() { c->cnt.host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+  } timer{ctx};
   const Tensor& v = vfull;
   auto p = std::make_shared<ApplyPlan>();
   p->nsite = nsite;

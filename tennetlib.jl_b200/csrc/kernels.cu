@@ -356,6 +356,7 @@ void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C
   if (prof) {
     CUDA_OK(cudaEventRecord(rec.b, ctx->stream));
     rec.flops = p.flops;
+    rec.cat = 0;
     rec.tiles = (int)(p.tiles_big.size() + p.tiles_small.size());
     ctx->prof_recs.push_back(rec);
   }
@@ -495,6 +496,7 @@ transform_kernel(const XfBlock* __restrict__ blocks, int nblocks, const XfContri
 
 void run_transform(Ctx* ctx, TransformPlan& p, const double* X, double* Y, const double* W) {
   if (p.ncols == 0) return;
+  Ctx::Scope prof_scope(ctx, 1);
   int64_t warps_needed = p.ncols;
   int64_t blocks = std::min<int64_t>((warps_needed + 7) / 8, (int64_t)ctx->num_sms * 32);
   transform_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_contribs, X, Y, W, p.ncols);
@@ -609,6 +611,7 @@ static inline int vec_grid(Ctx* ctx, int64_t n2) {
 }
 
 void vec_dot(Ctx* ctx, const double* x, const double* y, int64_t n, int slot) {
+  Ctx::Scope prof_scope(ctx, 2);
   TNL_CHECK(n % 2 == 0, "padded vector length must be even");
   dot_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(x, y, n / 2, ctx->d_partials, ctx->d_sync, ctx->d_scalars + slot);
   CUDA_OK(cudaGetLastError());
@@ -616,12 +619,14 @@ void vec_dot(Ctx* ctx, const double* x, const double* y, int64_t n, int slot) {
   ctx->cnt.vec_bytes += (x == y ? 1.0 : 2.0) * n * 8.0;
 }
 void vec_axpy_dev(Ctx* ctx, double* y, const double* x, int64_t n, int slot, double sign) {
+  Ctx::Scope prof_scope(ctx, 2);
   axpy_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(y, x, n / 2, ctx->d_scalars + slot, sign);
   CUDA_OK(cudaGetLastError());
   ctx->cnt.launches++;
   ctx->cnt.vec_bytes += 3.0 * n * 8.0;
 }
 void vec_axpy(Ctx* ctx, double* y, const double* x, int64_t n, double a) {
+  Ctx::Scope prof_scope(ctx, 2);
   axpy_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(y, x, n / 2, nullptr, a);
   CUDA_OK(cudaGetLastError());
   ctx->cnt.launches++;
@@ -629,6 +634,7 @@ void vec_axpy(Ctx* ctx, double* y, const double* x, int64_t n, double a) {
 }
 void vec_scale(Ctx* ctx, double* y, int64_t n, double a) { vec_scale_to(ctx, y, y, n, a); }
 void vec_scale_to(Ctx* ctx, double* y, const double* x, int64_t n, double a) {
+  Ctx::Scope prof_scope(ctx, 2);
   scale_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(y, x, n / 2, a);
   CUDA_OK(cudaGetLastError());
   ctx->cnt.launches++;
@@ -638,6 +644,7 @@ void vec_copy(Ctx* ctx, double* y, const double* x, int64_t n) {
   CUDA_OK(cudaMemcpyAsync(y, x, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 }
 void vec_lincomb(Ctx* ctx, double* y, const double* const* xs, const double* coef, int k, int64_t n) {
+  Ctx::Scope prof_scope(ctx, 2);
   TNL_CHECK(k <= LC_MAX, "too many vectors in linear combination");
   LincombArgs a;
   a.k = k;

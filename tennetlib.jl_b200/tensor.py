@@ -153,7 +153,13 @@ class Context:
     def profile_read(self):
         ms, n, fl, mx = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
         check(self.lib.tnl_profile_read(self.h, C.byref(ms), C.byref(n), C.byref(fl), C.byref(mx)), self.h)
-        return dict(total_ms=ms.value, launches=n.value, flops=fl.value, max_tflops=mx.value)
+        cat = (C.c_double * 8)()
+        check(self.lib.tnl_profile_categories(self.h, cat), self.h)
+        names = ("gemm", "transform", "vector", "collective")
+        return dict(total_ms=ms.value, launches=n.value, flops=fl.value, max_tflops=mx.value,
+                    category_ms={k: cat[i] for i, k in enumerate(names)},
+                    category_launches={k: int(cat[4 + i]) for i, k in enumerate(names[:3])},
+                    host_plan_ms_total=cat[7])
 
     def timer_start(self, slot: int = 0):
         check(self.lib.tnl_timer_start(self.h, slot), self.h)
