@@ -131,6 +131,8 @@ struct FG {                     // one charge group of the factorisation
   double* E = nullptr;                            // eigenvectors (eigen path) [n x n]
   std::vector<double> vals;                       // sigma (svd) or eigenvalues (eigen), LAPACK order
   std::vector<int> keep;                          // kept columns, descending weight
+  bool mine = true;                               // multi-GPU: this rank decomposes the group
+  int64_t nvals = 0;                              // number of spectrum values the group contributes
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -246,6 +248,23 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
     std::sort(fg.begin(), fg.end(), [](const FG& a, const FG& b) { return a.q < b.q; });
   }
 
+  // Multi-GPU: the per-charge-group decompositions are independent -- distribute them
+  // over the ranks (longest-processing-time first on n^3), exchange the spectrum, and sum the two factors.
+  const int W = ctx->world;
+  if (W > 1) {
+    std::vector<size_t> ord(fg.size());
+    std::iota(ord.begin(), ord.end(), 0);
+    auto cost = [&](const FG& f) { double n = (double)std::max(f.R, f.C); return n * n * n; };
+    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cost(fg[a]) > cost(fg[b]); });
+    std::vector<double> load(W, 0.0);
+    for (size_t i : ord) {
+      int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      load[r] += cost(fg[i]);
+      fg[i].mine = (r == ctx->rank);
+    }
+  }
+  for (FG& f : fg) f.nvals = which == 1 ? std::min(f.R, f.C) : (left ? f.R : f.C);
+
   std::vector<void*> temps;
   auto talloc = [&](int64_t n) {
     n = (std::max<int64_t>(n, 1) + 1) & ~int64_t(1);
@@ -260,7 +279,7 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
     // ------------------------------------------------------------------ SVD path
     for (FG& f : fg) {
       const int64_t R = f.R, C = f.C, k = std::min(R, C);
-      if (k == 0) continue;
+      if (k == 0 || !f.mine) continue;
       const bool tr = R < C;                       // gesvd needs m >= n
       const int64_t m = tr ? C : R, n = tr ? R : C;
       double* Awork = talloc(m * n);
@@ -314,7 +333,7 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
     auto off = [](const double* p) { return (int64_t)(reinterpret_cast<intptr_t>(p) / (intptr_t)sizeof(double)); };
     for (FG& f : fg) {
       const int64_t n = left ? f.R : f.C;
-      if (n == 0) continue;
+      if (n == 0 || !f.mine) continue;
       f.E = talloc(n * n);
       GemmProblem p{};
       p.M = p.N = (int)n; p.ldc = (int)n; p.c = off(f.E);
@@ -333,7 +352,7 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
       std::vector<double*> dr;
       for (FG& f : fg) {
         const int64_t n = left ? f.R : f.C;
-        if (n == 0 || !f.X || f.XK == 0) { dr.push_back(nullptr); continue; }
+        if (n == 0 || !f.mine || !f.X || f.XK == 0) { dr.push_back(nullptr); continue; }
         double* D = talloc(n * n);
         dr.push_back(D);
         GemmProblem p{};
@@ -358,7 +377,7 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
     std::vector<double*> Wvs;
     for (FG& f : fg) {
       const int64_t n = left ? f.R : f.C;
-      if (n == 0) continue;
+      if (n == 0 || !f.mine) continue;
       todo.push_back(&f);
       Wvs.push_back(talloc(n));
     }
@@ -403,6 +422,32 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
     }
     for (FG& f : fg)
       for (double w : f.vals) pool.push_back(std::fabs(w));
+  }
+
+  if (W > 1) {
+    // spectrum exchange: every rank fills the segments of its own groups, the rest is zero; one all-reduce
+    int64_t tot = 0;
+    for (FG& f : fg) tot += f.nvals;
+    std::vector<double> all((size_t)((tot + 1) & ~int64_t(1)), 0.0);
+    int64_t o = 0;
+    for (FG& f : fg) {
+      if (f.mine) for (int64_t i = 0; i < (int64_t)f.vals.size(); i++) all[o + i] = f.vals[i];
+      o += f.nvals;
+    }
+    if (tot > 0) {
+      double* d = ctx->upload(all);
+      comm_allreduce_sum(ctx, d, (int64_t)all.size());
+      CUDA_OK(cudaMemcpyAsync(all.data(), d, all.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->sync();
+      ctx->free(d);
+    }
+    o = 0;
+    pool.clear();
+    for (FG& f : fg) {
+      f.vals.assign(all.begin() + o, all.begin() + o + f.nvals);
+      o += f.nvals;
+      for (double v : f.vals) pool.push_back(which == 1 ? v * v : std::fabs(v));
+    }
   }
 
   // ---- pooled truncation
@@ -460,6 +505,7 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
     const Group& GL = gl >= 0 ? res.L->groups[gl] : kNoGroup;
     if (gl >= 0) TNL_CHECK(GL.R == f.R && GL.C == nk, "left factor group shape");
     double* Ld = gl >= 0 ? res.L->d + GL.base : nullptr;
+    if (!f.mine) continue;                         // another rank fills this group; summed by the all-reduce below
     if (which == 1) {
       TNL_CHECK(gr >= 0, "new link sector missing on the right factor");
       const Group& GR = res.R->groups[gr];
@@ -510,6 +556,10 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
     auto g = plan_gemm_raw(ctx, which == 2 && left, false, proj);
     run_gemm(ctx, *g, nullptr, nullptr, nullptr);
     ctx->sync();
+  }
+  if (W > 1) {
+    comm_allreduce_sum(ctx, res.L->d, res.L->nelem);
+    comm_allreduce_sum(ctx, res.R->d, res.R->nelem);
   }
   ctx->sync();
   for (void* p : temps) ctx->free(p);

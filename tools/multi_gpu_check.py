@@ -45,6 +45,18 @@ for kind, N, chi, pos in (("S=1", 8, 40, 4), ("S=1/2", 10, 24, 1), ("S=1", 6, 30
     ok_all &= good
     print(f"rank {rank}/{world} {kind} N={N} chi={chi} pos={pos}: apply err {err:.2e}  E dev {e_d:.12f} oracle {e_o:.12f} "
           f"local flops {env_d.apply_flops():.0f} {'OK' if good else 'FAIL'}", flush=True)
+# full sweeps with the distributed truncation (charge groups spread over the ranks) against the golden fixture
+import json
+G = json.load(open("tests/golden/oracle_golden.json"))
+for g in (G["dmrg"][0], G["dmrg"][2]):
+    sites = om.siteinds(g["kind"], g["N"])
+    H = om.heisenberg_mpo(sites)
+    e, env, sw = T.dmrg2(ctx, om.neel_mps(sites), H, T.DMRGParams(**g["params"]), outputlevel=0)
+    de = max(abs(a - b) for a, b in zip(sw.energy, g["energy"]))
+    good = sw.maxchi == g["maxchi"] and de < 1e-7 and abs(sw.energy[-1] - g["energy"][-1]) < 1e-10 * abs(g["energy"][-1])
+    ok_all &= good
+    print(f"rank {rank}/{world} dmrg {g['name']}: E {sw.energy[-1]:.12f} fixture {g['energy'][-1]:.12f} max dE {de:.2e} "
+          f"maxchi {sw.maxchi == g['maxchi']} {'OK' if good else 'FAIL'}", flush=True)
 t = torch.tensor([1.0 if ok_all else 0.0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
