@@ -17,10 +17,6 @@ Ctx::Ctx(int dev) : device(dev) {
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, dev));
   num_sms = prop.multiProcessorCount;
-  cudaMemPool_t pool;
-  CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
-  uint64_t thr = UINT64_MAX;
-  CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
   CUDA_OK(cudaMalloc(&d_scalars, 256 * sizeof(double)));
   CUDA_OK(cudaMallocHost(&h_scalars, 256 * sizeof(double)));
   CUDA_OK(cudaMalloc(&d_sync, sizeof(unsigned int)));
@@ -30,6 +26,9 @@ Ctx::Ctx(int dev) : device(dev) {
 }
 Ctx::~Ctx() {
   cudaStreamSynchronize(stream);
+  for (auto& kv : free_lists)
+    for (void* q : kv.second) cudaFree(q);
+  for (auto& kv : live) cudaFree(kv.first);
   if (solver_work) cudaFree(solver_work);
   cudaFree(d_scalars);
   cudaFreeHost(h_scalars);
@@ -38,14 +37,44 @@ Ctx::~Ctx() {
   cudaFree(d_info);
   cudaStreamDestroy(stream);
 }
+static size_t size_class(size_t bytes) {
+  if (bytes < 512) return 512;
+  // 8 classes per octave: at most 12.5 % internal waste, and sizes that drift a little from bond to bond
+  // land in the same class
+  int lg = 63 - __builtin_clzll((unsigned long long)bytes);
+  size_t step = (size_t)1 << (lg > 3 ? lg - 3 : 0);
+  return (bytes + step - 1) / step * step;
+}
 void* Ctx::alloc(size_t bytes) {
+  const size_t cls = size_class(bytes);
+  auto& fl = free_lists[cls];
   void* p = nullptr;
-  if (bytes == 0) bytes = 16;
-  CUDA_OK(cudaMallocAsync(&p, bytes, stream));
+  if (!fl.empty()) {
+    p = fl.back();
+    fl.pop_back();
+  } else {
+    cudaError_t e = cudaMalloc(&p, cls);
+    if (e != cudaSuccess) {
+      // out of memory: drop every cached block and retry once
+      cudaGetLastError();
+      cudaStreamSynchronize(stream);
+      for (auto& kv : free_lists) {
+        for (void* q : kv.second) { cudaFree(q); bytes_reserved -= kv.first; }
+        kv.second.clear();
+      }
+      CUDA_OK(cudaMalloc(&p, cls));
+    }
+    bytes_reserved += cls;
+  }
+  live[p] = cls;
   return p;
 }
 void Ctx::free(void* p) {
-  if (p) cudaFreeAsync(p, stream);
+  if (!p) return;
+  auto it = live.find(p);
+  if (it == live.end()) return;
+  free_lists[it->second].push_back(p);
+  live.erase(it);
 }
 
 GemmPlan::~GemmPlan() {
@@ -281,7 +310,8 @@ std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const 
     xb.yns[0] = xb.yns[1] = 0;
     if (nn > 0) { xb.nd0 = yb.d[newpos[0]]; xb.yns[0] = yb.st[newpos[0]]; }
     if (nn > 1) { xb.nd1 = yb.d[newpos[1]]; xb.yns[1] = yb.st[newpos[1]]; }
-    int64_t ncol = (int64_t)xb.nd0 * xb.nd1;
+    int64_t ncol = 1;                                   // passive columns; the new-index outputs share a warp
+    const int64_t nnew = (int64_t)xb.nd0 * xb.nd1;
     for (int k = 0; k < MAXP; k++) { xb.pd[k] = 1; xb.yps[k] = 0; }
     for (size_t k = 0; k < passY.size(); k++) {
       xb.pd[k] = yb.d[passY[k]];
@@ -313,7 +343,7 @@ std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const 
       if (nk > 1) { c.kd1 = sb.d[kpos[1]]; c.ks1 = sb.st[kpos[1]]; }
       c.woff = wb ? wb->off : 0;
       plan->contribs.push_back(c);
-      plan->flops += 2.0 * xb.I * (double)ncol * c.kd0 * c.kd1;
+      plan->flops += 2.0 * xb.I * (double)ncol * nnew * c.kd0 * c.kd1;
     };
     if (!W) {
       add(nullptr);

@@ -229,8 +229,14 @@ class Ctx {
 
   explicit Ctx(int device);
   ~Ctx();
+  // Size-class caching allocator on top of cudaMalloc: all work of a context is ordered on ONE stream, so a
+  // block may be handed out again as soon as it was freed (stream order protects it).  Keeps the per-bond
+  // allocation pattern (workspaces whose sizes change slightly from bond to bond) off the driver's slow path.
   void* alloc(size_t bytes);
   void free(void* p);
+  std::unordered_map<size_t, std::vector<void*>> free_lists;
+  std::unordered_map<void*, size_t> live;
+  size_t bytes_reserved = 0;
   void sync() { CUDA_OK(cudaStreamSynchronize(stream)); }
   template <class T> T* upload(const std::vector<T>& v) {
     if (v.empty()) return nullptr;

@@ -306,12 +306,133 @@ gemm_kernel_v2(const GemmProblem* __restrict__ probs, const GemmTile* __restrict
   }
 }
 
+template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+gemm_kernel_v3(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles,
+               const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase) {
+  constexpr int NT = (BM / WM) * (BN / WN) * 32;
+  using TileA = OpTile<BM, BK, TA>;
+  using TileB = OpTile<BN, BK, !TB>;
+  constexpr int STAGE_ELEMS = TileA::ELEMS + TileB::ELEMS;
+  constexpr int MI = WM / 8, NI = WN / 8, KK = BK / 4;
+  extern __shared__ __align__(16) double smem[];
+
+  const GemmTile tile = tiles[blockIdx.x];
+  const GemmProblem p = probs[tile.prob];
+  const double* pA = Abase + p.a;
+  const double* pB = Bbase + p.b;
+  double* pC = Cbase + p.c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp % (BM / WM)) * WM, wn0 = (warp / (BM / WM)) * WN;
+  const int m0 = tile.m0, n0 = tile.n0;
+  const int ktiles = (p.K + BK - 1) / BK;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  Loader<BM, BK, TA, NT> la;
+  Loader<BN, BK, !TB, NT> lb;
+  la.init(p.lda, m0, p.M, tid);
+  lb.init(p.ldb, n0, p.N, tid);
+
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int i = 0; i < MI; i++)
+#pragma unroll
+    for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < ktiles) {
+      double* sa = smem + s * STAGE_ELEMS;
+      la.issue(sa, pA, s, p.K);
+      lb.issue(sa + TileA::ELEMS, pB, s, p.K);
+    }
+    cp_async_commit();
+  }
+  // fragment element offsets of this lane inside a stage
+  const int fa = TA ? (wm0 + lr) * TileA::LD + lc : lc * TileA::LD + wm0 + lr;
+  const int fb = (!TB) ? (wn0 + lr) * TileB::LD + lc : lc * TileB::LD + wn0 + lr;
+  constexpr int FA_I = TA ? 8 * TileA::LD : 8;            // +8 rows of m
+  constexpr int FA_K = TA ? 4 : 4 * TileA::LD;            // +4 in k
+  constexpr int FB_J = (!TB) ? 8 * TileB::LD : 8;
+  constexpr int FB_K = (!TB) ? 4 : 4 * TileB::LD;
+
+  // Early-sync main loop: the wait + barrier for k-tile kt+1 and the cp.async issue for k-tile kt+STAGES-1 sit
+  // in front of the LAST group of 32 DMMAs of k-tile kt, so barrier latency and the first fragment loads of the
+  // next tile are covered by tensor work that is already in flight.
+  double a[2][MI], b[2][NI];
+  cp_async_wait<STAGES - 2>();
+  __syncthreads();
+  {
+    const double* sa = smem + fa;
+    const double* sb = smem + TileA::ELEMS + fb;
+#pragma unroll
+    for (int i = 0; i < MI; i++) a[0][i] = sa[i * FA_I];
+#pragma unroll
+    for (int j = 0; j < NI; j++) b[0][j] = sb[j * FB_J];
+  }
+  static_assert(KK % 2 == 0, "k-steps per tile must be even (register double buffering across tiles)");
+  for (int kt = 0; kt < ktiles; kt++) {
+    const double* sa = smem + (kt % STAGES) * STAGE_ELEMS + fa;
+    const double* sb = smem + (kt % STAGES) * STAGE_ELEMS + TileA::ELEMS + fb;
+#pragma unroll
+    for (int kk = 0; kk < KK; kk++) {
+      const int cur = kk & 1, nxt = cur ^ 1;
+      if (kk + 1 < KK) {
+#pragma unroll
+        for (int i = 0; i < MI; i++) a[nxt][i] = sa[i * FA_I + (kk + 1) * FA_K];
+#pragma unroll
+        for (int j = 0; j < NI; j++) b[nxt][j] = sb[j * FB_J + (kk + 1) * FB_K];
+      } else {
+        // tile kt+1 must have landed; every warp is past its last read of tile kt-1's stage
+        {
+          const int nk = kt + STAGES - 1;
+          // groups committed so far: tiles 0 .. kt+STAGES-2  ->  allow STAGES-3 pending to have tile kt+1 complete
+          cp_async_wait<(STAGES >= 3 ? STAGES - 3 : 0)>();
+          __syncthreads();
+          if (nk < ktiles) {
+            double* st = smem + (nk % STAGES) * STAGE_ELEMS;
+            la.issue(st, pA, nk, p.K);
+            lb.issue(st + TileA::ELEMS, pB, nk, p.K);
+          }
+          cp_async_commit();
+        }
+        if (kt + 1 < ktiles) {
+          const double* na = smem + ((kt + 1) % STAGES) * STAGE_ELEMS + fa;
+          const double* nb = smem + ((kt + 1) % STAGES) * STAGE_ELEMS + TileA::ELEMS + fb;
+#pragma unroll
+          for (int i = 0; i < MI; i++) a[nxt][i] = na[i * FA_I];
+#pragma unroll
+          for (int j = 0; j < NI; j++) b[nxt][j] = nb[j * FB_J];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < MI; i++)
+#pragma unroll
+        for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < MI; i++) {
+    int m = m0 + wm0 + i * 8 + lr;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < NI; j++) {
+      int n = n0 + wn0 + j * 8 + 2 * lc;
+      double* c = pC + (int64_t)n * p.ldc + m;
+      if (n < p.N) c[0] = acc[i][j][0];
+      if (n + 1 < p.N) c[p.ldc] = acc[i][j][1];
+    }
+  }
+}
+
 template <int VER, int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
 static void launch_gemm_one(Ctx* ctx, const GemmProblem* probs, const GemmTile* tiles, int ntiles,
                             const double* A, const double* B, double* C) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr size_t SMEM = sizeof(double) * STAGES * (OpTile<BM, BK, TA>::ELEMS + OpTile<BN, BK, !TB>::ELEMS);
-  auto kern = VER == 2 ? gemm_kernel_v2<BM, BN, BK, WM, WN, TA, TB, STAGES> : gemm_kernel<BM, BN, BK, WM, WN, TA, TB, STAGES>;
+  auto kern = VER == 3 ? gemm_kernel_v3<BM, BN, BK, WM, WN, TA, TB, STAGES>
+                       : (VER == 2 ? gemm_kernel_v2<BM, BN, BK, WM, WN, TA, TB, STAGES> : gemm_kernel<BM, BN, BK, WM, WN, TA, TB, STAGES>);
   static bool configured = false;   // one static per template instantiation
   if (!configured) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -349,6 +470,8 @@ void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C
     case 5: launch_gemm_cfg<2, 128, 128, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
     case 6: launch_gemm_cfg<2, 128, 128, 32, 32, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
     case 7: launch_gemm_cfg<2, 128, 128, 32, 32, 64, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    case 8: launch_gemm_cfg<3, 128, 128, 32, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    case 9: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 5>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
     case 2: launch_gemm_cfg<2, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
     default: launch_gemm_cfg<2, 128, 128, 32, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
   }
@@ -442,6 +565,8 @@ void gemm_selftest(Ctx* ctx, int M, int N, int K, bool ta, bool tb, int reps, bo
 // =================================================================================================
 // transform: Y(i, n.., p..) = sum_c sum_k X_c(i, k.., p..) * W_c(k, n)      one warp per output column
 // =================================================================================================
+// One warp per PASSIVE column of an output block: the X columns it needs are read once and all Na = nd0*nd1
+// new-index outputs are produced from registers (up to 4 at a time), lanes run along the stride-1 index i.
 __global__ void __launch_bounds__(256)
 transform_kernel(const XfBlock* __restrict__ blocks, int nblocks, const XfContrib* __restrict__ contribs,
                  const double* __restrict__ X, double* __restrict__ Y, const double* __restrict__ W, int64_t ncols) {
@@ -455,40 +580,60 @@ transform_kernel(const XfBlock* __restrict__ blocks, int nblocks, const XfContri
     }
     const XfBlock& b = blocks[lo];
     int64_t t = col - b.colstart;
-    int n0 = (int)(t % b.nd0); t /= b.nd0;
-    int n1 = (int)(t % b.nd1); t /= b.nd1;
-    int64_t ybase = b.yoff + n0 * b.yns[0] + n1 * b.yns[1];
+    int64_t ybase = b.yoff;
     int pidx[MAXP];
 #pragma unroll
     for (int k = 0; k < MAXP; k++) {
       pidx[k] = (int)(t % b.pd[k]); t /= b.pd[k];
       ybase += pidx[k] * b.yps[k];
     }
-    const int na = n0 + b.nd0 * n1;
-    const int I = b.I;
-    for (int i0 = 0; i0 < I; i0 += 128) {
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int c = b.cbeg; c < b.cbeg + b.cnum; c++) {
-        const XfContrib& cc = contribs[c];
-        int64_t xb = cc.xoff;
+    const int I = b.I, Na = b.nd0 * b.nd1;
+    for (int nc = 0; nc < Na; nc += 4) {
+      const int nn = min(4, Na - nc);
+      for (int i0 = 0; i0 < I; i0 += 128) {
+        double acc[4][4];
 #pragma unroll
-        for (int k = 0; k < MAXP; k++) xb += pidx[k] * cc.xps[k];
-        const int Ka = cc.kd0 * cc.kd1;
-        for (int a1 = 0; a1 < cc.kd1; a1++)
-          for (int a0 = 0; a0 < cc.kd0; a0++) {
-            const double w = W ? W[cc.woff + a0 + cc.kd0 * a1 + (int64_t)Ka * na] : 1.0;
-            const double* xp = X + xb + a0 * cc.ks0 + a1 * cc.ks1;
+        for (int n = 0; n < 4; n++)
+#pragma unroll
+          for (int u = 0; u < 4; u++) acc[n][u] = 0.0;
+        for (int c = b.cbeg; c < b.cbeg + b.cnum; c++) {
+          const XfContrib& cc = contribs[c];
+          int64_t xb = cc.xoff;
+#pragma unroll
+          for (int k = 0; k < MAXP; k++) xb += pidx[k] * cc.xps[k];
+          const int Ka = cc.kd0 * cc.kd1;
+          for (int a1 = 0; a1 < cc.kd1; a1++)
+            for (int a0 = 0; a0 < cc.kd0; a0++) {
+              const double* xp = X + xb + a0 * cc.ks0 + a1 * cc.ks1;
+              double x[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                int i = i0 + lane + 32 * u;
+                x[u] = i < I ? xp[i] : 0.0;
+              }
+              const double* wp = W ? W + cc.woff + a0 + cc.kd0 * a1 + (int64_t)Ka * nc : nullptr;
+#pragma unroll
+              for (int n = 0; n < 4; n++) {
+                if (n < nn) {
+                  const double w = wp ? wp[(int64_t)Ka * n] : 1.0;
+#pragma unroll
+                  for (int u = 0; u < 4; u++) acc[n][u] = fma(x[u], w, acc[n][u]);
+                }
+              }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < 4; n++) {
+          if (n < nn) {
+            const int na = nc + n;
+            double* yp = Y + ybase + (na % b.nd0) * b.yns[0] + (na / b.nd0) * b.yns[1];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
               int i = i0 + lane + 32 * u;
-              if (i < I) acc[u] = fma(xp[i], w, acc[u]);
+              if (i < I) yp[i] = acc[n][u];
             }
           }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        int i = i0 + lane + 32 * u;
-        if (i < I) Y[ybase + i] = acc[u];
+        }
       }
     }
   }
