@@ -17,6 +17,10 @@ Ctx::Ctx(int dev) : device(dev) {
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, dev));
   num_sms = prop.multiProcessorCount;
+  cudaMemPool_t pool;
+  CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t thr = UINT64_MAX;
+  CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
   CUDA_OK(cudaMalloc(&d_scalars, 256 * sizeof(double)));
   CUDA_OK(cudaMallocHost(&h_scalars, 256 * sizeof(double)));
   CUDA_OK(cudaMalloc(&d_sync, sizeof(unsigned int)));
@@ -26,9 +30,7 @@ Ctx::Ctx(int dev) : device(dev) {
 }
 Ctx::~Ctx() {
   cudaStreamSynchronize(stream);
-  for (auto& kv : free_lists)
-    for (void* q : kv.second) cudaFree(q);
-  for (auto& kv : live) cudaFree(kv.first);
+
   if (solver_work) cudaFree(solver_work);
   cudaFree(d_scalars);
   cudaFreeHost(h_scalars);
@@ -37,44 +39,16 @@ Ctx::~Ctx() {
   cudaFree(d_info);
   cudaStreamDestroy(stream);
 }
-static size_t size_class(size_t bytes) {
-  if (bytes < 512) return 512;
-  // 8 classes per octave: at most 12.5 % internal waste, and sizes that drift a little from bond to bond
-  // land in the same class
-  int lg = 63 - __builtin_clzll((unsigned long long)bytes);
-  size_t step = (size_t)1 << (lg > 3 ? lg - 3 : 0);
-  return (bytes + step - 1) / step * step;
-}
+// Stream-ordered allocation from the device's default memory pool (release threshold = never): blocks freed on
+// the context stream are reused by later allocations of any size without touching the OS.
 void* Ctx::alloc(size_t bytes) {
-  const size_t cls = size_class(bytes);
-  auto& fl = free_lists[cls];
   void* p = nullptr;
-  if (!fl.empty()) {
-    p = fl.back();
-    fl.pop_back();
-  } else {
-    cudaError_t e = cudaMalloc(&p, cls);
-    if (e != cudaSuccess) {
-      // out of memory: drop every cached block and retry once
-      cudaGetLastError();
-      cudaStreamSynchronize(stream);
-      for (auto& kv : free_lists) {
-        for (void* q : kv.second) { cudaFree(q); bytes_reserved -= kv.first; }
-        kv.second.clear();
-      }
-      CUDA_OK(cudaMalloc(&p, cls));
-    }
-    bytes_reserved += cls;
-  }
-  live[p] = cls;
+  if (bytes == 0) bytes = 16;
+  CUDA_OK(cudaMallocAsync(&p, bytes, stream));
   return p;
 }
 void Ctx::free(void* p) {
-  if (!p) return;
-  auto it = live.find(p);
-  if (it == live.end()) return;
-  free_lists[it->second].push_back(p);
-  live.erase(it);
+  if (p) cudaFreeAsync(p, stream);
 }
 
 GemmPlan::~GemmPlan() {

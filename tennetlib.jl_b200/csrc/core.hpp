@@ -202,7 +202,7 @@ class Ctx {
   unsigned int* d_sync = nullptr;   // "last block" counters
   double* d_partials = nullptr;
   int num_sms = 148;
-  int gemm_variant = 3;             // grouped DGEMM main-loop variant (3 = v2 loop, BK=32, 3 stages; see kernels.cu)
+  int gemm_variant = 10;            // grouped DGEMM main-loop variant (10 = early-sync loop, BK=16, 4 stages; see kernels.cu)
   // optional per-launch CUDA-event profile of the grouped GEMM kernel (bench.py roofline)
   struct ProfRec { cudaEvent_t a, b; double flops; int tiles; int cat; };   // cat: 0 gemm, 1 transform, 2 vec, 3 comm
   bool prof_gemm = false;
@@ -229,14 +229,8 @@ class Ctx {
 
   explicit Ctx(int device);
   ~Ctx();
-  // Size-class caching allocator on top of cudaMalloc: all work of a context is ordered on ONE stream, so a
-  // block may be handed out again as soon as it was freed (stream order protects it).  Keeps the per-bond
-  // allocation pattern (workspaces whose sizes change slightly from bond to bond) off the driver's slow path.
-  void* alloc(size_t bytes);
+  void* alloc(size_t bytes);        // stream-ordered (cudaMallocAsync on the context stream)
   void free(void* p);
-  std::unordered_map<size_t, std::vector<void*>> free_lists;
-  std::unordered_map<void*, size_t> live;
-  size_t bytes_reserved = 0;
   void sync() { CUDA_OK(cudaStreamSynchronize(stream)); }
   template <class T> T* upload(const std::vector<T>& v) {
     if (v.empty()) return nullptr;

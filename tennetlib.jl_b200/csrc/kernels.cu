@@ -471,9 +471,12 @@ void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C
     case 6: launch_gemm_cfg<2, 128, 128, 32, 32, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
     case 7: launch_gemm_cfg<2, 128, 128, 32, 32, 64, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
     case 8: launch_gemm_cfg<3, 128, 128, 32, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    case 9: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 5>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    case 11: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 6>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
     case 2: launch_gemm_cfg<2, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    default: launch_gemm_cfg<2, 128, 128, 32, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    case 3: launch_gemm_cfg<2, 128, 128, 32, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    case 9: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 5>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    case 12: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    default: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
   }
   launch_gemm_cfg<1, 64, 64, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_small, (int)p.tiles_small.size(), A, B, C);
   if (prof) {

@@ -336,7 +336,7 @@ def test_svd_drivers_agree(ctx, svd_alg):
         assert np.abs(M.T @ M - np.eye(M.shape[1])).max() < 1e-10
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 3, 10])
 def test_grouped_dgemm_kernel_against_naive_reference(ctx, variant):
     """Kernel-level check: DMMA grouped GEMM vs a one-thread-per-element FP64 reference kernel, ragged sizes,
     all four operand layouts (tails in M, N and K, odd leading dimensions)."""
