@@ -65,6 +65,9 @@ int tnl_comm_unique_id(char* out128);
 int tnl_comm_init(tnl_ctx_t ctx, const char* uid128, int32_t rank, int32_t world);
 int tnl_comm_destroy(tnl_ctx_t ctx);
 int tnl_shard_range(int32_t dim, int32_t world, int32_t sector, int32_t rank, int32_t* start, int32_t* count);
+/* collective micro-benchmark on the library stream: kind 0 = all-reduce of n doubles, 1 = reduce-scatter
+ * (n per rank), 2 = all-gather (n per rank); returns the average milliseconds per call */
+int tnl_comm_bench(tnl_ctx_t ctx, int64_t n, int32_t reps, int32_t kind, double* ms);
 
 /* ---- tensors: ITensor <-> device (replaces nothing in the reference; it is the marshalling the shim needs) */
 int tnl_tensor_import(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t* inds, int64_t nblocks,

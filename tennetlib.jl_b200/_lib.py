@@ -32,6 +32,7 @@ _SIGS = {
     "tnl_comm_unique_id": [C.c_char_p],
     "tnl_comm_init": [_P, C.c_char_p, C.c_int32, C.c_int32],
     "tnl_comm_destroy": [_P],
+    "tnl_comm_bench": [_P, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_double)],
     "tnl_shard_range": [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     "tnl_gemm_selftest": [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                           C.POINTER(C.c_double), C.POINTER(C.c_double)],

@@ -120,6 +120,33 @@ int tnl_comm_init(tnl_ctx_t c, const char* uid128, int32_t rank, int32_t world) 
 int tnl_comm_destroy(tnl_ctx_t c) {
   return guard(&c->ctx, [&] { comm_destroy(&c->ctx); });
 }
+int tnl_comm_bench(tnl_ctx_t c, int64_t n, int32_t reps, int32_t kind, double* ms) {
+  return guard(&c->ctx, [&] {
+    Ctx* ctx = &c->ctx;
+    const int W = ctx->world;
+    double* a = (double*)ctx->alloc((size_t)n * W * sizeof(double));
+    double* b = (double*)ctx->alloc((size_t)n * W * sizeof(double));
+    CUDA_OK(cudaMemsetAsync(a, 0, (size_t)n * W * sizeof(double), ctx->stream));
+    auto go = [&] {
+      if (kind == 0) comm_allreduce_sum(ctx, a, n);
+      else if (kind == 1) comm_reduce_scatter_sum(ctx, a, b, n);
+      else comm_allgather(ctx, a, b, n);
+    };
+    for (int i = 0; i < 3; i++) go();
+    ctx->sync();
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    CUDA_OK(cudaEventRecord(e0, ctx->stream));
+    for (int i = 0; i < reps; i++) go();
+    CUDA_OK(cudaEventRecord(e1, ctx->stream));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float f = 0;
+    CUDA_OK(cudaEventElapsedTime(&f, e0, e1));
+    *ms = f / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->free(a); ctx->free(b);
+  });
+}
 int tnl_shard_range(int32_t dim, int32_t world, int32_t sector, int32_t rank, int32_t* start, int32_t* count) {
   return guard(nullptr, [&] {
     TNL_CHECK(world >= 1 && rank >= 0 && rank < world && dim >= 0, "bad shard query");

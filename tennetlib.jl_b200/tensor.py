@@ -135,6 +135,11 @@ class Context:
     def comm_init(self, uid: bytes, rank: int, world: int):
         check(self.lib.tnl_comm_init(self.h, uid, rank, world), self.h)
 
+    def comm_bench(self, n: int, reps: int, kind: int) -> float:
+        ms = C.c_double()
+        check(self.lib.tnl_comm_bench(self.h, n, reps, kind, C.byref(ms)), self.h)
+        return ms.value
+
     def comm_destroy(self):
         check(self.lib.tnl_comm_destroy(self.h), self.h)
 

@@ -22,6 +22,12 @@ dist.broadcast(uid, 0)
 ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
 
 ok_all = True
+if os.environ.get("TNL_COMM_BENCH"):
+    for kind, name in ((0, "allreduce"), (1, "reduce_scatter"), (2, "allgather")):
+        for n in (1, 1024, 1 << 20, 3600000):
+            ms = ctx.comm_bench(n, 50, kind)
+            if rank == 0:
+                print(f"comm {name} n={n} doubles/rank: {ms * 1e3:.1f} us", flush=True)
 for kind, N, chi, pos in (("S=1", 8, 40, 4), ("S=1/2", 10, 24, 1), ("S=1", 6, 300, 3)):
     sites = om.siteinds(kind, N)
     H = om.heisenberg_mpo(sites)
