@@ -243,8 +243,9 @@ def run_ours(args):
     sampler.start()
     ctx.reset_counters()
     sysenv.profile = True
+    sysenv.profile_kernels = True
     sysenv.phase_ms = {}
-    phases0 = None
+    sysenv.phase_kernel_ms = {}
     ctx.profile_gemm(True)
     ctx.profile_read()
     apply_flops_total, numops_total = 0.0, 0
@@ -263,9 +264,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     clocks = sampler.stop()
     cnt = ctx.counters()
-    prof = ctx.profile_read()
+    ctx.profile_read()
+    prof = dict(sysenv.gemm_prof)
+    prof["category_ms"] = {}
+    for ph, d in sysenv.phase_kernel_ms.items():
+        for k, v in d.items():
+            prof["category_ms"][k] = prof["category_ms"].get(k, 0.0) + v
     ctx.profile_gemm(False)
     sysenv.profile = False
+    sysenv.profile_kernels = False
     phases = dict(sysenv.phase_ms)
 
     sysenv.set_nsite(2)
@@ -342,7 +349,8 @@ def run_ours(args):
             "krylov_vec": {"algorithmic_gb_per_step": cnt["vec_bytes"] / args.steps / 1e9},
             "transform": {"algorithmic_gb_per_step": cnt["transform_bytes"] / args.steps / 1e9},
             "device_ms_per_step_by_kernel_class": {k: v / args.steps for k, v in prof["category_ms"].items()},
-            "host_plan_ms_since_start": prof["host_plan_ms_total"],
+            "device_ms_per_step_by_phase_and_kernel_class": {ph: {k: v / args.steps for k, v in d.items()}
+                                                             for ph, d in sysenv.phase_kernel_ms.items()},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": tf_e2e, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "call": "tnl_tensor_import -> tnl_eigsolve_lanczos -> tnl_tensor_export"},

@@ -21,6 +21,9 @@ class StateEnvs:
         self.ctx = ctx
         self.profile = False           # when True, per-phase device times are accumulated in phase_ms
         self.phase_ms = {}
+        self.profile_kernels = False   # additionally split the device time of each phase by kernel class
+        self.phase_kernel_ms = {}
+        self.gemm_prof = dict(total_ms=0.0, launches=0, flops=0.0, max_tflops=0.0)
         self.last_solver_info = {}
         self.N = len(psi)
         if len(H) != self.N:
@@ -74,6 +77,14 @@ class StateEnvs:
             def __exit__(self_p, *exc):
                 if env.profile and exc[0] is None:
                     env.phase_ms[name] = env.phase_ms.get(name, 0.0) + env.ctx.timer_stop()
+                    if env.profile_kernels:          # device time by kernel class inside this phase
+                        pr = env.ctx.profile_read()
+                        acc = env.phase_kernel_ms.setdefault(name, {})
+                        for k, v in pr["category_ms"].items():
+                            acc[k] = acc.get(k, 0.0) + v
+                        g = env.gemm_prof
+                        g["total_ms"] += pr["total_ms"]; g["launches"] += pr["launches"]; g["flops"] += pr["flops"]
+                        g["max_tflops"] = max(g["max_tflops"], pr["max_tflops"])
                 return False
         return _P()
 
