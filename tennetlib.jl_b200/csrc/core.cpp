@@ -32,6 +32,9 @@ Ctx::~Ctx() {
   cudaStreamSynchronize(stream);
 
   if (solver_work) cudaFree(solver_work);
+  for (auto& sl : slots) if (sl.p) cudaFreeAsync(sl.p, stream);
+  for (auto& v : vec_pool) cudaFreeAsync(v.first, stream);
+  cudaStreamSynchronize(stream);
   cudaFree(d_scalars);
   cudaFreeHost(h_scalars);
   cudaFree(d_sync);
@@ -49,6 +52,60 @@ void* Ctx::alloc(size_t bytes) {
 }
 void Ctx::free(void* p) {
   if (p) cudaFreeAsync(p, stream);
+}
+
+double* Ctx::scratch(int slot, size_t nelem, bool zero) {
+  Slot& s = slots[slot];
+  size_t bytes = std::max<size_t>(nelem, 2) * sizeof(double);
+  if (bytes > s.cap) {
+    if (s.p) cudaFreeAsync(s.p, stream);
+    s.cap = bytes + bytes / 4;                       // headroom: sector sizes drift from bond to bond
+    CUDA_OK(cudaMallocAsync(&s.p, s.cap, stream));
+  }
+  if (zero) CUDA_OK(cudaMemsetAsync(s.p, 0, bytes, stream));
+  return (double*)s.p;
+}
+double* Ctx::vec_acquire(size_t nelem) {
+  double* p = nullptr;
+  size_t cap = 0;
+  for (size_t i = 0; i < vec_pool.size(); i++)
+    if (vec_pool[i].second >= nelem) { p = vec_pool[i].first; cap = vec_pool[i].second; vec_pool.erase(vec_pool.begin() + i); break; }
+  if (!p) {
+    if (!vec_pool.empty()) {                         // recycle the memory of a too-small buffer
+      cudaFreeAsync(vec_pool.back().first, stream);
+      vec_pool.pop_back();
+    }
+    cap = nelem + nelem / 4;
+    CUDA_OK(cudaMallocAsync(&p, cap * sizeof(double), stream));
+  }
+  CUDA_OK(cudaMemsetAsync(p, 0, nelem * sizeof(double), stream));
+  vec_caps[p] = cap;
+  return p;
+}
+void Ctx::vec_release(double* p, size_t) {
+  if (!p) return;
+  auto it = vec_caps.find(p);
+  if (it == vec_caps.end()) { cudaFreeAsync(p, stream); return; }
+  vec_pool.emplace_back(p, it->second);
+  vec_caps.erase(it);
+}
+void Ctx::arena_reset() {
+  if (arena_want > slots[SLOT_ARENA].cap / sizeof(double)) scratch(SLOT_ARENA, arena_want, false);
+  arena_off = 0;
+  arena_want = 0;
+}
+double* Ctx::arena_alloc(size_t nelem, bool* from_arena) {
+  nelem = (nelem + 31) & ~size_t(31);                // 256-byte granules
+  arena_want += nelem;
+  Slot& s = slots[SLOT_ARENA];
+  if ((arena_off + nelem) * sizeof(double) <= s.cap) {
+    double* p = (double*)s.p + arena_off;
+    arena_off += nelem;
+    *from_arena = true;
+    return p;
+  }
+  *from_arena = false;
+  return (double*)alloc(nelem * sizeof(double));
 }
 
 GemmPlan::~GemmPlan() {
@@ -142,7 +199,7 @@ Tensor::Tensor(Ctx* c, std::vector<Index> ii, int nr, bool alloc) : ctx(c), inds
   }
 }
 Tensor::~Tensor() {
-  if (d && ctx) ctx->free(d);
+  if (d && ctx && owns) ctx->free(d);
 }
 void Tensor::zero() { CUDA_OK(cudaMemsetAsync(d, 0, nelem * sizeof(double), ctx->stream)); }
 

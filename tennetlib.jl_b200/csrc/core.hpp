@@ -99,6 +99,7 @@ class Tensor {
   std::unordered_map<uint64_t, int> lut;           // packed coords -> block number
   std::vector<uint8_t> present;                    // imported tensors: which blocks the host supplied (empty = all)
   double* d = nullptr;
+  bool owns = true;                                // false: `d` points into a Ctx workspace slot
   int64_t nelem = 0;                               // padded element count of the buffer
 
   Tensor(Ctx* ctx, std::vector<Index> inds, int nrow, bool alloc = true);
@@ -231,6 +232,22 @@ class Ctx {
   ~Ctx();
   void* alloc(size_t bytes);        // stream-ordered (cudaMallocAsync on the context stream)
   void free(void* p);
+  // Persistent, grow-only workspaces for the big per-bond temporaries (T1..T3 of the apply, Krylov vectors,
+  // factorisation scratch): allocated once at their high-water mark instead of once per bond, so the timed path
+  // never waits for the driver to find / map gigabyte-sized blocks.
+  enum { SLOT_T1 = 0, SLOT_T2, SLOT_T3, SLOT_P, SLOT_PACKED, SLOT_LOCIN, SLOT_LOCOUT, SLOT_VLOC, SLOT_ARENA, NSLOTS };
+  struct Slot { void* p = nullptr; size_t cap = 0; };
+  Slot slots[NSLOTS];
+  double* scratch(int slot, size_t nelem, bool zero);
+  std::unordered_map<double*, size_t> vec_caps;
+  std::vector<std::pair<double*, size_t>> vec_pool;     // free Krylov-vector buffers (ptr, capacity in doubles)
+  double* vec_acquire(size_t nelem);                    // zero-filled
+  void vec_release(double* p, size_t cap);
+  // bump allocator inside SLOT_ARENA (factorisation temporaries); falls back to alloc() on overflow and grows
+  // the arena for the next call
+  size_t arena_off = 0, arena_want = 0;
+  void arena_reset();
+  double* arena_alloc(size_t nelem, bool* from_arena);
   void sync() { CUDA_OK(cudaStreamSynchronize(stream)); }
   template <class T> T* upload(const std::vector<T>& v) {
     if (v.empty()) return nullptr;

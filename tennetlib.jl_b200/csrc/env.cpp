@@ -21,6 +21,14 @@ static TensorP mk(Ctx* ctx, std::vector<Index> inds, int nrow) { return std::mak
 
 static Index with_dir(Index ix, int dir) { ix.dir = dir; return ix; }
 
+// tensor whose buffer lives in a persistent workspace slot of the context (zero-filled: pads must be zero)
+static TensorP mk_ws(Ctx* ctx, std::vector<Index> inds, int nrow, int slot) {
+  auto t = std::make_shared<Tensor>(ctx, std::move(inds), nrow, false);
+  t->d = ctx->scratch(slot, (size_t)t->nelem, true);
+  t->owns = false;
+  return t;
+}
+
 TensorP import_tensor(Ctx* ctx, const HostBlocks& hb, int nrow) {
   TNL_CHECK(hb.rank >= 1 && hb.rank <= MAXR, "import: bad rank");
   auto Y = mk(ctx, hb.inds, nrow);
@@ -173,10 +181,11 @@ void Env::makeL(int k) {
     TensorP Aq = as_nrow(ctx, A[ll], 1);            // [l | s r]
     TensorP As = as_nrow(ctx, A[ll], 2);            // [l s | r]
     const TensorP& W = Wlr[ll];
-    auto X1 = mk(ctx, {L->inds[0], L->inds[1], Aq->inds[1], Aq->inds[2]}, 2);
+    ap.reset();                                     // the apply workspaces are reused below
+    auto X1 = mk_ws(ctx, {L->inds[0], L->inds[1], Aq->inds[1], Aq->inds[2]}, 2, Ctx::SLOT_T1);
     auto g1 = plan_gemm(*L, false, *Aq, false, *X1);
     run_gemm(ctx, *g1, L->d, Aq->d, X1->d);
-    auto Y1 = mk(ctx, {X1->inds[0], W->inds[2], W->inds[3], X1->inds[3]}, 2);
+    auto Y1 = mk_ws(ctx, {X1->inds[0], W->inds[2], W->inds[3], X1->inds[3]}, 2, Ctx::SLOT_T2);
     auto x1 = plan_transform(*X1, *Y1, {0, -1, -1, 3}, W.get(), {1, 2});
     run_transform(ctx, *x1, X1->d, Y1->d, W->d);
     const Index& r = As->inds[2];
@@ -204,10 +213,11 @@ void Env::makeR(int k) {
     TensorP As = as_nrow(ctx, A[j], 2);
     const TensorP& W = Wrl[j];
     const Index &l = As->inds[0], &s = As->inds[1];
-    auto Z = mk(ctx, {with_dir(l, -l.dir), with_dir(s, -s.dir), R->inds[1], R->inds[2]}, 2);
+    ap.reset();
+    auto Z = mk_ws(ctx, {with_dir(l, -l.dir), with_dir(s, -s.dir), R->inds[1], R->inds[2]}, 2, Ctx::SLOT_T1);
     auto g1 = plan_gemm(*As, false, *R, false, *Z, /*dagA=*/true);
     run_gemm(ctx, *g1, As->d, R->d, Z->d);
-    auto Z2 = mk(ctx, {Z->inds[0], W->inds[2], W->inds[3], Z->inds[3]}, 2);
+    auto Z2 = mk_ws(ctx, {Z->inds[0], W->inds[2], W->inds[3], Z->inds[3]}, 2, Ctx::SLOT_T2);
     auto x1 = plan_transform(*Z, *Z2, {0, -1, -1, 3}, W.get(), {1, 2});
     run_transform(ctx, *x1, Z->d, Z2->d, W->d);
     auto Rn = mk(ctx, {Z2->inds[0], Z2->inds[1], Aq->inds[0]}, 2);
@@ -377,7 +387,7 @@ struct Env::ApplyPlan {
   std::vector<SliceMap> pack_maps;
   std::vector<TensorP> qloc;
   Ctx* ctx = nullptr;
-  ~ApplyPlan() { if (ctx) { ctx->free(packed); ctx->free(loc_in); ctx->free(loc_out); } }
+
   TensorP L, R, W1, W2;
   TensorP T1, T2, T3, P;
   std::unique_ptr<GemmPlan> g1, g4;
@@ -430,12 +440,9 @@ void Env::build_apply_plan(const Tensor& vfull) {
       const SliceMap& sm = sms[ctx->rank];
       p->vloc = qloc[ctx->rank];
       p->xs = plan_transform(v, *p->vloc, {0, 1, 2, 3}, nullptr, {}, &sm);
-      p->packed = (double*)ctx->alloc((size_t)p->nloc * ctx->world * sizeof(double));
-      CUDA_OK(cudaMemsetAsync(p->packed, 0, (size_t)p->nloc * ctx->world * sizeof(double), ctx->stream));
-      p->loc_in = (double*)ctx->alloc((size_t)p->nloc * sizeof(double));
-      p->loc_out = (double*)ctx->alloc((size_t)p->nloc * sizeof(double));
-      CUDA_OK(cudaMemsetAsync(p->loc_in, 0, (size_t)p->nloc * sizeof(double), ctx->stream));
-      CUDA_OK(cudaMemsetAsync(p->loc_out, 0, (size_t)p->nloc * sizeof(double), ctx->stream));
+      p->packed = ctx->scratch(Ctx::SLOT_PACKED, (size_t)p->nloc * ctx->world, true);
+      p->loc_in = ctx->scratch(Ctx::SLOT_LOCIN, (size_t)p->nloc, true);
+      p->loc_out = ctx->scratch(Ctx::SLOT_LOCOUT, (size_t)p->nloc, true);
       for (int k = 0; k < ctx->world; k++) p->unpack.push_back(plan_scatter(*qloc[k], Qfull, sms[k]));
       // pack plans need P: built below once P exists (same slice maps on P's last index)
       p->pack_maps = sms;
@@ -453,13 +460,13 @@ void Env::build_apply_plan(const Tensor& vfull) {
     }
     const Tensor& v = *vin;     // from here on: the (possibly sliced) input structure
     const Tensor &L = *p->L, &R = *p->R, &W1 = *p->W1, &W2 = *p->W2;
-    p->T1 = mk(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2], v.inds[3]}, 2);
+    p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2], v.inds[3]}, 2, Ctx::SLOT_T1);
     p->g1 = plan_gemm(L, false, v, false, *p->T1);
-    p->T2 = mk(ctx, {L.inds[0], W1.inds[2], W1.inds[3], v.inds[2], v.inds[3]}, 5);
+    p->T2 = mk_ws(ctx, {L.inds[0], W1.inds[2], W1.inds[3], v.inds[2], v.inds[3]}, 5, Ctx::SLOT_T2);
     p->x2 = plan_transform(*p->T1, *p->T2, {0, -1, -1, 3, 4}, &W1, {1, 2});
-    p->T3 = mk(ctx, {L.inds[0], W1.inds[2], W2.inds[2], W2.inds[3], v.inds[3]}, 3);
+    p->T3 = mk_ws(ctx, {L.inds[0], W1.inds[2], W2.inds[2], W2.inds[3], v.inds[3]}, 3, Ctx::SLOT_T3);
     p->x3 = plan_transform(*p->T2, *p->T3, {0, 1, -1, -1, 4}, &W2, {2, 3});
-    p->P = mk(ctx, {L.inds[0], W1.inds[2], W2.inds[2], R.inds[0]}, 3);
+    p->P = mk_ws(ctx, {L.inds[0], W1.inds[2], W2.inds[2], R.inds[0]}, 3, Ctx::SLOT_P);
     p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
     Tensor Q(ctx, p->P->inds, 1, false);
     TNL_CHECK(Q.nelem == vfull.nelem, "H_eff output layout differs from the input layout (index mismatch)");
@@ -472,11 +479,11 @@ void Env::build_apply_plan(const Tensor& vfull) {
     TNL_CHECK(v.rank() == 3 && rpos - lpos == 2, "one-site apply needs a (l,s,r) vector and nsite=1 position");
     p->W1 = Wlr[first - 1];
     const Tensor &L = *p->L, &R = *p->R, &W1 = *p->W1;
-    p->T1 = mk(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2]}, 2);
+    p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2]}, 2, Ctx::SLOT_T1);
     p->g1 = plan_gemm(L, false, v, false, *p->T1);
-    p->T3 = mk(ctx, {L.inds[0], W1.inds[2], W1.inds[3], v.inds[2]}, 2);
+    p->T3 = mk_ws(ctx, {L.inds[0], W1.inds[2], W1.inds[3], v.inds[2]}, 2, Ctx::SLOT_T3);
     p->x2 = plan_transform(*p->T1, *p->T3, {0, -1, -1, 3}, &W1, {1, 2});
-    p->P = mk(ctx, {L.inds[0], W1.inds[2], R.inds[0]}, 2);
+    p->P = mk_ws(ctx, {L.inds[0], W1.inds[2], R.inds[0]}, 2, Ctx::SLOT_P);
     p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
     Tensor Q(ctx, p->P->inds, 1, false);
     TNL_CHECK(Q.nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
@@ -485,11 +492,11 @@ void Env::build_apply_plan(const Tensor& vfull) {
   } else if (nsite == 0) {
     TNL_CHECK(v.rank() == 2 && rpos - lpos == 1, "zero-site apply needs a (l,r) bond matrix and nsite=0 position");
     const Tensor &L = *p->L, &R = *p->R;
-    p->T1 = mk(ctx, {L.inds[0], L.inds[1], v.inds[1]}, 2);            // [(l' w) | r]
+    p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1]}, 2, Ctx::SLOT_T1);            // [(l' w) | r]
     p->g1 = plan_gemm(L, false, v, false, *p->T1);
-    p->T3 = mk(ctx, p->T1->inds, 1);                                  // [l' | (w r)]
+    p->T3 = mk_ws(ctx, p->T1->inds, 1, Ctx::SLOT_T3);                                  // [l' | (w r)]
     p->x2 = plan_transform(*p->T1, *p->T3, {0, 1, 2}, nullptr, {});
-    p->P = mk(ctx, {L.inds[0], R.inds[0]}, 1);
+    p->P = mk_ws(ctx, {L.inds[0], R.inds[0]}, 1, Ctx::SLOT_P);
     p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
     TNL_CHECK(p->P->nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
     p->flops = p->g1->flops + p->g4->flops;
@@ -662,11 +669,7 @@ LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter,
   const int howmany = 1;
   std::vector<double*> V;                  // Krylov basis (device buffers)
   // pads between charge groups must stay zero: the flat BLAS-1 kernels run over the padded buffer
-  auto newvec = [&]() {
-    double* p = (double*)ctx->alloc(n * sizeof(double));
-    CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(double), ctx->stream));
-    return p;
-  };
+  auto newvec = [&]() { return ctx->vec_acquire((size_t)n); };
   double* r = newvec();
   auto applyraw = [&](double* vin, double* vout) { if (sh) apply_local(vin, vout); else apply_ptr(phi, vin, vout); };
   // inner products: local partial sum, then a one-double all-reduce on the stream (no host round trip)
@@ -795,7 +798,7 @@ LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter,
         vec_lincomb(ctx, y, V.data(), coef.data(), K, n);
         newV.push_back(y);
       }
-      for (double* p : V) ctx->free(p);
+      for (double* p : V) ctx->vec_release(p, 0);
       V = newV;
       alphas.resize(keep);
       betas.resize(keep);
@@ -817,11 +820,11 @@ LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter,
     comm_allgather(ctx, phi_loc, ap->packed, ap->nloc);
     for (int k = 0; k < ctx->world; k++)
       run_transform(ctx, *ap->unpack[k], ap->packed + (int64_t)k * ap->nloc, phi_full, nullptr);
-    ctx->free(phi_loc);
+    ctx->vec_release(phi_loc, 0);
   }
   ctx->sync();
-  for (double* p : V) ctx->free(p);
-  if (std::find(V.begin(), V.end(), r) == V.end()) ctx->free(r);
+  for (double* p : V) ctx->vec_release(p, 0);
+  if (std::find(V.begin(), V.end(), r) == V.end()) ctx->vec_release(r, 0);
   res.eval = D[0];
   res.converged = converged;
   res.normres = std::fabs(f[0]);
@@ -841,10 +844,11 @@ TensorP Env::noise_tensor(const Tensor& phi, bool left) {
   if (left) {
     TensorP L = lproj();
     const TensorP& W1 = Wlr[first - 1];
-    auto T1 = std::make_shared<Tensor>(ctx, std::vector<Index>{L->inds[0], L->inds[1], phi.inds[1], phi.inds[2], phi.inds[3]}, 2);
+    ap.reset();                                     // reuse the apply workspaces (the plan dies with the bond anyway)
+    auto T1 = mk_ws(ctx, {L->inds[0], L->inds[1], phi.inds[1], phi.inds[2], phi.inds[3]}, 2, Ctx::SLOT_T1);
     auto g1 = plan_gemm(*L, false, phi, false, *T1);
     run_gemm(ctx, *g1, L->d, phi.d, T1->d);
-    auto X = std::make_shared<Tensor>(ctx, std::vector<Index>{L->inds[0], W1->inds[2], W1->inds[3], phi.inds[2], phi.inds[3]}, 2);
+    auto X = mk_ws(ctx, {L->inds[0], W1->inds[2], W1->inds[3], phi.inds[2], phi.inds[3]}, 2, Ctx::SLOT_T2);
     auto x = plan_transform(*T1, *X, {0, -1, -1, 3, 4}, W1.get(), {1, 2});
     run_transform(ctx, *x, T1->d, X->d, W1->d);
     ctx->sync();
@@ -853,10 +857,11 @@ TensorP Env::noise_tensor(const Tensor& phi, bool left) {
   TensorP R = relayout(ctx, *rproj(), 2);                       // [(r' w) | r]
   TensorP P3 = relayout(ctx, phi, 3);                           // [(l s1 s2) | r]
   const TensorP& W2 = Wnr[first];                               // (s, wr | wl, s')
-  auto Xa = std::make_shared<Tensor>(ctx, std::vector<Index>{phi.inds[0], phi.inds[1], phi.inds[2], R->inds[0], R->inds[1]}, 3);
+  ap.reset();
+  auto Xa = mk_ws(ctx, {phi.inds[0], phi.inds[1], phi.inds[2], R->inds[0], R->inds[1]}, 3, Ctx::SLOT_T1);
   auto g1 = plan_gemm(*P3, false, *R, true, *Xa);
   run_gemm(ctx, *g1, P3->d, R->d, Xa->d);
-  auto X = std::make_shared<Tensor>(ctx, std::vector<Index>{phi.inds[0], phi.inds[1], W2->inds[2], W2->inds[3], R->inds[0]}, 3);
+  auto X = mk_ws(ctx, {phi.inds[0], phi.inds[1], W2->inds[2], W2->inds[3], R->inds[0]}, 3, Ctx::SLOT_T2);
   auto x = plan_transform(*Xa, *X, {0, 1, -1, -1, 3}, W2.get(), {2, 4});
   run_transform(ctx, *x, Xa->d, X->d, W2->d);
   ctx->sync();

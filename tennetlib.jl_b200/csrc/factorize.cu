@@ -265,12 +265,14 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
   }
   for (FG& f : fg) f.nvals = which == 1 ? std::min(f.R, f.C) : (left ? f.R : f.C);
 
-  std::vector<void*> temps;
+  std::vector<void*> temps;                        // overflow allocations (arena too small this time)
+  ctx->arena_reset();
   auto talloc = [&](int64_t n) {
     n = (std::max<int64_t>(n, 1) + 1) & ~int64_t(1);
-    double* p = (double*)ctx->alloc(n * sizeof(double));
+    bool in_arena = false;
+    double* p = ctx->arena_alloc((size_t)n, &in_arena);
     CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(double), ctx->stream));
-    temps.push_back(p);
+    if (!in_arena) temps.push_back(p);
     return p;
   };
   std::vector<double> pool;
