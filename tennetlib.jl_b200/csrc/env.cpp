@@ -76,6 +76,19 @@ TensorP relayout(Ctx* ctx, const Tensor& t, int nrow) {
 }
 TensorP to_natural(Ctx* ctx, const Tensor& t) { return relayout(ctx, t, t.rank()); }
 
+// relayout into a persistent workspace slot (transient result)
+static TensorP relayout_ws(Ctx* ctx, const Tensor& t, int nrow, int slot) {
+  auto Y = std::make_shared<Tensor>(ctx, t.inds, nrow, false);
+  Y->d = ctx->scratch(slot, (size_t)Y->nelem, true);
+  Y->owns = false;
+  std::vector<int> xmap(t.rank());
+  std::iota(xmap.begin(), xmap.end(), 0);
+  auto plan = plan_transform(t, *Y, xmap, nullptr, {});
+  run_transform(ctx, *plan, t.d, Y->d, nullptr);
+  ctx->sync();
+  return Y;
+}
+
 static TensorP as_nrow(Ctx* ctx, const TensorP& t, int nrow) { return t->nrow == nrow ? t : relayout(ctx, *t, nrow); }
 
 // host permutation of a tiny tensor (MPO site operators)
@@ -189,7 +202,7 @@ void Env::makeL(int k) {
     auto x1 = plan_transform(*X1, *Y1, {0, -1, -1, 3}, W.get(), {1, 2});
     run_transform(ctx, *x1, X1->d, Y1->d, W->d);
     const Index& r = As->inds[2];
-    auto Ln = mk(ctx, {with_dir(r, -r.dir), Y1->inds[2], Y1->inds[3]}, 1);
+    auto Ln = mk_ws(ctx, {with_dir(r, -r.dir), Y1->inds[2], Y1->inds[3]}, 1, Ctx::SLOT_P);
     auto g2 = plan_gemm(*As, true, *Y1, false, *Ln, /*dagA=*/true);
     run_gemm(ctx, *g2, As->d, Y1->d, Ln->d);
     ctx->sync();
@@ -220,7 +233,7 @@ void Env::makeR(int k) {
     auto Z2 = mk_ws(ctx, {Z->inds[0], W->inds[2], W->inds[3], Z->inds[3]}, 2, Ctx::SLOT_T2);
     auto x1 = plan_transform(*Z, *Z2, {0, -1, -1, 3}, W.get(), {1, 2});
     run_transform(ctx, *x1, Z->d, Z2->d, W->d);
-    auto Rn = mk(ctx, {Z2->inds[0], Z2->inds[1], Aq->inds[0]}, 2);
+    auto Rn = mk_ws(ctx, {Z2->inds[0], Z2->inds[1], Aq->inds[0]}, 2, Ctx::SLOT_P);
     auto g2 = plan_gemm(*Z2, false, *Aq, true, *Rn);
     run_gemm(ctx, *g2, Z2->d, Aq->d, Rn->d);
     ctx->sync();
@@ -365,7 +378,8 @@ TensorP Env::make_phi(int pos) {
   TNL_CHECK(pos >= 1 && pos < N, "bond out of range");
   TensorP A1 = as_nrow(ctx, A[pos - 1], 2);
   TensorP A2 = as_nrow(ctx, A[pos], 1);
-  auto S = mk(ctx, {A1->inds[0], A1->inds[1], A2->inds[1], A2->inds[2]}, 2);
+  ap.reset();
+  auto S = mk_ws(ctx, {A1->inds[0], A1->inds[1], A2->inds[1], A2->inds[2]}, 2, Ctx::SLOT_T3);
   auto g = plan_gemm(*A1, false, *A2, false, *S);
   run_gemm(ctx, *g, A1->d, A2->d, S->d);
   ctx->sync();
@@ -876,7 +890,8 @@ FactorizeResult Env::replacebond(int pos, const Tensor& phi, FactorizeParams prm
     X = noise_tensor(phi, prm.ortho_left != 0);
     prm.noiseX = X.get();
   }
-  TensorP S = relayout(ctx, phi, 2);
+  ap.reset();
+  TensorP S = relayout_ws(ctx, phi, 2, Ctx::SLOT_T3);
   FactorizeResult f = factorize(ctx, *S, prm);
   if (normalize) {
     Tensor& t = prm.ortho_left ? *f.R : *f.L;
