@@ -221,6 +221,7 @@ def run_ours(args):
     sysenv.orthogonalize(b0)
     sysenv.set_nsite(2)
     sysenv.position(b0)
+    ctx.reserve(int(args.reserve_gb * (1 << 30)))      # pool head-room for the per-bond allocations of the sweep
     ctx.sync()
     t_setup = time.time() - t_setup
 
@@ -374,6 +375,8 @@ def main():
                     help="SVD driver of the truncation: gesvd, gesvdp (polar) or Gram-eigh with accuracy guard + gesvdp fallback")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
                     help="N>1: shard the H_eff apply of ONE sweep over the GPUs (strong scaling) or run independent replicas")
+    ap.add_argument("--reserve-gb", dest="reserve_gb", type=float, default=12.0,
+                    help="device memory pool head-room reserved before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu)")
     args = ap.parse_args()

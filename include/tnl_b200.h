@@ -40,6 +40,9 @@ const char* tnl_last_error(tnl_ctx_t ctx); /* ctx may be NULL: last error of the
 int tnl_get_counters(tnl_ctx_t ctx, double* out8);
 int tnl_reset_counters(tnl_ctx_t ctx);
 int tnl_ctx_sync(tnl_ctx_t ctx);
+/* pre-grow the context's device memory pool by `bytes` (kept mapped for the lifetime of the process) so that the
+ * per-bond allocations of a sweep never wait for the driver to map new physical memory */
+int tnl_ctx_reserve(tnl_ctx_t ctx, int64_t bytes);
 /* CUDA-event timing on the library's own stream (bench.py times kernels here, not on torch's stream). */
 int tnl_timer_start(tnl_ctx_t ctx, int32_t slot); /* slot 0..3 */
 int tnl_timer_stop(tnl_ctx_t ctx, int32_t slot, double* milliseconds);

@@ -27,6 +27,7 @@ _SIGS = {
     "tnl_get_counters": [_P, C.POINTER(C.c_double)],
     "tnl_reset_counters": [_P],
     "tnl_ctx_sync": [_P],
+    "tnl_ctx_reserve": [_P, C.c_int64],
     "tnl_timer_start": [_P, C.c_int32],
     "tnl_timer_stop": [_P, C.c_int32, C.POINTER(C.c_double)],
     "tnl_comm_unique_id": [C.c_char_p],

@@ -92,6 +92,16 @@ int tnl_get_counters(tnl_ctx_t c, double* o) {
   });
 }
 int tnl_reset_counters(tnl_ctx_t c) { return guard(&c->ctx, [&] { c->ctx.cnt = Counters(); }); }
+int tnl_ctx_reserve(tnl_ctx_t c, int64_t bytes) {
+  return guard(&c->ctx, [&] {
+    // grow the stream-ordered pool once (release threshold = never): later allocations are carved from it
+    // without asking the driver for new physical memory in the middle of a sweep
+    void* p = nullptr;
+    CUDA_OK(cudaMallocAsync(&p, (size_t)bytes, c->ctx.stream));
+    CUDA_OK(cudaFreeAsync(p, c->ctx.stream));
+    c->ctx.sync();
+  });
+}
 int tnl_ctx_sync(tnl_ctx_t c) { return guard(&c->ctx, [&] { c->ctx.sync(); }); }
 int tnl_timer_start(tnl_ctx_t c, int32_t slot) {
   return guard(&c->ctx, [&] {

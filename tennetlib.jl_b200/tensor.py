@@ -126,6 +126,10 @@ class Context:
     def sync(self):
         check(self.lib.tnl_ctx_sync(self.h), self.h)
 
+    def reserve(self, nbytes: int):
+        """Pre-grow the device memory pool (see tnl_ctx_reserve)."""
+        check(self.lib.tnl_ctx_reserve(self.h, int(nbytes)), self.h)
+
     # ---- multi-GPU (one process per GPU)
     def comm_unique_id(self) -> bytes:
         buf = C.create_string_buffer(128)
