@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {s}")
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-L/usr/local/cuda/lib64", "-lcusolver", "-lcudart", "-ldl",
+    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-L/usr/local/cuda/lib64", "-lcusolver", "-lcudart", "-ldl", "-lpthread",
                                                   "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
     return OUT

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <thread>
 
 #include "env.hpp"
 
@@ -394,22 +395,43 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
     std::vector<int> slot_of(todo.size());
     std::vector<int> used(sides.size(), 0);
     for (size_t k = 0; k < order.size(); k++) {
-      FG& f = *todo[order[k]];
-      const int64_t n = left ? f.R : f.C;
-      SideSolver& sv = sides[k % sides.size()];
-      int lwork = 0;
-      CUSOLVER_OK(cusolverDnDsyevd_bufferSize(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, f.E, (int)n,
-                                              Wvs[order[k]], &lwork));
-      if ((size_t)lwork * sizeof(double) > sv.bytes) {
-        CUDA_OK(cudaStreamSynchronize(sv.s));
-        if (sv.work) cudaFree(sv.work);
-        sv.bytes = (size_t)lwork * sizeof(double) * 5 / 4;
-        CUDA_OK(cudaMalloc(&sv.work, sv.bytes));
-      }
       TNL_CHECK(used[k % sides.size()] < 64, "too many charge groups per side stream");
       slot_of[order[k]] = used[k % sides.size()]++;
-      CUSOLVER_OK(cusolverDnDsyevd(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, f.E, (int)n,
-                                   Wvs[order[k]], sv.work, lwork, sv.info + slot_of[order[k]]));
+    }
+    // cusolverDnDsyevd is largely host-driven (its calls block while panels are factorised), so each side
+    // solver gets its own host thread: the decompositions of the large charge groups really run concurrently
+    std::vector<std::string> errs(sides.size());
+    auto worker = [&](size_t si) {
+      try {
+        CUDA_OK(cudaSetDevice(ctx->device));
+        SideSolver& sv = sides[si];
+        for (size_t k = si; k < order.size(); k += sides.size()) {
+          FG& f = *todo[order[k]];
+          const int64_t n = left ? f.R : f.C;
+          int lwork = 0;
+          CUSOLVER_OK(cusolverDnDsyevd_bufferSize(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, f.E,
+                                                  (int)n, Wvs[order[k]], &lwork));
+          if ((size_t)lwork * sizeof(double) > sv.bytes) {
+            CUDA_OK(cudaStreamSynchronize(sv.s));
+            if (sv.work) cudaFree(sv.work);
+            sv.bytes = (size_t)lwork * sizeof(double) * 5 / 4;
+            CUDA_OK(cudaMalloc(&sv.work, sv.bytes));
+          }
+          CUSOLVER_OK(cusolverDnDsyevd(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, f.E, (int)n,
+                                       Wvs[order[k]], sv.work, lwork, sv.info + slot_of[order[k]]));
+        }
+        CUDA_OK(cudaStreamSynchronize(sv.s));
+      } catch (const std::exception& e) {
+        errs[si] = e.what();
+      }
+    };
+    {
+      std::vector<std::thread> th;
+      const size_t nth = std::min(sides.size(), order.size());
+      for (size_t si = 1; si < nth; si++) th.emplace_back(worker, si);
+      if (nth > 0) worker(0);
+      for (auto& t : th) t.join();
+      for (auto& e : errs) TNL_CHECK(e.empty(), e);
     }
     for (auto& sv : sides) CUDA_OK(cudaStreamSynchronize(sv.s));
     for (size_t k = 0; k < order.size(); k++) {
