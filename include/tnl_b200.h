@@ -119,6 +119,11 @@ int tnl_heff_apply(tnl_env_t env, tnl_tensor_t v, tnl_tensor_t* out);
 int tnl_eigsolve_lanczos(tnl_env_t env, tnl_tensor_t phi, double tol, int32_t krylovdim, int32_t maxiter,
                          int32_t eager, double* eval, int32_t* converged, int32_t* numops, int32_t* numiter,
                          double* normres);
+/* exp_solver: src/base/solver.jl:66-88 -> KrylovKit.exponentiate(env, t, phi; Lanczos): phi <- exp(t * H_eff) phi in
+ * place, t = t_re + i t_im.  This build evolves real tensors only: t_im must be 0 (imaginary-time TDVP); a complex
+ * step returns status 2.  *err = accumulated error estimate (info.normres). */
+int tnl_exponentiate(tnl_env_t env, tnl_tensor_t phi, double t_re, double t_im, double tol, int32_t krylovdim,
+                     int32_t maxiter, int32_t eager, int32_t* converged, int32_t* numops, int32_t* numiter, double* err);
 /* real(scalar(dag(phi) * PH(phi))) : src/mps/update_site.jl:51-57 */
 int tnl_expectation(tnl_env_t env, tnl_tensor_t phi, double* e);
 /* noiseterm + replacebond! : src/mps/update_site.jl:59-76.  which_decomp low 4 bits: 0 = reference rule,
@@ -130,10 +135,14 @@ int tnl_replacebond(tnl_env_t env, int32_t pos, tnl_tensor_t phi, int32_t ortho_
 
 /* one-site update tail, src/mps/update_site.jl:158-186: U,S,V = svd(phi, uinds; maxdim, mindim, cutoff);
  * normalize!(S); psi[pos] = U; psi[posnext] = (S*V)*psi[posnext]  (posnext = pos+1 for ortho left, pos-1 for right).
- * svd_alg: 0 = gesvd, 1 = gesvdp, 2 = guarded Gram-eigh. */
+ * svd_alg: 0 = gesvd, 1 = gesvdp, 2 = guarded Gram-eigh.
+ * carry == NULL: as above.  carry != NULL (TDVP, update_site.jl:172-186): only psi[pos] = U is stored and
+ * *carry = S*V (ortho left) or U*S (ortho right) is returned; after the zero-site backward evolution the caller
+ * hands it to tnl_env_absorb_bond, which performs psi[posnext] = carry * psi[posnext]. */
 int tnl_svd_split(tnl_env_t env, int32_t pos, tnl_tensor_t phi, int32_t ortho_left, int64_t maxdim, int64_t mindim,
                   double cutoff, int32_t normalize, int32_t svd_alg, double* truncerr, double* eigs, int64_t cap,
-                  int64_t* neigs);
+                  int64_t* neigs, tnl_tensor_t* carry);
+int tnl_env_absorb_bond(tnl_env_t env, int32_t pos, int32_t ortho_left, tnl_tensor_t carry);
 
 #ifdef __cplusplus
 }

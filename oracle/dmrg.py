@@ -17,7 +17,7 @@ from typing import List, Sequence
 import numpy as np
 
 from .blocksparse import BSTensor, contract, factorize, inner
-from .krylov import eigsolve_lanczos
+from .krylov import eigsolve_lanczos, exponentiate
 from .projmpo import ProjMPO, ProjMPO_MPS2, drho_matrices
 
 FLOAT64_THRESHOLD = 1e-15          # src/base/global_variables.jl:10-26
@@ -141,6 +141,21 @@ def eig_solver(env, phi0, time_step=None, **kw):
     return val, vec
 
 
+def exp_solver(env, phi0, time_step, **kw):
+    """src/base/solver.jl:66-88 (returns NaN as energy: the caller evaluates <phi|H|phi>)."""
+    if time_step is None:
+        raise RuntimeError("`exp_solver()` is not defined with `time_step=None` !!")
+    psi, info = exponentiate(env, time_step, phi0,
+                             tol=kw.get("solver_tol", 1e-12),
+                             krylovdim=kw.get("solver_krylovdim", 30),
+                             maxiter=kw.get("solver_maxiter", 100),
+                             eager=kw.get("solver_eager", True))
+    if kw.get("solver_check_convergence", False) and info["converged"] < 1:
+        raise RuntimeError("`eig_solver()` not converged !!")          # message as in the reference (solver.jl:84)
+    exp_solver.last_info = info
+    return float("nan"), psi
+
+
 def halfsweep_done(N, pos, nsite, ortho):
     if pos == 1 and ortho == "right":
         return True
@@ -171,13 +186,23 @@ def _update_two_site(sysenv: StateEnvs, solver, pos, ortho, time_step, normalize
     spec = replacebond(psi, pos, phi, maxdim=maxdim, mindim=mindim, cutoff=cutoff, eigen_perturbation=drho,
                        ortho=ortho, normalize=normalize, which_decomp=None, svd_alg=svd_alg)
     if reverse_step and not halfsweep_done(len(sysenv), pos, 2, ortho):
-        raise NotImplementedError("TDVP reverse step: SURVEY.md section 8(f) next row")
+        # TDVP backward evolution of the new centre site (src/mps/update_site.jl:78-87)
+        pos1 = pos + 1 if ortho == "left" else pos
+        phi0 = psi[pos1]
+        sysenv.set_nsite(1)
+        sysenv.position(pos1)
+        energy, phi0 = solver(sysenv, phi0, -time_step, **kw)
+        if normalize:
+            phi0 = phi0.scale(1.0 / phi0.norm())
+        if np.isnan(energy):
+            energy = float(np.real(inner(phi0, sysenv.PH(phi0))))
+        psi[pos1] = phi0
     return energy, spec.truncerr, spec.eigs
 
 
 def _update_one_site(sysenv: StateEnvs, solver, pos, ortho, time_step, normalize, maxdim, mindim, cutoff,
                      svd_alg, noise, reverse_step, **kw):
-    """src/mps/update_site.jl:94-190 (DMRG branch; the TDVP reverse step is not restated)."""
+    """src/mps/update_site.jl:94-190."""
     psi = sysenv.psi
     assert 0 < pos <= len(sysenv)
     assert psi.orthocenter() == pos
@@ -207,8 +232,6 @@ def _update_one_site(sysenv: StateEnvs, solver, pos, ortho, time_step, normalize
                            ortho=ortho, normalize=normalize, which_decomp=None, svd_alg=svd_alg)
         sysenv.set_nsite(1)
         return energy, spec.truncerr, spec.eigs
-    if reverse_step:
-        raise NotImplementedError("TDVP reverse step: SURVEY.md section 8 row a7")
     nxt = psi[posnext]
     uinds = [ix for ix in phi.inds if ix not in nxt.inds]
     if ortho == "left":
@@ -217,8 +240,10 @@ def _update_one_site(sysenv: StateEnvs, solver, pos, ortho, time_step, normalize
         if normalize:
             R = R.scale(1.0 / R.norm())                                                    # normalize!(S)
         psi[pos] = U
-        psi[posnext] = contract(R, nxt)
         psi.llim, psi.rlim = pos, pos + 2
+        if reverse_step:
+            energy, R = _reverse_zero_site(sysenv, solver, R, pos + 1, time_step, normalize, **kw)
+        psi[posnext] = contract(R, nxt)
     else:
         left = [ix for ix in phi.inds if ix not in uinds]
         L, V, spec, u = factorize(phi, left, ortho="right", maxdim=maxdim, mindim=mindim, cutoff=cutoff,
@@ -226,9 +251,23 @@ def _update_one_site(sysenv: StateEnvs, solver, pos, ortho, time_step, normalize
         if normalize:
             L = L.scale(1.0 / L.norm())
         psi[pos] = V
-        psi[posnext] = contract(nxt, L)
         psi.llim, psi.rlim = pos - 2, pos
+        if reverse_step:
+            energy, L = _reverse_zero_site(sysenv, solver, L, pos, time_step, normalize, **kw)
+        psi[posnext] = contract(nxt, L)
     return energy, spec.truncerr, spec.eigs
+
+
+def _reverse_zero_site(sysenv, solver, phi0, pos1, time_step, normalize, **kw):
+    """TDVP backward evolution of the bond matrix (src/mps/update_site.jl:178-185)."""
+    sysenv.set_nsite(0)
+    sysenv.position(pos1)
+    energy, phi0 = solver(sysenv, phi0, -time_step, **kw)
+    if normalize:
+        phi0 = phi0.scale(1.0 / phi0.norm())
+    if np.isnan(energy):
+        energy = float(np.real(inner(phi0, sysenv.PH(phi0))))
+    return energy, phi0
 
 
 def update_position(sysenv: StateEnvs, solver, pos, nsite, ortho, **kw):
@@ -361,3 +400,30 @@ def dmrg1(psi0: MPS, H, params: DMRGParams, **kw):
     sysenv = StateEnvs(psi0, H)
     sw = dmrg_(sysenv, params, 1, **kw)
     return sw.energy[-1], sysenv.psi, sw
+
+
+class TDVPEngine:
+    """src/mps/tdvp.jl:17-66."""
+
+    def __init__(self, psi: MPS, H, Ms=None, weight: float = -1.0):
+        self.sysenv = StateEnvs(psi, H, Ms, weight)
+        self.swdata = SweepData()
+        self.abstime = 0.0
+
+    def getpsi(self):
+        return self.sysenv.psi.copy()
+
+
+def tdvpsweep(engine: TDVPEngine, time_step, nsite=2, solver=exp_solver, **kw):
+    """`tdvpsweep!` src/mps/tdvp.jl:247-277: psi' = exp(time_step * H) psi, second-order sweep
+    (half a step left-to-right, half a step right-to-left, backward steps in between)."""
+    if solver is not exp_solver:
+        raise RuntimeError("`tdvpsweep!()`: `solver` must be `exp_solver` !!")
+    if nsite in (1, 2):
+        if kw.get("extendat", None) is not None:
+            raise RuntimeError("`tdvpsweep!()`: `extendat` must be `nothing` for `nsite == 2` or `nsite == 1`.")
+        kw.pop("extendat", None)
+        fullsweep(engine.sysenv, solver, nsite, engine.swdata, time_step=0.5 * time_step, reverse_step=True, **kw)
+    else:
+        raise NotImplementedError("dynamic_fullsweep! needs krylov_extend! (SURVEY.md section 8f rank 1)")
+    engine.abstime += abs(time_step)

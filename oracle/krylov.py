@@ -179,3 +179,137 @@ def eigsolve_lanczos(A: Callable, x0, tol: float = 1e-14, krylovdim: int = 5, ma
         vec = ops.add(vec, V[i], U[i, 0])
     info = dict(converged=converged, normres=abs(f[0]), numiter=numiter, numops=numops)
     return float(D[0]), vec, info
+
+
+# ---------------------------------------------------------------------------------------------------
+# exponentiate -- restatement of KrylovKit.jl `exponentiate(A, t, x0; Lanczos)` = `expintegrator` with p = 1
+# (third-party, not vendored; reached from `exp_solver`, /root/reference/src/base/solver.jl:66-88, with
+# krylovdim=30, maxiter=100, tol=1e-12, eager=true).  Published algorithm (Niesen & Wright style phi-function
+# integrator): u(t) = u0 + t*phi_1(tA) A u0.  One extra apply w1 = A u0 (beta = ||w1||), Lanczos factorisation
+# started from w1 (`initialize` / `expand!` exactly as in eigsolve above), small dense exponential of the
+# (K+2)x(K+2) augmented matrix [[s*dt*T, e1, 0], [0, 0, 1], [0, 0, 0]] whose column K+1 holds phi_1 and column
+# K+2 holds phi_2, error estimate eps = |dt * beta * normres * expH[K, K+2]| against eta = tol/|t| per unit
+# time, adaptive sub-stepping (safety factors delta = 1.2, gamma = 0.8) when the basis is full, eager exit at
+# every K, first-correction term residual * expH[K, K+2].
+def _aug_exp(alphas, betas, K, s_dt):
+    from scipy.linalg import expm
+    dt = np.result_type(np.asarray(s_dt).dtype, np.float64)
+    H = np.zeros((K + 2, K + 2), dtype=dt)
+    for j in range(K):
+        H[j, j] = alphas[j] * s_dt
+    for j in range(K - 1):
+        H[j, j + 1] = H[j + 1, j] = betas[j] * s_dt
+    H[0, K] = 1.0
+    H[K, K + 1] = 1.0
+    return expm(H)
+
+
+def exponentiate(A: Callable, t, x0, tol: float = 1e-12, krylovdim: int = 30, maxiter: int = 100,
+                 eager: bool = True, ops=VecOps):
+    """Returns (exp(t*A) x0, info) with info = dict(converged, normres (= total error), numiter, numops)."""
+    cplx = isinstance(t, complex) or np.iscomplexobj(t)
+    t = complex(t) if cplx else float(t)
+    tau = abs(t)
+    if tau == 0:
+        return ops.scale(x0, 1.0), dict(converged=1, normres=0.0, numiter=0, numops=0)
+    sgn = t / tau
+    tau0 = 0.0
+    dtau = tau - tau0
+    delta, gamma = 1.2, 0.8
+    eta = tol / tau
+    totalerr = 0.0
+    w0 = ops.scale(x0, 1.0 + 0.0j if cplx else 1.0)
+    w1 = A(w0)
+    numops = 1
+    beta = ops.norm(w1)
+    if beta < tol:
+        return w0, dict(converged=1, normres=beta, numiter=0, numops=numops)
+
+    def lanczos_init(x):
+        b0 = ops.norm(x)
+        Ax = A(x)
+        al = ops.inner(x, Ax) / (b0 * b0)
+        v = ops.scale(x, 1.0 / b0)
+        r = ops.scale(Ax, 1.0 / b0)
+        r = ops.add(r, v, -al)
+        da = ops.inner(v, r)
+        al = al + da
+        r = ops.add(r, v, -da)
+        return [v], [float(np.real(al))], [ops.norm(r)], r
+
+    V, alphas, betas, r = lanczos_init(w1)
+    numops += 1
+    numiter = 1
+
+    def step(dt_):
+        """small exponential, error estimate"""
+        K = len(alphas)
+        E = _aug_exp(alphas, betas, K, sgn * dt_)
+        eps = abs(dt_ * beta * betas[-1] * E[K - 1, K + 1])
+        return E, eps
+
+    def take(E, dt_):
+        nonlocal w0
+        K = len(alphas)
+        y = ops.scale(V[0], E[0, K])
+        for i in range(1, K):
+            y = ops.add(y, V[i], E[i, K])
+        y = ops.add(y, r, E[K - 1, K + 1])           # first correction
+        w0 = ops.add(w0, y, beta * sgn * dt_)
+
+    while True:
+        K = len(alphas)
+        if K == krylovdim:
+            dtau = min(dtau, tau - tau0)
+            E, eps = step(dtau)
+            omega = eps / (dtau * eta)
+            q = K / 2
+            while omega > 1:
+                eps_prev, dtau_prev = eps, dtau
+                dtau *= (gamma / omega) ** (1.0 / (q + 1))
+                E, eps = step(dtau)
+                omega = eps / (dtau * eta)
+                q = max(0.0, np.log(eps / eps_prev) / np.log(dtau / dtau_prev) - 1)
+            totalerr += eps
+            take(E, dtau)
+            tau0 += dtau
+            if omega < gamma:
+                dtau *= (gamma / omega) ** (1.0 / (q + 1)) if omega > 0 else delta
+        elif betas[-1] <= (tau - tau0) * eta or eager:
+            E, eps = step(tau - tau0)
+            omega = eps / ((tau - tau0) * eta)
+            if omega < 1:
+                totalerr += eps
+                take(E, tau - tau0)
+                tau0 = tau
+        if tau0 >= tau:
+            return w0, dict(converged=1, normres=totalerr, numiter=numiter, numops=numops)
+        if K < krylovdim:
+            # expand! + lanczosrecurrence (ModifiedGramSchmidt2), as in eigsolve_lanczos
+            bold = betas[-1]
+            vnew = ops.scale(r, 1.0 / bold)
+            V.append(vnew)
+            w = A(vnew)
+            numops += 1
+            w = ops.add(w, V[-2], -bold)
+            a = ops.inner(vnew, w)
+            w = ops.add(w, vnew, -a)
+            s = a
+            for qv in V:
+                s = ops.inner(qv, w)
+                w = ops.add(w, qv, -s)
+            a = a + s
+            alphas.append(float(np.real(a)))
+            betas.append(ops.norm(w))
+            r = w
+        else:
+            if numiter == maxiter:
+                return w0, dict(converged=0, normres=totalerr, numiter=numiter, numops=numops)
+            numiter += 1
+            w1 = A(w0)
+            numops += 1
+            beta = ops.norm(w1)
+            if beta < tol:
+                return w0, dict(converged=1, normres=beta, numiter=numiter, numops=numops)
+            V, alphas, betas, r = lanczos_init(w1)
+            numops += 1

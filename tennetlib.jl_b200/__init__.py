@@ -8,9 +8,10 @@ from .dmrg import DMRGParams, dmrg, dmrg1, dmrg2, dmrg_
 from .solver import eig_solver, exp_solver
 from .state_envs import StateEnvs
 from .sweep import SweepData, fullsweep
+from .tdvp import TDVPEngine, getenergy, getentropy, maxchi, sweepcount, tdvpsweep, totalerror
 from .tensor import Context, DeviceTensor, HostTensor, Index
 from .update_site import halfsweep_done, update_position
 
 __all__ = ["Context", "DeviceTensor", "HostTensor", "Index", "StateEnvs", "eig_solver", "exp_solver",
            "update_position", "halfsweep_done", "fullsweep", "SweepData", "DMRGParams", "dmrg_", "dmrg", "dmrg1", "dmrg2",
-           "load", "so_path", "TnlError", "EXPORTED"]
+           "TDVPEngine", "tdvpsweep", "sweepcount", "getenergy", "getentropy", "maxchi", "totalerror", "load", "so_path", "TnlError", "EXPORTED"]

@@ -70,7 +70,10 @@ _SIGS = {
                              C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)],
     "tnl_expectation": [_P, _P, C.POINTER(C.c_double)],
     "tnl_svd_split": [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.c_int32,
-                      C.POINTER(C.c_double), _P, C.c_int64, C.POINTER(C.c_int64)],
+                      C.POINTER(C.c_double), _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(_P)],
+    "tnl_env_absorb_bond": [_P, C.c_int32, C.c_int32, _P],
+    "tnl_exponentiate": [_P, _P, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
+                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)],
     "tnl_replacebond": [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int32,
                         C.c_int32, C.POINTER(C.c_double), _P, C.c_int64, C.POINTER(C.c_int64)],
 }

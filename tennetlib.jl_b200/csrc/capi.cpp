@@ -368,6 +368,17 @@ int tnl_eigsolve_lanczos(tnl_env_t e, tnl_tensor_t phi, double tol, int32_t kryl
     *eval = r.eval; *converged = r.converged; *numops = r.numops; *numiter = r.numiter; *normres = r.normres;
   });
 }
+int tnl_exponentiate(tnl_env_t e, tnl_tensor_t phi, double t_re, double t_im, double tol, int32_t krylovdim,
+                     int32_t maxiter, int32_t eager, int32_t* converged, int32_t* numops, int32_t* numiter, double* err) {
+  return guard(e->env.ctx, [&] {
+    if (phi->t->nrow != 1) phi->t = relayout(e->env.ctx, *phi->t, 1);
+    ExpResult r = e->env.exponentiate(*phi->t, t_re, t_im, tol, krylovdim, maxiter, eager != 0);
+    *converged = r.converged; *numops = r.numops; *numiter = r.numiter; *err = r.err;
+  });
+}
+int tnl_env_absorb_bond(tnl_env_t e, int32_t pos, int32_t ortho_left, tnl_tensor_t carry) {
+  return guard(e->env.ctx, [&] { e->env.absorb_bond(pos, ortho_left != 0, *carry->t); });
+}
 int tnl_expectation(tnl_env_t e, tnl_tensor_t phi, double* out) {
   return guard(e->env.ctx, [&] {
     TensorP vq = phi->t->nrow == 1 ? phi->t : relayout(e->env.ctx, *phi->t, 1);
@@ -396,7 +407,7 @@ int tnl_replacebond(tnl_env_t e, int32_t pos, tnl_tensor_t phi, int32_t ortho_le
 
 int tnl_svd_split(tnl_env_t e, int32_t pos, tnl_tensor_t phi, int32_t ortho_left, int64_t maxdim, int64_t mindim,
                   double cutoff, int32_t normalize, int32_t svd_alg, double* truncerr, double* eigs, int64_t cap,
-                  int64_t* neigs) {
+                  int64_t* neigs, tnl_tensor_t* carry) {
   return guard(e->env.ctx, [&] {
     FactorizeParams prm;
     prm.ortho_left = ortho_left;
@@ -404,7 +415,8 @@ int tnl_svd_split(tnl_env_t e, int32_t pos, tnl_tensor_t phi, int32_t ortho_left
     prm.mindim = mindim;
     prm.cutoff = cutoff;
     prm.svd_alg = svd_alg;
-    FactorizeResult f = e->env.svd_split(pos, *phi->t, prm, normalize != 0);
+    FactorizeResult f = e->env.svd_split(pos, *phi->t, prm, normalize != 0, carry == nullptr);
+    if (carry) *carry = new tnl_tensor_s{ortho_left ? f.R : f.L};
     *truncerr = f.truncerr;
     *neigs = (int64_t)f.eigs.size();
     for (int64_t i = 0; i < std::min<int64_t>(cap, *neigs); i++) eigs[i] = f.eigs[i];

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <complex>
 #include <cstring>
 #include <numeric>
 
@@ -845,6 +846,196 @@ LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter,
   return res;
 }
 
+// ------------------------------------------------------------------------------ exponentiate
+// phi_1(z) = (e^z - 1)/z and phi_2(z) = (e^z - 1 - z)/z^2, series for small |z|
+static std::complex<double> phi_fn(std::complex<double> z, int order) {
+  if (std::abs(z) < 0.5) {
+    std::complex<double> term = order == 1 ? 1.0 : 0.5, sum = 0.0;
+    for (int k = 0; k < 30; k++) { sum += term; term *= z / double(k + order + 1); }
+    return sum;
+  }
+  const std::complex<double> e = std::exp(z);
+  return order == 1 ? (e - 1.0) / z : (e - 1.0 - z) / (z * z);
+}
+
+// Restatement of KrylovKit.exponentiate(A, t, x0; Lanczos(krylovdim, maxiter, tol, eager)) = expintegrator with
+// p = 1 (reference call site src/base/solver.jl:66-88): u(t) = u0 + t phi_1(tA) A u0.  One extra apply w1 = A u0,
+// Lanczos factorisation started from w1 (MGS2, same recurrence as eigsolve), columns K+1 / K+2 of the exponential
+// of the augmented (K+2)x(K+2) matrix = phi_1(s dt T) e1 / phi_2(s dt T) e1 (evaluated through the eigensystem of
+// the real tridiagonal T on the host), error estimate |dt beta normres expH[K,K+2]| against eta = tol/|t| per
+// unit time, adaptive sub-steps (gamma = 0.8) when the basis is full, eager exit at every K, first-correction
+// term.  The same algorithm is restated independently in oracle/krylov.py.  All vectors stay in HBM.
+ExpResult Env::exponentiate(Tensor& phi, double t_re, double t_im, double tol, int krylovdim, int maxiter, bool eager) {
+  TNL_CHECK(t_im == 0.0, "complex time steps need complex tensors: this build evolves in real (imaginary-time) steps only");
+  TNL_CHECK(krylovdim >= 1 && krylovdim < LC_MAX_HOST, "krylovdim out of range");
+  ExpResult res;
+  const double t = t_re;
+  const double tau = std::fabs(t);
+  if (tau == 0.0) { res.converged = 1; return res; }
+  ensure_plan(phi);
+  const bool sh = ap->sharded;
+  const int64_t n = sh ? ap->nloc : phi.nelem;
+  const double sgn = t / tau;
+  auto newvec = [&]() { return ctx->vec_acquire((size_t)n); };
+  auto applyraw = [&](double* vin, double* vout) { if (sh) apply_local(vin, vout); else apply_ptr(phi, vin, vout); res.numops++; };
+  auto dot = [&](const double* x, const double* y, int slot) {
+    tnl::vec_dot(ctx, x, y, n, slot);
+    if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + slot, 1);
+  };
+  double* w0 = phi.d;
+  double* phi_loc = nullptr;
+  if (sh) {
+    phi_loc = newvec();
+    run_transform(ctx, *ap->xs, phi.d, phi_loc, nullptr);
+    w0 = phi_loc;
+  }
+  std::vector<double*> V;
+  std::vector<double> alphas, betas;
+  double* r = nullptr;
+  double* w1 = newvec();
+  double beta = 0.0;
+  auto release_basis = [&]() {
+    for (double* p : V) ctx->vec_release(p, 0);
+    V.clear();
+    if (r) ctx->vec_release(r, 0);
+    r = nullptr;
+  };
+  // LanczosIterator initialize on x = w1 (not consumed)
+  auto lanczos_init = [&]() {
+    release_basis();
+    alphas.clear(); betas.clear();
+    r = newvec();
+    applyraw(w1, r);
+    dot(w1, r, 0);
+    fetch_scalars(ctx, 1);
+    double alpha = ctx->h_scalars[0] / (beta * beta);
+    double* v0 = newvec();
+    vec_scale_to(ctx, v0, w1, n, 1.0 / beta);
+    vec_scale(ctx, r, n, 1.0 / beta);
+    vec_axpy(ctx, r, v0, n, -alpha);
+    dot(v0, r, 0);
+    vec_axpy_dev(ctx, r, v0, n, 0, -1.0);
+    dot(r, r, 1);
+    fetch_scalars(ctx, 2);
+    alphas.push_back(alpha + ctx->h_scalars[0]);
+    betas.push_back(std::sqrt(ctx->h_scalars[1]));
+    V.push_back(v0);
+  };
+  auto start = [&]() -> bool {          // w1 = A w0, beta = |w1|; false: w0 is a fixed point
+    applyraw(w0, w1);
+    dot(w1, w1, 0);
+    fetch_scalars(ctx, 1);
+    beta = std::sqrt(ctx->h_scalars[0]);
+    return beta >= tol;
+  };
+  // small exponential: c1 = phi_1(s dt T) e1, c2last = [phi_2(s dt T) e1]_K ; returns the error estimate
+  std::vector<double> c1;
+  double c2last = 0.0;
+  auto small_exp = [&](double dt) {
+    const int K = (int)alphas.size();
+    std::vector<double> T((size_t)K * K, 0.0), D, Q;
+    for (int j = 0; j < K; j++) T[(size_t)j * K + j] = alphas[j];
+    for (int j = 0; j + 1 < K; j++) T[(size_t)j * K + j + 1] = T[(size_t)(j + 1) * K + j] = betas[j];
+    if (K == 1) { D = {alphas[0]}; Q = {1.0}; } else sym_eig(K, T, D, Q);
+    c1.assign(K, 0.0);
+    c2last = 0.0;
+    for (int j = 0; j < K; j++) {
+      const double p1 = phi_fn(sgn * dt * D[j], 1).real(), p2 = phi_fn(sgn * dt * D[j], 2).real();
+      const double q0 = Q[(size_t)0 * K + j];
+      for (int i = 0; i < K; i++) c1[i] += Q[(size_t)i * K + j] * p1 * q0;
+      c2last += Q[(size_t)(K - 1) * K + j] * p2 * q0;
+    }
+    return std::fabs(dt * beta * betas.back() * c2last);
+  };
+  // w0 += beta * s * dt * (V c1 + c2last * r)
+  auto take = [&](double dt) {
+    const int K = (int)alphas.size();
+    std::vector<const double*> xs(V.begin(), V.begin() + K);
+    std::vector<double> cf(c1);
+    xs.push_back(r);
+    cf.push_back(c2last);
+    double* y = newvec();
+    vec_lincomb(ctx, y, xs.data(), cf.data(), K + 1, n);
+    vec_axpy(ctx, w0, y, n, beta * sgn * dt);
+    ctx->vec_release(y, 0);
+  };
+  const double gamma = 0.8;
+  const double eta = tol / tau;
+  double tau0 = 0.0, dtau = tau, totalerr = 0.0;
+  res.numiter = 1;
+  bool fixed_point = !start();
+  if (!fixed_point) lanczos_init();
+  while (!fixed_point) {
+    const int K = (int)alphas.size();
+    if (K == krylovdim) {
+      dtau = std::min(dtau, tau - tau0);
+      double eps = small_exp(dtau);
+      double omega = eps / (dtau * eta);
+      double q = K / 2.0;
+      while (omega > 1.0) {
+        const double eps_prev = eps, dtau_prev = dtau;
+        dtau *= std::pow(gamma / omega, 1.0 / (q + 1.0));
+        eps = small_exp(dtau);
+        omega = eps / (dtau * eta);
+        q = std::max(0.0, std::log(eps / eps_prev) / std::log(dtau / dtau_prev) - 1.0);
+      }
+      totalerr += eps;
+      take(dtau);
+      tau0 += dtau;
+      if (omega < gamma) dtau *= omega > 0.0 ? std::pow(gamma / omega, 1.0 / (q + 1.0)) : 1.2;
+    } else if (betas.back() <= (tau - tau0) * eta || eager) {
+      const double eps = small_exp(tau - tau0);
+      const double omega = eps / ((tau - tau0) * eta);
+      if (omega < 1.0) {
+        totalerr += eps;
+        take(tau - tau0);
+        tau0 = tau;
+      }
+    }
+    if (tau0 >= tau) { res.converged = 1; break; }
+    if (K < krylovdim) {
+      // expand! + lanczosrecurrence (ModifiedGramSchmidt2)
+      const double bold = betas.back();
+      double* vnew = r;
+      vec_scale(ctx, vnew, n, 1.0 / bold);
+      V.push_back(vnew);
+      double* w = newvec();
+      r = nullptr;
+      applyraw(vnew, w);
+      const int m = (int)V.size();
+      vec_axpy(ctx, w, V[m - 2], n, -bold);
+      dot(vnew, w, 0);
+      vec_axpy_dev(ctx, w, vnew, n, 0, -1.0);
+      for (int qi = 0; qi < m; qi++) {
+        dot(V[qi], w, 1 + qi);
+        vec_axpy_dev(ctx, w, V[qi], n, 1 + qi, -1.0);
+      }
+      dot(w, w, 1 + m);
+      fetch_scalars(ctx, 2 + m);
+      alphas.push_back(ctx->h_scalars[0] + ctx->h_scalars[m]);
+      betas.push_back(std::sqrt(ctx->h_scalars[1 + m]));
+      r = w;
+    } else {
+      if (res.numiter == maxiter) { res.converged = 0; break; }
+      res.numiter++;
+      if (!start()) { fixed_point = true; break; }
+      lanczos_init();
+    }
+  }
+  if (fixed_point) { res.converged = 1; totalerr = beta; }
+  release_basis();
+  ctx->vec_release(w1, 0);
+  if (sh) {
+    comm_allgather(ctx, phi_loc, ap->packed, ap->nloc);
+    for (int k = 0; k < ctx->world; k++)
+      run_transform(ctx, *ap->unpack[k], ap->packed + (int64_t)k * ap->nloc, phi.d, nullptr);
+    ctx->vec_release(phi_loc, 0);
+  }
+  ctx->sync();
+  res.err = totalerr;
+  return res;
+}
+
 }  // namespace tnl
 
 namespace tnl {
@@ -909,7 +1100,7 @@ FactorizeResult Env::replacebond(int pos, const Tensor& phi, FactorizeParams prm
 
 // One-site split (src/mps/update_site.jl:158-186 without the TDVP reverse step):
 //   U, S, V = svd(phi, uinds; maxdim, mindim, cutoff); normalize!(S); psi[pos] = U; psi[posnext] = (S*V) * psi[posnext]
-FactorizeResult Env::svd_split(int pos, const Tensor& phi, FactorizeParams prm, bool normalize) {
+FactorizeResult Env::svd_split(int pos, const Tensor& phi, FactorizeParams prm, bool normalize, bool absorb) {
   TNL_CHECK(pos >= 1 && pos <= N && phi.rank() == 3, "svd_split: bad site / tensor");
   prm.which = 1;                                    // `svd`, not `factorize`: always the SVD path
   prm.noise = 0.0;
@@ -925,27 +1116,38 @@ FactorizeResult Env::svd_split(int pos, const Tensor& phi, FactorizeParams prm, 
     TNL_CHECK(nrm > 0, "svd_split: zero norm");
     vec_scale(ctx, carry.d, carry.nelem, 1.0 / nrm);
   }
+  A[pos - 1] = left ? f.L : f.R;
+  invalidate(pos, pos);
+  if (absorb) absorb_bond(pos, left, left ? *f.R : *f.L);
+  return f;
+}
+
+// psi[posnext] = carry * psi[posnext]  (src/mps/update_site.jl:186); carry = (m, r) [left] or (l, m) [right]
+void Env::absorb_bond(int pos, bool left, const Tensor& carry) {
+  TNL_CHECK(carry.rank() == 2, "absorb: the bond tensor must have two indices");
   if (left) {
-    A[pos - 1] = f.L;
+    TNL_CHECK(pos < N, "absorb: no right neighbour");
+    TensorP C1 = carry.nrow == 1 ? nullptr : relayout(ctx, carry, 1);
+    const Tensor& Cm = C1 ? *C1 : carry;
     TensorP nx = as_nrow(ctx, A[pos], 1);
-    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{f.R->inds[0], nx->inds[1], nx->inds[2]}, 1);
-    auto g = plan_gemm(*f.R, false, *nx, false, *An);
-    run_gemm(ctx, *g, f.R->d, nx->d, An->d);
+    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{Cm.inds[0], nx->inds[1], nx->inds[2]}, 1);
+    auto g = plan_gemm(Cm, false, *nx, false, *An);
+    run_gemm(ctx, *g, Cm.d, nx->d, An->d);
     ctx->sync();
     A[pos] = An;
-    invalidate(pos, pos + 1);
+    invalidate(pos + 1, pos + 1);
   } else {
-    A[pos - 1] = f.R;
+    TNL_CHECK(pos > 1, "absorb: no left neighbour");
     TensorP pv = as_nrow(ctx, A[pos - 2], 2);
-    TensorP Cm = as_nrow(ctx, f.L, 1);
-    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{pv->inds[0], pv->inds[1], f.L->inds[1]}, 2);
-    auto g = plan_gemm(*pv, false, *Cm, false, *An);
-    run_gemm(ctx, *g, pv->d, Cm->d, An->d);
+    TensorP C1 = carry.nrow == 1 ? nullptr : relayout(ctx, carry, 1);
+    const Tensor& Cm = C1 ? *C1 : carry;
+    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{pv->inds[0], pv->inds[1], Cm.inds[1]}, 2);
+    auto g = plan_gemm(*pv, false, Cm, false, *An);
+    run_gemm(ctx, *g, pv->d, Cm.d, An->d);
     ctx->sync();
     A[pos - 2] = An;
-    invalidate(pos - 1, pos);
+    invalidate(pos - 1, pos - 1);
   }
-  return f;
 }
 
 // ITensorMPS `orthogonalize!`: QR gauge moves of the centre from site `from` to site `to` (no truncation).

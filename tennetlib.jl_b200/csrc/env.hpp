@@ -48,6 +48,14 @@ struct LanczosResult {
   double normres = 0;
 };
 
+struct ExpResult {
+  int converged = 0;
+  int numops = 0;
+  int numiter = 0;
+  double err = 0;               // accumulated error estimate (KrylovKit info.normres)
+};
+constexpr int LC_MAX_HOST = 32;   // vec_lincomb takes at most this many vectors (krylovdim + residual)
+
 class Env {
  public:
   Ctx* ctx;
@@ -85,9 +93,13 @@ class Env {
   void apply_local(const double* vloc, double* outloc);   // sharded core (multi-GPU)
   void ensure_plan(const Tensor& proto);
   LanczosResult eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter, bool eager);
+  // exp_solver: phi <- exp(t * H_eff) phi  (KrylovKit.exponentiate)
+  ExpResult exponentiate(Tensor& phi, double t_re, double t_im, double tol, int krylovdim, int maxiter, bool eager);
   double expectation(const Tensor& phi);
   FactorizeResult replacebond(int pos, const Tensor& phi, FactorizeParams prm, bool normalize);
-  FactorizeResult svd_split(int pos, const Tensor& phi, FactorizeParams prm, bool normalize);
+  // absorb = false: psi[pos] = U only; the caller evolves the bond tensor (TDVP reverse step) and calls absorb_bond
+  FactorizeResult svd_split(int pos, const Tensor& phi, FactorizeParams prm, bool normalize, bool absorb = true);
+  void absorb_bond(int pos, bool left, const Tensor& carry);
   void move_center(int from, int to);                   // QR gauge moves, ITensorMPS orthogonalize!
   double apply_flops() const;                           // algorithmic flops of one H_eff apply at the current position
 

@@ -29,5 +29,24 @@ def eig_solver(env, phi0, time_step=None, **kwargs):
 
 
 def exp_solver(env, phi0, time_step, **kwargs):
-    """src/base/solver.jl:66-88 -- TDVP exponentiation: SURVEY.md section 8 row a7, not built yet."""
-    raise NotImplementedError("exp_solver (KrylovKit.exponentiate) is a later row of the scope table")
+    """src/base/solver.jl:66-88: phi <- exp(time_step * H_eff) phi0 with KrylovKit.exponentiate's Lanczos
+    integrator on the device (`tnl_exponentiate`).  Returns (NaN, phi) like the reference; the caller evaluates
+    the energy.  Complex time steps need complex tensors, which this build does not have: the C ABI rejects them."""
+    if time_step is None:
+        raise RuntimeError(f"`exp_solver()` is not defined with `time_step={time_step}` !!")
+    if not kwargs.get("ishermitian", True):
+        raise NotImplementedError("device exp_solver supports ishermitian=true")
+    t = complex(time_step)
+    tol = kwargs.get("solver_tol", 1e-12)
+    krylovdim = kwargs.get("solver_krylovdim", 30)
+    maxiter = kwargs.get("solver_maxiter", 100)
+    eager = kwargs.get("solver_eager", True)
+    conv, nops, nit, err = C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
+    check(env.ctx.lib.tnl_exponentiate(env.h, phi0.h, t.real, t.imag, float(tol), int(krylovdim), int(maxiter),
+                                       1 if eager else 0, C.byref(conv), C.byref(nops), C.byref(nit), C.byref(err)),
+          env.ctx.h)
+    env.last_solver_info = dict(converged=conv.value, numops=nops.value, numiter=nit.value, normres=err.value,
+                                apply_flops=env.apply_flops())
+    if kwargs.get("solver_check_convergence", False) and conv.value < 1:
+        raise RuntimeError("`eig_solver()` not converged !!")      # message as in the reference (solver.jl:84)
+    return float("nan"), phi0

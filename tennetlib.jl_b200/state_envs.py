@@ -118,22 +118,29 @@ class StateEnvs:
         check(self.ctx.lib.tnl_env_set_state(self.h, j, t.h), self.ctx.h)
 
     def svd_split(self, pos: int, phi: DeviceTensor, *, maxdim, mindim, cutoff, ortho, normalize,
-                  svd_alg="divide_and_conquer"):
-        """One-site tail (update_site.jl:158-186): psi[pos] = U, psi[posnext] = (S*V)*psi[posnext]."""
+                  svd_alg="divide_and_conquer", absorb: bool = True):
+        """One-site tail (update_site.jl:158-186): psi[pos] = U, psi[posnext] = (S*V)*psi[posnext].
+        absorb=False (TDVP): returns (truncerr, eigs, S*V) and leaves psi[posnext] alone -- see absorb_bond."""
         cap = 1 << 16
         eigs = np.zeros(cap)
         truncerr = C.c_double()
         neigs = C.c_int64()
+        carry = C.c_void_p()
         md = 0 if maxdim is None or maxdim >= (1 << 62) else int(maxdim)
         alg = {"divide_and_conquer": 0, "qr_iteration": 0, "recursive": 0, "polar": 1, "gram": 2}[svd_alg]
         check(self.ctx.lib.tnl_svd_split(self.h, pos, phi.h, 1 if ortho == "left" else 0, md, int(mindim), float(cutoff),
                                          1 if normalize else 0, alg, C.byref(truncerr), eigs.ctypes.data, cap,
-                                         C.byref(neigs)), self.ctx.h)
+                                         C.byref(neigs), None if absorb else C.byref(carry)), self.ctx.h)
         if ortho == "left":
             self.llim, self.rlim = pos, pos + 2                  # setleftlim!(psi, pos)
         else:
             self.llim, self.rlim = pos - 2, pos                  # setrightlim!(psi, pos)
-        return truncerr.value, eigs[:min(neigs.value, cap)].copy()
+        out = (truncerr.value, eigs[:min(neigs.value, cap)].copy())
+        return out if absorb else out + (DeviceTensor(self.ctx, carry),)
+
+    def absorb_bond(self, pos: int, ortho: str, carry: DeviceTensor):
+        """psi[posnext] = carry * psi[posnext] (update_site.jl:186)."""
+        check(self.ctx.lib.tnl_env_absorb_bond(self.h, pos, 1 if ortho == "left" else 0, carry.h), self.ctx.h)
 
     def getpsi(self) -> List[HostTensor]:
         """getpsi (state_envs.jl:36): host copy of the MPS."""

@@ -1,4 +1,5 @@
-"""Local updates -- mirror of /root/reference/src/mps/update_site.jl:13-90,231-277 (two-site branch)."""
+"""Local updates -- mirror of /root/reference/src/mps/update_site.jl:13-277 (two-site and one-site updates,
+DMRG and TDVP branches)."""
 from __future__ import annotations
 
 import math
@@ -40,7 +41,19 @@ def _update_two_site(sysenv, solver, pos, ortho, time_step, normalize, maxdim, m
                                             ortho=ortho, normalize=normalize, which_decomp=kwargs.get("which_decomp"),
                                             svd_alg=svd_alg)
     if reverse_step and not halfsweep_done(len(sysenv), pos, nsite, ortho):
-        raise NotImplementedError("TDVP reverse step needs exp_solver (later row of the scope table)")
+        # TDVP backward evolution of the new centre site (update_site.jl:78-87)
+        pos1 = pos + 1 if ortho == "left" else pos
+        phi0 = sysenv.site_tensor(pos1).copy()
+        sysenv.set_nsite(nsite - 1)
+        with sysenv.phase("position"):
+            sysenv.position(pos1)
+        with sysenv.phase("solver"):
+            energy, phi0 = solver(sysenv, phi0, -time_step, **kwargs)
+        if normalize:
+            phi0.scale_(1.0 / phi0.norm())
+        if isinstance(energy, float) and math.isnan(energy):
+            energy = sysenv.expectation(phi0)
+        sysenv.set_site_tensor(pos1, phi0)
     return energy, truncerr, eigs
 
 
@@ -75,11 +88,26 @@ def _update_one_site(sysenv, solver, pos, ortho, time_step, normalize, maxdim, m
                                                 ortho=ortho, normalize=normalize, which_decomp=None, svd_alg=svd_alg)
         sysenv.set_nsite(nsite)
         return energy, truncerr, eigs
-    if reverse_step:
-        raise NotImplementedError("TDVP reverse step needs exp_solver (later row of the scope table)")
+    if not reverse_step:
+        with sysenv.phase("replacebond"):
+            truncerr, eigs = sysenv.svd_split(pos, phi, maxdim=maxdim, mindim=mindim, cutoff=cutoff, ortho=ortho,
+                                              normalize=normalize, svd_alg=svd_alg)
+        return energy, truncerr, eigs
+    # TDVP (update_site.jl:158-186): psi[pos] = U, phi0 = S*V evolved backwards with the zero-site H_eff, then absorbed
     with sysenv.phase("replacebond"):
-        truncerr, eigs = sysenv.svd_split(pos, phi, maxdim=maxdim, mindim=mindim, cutoff=cutoff, ortho=ortho,
-                                          normalize=normalize, svd_alg=svd_alg)
+        truncerr, eigs, phi0 = sysenv.svd_split(pos, phi, maxdim=maxdim, mindim=mindim, cutoff=cutoff, ortho=ortho,
+                                                normalize=normalize, svd_alg=svd_alg, absorb=False)
+    pos1 = pos + 1 if ortho == "left" else pos
+    sysenv.set_nsite(nsite - 1)
+    with sysenv.phase("position"):
+        sysenv.position(pos1)
+    with sysenv.phase("solver"):
+        energy, phi0 = solver(sysenv, phi0, -time_step, **kwargs)
+    if normalize:
+        phi0.scale_(1.0 / phi0.norm())
+    if isinstance(energy, float) and math.isnan(energy):
+        energy = sysenv.expectation(phi0)
+    sysenv.absorb_bond(pos, ortho, phi0)
     return energy, truncerr, eigs
 
 

@@ -357,3 +357,110 @@ def test_sharded_apply_two_gpus_matches_oracle():
                         "--master-addr", "127.0.0.1", "--master-port", "29517", "tools/multi_gpu_check.py"],
                        cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTI-GPU CHECK PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------- TDVP / exp_solver
+@pytest.mark.parametrize("nsite,t", [(2, -0.1), (1, -0.05), (0, 0.07), (2, 0.6)])
+def test_exp_solver_matches_oracle(ctx, nsite, t):
+    """tnl_exponentiate vs the oracle restatement of KrylovKit.exponentiate on the same H_eff and vector."""
+    T, ob, od, ok, om, op = _imports()
+    sites, H, mps = _setup(om, od, "S=1", 8, 24, 3, 4)
+    env_o = od.StateEnvs(mps, H)
+    pos = 4
+    if nsite == 0:
+        v_o = env_o.psi[4]
+        L, R, spec, u = ob.factorize(v_o, v_o.inds[:2], ortho="left", which_decomp="svd", cutoff=0.0)
+        env_o.psi[4] = L
+        phi_o, pos = R, 5
+        env_d = T.StateEnvs(ctx, env_o.psi.t, H, llim=4, rlim=6)
+    else:
+        env_d = T.StateEnvs(ctx, mps.t, H, llim=3, rlim=5)
+        phi_o = ob.contract(env_o.psi[4], env_o.psi[5]) if nsite == 2 else env_o.psi[4]
+    env_o.set_nsite(nsite); env_o.position(pos)
+    env_d.set_nsite(nsite); env_d.position(pos)
+    phi_d = T.DeviceTensor.from_host(ctx, phi_o, 1)
+    e_o, out_o = od.exp_solver(env_o, phi_o, t)
+    e_d, out_d = T.exp_solver(env_d, phi_d, t)
+    assert np.isnan(e_o) and np.isnan(e_d)
+    info_o, info_d = od.exp_solver.last_info, env_d.last_solver_info
+    assert info_d["converged"] == 1 and info_o["converged"] == 1
+    assert abs(info_d["numops"] - info_o["numops"]) <= 1          # the eager exit test sits at the tolerance
+    ref = out_o.permute(phi_o.inds).to_dense()
+    assert rel(out_d.to_host().to_dense(), ref) < 1e-10
+    # imaginary-time evolution is not norm preserving; the norm must match too
+    assert abs(out_d.norm() - out_o.norm()) < 1e-11 * out_o.norm()
+
+
+def test_exp_solver_substeps_when_the_basis_is_full(ctx):
+    """krylovdim too small for one step: adaptive sub-stepping + restarts (expintegrator outer loop)."""
+    T, ob, od, ok, om, op = _imports()
+    sites, H, mps = _setup(om, od, "S=1", 8, 24, 5, 4)
+    env_o = od.StateEnvs(mps, H)
+    env_d = T.StateEnvs(ctx, mps.t, H, llim=3, rlim=5)
+    env_o.set_nsite(2); env_o.position(4)
+    env_d.set_nsite(2); env_d.position(4)
+    phi_o = ob.contract(env_o.psi[4], env_o.psi[5])
+    phi_d = env_d.make_phi(4)
+    kw = dict(solver_krylovdim=6, solver_maxiter=200, solver_tol=1e-11)
+    _, out_o = od.exp_solver(env_o, phi_o, -0.8, **kw)
+    _, out_d = T.exp_solver(env_d, phi_d, -0.8, **kw)
+    assert od.exp_solver.last_info["numiter"] > 1 and env_d.last_solver_info["numiter"] > 1
+    assert env_d.last_solver_info["converged"] == 1
+    assert rel(out_d.to_host().to_dense(), out_o.permute(phi_o.inds).to_dense()) < 1e-9
+
+
+def test_exp_solver_rejects_complex_steps_and_missing_step(ctx):
+    T, ob, od, ok, om, op = _imports()
+    sites, H, mps = _setup(om, od, "S=1", 6, 12, 5, 3)
+    env_d = T.StateEnvs(ctx, mps.t, H, llim=2, rlim=4)
+    env_d.set_nsite(2); env_d.position(3)
+    phi = env_d.make_phi(3)
+    with pytest.raises(RuntimeError):
+        T.exp_solver(env_d, phi, None)
+    with pytest.raises(T.TnlError, match="complex"):
+        T.exp_solver(env_d, phi, -0.05j)
+
+
+@pytest.mark.parametrize("nsite", [2, 1])
+def test_tdvp_imaginary_time_sweeps_match_oracle(ctx, nsite):
+    """tdvpsweep! (src/mps/tdvp.jl:247-277) with a real step: energies per sweep, bond dimensions, truncation
+    errors and the final state against the oracle; the energy decreases monotonically towards E0."""
+    T, ob, od, ok, om, op = _imports()
+    N = 8
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites)
+    psi0 = od.MPS(om.neel_mps(sites))
+    eng_o = od.TDVPEngine(psi0, H)
+    eng_d = T.TDVPEngine(ctx, psi0.t, H)
+    sched = [(2, -0.1)] * 2 + [(nsite, -0.1)] * 3            # bond dimensions have to grow with two-site sweeps first
+    for ns, dt in sched:
+        od.tdvpsweep(eng_o, dt, ns, maxdim=16, cutoff=1e-12)
+        T.tdvpsweep(eng_d, dt, ns, maxdim=16, cutoff=1e-12, outputlevel=0)
+    assert eng_d.swdata.maxchi == eng_o.swdata.maxchi
+    assert np.allclose(eng_d.swdata.energy, eng_o.swdata.energy, rtol=1e-10, atol=0)
+    assert np.allclose(eng_d.swdata.maxtruncerr, eng_o.swdata.maxtruncerr, rtol=0, atol=1e-12)
+    assert np.allclose(eng_d.swdata.entropy, eng_o.swdata.entropy, rtol=0, atol=1e-9)
+    assert all(b <= a + 1e-12 for a, b in zip(eng_d.swdata.energy, eng_d.swdata.energy[1:]))
+    assert abs(eng_d.abstime - 0.5) < 1e-14
+    vo = om.mps_to_dense(eng_o.sysenv.psi.t)
+    vd = om.mps_to_dense(eng_d.getpsi())
+    assert abs(abs(np.vdot(vo, vd)) - 1.0) < 1e-10
+
+
+def test_tdvp_two_site_follows_exact_imaginary_time_evolution(ctx):
+    """Size-independent property: exp(-tau H)|Neel> from dense linear algebra vs TDVP on the device."""
+    import scipy.linalg as sl
+    T, ob, od, ok, om, op = _imports()
+    N = 8
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites)
+    psi0 = om.neel_mps(sites)
+    eng = T.TDVPEngine(ctx, psi0, H)
+    for _ in range(5):
+        T.tdvpsweep(eng, -0.02, 2, maxdim=16, cutoff=1e-14, outputlevel=0)
+    Hd = om.mpo_to_dense(H)
+    v = sl.expm(-0.1 * Hd) @ om.mps_to_dense(psi0)
+    v /= np.linalg.norm(v)
+    w = om.mps_to_dense(eng.getpsi())
+    assert abs(abs(np.vdot(v, w)) - 1.0) < 1e-8          # O(dt^3) per step splitting error
+    assert abs(T.getenergy(eng) - float(v @ Hd @ v)) < 1e-6

@@ -177,3 +177,62 @@ def test_one_site_dmrg_matches_ed():
     od.dmrg_(env, od.DMRGParams(nsweeps=[4], maxdim=[64], cutoff=1e-14, noise=1e-3, noisedecay=2, disable_noise_after=2), 2)
     sw = od.dmrg_(env, od.DMRGParams(nsweeps=[2], maxdim=[64], cutoff=0.0), 1)       # docs/src/mps/example_dmrg.md:62-71
     assert abs(sw.energy[-1] - E0_S12_N12) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------- exponentiate / TDVP
+@pytest.mark.parametrize("n,kd,t,eager", [(60, 30, -0.3, True), (150, 30, -0.05j, True), (150, 10, -0.5, False),
+                                          (200, 8, 0.4j, False), (50, 30, 0.2, True)])
+def test_exponentiate_matches_dense_expm(n, kd, t, eager):
+    """KrylovKit.exponentiate restatement vs scipy.linalg.expm on a dense symmetric matrix (one-shot eager exit,
+    sub-stepping with restarts, real and imaginary steps)."""
+    import scipy.linalg as sl
+    from oracle.krylov import exponentiate
+    rng = np.random.default_rng(n)
+    M = rng.standard_normal((n, n)); M = (M + M.T) / 2
+    x = rng.standard_normal(n); x /= np.linalg.norm(x)
+    y, info = exponentiate(lambda v: M @ v, t, x, krylovdim=kd, maxiter=1000, eager=eager)
+    ref = sl.expm(t * M) @ x
+    assert info["converged"] == 1
+    assert np.linalg.norm(y - ref) < 5e-12 * np.linalg.norm(ref)
+    if not eager:
+        assert info["numiter"] > 1           # the basis filled up: sub-steps were taken
+
+
+def test_exponentiate_fixed_point_and_zero_step():
+    from oracle.krylov import exponentiate
+    x = np.ones(5) / np.sqrt(5)
+    y, info = exponentiate(lambda v: 0.0 * v, -0.1, x)
+    assert info["converged"] == 1 and np.array_equal(y, x)
+    y, info = exponentiate(lambda v: v, 0.0, x)
+    assert info["numops"] == 0 and np.array_equal(y, x)
+
+
+@pytest.mark.parametrize("nsite,ts", [(2, -0.05), (2, -0.05j), (1, -0.05), (1, -0.05j)])
+def test_tdvp_sweeps_follow_exact_evolution(nsite, ts):
+    """tdvpsweep! restatement (two-site / one-site with backward steps) vs exp(t H)|Neel> for S=1/2 N=8;
+    real time conserves the energy, imaginary time lowers it."""
+    import scipy.linalg as sl
+    from oracle import dmrg as od, models as om
+    N = 8
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites)
+    Hd = om.mpo_to_dense(H)
+    psi0 = od.MPS(om.neel_mps(sites))
+    v0 = om.mps_to_dense(psi0.t)
+    eng = od.TDVPEngine(psi0, H)
+    nsteps = 0
+    if nsite == 1:                      # one-site TDVP cannot grow the bonds: start with two-site sweeps
+        for _ in range(2):
+            od.tdvpsweep(eng, ts, 2, maxdim=16, cutoff=1e-14); nsteps += 1
+    for _ in range(3):
+        od.tdvpsweep(eng, ts, nsite, maxdim=16, cutoff=1e-14); nsteps += 1
+    v = sl.expm(nsteps * ts * Hd) @ v0
+    v /= np.linalg.norm(v)
+    w = om.mps_to_dense(eng.sysenv.psi.t)
+    assert abs(abs(np.vdot(v, w)) - 1.0) < 1e-9
+    assert abs(eng.swdata.energy[-1] - np.real(np.vdot(v, Hd @ v))) < 1e-5
+    assert abs(eng.abstime - nsteps * 0.05) < 1e-14
+    if isinstance(ts, complex):
+        assert abs(eng.swdata.energy[-1] - eng.swdata.energy[0]) < 1e-9      # energy conservation
+    else:
+        assert eng.swdata.energy[-1] < eng.swdata.energy[0]
