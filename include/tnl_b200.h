@@ -99,6 +99,11 @@ int tnl_env_destroy(tnl_env_t env);
 /* MPO tensor W_site(wl, s', s, wr) in host format (StateEnvs(psi, H::MPO), state_envs.jl:54-60) */
 int tnl_env_set_site_op(tnl_env_t env, int32_t site, int32_t nq, const tnl_index_t* inds4, int64_t nblocks,
                         const int32_t* coords, const int64_t* offsets, const double* data);
+/* StateEnvs(psi, Hs::Vector{MPO}) = ProjMPOSum2 (src/mps/state_envs.jl:63-70, src/mps/projmposum2.jl:15-145):
+ * site operator of MPO number `term` (0-based; term 0 is what tnl_env_set_site_op sets).  product and noiseterm
+ * become sums over the terms; every term keeps its own environments over the shared state. */
+int tnl_env_set_site_op_term(tnl_env_t env, int32_t term, int32_t site, int32_t nq, const tnl_index_t* inds4,
+                             int64_t nblocks, const int32_t* coords, const int64_t* offsets, const double* data);
 /* MPS tensor A_site(l, s, r); the env shares the tensor (no copy) */
 int tnl_env_set_state(tnl_env_t env, int32_t site, tnl_tensor_t a);
 int tnl_env_get_state(tnl_env_t env, int32_t site, tnl_tensor_t* out); /* getpsi, state_envs.jl:36 */

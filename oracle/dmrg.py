@@ -18,7 +18,7 @@ import numpy as np
 
 from .blocksparse import BSTensor, contract, factorize, inner
 from .krylov import eigsolve_lanczos, exponentiate
-from .projmpo import ProjMPO, ProjMPO_MPS2, drho_matrices
+from .projmpo import ProjMPO, ProjMPO_MPS2, ProjMPOSum2, drho_matrices
 
 FLOAT64_THRESHOLD = 1e-15          # src/base/global_variables.jl:10-26
 
@@ -108,7 +108,13 @@ class StateEnvs:
     def __init__(self, psi: MPS, H: Sequence[BSTensor], Ms=None, weight: float = -1.0):
         self.psi = psi.copy()
         # StateEnvs(psi, H, Ms; weight)  (src/mps/state_envs.jl:86-103) when penalised states are given
-        self.PH = ProjMPO(H) if not Ms else ProjMPO_MPS2(H, [m.t if isinstance(m, MPS) else m for m in Ms], weight)
+        if len(H) and isinstance(H[0], (list, tuple)):
+            # StateEnvs(psi, Hs::Vector{MPO}) (src/mps/state_envs.jl:63-70)
+            if Ms:
+                raise NotImplementedError("ProjMPOSum_MPS (sum of MPOs + penalised states) is not restated")
+            self.PH = ProjMPOSum2(H)
+        else:
+            self.PH = ProjMPO(H) if not Ms else ProjMPO_MPS2(H, [m.t if isinstance(m, MPS) else m for m in Ms], weight)
 
     def __len__(self):
         return len(self.psi)

@@ -127,6 +127,50 @@ class ProjMPO:
         return contract(nt, nt.noprime().dag())
 
 
+class ProjMPOSum2:
+    """src/mps/projmposum2.jl:15-145: a vector of ProjMPO over the same state; product and noiseterm are sums."""
+
+    def __init__(self, Hs: Sequence[Sequence[BSTensor]]):
+        self.PHs = [ProjMPO(H) for H in Hs]
+        self.N = self.PHs[0].N
+
+    @property
+    def nsite(self):
+        return self.PHs[0].nsite
+
+    @property
+    def lpos(self):
+        return self.PHs[0].lpos
+
+    @property
+    def rpos(self):
+        return self.PHs[0].rpos
+
+    def set_nsite(self, n: int):
+        for p in self.PHs:
+            p.set_nsite(n)
+
+    def position(self, psi, pos: int):
+        for p in self.PHs:
+            p.position(psi, pos)
+
+    def product(self, v: BSTensor) -> BSTensor:
+        Pv = None
+        for p in self.PHs:
+            t = p.product(v)
+            Pv = t if Pv is None else Pv.add(t.permute(Pv.inds))
+        return Pv
+
+    __call__ = product
+
+    def noiseterm(self, phi: BSTensor, ortho: str) -> BSTensor:
+        nt = None
+        for p in self.PHs:
+            t = p.noiseterm(phi, ortho)
+            nt = t if nt is None else nt.add(t.permute(nt.inds))
+        return nt
+
+
 def drho_matrices(drho: BSTensor, scale: float):
     """Per-charge matrices of scale*drho, rows = primed index group (layout of `matricize`)."""
     primed = [ix for ix in drho.inds if ix.plev > 0]

@@ -314,6 +314,13 @@ int tnl_env_set_site_op(tnl_env_t e, int32_t site, int32_t nq, const tnl_index_t
     e->env.set_site_op(site, hb);
   });
 }
+int tnl_env_set_site_op_term(tnl_env_t e, int32_t term, int32_t site, int32_t nq, const tnl_index_t* inds4,
+                             int64_t nblocks, const int32_t* coords, const int64_t* offsets, const double* data) {
+  return guard(e->env.ctx, [&] {
+    HostBlocks hb = make_host(4, nq, inds4, nblocks, coords, offsets, data);
+    e->env.term(term).set_site_op(site, hb);
+  });
+}
 int tnl_env_add_penalty(tnl_env_t e, double weight, int32_t nsites, const tnl_tensor_t* tensors) {
   return guard(e->env.ctx, [&] {
     std::vector<TensorP> M;
@@ -336,7 +343,7 @@ int tnl_env_get_state(tnl_env_t e, int32_t site, tnl_tensor_t* out) {
 int tnl_env_set_nsite(tnl_env_t e, int32_t nsite) {
   return guard(e->env.ctx, [&] {
     TNL_CHECK(nsite >= 0 && nsite <= 2, "nsite must be 0, 1 or 2");
-    e->env.nsite = nsite;
+    e->env.set_nsite(nsite);
   });
 }
 int tnl_env_position(tnl_env_t e, int32_t pos) {

@@ -59,6 +59,7 @@ double* Ctx::scratch(int slot, size_t nelem, bool zero) {
   size_t bytes = std::max<size_t>(nelem, 2) * sizeof(double);
   if (bytes > s.cap) {
     if (s.p) cudaFreeAsync(s.p, stream);
+    slot_epoch++;
     s.cap = bytes + bytes / 4;                       // headroom: sector sizes drift from bond to bond
     CUDA_OK(cudaMallocAsync(&s.p, s.cap, stream));
   }

@@ -238,6 +238,7 @@ class Ctx {
   enum { SLOT_T1 = 0, SLOT_T2, SLOT_T3, SLOT_P, SLOT_PACKED, SLOT_LOCIN, SLOT_LOCOUT, SLOT_VLOC, SLOT_ARENA, NSLOTS };
   struct Slot { void* p = nullptr; size_t cap = 0; };
   Slot slots[NSLOTS];
+  uint64_t slot_epoch = 1;          // bumped when a slot is reallocated or reused outside an apply plan
   double* scratch(int slot, size_t nelem, bool zero);
   std::unordered_map<double*, size_t> vec_caps;
   std::vector<std::pair<double*, size_t>> vec_pool;     // free Krylov-vector buffers (ptr, capacity in doubles)

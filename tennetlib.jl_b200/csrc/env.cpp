@@ -138,7 +138,20 @@ void Env::set_site_op(int site, const HostBlocks& hb) {
   lpos = 0; rpos = N + 1; ap.reset(); Ledge.reset(); Redge.reset();
 }
 
+Env& Env::term(int k) {
+  TNL_CHECK(!parent, "terms are addressed through the top environment");
+  TNL_CHECK(k >= 0 && k < 64, "MPO term index out of range");
+  while ((int)more.size() < k) more.push_back(std::make_unique<Env>(ctx, N, this));
+  return k == 0 ? *this : *more[k - 1];
+}
+
+void Env::set_nsite(int n) {
+  nsite = n;
+  for (auto& m : more) m->nsite = n;
+}
+
 void Env::set_state(int site, TensorP a) {
+  TNL_CHECK(!parent, "the state belongs to the top environment");
   TNL_CHECK(site >= 1 && site <= N, "site out of range");
   TNL_CHECK(a->rank() == 3, "site tensor must be (l, s, r)");
   A[site - 1] = std::move(a);
@@ -157,6 +170,7 @@ void Env::invalidate(int lo, int hi) {
     p.mloc.reset();
   }
   ap.reset();
+  for (auto& m : more) m->invalidate(lo, hi);
 }
 
 static void set_one(Ctx* ctx, Tensor& t) {
@@ -184,7 +198,89 @@ void Env::ensure_edges() {
 TensorP Env::lproj() { return lpos <= 0 ? Ledge : LR[lpos - 1]; }
 TensorP Env::rproj() { return rpos >= N + 1 ? Redge : LR[rpos - 1]; }
 
-// L_j = L_{j-1} * A_j * W_j * dag(prime(A_j))      (ITensorMPS ProjMPO._makeL!)
+static Index trivial_like(const Index& proto, int dir) {
+  Index t;
+  t.nq = proto.nq;
+  t.dir = dir;
+  t.dims = {1};
+  t.qns = {charge_zero()};
+  return t;
+}
+bool is_trivial_link(const Index& ix) { return ix.nsect() == 1 && ix.dims[0] == 1 && ix.qns[0] == charge_zero(); }
+
+// view of `src` with a trivial (dim 1, charge 0) index inserted at position `at`; shares src's buffer.  With the
+// new index in the same (row / column) group as its neighbours the charge-fused layout is byte-identical
+// (build_layout enumerates the same combos in the same order), which is checked.
+static TensorP view_with_trivial(Ctx* ctx, const Tensor& src, int at, int nrow, const Index& w0, const double* data) {
+  std::vector<Index> inds = src.inds;
+  inds.insert(inds.begin() + at, w0);
+  auto v = std::make_shared<Tensor>(ctx, inds, nrow, false);
+  TNL_CHECK(v->nelem == src.nelem && v->blocks.size() == src.blocks.size(), "trivial-link view changed the layout");
+  for (size_t i = 0; i < v->blocks.size(); i++)
+    TNL_CHECK(v->blocks[i].off == src.blocks[i].off, "trivial-link view changed the block offsets");
+  v->d = const_cast<double*>(data);
+  v->owns = false;
+  return v;
+}
+
+// L_j = L_{j-1} * A_j * W_j * dag(prime(A_j))      (ITensorMPS ProjMPO._makeL!; the same three contractions per id
+// in ProjCouplingModel._makeL!, src/mps/projcouplingmodel.jl:123-196).  L == nullptr: the term starts at this
+// site (src/mps/projcouplingmodel.jl:151-165, "uncommon tensor" branch with the site operator) -- L is the
+// identity on the link and W's left link is trivial, so the first GEMM is skipped.
+TensorP Env::step_left(const Tensor* L, const TensorP& Asite, const Tensor& W) {
+  TensorP Aq = as_nrow(ctx, Asite, 1);            // [l | s r]
+  TensorP As = as_nrow(ctx, Asite, 2);            // [l s | r]
+  ap.reset();                                     // the apply workspaces are reused below
+  ctx->slot_epoch++;
+  TensorP X1;
+  if (L) {
+    X1 = mk_ws(ctx, {L->inds[0], L->inds[1], Aq->inds[1], Aq->inds[2]}, 2, Ctx::SLOT_T1);
+    auto g1 = plan_gemm(*L, false, *Aq, false, *X1);
+    run_gemm(ctx, *g1, L->d, Aq->d, X1->d);
+  } else {
+    TNL_CHECK(is_trivial_link(W.inds[0]), "a term that starts here must have a trivial left link");
+    X1 = view_with_trivial(ctx, *Aq, 1, 2, trivial_like(W.inds[0], -W.inds[0].dir), Aq->d);
+  }
+  auto Y1 = mk_ws(ctx, {X1->inds[0], W.inds[2], W.inds[3], X1->inds[3]}, 2, Ctx::SLOT_T2);
+  auto x1 = plan_transform(*X1, *Y1, {0, -1, -1, 3}, &W, {1, 2});
+  run_transform(ctx, *x1, X1->d, Y1->d, W.d);
+  const Index& r = As->inds[2];
+  auto Ln = mk_ws(ctx, {with_dir(r, -r.dir), Y1->inds[2], Y1->inds[3]}, 1, Ctx::SLOT_P);
+  auto g2 = plan_gemm(*As, true, *Y1, false, *Ln, /*dagA=*/true);
+  run_gemm(ctx, *g2, As->d, Y1->d, Ln->d);
+  ctx->sync();
+  return relayout(ctx, *Ln, 2);
+}
+
+// R_j = dag(prime(A_j)) * R_{j+1} * W_j * A_j  (mirror image; same sum, bra contracted first).  W in the
+// (s', wr | wl, s) form.  R == nullptr: the term ends at this site (identity on the link, trivial right link).
+TensorP Env::step_right(const Tensor* R, const TensorP& Asite, const Tensor& W) {
+  TensorP Aq = as_nrow(ctx, Asite, 1);
+  TensorP As = as_nrow(ctx, Asite, 2);
+  const Index &l = As->inds[0], &s = As->inds[1], &r = As->inds[2];
+  ap.reset();
+  ctx->slot_epoch++;
+  TensorP Z;
+  if (R) {
+    Z = mk_ws(ctx, {with_dir(l, -l.dir), with_dir(s, -s.dir), R->inds[1], R->inds[2]}, 2, Ctx::SLOT_T1);
+    auto g1 = plan_gemm(*As, false, *R, false, *Z, /*dagA=*/true);
+    run_gemm(ctx, *g1, As->d, R->d, Z->d);
+  } else {
+    TNL_CHECK(is_trivial_link(W.inds[1]), "a term that ends here must have a trivial right link");
+    // dag(A) has the same data and block coordinates as A; the transform below matches blocks by coordinates
+    Z = view_with_trivial(ctx, *As, 2, 2, trivial_like(W.inds[1], -W.inds[1].dir), As->d);
+  }
+  const Index zr = R ? Z->inds[3] : with_dir(r, -r.dir);
+  auto Z2 = mk_ws(ctx, {with_dir(l, -l.dir), W.inds[2], W.inds[3], zr}, 2, Ctx::SLOT_T2);
+  auto x1 = plan_transform(*Z, *Z2, {0, -1, -1, 3}, &W, {1, 2});
+  run_transform(ctx, *x1, Z->d, Z2->d, W.d);
+  auto Rn = mk_ws(ctx, {Z2->inds[0], Z2->inds[1], Aq->inds[0]}, 2, Ctx::SLOT_P);
+  auto g2 = plan_gemm(*Z2, false, *Aq, true, *Rn);
+  run_gemm(ctx, *g2, Z2->d, Aq->d, Rn->d);
+  ctx->sync();
+  return relayout(ctx, *Rn, 1);
+}
+
 void Env::makeL(int k) {
   ensure_edges();
   int ll = lpos;
@@ -192,29 +288,13 @@ void Env::makeL(int k) {
   ll = std::max(ll, 0);
   TensorP L = lproj();
   while (ll < k) {
-    TensorP Aq = as_nrow(ctx, A[ll], 1);            // [l | s r]
-    TensorP As = as_nrow(ctx, A[ll], 2);            // [l s | r]
-    const TensorP& W = Wlr[ll];
-    ap.reset();                                     // the apply workspaces are reused below
-    auto X1 = mk_ws(ctx, {L->inds[0], L->inds[1], Aq->inds[1], Aq->inds[2]}, 2, Ctx::SLOT_T1);
-    auto g1 = plan_gemm(*L, false, *Aq, false, *X1);
-    run_gemm(ctx, *g1, L->d, Aq->d, X1->d);
-    auto Y1 = mk_ws(ctx, {X1->inds[0], W->inds[2], W->inds[3], X1->inds[3]}, 2, Ctx::SLOT_T2);
-    auto x1 = plan_transform(*X1, *Y1, {0, -1, -1, 3}, W.get(), {1, 2});
-    run_transform(ctx, *x1, X1->d, Y1->d, W->d);
-    const Index& r = As->inds[2];
-    auto Ln = mk_ws(ctx, {with_dir(r, -r.dir), Y1->inds[2], Y1->inds[3]}, 1, Ctx::SLOT_P);
-    auto g2 = plan_gemm(*As, true, *Y1, false, *Ln, /*dagA=*/true);
-    run_gemm(ctx, *g2, As->d, Y1->d, Ln->d);
-    ctx->sync();
-    L = relayout(ctx, *Ln, 2);
+    L = step_left(L.get(), A[ll], *Wlr[ll]);
     LR[ll] = L;
     ll++;
   }
   lpos = k;
 }
 
-// R_j = dag(prime(A_j)) * R_{j+1} * W_j * A_j  (mirror image; same sum, bra contracted first)
 void Env::makeR(int k) {
   ensure_edges();
   int rl = rpos;
@@ -223,22 +303,7 @@ void Env::makeR(int k) {
   TensorP R = rproj();
   while (rl > k) {
     int j = rl - 2;
-    TensorP Aq = as_nrow(ctx, A[j], 1);
-    TensorP As = as_nrow(ctx, A[j], 2);
-    const TensorP& W = Wrl[j];
-    const Index &l = As->inds[0], &s = As->inds[1];
-    ap.reset();
-    auto Z = mk_ws(ctx, {with_dir(l, -l.dir), with_dir(s, -s.dir), R->inds[1], R->inds[2]}, 2, Ctx::SLOT_T1);
-    auto g1 = plan_gemm(*As, false, *R, false, *Z, /*dagA=*/true);
-    run_gemm(ctx, *g1, As->d, R->d, Z->d);
-    auto Z2 = mk_ws(ctx, {Z->inds[0], W->inds[2], W->inds[3], Z->inds[3]}, 2, Ctx::SLOT_T2);
-    auto x1 = plan_transform(*Z, *Z2, {0, -1, -1, 3}, W.get(), {1, 2});
-    run_transform(ctx, *x1, Z->d, Z2->d, W->d);
-    auto Rn = mk_ws(ctx, {Z2->inds[0], Z2->inds[1], Aq->inds[0]}, 2, Ctx::SLOT_P);
-    auto g2 = plan_gemm(*Z2, false, *Aq, true, *Rn);
-    run_gemm(ctx, *g2, Z2->d, Aq->d, Rn->d);
-    ctx->sync();
-    R = relayout(ctx, *Rn, 1);
+    R = step_right(R.get(), A[j], *Wrl[j]);
     LR[j] = R;
     rl--;
   }
@@ -247,10 +312,16 @@ void Env::makeR(int k) {
 
 void Env::position(int pos) {
   int lp = lpos, rp = rpos;
-  makeL(pos - 1);
-  makeR(pos + nsite);
+  if (cm) {
+    cm_makeL(pos - 1);
+    cm_makeR(pos + nsite);
+  } else {
+    makeL(pos - 1);
+    makeR(pos + nsite);
+  }
   if (lp != lpos || rp != rpos) ap.reset();
   for (auto& p : pens) position_penalty(p, pos);
+  for (auto& m : more) { m->nsite = nsite; m->position(pos); }
 }
 
 // ------------------------------------------------------------------------ excited-state penalty
@@ -380,6 +451,7 @@ TensorP Env::make_phi(int pos) {
   TensorP A1 = as_nrow(ctx, A[pos - 1], 2);
   TensorP A2 = as_nrow(ctx, A[pos], 1);
   ap.reset();
+  ctx->slot_epoch++;
   auto S = mk_ws(ctx, {A1->inds[0], A1->inds[1], A2->inds[1], A2->inds[2]}, 2, Ctx::SLOT_T3);
   auto g = plan_gemm(*A1, false, *A2, false, *S);
   run_gemm(ctx, *g, A1->d, A2->d, S->d);
@@ -409,9 +481,20 @@ struct Env::ApplyPlan {
   std::unique_ptr<TransformPlan> x2, x3, x5;
   int64_t nelem;
   double flops;
+  uint64_t epoch = 0;                // ctx->slot_epoch when the plan was built (workspace pointers valid)
 };
 
 void Env::build_apply_plan(const Tensor& vfull) {
+  const int first = lpos + 1;      // 1-based first site of the range
+  TNL_CHECK(rpos - lpos == nsite + 1, "environments are not positioned for this nsite");
+  ap = make_plan(vfull, lproj(), nsite >= 1 ? Wlr[first - 1] : nullptr, nsite == 2 ? Wlr[first] : nullptr, rproj(), true);
+}
+
+// Plan of one H_eff term  v -> L * W1 * W2 * R  (any of L / R may be absent: a CouplingModel term that starts or
+// ends inside the site range, src/mps/projcouplingmodel.jl:315-356 -- the corresponding GEMM is skipped and the
+// operand is a trivial-link VIEW of its neighbour, no flops and no copy).
+std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, TensorP W1p, TensorP W2p, TensorP Rp,
+                                               bool allow_shard) {
   struct Timer {
     Ctx* c; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     ~Timer() { c->cnt.host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
@@ -419,17 +502,18 @@ void Env::build_apply_plan(const Tensor& vfull) {
   const Tensor& v = vfull;
   auto p = std::make_shared<ApplyPlan>();
   p->nsite = nsite;
-  p->L = lproj();
-  p->R = rproj();
-  TNL_CHECK(p->L && p->R, "environments not positioned");
+  p->L = Lp;
+  p->R = Rp;
+  TNL_CHECK(p->L || p->R || nsite > 0, "a zero-site term needs an environment");
   TNL_CHECK(v.nrow == 1, "Krylov vectors use the [l | rest] layout");
-  const int first = lpos + 1;      // 1-based first site of the range
+  // link carried by the running tensor before the first / after the last site operator when L / R is absent
+  auto win = [&](const TensorP& W) { return trivial_like(W->inds[0], -W->inds[0].dir); };
   if (nsite == 2) {
-    TNL_CHECK(v.rank() == 4 && rpos - lpos == 3, "two-site apply needs a (l,s1,s2,r) vector and nsite=2 position");
-    p->W1 = Wlr[first - 1];
-    p->W2 = Wlr[first];
+    TNL_CHECK(v.rank() == 4, "two-site apply needs a (l,s1,s2,r) vector");
+    p->W1 = W1p;
+    p->W2 = W2p;
     const Tensor* vin = &v;
-    if (ctx->world > 1) {
+    if (ctx->world > 1 && allow_shard && p->L && p->R) {
       // Sharded apply: every rank owns a contiguous share of each sector of the right
       // link r.  It contracts L with its slice of v, carries the slice through the site operators and contracts
       // with its slice of R over (w, r_local): a partial H_eff v of full size, summed by one NCCL all-reduce.
@@ -474,55 +558,112 @@ void Env::build_apply_plan(const Tensor& vfull) {
       vin = p->vloc.get();
     }
     const Tensor& v = *vin;     // from here on: the (possibly sliced) input structure
-    const Tensor &L = *p->L, &R = *p->R, &W1 = *p->W1, &W2 = *p->W2;
-    p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2], v.inds[3]}, 2, Ctx::SLOT_T1);
-    p->g1 = plan_gemm(L, false, v, false, *p->T1);
-    p->T2 = mk_ws(ctx, {L.inds[0], W1.inds[2], W1.inds[3], v.inds[2], v.inds[3]}, 5, Ctx::SLOT_T2);
+    const Tensor &W1 = *p->W1, &W2 = *p->W2;
+    const Index lout = p->L ? p->L->inds[0] : v.inds[0];
+    if (p->L) {
+      const Tensor& L = *p->L;
+      p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2], v.inds[3]}, 2, Ctx::SLOT_T1);
+      p->g1 = plan_gemm(L, false, v, false, *p->T1);
+    } else {
+      TNL_CHECK(is_trivial_link(W1.inds[0]), "term without a left environment must start with a trivial link");
+      p->T1 = view_with_trivial(ctx, v, 1, 2, win(p->W1), nullptr);          // data = the input vector itself
+    }
+    p->T2 = mk_ws(ctx, {lout, W1.inds[2], W1.inds[3], v.inds[2], v.inds[3]}, 5, Ctx::SLOT_T2);
     p->x2 = plan_transform(*p->T1, *p->T2, {0, -1, -1, 3, 4}, &W1, {1, 2});
-    p->T3 = mk_ws(ctx, {L.inds[0], W1.inds[2], W2.inds[2], W2.inds[3], v.inds[3]}, 3, Ctx::SLOT_T3);
+    p->T3 = mk_ws(ctx, {lout, W1.inds[2], W2.inds[2], W2.inds[3], v.inds[3]}, 3, Ctx::SLOT_T3);
     p->x3 = plan_transform(*p->T2, *p->T3, {0, 1, -1, -1, 4}, &W2, {2, 3});
-    p->P = mk_ws(ctx, {L.inds[0], W1.inds[2], W2.inds[2], R.inds[0]}, 3, Ctx::SLOT_P);
-    p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
+    if (p->R) {
+      const Tensor& R = *p->R;
+      p->P = mk_ws(ctx, {lout, W1.inds[2], W2.inds[2], R.inds[0]}, 3, Ctx::SLOT_P);
+      p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
+    } else {
+      TNL_CHECK(is_trivial_link(W2.inds[3]), "term without a right environment must end with a trivial link");
+      p->P = std::make_shared<Tensor>(ctx, std::vector<Index>{lout, W1.inds[2], W2.inds[2], v.inds[3]}, 3, false);
+      TNL_CHECK(p->P->nelem == p->T3->nelem, "trivial-link view changed the layout");
+      p->P->d = p->T3->d;
+      p->P->owns = false;
+    }
     Tensor Q(ctx, p->P->inds, 1, false);
     TNL_CHECK(Q.nelem == vfull.nelem, "H_eff output layout differs from the input layout (index mismatch)");
     p->x5 = plan_transform(*p->P, Q, {0, 1, 2, 3}, nullptr, {});
     if (p->sharded)
       for (int k = 0; k < ctx->world; k++)
         p->pack.push_back(plan_transform(*p->P, *p->qloc[k], {0, 1, 2, 3}, nullptr, {}, &p->pack_maps[k]));
-    p->flops = p->g1->flops + p->x2->flops + p->x3->flops + p->g4->flops;
+    p->flops = (p->g1 ? p->g1->flops : 0.0) + p->x2->flops + p->x3->flops + (p->g4 ? p->g4->flops : 0.0);
   } else if (nsite == 1) {
-    TNL_CHECK(v.rank() == 3 && rpos - lpos == 2, "one-site apply needs a (l,s,r) vector and nsite=1 position");
-    p->W1 = Wlr[first - 1];
-    const Tensor &L = *p->L, &R = *p->R, &W1 = *p->W1;
-    p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2]}, 2, Ctx::SLOT_T1);
-    p->g1 = plan_gemm(L, false, v, false, *p->T1);
-    p->T3 = mk_ws(ctx, {L.inds[0], W1.inds[2], W1.inds[3], v.inds[2]}, 2, Ctx::SLOT_T3);
+    TNL_CHECK(v.rank() == 3, "one-site apply needs a (l,s,r) vector");
+    p->W1 = W1p;
+    const Tensor& W1 = *p->W1;
+    const Index lout = p->L ? p->L->inds[0] : v.inds[0];
+    if (p->L) {
+      const Tensor& L = *p->L;
+      p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2]}, 2, Ctx::SLOT_T1);
+      p->g1 = plan_gemm(L, false, v, false, *p->T1);
+    } else {
+      TNL_CHECK(is_trivial_link(W1.inds[0]), "term without a left environment must start with a trivial link");
+      p->T1 = view_with_trivial(ctx, v, 1, 2, win(p->W1), nullptr);
+    }
+    p->T3 = mk_ws(ctx, {lout, W1.inds[2], W1.inds[3], v.inds[2]}, 2, Ctx::SLOT_T3);
     p->x2 = plan_transform(*p->T1, *p->T3, {0, -1, -1, 3}, &W1, {1, 2});
-    p->P = mk_ws(ctx, {L.inds[0], W1.inds[2], R.inds[0]}, 2, Ctx::SLOT_P);
-    p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
+    if (p->R) {
+      const Tensor& R = *p->R;
+      p->P = mk_ws(ctx, {lout, W1.inds[2], R.inds[0]}, 2, Ctx::SLOT_P);
+      p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
+    } else {
+      TNL_CHECK(is_trivial_link(W1.inds[3]), "term without a right environment must end with a trivial link");
+      p->P = std::make_shared<Tensor>(ctx, std::vector<Index>{lout, W1.inds[2], v.inds[2]}, 2, false);
+      TNL_CHECK(p->P->nelem == p->T3->nelem, "trivial-link view changed the layout");
+      p->P->d = p->T3->d;
+      p->P->owns = false;
+    }
     Tensor Q(ctx, p->P->inds, 1, false);
     TNL_CHECK(Q.nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
     p->x5 = plan_transform(*p->P, Q, {0, 1, 2}, nullptr, {});
-    p->flops = p->g1->flops + p->x2->flops + p->g4->flops;
+    p->flops = (p->g1 ? p->g1->flops : 0.0) + p->x2->flops + (p->g4 ? p->g4->flops : 0.0);
   } else if (nsite == 0) {
-    TNL_CHECK(v.rank() == 2 && rpos - lpos == 1, "zero-site apply needs a (l,r) bond matrix and nsite=0 position");
-    const Tensor &L = *p->L, &R = *p->R;
-    p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1]}, 2, Ctx::SLOT_T1);            // [(l' w) | r]
-    p->g1 = plan_gemm(L, false, v, false, *p->T1);
-    p->T3 = mk_ws(ctx, p->T1->inds, 1, Ctx::SLOT_T3);                                  // [l' | (w r)]
-    p->x2 = plan_transform(*p->T1, *p->T3, {0, 1, 2}, nullptr, {});
-    p->P = mk_ws(ctx, {L.inds[0], R.inds[0]}, 1, Ctx::SLOT_P);
-    p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
-    TNL_CHECK(p->P->nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
-    p->flops = p->g1->flops + p->g4->flops;
+    TNL_CHECK(v.rank() == 2, "zero-site apply needs a (l,r) bond matrix");
+    if (p->L && p->R) {
+      const Tensor &L = *p->L, &R = *p->R;
+      p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1]}, 2, Ctx::SLOT_T1);            // [(l' w) | r]
+      p->g1 = plan_gemm(L, false, v, false, *p->T1);
+      p->T3 = mk_ws(ctx, p->T1->inds, 1, Ctx::SLOT_T3);                                  // [l' | (w r)]
+      p->x2 = plan_transform(*p->T1, *p->T3, {0, 1, 2}, nullptr, {});
+      p->P = mk_ws(ctx, {L.inds[0], R.inds[0]}, 1, Ctx::SLOT_P);
+      p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
+      TNL_CHECK(p->P->nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
+      p->flops = p->g1->flops + p->g4->flops;
+    } else if (p->L) {
+      // out[l' | r] = L[(l' w0) | l] v[l | r]   (local left environment: the link is trivial)
+      const Tensor& L = *p->L;
+      TNL_CHECK(is_trivial_link(L.inds[1]), "left-only zero-site term must carry a trivial link");
+      p->P = std::make_shared<Tensor>(ctx, std::vector<Index>{L.inds[0], L.inds[1], v.inds[1]}, 2, false);
+      TNL_CHECK(p->P->nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
+      p->g1 = plan_gemm(L, false, v, false, *p->P);
+      p->flops = p->g1->flops;
+    } else {
+      // out[l | r'] = v[l | (w0 r)] R[r' | (w0 r)]^T
+      const Tensor& R = *p->R;
+      TNL_CHECK(is_trivial_link(R.inds[1]), "right-only zero-site term must carry a trivial link");
+      p->T3 = view_with_trivial(ctx, v, 1, 1, with_dir(R.inds[1], -R.inds[1].dir), nullptr);
+      p->P = std::make_shared<Tensor>(ctx, std::vector<Index>{v.inds[0], R.inds[0]}, 1, false);
+      TNL_CHECK(p->P->nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
+      p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
+      p->flops = p->g4->flops;
+    }
   } else {
     throw Error(2, "nsite must be 0, 1 or 2");
   }
   p->nelem = vfull.nelem;
-  ap = p;
+  p->epoch = ctx->slot_epoch;
+  return p;
 }
 
-double Env::apply_flops() const { return ap ? ap->flops : 0.0; }
+double Env::apply_flops() const {
+  if (cm) return cm_apply_flops();
+  double f = ap ? ap->flops : 0.0;
+  for (auto& m : more) f += m->apply_flops();
+  return f;
+}
 
 void Env::apply(const Tensor& v, Tensor& out) {
   TNL_CHECK(out.nelem == v.nelem && out.nrow == 1, "output vector layout mismatch");
@@ -538,6 +679,14 @@ void Env::apply_local(const double* vloc, double* outloc) {
   run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
   for (int k = 0; k < ctx->world; k++) run_transform(ctx, *p.pack[k], p.P->d, p.packed + (int64_t)k * p.nloc, nullptr);
   comm_reduce_scatter_sum(ctx, p.packed, outloc, p.nloc);
+  if (!more.empty()) {
+    double* tmp = ctx->vec_acquire((size_t)p.nloc);
+    for (auto& m : more) {
+      m->apply_local(vloc, tmp);
+      vec_axpy(ctx, outloc, tmp, p.nloc, 1.0);
+    }
+    ctx->vec_release(tmp, 0);
+  }
   for (auto& pen : pens) {
     if (pen.dead) continue;
     if (!pen.mloc) {
@@ -550,18 +699,56 @@ void Env::apply_local(const double* vloc, double* outloc) {
     comm_allreduce_sum(ctx, ctx->d_scalars + 200, 1);
     vec_axpy_dev(ctx, outloc, pen.mloc->d, p.nloc, 200, weight);
   }
-  ctx->cnt.apply_count += 1;
+  if (!parent) ctx->cnt.apply_count += 1;
 }
 
 void Env::ensure_plan(const Tensor& proto) {
-  if (!ap || ap->nsite != nsite || ap->nelem != proto.nelem) build_apply_plan(proto);
+  if (cm) { cm_ensure_plans(proto); return; }
+  // the terms of an MPO sum share the context's workspace slots: a plan is stale when a slot was reallocated
+  // (or reused by another phase) after it was built; two passes reach a fixed point because capacities only grow
+  for (int pass = 0; pass < 3; pass++) {
+    bool rebuilt = false;
+    if (!ap || ap->nsite != nsite || ap->nelem != proto.nelem || ap->epoch != ctx->slot_epoch) { build_apply_plan(proto); rebuilt = true; }
+    for (auto& m : more) {
+      m->nsite = nsite;
+      if (!m->ap || m->ap->nsite != nsite || m->ap->nelem != proto.nelem || m->ap->epoch != ctx->slot_epoch) { m->build_apply_plan(proto); rebuilt = true; }
+    }
+    if (!rebuilt || more.empty()) break;
+    TNL_CHECK(pass < 2, "apply plans of the MPO sum did not stabilise");
+  }
   if (ap->sharded)
     for (auto& pen : pens)
       if (!pen.dead) build_penalty_vector(pen, proto);
 }
 
+// one term, not sharded: vout = L * W1 * W2 * R applied to vin (absent L / R: trivial-link views, see make_plan)
+void Env::run_plan(ApplyPlan& p, const double* vin, double* vout) {
+  if (p.nsite == 0) {
+    if (p.L && p.R) {
+      run_gemm(ctx, *p.g1, p.L->d, vin, p.T1->d);
+      run_transform(ctx, *p.x2, p.T1->d, p.T3->d, nullptr);
+      run_gemm(ctx, *p.g4, p.T3->d, p.R->d, vout);
+    } else if (p.L) {
+      run_gemm(ctx, *p.g1, p.L->d, vin, vout);
+    } else {
+      run_gemm(ctx, *p.g4, vin, p.R->d, vout);
+    }
+    return;
+  }
+  const double* t1 = vin;
+  if (p.g1) { run_gemm(ctx, *p.g1, p.L->d, vin, p.T1->d); t1 = p.T1->d; }
+  if (p.nsite == 2) {
+    run_transform(ctx, *p.x2, t1, p.T2->d, p.W1->d);
+    run_transform(ctx, *p.x3, p.T2->d, p.T3->d, p.W2->d);
+  } else {
+    run_transform(ctx, *p.x2, t1, p.T3->d, p.W1->d);
+  }
+  if (p.g4) run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
+  run_transform(ctx, *p.x5, p.P->d, vout, nullptr);
+}
+
 void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
-  ensure_plan(proto);
+  if (!parent) ensure_plan(proto);
   ApplyPlan& p = *ap;
   if (p.sharded) {
     run_transform(ctx, *p.xs, vin, p.loc_in, nullptr);
@@ -570,21 +757,16 @@ void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
     for (int k = 0; k < ctx->world; k++) run_transform(ctx, *p.unpack[k], p.packed + (int64_t)k * p.nloc, vout, nullptr);
     return;
   }
-  struct { const double* d; } v{vin};
-  struct { double* d; } out{vout};
-  run_gemm(ctx, *p.g1, p.L->d, v.d, p.T1->d);
-  if (p.nsite == 2) {
-    run_transform(ctx, *p.x2, p.T1->d, p.T2->d, p.W1->d);
-    run_transform(ctx, *p.x3, p.T2->d, p.T3->d, p.W2->d);
-    run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
-    run_transform(ctx, *p.x5, p.P->d, out.d, nullptr);
-  } else if (p.nsite == 1) {
-    run_transform(ctx, *p.x2, p.T1->d, p.T3->d, p.W1->d);
-    run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
-    run_transform(ctx, *p.x5, p.P->d, out.d, nullptr);
-  } else {
-    run_transform(ctx, *p.x2, p.T1->d, p.T3->d, nullptr);
-    run_gemm(ctx, *p.g4, p.T3->d, p.R->d, out.d);
+  if (cm) cm_apply(proto, vin, vout);
+  else run_plan(p, vin, vout);
+  // + sum_k H_k v   (ProjMPOSum2.product, src/mps/projmposum2.jl:86-101)
+  if (!more.empty()) {
+    double* tmp = ctx->vec_acquire((size_t)proto.nelem);
+    for (auto& m : more) {
+      m->apply_ptr(proto, vin, tmp);
+      vec_axpy(ctx, vout, tmp, proto.nelem, 1.0);
+    }
+    ctx->vec_release(tmp, 0);
   }
   // + weight * sum_M <m|v> |m>   (ProjMPO_MPS2.product)
   for (auto& pen : pens) {
@@ -593,7 +775,7 @@ void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
     vec_dot(ctx, pen.m->d, vin, proto.nelem, 200);
     vec_axpy_dev(ctx, vout, pen.m->d, proto.nelem, 200, weight);
   }
-  ctx->cnt.apply_count += 1;
+  if (!parent) ctx->cnt.apply_count += 1;
 }
 
 double Env::expectation(const Tensor& phi) {
@@ -1043,32 +1225,58 @@ namespace tnl {
 // ------------------------------------------------------------------------------- noise term
 // ITensorMPS `noiseterm(::ProjMPO, phi, ortho)`: nt = L*W_j*phi (left) | phi*W_{j+1}*R (right); the density
 // perturbation nt*dag(noprime(nt)) is formed inside factorize() as X X^T / X^T X per charge group.
-TensorP Env::noise_tensor(const Tensor& phi, bool left) {
+TensorP Env::noise_tensor(const Tensor& phi, bool left, bool own_storage) {
   TNL_CHECK(nsite == 2 && phi.rank() == 4, "noise term only defined for 2-site ProjMPO");
   const int first = lpos + 1;
+  return left ? noise_operand(phi, true, lproj().get(), *Wlr[first - 1], own_storage)
+              : noise_operand(phi, false, rproj().get(), *Wnr[first], own_storage);
+}
+
+// One noise operand X with drho = X X^T (left) / X^T X (right), for one term of the Hamiltonian:
+//   left : X[(l' s1') | (w s2 r)] = E(l',w,l) W(w; s1', s1; w') phi      E = left environment or absent
+//   right: X[(l s1 w) | (s2' r')] = phi W(w; s2', s2; w') E(r', w', r)  E = right environment or absent
+// (ITensorMPS noiseterm(::ProjMPO); per id in src/mps/projcouplingmodel.jl:391-492).  The first operand of a bond
+// may live in workspace slot T2; further operands (MPO sums, CouplingModel ids) own their memory.
+TensorP Env::noise_operand(const Tensor& phi, bool left, const Tensor* E, const Tensor& W, bool own_storage) {
+  auto mk_x = [&](std::vector<Index> inds, int nrow) {
+    return own_storage ? mk(ctx, std::move(inds), nrow) : mk_ws(ctx, std::move(inds), nrow, Ctx::SLOT_T2);
+  };
+  ap.reset();                                     // reuse the apply workspaces (the plan dies with the bond anyway)
+  ctx->slot_epoch++;
   if (left) {
-    TensorP L = lproj();
-    const TensorP& W1 = Wlr[first - 1];
-    ap.reset();                                     // reuse the apply workspaces (the plan dies with the bond anyway)
-    auto T1 = mk_ws(ctx, {L->inds[0], L->inds[1], phi.inds[1], phi.inds[2], phi.inds[3]}, 2, Ctx::SLOT_T1);
-    auto g1 = plan_gemm(*L, false, phi, false, *T1);
-    run_gemm(ctx, *g1, L->d, phi.d, T1->d);
-    auto X = mk_ws(ctx, {L->inds[0], W1->inds[2], W1->inds[3], phi.inds[2], phi.inds[3]}, 2, Ctx::SLOT_T2);
-    auto x = plan_transform(*T1, *X, {0, -1, -1, 3, 4}, W1.get(), {1, 2});
-    run_transform(ctx, *x, T1->d, X->d, W1->d);
+    TensorP T1;
+    if (E) {
+      T1 = mk_ws(ctx, {E->inds[0], E->inds[1], phi.inds[1], phi.inds[2], phi.inds[3]}, 2, Ctx::SLOT_T1);
+      auto g1 = plan_gemm(*E, false, phi, false, *T1);
+      run_gemm(ctx, *g1, E->d, phi.d, T1->d);
+    } else {
+      TNL_CHECK(is_trivial_link(W.inds[0]), "term without a left environment must start with a trivial link");
+      T1 = view_with_trivial(ctx, phi, 1, 2, trivial_like(W.inds[0], -W.inds[0].dir), phi.d);
+    }
+    auto X = mk_x({T1->inds[0], W.inds[2], W.inds[3], phi.inds[2], phi.inds[3]}, 2);
+    auto x = plan_transform(*T1, *X, {0, -1, -1, 3, 4}, &W, {1, 2});
+    run_transform(ctx, *x, T1->d, X->d, W.d);
     ctx->sync();
     return X;
   }
-  TensorP R = relayout(ctx, *rproj(), 2);                       // [(r' w) | r]
   TensorP P3 = relayout(ctx, phi, 3);                           // [(l s1 s2) | r]
-  const TensorP& W2 = Wnr[first];                               // (s, wr | wl, s')
-  ap.reset();
-  auto Xa = mk_ws(ctx, {phi.inds[0], phi.inds[1], phi.inds[2], R->inds[0], R->inds[1]}, 3, Ctx::SLOT_T1);
-  auto g1 = plan_gemm(*P3, false, *R, true, *Xa);
-  run_gemm(ctx, *g1, P3->d, R->d, Xa->d);
-  auto X = mk_ws(ctx, {phi.inds[0], phi.inds[1], W2->inds[2], W2->inds[3], R->inds[0]}, 3, Ctx::SLOT_T2);
-  auto x = plan_transform(*Xa, *X, {0, 1, -1, -1, 3}, W2.get(), {2, 4});
-  run_transform(ctx, *x, Xa->d, X->d, W2->d);
+  TensorP Xa;
+  Index rout;
+  if (E) {
+    TensorP R = relayout(ctx, *E, 2);                           // [(r' w) | r]
+    Xa = mk_ws(ctx, {phi.inds[0], phi.inds[1], phi.inds[2], R->inds[0], R->inds[1]}, 3, Ctx::SLOT_T1);
+    auto g1 = plan_gemm(*P3, false, *R, true, *Xa);
+    run_gemm(ctx, *g1, P3->d, R->d, Xa->d);
+    ctx->sync();
+    rout = R->inds[0];
+  } else {
+    TNL_CHECK(is_trivial_link(W.inds[1]), "term without a right environment must end with a trivial link");
+    Xa = view_with_trivial(ctx, *P3, 4, 3, trivial_like(W.inds[1], -W.inds[1].dir), P3->d);
+    rout = phi.inds[3];
+  }
+  auto X = mk_x({phi.inds[0], phi.inds[1], W.inds[2], W.inds[3], rout}, 3);       // W = (s, wr | wl, s')
+  auto x = plan_transform(*Xa, *X, {0, 1, -1, -1, 3}, &W, {2, 4});
+  run_transform(ctx, *x, Xa->d, X->d, W.d);
   ctx->sync();
   return X;
 }
@@ -1076,12 +1284,31 @@ TensorP Env::noise_tensor(const Tensor& phi, bool left) {
 // ITensorMPS `replacebond!(psi, pos, phi; ortho, maxdim, mindim, cutoff, eigen_perturbation, normalize)`
 FactorizeResult Env::replacebond(int pos, const Tensor& phi, FactorizeParams prm, bool normalize) {
   TNL_CHECK(pos >= 1 && pos < N && phi.rank() == 4, "replacebond: bad bond / tensor");
+  TNL_CHECK(!parent, "replacebond is an operation of the top environment");
   TensorP X;
+  std::vector<TensorP> Xmore;
   if (prm.noise != 0.0) {
-    X = noise_tensor(phi, prm.ortho_left != 0);
-    prm.noiseX = X.get();
+    if (cm) {
+      Xmore = cm_noise_operands(phi, prm.ortho_left != 0);
+      TNL_CHECK(!Xmore.empty(), "CouplingModel noise term: no term touches the kept site");
+      X = Xmore.back();
+      Xmore.pop_back();
+      for (auto& x : Xmore) prm.noiseXmore.push_back(x.get());
+      prm.noiseX = X.get();
+    }
+    // noiseterm(::ProjMPOSum2) = sum of the terms' noise terms (src/mps/projmposum2.jl:130-145)
+    for (auto& m : more) {
+      m->nsite = nsite;
+      Xmore.push_back(m->noise_tensor(phi, prm.ortho_left != 0, true));
+      prm.noiseXmore.push_back(Xmore.back().get());
+    }
+    if (!cm) {
+      X = noise_tensor(phi, prm.ortho_left != 0, false);
+      prm.noiseX = X.get();
+    }
   }
   ap.reset();
+  ctx->slot_epoch++;
   TensorP S = relayout_ws(ctx, phi, 2, Ctx::SLOT_T3);
   FactorizeResult f = factorize(ctx, *S, prm);
   if (normalize) {
@@ -1182,6 +1409,289 @@ void Env::move_center(int from, int to) {
     A[j] = An;
   }
   invalidate(std::min(from, to), std::max(from, to));
+}
+
+}  // namespace tnl
+
+// =================================================================================================
+// ProjCouplingModel (src/mps/projcouplingmodel.jl): the Hamiltonian is a set of terms ("ids"), each present on a
+// subset of the sites.  On the device every id is an MPO-like term over its support: site operators in the
+// (wl, s', s, wr) form with TRIVIAL (dim 1, charge 0) links where the reference tensor has no OpLink, identity
+// fillers on sites the term skips, and environments E_id(l', w, l).  Environments whose link is trivial (the
+// reference's order-2 results, :170-189) are summed into one local tensor per bond.
+// =================================================================================================
+namespace tnl {
+
+struct Env::CM {
+  struct Op { TensorP Wlr, Wrl, Wnr; Index wl, wr; };
+  std::vector<std::map<int64_t, Op>> M;               // CouplingModel.terms: per site, id -> operator
+  std::vector<std::map<int64_t, TensorP>> LR;         // environments per site: id -> E_id  (L: nrow 2, R: nrow 1)
+  std::map<std::string, Op> fillers;                  // identity operators of pass-through sites
+  int64_t next_local = -1;                            // ids of the accumulated local tensors (gen_rand_id upstream)
+  std::vector<std::pair<int64_t, std::shared_ptr<ApplyPlan>>> plans;
+  int plan_lpos = -1, plan_rpos = -1;
+  explicit CM(int n) : M(n), LR(n) {}
+};
+
+void Env::CMDeleter::operator()(CM* p) const { delete p; }
+
+static Env::CM::Op make_op(Ctx* ctx, const HostBlocks& hb) {
+  Env::CM::Op op;
+  auto lr = permute_host(hb, {0, 2, 1, 3});     // (wl, s | s', wr)
+  auto rl = permute_host(hb, {1, 3, 0, 2});     // (s', wr | wl, s)
+  auto nr = permute_host(hb, {2, 3, 0, 1});     // (s, wr | wl, s')
+  op.Wlr = import_tensor(ctx, lr.hb, 4);
+  op.Wrl = import_tensor(ctx, rl.hb, 4);
+  op.Wnr = import_tensor(ctx, nr.hb, 4);
+  op.wl = hb.inds[0];
+  op.wr = hb.inds[3];
+  return op;
+}
+
+void Env::cm_set_term(int site, int64_t id, const HostBlocks& hb) {
+  TNL_CHECK(!parent && more.empty(), "a CouplingModel environment cannot be mixed with MPO terms");
+  TNL_CHECK(site >= 1 && site <= N, "site out of range");
+  TNL_CHECK(hb.rank == 4, "CouplingModel site tensor must be given as (wl, s', s, wr) with trivial links where it has no OpLink");
+  TNL_CHECK(id >= 0, "term ids must be non-negative");
+  if (!cm) cm.reset(new CM(N));
+  cm->M[site - 1][id] = make_op(ctx, hb);
+  lpos = 0; rpos = N + 1; ap.reset();
+  cm->plans.clear();
+}
+
+// identity on the site and on the link: W(wl, s', s, wr) = delta(wl, wr) delta(s', s)
+static const Env::CM::Op& cm_filler(Ctx* ctx, Env::CM& cm, const Index& site_ket, const Index& wl, const Index& wr) {
+  std::string key;
+  auto add = [&](const Index& ix) {
+    key += std::to_string(ix.dir) + ":";
+    for (int k = 0; k < ix.nsect(); k++) {
+      key += std::to_string(ix.dims[k]) + "/";
+      for (int a = 0; a < ix.nq; a++) key += std::to_string(ix.qns[k][a]) + ",";
+    }
+    key += "|";
+  };
+  add(site_ket); add(wl); add(wr);
+  auto it = cm.fillers.find(key);
+  if (it != cm.fillers.end()) return it->second;
+  TNL_CHECK(wl.dims == wr.dims && wl.qns == wr.qns && wl.dir == -wr.dir, "pass-through links must be a dagged pair");
+  HostBlocks hb;
+  hb.rank = 4;
+  Index sp = site_ket, sk = site_ket;
+  sk.dir = -site_ket.dir;                       // (s' : arrow of the ket index, s : its dagger) as in an MPO tensor
+  hb.inds = {wl, sp, sk, wr};
+  std::vector<double> data;
+  for (int a = 0; a < wl.nsect(); a++)
+    for (int m = 0; m < site_ket.nsect(); m++) {
+      const int dw = wl.dims[a], ds = site_ket.dims[m];
+      hb.coords.push_back({a, m, m, a});
+      hb.offsets.push_back((int64_t)data.size());
+      const size_t base = data.size();
+      data.resize(base + (size_t)dw * ds * ds * dw, 0.0);
+      for (int w = 0; w < dw; w++)
+        for (int x = 0; x < ds; x++)
+          data[base + w + (size_t)dw * (x + (size_t)ds * (x + (size_t)ds * w))] = 1.0;
+    }
+  hb.data = data.data();
+  return cm.fillers.emplace(key, make_op(ctx, hb)).first->second;
+}
+
+static bool same_space_dag(const Index& a, const Index& b) { return a.dims == b.dims && a.qns == b.qns && a.dir == -b.dir; }
+
+// ProjCouplingModel._makeL! (src/mps/projcouplingmodel.jl:123-196)
+void Env::cm_makeL(int k) {
+  int ll = lpos;
+  if (ll >= k) { lpos = k; return; }
+  ll = std::max(ll, 0);
+  while (ll < k) {
+    const std::map<int64_t, TensorP> empty;
+    const auto& L = ll <= 0 ? empty : cm->LR[ll - 1];
+    const auto& Ms = cm->M[ll];
+    std::map<int64_t, TensorP> next;
+    TensorP local;
+    std::vector<int64_t> ids;
+    for (auto& kv : L) ids.push_back(kv.first);
+    for (auto& kv : Ms) if (!L.count(kv.first)) ids.push_back(kv.first);
+    const Index& sket = A[ll]->inds[1];
+    for (int64_t id : ids) {
+      auto li = L.find(id);
+      auto mi = Ms.find(id);
+      const Tensor* Lid = li == L.end() ? nullptr : li->second.get();
+      const CM::Op* op;
+      if (mi != Ms.end()) {
+        op = &mi->second;
+        if (Lid) TNL_CHECK(same_space_dag(Lid->inds[1], op->wl), "CouplingModel: OpLink of a term does not match its left environment");
+      } else {
+        op = &cm_filler(ctx, *cm, sket, with_dir(Lid->inds[1], -Lid->inds[1].dir), Lid->inds[1]);
+      }
+      TensorP Ln = step_left(Lid, A[ll], *op->Wlr);
+      if (is_trivial_link(Ln->inds[1])) {
+        if (!local) local = Ln;
+        else {
+          TNL_CHECK(local->nelem == Ln->nelem, "local environment layouts differ");
+          vec_axpy(ctx, local->d, Ln->d, Ln->nelem, 1.0);
+          ctx->sync();
+        }
+      } else {
+        next[id] = Ln;
+      }
+    }
+    if (local) next[cm->next_local--] = local;
+    cm->LR[ll] = std::move(next);
+    ll++;
+  }
+  lpos = k;
+}
+
+// ProjCouplingModel._makeR! (src/mps/projcouplingmodel.jl:212-286)
+void Env::cm_makeR(int k) {
+  int rl = rpos;
+  if (rl <= k) { rpos = k; return; }
+  rl = std::min(rl, N + 1);
+  while (rl > k) {
+    const int j = rl - 2;                              // 0-based site being absorbed
+    const std::map<int64_t, TensorP> empty;
+    const auto& R = rl >= N + 1 ? empty : cm->LR[rl - 1];
+    const auto& Ms = cm->M[j];
+    std::map<int64_t, TensorP> next;
+    TensorP local;
+    std::vector<int64_t> ids;
+    for (auto& kv : R) ids.push_back(kv.first);
+    for (auto& kv : Ms) if (!R.count(kv.first)) ids.push_back(kv.first);
+    const Index& sket = A[j]->inds[1];
+    for (int64_t id : ids) {
+      auto ri = R.find(id);
+      auto mi = Ms.find(id);
+      const Tensor* Rid = ri == R.end() ? nullptr : ri->second.get();
+      const CM::Op* op;
+      if (mi != Ms.end()) {
+        op = &mi->second;
+        if (Rid) TNL_CHECK(same_space_dag(Rid->inds[1], op->wr), "CouplingModel: OpLink of a term does not match its right environment");
+      } else {
+        op = &cm_filler(ctx, *cm, sket, Rid->inds[1], with_dir(Rid->inds[1], -Rid->inds[1].dir));
+      }
+      TensorP Rn = step_right(Rid, A[j], *op->Wrl);
+      if (is_trivial_link(Rn->inds[1])) {
+        if (!local) local = Rn;
+        else {
+          TNL_CHECK(local->nelem == Rn->nelem, "local environment layouts differ");
+          vec_axpy(ctx, local->d, Rn->d, Rn->nelem, 1.0);
+          ctx->sync();
+        }
+      } else {
+        next[id] = Rn;
+      }
+    }
+    if (local) next[cm->next_local--] = local;
+    cm->LR[j] = std::move(next);
+    rl--;
+  }
+  rpos = k;
+}
+
+// the pieces of one id at the current position: environment, site operators (fillers where the id skips a site)
+struct CMPieces { TensorP L, R; const Env::CM::Op* W[2] = {nullptr, nullptr}; };
+
+static std::vector<std::pair<int64_t, CMPieces>> cm_collect(Env& e, Env::CM& cm) {
+  const std::map<int64_t, TensorP> empty;
+  const auto& L = e.lpos <= 0 ? empty : cm.LR[e.lpos - 1];
+  const auto& R = e.rpos >= e.N + 1 ? empty : cm.LR[e.rpos - 1];
+  std::vector<int64_t> ids;
+  auto push = [&](int64_t id) { if (std::find(ids.begin(), ids.end(), id) == ids.end()) ids.push_back(id); };
+  for (auto& kv : L) push(kv.first);
+  for (int sidx = 0; sidx < e.nsite; sidx++)
+    for (auto& kv : cm.M[e.lpos + sidx]) push(kv.first);
+  for (auto& kv : R) push(kv.first);
+  std::vector<std::pair<int64_t, CMPieces>> out;
+  for (int64_t id : ids) {
+    CMPieces pc;
+    auto li = L.find(id);
+    auto ri = R.find(id);
+    if (li != L.end()) pc.L = li->second;
+    if (ri != R.end()) pc.R = ri->second;
+    Index cur = pc.L ? pc.L->inds[1] : Index{};        // link carried to the right (as it sits on the environment)
+    bool have = (bool)pc.L;
+    for (int sidx = 0; sidx < e.nsite; sidx++) {
+      const int site = e.lpos + sidx;                    // 0-based
+      auto mi = cm.M[site].find(id);
+      if (mi != cm.M[site].end()) {
+        pc.W[sidx] = &mi->second;
+        if (have) TNL_CHECK(same_space_dag(cur, mi->second.wl), "CouplingModel: OpLinks of a term do not chain");
+        else TNL_CHECK(is_trivial_link(mi->second.wl), "CouplingModel: a term starts with an open OpLink");
+      } else {
+        Index t;
+        if (!have) {                                     // nothing to the left: trivial pass-through
+          t.nq = e.A[site]->inds[1].nq; t.dir = +1; t.dims = {1}; t.qns = {charge_zero()};
+          cur = t;
+        }
+        pc.W[sidx] = &cm_filler(e.ctx, cm, e.A[site]->inds[1], with_dir(cur, -cur.dir), cur);
+      }
+      cur = pc.W[sidx]->wr;
+      have = true;
+    }
+    if (pc.R) TNL_CHECK(!have || same_space_dag(cur, pc.R->inds[1]), "CouplingModel: OpLink does not match the right environment");
+    else TNL_CHECK(!have || is_trivial_link(cur), "CouplingModel: a term ends with an open OpLink");
+    out.emplace_back(id, pc);
+  }
+  return out;
+}
+
+void Env::cm_ensure_plans(const Tensor& proto) {
+  TNL_CHECK(rpos - lpos == nsite + 1, "environments are not positioned for this nsite");
+  for (int pass = 0; pass < 4; pass++) {
+    bool stale = !ap || cm->plans.empty() || cm->plan_lpos != lpos || cm->plan_rpos != rpos || ap->nsite != nsite ||
+                 ap->nelem != proto.nelem;
+    for (auto& pl : cm->plans) stale = stale || pl.second->epoch != ctx->slot_epoch;
+    if (!stale) return;
+    TNL_CHECK(pass < 3, "apply plans of the CouplingModel did not stabilise");
+    cm->plans.clear();
+    for (auto& kv : cm_collect(*this, *cm)) {
+      const CMPieces& pc = kv.second;
+      cm->plans.emplace_back(kv.first, make_plan(proto, pc.L, pc.W[0] ? pc.W[0]->Wlr : nullptr,
+                                                 pc.W[1] ? pc.W[1]->Wlr : nullptr, pc.R, false));
+    }
+    TNL_CHECK(!cm->plans.empty(), "CouplingModel has no term at this position");
+    cm->plan_lpos = lpos; cm->plan_rpos = rpos;
+    ap = cm->plans[0].second;                            // representative (nsite / nelem / epoch bookkeeping)
+    const uint64_t e = ctx->slot_epoch;                  // a slot grew while the later plans were built?
+    bool ok = true;
+    for (auto& pl : cm->plans) ok = ok && pl.second->epoch == e;
+    if (ok) return;
+  }
+}
+
+// ProjCouplingModel.product (src/mps/projcouplingmodel.jl:315-383): sum over ids of contract(v, tensors of the id)
+void Env::cm_apply(const Tensor& proto, const double* vin, double* vout) {
+  double* tmp = nullptr;
+  bool first = true;
+  for (auto& pl : cm->plans) {
+    if (first) { run_plan(*pl.second, vin, vout); first = false; continue; }
+    if (!tmp) tmp = ctx->vec_acquire((size_t)proto.nelem);
+    run_plan(*pl.second, vin, tmp);
+    vec_axpy(ctx, vout, tmp, proto.nelem, 1.0);
+  }
+  if (tmp) ctx->vec_release(tmp, 0);
+}
+
+double Env::cm_apply_flops() const {
+  double f = 0.0;
+  for (auto& pl : cm->plans) f += pl.second->flops;
+  return f;
+}
+
+// noiseterm(::ProjCouplingModel) (src/mps/projcouplingmodel.jl:391-492): one operand per id that touches the
+// environment or the site operator on the kept side
+std::vector<TensorP> Env::cm_noise_operands(const Tensor& phi, bool left) {
+  TNL_CHECK(nsite == 2 && phi.rank() == 4, "noise term only defined for 2-site ProjMPO");
+  std::vector<TensorP> out;
+  for (auto& kv : cm_collect(*this, *cm)) {
+    const CMPieces& pc = kv.second;
+    const int site = left ? lpos : lpos + 1;
+    const bool on_site = cm->M[site].count(kv.first) > 0;
+    if (left ? !(pc.L || on_site) : !(pc.R || on_site)) continue;
+    out.push_back(left ? noise_operand(phi, true, pc.L.get(), *pc.W[0]->Wlr, true)
+                       : noise_operand(phi, false, pc.R.get(), *pc.W[1]->Wnr, true));
+  }
+  return out;
 }
 
 }  // namespace tnl

@@ -29,6 +29,7 @@ struct FactorizeParams {
   int svd_alg = 0;              // svd path: 0 = cusolverDnDgesvd (QR iteration), 1 = cusolverDnXgesvdp (polar)
   double noise = 0.0;           // scale of the density-matrix perturbation
   const Tensor* noiseX = nullptr;   // see factorize.cu
+  std::vector<const Tensor*> noiseXmore;   // further noise operands (MPO sums): rho += noise * sum_k X_k X_k^T
   int new_dir_on_L = -1;        // arrow of the new index on the left factor
 };
 struct FactorizeResult {
@@ -48,6 +49,8 @@ struct LanczosResult {
   double normres = 0;
 };
 
+bool is_trivial_link(const Index& ix);
+
 struct ExpResult {
   int converged = 0;
   int numops = 0;
@@ -64,7 +67,22 @@ class Env {
   int lpos, rpos;
   std::vector<TensorP> Wlr, Wrl, Wnr; // MPO tensors as transform operands: (wl,s | s',wr), (s',wr | wl,s), (s,wr | wl,s')
   std::vector<Index> Wl, Wr;         // MPO link indices per site
-  std::vector<TensorP> A;            // site tensors (l, s, r), any nrow
+  std::vector<TensorP> A_store;
+  std::vector<TensorP>& A;           // site tensors (l, s, r), any nrow; terms of an MPO sum share the top env's
+  // StateEnvs(psi, Hs::Vector{MPO}) = ProjMPOSum2 (src/mps/projmposum2.jl:15-145): the further MPOs H_2, H_3, ...
+  // are full environments of their own (W tensors, L/R cache, watermarks, apply plan) over the SAME state;
+  // product = sum of the terms' products, noiseterm = sum of the terms' noise terms.
+  std::vector<std::unique_ptr<Env>> more;
+  Env* parent = nullptr;
+  // StateEnvs(psi, H::CouplingModel) = ProjCouplingModel (src/mps/projcouplingmodel.jl): per-id site operators
+  // and environments; see the implementation notes in env.cpp
+  struct CM;
+  struct CMDeleter { void operator()(CM* p) const; };
+  std::unique_ptr<CM, CMDeleter> cm;
+  void cm_set_term(int site, int64_t id, const HostBlocks& hb);   // (wl, s', s, wr) with trivial links as needed
+  Env& term(int k);                  // k = 0: this env; k >= 1: more[k-1] (created on demand)
+  int nterms() const { return 1 + (int)more.size(); }
+  void set_nsite(int n);
   std::vector<TensorP> LR;           // LR[j] = L_{j+1} (nrow 2) or R_{j+1} (nrow 1), 0-based slot j = site j+1
   TensorP Ledge, Redge;
   // excited-state penalty  weight * sum_M |M><M|  (ProjMPO_MPS2, src/mps/projmpo_mps2.jl:94-134)
@@ -82,7 +100,9 @@ class Env {
   void add_penalty(const std::vector<TensorP>& M, double w);
   void invalidate(int lo, int hi);
 
-  Env(Ctx* c, int n) : ctx(c), N(n), lpos(0), rpos(n + 1), Wlr(n), Wrl(n), Wnr(n), Wl(n), Wr(n), A(n), LR(n) {}
+  Env(Ctx* c, int n, Env* par = nullptr)
+      : ctx(c), N(n), lpos(0), rpos(n + 1), Wlr(n), Wrl(n), Wnr(n), Wl(n), Wr(n), A_store(par ? 0 : n),
+        A(par ? par->A_store : A_store), LR(n), parent(par) {}
 
   void set_site_op(int site, const HostBlocks& hb);     // W(wl, s', s, wr), 1-based site
   void set_state(int site, TensorP a);
@@ -107,12 +127,23 @@ class Env {
   struct ApplyPlan;
   std::shared_ptr<ApplyPlan> ap;
   void build_apply_plan(const Tensor& v);
+  std::shared_ptr<ApplyPlan> make_plan(const Tensor& v, TensorP L, TensorP W1, TensorP W2, TensorP R, bool allow_shard);
+  void run_plan(ApplyPlan& p, const double* vin, double* vout);
+  TensorP step_left(const Tensor* L, const TensorP& Asite, const Tensor& W);
+  TensorP step_right(const Tensor* R, const TensorP& Asite, const Tensor& W);
   TensorP lproj();
   TensorP rproj();
   void ensure_edges();
   void makeL(int k);
   void makeR(int k);
-  TensorP noise_tensor(const Tensor& phi, bool left);
+  TensorP noise_tensor(const Tensor& phi, bool left, bool own_storage);
+  TensorP noise_operand(const Tensor& phi, bool left, const Tensor* E, const Tensor& W, bool own_storage);
+  void cm_makeL(int k);
+  void cm_makeR(int k);
+  void cm_ensure_plans(const Tensor& proto);
+  void cm_apply(const Tensor& proto, const double* vin, double* vout);
+  double cm_apply_flops() const;
+  std::vector<TensorP> cm_noise_operands(const Tensor& phi, bool left);
   void position_penalty(Penalty& p, int pos);
   void build_penalty_vector(Penalty& p, const Tensor& proto);
 };

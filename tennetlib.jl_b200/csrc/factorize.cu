@@ -125,7 +125,8 @@ struct FG {                     // one charge group of the factorisation
   Charge q;
   int64_t R = 0, C = 0;
   const double* M = nullptr; int64_t ldm = 0;     // data of T (nullptr: group opened by the noise term only)
-  const double* X = nullptr; int64_t ldx = 0, XK = 0;   // noise operand
+  struct NoiseOp { const double* X = nullptr; int64_t ldx = 0, XK = 0; };
+  std::vector<NoiseOp> Xs;                        // noise operands, one slot per MPO term (X == nullptr: none)
   // results
   double* U = nullptr; int64_t ldu = 0;           // left vectors  [R x k]
   double* Vt = nullptr; int64_t ldv = 0;          // right vectors [k x C]  (svd path)
@@ -230,21 +231,27 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
     FG f; f.q = g.q; f.R = g.R; f.C = g.C; f.M = T.d + g.base; f.ldm = g.ld;
     fg.push_back(f);
   }
+  std::vector<const Tensor*> nops;
   if (noisy && which == 2) {
-    const Tensor& X = *prm.noiseX;
-    for (const Group& g : X.groups) {
-      // ortho left : X = [(rows) | K] rows match T's row group;  ortho right: X = [K | (cols)] cols match T's cols
-      Charge q = g.q;
-      auto it = std::find_if(fg.begin(), fg.end(), [&](const FG& f) { return f.q == q; });
-      if (it == fg.end()) {
-        FG f; f.q = q;
-        if (left) { f.R = g.R; f.C = 0; } else { f.R = 0; f.C = g.C; }
-        fg.push_back(f);
-        it = fg.end() - 1;
+    nops.push_back(prm.noiseX);
+    for (const Tensor* x : prm.noiseXmore) nops.push_back(x);
+    for (size_t t = 0; t < nops.size(); t++) {
+      const Tensor& X = *nops[t];
+      for (const Group& g : X.groups) {
+        // ortho left : X = [(rows) | K] rows match T's row group;  ortho right: X = [K | (cols)] cols match T's cols
+        Charge q = g.q;
+        auto it = std::find_if(fg.begin(), fg.end(), [&](const FG& f) { return f.q == q; });
+        if (it == fg.end()) {
+          FG f; f.q = q;
+          if (left) { f.R = g.R; f.C = 0; } else { f.R = 0; f.C = g.C; }
+          fg.push_back(f);
+          it = fg.end() - 1;
+        }
+        if (left) TNL_CHECK(it->R == g.R, "noise operand rows do not match");
+        else TNL_CHECK(it->C == g.C, "noise operand cols do not match");
+        it->Xs.resize(nops.size());
+        it->Xs[t].X = X.d + g.base; it->Xs[t].ldx = g.ld; it->Xs[t].XK = left ? g.C : g.R;
       }
-      if (left) TNL_CHECK(it->R == g.R, "noise operand rows do not match");
-      else TNL_CHECK(it->C == g.C, "noise operand cols do not match");
-      it->X = X.d + g.base; it->ldx = g.ld; it->XK = left ? g.C : g.R;
     }
     std::sort(fg.begin(), fg.end(), [](const FG& a, const FG& b) { return a.q < b.q; });
   }
@@ -352,27 +359,35 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
     auto g = plan_gemm_raw(ctx, !left, left, pr);
     run_gemm(ctx, *g, nullptr, nullptr, nullptr);
     if (noisy) {
-      std::vector<double*> dr;
-      for (FG& f : fg) {
-        const int64_t n = left ? f.R : f.C;
-        if (n == 0 || !f.mine || !f.X || f.XK == 0) { dr.push_back(nullptr); continue; }
-        double* D = talloc(n * n);
-        dr.push_back(D);
-        GemmProblem p{};
-        p.M = p.N = (int)n; p.K = (int)f.XK; p.ldc = (int)n; p.c = off(D);
-        p.a = p.b = off(f.X); p.lda = p.ldb = (int)f.ldx;
-        prn.push_back(p);
+      // rho += noise * sum_t X_t X_t^T (one grouped DGEMM + axpy per MPO term; the D buffers are reused)
+      std::vector<double*> dr(fg.size(), nullptr);
+      for (size_t t = 0; t < nops.size(); t++) {
+        prn.clear();
+        std::vector<char> has(fg.size(), 0);
+        size_t i = 0;
+        for (FG& f : fg) {
+          const int64_t n = left ? f.R : f.C;
+          const size_t gi = i++;
+          if (n == 0 || !f.mine || f.Xs.size() <= t || !f.Xs[t].X || f.Xs[t].XK == 0) continue;
+          if (!dr[gi]) dr[gi] = talloc(n * n);
+          has[gi] = 1;
+          GemmProblem p{};
+          p.M = p.N = (int)n; p.K = (int)f.Xs[t].XK; p.ldc = (int)n; p.c = off(dr[gi]);
+          p.a = p.b = off(f.Xs[t].X); p.lda = p.ldb = (int)f.Xs[t].ldx;
+          prn.push_back(p);
+        }
+        if (prn.empty()) continue;
+        auto gn = plan_gemm_raw(ctx, !left, left, prn);
+        run_gemm(ctx, *gn, nullptr, nullptr, nullptr);
+        i = 0;
+        for (FG& f : fg) {
+          const int64_t n = left ? f.R : f.C;
+          const size_t gi = i++;
+          // talloc buffers are zero-initialised and padded to an even length, so the padded axpy is exact
+          if (has[gi]) vec_axpy(ctx, f.E, dr[gi], (n * n + 1) & ~int64_t(1), prm.noise);
+        }
+        ctx->sync();                               // gn's device arrays die with this iteration
       }
-      auto gn = plan_gemm_raw(ctx, !left, left, prn);
-      run_gemm(ctx, *gn, nullptr, nullptr, nullptr);
-      size_t i = 0;
-      for (FG& f : fg) {
-        const int64_t n = left ? f.R : f.C;
-        // talloc buffers are zero-initialised and padded to an even length, so the padded axpy is exact
-        if (dr[i]) vec_axpy(ctx, f.E, dr[i], (n * n + 1) & ~int64_t(1), prm.noise);
-        i++;
-      }
-      ctx->sync();
     }
     // Hermitian eigendecompositions, one per charge group, spread over side streams so that the
     // host-latency-bound phases of cusolverDnDsyevd of different groups overlap

@@ -12,7 +12,7 @@ from .tensor import Context, DeviceTensor, HostTensor, _index_array, flatten_blo
 
 
 class StateEnvs:
-    """StateEnvs(psi::MPS, H::MPO).  `psi`: sequence of site tensors A_j(l, s, r) (host tensors or
+    """StateEnvs(psi::MPS, H::MPO) or StateEnvs(psi::MPS, Hs::Vector{MPO}) (sum of MPOs).  `psi`: sequence of site tensors A_j(l, s, r) (host tensors or
     DeviceTensors); `H`: sequence of MPO tensors W_j(wl, s', s, wr) (host).  As in the reference the state is
     copied on construction (state_envs.jl:59)."""
 
@@ -26,16 +26,20 @@ class StateEnvs:
         self.gemm_prof = dict(total_ms=0.0, launches=0, flops=0.0, max_tflops=0.0)
         self.last_solver_info = {}
         self.N = len(psi)
-        if len(H) != self.N:
+        # StateEnvs(psi, H::MPO) -> ProjMPO ; StateEnvs(psi, Hs::Vector{MPO}) -> ProjMPOSum2 (state_envs.jl:54-70)
+        Hs = list(H) if len(H) and isinstance(H[0], (list, tuple)) else [H]
+        if any(len(Hk) != self.N for Hk in Hs):
             raise ValueError("MPS and MPO lengths differ")
+        self.nterms = len(Hs)
         h = C.c_void_p()
         check(ctx.lib.tnl_env_create(ctx.h, self.N, C.byref(h)), ctx.h)
         self.h = h
-        for j, W in enumerate(H):
-            arr, nq, keep = _index_array(W.inds)
-            coords, offsets, data, nb = flatten_blocks(W)
-            check(ctx.lib.tnl_env_set_site_op(self.h, j + 1, nq, arr, nb, coords.ctypes.data, offsets.ctypes.data,
-                                              data.ctypes.data), ctx.h)
+        for k, Hk in enumerate(Hs):
+            for j, W in enumerate(Hk):
+                arr, nq, keep = _index_array(W.inds)
+                coords, offsets, data, nb = flatten_blocks(W)
+                check(ctx.lib.tnl_env_set_site_op_term(self.h, k, j + 1, nq, arr, nb, coords.ctypes.data,
+                                                       offsets.ctypes.data, data.ctypes.data), ctx.h)
         for j, A in enumerate(psi):
             dt = (A.copy() if copy else A) if isinstance(A, DeviceTensor) else DeviceTensor.from_host(ctx, A, nrow=2)
             check(ctx.lib.tnl_env_set_state(self.h, j + 1, dt.h), ctx.h)

@@ -384,9 +384,11 @@ def test_exp_solver_matches_oracle(ctx, nsite, t):
     assert np.isnan(e_o) and np.isnan(e_d)
     info_o, info_d = od.exp_solver.last_info, env_d.last_solver_info
     assert info_d["converged"] == 1 and info_o["converged"] == 1
-    assert abs(info_d["numops"] - info_o["numops"]) <= 1          # the eager exit test sits at the tolerance
     ref = out_o.permute(phi_o.inds).to_dense()
     assert rel(out_d.to_host().to_dense(), ref) < 1e-10
+    # the eager exit test sits at the tolerance; for growing exponentials (t > 0) the error estimate
+    # |dt beta normres expH[K, K+2]| is itself at the rounding level of the small exponential
+    assert abs(info_d["numops"] - info_o["numops"]) <= (1 if t < 0 else 3)
     # imaginary-time evolution is not norm preserving; the norm must match too
     assert abs(out_d.norm() - out_o.norm()) < 1e-11 * out_o.norm()
 
@@ -401,11 +403,12 @@ def test_exp_solver_substeps_when_the_basis_is_full(ctx):
     env_d.set_nsite(2); env_d.position(4)
     phi_o = ob.contract(env_o.psi[4], env_o.psi[5])
     phi_d = env_d.make_phi(4)
-    kw = dict(solver_krylovdim=6, solver_maxiter=200, solver_tol=1e-11)
-    _, out_o = od.exp_solver(env_o, phi_o, -0.8, **kw)
-    _, out_d = T.exp_solver(env_d, phi_d, -0.8, **kw)
+    kw = dict(solver_krylovdim=8, solver_maxiter=100, solver_tol=1e-11)
+    _, out_o = od.exp_solver(env_o, phi_o, -0.2, **kw)
+    _, out_d = T.exp_solver(env_d, phi_d, -0.2, **kw)
     assert od.exp_solver.last_info["numiter"] > 1 and env_d.last_solver_info["numiter"] > 1
-    assert env_d.last_solver_info["converged"] == 1
+    assert od.exp_solver.last_info["converged"] == 1 and env_d.last_solver_info["converged"] == 1
+    assert abs(env_d.last_solver_info["numiter"] - od.exp_solver.last_info["numiter"]) <= 2
     assert rel(out_d.to_host().to_dense(), out_o.permute(phi_o.inds).to_dense()) < 1e-9
 
 
@@ -464,3 +467,47 @@ def test_tdvp_two_site_follows_exact_imaginary_time_evolution(ctx):
     w = om.mps_to_dense(eng.getpsi())
     assert abs(abs(np.vdot(v, w)) - 1.0) < 1e-8          # O(dt^3) per step splitting error
     assert abs(T.getenergy(eng) - float(v @ Hd @ v)) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- ProjMPOSum2
+def test_mpo_sum_apply_noise_and_dmrg_match_oracle(ctx):
+    """StateEnvs(psi, Hs::Vector{MPO}) (src/mps/projmposum2.jl): apply, eig_solver, noisy + noise-free replacebond!
+    and a full DMRG run against the oracle, with two MPOs of different bond dimension."""
+    T, ob, od, ok, om, op = _imports()
+    N = 8
+    sites = om.siteinds("S=1", N)
+    Hs = [om.heisenberg_mpo(sites, Jz=1.0, Jxy=0.0), om.heisenberg_mpo(sites, Jz=0.0, Jxy=1.0)]
+    H = om.heisenberg_mpo(sites)
+    qn, dm = om.gaussian_link_sectors(30, 1.3, 4)
+    mps = od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(7)))
+    od.orthogonalize(mps, 4)
+    env_o = od.StateEnvs(mps, Hs)
+    env_d = T.StateEnvs(ctx, mps.t, Hs, llim=3, rlim=5)
+    env_1 = T.StateEnvs(ctx, mps.t, H, llim=3, rlim=5)
+    assert env_d.nterms == 2
+    env_o.set_nsite(2); env_o.position(4)
+    phi_o = ob.contract(env_o.psi[4], env_o.psi[5])
+    for e in (env_d, env_1):
+        e.set_nsite(2)
+    phi_d = env_d.make_phi(4)
+    env_d.position(4); env_1.position(4)
+    ref = env_o.product(phi_o).permute(phi_o.inds).to_dense()
+    assert rel(env_d.product(phi_d).to_host().to_dense(), ref) < 1e-12
+    assert rel(env_1.product(env_1.make_phi(4)).to_host().to_dense(), ref) < 1e-12      # sum == single MPO
+    for noise in (1e-3, 0.0):
+        eo, to, so = od.update_position(env_o, od.eig_solver, 4, 2, "left", maxdim=24, cutoff=1e-13, noise=noise)
+        ed, td, sd = T.update_position(env_d, T.eig_solver, 4, 2, "left", maxdim=24, cutoff=1e-13, noise=noise)
+        assert abs(ed - eo) < 1e-10 * abs(eo)
+        assert len(sd) == len(so) and abs(td - to) < 1e-10
+        assert np.allclose(sd, so, rtol=0, atol=1e-9 if noise else 1e-12)
+        od.orthogonalize(env_o.psi, 4); env_d.orthogonalize(4)
+        # keep the two states identical for the next round (noisy eigenvectors differ in null directions)
+        env_d = T.StateEnvs(ctx, env_o.psi.t, Hs, llim=3, rlim=5)
+    # full DMRG: two-site with noise, then one-site
+    psi0 = od.MPS(om.neel_mps(sites))
+    prm = dict(maxdim=[10, 20], nsweeps=[2, 2], cutoff=1e-13, noise=[1e-4, 0.0])
+    Eo, _, swo = od.dmrg2(psi0, Hs, od.DMRGParams(**prm))
+    Ed, _, swd = T.dmrg2(ctx, psi0.t, Hs, T.DMRGParams(**prm), outputlevel=0)
+    assert swd.maxchi == swo.maxchi
+    assert abs(Ed - Eo) < 1e-9 * abs(Eo)
+    assert abs(swd.energy[-1] - swo.energy[-1]) < 1e-10 * abs(Eo)

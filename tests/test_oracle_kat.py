@@ -236,3 +236,32 @@ def test_tdvp_sweeps_follow_exact_evolution(nsite, ts):
         assert abs(eng.swdata.energy[-1] - eng.swdata.energy[0]) < 1e-9      # energy conservation
     else:
         assert eng.swdata.energy[-1] < eng.swdata.energy[0]
+
+
+def test_mpo_sum_equals_single_mpo():
+    """ProjMPOSum2 restatement: H = H_zz + H_xy as two MPOs gives the same H_eff apply, noise term and DMRG energy
+    as the single MPO (src/mps/projmposum2.jl:86-145)."""
+    from oracle import blocksparse as ob, dmrg as od, models as om
+    N = 8
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites)
+    Hs = [om.heisenberg_mpo(sites, Jz=1.0, Jxy=0.0), om.heisenberg_mpo(sites, Jz=0.0, Jxy=1.0)]
+    qn, dm = om.gaussian_link_sectors(12, 1.3, 4, step=1)
+    mps = od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(5)))
+    od.orthogonalize(mps, 4)
+    e1, e2 = od.StateEnvs(mps, H), od.StateEnvs(mps, Hs)
+    for e in (e1, e2):
+        e.set_nsite(2); e.position(4)
+    phi = ob.contract(mps[4], mps[5])
+    a, b = e1.product(phi), e2.product(phi)
+    assert np.abs(a.to_dense() - b.permute(a.inds).to_dense()).max() < 1e-13
+    na, nb = e1.PH.noiseterm(phi, "left"), e2.PH.noiseterm(phi, "left")
+    # the noise term is quadratic in H: sum_k (L W_k phi)(..)^dag != (L W phi)(..)^dag in general; only its structure
+    # (indices, hermiticity, positivity) is shared
+    assert [ix.dim for ix in na.inds] == [ix.dim for ix in nb.inds]
+    psi0 = od.MPS(om.neel_mps(sites))
+    prm = od.DMRGParams(maxdim=[16, 32], nsweeps=[3, 3], cutoff=1e-14, noise=[1e-3, 0.0])
+    E1, _, _ = od.dmrg2(psi0, H, prm)
+    E2, _, _ = od.dmrg2(psi0, Hs, prm)
+    E0 = -3.374932598687897          # ED, S=1/2 N=8 OBC
+    assert abs(E1 - E0) < 1e-9 and abs(E2 - E0) < 1e-9
