@@ -104,6 +104,16 @@ int tnl_env_set_site_op(tnl_env_t env, int32_t site, int32_t nq, const tnl_index
  * become sums over the terms; every term keeps its own environments over the shared state. */
 int tnl_env_set_site_op_term(tnl_env_t env, int32_t term, int32_t site, int32_t nq, const tnl_index_t* inds4,
                              int64_t nblocks, const int32_t* coords, const int64_t* offsets, const double* data);
+/* StateEnvs(psi, H::CouplingModel) = ProjCouplingModel (src/mps/state_envs.jl:73-79, src/mps/projcouplingmodel.jl,
+ * src/base/couplingmodel.jl:14-17): tensor of term `id` (the key of the IDTensors dictionary, any non-negative
+ * integer) on `site`, handed over as W(wl, s', s, wr) where wl / wr are the OpLinks shared with the term's previous
+ * / next tensor (has_wl / has_wr = 1); where the reference tensor has no such OpLink (first / last / only tensor of
+ * a term: has_wl / has_wr = 0) the caller inserts a dim-1 charge-0 index.  Sites a term skips get no call.  An environment is either MPO-based
+ * (tnl_env_set_site_op*) or CouplingModel-based, not both.  makeL!/makeR!/product/noiseterm then follow
+ * projcouplingmodel.jl:123-492 id by id. */
+int tnl_env_cm_set_term(tnl_env_t env, int32_t site, int64_t id, int32_t has_wl, int32_t has_wr, int32_t nq,
+                        const tnl_index_t* inds4, int64_t nblocks, const int32_t* coords, const int64_t* offsets,
+                        const double* data);
 /* MPS tensor A_site(l, s, r); the env shares the tensor (no copy) */
 int tnl_env_set_state(tnl_env_t env, int32_t site, tnl_tensor_t a);
 int tnl_env_get_state(tnl_env_t env, int32_t site, tnl_tensor_t* out); /* getpsi, state_envs.jl:36 */

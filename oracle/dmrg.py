@@ -108,7 +108,13 @@ class StateEnvs:
     def __init__(self, psi: MPS, H: Sequence[BSTensor], Ms=None, weight: float = -1.0):
         self.psi = psi.copy()
         # StateEnvs(psi, H, Ms; weight)  (src/mps/state_envs.jl:86-103) when penalised states are given
-        if len(H) and isinstance(H[0], (list, tuple)):
+        from .couplingmodel import CouplingModel, ProjCouplingModel
+        if isinstance(H, CouplingModel):
+            # StateEnvs(psi, H::CouplingModel) (src/mps/state_envs.jl:73-79)
+            if Ms:
+                raise NotImplementedError("ProjCouplingModel_MPS (CouplingModel + penalised states) is not restated")
+            self.PH = ProjCouplingModel(H)
+        elif len(H) and isinstance(H[0], (list, tuple)):
             # StateEnvs(psi, Hs::Vector{MPO}) (src/mps/state_envs.jl:63-70)
             if Ms:
                 raise NotImplementedError("ProjMPOSum_MPS (sum of MPOs + penalised states) is not restated")

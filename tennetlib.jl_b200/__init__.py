@@ -4,6 +4,7 @@ Product code only: CUDA kernels + C ABI in `csrc/` (libtnl_b200.so) and the host
 interface (`StateEnvs`, `eig_solver`, `update_position`, `fullsweep`, `DMRGParams`, `dmrg_`/`dmrg2`).
 Nothing here imports `oracle/`; there is no CPU fallback."""
 from ._lib import EXPORTED, TnlError, load, so_path
+from .couplingmodel import CouplingModel
 from .dmrg import DMRGParams, dmrg, dmrg1, dmrg2, dmrg_
 from .solver import eig_solver, exp_solver
 from .state_envs import StateEnvs
@@ -14,4 +15,4 @@ from .update_site import halfsweep_done, update_position
 
 __all__ = ["Context", "DeviceTensor", "HostTensor", "Index", "StateEnvs", "eig_solver", "exp_solver",
            "update_position", "halfsweep_done", "fullsweep", "SweepData", "DMRGParams", "dmrg_", "dmrg", "dmrg1", "dmrg2",
-           "TDVPEngine", "tdvpsweep", "sweepcount", "getenergy", "getentropy", "maxchi", "totalerror", "load", "so_path", "TnlError", "EXPORTED"]
+           "CouplingModel", "TDVPEngine", "tdvpsweep", "sweepcount", "getenergy", "getentropy", "maxchi", "totalerror", "load", "so_path", "TnlError", "EXPORTED"]

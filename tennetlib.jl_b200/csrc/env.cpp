@@ -1423,9 +1423,10 @@ void Env::move_center(int from, int to) {
 namespace tnl {
 
 struct Env::CM {
-  struct Op { TensorP Wlr, Wrl, Wnr; Index wl, wr; };
+  struct Op { TensorP Wlr, Wrl, Wnr; Index wl, wr; bool open_l = false, open_r = false; };
+  struct E { TensorP t; bool open = false; };          // environment of one id; open: carries a real OpLink
   std::vector<std::map<int64_t, Op>> M;               // CouplingModel.terms: per site, id -> operator
-  std::vector<std::map<int64_t, TensorP>> LR;         // environments per site: id -> E_id  (L: nrow 2, R: nrow 1)
+  std::vector<std::map<int64_t, E>> LR;               // environments per site: id -> E_id  (L: nrow 2, R: nrow 1)
   std::map<std::string, Op> fillers;                  // identity operators of pass-through sites
   int64_t next_local = -1;                            // ids of the accumulated local tensors (gen_rand_id upstream)
   std::vector<std::pair<int64_t, std::shared_ptr<ApplyPlan>>> plans;
@@ -1448,13 +1449,18 @@ static Env::CM::Op make_op(Ctx* ctx, const HostBlocks& hb) {
   return op;
 }
 
-void Env::cm_set_term(int site, int64_t id, const HostBlocks& hb) {
+void Env::cm_set_term(int site, int64_t id, const HostBlocks& hb, bool open_l, bool open_r) {
   TNL_CHECK(!parent && more.empty(), "a CouplingModel environment cannot be mixed with MPO terms");
   TNL_CHECK(site >= 1 && site <= N, "site out of range");
   TNL_CHECK(hb.rank == 4, "CouplingModel site tensor must be given as (wl, s', s, wr) with trivial links where it has no OpLink");
   TNL_CHECK(id >= 0, "term ids must be non-negative");
   if (!cm) cm.reset(new CM(N));
-  cm->M[site - 1][id] = make_op(ctx, hb);
+  TNL_CHECK(open_l || is_trivial_link(hb.inds[0]), "a missing left OpLink must be given as a dim-1 charge-0 index");
+  TNL_CHECK(open_r || is_trivial_link(hb.inds[3]), "a missing right OpLink must be given as a dim-1 charge-0 index");
+  CM::Op op = make_op(ctx, hb);
+  op.open_l = open_l;
+  op.open_r = open_r;
+  cm->M[site - 1][id] = std::move(op);
   lpos = 0; rpos = N + 1; ap.reset();
   cm->plans.clear();
 }
@@ -1503,10 +1509,10 @@ void Env::cm_makeL(int k) {
   if (ll >= k) { lpos = k; return; }
   ll = std::max(ll, 0);
   while (ll < k) {
-    const std::map<int64_t, TensorP> empty;
+    const std::map<int64_t, CM::E> empty;
     const auto& L = ll <= 0 ? empty : cm->LR[ll - 1];
     const auto& Ms = cm->M[ll];
-    std::map<int64_t, TensorP> next;
+    std::map<int64_t, CM::E> next;
     TensorP local;
     std::vector<int64_t> ids;
     for (auto& kv : L) ids.push_back(kv.first);
@@ -1515,16 +1521,21 @@ void Env::cm_makeL(int k) {
     for (int64_t id : ids) {
       auto li = L.find(id);
       auto mi = Ms.find(id);
-      const Tensor* Lid = li == L.end() ? nullptr : li->second.get();
+      const Tensor* Lid = li == L.end() ? nullptr : li->second.t.get();
       const CM::Op* op;
+      bool open;
       if (mi != Ms.end()) {
         op = &mi->second;
         if (Lid) TNL_CHECK(same_space_dag(Lid->inds[1], op->wl), "CouplingModel: OpLink of a term does not match its left environment");
+        TNL_CHECK((Lid && li->second.open) == op->open_l, "CouplingModel: a term's left OpLink has no partner");
+        open = op->open_r;
       } else {
         op = &cm_filler(ctx, *cm, sket, with_dir(Lid->inds[1], -Lid->inds[1].dir), Lid->inds[1]);
+        open = li->second.open;
       }
       TensorP Ln = step_left(Lid, A[ll], *op->Wlr);
-      if (is_trivial_link(Ln->inds[1])) {
+      if (!open) {
+        TNL_CHECK(is_trivial_link(Ln->inds[1]), "CouplingModel: closed term with a non-trivial link");
         if (!local) local = Ln;
         else {
           TNL_CHECK(local->nelem == Ln->nelem, "local environment layouts differ");
@@ -1532,10 +1543,10 @@ void Env::cm_makeL(int k) {
           ctx->sync();
         }
       } else {
-        next[id] = Ln;
+        next[id] = CM::E{Ln, true};
       }
     }
-    if (local) next[cm->next_local--] = local;
+    if (local) next[cm->next_local--] = CM::E{local, false};
     cm->LR[ll] = std::move(next);
     ll++;
   }
@@ -1549,10 +1560,10 @@ void Env::cm_makeR(int k) {
   rl = std::min(rl, N + 1);
   while (rl > k) {
     const int j = rl - 2;                              // 0-based site being absorbed
-    const std::map<int64_t, TensorP> empty;
+    const std::map<int64_t, CM::E> empty;
     const auto& R = rl >= N + 1 ? empty : cm->LR[rl - 1];
     const auto& Ms = cm->M[j];
-    std::map<int64_t, TensorP> next;
+    std::map<int64_t, CM::E> next;
     TensorP local;
     std::vector<int64_t> ids;
     for (auto& kv : R) ids.push_back(kv.first);
@@ -1561,16 +1572,21 @@ void Env::cm_makeR(int k) {
     for (int64_t id : ids) {
       auto ri = R.find(id);
       auto mi = Ms.find(id);
-      const Tensor* Rid = ri == R.end() ? nullptr : ri->second.get();
+      const Tensor* Rid = ri == R.end() ? nullptr : ri->second.t.get();
       const CM::Op* op;
+      bool open;
       if (mi != Ms.end()) {
         op = &mi->second;
         if (Rid) TNL_CHECK(same_space_dag(Rid->inds[1], op->wr), "CouplingModel: OpLink of a term does not match its right environment");
+        TNL_CHECK((Rid && ri->second.open) == op->open_r, "CouplingModel: a term's right OpLink has no partner");
+        open = op->open_l;
       } else {
         op = &cm_filler(ctx, *cm, sket, Rid->inds[1], with_dir(Rid->inds[1], -Rid->inds[1].dir));
+        open = ri->second.open;
       }
       TensorP Rn = step_right(Rid, A[j], *op->Wrl);
-      if (is_trivial_link(Rn->inds[1])) {
+      if (!open) {
+        TNL_CHECK(is_trivial_link(Rn->inds[1]), "CouplingModel: closed term with a non-trivial link");
         if (!local) local = Rn;
         else {
           TNL_CHECK(local->nelem == Rn->nelem, "local environment layouts differ");
@@ -1578,10 +1594,10 @@ void Env::cm_makeR(int k) {
           ctx->sync();
         }
       } else {
-        next[id] = Rn;
+        next[id] = CM::E{Rn, true};
       }
     }
-    if (local) next[cm->next_local--] = local;
+    if (local) next[cm->next_local--] = CM::E{local, false};
     cm->LR[j] = std::move(next);
     rl--;
   }
@@ -1592,7 +1608,7 @@ void Env::cm_makeR(int k) {
 struct CMPieces { TensorP L, R; const Env::CM::Op* W[2] = {nullptr, nullptr}; };
 
 static std::vector<std::pair<int64_t, CMPieces>> cm_collect(Env& e, Env::CM& cm) {
-  const std::map<int64_t, TensorP> empty;
+  const std::map<int64_t, Env::CM::E> empty;
   const auto& L = e.lpos <= 0 ? empty : cm.LR[e.lpos - 1];
   const auto& R = e.rpos >= e.N + 1 ? empty : cm.LR[e.rpos - 1];
   std::vector<int64_t> ids;
@@ -1606,21 +1622,23 @@ static std::vector<std::pair<int64_t, CMPieces>> cm_collect(Env& e, Env::CM& cm)
     CMPieces pc;
     auto li = L.find(id);
     auto ri = R.find(id);
-    if (li != L.end()) pc.L = li->second;
-    if (ri != R.end()) pc.R = ri->second;
+    if (li != L.end()) pc.L = li->second.t;
+    if (ri != R.end()) pc.R = ri->second.t;
     Index cur = pc.L ? pc.L->inds[1] : Index{};        // link carried to the right (as it sits on the environment)
     bool have = (bool)pc.L;
+    bool open = pc.L && li->second.open;                // the carried link is a real OpLink
     for (int sidx = 0; sidx < e.nsite; sidx++) {
       const int site = e.lpos + sidx;                    // 0-based
       auto mi = cm.M[site].find(id);
       if (mi != cm.M[site].end()) {
         pc.W[sidx] = &mi->second;
         if (have) TNL_CHECK(same_space_dag(cur, mi->second.wl), "CouplingModel: OpLinks of a term do not chain");
-        else TNL_CHECK(is_trivial_link(mi->second.wl), "CouplingModel: a term starts with an open OpLink");
+        TNL_CHECK(open == mi->second.open_l, "CouplingModel: a term's OpLink has no partner on the left");
+        open = mi->second.open_r;
       } else {
         Index t;
         if (!have) {                                     // nothing to the left: trivial pass-through
-          t.nq = e.A[site]->inds[1].nq; t.dir = +1; t.dims = {1}; t.qns = {charge_zero()};
+          t.nq = e.A[site]->inds[1].nq; t.dir = -1; t.dims = {1}; t.qns = {charge_zero()};
           cur = t;
         }
         pc.W[sidx] = &cm_filler(e.ctx, cm, e.A[site]->inds[1], with_dir(cur, -cur.dir), cur);
@@ -1628,8 +1646,12 @@ static std::vector<std::pair<int64_t, CMPieces>> cm_collect(Env& e, Env::CM& cm)
       cur = pc.W[sidx]->wr;
       have = true;
     }
-    if (pc.R) TNL_CHECK(!have || same_space_dag(cur, pc.R->inds[1]), "CouplingModel: OpLink does not match the right environment");
-    else TNL_CHECK(!have || is_trivial_link(cur), "CouplingModel: a term ends with an open OpLink");
+    if (pc.R) {
+      TNL_CHECK(!have || same_space_dag(cur, pc.R->inds[1]), "CouplingModel: OpLink does not match the right environment");
+      TNL_CHECK(open == ri->second.open, "CouplingModel: a term's OpLink has no partner on the right");
+    } else {
+      TNL_CHECK(!open, "CouplingModel: a term ends with an open OpLink");
+    }
     out.emplace_back(id, pc);
   }
   return out;

@@ -79,7 +79,8 @@ class Env {
   struct CM;
   struct CMDeleter { void operator()(CM* p) const; };
   std::unique_ptr<CM, CMDeleter> cm;
-  void cm_set_term(int site, int64_t id, const HostBlocks& hb);   // (wl, s', s, wr) with trivial links as needed
+  // W(wl, s', s, wr); open_l / open_r: wl / wr is a real OpLink (otherwise a dim-1 charge-0 placeholder)
+  void cm_set_term(int site, int64_t id, const HostBlocks& hb, bool open_l, bool open_r);
   Env& term(int k);                  // k = 0: this env; k >= 1: more[k-1] (created on demand)
   int nterms() const { return 1 + (int)more.size(); }
   void set_nsite(int n);

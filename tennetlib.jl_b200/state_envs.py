@@ -8,6 +8,7 @@ from typing import List, Sequence
 import numpy as np
 
 from ._lib import check
+from .couplingmodel import canonical_terms, is_coupling_model
 from .tensor import Context, DeviceTensor, HostTensor, _index_array, flatten_blocks
 
 
@@ -26,8 +27,15 @@ class StateEnvs:
         self.gemm_prof = dict(total_ms=0.0, launches=0, flops=0.0, max_tflops=0.0)
         self.last_solver_info = {}
         self.N = len(psi)
-        # StateEnvs(psi, H::MPO) -> ProjMPO ; StateEnvs(psi, Hs::Vector{MPO}) -> ProjMPOSum2 (state_envs.jl:54-70)
-        Hs = list(H) if len(H) and isinstance(H[0], (list, tuple)) else [H]
+        # StateEnvs(psi, H::MPO) -> ProjMPO ; StateEnvs(psi, Hs::Vector{MPO}) -> ProjMPOSum2 ;
+        # StateEnvs(psi, H::CouplingModel) -> ProjCouplingModel (state_envs.jl:54-79)
+        self.is_coupling_model = is_coupling_model(H)
+        if self.is_coupling_model:
+            Hs, cm_terms = [], canonical_terms(H)
+            if len(cm_terms) != self.N:
+                raise ValueError("MPS and CouplingModel lengths differ")
+        else:
+            Hs = list(H) if len(H) and isinstance(H[0], (list, tuple)) else [H]
         if any(len(Hk) != self.N for Hk in Hs):
             raise ValueError("MPS and MPO lengths differ")
         self.nterms = len(Hs)
@@ -40,6 +48,14 @@ class StateEnvs:
                 coords, offsets, data, nb = flatten_blocks(W)
                 check(ctx.lib.tnl_env_set_site_op_term(self.h, k, j + 1, nq, arr, nb, coords.ctypes.data,
                                                        offsets.ctypes.data, data.ctypes.data), ctx.h)
+        if self.is_coupling_model:
+            for j, terms in enumerate(cm_terms):
+                for tid, W in terms.items():
+                    arr, nq, keep = _index_array(W.inds)
+                    coords, offsets, data, nb = flatten_blocks(W)
+                    check(ctx.lib.tnl_env_cm_set_term(self.h, j + 1, int(tid), int(W.has_wl), int(W.has_wr), nq, arr, nb,
+                                                      coords.ctypes.data,
+                                                      offsets.ctypes.data, data.ctypes.data), ctx.h)
         for j, A in enumerate(psi):
             dt = (A.copy() if copy else A) if isinstance(A, DeviceTensor) else DeviceTensor.from_host(ctx, A, nrow=2)
             check(ctx.lib.tnl_env_set_state(self.h, j + 1, dt.h), ctx.h)

@@ -511,3 +511,116 @@ def test_mpo_sum_apply_noise_and_dmrg_match_oracle(ctx):
     assert swd.maxchi == swo.maxchi
     assert abs(Ed - Eo) < 1e-9 * abs(Eo)
     assert abs(swd.energy[-1] - swo.energy[-1]) < 1e-10 * abs(Eo)
+
+
+# ---------------------------------------------------------------------------------------------- ProjCouplingModel
+def _cm_setup(om, od, oc, kind, N, chi, seed, center, **model_kw):
+    sites = om.siteinds(kind, N)
+    M = oc.heisenberg_coupling_model(sites, **model_kw)
+    qn, dm = om.gaussian_link_sectors(chi, 1.3, 4, step=2 if kind == "S=1" else 1)
+    mps = od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(seed)))
+    od.orthogonalize(mps, center)
+    return sites, M, mps
+
+
+@pytest.mark.parametrize("model_kw", [dict(merge=True), dict(merge=False), dict(merge=True, field=0.3, j2=0.5)])
+def test_coupling_model_apply_matches_oracle(ctx, model_kw):
+    """StateEnvs(psi, H::CouplingModel): environments and product(v) id by id (src/mps/projcouplingmodel.jl:123-383)
+    for two-, one- and zero-site vectors, at the edges and mid-chain; terms that skip sites (j2) and one-site terms
+    (field) included.  The sum over ids must also equal the MPO of the same Hamiltonian."""
+    T, ob, od, ok, om, op = _imports()
+    from oracle import couplingmodel as oc
+    N = 8
+    sites, M, mps = _cm_setup(om, od, oc, "S=1", N, 24, 3, 1, **model_kw)
+    env_o = od.StateEnvs(mps, M)
+    env_d = T.StateEnvs(ctx, mps.t, M, llim=0, rlim=2)
+    assert env_d.is_coupling_model
+    for pos in (1, 4, N - 1):
+        env_o.set_nsite(2); env_o.position(pos)
+        env_d.set_nsite(2)
+        phi_o = ob.contract(env_o.psi[pos], env_o.psi[pos + 1])
+        phi_d = env_d.make_phi(pos)
+        env_d.position(pos)
+        ref = env_o.product(phi_o).permute(phi_o.inds).to_dense()
+        assert rel(env_d.product(phi_d).to_host().to_dense(), ref) < 1e-12
+        w = phi_d.copy().fill_random(7)
+        a = w.dot(env_d.product(phi_d)); b = env_d.product(w).dot(phi_d)
+        assert abs(a - b) < 1e-10 * max(1.0, abs(a))                     # hermiticity of the summed H_eff
+    if model_kw == dict(merge=True):
+        # same Hamiltonian as an MPO: equal H_eff once the orthogonality centre sits inside the site range (terms
+        # without a tensor on one side act as the identity there, which presumes orthonormal block bases)
+        mps4 = mps.copy()
+        od.orthogonalize(mps4, 4)
+        env_m = T.StateEnvs(ctx, mps4.t, om.heisenberg_mpo(sites), llim=3, rlim=5)
+        env_c = T.StateEnvs(ctx, mps4.t, M, llim=3, rlim=5)
+        env_m.set_nsite(2); env_c.set_nsite(2)
+        phi = env_m.make_phi(4)
+        env_m.position(4); env_c.position(4)
+        assert rel(env_c.product(phi).to_host().to_dense(), env_m.product(phi).to_host().to_dense()) < 1e-12
+    # one-site and zero-site
+    env_o.set_nsite(1); env_o.position(4)
+    env_d.set_nsite(1); env_d.position(4)
+    v_o = env_o.psi[4]
+    ref = env_o.product(v_o).permute(v_o.inds).to_dense()
+    assert rel(env_d.product(env_d.site_tensor(4)).to_host().to_dense(), ref) < 1e-12
+    # zero-site: bond matrix between sites 4 and 5 (psi[4] = U, C = S*V as in update_site.jl:162-186)
+    v4 = env_o.psi[4]
+    Lf, Rf, spec, u = ob.factorize(v4, v4.inds[:2], ortho="left", which_decomp="svd", cutoff=0.0)
+    env_o.psi[4] = Lf
+    env_o.PH.lpos, env_o.PH.rpos = 0, N + 1
+    env_d2 = T.StateEnvs(ctx, env_o.psi.t, M, llim=4, rlim=6)
+    env_o.set_nsite(0); env_o.position(5)
+    env_d2.set_nsite(0); env_d2.position(5)
+    Cd = T.DeviceTensor.from_host(ctx, Rf, 1)
+    ref = env_o.product(Rf).permute(Rf.inds).to_dense()
+    assert rel(env_d2.product(Cd).to_host().to_dense(), ref) < 1e-12
+
+
+@pytest.mark.parametrize("merge", [True, False])
+def test_coupling_model_dmrg_matches_oracle_and_ed(ctx, merge):
+    """dmrg2 / dmrg1 on a CouplingModel (the reference's own test model, test/test_MPS_DMRG.jl:28-36,104-113):
+    noisy and noise-free sweeps against the oracle, final energy against exact diagonalisation."""
+    T, ob, od, ok, om, op = _imports()
+    from oracle import couplingmodel as oc
+    N = 8
+    sites = om.siteinds("S=1/2", N)
+    M = oc.heisenberg_coupling_model(sites, merge=merge)
+    psi0 = od.MPS(om.neel_mps(sites))
+    prm = dict(maxdim=[8, 20], nsweeps=[2, 3], cutoff=1e-14, noise=[1e-3, 0.0])
+    Eo, _, swo = od.dmrg2(psi0, M, od.DMRGParams(**prm))
+    Ed, env_d, swd = T.dmrg2(ctx, psi0.t, M, T.DMRGParams(**prm), outputlevel=0)
+    assert swd.maxchi == swo.maxchi
+    assert abs(swd.energy[-1] - swo.energy[-1]) < 1e-10 * abs(Eo)
+    assert abs(Ed - (-3.374932598687897)) < 1e-9
+    # one-site sweeps afterwards keep the energy
+    E1, _, sw1 = T.dmrg1(ctx, env_d.getpsi(), M, T.DMRGParams(maxdim=[20], nsweeps=[1], cutoff=1e-14), llim=0, rlim=2,
+                         outputlevel=0)
+    assert abs(E1 - Ed) < 1e-9
+
+
+def test_coupling_model_noise_term_and_tdvp(ctx):
+    """Noisy replacebond! (noiseterm(::ProjCouplingModel), src/mps/projcouplingmodel.jl:391-492) and TDVP sweeps on a
+    CouplingModel with next-nearest-neighbour terms, against the oracle."""
+    T, ob, od, ok, om, op = _imports()
+    from oracle import couplingmodel as oc
+    N = 8
+    sites, M, mps = _cm_setup(om, od, oc, "S=1", N, 24, 9, 4, merge=True, j2=0.4)
+    env_o = od.StateEnvs(mps, M)
+    for ortho, pos, center in (("left", 4, 4), ("right", 3, 4)):
+        od.orthogonalize(env_o.psi, center)
+        env_d = T.StateEnvs(ctx, env_o.psi.t, M, llim=center - 1, rlim=center + 1)
+        eo, to, so = od.update_position(env_o, od.eig_solver, pos, 2, ortho, maxdim=20, cutoff=1e-13, noise=1e-3)
+        ed, td, sd = T.update_position(env_d, T.eig_solver, pos, 2, ortho, maxdim=20, cutoff=1e-13, noise=1e-3)
+        assert abs(ed - eo) < 1e-10 * abs(eo)
+        assert len(sd) == len(so) and abs(td - to) < 1e-10
+        assert np.allclose(sd, so, rtol=0, atol=1e-9)
+    sites = om.siteinds("S=1/2", N)
+    M = oc.heisenberg_coupling_model(sites, merge=True, j2=0.3)
+    psi0 = od.MPS(om.neel_mps(sites))
+    eng_o = od.TDVPEngine(psi0, M)
+    eng_d = T.TDVPEngine(ctx, psi0.t, M)
+    for ns in (2, 2, 1):
+        od.tdvpsweep(eng_o, -0.05, ns, maxdim=16, cutoff=1e-12)
+        T.tdvpsweep(eng_d, -0.05, ns, maxdim=16, cutoff=1e-12, outputlevel=0)
+    assert eng_d.swdata.maxchi == eng_o.swdata.maxchi
+    assert np.allclose(eng_d.swdata.energy, eng_o.swdata.energy, rtol=1e-10, atol=0)
