@@ -178,6 +178,13 @@ def halfsweep_done(N, pos, nsite, ortho):
     return False
 
 
+def _kept_side(psi, b, phi, ortho):
+    """Indices of the side of the bond whose density matrix is diagonalised, in the order `replacebond` /
+    `factorize` group them: psi[b]'s indices for ortho left, the remaining indices of phi (in phi's order) else."""
+    left = [ix for ix in psi[b].inds if ix in phi.inds]
+    return left if ortho == "left" else [ix for ix in phi.inds if ix not in left]
+
+
 def _update_two_site(sysenv: StateEnvs, solver, pos, ortho, time_step, normalize, maxdim, mindim, cutoff,
                      svd_alg, noise, reverse_step, **kw):
     psi = sysenv.psi
@@ -193,7 +200,7 @@ def _update_two_site(sysenv: StateEnvs, solver, pos, ortho, time_step, normalize
         energy = float(np.real(inner(phi, sysenv.PH(phi))))
     drho = None
     if abs(noise) > FLOAT64_THRESHOLD:
-        d = drho_matrices(sysenv.PH.noiseterm(phi, ortho), noise)
+        d = drho_matrices(sysenv.PH.noiseterm(phi, ortho), noise, _kept_side(psi, pos, phi, ortho))
         drho = d if ortho == "left" else {tuple(-x for x in q): M for q, M in d.items()}
     spec = replacebond(psi, pos, phi, maxdim=maxdim, mindim=mindim, cutoff=cutoff, eigen_perturbation=drho,
                        ortho=ortho, normalize=normalize, which_decomp=None, svd_alg=svd_alg)
@@ -238,7 +245,7 @@ def _update_one_site(sysenv: StateEnvs, solver, pos, ortho, time_step, normalize
         psi[pos] = phi                               # keeps the index bookkeeping of psi[pos0] for replacebond
         sysenv.set_nsite(2)
         sysenv.position(pos0)
-        d = drho_matrices(sysenv.PH.noiseterm(phi2, ortho), noise)
+        d = drho_matrices(sysenv.PH.noiseterm(phi2, ortho), noise, _kept_side(psi, pos0, phi2, ortho))
         drho = d if ortho == "left" else {tuple(-x for x in q): M for q, M in d.items()}
         spec = replacebond(psi, pos0, phi2, maxdim=maxdim, mindim=mindim, cutoff=cutoff, eigen_perturbation=drho,
                            ortho=ortho, normalize=normalize, which_decomp=None, svd_alg=svd_alg)

@@ -171,9 +171,17 @@ class ProjMPOSum2:
         return nt
 
 
-def drho_matrices(drho: BSTensor, scale: float):
-    """Per-charge matrices of scale*drho, rows = primed index group (layout of `matricize`)."""
-    primed = [ix for ix in drho.inds if ix.plev > 0]
+def drho_matrices(drho: BSTensor, scale: float, order: Sequence[Index] | None = None):
+    """Per-charge matrices of scale*drho, rows = primed index group (layout of `matricize`).  `order`: the
+    (unprimed) indices of the kept side in the order the factorisation groups them -- the noise term of a
+    CouplingModel comes out with its indices in another order than the two-site tensor's."""
+    if order is None:
+        primed = [ix for ix in drho.inds if ix.plev > 0]
+    else:
+        primed = [next(jx for jx in drho.inds if jx.id == ix.id and jx.plev > 0) for ix in order]
+    # columns in the same order as the rows (the noise term's own index order is arbitrary)
+    unprimed = [next(jx for jx in drho.inds if jx.id == ix.id and jx.plev == 0) for ix in primed]
+    drho = drho.permute(primed + unprimed)
     _, groups, _, _, _ = matricize(drho, primed)
     return {q: scale * M for q, (M, _, _) in groups.items()}
 

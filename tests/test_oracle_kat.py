@@ -265,3 +265,72 @@ def test_mpo_sum_equals_single_mpo():
     E2, _, _ = od.dmrg2(psi0, Hs, prm)
     E0 = -3.374932598687897          # ED, S=1/2 N=8 OBC
     assert abs(E1 - E0) < 1e-9 and abs(E2 - E0) < 1e-9
+
+
+def _mpo_as_coupling_model(H, sites):
+    """CouplingModel(mpos::MPO...) (src/base/couplingmodel.jl:352-379): one id, links retagged "OpLink"."""
+    from oracle import blocksparse as ob, couplingmodel as oc
+    N = len(H)
+    terms = [dict() for _ in range(N)]
+    for j, W in enumerate(H):
+        inds = [ix.copy(tags="OpLink") if "Link" in ix.tags else ix for ix in W.inds]
+        blocks = dict(W.blocks)
+        if j == 0:
+            inds, blocks = inds[1:], {c[1:]: b[0] for c, b in blocks.items()}
+        if j == N - 1:
+            inds, blocks = inds[:-1], {c[:-1]: b[..., 0] for c, b in blocks.items()}
+        terms[j][7] = ob.BSTensor(inds, blocks)
+    return oc.CouplingModel(sites, terms)
+
+
+def test_coupling_model_restatement_against_dense_and_mpo():
+    """CouplingModel / ProjCouplingModel restatement: the model equals the dense Hamiltonian (merged and unmerged
+    terms, next-nearest-neighbour terms that skip a site, one-site terms), <phi|H_eff|phi> equals the dense
+    expectation at several positions, and a single-id model built from an MPO reproduces the ProjMPO update
+    (energy, truncation error, spectrum) including the noise term on both sweep directions."""
+    from oracle import blocksparse as ob, couplingmodel as oc, dmrg as od, models as om
+    N = 6
+    for kind in ("S=1/2", "S=1"):
+        sites = om.siteinds(kind, N)
+        Hd = om.mpo_to_dense(om.heisenberg_mpo(sites))
+        for merge in (True, False):
+            M = oc.heisenberg_coupling_model(sites, merge=merge)
+            assert np.abs(oc.coupling_model_to_dense(M) - Hd).max() < 1e-14
+    M = oc.heisenberg_coupling_model(sites, merge=True, field=0.3, j2=0.5)
+    Md = oc.coupling_model_to_dense(M)
+    assert np.abs(Md - Md.T).max() < 1e-14
+    qn, dm = om.gaussian_link_sectors(10, 1.3, 4, step=2)
+    mps = od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(5)))
+    v = None
+    for nsite, pos in ((2, 3), (1, 3), (2, 1), (2, 5)):
+        od.orthogonalize(mps, pos)
+        P = oc.ProjCouplingModel(M)
+        P.set_nsite(nsite); P.position(mps.t, pos)
+        phi = ob.contract(mps[pos], mps[pos + 1]) if nsite == 2 else mps[pos]
+        v = om.mps_to_dense(mps.t)
+        assert abs(ob.inner(phi, P.product(phi)) / ob.inner(phi, phi) - v @ Md @ v / (v @ v)) < 1e-12
+    H = om.heisenberg_mpo(sites)
+    Mh = _mpo_as_coupling_model(H, sites)
+    od.orthogonalize(mps, 3)
+    for ortho, pos in (("left", 3), ("right", 2)):
+        res = [od.update_position(od.StateEnvs(mps, X), od.eig_solver, pos, 2, ortho, maxdim=8, cutoff=1e-13, noise=1e-3)
+               for X in (H, Mh)]
+        assert abs(res[0][0] - res[1][0]) < 1e-12
+        assert abs(res[0][1] - res[1][1]) < 1e-13
+        assert np.abs(res[0][2] - res[1][2]).max() < 1e-13
+
+
+def test_coupling_model_dmrg_and_tdvp_kat():
+    """The reference's own test model (test/test_MPS_DMRG.jl:28-36,104-113) through the restated ProjCouplingModel:
+    DMRG reaches the ED ground-state energy for merged and unmerged terms; TDVP lowers the energy in imaginary time."""
+    from oracle import couplingmodel as oc, dmrg as od, models as om
+    sites = om.siteinds("S=1/2", 8)
+    for merge in (True, False):
+        M = oc.heisenberg_coupling_model(sites, merge=merge)
+        E, _, _ = od.dmrg2(od.MPS(om.neel_mps(sites)), M,
+                           od.DMRGParams(maxdim=[8, 20], nsweeps=[2, 3], cutoff=1e-14, noise=[1e-3, 0.0]))
+        assert abs(E - (-3.374932598687897)) < 1e-10
+    eng = od.TDVPEngine(od.MPS(om.neel_mps(sites)), oc.heisenberg_coupling_model(sites, merge=True, j2=0.3))
+    for ns in (2, 2, 1):
+        od.tdvpsweep(eng, -0.05, ns, maxdim=16, cutoff=1e-12)
+    assert eng.swdata.energy[0] > eng.swdata.energy[1] > eng.swdata.energy[2]
