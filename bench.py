@@ -246,6 +246,7 @@ def run_ours(args):
     sysenv.profile = True
     sysenv.profile_kernels = True
     sysenv.phase_ms = {}
+    sysenv.phase_log = []
     sysenv.phase_kernel_ms = {}
     ctx.profile_gemm(True)
     ctx.profile_read()
@@ -345,6 +346,7 @@ def run_ours(args):
             "allreduce_gb_per_step": cnt["_"] / args.steps / 1e9,
             "sweep_time_s_est": 198 * ms_per_step * 1e-3,
             "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+            "phase_ms_max_over_steps": {k: max(v for n, v in sysenv.phase_log if n == k) for k in phases},
             "apply_gflop": apply_flops_total / max(1, numops_total) / 1e9, "applies_per_step": numops_total / args.steps,
             "energies": energies[-2:], "setup_s": t_setup,
             "krylov_vec": {"algorithmic_gb_per_step": cnt["vec_bytes"] / args.steps / 1e9},

@@ -109,16 +109,13 @@ class StateEnvs:
         self.psi = psi.copy()
         # StateEnvs(psi, H, Ms; weight)  (src/mps/state_envs.jl:86-103) when penalised states are given
         from .couplingmodel import CouplingModel, ProjCouplingModel
+        Mt = [m.t if isinstance(m, MPS) else m for m in Ms] if Ms else None
         if isinstance(H, CouplingModel):
-            # StateEnvs(psi, H::CouplingModel) (src/mps/state_envs.jl:73-79)
-            if Ms:
-                raise NotImplementedError("ProjCouplingModel_MPS (CouplingModel + penalised states) is not restated")
-            self.PH = ProjCouplingModel(H)
+            # StateEnvs(psi, H::CouplingModel[, Ms; weight]) (src/mps/state_envs.jl:73-79,131-150)
+            self.PH = ProjCouplingModel(H) if not Ms else ProjMPO_MPS2(None, Mt, weight, PH=ProjCouplingModel(H))
         elif len(H) and isinstance(H[0], (list, tuple)):
-            # StateEnvs(psi, Hs::Vector{MPO}) (src/mps/state_envs.jl:63-70)
-            if Ms:
-                raise NotImplementedError("ProjMPOSum_MPS (sum of MPOs + penalised states) is not restated")
-            self.PH = ProjMPOSum2(H)
+            # StateEnvs(psi, Hs::Vector{MPO}[, Ms; weight]) (src/mps/state_envs.jl:63-70,106-128)
+            self.PH = ProjMPOSum2(H) if not Ms else ProjMPO_MPS2(None, Mt, weight, PH=ProjMPOSum2(H))
         else:
             self.PH = ProjMPO(H) if not Ms else ProjMPO_MPS2(H, [m.t if isinstance(m, MPS) else m for m in Ms], weight)
 
@@ -363,6 +360,58 @@ def fullsweep(sysenv: StateEnvs, solver, nsite: int, swdata: SweepData, **kw):
     return np.nan, np.nan
 
 
+def dynamic_fullsweep(sysenv: StateEnvs, solver, swdata: SweepData, eigthreshold: float = 1e-12, extendat=None, **kw):
+    """src/mps/sweep.jl:257-382: bond by bond one-site update where the smallest kept Schmidt weight of the
+    previous half sweep is below `eigthreshold` or the bond is saturated at `maxdim`, two-site update otherwise.
+    The first sweep (and every `extendat`-th) is a plain two-site sweep for every PH but ProjMPO, which needs the
+    Global Subspace Expansion (`krylov_extend!`, not restated)."""
+    from .projmpo import ProjMPO as _ProjMPO
+    maxdim = kw.get("maxdim", None)
+    first = swdata.sweepcount == 0 or (extendat is not None and (swdata.sweepcount + 1) % extendat == 0)
+    if first:
+        if type(sysenv.PH) is _ProjMPO:
+            raise NotImplementedError("dynamic_fullsweep! on StateEnvs{ProjMPO} starts with krylov_extend! (not restated)")
+        return fullsweep(sysenv, solver, 2, swdata, **kw)
+    psi = sysenv.psi
+    if (not psi.isortho()) or psi.orthocenter() != 1:
+        orthogonalize(psi, 1)
+    energy = np.nan
+    maxtruncerr = 0.0
+    swdata.sweepcount += 1
+    N = len(sysenv)
+    lasteigs = [None] * (N - 1)
+    big = (1 << 62) if maxdim is None else maxdim
+
+    def pick(bond):
+        return 1 if (swdata.lasteigs[bond - 1][-1] < eigthreshold or psi[bond].inds[2].dim >= big) else 2
+    for bond in range(1, N):
+        nsite = pick(bond)
+        energy, err, eigs = update_position(sysenv, solver, bond, nsite, "left", **kw)
+        lasteigs[bond - 1] = eigs
+        maxtruncerr = max(err, maxtruncerr)
+        if nsite == 1 and bond == N - 1:
+            energy, _, _ = update_position(sysenv, solver, bond + 1, nsite, "left", **kw)
+    swdata.lasteigs = lasteigs
+    lasteigs = list(lasteigs)
+    for bond in range(N - 1, 0, -1):
+        nsite = pick(bond)
+        site = bond + 1 if nsite == 1 else bond
+        energy, err, eigs = update_position(sysenv, solver, site, nsite, "right", **kw)
+        lasteigs[bond - 1] = eigs
+        maxtruncerr = max(err, maxtruncerr)
+        if nsite == 1 and bond == 1:
+            energy, _, _ = update_position(sysenv, solver, bond, nsite, "right", **kw)
+    swdata.lasteigs = lasteigs
+    swdata.maxchi.append(max(A.inds[2].dim for A in psi.t[:-1]))
+    swdata.energy.append(energy)
+    mideigs = lasteigs[N // 2 - 1]
+    swdata.entropy.append(_entropy(mideigs / np.sum(mideigs)))
+    swdata.maxtruncerr.append(maxtruncerr)
+    if swdata.sweepcount > 1:
+        return swdata.energy[-1] - swdata.energy[-2], swdata.entropy[-1] - swdata.entropy[-2]
+    return np.nan, np.nan
+
+
 class DMRGParams:
     """src/mps/dmrg.jl:26-33,72-102."""
 
@@ -443,6 +492,8 @@ def tdvpsweep(engine: TDVPEngine, time_step, nsite=2, solver=exp_solver, **kw):
             raise RuntimeError("`tdvpsweep!()`: `extendat` must be `nothing` for `nsite == 2` or `nsite == 1`.")
         kw.pop("extendat", None)
         fullsweep(engine.sysenv, solver, nsite, engine.swdata, time_step=0.5 * time_step, reverse_step=True, **kw)
+    elif nsite == "dynamic":
+        dynamic_fullsweep(engine.sysenv, solver, engine.swdata, time_step=0.5 * time_step, reverse_step=True, **kw)
     else:
-        raise NotImplementedError("dynamic_fullsweep! needs krylov_extend! (SURVEY.md section 8f rank 1)")
+        raise RuntimeError('`tdvpsweep!()`: `nsite` must be `"dynamic"`, `2`, or `1` !!')
     engine.abstime += abs(time_step)

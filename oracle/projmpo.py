@@ -262,12 +262,14 @@ class ProjMPS2:
 
 
 class ProjMPO_MPS2:
-    """PH + weight * sum_M |M><M| (src/mps/projmpo_mps2.jl:94-134); noiseterm forwards to PH."""
+    """PH + weight * sum_M |M><M| (src/mps/projmpo_mps2.jl:94-134); noiseterm forwards to PH.  With `PH` given
+    explicitly the same wrapper is ProjMPOSum_MPS (src/mps/projmposum_mps.jl:94-100) and ProjCouplingModel_MPS
+    (src/mps/projcouplingmodel_mps.jl:95-101), which differ only in the type of PH."""
 
-    def __init__(self, H, Ms, weight: float):
+    def __init__(self, H, Ms, weight: float, PH=None):
         if weight <= 0.0:
             raise ValueError(f"`weight` parameter should be > 0.0 (value passed was `weight={weight}`)")
-        self.PH = ProjMPO(H)
+        self.PH = ProjMPO(H) if PH is None else PH
         self.pm = [ProjMPS2(M) for M in Ms]
         self.weight = weight
         self.N = self.PH.N

@@ -8,11 +8,11 @@ from .couplingmodel import CouplingModel
 from .dmrg import DMRGParams, dmrg, dmrg1, dmrg2, dmrg_
 from .solver import eig_solver, exp_solver
 from .state_envs import StateEnvs
-from .sweep import SweepData, fullsweep
+from .sweep import SweepData, dynamic_fullsweep, fullsweep
 from .tdvp import TDVPEngine, getenergy, getentropy, maxchi, sweepcount, tdvpsweep, totalerror
 from .tensor import Context, DeviceTensor, HostTensor, Index
 from .update_site import halfsweep_done, update_position
 
 __all__ = ["Context", "DeviceTensor", "HostTensor", "Index", "StateEnvs", "eig_solver", "exp_solver",
-           "update_position", "halfsweep_done", "fullsweep", "SweepData", "DMRGParams", "dmrg_", "dmrg", "dmrg1", "dmrg2",
+           "update_position", "halfsweep_done", "fullsweep", "dynamic_fullsweep", "SweepData", "DMRGParams", "dmrg_", "dmrg", "dmrg1", "dmrg2",
            "CouplingModel", "TDVPEngine", "tdvpsweep", "sweepcount", "getenergy", "getentropy", "maxchi", "totalerror", "load", "so_path", "TnlError", "EXPORTED"]

@@ -113,7 +113,7 @@ GemmPlan::~GemmPlan() {
   if (ctx) { ctx->free(d_probs); ctx->free(d_tiles_big); ctx->free(d_tiles_small); }
 }
 TransformPlan::~TransformPlan() {
-  if (ctx) { ctx->free(d_blocks); ctx->free(d_contribs); }
+  if (ctx) { ctx->free(d_blocks); ctx->free(d_contribs); ctx->free(d_flats); }
 }
 
 // --------------------------------------------------------------------------------------- Tensor
@@ -395,9 +395,33 @@ std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const 
   }
   plan->ncols = col;
   plan->bytes = 8.0 * ((double)X.logical_elems() + (double)Y.logical_elems());
-  plan->d_blocks = Y.ctx->upload(plan->blocks);
-  plan->d_contribs = Y.ctx->upload(plan->contribs);
+  finalize_transform_plan(*plan, W != nullptr);
   return plan;
+}
+
+void finalize_transform_plan(TransformPlan& p, bool has_w) {
+  p.flats.clear();
+  for (XfBlock& b : p.blocks) {
+    b.fbeg = (int)p.flats.size();
+    for (int c = b.cbeg; c < b.cbeg + b.cnum; c++) {
+      const XfContrib& cc = p.contribs[c];
+      const int Ka = cc.kd0 * cc.kd1;
+      for (int a1 = 0; a1 < cc.kd1; a1++)
+        for (int a0 = 0; a0 < cc.kd0; a0++) {
+          XfFlat f{};
+          f.xoff = cc.xoff + a0 * cc.ks0 + a1 * cc.ks1;
+          for (int k = 0; k < MAXP; k++) f.xps[k] = cc.xps[k];
+          f.woff = cc.woff + a0 + (int64_t)cc.kd0 * a1;
+          f.wst = Ka;
+          p.flats.push_back(f);
+        }
+    }
+    b.fnum = (int)p.flats.size() - b.fbeg;
+  }
+  p.pure_copy = !has_w;
+  p.d_blocks = p.ctx->upload(p.blocks);
+  p.d_contribs = p.ctx->upload(p.contribs);
+  p.d_flats = p.ctx->upload(p.flats);
 }
 
 std::unique_ptr<TransformPlan> plan_scatter(const Tensor& X, Tensor& Y, const SliceMap& slice) {
@@ -438,8 +462,7 @@ std::unique_ptr<TransformPlan> plan_scatter(const Tensor& X, Tensor& Y, const Sl
   }
   plan->ncols = col;
   plan->bytes = 16.0 * (double)X.logical_elems();
-  plan->d_blocks = Y.ctx->upload(plan->blocks);
-  plan->d_contribs = Y.ctx->upload(plan->contribs);
+  finalize_transform_plan(*plan, false);
   return plan;
 }
 

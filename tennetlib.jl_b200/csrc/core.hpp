@@ -166,12 +166,23 @@ struct XfBlock {
   int I;                     // leading (stride-1) dim
   int cbeg, cnum;            // contribution range
   int64_t colstart;          // first global column of this block (columns = Na * prod(pd))
+  int fbeg, fnum;            // range in the flattened contribution list (one entry per contracted element)
+};
+// one contracted element (k0, k1) of one contribution: a column of X and the W row that multiplies it
+struct XfFlat {
+  int64_t xoff;              // X element offset of (i=0, this k, p=0)
+  int64_t xps[MAXP];
+  int64_t woff;              // W element offset of (this k, n=0)
+  int wst;                   // W stride between consecutive n (= Ka of the contribution)
 };
 struct TransformPlan {
   std::vector<XfBlock> blocks;
   std::vector<XfContrib> contribs;
+  std::vector<XfFlat> flats;
   XfBlock* d_blocks = nullptr;
   XfContrib* d_contribs = nullptr;
+  XfFlat* d_flats = nullptr;
+  bool pure_copy = false;    // no W: every output column is a copy of one input column (or zero)
   int64_t ncols = 0;
   double bytes = 0;          // algorithmic bytes moved (read X once + write Y once)
   double flops = 0;
@@ -292,6 +303,7 @@ std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const 
 // inverse of a sliced transform: every block of the LOCAL tensor X is written into the sub-range of the matching
 // block of the full tensor Y (index `slice.ypos`, Y sector slice.orig[k], elements from slice.start[k])
 std::unique_ptr<TransformPlan> plan_scatter(const Tensor& X, Tensor& Y, const SliceMap& slice);
+void finalize_transform_plan(TransformPlan& p, bool has_w);   // flattens the contributions and uploads the plan
 void run_transform(Ctx* ctx, TransformPlan& p, const double* X, double* Y, const double* W);
 
 // flat vector kernels on padded buffers of equal layout

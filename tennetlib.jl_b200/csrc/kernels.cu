@@ -642,12 +642,148 @@ transform_kernel(const XfBlock* __restrict__ blocks, int nblocks, const XfContri
   }
 }
 
+// v2: the contributions are flattened to one entry per contracted element, and the X columns of FB entries
+// (FB x 4 x 32 doubles per warp) are requested before the first FMA consumes one -- 4x the bytes in flight of the
+// first kernel, which was latency bound at ~50 % of the HBM roofline (profiles/r01b_ncu_hbm.md).
+constexpr int XF_FB = 4;
+__global__ void __launch_bounds__(256)
+transform_kernel_v2(const XfBlock* __restrict__ blocks, int nblocks, const XfFlat* __restrict__ flats,
+                    const double* __restrict__ X, double* __restrict__ Y, const double* __restrict__ W, int64_t ncols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; col < ncols; col += nwarps) {
+    int lo = 0, hi = nblocks - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (blocks[mid].colstart <= col) lo = mid; else hi = mid - 1;
+    }
+    const XfBlock& b = blocks[lo];
+    int64_t t = col - b.colstart;
+    int64_t ybase = b.yoff;
+    int pidx[MAXP];
+#pragma unroll
+    for (int k = 0; k < MAXP; k++) {
+      pidx[k] = (int)(t % b.pd[k]); t /= b.pd[k];
+      ybase += pidx[k] * b.yps[k];
+    }
+    const int I = b.I, Na = b.nd0 * b.nd1;
+    const int fend = b.fbeg + b.fnum;
+    for (int nc = 0; nc < Na; nc += 4) {
+      const int nn = min(4, Na - nc);
+      for (int i0 = 0; i0 < I; i0 += 128) {
+        double acc[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; n++)
+#pragma unroll
+          for (int u = 0; u < 4; u++) acc[n][u] = 0.0;
+        for (int f0 = b.fbeg; f0 < fend; f0 += XF_FB) {
+          double x[XF_FB][4];
+          const double* wp[XF_FB];
+          int wst[XF_FB];
+#pragma unroll
+          for (int k = 0; k < XF_FB; k++) {
+            const bool on = f0 + k < fend;
+            const XfFlat& ff = flats[on ? f0 + k : f0];
+            int64_t xb = ff.xoff;
+#pragma unroll
+            for (int q = 0; q < MAXP; q++) xb += pidx[q] * ff.xps[q];
+            const double* xp = X + xb;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int i = i0 + lane + 32 * u;
+              x[k][u] = (on && i < I) ? xp[i] : 0.0;
+            }
+            wp[k] = on ? W + ff.woff + (int64_t)ff.wst * nc : nullptr;
+            wst[k] = ff.wst;
+          }
+#pragma unroll
+          for (int k = 0; k < XF_FB; k++) {
+            if (wp[k]) {
+#pragma unroll
+              for (int n = 0; n < 4; n++) {
+                if (n < nn) {
+                  const double w = wp[k][(int64_t)wst[k] * n];
+#pragma unroll
+                  for (int u = 0; u < 4; u++) acc[n][u] = fma(x[k][u], w, acc[n][u]);
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int n = 0; n < 4; n++) {
+          if (n < nn) {
+            const int na = nc + n;
+            double* yp = Y + ybase + (na % b.nd0) * b.yns[0] + (na / b.nd0) * b.yns[1];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int i = i0 + lane + 32 * u;
+              if (i < I) yp[i] = acc[n][u];
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// pure relayout (no W): every output column is one input column (or zero); 8 x 32 doubles in flight per warp
+__global__ void __launch_bounds__(256)
+relayout_kernel(const XfBlock* __restrict__ blocks, int nblocks, const XfFlat* __restrict__ flats,
+                const double* __restrict__ X, double* __restrict__ Y, int64_t ncols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; col < ncols; col += nwarps) {
+    int lo = 0, hi = nblocks - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (blocks[mid].colstart <= col) lo = mid; else hi = mid - 1;
+    }
+    const XfBlock& b = blocks[lo];
+    int64_t t = col - b.colstart;
+    int64_t ybase = b.yoff;
+    int64_t xb = 0;
+    const bool has = b.fnum > 0;
+    const XfFlat& ff = flats[has ? b.fbeg : 0];
+    if (has) xb = ff.xoff;
+#pragma unroll
+    for (int k = 0; k < MAXP; k++) {
+      const int pi = (int)(t % b.pd[k]); t /= b.pd[k];
+      ybase += pi * b.yps[k];
+      if (has) xb += pi * ff.xps[k];
+    }
+    const int I = b.I;
+    const double* xp = X + xb;
+    double* yp = Y + ybase;
+    for (int i0 = 0; i0 < I; i0 += 256) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = i0 + lane + 32 * u;
+        v[u] = (has && i < I) ? xp[i] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = i0 + lane + 32 * u;
+        if (i < I) yp[i] = v[u];
+      }
+    }
+  }
+}
+
 void run_transform(Ctx* ctx, TransformPlan& p, const double* X, double* Y, const double* W) {
   if (p.ncols == 0) return;
   Ctx::Scope prof_scope(ctx, 1);
   int64_t warps_needed = p.ncols;
   int64_t blocks = std::min<int64_t>((warps_needed + 7) / 8, (int64_t)ctx->num_sms * 32);
-  transform_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_contribs, X, Y, W, p.ncols);
+  static const int variant = [] { const char* e = getenv("TNL_XF"); return e ? atoi(e) : 2; }();
+  if (variant < 2 || p.flats.empty()) {
+    transform_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_contribs, X, Y, W, p.ncols);
+  } else if (!W) {
+    relayout_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_flats, X, Y, p.ncols);
+  } else {
+    transform_kernel_v2<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_flats, X, Y, W, p.ncols);
+  }
   CUDA_OK(cudaGetLastError());
   ctx->cnt.launches++;
   ctx->cnt.xf_bytes += p.bytes;

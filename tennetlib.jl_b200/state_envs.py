@@ -22,6 +22,7 @@ class StateEnvs:
         self.ctx = ctx
         self.profile = False           # when True, per-phase device times are accumulated in phase_ms
         self.phase_ms = {}
+        self.phase_log = []            # (phase, ms) in call order: shows one-off hiccups that an average hides
         self.profile_kernels = False   # additionally split the device time of each phase by kernel class
         self.phase_kernel_ms = {}
         self.gemm_prof = dict(total_ms=0.0, launches=0, flops=0.0, max_tflops=0.0)
@@ -59,7 +60,10 @@ class StateEnvs:
         for j, A in enumerate(psi):
             dt = (A.copy() if copy else A) if isinstance(A, DeviceTensor) else DeviceTensor.from_host(ctx, A, nrow=2)
             check(ctx.lib.tnl_env_set_state(self.h, j + 1, dt.h), ctx.h)
-        # StateEnvs(psi, H, Ms; weight) (state_envs.jl:86-103): penalised states for excited-state DMRG
+        # StateEnvs(psi, H, Ms; weight) (state_envs.jl:86-150): penalised states for excited-state DMRG; the same
+        # rank-1 terms on top of an MPO (ProjMPO_MPS2), a sum of MPOs (ProjMPOSum_MPS) or a CouplingModel
+        # (ProjCouplingModel_MPS)
+        self.has_penalty = bool(Ms)
         if Ms:
             if weight <= 0.0:
                 raise ValueError(f"`weight` parameter should be > 0.0 (value passed was `weight={weight}`)")
@@ -96,7 +100,9 @@ class StateEnvs:
 
             def __exit__(self_p, *exc):
                 if env.profile and exc[0] is None:
-                    env.phase_ms[name] = env.phase_ms.get(name, 0.0) + env.ctx.timer_stop()
+                    dt = env.ctx.timer_stop()
+                    env.phase_ms[name] = env.phase_ms.get(name, 0.0) + dt
+                    env.phase_log.append((name, dt))
                     if env.profile_kernels:          # device time by kernel class inside this phase
                         pr = env.ctx.profile_read()
                         acc = env.phase_kernel_ms.setdefault(name, {})
@@ -165,6 +171,9 @@ class StateEnvs:
     def getpsi(self) -> List[HostTensor]:
         """getpsi (state_envs.jl:36): host copy of the MPS."""
         return [self.site_tensor(j).to_host() for j in range(1, self.N + 1)]
+
+    def linkdim(self, bond: int) -> int:
+        return self.site_tensor(bond).inds[2].dim
 
     def linkdims(self) -> List[int]:
         return [self.site_tensor(j).inds[2].dim for j in range(1, self.N)]

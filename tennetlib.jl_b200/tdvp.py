@@ -3,7 +3,7 @@ from __future__ import annotations
 
 from .solver import exp_solver
 from .state_envs import StateEnvs
-from .sweep import SweepData, fullsweep
+from .sweep import SweepData, dynamic_fullsweep, fullsweep
 
 
 class TDVPEngine:
@@ -40,13 +40,14 @@ def totalerror(engine: TDVPEngine) -> float:
 
 def tdvpsweep(engine: TDVPEngine, time_step, nsite=2, solver=exp_solver, **kwargs):
     """`tdvpsweep!`: psi' = exp(time_step * H) psi by one second-order sweep (half a step left-to-right, half a
-    step right-to-left, backward evolutions of the centre in between).  `nsite="dynamic"` needs the Global Subspace
-    Expansion (`krylov_extend!`), which is not built."""
+    step right-to-left, backward evolutions of the centre in between).  `nsite="dynamic"` mixes one- and two-site
+    updates bond by bond (`dynamic_fullsweep!`); on a single MPO it would start with the Global Subspace Expansion
+    (`krylov_extend!`), which is not built and raises."""
     if solver is not exp_solver:
         raise RuntimeError("`tdvpsweep!()`: `solver` must be `exp_solver` !!")
     if nsite == "dynamic":
-        raise NotImplementedError('`tdvpsweep!(nsite="dynamic")` needs `krylov_extend!` (not built); use nsite=2 or 1')
-    if nsite in (1, 2):
+        dynamic_fullsweep(engine.sysenv, solver, engine.swdata, time_step=0.5 * time_step, reverse_step=True, **kwargs)
+    elif nsite in (1, 2):
         if kwargs.pop("extendat", None) is not None:
             raise RuntimeError("`tdvpsweep!()`: `extendat` must be `nothing` for `nsite == 2` or `nsite == 1`. \n"
                                " Manually call `krylov_extend!(engine.sysenv; kwargs...)` for global subspace expansion.")

@@ -624,3 +624,29 @@ def test_coupling_model_noise_term_and_tdvp(ctx):
         T.tdvpsweep(eng_d, -0.05, ns, maxdim=16, cutoff=1e-12, outputlevel=0)
     assert eng_d.swdata.maxchi == eng_o.swdata.maxchi
     assert np.allclose(eng_d.swdata.energy, eng_o.swdata.energy, rtol=1e-10, atol=0)
+
+
+def test_dynamic_tdvp_and_penalty_on_coupling_model(ctx):
+    """`tdvpsweep!(nsite="dynamic")` (dynamic_fullsweep!, src/mps/sweep.jl:257-382) and excited-state DMRG with
+    StateEnvs(psi, H::CouplingModel, Ms; weight) (ProjCouplingModel_MPS) against the oracle."""
+    T, ob, od, ok, om, op = _imports()
+    from oracle import couplingmodel as oc
+    sites = om.siteinds("S=1/2", 8)
+    M = oc.heisenberg_coupling_model(sites, merge=True)
+    psi0 = od.MPS(om.neel_mps(sites))
+    eng_o, eng_d = od.TDVPEngine(psi0, M), T.TDVPEngine(ctx, psi0.t, M)
+    for _ in range(6):
+        od.tdvpsweep(eng_o, -0.1, "dynamic", maxdim=6, cutoff=1e-12, extendat=5)
+        T.tdvpsweep(eng_d, -0.1, "dynamic", maxdim=6, cutoff=1e-12, extendat=5, outputlevel=0)
+    assert eng_d.swdata.maxchi == eng_o.swdata.maxchi
+    assert np.allclose(eng_d.swdata.energy, eng_o.swdata.energy, rtol=1e-10, atol=0)
+    with pytest.raises(NotImplementedError):          # single MPO: needs krylov_extend!
+        T.tdvpsweep(T.TDVPEngine(ctx, psi0.t, om.heisenberg_mpo(sites)), -0.1, "dynamic", maxdim=6, outputlevel=0)
+    prm = dict(maxdim=[16, 32], nsweeps=[3, 3], cutoff=1e-14, noise=[1e-3, 0.0])
+    E0o, p0o, _ = od.dmrg2(psi0, M, od.DMRGParams(**prm))
+    E1o, _, _ = od.dmrg2(psi0, M, od.DMRGParams(**prm), Ms=[p0o], weight=10.0)
+    E0d, env0, _ = T.dmrg2(ctx, psi0.t, M, T.DMRGParams(**prm), outputlevel=0)
+    E1d, _, _ = T.dmrg2(ctx, psi0.t, M, T.DMRGParams(**prm), Ms=[env0.getpsi()], weight=10.0, outputlevel=0)
+    assert abs(E0d - E0o) < 1e-10 * abs(E0o)
+    assert abs(E1d - E1o) < 1e-8 * abs(E1o)
+    assert abs(E1d - (-2.9822404877)) < 1e-6          # ED: first excited state of S=1/2 N=8 in the Sz=0 sector
