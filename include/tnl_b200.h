@@ -76,6 +76,16 @@ int tnl_comm_bench(tnl_ctx_t ctx, int64_t n, int32_t reps, int32_t kind, double*
 int tnl_tensor_import(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t* inds, int64_t nblocks,
                       const int32_t* coords, const int64_t* offsets, const double* data, int32_t nrow,
                       tnl_tensor_t* out);
+/* ComplexF64 tensors (TDVP in real time, SURVEY.md section 8 rows a1/a5/a7 "C128"): the host hands over / receives
+ * NDTensors' interleaved (re, im) storage (offsets count complex elements); on the device the tensor is PLANAR --
+ * two real planes in the same charge-fused layout -- so every contraction stays on the FP64 DMMA kernels.
+ * tnl_tensor_export writes 2 * nelem doubles for a complex tensor.  Site operators (MPO / CouplingModel tensors)
+ * are real.  Not built for complex tensors: eig_solver, QR gauge moves, the noise term, penalties, sharding. */
+int tnl_tensor_import_c128(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t* inds, int64_t nblocks,
+                           const int32_t* coords, const int64_t* offsets, const double* data_re_im, int32_t nrow,
+                           tnl_tensor_t* out);
+int tnl_tensor_is_complex(tnl_tensor_t t, int32_t* out);
+int tnl_tensor_promote(tnl_tensor_t t); /* real -> complex with zero imaginary part, in place */
 int tnl_tensor_create(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t* inds, int32_t nrow,
                       tnl_tensor_t* out); /* all symmetry-allowed blocks, zero */
 int tnl_tensor_free(tnl_tensor_t t);
@@ -88,7 +98,8 @@ int tnl_tensor_export(tnl_tensor_t t, int32_t* coords, int64_t* offsets, double*
 int tnl_tensor_fill_random(tnl_tensor_t t, uint64_t seed); /* uniform [-1,1), counter based */
 
 /* ---- Krylov vector interface (VectorInterface inner / norm / scale!! / add!! on ITensors) ---- */
-int tnl_vec_dot(tnl_tensor_t x, tnl_tensor_t y, double* out);
+int tnl_vec_dot(tnl_tensor_t x, tnl_tensor_t y, double* out); /* complex tensors: the real part */
+int tnl_vec_dot_c(tnl_tensor_t x, tnl_tensor_t y, double* re, double* im); /* <x,y> = sum conj(x) y */
 int tnl_vec_norm(tnl_tensor_t x, double* out);
 int tnl_vec_scale(tnl_tensor_t x, double a);
 int tnl_vec_axpy(tnl_tensor_t y, tnl_tensor_t x, double a); /* y += a*x */
@@ -135,8 +146,8 @@ int tnl_eigsolve_lanczos(tnl_env_t env, tnl_tensor_t phi, double tol, int32_t kr
                          int32_t eager, double* eval, int32_t* converged, int32_t* numops, int32_t* numiter,
                          double* normres);
 /* exp_solver: src/base/solver.jl:66-88 -> KrylovKit.exponentiate(env, t, phi; Lanczos): phi <- exp(t * H_eff) phi in
- * place, t = t_re + i t_im.  This build evolves real tensors only: t_im must be 0 (imaginary-time TDVP); a complex
- * step returns status 2.  *err = accumulated error estimate (info.normres). */
+ * place, t = t_re + i t_im.  With t_im != 0 (real-time evolution, time_step = -im*dt) or complex environments a
+ * real phi is promoted to a complex tensor first.  *err = accumulated error estimate (info.normres). */
 int tnl_exponentiate(tnl_env_t env, tnl_tensor_t phi, double t_re, double t_im, double tol, int32_t krylovdim,
                      int32_t maxiter, int32_t eager, int32_t* converged, int32_t* numops, int32_t* numiter, double* err);
 /* real(scalar(dag(phi) * PH(phi))) : src/mps/update_site.jl:51-57 */

@@ -42,6 +42,11 @@ _SIGS = {
     "tnl_profile_read": [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "tnl_profile_categories": [_P, C.POINTER(C.c_double)],
     "tnl_tensor_import": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int64, _P, _P, _P, C.c_int32, C.POINTER(_P)],
+    "tnl_tensor_import_c128": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int64, _P, _P, _P, C.c_int32,
+                               C.POINTER(_P)],
+    "tnl_tensor_is_complex": [_P, C.POINTER(C.c_int32)],
+    "tnl_tensor_promote": [_P],
+    "tnl_vec_dot_c": [_P, _P, C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "tnl_tensor_create": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int32, C.POINTER(_P)],
     "tnl_tensor_free": [_P],
     "tnl_tensor_copy": [_P, C.POINTER(_P)],

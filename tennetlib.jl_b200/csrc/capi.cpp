@@ -212,6 +212,29 @@ int tnl_tensor_import(tnl_ctx_t c, int32_t rank, int32_t nq, const tnl_index_t* 
     *out = new tnl_tensor_s{import_tensor(&c->ctx, hb, nrow)};
   });
 }
+int tnl_tensor_import_c128(tnl_ctx_t c, int32_t rank, int32_t nq, const tnl_index_t* inds, int64_t nblocks,
+                           const int32_t* coords, const int64_t* offsets, const double* data_re_im, int32_t nrow,
+                           tnl_tensor_t* out) {
+  return guard(&c->ctx, [&] {
+    HostBlocks hb = make_host(rank, nq, inds, nblocks, coords, offsets, data_re_im);
+    hb.cplx = true;
+    *out = new tnl_tensor_s{import_tensor(&c->ctx, hb, nrow)};
+  });
+}
+int tnl_tensor_is_complex(tnl_tensor_t t, int32_t* out) {
+  return guard(t->t->ctx, [&] { *out = t->t->cplx ? 1 : 0; });
+}
+// real -> planar complex with a zero imaginary plane (no-op on complex tensors)
+static TensorP promoted(const TensorP& t) {
+  if (t->cplx) return t;
+  auto n = std::make_shared<Tensor>(t->ctx, t->inds, t->nrow, true, true);
+  vec_copy(t->ctx, n->d, t->d, t->nelem);
+  n->present = t->present;
+  return n;
+}
+int tnl_tensor_promote(tnl_tensor_t t) {
+  return guard(t->t->ctx, [&] { t->t = promoted(t->t); });
+}
 int tnl_tensor_create(tnl_ctx_t c, int32_t rank, int32_t nq, const tnl_index_t* inds, int32_t nrow, tnl_tensor_t* out) {
   return guard(&c->ctx, [&] {
     *out = new tnl_tensor_s{std::make_shared<Tensor>(&c->ctx, make_inds(rank, nq, inds), nrow)};
@@ -222,8 +245,8 @@ int tnl_tensor_free(tnl_tensor_t t) {
 }
 int tnl_tensor_copy(tnl_tensor_t t, tnl_tensor_t* out) {
   return guard(t->t->ctx, [&] {
-    auto n = std::make_shared<Tensor>(t->t->ctx, t->t->inds, t->t->nrow);
-    vec_copy(t->t->ctx, n->d, t->t->d, t->t->nelem);
+    auto n = std::make_shared<Tensor>(t->t->ctx, t->t->inds, t->t->nrow, true, t->t->cplx);
+    vec_copy(t->t->ctx, n->d, t->t->d, t->t->planes() * t->t->nelem);
     n->present = t->t->present;
     *out = new tnl_tensor_s{n};
   });
@@ -262,24 +285,60 @@ int tnl_tensor_export(tnl_tensor_t t, int32_t* coords, int64_t* offsets, double*
       offsets[b] = nat->blocks[b].off;
     }
     int64_t n = nat->logical_elems();
-    if (n) CUDA_OK(cudaMemcpyAsync(data, nat->d, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->sync();
+    if (!nat->cplx) {
+      if (n) CUDA_OK(cudaMemcpyAsync(data, nat->d, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->sync();
+    } else {
+      // complex tensors come back interleaved (re, im) like NDTensors ComplexF64 storage: 2 * nelem doubles
+      std::vector<double> re((size_t)n), im((size_t)n);
+      if (n) {
+        CUDA_OK(cudaMemcpyAsync(re.data(), nat->d, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_OK(cudaMemcpyAsync(im.data(), nat->im(), n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      ctx->sync();
+      for (int64_t e = 0; e < n; e++) { data[2 * e] = re[e]; data[2 * e + 1] = im[e]; }
+    }
   });
 }
 int tnl_tensor_fill_random(tnl_tensor_t t, uint64_t seed) {
-  return guard(t->t->ctx, [&] { fill_random(t->t->ctx, *t->t, seed); t->t->ctx->sync(); });
+  return guard(t->t->ctx, [&] {
+    fill_random(t->t->ctx, *t->t, seed);
+    if (t->t->cplx) {                          // second plane from an independent counter stream
+      Tensor v(t->t->ctx, t->t->inds, t->t->nrow, false);
+      v.d = t->t->im();
+      v.owns = false;
+      fill_random(t->t->ctx, v, seed ^ 0x5DEECE66Dull);
+    }
+    t->t->ctx->sync();
+  });
 }
 
 static void same_layout(const Tensor& a, const Tensor& b) {
-  TNL_CHECK(a.nelem == b.nelem && a.nrow == b.nrow && a.rank() == b.rank(), "vectors have different layouts");
+  TNL_CHECK(a.nelem == b.nelem && a.nrow == b.nrow && a.rank() == b.rank() && a.cplx == b.cplx,
+            "vectors have different layouts");
 }
 int tnl_vec_dot(tnl_tensor_t x, tnl_tensor_t y, double* out) {
   return guard(x->t->ctx, [&] {
     same_layout(*x->t, *y->t);
     Ctx* ctx = x->t->ctx;
-    vec_dot(ctx, x->t->d, y->t->d, x->t->nelem, 0);
+    vec_dot(ctx, x->t->d, y->t->d, x->t->planes() * x->t->nelem, 0);   // complex: the real part of <x, y>
     fetch_scalars(ctx, 1);
     *out = ctx->h_scalars[0];
+  });
+}
+int tnl_vec_dot_c(tnl_tensor_t x, tnl_tensor_t y, double* re, double* im) {
+  return guard(x->t->ctx, [&] {
+    same_layout(*x->t, *y->t);
+    Ctx* ctx = x->t->ctx;
+    if (x->t->cplx) {
+      vec_cdot(ctx, x->t->d, y->t->d, x->t->nelem, 0);
+      fetch_scalars(ctx, 2);
+      *re = ctx->h_scalars[0]; *im = ctx->h_scalars[1];
+    } else {
+      vec_dot(ctx, x->t->d, y->t->d, x->t->nelem, 0);
+      fetch_scalars(ctx, 1);
+      *re = ctx->h_scalars[0]; *im = 0.0;
+    }
   });
 }
 int tnl_vec_norm(tnl_tensor_t x, double* out) {
@@ -289,12 +348,12 @@ int tnl_vec_norm(tnl_tensor_t x, double* out) {
   return rc;
 }
 int tnl_vec_scale(tnl_tensor_t x, double a) {
-  return guard(x->t->ctx, [&] { vec_scale(x->t->ctx, x->t->d, x->t->nelem, a); });
+  return guard(x->t->ctx, [&] { vec_scale(x->t->ctx, x->t->d, x->t->planes() * x->t->nelem, a); });
 }
 int tnl_vec_axpy(tnl_tensor_t y, tnl_tensor_t x, double a) {
   return guard(x->t->ctx, [&] {
     same_layout(*x->t, *y->t);
-    vec_axpy(x->t->ctx, y->t->d, x->t->d, x->t->nelem, a);
+    vec_axpy(x->t->ctx, y->t->d, x->t->d, x->t->planes() * x->t->nelem, a);
   });
 }
 
@@ -369,7 +428,8 @@ int tnl_env_apply_flops(tnl_env_t e, double* flops) {
 int tnl_heff_apply(tnl_env_t e, tnl_tensor_t v, tnl_tensor_t* out) {
   return guard(e->env.ctx, [&] {
     TensorP vq = v->t->nrow == 1 ? v->t : relayout(e->env.ctx, *v->t, 1);
-    auto o = std::make_shared<Tensor>(e->env.ctx, vq->inds, 1);
+    if (e->env.complex_at_position()) vq = promoted(vq);       // complex environments: complex product
+    auto o = std::make_shared<Tensor>(e->env.ctx, vq->inds, 1, true, vq->cplx);
     e->env.apply(*vq, *o);
     e->env.ctx->sync();
     *out = new tnl_tensor_s{o};
@@ -387,6 +447,7 @@ int tnl_exponentiate(tnl_env_t e, tnl_tensor_t phi, double t_re, double t_im, do
                      int32_t maxiter, int32_t eager, int32_t* converged, int32_t* numops, int32_t* numiter, double* err) {
   return guard(e->env.ctx, [&] {
     if (phi->t->nrow != 1) phi->t = relayout(e->env.ctx, *phi->t, 1);
+    if (t_im != 0.0 || e->env.complex_at_position()) phi->t = promoted(phi->t);   // real-time step: ComplexF64 from here on
     ExpResult r = e->env.exponentiate(*phi->t, t_re, t_im, tol, krylovdim, maxiter, eager != 0);
     *converged = r.converged; *numops = r.numops; *numiter = r.numiter; *err = r.err;
   });
@@ -397,6 +458,7 @@ int tnl_env_absorb_bond(tnl_env_t e, int32_t pos, int32_t ortho_left, tnl_tensor
 int tnl_expectation(tnl_env_t e, tnl_tensor_t phi, double* out) {
   return guard(e->env.ctx, [&] {
     TensorP vq = phi->t->nrow == 1 ? phi->t : relayout(e->env.ctx, *phi->t, 1);
+    if (e->env.complex_at_position()) vq = promoted(vq);
     *out = e->env.expectation(*vq);
   });
 }

@@ -192,17 +192,17 @@ void build_layout(Tensor& t) {
   t.nelem = std::max<int64_t>(base, 2);
 }
 
-Tensor::Tensor(Ctx* c, std::vector<Index> ii, int nr, bool alloc) : ctx(c), inds(std::move(ii)), nrow(nr) {
+Tensor::Tensor(Ctx* c, std::vector<Index> ii, int nr, bool alloc, bool cx) : ctx(c), inds(std::move(ii)), nrow(nr), cplx(cx) {
   build_layout(*this);
   if (alloc) {
-    d = (double*)ctx->alloc(nelem * sizeof(double));
-    CUDA_OK(cudaMemsetAsync(d, 0, nelem * sizeof(double), ctx->stream));
+    d = (double*)ctx->alloc(planes() * nelem * sizeof(double));
+    CUDA_OK(cudaMemsetAsync(d, 0, planes() * nelem * sizeof(double), ctx->stream));
   }
 }
 Tensor::~Tensor() {
   if (d && ctx && owns) ctx->free(d);
 }
-void Tensor::zero() { CUDA_OK(cudaMemsetAsync(d, 0, nelem * sizeof(double), ctx->stream)); }
+void Tensor::zero() { CUDA_OK(cudaMemsetAsync(d, 0, planes() * nelem * sizeof(double), ctx->stream)); }
 
 // ------------------------------------------------------------------------------------ GEMM plan
 static bool combos_equal(const std::vector<Combo>& a, int na, const std::vector<Combo>& b, int nb) {

@@ -100,9 +100,15 @@ class Tensor {
   std::vector<uint8_t> present;                    // imported tensors: which blocks the host supplied (empty = all)
   double* d = nullptr;
   bool owns = true;                                // false: `d` points into a Ctx workspace slot
-  int64_t nelem = 0;                               // padded element count of the buffer
+  int64_t nelem = 0;                               // padded element count of the buffer (of ONE plane)
+  // ComplexF64 tensors are stored PLANAR: real plane at d, imaginary plane at d + nelem, both in the same
+  // charge-fused layout -- a complex contraction is four (two) launches of the real FP64 DMMA kernel, the
+  // site-operator transforms (real MPOs) run plane by plane, norms / real scalings see one flat buffer of 2*nelem
+  bool cplx = false;
+  double* im() const { return d + nelem; }
+  int64_t planes() const { return cplx ? 2 : 1; }
 
-  Tensor(Ctx* ctx, std::vector<Index> inds, int nrow, bool alloc = true);
+  Tensor(Ctx* ctx, std::vector<Index> inds, int nrow, bool alloc = true, bool cplx = false);
   ~Tensor();
   Tensor(const Tensor&) = delete;
   Tensor& operator=(const Tensor&) = delete;
@@ -277,7 +283,8 @@ void build_layout(Tensor& t);
 // bookkeeping changes.
 std::unique_ptr<GemmPlan> plan_gemm(const Tensor& A, bool transA, const Tensor& B, bool transB, Tensor& C,
                                     bool dagA = false, bool dagB = false);
-void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C);
+// C = alpha * op(A) op(B)  (accum: += ; alpha = +-1 and accumulate serve the planar complex products)
+void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C, double alpha = 1.0, bool accum = false);
 // ad-hoc problems (factorisation internals); builds tiles and uploads
 std::unique_ptr<GemmPlan> plan_gemm_raw(Ctx* ctx, bool transA, bool transB, const std::vector<GemmProblem>& probs);
 void gemm_selftest(Ctx* ctx, int M, int N, int K, bool ta, bool tb, int reps, bool verify, double* ms, double* maxerr);
@@ -314,6 +321,15 @@ void vec_scale(Ctx* ctx, double* y, int64_t n, double a);
 void vec_scale_to(Ctx* ctx, double* y, const double* x, int64_t n, double a);         // y = a*x
 void vec_copy(Ctx* ctx, double* y, const double* x, int64_t n);
 void vec_lincomb(Ctx* ctx, double* y, const double* const* xs, const double* coef, int k, int64_t n);
+// planar complex vectors [re | im] with planes of n doubles; scalar slots hold (re, im) pairs
+void vec_cdot(Ctx* ctx, const double* x, const double* y, int64_t n, int slot);      // d_scalars[slot, slot+1] = <x,y>
+void vec_caxpy_dev(Ctx* ctx, double* y, const double* x, int64_t n, int slot, double sign);
+void vec_caxpy(Ctx* ctx, double* y, const double* x, int64_t n, double ar, double ai);
+void vec_clincomb(Ctx* ctx, double* y, const double* const* xs, const double* cr, const double* ci, int k, int64_t n);
+void cgemm(Ctx* ctx, GemmPlan& p, const double* Ar, const double* Ai, bool conjA, const double* Br, const double* Bi,
+           bool conjB, double* Cr, double* Ci);
+void cgemm(Ctx* ctx, GemmPlan& p, const Tensor& A, bool conjA, const Tensor& B, bool conjB, Tensor& C);
+void run_transform_c(Ctx* ctx, TransformPlan& p, const Tensor& X, Tensor& Y, const double* W);
 void fetch_scalars(Ctx* ctx, int n);                                                  // d_scalars -> h_scalars, sync
 void fill_random(Ctx* ctx, Tensor& t, uint64_t seed);
 void scale_rows_or_cols(Ctx* ctx, double* A, int64_t ld, int64_t R, int64_t C, const double* s, bool rows);

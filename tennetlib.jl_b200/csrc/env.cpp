@@ -18,21 +18,23 @@
 namespace tnl {
 
 // ------------------------------------------------------------------------------ tensor helpers
-static TensorP mk(Ctx* ctx, std::vector<Index> inds, int nrow) { return std::make_shared<Tensor>(ctx, std::move(inds), nrow); }
+static TensorP mk(Ctx* ctx, std::vector<Index> inds, int nrow, bool cplx = false) {
+  return std::make_shared<Tensor>(ctx, std::move(inds), nrow, true, cplx);
+}
 
 static Index with_dir(Index ix, int dir) { ix.dir = dir; return ix; }
 
 // tensor whose buffer lives in a persistent workspace slot of the context (zero-filled: pads must be zero)
-static TensorP mk_ws(Ctx* ctx, std::vector<Index> inds, int nrow, int slot) {
-  auto t = std::make_shared<Tensor>(ctx, std::move(inds), nrow, false);
-  t->d = ctx->scratch(slot, (size_t)t->nelem, true);
+static TensorP mk_ws(Ctx* ctx, std::vector<Index> inds, int nrow, int slot, bool cplx = false) {
+  auto t = std::make_shared<Tensor>(ctx, std::move(inds), nrow, false, cplx);
+  t->d = ctx->scratch(slot, (size_t)(t->planes() * t->nelem), true);
   t->owns = false;
   return t;
 }
 
 TensorP import_tensor(Ctx* ctx, const HostBlocks& hb, int nrow) {
   TNL_CHECK(hb.rank >= 1 && hb.rank <= MAXR, "import: bad rank");
-  auto Y = mk(ctx, hb.inds, nrow);
+  auto Y = mk(ctx, hb.inds, nrow, hb.cplx);
   Tensor X(ctx, hb.inds, hb.rank, false);
   X.blocks.clear();
   X.lut.clear();
@@ -54,11 +56,22 @@ TensorP import_tensor(Ctx* ctx, const HostBlocks& hb, int nrow) {
     total = std::max(total, b.off + st);
   }
   double* tmp = (double*)ctx->alloc(std::max<int64_t>(total, 1) * sizeof(double));
-  if (total) CUDA_OK(cudaMemcpyAsync(tmp, hb.data, total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   std::vector<int> xmap(hb.rank);
   std::iota(xmap.begin(), xmap.end(), 0);
   auto plan = plan_transform(X, *Y, xmap, nullptr, {});
-  run_transform(ctx, *plan, tmp, Y->d, nullptr);
+  if (hb.cplx) {
+    // host data is interleaved ComplexF64 (NDTensors layout); the device keeps two planes
+    std::vector<double> plane((size_t)std::max<int64_t>(total, 1));
+    for (int pl = 0; pl < 2; pl++) {
+      for (int64_t e = 0; e < total; e++) plane[e] = hb.data[2 * e + pl];
+      if (total) CUDA_OK(cudaMemcpyAsync(tmp, plane.data(), total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      run_transform(ctx, *plan, tmp, pl == 0 ? Y->d : Y->im(), nullptr);
+      ctx->sync();
+    }
+  } else {
+    if (total) CUDA_OK(cudaMemcpyAsync(tmp, hb.data, total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    run_transform(ctx, *plan, tmp, Y->d, nullptr);
+  }
   Y->present.resize(Y->blocks.size());
   for (size_t i = 0; i < Y->blocks.size(); i++) Y->present[i] = X.find(Y->blocks[i].c) >= 0;
   ctx->sync();
@@ -67,11 +80,11 @@ TensorP import_tensor(Ctx* ctx, const HostBlocks& hb, int nrow) {
 }
 
 TensorP relayout(Ctx* ctx, const Tensor& t, int nrow) {
-  auto Y = mk(ctx, t.inds, nrow);
+  auto Y = mk(ctx, t.inds, nrow, t.cplx);
   std::vector<int> xmap(t.rank());
   std::iota(xmap.begin(), xmap.end(), 0);
   auto plan = plan_transform(t, *Y, xmap, nullptr, {});
-  run_transform(ctx, *plan, t.d, Y->d, nullptr);
+  run_transform_c(ctx, *plan, t, *Y, nullptr);
   ctx->sync();   // the plan's device arrays die with `plan`
   return Y;
 }
@@ -79,13 +92,13 @@ TensorP to_natural(Ctx* ctx, const Tensor& t) { return relayout(ctx, t, t.rank()
 
 // relayout into a persistent workspace slot (transient result)
 static TensorP relayout_ws(Ctx* ctx, const Tensor& t, int nrow, int slot) {
-  auto Y = std::make_shared<Tensor>(ctx, t.inds, nrow, false);
-  Y->d = ctx->scratch(slot, (size_t)Y->nelem, true);
+  auto Y = std::make_shared<Tensor>(ctx, t.inds, nrow, false, t.cplx);
+  Y->d = ctx->scratch(slot, (size_t)(Y->planes() * Y->nelem), true);
   Y->owns = false;
   std::vector<int> xmap(t.rank());
   std::iota(xmap.begin(), xmap.end(), 0);
   auto plan = plan_transform(t, *Y, xmap, nullptr, {});
-  run_transform(ctx, *plan, t.d, Y->d, nullptr);
+  run_transform_c(ctx, *plan, t, *Y, nullptr);
   ctx->sync();
   return Y;
 }
@@ -214,7 +227,7 @@ bool is_trivial_link(const Index& ix) { return ix.nsect() == 1 && ix.dims[0] == 
 static TensorP view_with_trivial(Ctx* ctx, const Tensor& src, int at, int nrow, const Index& w0, const double* data) {
   std::vector<Index> inds = src.inds;
   inds.insert(inds.begin() + at, w0);
-  auto v = std::make_shared<Tensor>(ctx, inds, nrow, false);
+  auto v = std::make_shared<Tensor>(ctx, inds, nrow, false, src.cplx);
   TNL_CHECK(v->nelem == src.nelem && v->blocks.size() == src.blocks.size(), "trivial-link view changed the layout");
   for (size_t i = 0; i < v->blocks.size(); i++)
     TNL_CHECK(v->blocks[i].off == src.blocks[i].off, "trivial-link view changed the block offsets");
@@ -234,20 +247,20 @@ TensorP Env::step_left(const Tensor* L, const TensorP& Asite, const Tensor& W) {
   ctx->slot_epoch++;
   TensorP X1;
   if (L) {
-    X1 = mk_ws(ctx, {L->inds[0], L->inds[1], Aq->inds[1], Aq->inds[2]}, 2, Ctx::SLOT_T1);
+    X1 = mk_ws(ctx, {L->inds[0], L->inds[1], Aq->inds[1], Aq->inds[2]}, 2, Ctx::SLOT_T1, L->cplx || Aq->cplx);
     auto g1 = plan_gemm(*L, false, *Aq, false, *X1);
-    run_gemm(ctx, *g1, L->d, Aq->d, X1->d);
+    cgemm(ctx, *g1, *L, false, *Aq, false, *X1);
   } else {
     TNL_CHECK(is_trivial_link(W.inds[0]), "a term that starts here must have a trivial left link");
     X1 = view_with_trivial(ctx, *Aq, 1, 2, trivial_like(W.inds[0], -W.inds[0].dir), Aq->d);
   }
-  auto Y1 = mk_ws(ctx, {X1->inds[0], W.inds[2], W.inds[3], X1->inds[3]}, 2, Ctx::SLOT_T2);
+  auto Y1 = mk_ws(ctx, {X1->inds[0], W.inds[2], W.inds[3], X1->inds[3]}, 2, Ctx::SLOT_T2, X1->cplx);
   auto x1 = plan_transform(*X1, *Y1, {0, -1, -1, 3}, &W, {1, 2});
-  run_transform(ctx, *x1, X1->d, Y1->d, W.d);
+  run_transform_c(ctx, *x1, *X1, *Y1, W.d);
   const Index& r = As->inds[2];
-  auto Ln = mk_ws(ctx, {with_dir(r, -r.dir), Y1->inds[2], Y1->inds[3]}, 1, Ctx::SLOT_P);
+  auto Ln = mk_ws(ctx, {with_dir(r, -r.dir), Y1->inds[2], Y1->inds[3]}, 1, Ctx::SLOT_P, Y1->cplx || As->cplx);
   auto g2 = plan_gemm(*As, true, *Y1, false, *Ln, /*dagA=*/true);
-  run_gemm(ctx, *g2, As->d, Y1->d, Ln->d);
+  cgemm(ctx, *g2, *As, /*conj: the bra*/true, *Y1, false, *Ln);
   ctx->sync();
   return relayout(ctx, *Ln, 2);
 }
@@ -260,23 +273,32 @@ TensorP Env::step_right(const Tensor* R, const TensorP& Asite, const Tensor& W) 
   const Index &l = As->inds[0], &s = As->inds[1], &r = As->inds[2];
   ap.reset();
   ctx->slot_epoch++;
-  TensorP Z;
+  TensorP Z, conj_keep;
   if (R) {
-    Z = mk_ws(ctx, {with_dir(l, -l.dir), with_dir(s, -s.dir), R->inds[1], R->inds[2]}, 2, Ctx::SLOT_T1);
+    Z = mk_ws(ctx, {with_dir(l, -l.dir), with_dir(s, -s.dir), R->inds[1], R->inds[2]}, 2, Ctx::SLOT_T1, As->cplx || R->cplx);
     auto g1 = plan_gemm(*As, false, *R, false, *Z, /*dagA=*/true);
-    run_gemm(ctx, *g1, As->d, R->d, Z->d);
+    cgemm(ctx, *g1, *As, /*conj: the bra*/true, *R, false, *Z);
   } else {
     TNL_CHECK(is_trivial_link(W.inds[1]), "a term that ends here must have a trivial right link");
-    // dag(A) has the same data and block coordinates as A; the transform below matches blocks by coordinates
-    Z = view_with_trivial(ctx, *As, 2, 2, trivial_like(W.inds[1], -W.inds[1].dir), As->d);
+    // dag(A) has the same block coordinates as A; the transform below matches blocks by coordinates.  A complex
+    // A needs its conjugate here: a copy with the imaginary plane negated
+    if (As->cplx) {
+      TensorP Ac = mk(ctx, As->inds, 2, true);
+      vec_copy(ctx, Ac->d, As->d, As->nelem);
+      vec_scale_to(ctx, Ac->im(), As->im(), As->nelem, -1.0);
+      conj_keep = Ac;
+      Z = view_with_trivial(ctx, *Ac, 2, 2, trivial_like(W.inds[1], -W.inds[1].dir), Ac->d);
+    } else {
+      Z = view_with_trivial(ctx, *As, 2, 2, trivial_like(W.inds[1], -W.inds[1].dir), As->d);
+    }
   }
   const Index zr = R ? Z->inds[3] : with_dir(r, -r.dir);
-  auto Z2 = mk_ws(ctx, {with_dir(l, -l.dir), W.inds[2], W.inds[3], zr}, 2, Ctx::SLOT_T2);
+  auto Z2 = mk_ws(ctx, {with_dir(l, -l.dir), W.inds[2], W.inds[3], zr}, 2, Ctx::SLOT_T2, Z->cplx);
   auto x1 = plan_transform(*Z, *Z2, {0, -1, -1, 3}, &W, {1, 2});
-  run_transform(ctx, *x1, Z->d, Z2->d, W.d);
-  auto Rn = mk_ws(ctx, {Z2->inds[0], Z2->inds[1], Aq->inds[0]}, 2, Ctx::SLOT_P);
+  run_transform_c(ctx, *x1, *Z, *Z2, W.d);
+  auto Rn = mk_ws(ctx, {Z2->inds[0], Z2->inds[1], Aq->inds[0]}, 2, Ctx::SLOT_P, Z2->cplx || Aq->cplx);
   auto g2 = plan_gemm(*Z2, false, *Aq, true, *Rn);
-  run_gemm(ctx, *g2, Z2->d, Aq->d, Rn->d);
+  cgemm(ctx, *g2, *Z2, false, *Aq, false, *Rn);
   ctx->sync();
   return relayout(ctx, *Rn, 1);
 }
@@ -340,6 +362,7 @@ void Env::add_penalty(const std::vector<TensorP>& M, double w) {
 
 void Env::position_penalty(Penalty& p, int pos) {
   if (p.dead) return;
+  for (auto& a : A) TNL_CHECK(!a || !a->cplx, "excited-state penalties on complex states are not built");
   if (!p.Ledge) {
     const Index &a0 = A[0]->inds[0], &m0 = p.M[0]->inds[0], &aN = A[N - 1]->inds[2], &mN = p.M[N - 1]->inds[2];
     p.Ledge = mk(ctx, {with_dir(a0, -a0.dir), with_dir(m0, m0.dir)}, 1);
@@ -452,9 +475,9 @@ TensorP Env::make_phi(int pos) {
   TensorP A2 = as_nrow(ctx, A[pos], 1);
   ap.reset();
   ctx->slot_epoch++;
-  auto S = mk_ws(ctx, {A1->inds[0], A1->inds[1], A2->inds[1], A2->inds[2]}, 2, Ctx::SLOT_T3);
+  auto S = mk_ws(ctx, {A1->inds[0], A1->inds[1], A2->inds[1], A2->inds[2]}, 2, Ctx::SLOT_T3, A1->cplx || A2->cplx);
   auto g = plan_gemm(*A1, false, *A2, false, *S);
-  run_gemm(ctx, *g, A1->d, A2->d, S->d);
+  cgemm(ctx, *g, *A1, false, *A2, false, *S);
   ctx->sync();
   return relayout(ctx, *S, 1);
 }
@@ -482,6 +505,7 @@ struct Env::ApplyPlan {
   int64_t nelem;
   double flops;
   uint64_t epoch = 0;                // ctx->slot_epoch when the plan was built (workspace pointers valid)
+  bool cplx = false;                 // planar complex vectors: plane distance = nelem
 };
 
 void Env::build_apply_plan(const Tensor& vfull) {
@@ -504,6 +528,9 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
   p->nsite = nsite;
   p->L = Lp;
   p->R = Rp;
+  const bool cp = v.cplx;
+  p->cplx = cp;
+  TNL_CHECK(cp || !((Lp && Lp->cplx) || (Rp && Rp->cplx)), "complex environments need a complex vector (promote it first)");
   TNL_CHECK(p->L || p->R || nsite > 0, "a zero-site term needs an environment");
   TNL_CHECK(v.nrow == 1, "Krylov vectors use the [l | rest] layout");
   // link carried by the running tensor before the first / after the last site operator when L / R is absent
@@ -513,7 +540,7 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
     p->W1 = W1p;
     p->W2 = W2p;
     const Tensor* vin = &v;
-    if (ctx->world > 1 && allow_shard && p->L && p->R) {
+    if (ctx->world > 1 && allow_shard && p->L && p->R && !cp) {
       // Sharded apply: every rank owns a contiguous share of each sector of the right
       // link r.  It contracts L with its slice of v, carries the slice through the site operators and contracts
       // with its slice of R over (w, r_local): a partial H_eff v of full size, summed by one NCCL all-reduce.
@@ -562,23 +589,23 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
     const Index lout = p->L ? p->L->inds[0] : v.inds[0];
     if (p->L) {
       const Tensor& L = *p->L;
-      p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2], v.inds[3]}, 2, Ctx::SLOT_T1);
+      p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2], v.inds[3]}, 2, Ctx::SLOT_T1, cp);
       p->g1 = plan_gemm(L, false, v, false, *p->T1);
     } else {
       TNL_CHECK(is_trivial_link(W1.inds[0]), "term without a left environment must start with a trivial link");
       p->T1 = view_with_trivial(ctx, v, 1, 2, win(p->W1), nullptr);          // data = the input vector itself
     }
-    p->T2 = mk_ws(ctx, {lout, W1.inds[2], W1.inds[3], v.inds[2], v.inds[3]}, 5, Ctx::SLOT_T2);
+    p->T2 = mk_ws(ctx, {lout, W1.inds[2], W1.inds[3], v.inds[2], v.inds[3]}, 5, Ctx::SLOT_T2, cp);
     p->x2 = plan_transform(*p->T1, *p->T2, {0, -1, -1, 3, 4}, &W1, {1, 2});
-    p->T3 = mk_ws(ctx, {lout, W1.inds[2], W2.inds[2], W2.inds[3], v.inds[3]}, 3, Ctx::SLOT_T3);
+    p->T3 = mk_ws(ctx, {lout, W1.inds[2], W2.inds[2], W2.inds[3], v.inds[3]}, 3, Ctx::SLOT_T3, cp);
     p->x3 = plan_transform(*p->T2, *p->T3, {0, 1, -1, -1, 4}, &W2, {2, 3});
     if (p->R) {
       const Tensor& R = *p->R;
-      p->P = mk_ws(ctx, {lout, W1.inds[2], W2.inds[2], R.inds[0]}, 3, Ctx::SLOT_P);
+      p->P = mk_ws(ctx, {lout, W1.inds[2], W2.inds[2], R.inds[0]}, 3, Ctx::SLOT_P, cp);
       p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
     } else {
       TNL_CHECK(is_trivial_link(W2.inds[3]), "term without a right environment must end with a trivial link");
-      p->P = std::make_shared<Tensor>(ctx, std::vector<Index>{lout, W1.inds[2], W2.inds[2], v.inds[3]}, 3, false);
+      p->P = std::make_shared<Tensor>(ctx, std::vector<Index>{lout, W1.inds[2], W2.inds[2], v.inds[3]}, 3, false, cp);
       TNL_CHECK(p->P->nelem == p->T3->nelem, "trivial-link view changed the layout");
       p->P->d = p->T3->d;
       p->P->owns = false;
@@ -597,21 +624,21 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
     const Index lout = p->L ? p->L->inds[0] : v.inds[0];
     if (p->L) {
       const Tensor& L = *p->L;
-      p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2]}, 2, Ctx::SLOT_T1);
+      p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1], v.inds[2]}, 2, Ctx::SLOT_T1, cp);
       p->g1 = plan_gemm(L, false, v, false, *p->T1);
     } else {
       TNL_CHECK(is_trivial_link(W1.inds[0]), "term without a left environment must start with a trivial link");
       p->T1 = view_with_trivial(ctx, v, 1, 2, win(p->W1), nullptr);
     }
-    p->T3 = mk_ws(ctx, {lout, W1.inds[2], W1.inds[3], v.inds[2]}, 2, Ctx::SLOT_T3);
+    p->T3 = mk_ws(ctx, {lout, W1.inds[2], W1.inds[3], v.inds[2]}, 2, Ctx::SLOT_T3, cp);
     p->x2 = plan_transform(*p->T1, *p->T3, {0, -1, -1, 3}, &W1, {1, 2});
     if (p->R) {
       const Tensor& R = *p->R;
-      p->P = mk_ws(ctx, {lout, W1.inds[2], R.inds[0]}, 2, Ctx::SLOT_P);
+      p->P = mk_ws(ctx, {lout, W1.inds[2], R.inds[0]}, 2, Ctx::SLOT_P, cp);
       p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
     } else {
       TNL_CHECK(is_trivial_link(W1.inds[3]), "term without a right environment must end with a trivial link");
-      p->P = std::make_shared<Tensor>(ctx, std::vector<Index>{lout, W1.inds[2], v.inds[2]}, 2, false);
+      p->P = std::make_shared<Tensor>(ctx, std::vector<Index>{lout, W1.inds[2], v.inds[2]}, 2, false, cp);
       TNL_CHECK(p->P->nelem == p->T3->nelem, "trivial-link view changed the layout");
       p->P->d = p->T3->d;
       p->P->owns = false;
@@ -624,11 +651,11 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
     TNL_CHECK(v.rank() == 2, "zero-site apply needs a (l,r) bond matrix");
     if (p->L && p->R) {
       const Tensor &L = *p->L, &R = *p->R;
-      p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1]}, 2, Ctx::SLOT_T1);            // [(l' w) | r]
+      p->T1 = mk_ws(ctx, {L.inds[0], L.inds[1], v.inds[1]}, 2, Ctx::SLOT_T1, cp);            // [(l' w) | r]
       p->g1 = plan_gemm(L, false, v, false, *p->T1);
-      p->T3 = mk_ws(ctx, p->T1->inds, 1, Ctx::SLOT_T3);                                  // [l' | (w r)]
+      p->T3 = mk_ws(ctx, p->T1->inds, 1, Ctx::SLOT_T3, cp);                                  // [l' | (w r)]
       p->x2 = plan_transform(*p->T1, *p->T3, {0, 1, 2}, nullptr, {});
-      p->P = mk_ws(ctx, {L.inds[0], R.inds[0]}, 1, Ctx::SLOT_P);
+      p->P = mk_ws(ctx, {L.inds[0], R.inds[0]}, 1, Ctx::SLOT_P, cp);
       p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
       TNL_CHECK(p->P->nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
       p->flops = p->g1->flops + p->g4->flops;
@@ -636,7 +663,7 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
       // out[l' | r] = L[(l' w0) | l] v[l | r]   (local left environment: the link is trivial)
       const Tensor& L = *p->L;
       TNL_CHECK(is_trivial_link(L.inds[1]), "left-only zero-site term must carry a trivial link");
-      p->P = std::make_shared<Tensor>(ctx, std::vector<Index>{L.inds[0], L.inds[1], v.inds[1]}, 2, false);
+      p->P = std::make_shared<Tensor>(ctx, std::vector<Index>{L.inds[0], L.inds[1], v.inds[1]}, 2, false, cp);
       TNL_CHECK(p->P->nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
       p->g1 = plan_gemm(L, false, v, false, *p->P);
       p->flops = p->g1->flops;
@@ -645,7 +672,7 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
       const Tensor& R = *p->R;
       TNL_CHECK(is_trivial_link(R.inds[1]), "right-only zero-site term must carry a trivial link");
       p->T3 = view_with_trivial(ctx, v, 1, 1, with_dir(R.inds[1], -R.inds[1].dir), nullptr);
-      p->P = std::make_shared<Tensor>(ctx, std::vector<Index>{v.inds[0], R.inds[0]}, 1, false);
+      p->P = std::make_shared<Tensor>(ctx, std::vector<Index>{v.inds[0], R.inds[0]}, 1, false, cp);
       TNL_CHECK(p->P->nelem == v.nelem, "H_eff output layout differs from the input layout (index mismatch)");
       p->g4 = plan_gemm(*p->T3, false, R, true, *p->P);
       p->flops = p->g4->flops;
@@ -666,7 +693,7 @@ double Env::apply_flops() const {
 }
 
 void Env::apply(const Tensor& v, Tensor& out) {
-  TNL_CHECK(out.nelem == v.nelem && out.nrow == 1, "output vector layout mismatch");
+  TNL_CHECK(out.nelem == v.nelem && out.nrow == 1 && out.cplx == v.cplx, "output vector layout mismatch");
   apply_ptr(v, v.d, out.d);
 }
 
@@ -708,10 +735,10 @@ void Env::ensure_plan(const Tensor& proto) {
   // (or reused by another phase) after it was built; two passes reach a fixed point because capacities only grow
   for (int pass = 0; pass < 3; pass++) {
     bool rebuilt = false;
-    if (!ap || ap->nsite != nsite || ap->nelem != proto.nelem || ap->epoch != ctx->slot_epoch) { build_apply_plan(proto); rebuilt = true; }
+    if (!ap || ap->nsite != nsite || ap->nelem != proto.nelem || ap->cplx != proto.cplx || ap->epoch != ctx->slot_epoch) { build_apply_plan(proto); rebuilt = true; }
     for (auto& m : more) {
       m->nsite = nsite;
-      if (!m->ap || m->ap->nsite != nsite || m->ap->nelem != proto.nelem || m->ap->epoch != ctx->slot_epoch) { m->build_apply_plan(proto); rebuilt = true; }
+      if (!m->ap || m->ap->nsite != nsite || m->ap->nelem != proto.nelem || m->ap->cplx != proto.cplx || m->ap->epoch != ctx->slot_epoch) { m->build_apply_plan(proto); rebuilt = true; }
     }
     if (!rebuilt || more.empty()) break;
     TNL_CHECK(pass < 2, "apply plans of the MPO sum did not stabilise");
@@ -723,28 +750,43 @@ void Env::ensure_plan(const Tensor& proto) {
 
 // one term, not sharded: vout = L * W1 * W2 * R applied to vin (absent L / R: trivial-link views, see make_plan)
 void Env::run_plan(ApplyPlan& p, const double* vin, double* vout) {
+  const bool cp = p.cplx;
+  const int64_t n = p.nelem;                               // plane distance of the Krylov vectors
+  const double* vin_i = cp ? vin + n : nullptr;
+  double* vout_i = cp ? vout + n : nullptr;
+  auto imc = [&](const TensorP& t) -> const double* { return t->cplx ? t->im() : nullptr; };
+  auto imw = [&](const TensorP& t) -> double* { return t->cplx ? t->im() : nullptr; };
+  auto xf = [&](TransformPlan& x, const double* sr, const double* si, double* dr, double* di, const double* W) {
+    run_transform(ctx, x, sr, dr, W);
+    if (cp) run_transform(ctx, x, si, di, W);
+  };
   if (p.nsite == 0) {
     if (p.L && p.R) {
-      run_gemm(ctx, *p.g1, p.L->d, vin, p.T1->d);
-      run_transform(ctx, *p.x2, p.T1->d, p.T3->d, nullptr);
-      run_gemm(ctx, *p.g4, p.T3->d, p.R->d, vout);
+      cgemm(ctx, *p.g1, p.L->d, imc(p.L), false, vin, vin_i, false, p.T1->d, imw(p.T1));
+      xf(*p.x2, p.T1->d, imc(p.T1), p.T3->d, imw(p.T3), nullptr);
+      cgemm(ctx, *p.g4, p.T3->d, imc(p.T3), false, p.R->d, imc(p.R), false, vout, vout_i);
     } else if (p.L) {
-      run_gemm(ctx, *p.g1, p.L->d, vin, vout);
+      cgemm(ctx, *p.g1, p.L->d, imc(p.L), false, vin, vin_i, false, vout, vout_i);
     } else {
-      run_gemm(ctx, *p.g4, vin, p.R->d, vout);
+      cgemm(ctx, *p.g4, vin, vin_i, false, p.R->d, imc(p.R), false, vout, vout_i);
     }
     return;
   }
   const double* t1 = vin;
-  if (p.g1) { run_gemm(ctx, *p.g1, p.L->d, vin, p.T1->d); t1 = p.T1->d; }
-  if (p.nsite == 2) {
-    run_transform(ctx, *p.x2, t1, p.T2->d, p.W1->d);
-    run_transform(ctx, *p.x3, p.T2->d, p.T3->d, p.W2->d);
-  } else {
-    run_transform(ctx, *p.x2, t1, p.T3->d, p.W1->d);
+  const double* t1i = vin_i;
+  if (p.g1) {
+    cgemm(ctx, *p.g1, p.L->d, imc(p.L), false, vin, vin_i, false, p.T1->d, imw(p.T1));
+    t1 = p.T1->d;
+    t1i = imc(p.T1);
   }
-  if (p.g4) run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
-  run_transform(ctx, *p.x5, p.P->d, vout, nullptr);
+  if (p.nsite == 2) {
+    xf(*p.x2, t1, t1i, p.T2->d, imw(p.T2), p.W1->d);
+    xf(*p.x3, p.T2->d, imc(p.T2), p.T3->d, imw(p.T3), p.W2->d);
+  } else {
+    xf(*p.x2, t1, t1i, p.T3->d, imw(p.T3), p.W1->d);
+  }
+  if (p.g4) cgemm(ctx, *p.g4, p.T3->d, imc(p.T3), false, p.R->d, imc(p.R), false, p.P->d, imw(p.P));
+  xf(*p.x5, p.P->d, imc(p.P), vout, vout_i, nullptr);
 }
 
 void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
@@ -761,14 +803,16 @@ void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
   else run_plan(p, vin, vout);
   // + sum_k H_k v   (ProjMPOSum2.product, src/mps/projmposum2.jl:86-101)
   if (!more.empty()) {
-    double* tmp = ctx->vec_acquire((size_t)proto.nelem);
+    const int64_t nv = proto.planes() * proto.nelem;
+    double* tmp = ctx->vec_acquire((size_t)nv);
     for (auto& m : more) {
       m->apply_ptr(proto, vin, tmp);
-      vec_axpy(ctx, vout, tmp, proto.nelem, 1.0);
+      vec_axpy(ctx, vout, tmp, nv, 1.0);
     }
     ctx->vec_release(tmp, 0);
   }
   // + weight * sum_M <m|v> |m>   (ProjMPO_MPS2.product)
+  TNL_CHECK(!proto.cplx || pens.empty(), "excited-state penalties on complex vectors are not built");
   for (auto& pen : pens) {
     if (pen.dead) continue;
     build_penalty_vector(pen, proto);
@@ -779,9 +823,9 @@ void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
 }
 
 double Env::expectation(const Tensor& phi) {
-  Tensor tmp(ctx, phi.inds, 1);
+  Tensor tmp(ctx, phi.inds, 1, true, phi.cplx);
   apply(phi, tmp);
-  vec_dot(ctx, phi.d, tmp.d, phi.nelem, 0);
+  vec_dot(ctx, phi.d, tmp.d, phi.planes() * phi.nelem, 0);     // real part of <phi|H|phi>: one flat pass over both planes
   fetch_scalars(ctx, 1);
   return ctx->h_scalars[0];
 }
@@ -860,6 +904,7 @@ static void householder(const std::vector<double>& x, int i, double& beta, std::
 // The same algorithm is restated independently in oracle/krylov.py.
 LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter, bool eager) {
   TNL_CHECK(krylovdim >= 1 && krylovdim < 200, "krylovdim out of range");
+  TNL_CHECK(!phi.cplx, "eig_solver on complex tensors is not built (TDVP / exp_solver is)");
   ensure_plan(phi);
   const bool sh = ap->sharded;                       // Krylov vectors live as r-slices, one per rank
   const int64_t n = sh ? ap->nloc : phi.nelem;
@@ -1048,21 +1093,37 @@ static std::complex<double> phi_fn(std::complex<double> z, int order) {
 // unit time, adaptive sub-steps (gamma = 0.8) when the basis is full, eager exit at every K, first-correction
 // term.  The same algorithm is restated independently in oracle/krylov.py.  All vectors stay in HBM.
 ExpResult Env::exponentiate(Tensor& phi, double t_re, double t_im, double tol, int krylovdim, int maxiter, bool eager) {
-  TNL_CHECK(t_im == 0.0, "complex time steps need complex tensors: this build evolves in real (imaginary-time) steps only");
+  using cd = std::complex<double>;
+  const bool cx = phi.cplx;
+  TNL_CHECK(t_im == 0.0 || cx, "a complex time step needs a complex (planar) vector: promote phi first");
   TNL_CHECK(krylovdim >= 1 && krylovdim < LC_MAX_HOST, "krylovdim out of range");
   ExpResult res;
-  const double t = t_re;
-  const double tau = std::fabs(t);
+  const cd t(t_re, t_im);
+  const double tau = std::abs(t);
   if (tau == 0.0) { res.converged = 1; return res; }
   ensure_plan(phi);
   const bool sh = ap->sharded;
-  const int64_t n = sh ? ap->nloc : phi.nelem;
-  const double sgn = t / tau;
-  auto newvec = [&]() { return ctx->vec_acquire((size_t)n); };
+  TNL_CHECK(!(sh && cx), "complex vectors are not sharded");
+  const int64_t n = sh ? ap->nloc : phi.nelem;        // plane size
+  const int64_t nv = cx ? 2 * n : n;                  // doubles per Krylov vector
+  const cd sgn = t / tau;
+  auto newvec = [&]() { return ctx->vec_acquire((size_t)nv); };
   auto applyraw = [&](double* vin, double* vout) { if (sh) apply_local(vin, vout); else apply_ptr(phi, vin, vout); res.numops++; };
-  auto dot = [&](const double* x, const double* y, int slot) {
-    tnl::vec_dot(ctx, x, y, n, slot);
-    if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + slot, 1);
+  // <x, y> into scalar slots (2k, 2k+1) = (re, im); the imaginary part of a real product is left untouched
+  auto dot = [&](const double* x, const double* y, int k) {
+    if (cx) vec_cdot(ctx, x, y, n, 2 * k);
+    else {
+      tnl::vec_dot(ctx, x, y, n, 2 * k);
+      if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + 2 * k, 1);
+    }
+  };
+  auto norm2 = [&](const double* x, int k) {          // |x|^2: one flat pass over both planes
+    tnl::vec_dot(ctx, x, x, nv, 2 * k);
+    if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + 2 * k, 1);
+  };
+  auto axpy_slot = [&](double* y, const double* x, int k) {      // y -= s_k x
+    if (cx) vec_caxpy_dev(ctx, y, x, n, 2 * k, -1.0);
+    else vec_axpy_dev(ctx, y, x, n, 2 * k, -1.0);
   };
   double* w0 = phi.d;
   double* phi_loc = nullptr;
@@ -1089,56 +1150,63 @@ ExpResult Env::exponentiate(Tensor& phi, double t_re, double t_im, double tol, i
     r = newvec();
     applyraw(w1, r);
     dot(w1, r, 0);
-    fetch_scalars(ctx, 1);
+    fetch_scalars(ctx, 2);
     double alpha = ctx->h_scalars[0] / (beta * beta);
     double* v0 = newvec();
-    vec_scale_to(ctx, v0, w1, n, 1.0 / beta);
-    vec_scale(ctx, r, n, 1.0 / beta);
-    vec_axpy(ctx, r, v0, n, -alpha);
+    vec_scale_to(ctx, v0, w1, nv, 1.0 / beta);
+    vec_scale(ctx, r, nv, 1.0 / beta);
+    vec_axpy(ctx, r, v0, nv, -alpha);
     dot(v0, r, 0);
-    vec_axpy_dev(ctx, r, v0, n, 0, -1.0);
-    dot(r, r, 1);
-    fetch_scalars(ctx, 2);
+    axpy_slot(r, v0, 0);
+    norm2(r, 1);
+    fetch_scalars(ctx, 4);
     alphas.push_back(alpha + ctx->h_scalars[0]);
-    betas.push_back(std::sqrt(ctx->h_scalars[1]));
+    betas.push_back(std::sqrt(ctx->h_scalars[2]));
     V.push_back(v0);
   };
   auto start = [&]() -> bool {          // w1 = A w0, beta = |w1|; false: w0 is a fixed point
     applyraw(w0, w1);
-    dot(w1, w1, 0);
+    norm2(w1, 0);
     fetch_scalars(ctx, 1);
     beta = std::sqrt(ctx->h_scalars[0]);
     return beta >= tol;
   };
   // small exponential: c1 = phi_1(s dt T) e1, c2last = [phi_2(s dt T) e1]_K ; returns the error estimate
-  std::vector<double> c1;
-  double c2last = 0.0;
+  std::vector<cd> c1;
+  cd c2last = 0.0;
   auto small_exp = [&](double dt) {
     const int K = (int)alphas.size();
     std::vector<double> T((size_t)K * K, 0.0), D, Q;
     for (int j = 0; j < K; j++) T[(size_t)j * K + j] = alphas[j];
     for (int j = 0; j + 1 < K; j++) T[(size_t)j * K + j + 1] = T[(size_t)(j + 1) * K + j] = betas[j];
     if (K == 1) { D = {alphas[0]}; Q = {1.0}; } else sym_eig(K, T, D, Q);
-    c1.assign(K, 0.0);
+    c1.assign(K, cd(0.0));
     c2last = 0.0;
     for (int j = 0; j < K; j++) {
-      const double p1 = phi_fn(sgn * dt * D[j], 1).real(), p2 = phi_fn(sgn * dt * D[j], 2).real();
+      const cd p1 = phi_fn(sgn * dt * D[j], 1), p2 = phi_fn(sgn * dt * D[j], 2);
       const double q0 = Q[(size_t)0 * K + j];
-      for (int i = 0; i < K; i++) c1[i] += Q[(size_t)i * K + j] * p1 * q0;
-      c2last += Q[(size_t)(K - 1) * K + j] * p2 * q0;
+      for (int i = 0; i < K; i++) c1[i] += Q[(size_t)i * K + j] * q0 * p1;
+      c2last += Q[(size_t)(K - 1) * K + j] * q0 * p2;
     }
-    return std::fabs(dt * beta * betas.back() * c2last);
+    return std::abs(dt * beta * betas.back() * c2last);
   };
   // w0 += beta * s * dt * (V c1 + c2last * r)
   auto take = [&](double dt) {
     const int K = (int)alphas.size();
     std::vector<const double*> xs(V.begin(), V.begin() + K);
-    std::vector<double> cf(c1);
     xs.push_back(r);
-    cf.push_back(c2last);
+    std::vector<double> cr, ci;
+    for (int i = 0; i < K; i++) { cr.push_back(c1[i].real()); ci.push_back(c1[i].imag()); }
+    cr.push_back(c2last.real()); ci.push_back(c2last.imag());
     double* y = newvec();
-    vec_lincomb(ctx, y, xs.data(), cf.data(), K + 1, n);
-    vec_axpy(ctx, w0, y, n, beta * sgn * dt);
+    const cd f = beta * sgn * dt;
+    if (cx) {
+      vec_clincomb(ctx, y, xs.data(), cr.data(), ci.data(), K + 1, n);
+      vec_caxpy(ctx, w0, y, n, f.real(), f.imag());
+    } else {
+      vec_lincomb(ctx, y, xs.data(), cr.data(), K + 1, n);
+      vec_axpy(ctx, w0, y, n, f.real());
+    }
     ctx->vec_release(y, 0);
   };
   const double gamma = 0.8;
@@ -1179,23 +1247,23 @@ ExpResult Env::exponentiate(Tensor& phi, double t_re, double t_im, double tol, i
       // expand! + lanczosrecurrence (ModifiedGramSchmidt2)
       const double bold = betas.back();
       double* vnew = r;
-      vec_scale(ctx, vnew, n, 1.0 / bold);
+      vec_scale(ctx, vnew, nv, 1.0 / bold);
       V.push_back(vnew);
       double* w = newvec();
       r = nullptr;
       applyraw(vnew, w);
       const int m = (int)V.size();
-      vec_axpy(ctx, w, V[m - 2], n, -bold);
+      vec_axpy(ctx, w, V[m - 2], nv, -bold);
       dot(vnew, w, 0);
-      vec_axpy_dev(ctx, w, vnew, n, 0, -1.0);
+      axpy_slot(w, vnew, 0);
       for (int qi = 0; qi < m; qi++) {
         dot(V[qi], w, 1 + qi);
-        vec_axpy_dev(ctx, w, V[qi], n, 1 + qi, -1.0);
+        axpy_slot(w, V[qi], 1 + qi);
       }
-      dot(w, w, 1 + m);
-      fetch_scalars(ctx, 2 + m);
-      alphas.push_back(ctx->h_scalars[0] + ctx->h_scalars[m]);
-      betas.push_back(std::sqrt(ctx->h_scalars[1 + m]));
+      norm2(w, 1 + m);
+      fetch_scalars(ctx, 2 * (2 + m));
+      alphas.push_back(ctx->h_scalars[0] + ctx->h_scalars[2 * m]);       // alpha + last correction (against vnew)
+      betas.push_back(std::sqrt(ctx->h_scalars[2 * (1 + m)]));
       r = w;
     } else {
       if (res.numiter == maxiter) { res.converged = 0; break; }
@@ -1241,6 +1309,7 @@ TensorP Env::noise_operand(const Tensor& phi, bool left, const Tensor* E, const 
   auto mk_x = [&](std::vector<Index> inds, int nrow) {
     return own_storage ? mk(ctx, std::move(inds), nrow) : mk_ws(ctx, std::move(inds), nrow, Ctx::SLOT_T2);
   };
+  TNL_CHECK(!phi.cplx && !(E && E->cplx), "noise term on complex tensors is not built");
   ap.reset();                                     // reuse the apply workspaces (the plan dies with the bond anyway)
   ctx->slot_epoch++;
   if (left) {
@@ -1313,11 +1382,11 @@ FactorizeResult Env::replacebond(int pos, const Tensor& phi, FactorizeParams prm
   FactorizeResult f = factorize(ctx, *S, prm);
   if (normalize) {
     Tensor& t = prm.ortho_left ? *f.R : *f.L;
-    vec_dot(ctx, t.d, t.d, t.nelem, 0);
+    vec_dot(ctx, t.d, t.d, t.planes() * t.nelem, 0);
     fetch_scalars(ctx, 1);
     double nrm = std::sqrt(ctx->h_scalars[0]);
     TNL_CHECK(nrm > 0, "replacebond: zero norm");
-    vec_scale(ctx, t.d, t.nelem, 1.0 / nrm);
+    vec_scale(ctx, t.d, t.planes() * t.nelem, 1.0 / nrm);
   }
   A[pos - 1] = f.L;
   A[pos] = f.R;
@@ -1337,11 +1406,11 @@ FactorizeResult Env::svd_split(int pos, const Tensor& phi, FactorizeParams prm, 
   FactorizeResult f = factorize(ctx, *T, prm);
   Tensor& carry = left ? *f.R : *f.L;               // S*V (m, r)  or  U*S (l, m)
   if (normalize) {
-    vec_dot(ctx, carry.d, carry.d, carry.nelem, 0);
+    vec_dot(ctx, carry.d, carry.d, carry.planes() * carry.nelem, 0);
     fetch_scalars(ctx, 1);
     double nrm = std::sqrt(ctx->h_scalars[0]);
     TNL_CHECK(nrm > 0, "svd_split: zero norm");
-    vec_scale(ctx, carry.d, carry.nelem, 1.0 / nrm);
+    vec_scale(ctx, carry.d, carry.planes() * carry.nelem, 1.0 / nrm);
   }
   A[pos - 1] = left ? f.L : f.R;
   invalidate(pos, pos);
@@ -1357,9 +1426,9 @@ void Env::absorb_bond(int pos, bool left, const Tensor& carry) {
     TensorP C1 = carry.nrow == 1 ? nullptr : relayout(ctx, carry, 1);
     const Tensor& Cm = C1 ? *C1 : carry;
     TensorP nx = as_nrow(ctx, A[pos], 1);
-    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{Cm.inds[0], nx->inds[1], nx->inds[2]}, 1);
+    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{Cm.inds[0], nx->inds[1], nx->inds[2]}, 1, true, Cm.cplx || nx->cplx);
     auto g = plan_gemm(Cm, false, *nx, false, *An);
-    run_gemm(ctx, *g, Cm.d, nx->d, An->d);
+    cgemm(ctx, *g, Cm, false, *nx, false, *An);
     ctx->sync();
     A[pos] = An;
     invalidate(pos + 1, pos + 1);
@@ -1368,9 +1437,9 @@ void Env::absorb_bond(int pos, bool left, const Tensor& carry) {
     TensorP pv = as_nrow(ctx, A[pos - 2], 2);
     TensorP C1 = carry.nrow == 1 ? nullptr : relayout(ctx, carry, 1);
     const Tensor& Cm = C1 ? *C1 : carry;
-    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{pv->inds[0], pv->inds[1], Cm.inds[1]}, 2);
+    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{pv->inds[0], pv->inds[1], Cm.inds[1]}, 2, true, pv->cplx || Cm.cplx);
     auto g = plan_gemm(*pv, false, Cm, false, *An);
-    run_gemm(ctx, *g, pv->d, Cm.d, An->d);
+    cgemm(ctx, *g, *pv, false, Cm, false, *An);
     ctx->sync();
     A[pos - 2] = An;
     invalidate(pos - 1, pos - 1);
@@ -1381,6 +1450,8 @@ void Env::absorb_bond(int pos, bool left, const Tensor& carry) {
 // move_center(N, 1) right-canonicalises an arbitrary MPS (sweep.jl:100-102).
 void Env::move_center(int from, int to) {
   TNL_CHECK(from >= 1 && from <= N && to >= 1 && to <= N, "site out of range");
+  for (int j = std::min(from, to); j <= std::max(from, to); j++)
+    TNL_CHECK(!A[j - 1]->cplx, "QR gauge moves of complex tensors are not built");
   FactorizeParams prm;
   prm.which = 3;
   for (int j = from; j > to; j--) {                // right-orthonormalise site j, push the rest into j-1
@@ -1661,7 +1732,7 @@ void Env::cm_ensure_plans(const Tensor& proto) {
   TNL_CHECK(rpos - lpos == nsite + 1, "environments are not positioned for this nsite");
   for (int pass = 0; pass < 4; pass++) {
     bool stale = !ap || cm->plans.empty() || cm->plan_lpos != lpos || cm->plan_rpos != rpos || ap->nsite != nsite ||
-                 ap->nelem != proto.nelem;
+                 ap->nelem != proto.nelem || ap->cplx != proto.cplx;
     for (auto& pl : cm->plans) stale = stale || pl.second->epoch != ctx->slot_epoch;
     if (!stale) return;
     TNL_CHECK(pass < 3, "apply plans of the CouplingModel did not stabilise");
@@ -1687,9 +1758,10 @@ void Env::cm_apply(const Tensor& proto, const double* vin, double* vout) {
   bool first = true;
   for (auto& pl : cm->plans) {
     if (first) { run_plan(*pl.second, vin, vout); first = false; continue; }
-    if (!tmp) tmp = ctx->vec_acquire((size_t)proto.nelem);
+    const int64_t nv = proto.planes() * proto.nelem;
+    if (!tmp) tmp = ctx->vec_acquire((size_t)nv);
     run_plan(*pl.second, vin, tmp);
-    vec_axpy(ctx, vout, tmp, proto.nelem, 1.0);
+    vec_axpy(ctx, vout, tmp, nv, 1.0);
   }
   if (tmp) ctx->vec_release(tmp, 0);
 }
@@ -1714,6 +1786,20 @@ std::vector<TensorP> Env::cm_noise_operands(const Tensor& phi, bool left) {
                        : noise_operand(phi, false, pc.R.get(), *pc.W[1]->Wnr, true));
   }
   return out;
+}
+
+bool Env::complex_at_position() const {
+  auto cx = [](const TensorP& t) { return t && t->cplx; };
+  bool any = false;
+  if (cm) {
+    if (lpos >= 1) for (auto& kv : cm->LR[lpos - 1]) any = any || cx(kv.second.t);
+    if (rpos <= N) for (auto& kv : cm->LR[rpos - 1]) any = any || cx(kv.second.t);
+  } else {
+    if (lpos >= 1) any = any || cx(LR[lpos - 1]);
+    if (rpos <= N) any = any || cx(LR[rpos - 1]);
+  }
+  for (auto& m : more) any = any || m->complex_at_position();
+  return any;
 }
 
 }  // namespace tnl

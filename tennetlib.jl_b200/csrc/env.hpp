@@ -13,6 +13,7 @@ struct HostBlocks {             // NDTensors-style flat host tensor (column-majo
   std::vector<std::vector<int>> coords;
   std::vector<int64_t> offsets;
   const double* data = nullptr;
+  bool cplx = false;            // data is interleaved ComplexF64 (offsets count complex elements)
 };
 
 TensorP import_tensor(Ctx* ctx, const HostBlocks& hb, int nrow);
@@ -123,6 +124,7 @@ class Env {
   void absorb_bond(int pos, bool left, const Tensor& carry);
   void move_center(int from, int to);                   // QR gauge moves, ITensorMPS orthogonalize!
   double apply_flops() const;                           // algorithmic flops of one H_eff apply at the current position
+  bool complex_at_position() const;                     // any environment tensor bounding the site range is complex
 
  private:
   struct ApplyPlan;

@@ -209,7 +209,207 @@ static FactorizeResult factorize_qr(Ctx* ctx, const Tensor& T, bool left, int ne
   return res;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// ComplexF64 (planar) tensors: Hermitian-eigenproblem route only.  rho = M M^+ (ortho left) or M^+ M (right)
+// with four launches of the real grouped DGEMM, planar -> interleaved, cusolverDnZheevd per charge group,
+// eigenvectors back to planes, the other factor by projection.  Covers `factorize`'s eigen path and -- as in the
+// "gram" driver of the real code -- its SVD path (same kept spectrum sigma^2, same truncation); the dedicated
+// complex SVD / QR drivers and the noise term are not built.
+__global__ void interleave_kernel(double2* __restrict__ z, const double* __restrict__ re, const double* __restrict__ im, int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+    z[e] = make_double2(re[e], im[e]);
+}
+__global__ void deinterleave_kernel(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ z, int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const double2 v = z[e];
+    re[e] = v.x;
+    im[e] = v.y;
+  }
+}
+
+static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const FactorizeParams& prm) {
+  const int split = T.nrow;
+  TNL_CHECK(prm.noise == 0.0 || prm.noiseX == nullptr, "noise term on complex tensors is not built");
+  TNL_CHECK(prm.which != 3, "QR gauge moves of complex tensors are not built");
+  const bool left = prm.ortho_left != 0;
+  cusolverDnHandle_t H = solver(ctx);
+  const int64_t tn = T.nelem;
+  std::vector<FG> fg;
+  for (const Group& g : T.groups) {
+    FG f; f.q = g.q; f.R = g.R; f.C = g.C; f.M = T.d + g.base; f.ldm = g.ld;
+    fg.push_back(f);
+  }
+  std::vector<void*> temps;
+  auto talloc = [&](int64_t n) {
+    n = (std::max<int64_t>(n, 1) + 1) & ~int64_t(1);
+    double* p = (double*)ctx->alloc((size_t)n * sizeof(double));
+    CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(double), ctx->stream));
+    temps.push_back(p);
+    return p;
+  };
+  auto off = [](const double* p) { return (int64_t)(reinterpret_cast<intptr_t>(p) / (intptr_t)sizeof(double)); };
+  // ---- rho per group (planes Er, Ei with leading dimension n)
+  std::vector<double*> Er(fg.size(), nullptr), Ei(fg.size(), nullptr);
+  {
+    std::vector<GemmProblem> pr;
+    std::vector<size_t> which_g;
+    for (size_t gi = 0; gi < fg.size(); gi++) {
+      FG& f = fg[gi];
+      const int64_t n = left ? f.R : f.C;
+      if (n == 0) continue;
+      Er[gi] = talloc(n * n);
+      Ei[gi] = talloc(n * n);
+      GemmProblem p{};
+      p.M = p.N = (int)n; p.ldc = (int)n; p.K = (int)(left ? f.C : f.R);
+      p.a = p.b = off(f.M); p.lda = p.ldb = (int)f.ldm;
+      p.c = off(Er[gi]);
+      pr.push_back(p);
+      which_g.push_back(gi);
+    }
+    // the real and imaginary result planes live in separate allocations: one plan per plane pair is avoided by
+    // addressing everything relative to nullptr and shifting the C offsets for the imaginary pass
+    auto gr = plan_gemm_raw(ctx, !left, left, pr);
+    std::vector<GemmProblem> pi = pr;
+    for (size_t k = 0; k < pi.size(); k++) pi[k].c = off(Ei[which_g[k]]);
+    auto gi2 = plan_gemm_raw(ctx, !left, left, pi);
+    const double* Mr = nullptr;                  // offsets are absolute addresses / 8
+    const double* Mi = Mr + tn;                  // imaginary plane of T: + nelem doubles
+    // left : rho = M M^+  -> A = M, B^T = conj(M):  Cr = Mr Mr^T + Mi Mi^T ; Ci = Mi Mr^T - Mr Mi^T
+    // right: rho = M^+ M  -> A^T = conj(M), B = M:  Cr = Mr^T Mr + Mi^T Mi ; Ci = Mr^T Mi - Mi^T Mr
+    run_gemm(ctx, *gr, Mr, Mr, nullptr, 1.0, false);
+    run_gemm(ctx, *gr, Mi, Mi, nullptr, 1.0, true);
+    if (left) {
+      run_gemm(ctx, *gi2, Mi, Mr, nullptr, 1.0, false);
+      run_gemm(ctx, *gi2, Mr, Mi, nullptr, -1.0, true);
+    } else {
+      run_gemm(ctx, *gi2, Mr, Mi, nullptr, 1.0, false);
+      run_gemm(ctx, *gi2, Mi, Mr, nullptr, -1.0, true);
+    }
+    ctx->sync();
+  }
+  // ---- Hermitian eigendecompositions
+  std::vector<double> pool;
+  for (size_t gi = 0; gi < fg.size(); gi++) {
+    FG& f = fg[gi];
+    const int64_t n = left ? f.R : f.C;
+    if (n == 0) continue;
+    double2* Z = (double2*)talloc(2 * n * n);
+    double* Wv = talloc(n);
+    const int grid = (int)std::min<int64_t>((n * n + 255) / 256, 1184);
+    interleave_kernel<<<grid, 256, 0, ctx->stream>>>(Z, Er[gi], Ei[gi], n * n);
+    CUDA_OK(cudaGetLastError());
+    int lwork = 0;
+    CUSOLVER_OK(cusolverDnZheevd_bufferSize(H, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n,
+                                            (cuDoubleComplex*)Z, (int)n, Wv, &lwork));
+    double* work = solver_ws(ctx, (size_t)lwork * 2);
+    CUSOLVER_OK(cusolverDnZheevd(H, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, (cuDoubleComplex*)Z, (int)n,
+                                 Wv, (cuDoubleComplex*)work, lwork, ctx->d_info));
+    deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>(Er[gi], Ei[gi], Z, n * n);     // eigenvectors, planar
+    CUDA_OK(cudaGetLastError());
+    f.vals.resize(n);
+    int info = 0;
+    CUDA_OK(cudaMemcpyAsync(f.vals.data(), Wv, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    TNL_CHECK(info == 0, "cusolverDnZheevd did not converge");
+    for (double w : f.vals) pool.push_back(std::fabs(w));
+  }
+  // ---- pooled truncation (identical to the real path)
+  std::sort(pool.begin(), pool.end(), std::greater<double>());
+  FactorizeResult res;
+  res.path = "eigen(complex)";
+  double docut = 0.0;
+  truncate_spectrum(pool, prm.maxdim, prm.mindim, prm.cutoff, res.truncerr, docut);
+  res.eigs = pool;
+  Index m;
+  m.nq = T.inds[0].nq;
+  std::vector<size_t> kept;
+  for (size_t gi = 0; gi < fg.size(); gi++) {
+    FG& f = fg[gi];
+    if (f.vals.empty()) continue;
+    std::vector<int> order(f.vals.size());
+    std::iota(order.begin(), order.end(), 0);
+    auto wt = [&](int i) { return std::fabs(f.vals[i]); };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return wt(a) > wt(b); });
+    for (int i : order)
+      if (wt(i) > docut) f.keep.push_back(i);
+    if (f.keep.empty()) continue;
+    m.dims.push_back((int)f.keep.size());
+    m.qns.push_back(f.q);
+    kept.push_back(gi);
+  }
+  m.dir = prm.new_dir_on_L;
+  std::vector<Index> li(T.inds.begin(), T.inds.begin() + split), ri;
+  li.push_back(m);
+  ri.push_back(m.dag());
+  ri.insert(ri.end(), T.inds.begin() + split, T.inds.end());
+  res.L = std::make_shared<Tensor>(ctx, li, split, true, true);
+  res.R = std::make_shared<Tensor>(ctx, ri, 1, true, true);
+  const int64_t ln = res.L->nelem, rn = res.R->nelem;
+  std::vector<GemmProblem> proj;
+  for (size_t gi : kept) {
+    FG& f = fg[gi];
+    const int nk = (int)f.keep.size();
+    const int gl = res.L->find_group(f.q), gr = res.R->find_group(f.q);
+    TNL_CHECK(gl >= 0 && gr >= 0, "new link sector missing on a factor");
+    const Group &GL = res.L->groups[gl], &GR = res.R->groups[gr];
+    TNL_CHECK(GL.R == f.R && GL.C == nk && GR.R == nk && GR.C == f.C, "factor group shape");
+    double* Ld = res.L->d + GL.base;
+    double* Rd = res.R->d + GR.base;
+    if (left) {
+      // L = V_k ; R = V_k^+ M
+      gather_cols(ctx, Ld, GL.ld, Er[gi], f.R, f.R, f.keep, nullptr);
+      gather_cols(ctx, Ld + ln, GL.ld, Ei[gi], f.R, f.R, f.keep, nullptr);
+      GemmProblem p{};
+      p.M = nk; p.N = (int)f.C; p.K = (int)f.R;
+      p.a = off(Ld); p.lda = (int)GL.ld; p.b = off(f.M); p.ldb = (int)f.ldm;
+      p.c = off(Rd); p.ldc = (int)GR.ld;
+      proj.push_back(p);
+    } else {
+      // R = V_k^+ (rows) ; L = M V_k
+      const int64_t ldk = (f.C + 1) & ~int64_t(1);
+      double* Vk = talloc(2 * ldk * nk);          // planes of ldk*nk
+      gather_cols(ctx, Vk, ldk, Er[gi], f.C, f.C, f.keep, nullptr);
+      gather_cols(ctx, Vk + ldk * nk, ldk, Ei[gi], f.C, f.C, f.keep, nullptr);
+      transpose(ctx, Rd, GR.ld, Vk, ldk, f.C, nk);
+      transpose(ctx, Rd + rn, GR.ld, Vk + ldk * nk, ldk, f.C, nk);
+      std::vector<double> neg(nk, -1.0);
+      double* dneg = ctx->upload(neg);
+      scale_rows_or_cols(ctx, Rd + rn, GR.ld, nk, f.C, dneg, true);      // conjugate
+      ctx->free(dneg);
+      GemmProblem p{};
+      p.M = (int)f.R; p.N = nk; p.K = (int)f.C;
+      p.a = off(f.M); p.lda = (int)f.ldm; p.b = off(Vk); p.ldb = (int)ldk;
+      p.c = off(Ld); p.ldc = (int)GL.ld;
+      // the imaginary plane of Vk sits ldk*nk doubles after the real one: remember it through the K-independent offset
+      proj.push_back(p);
+      f.ldu = ldk * nk;                            // plane distance of this group's Vk
+    }
+  }
+  if (!proj.empty()) {
+    if (left) {
+      // R = conj(L)^T M : planes of L are ln apart, of M tn apart, of R rn apart
+      auto g = plan_gemm_raw(ctx, true, false, proj);
+      const double* z = nullptr;
+      cgemm(ctx, *g, z, z + ln, true, z, z + tn, false, (double*)z, (double*)z + rn);
+    } else {
+      // L = M V_k : the plane distance of Vk differs per group -> one launch set per group
+      for (size_t k = 0; k < proj.size(); k++) {
+        auto g = plan_gemm_raw(ctx, false, false, {proj[k]});
+        const double* z = nullptr;
+        cgemm(ctx, *g, z, z + tn, false, z, z + fg[kept[k]].ldu, false, (double*)z, (double*)z + ln);
+        ctx->sync();
+      }
+    }
+    ctx->sync();
+  }
+  ctx->sync();
+  for (void* p : temps) ctx->free(p);
+  return res;
+}
+
 FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm) {
+  if (T.cplx) return factorize_complex(ctx, T, prm);
   const int split = T.nrow, rank = T.rank();
   TNL_CHECK(split >= 1 && split < rank, "factorize needs a proper bipartition");
   int which = prm.which;

@@ -79,7 +79,8 @@ struct OpTile {
 template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 gemm_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles,
-            const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase) {
+            const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase,
+            double alpha, int accum) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   using TileA = OpTile<BM, BK, TA>;     // A is k-fast when transposed (stored [k, m])
   using TileB = OpTile<BN, BK, !TB>;    // B is k-fast when NOT transposed (stored [k, n])
@@ -145,8 +146,9 @@ gemm_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ 
     for (int j = 0; j < WN / 8; j++) {
       int n = n0 + wn0 + j * 8 + 2 * lc;
       double* c = pC + (int64_t)n * p.ldc + m;
-      if (n < p.N) c[0] = acc[i][j][0];
-      if (n + 1 < p.N) c[p.ldc] = acc[i][j][1];
+      // C = alpha * A B (+ C): alpha = +-1 and the accumulate mode serve the planar complex products
+      if (n < p.N) c[0] = accum ? fma(alpha, acc[i][j][0], c[0]) : alpha * acc[i][j][0];
+      if (n + 1 < p.N) c[p.ldc] = accum ? fma(alpha, acc[i][j][1], c[p.ldc]) : alpha * acc[i][j][1];
     }
   }
 }
@@ -210,7 +212,8 @@ struct Loader {
 template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 gemm_kernel_v2(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles,
-               const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase) {
+               const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase,
+            double alpha, int accum) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   using TileA = OpTile<BM, BK, TA>;
   using TileB = OpTile<BN, BK, !TB>;
@@ -300,8 +303,9 @@ gemm_kernel_v2(const GemmProblem* __restrict__ probs, const GemmTile* __restrict
     for (int j = 0; j < NI; j++) {
       int n = n0 + wn0 + j * 8 + 2 * lc;
       double* c = pC + (int64_t)n * p.ldc + m;
-      if (n < p.N) c[0] = acc[i][j][0];
-      if (n + 1 < p.N) c[p.ldc] = acc[i][j][1];
+      // C = alpha * A B (+ C): alpha = +-1 and the accumulate mode serve the planar complex products
+      if (n < p.N) c[0] = accum ? fma(alpha, acc[i][j][0], c[0]) : alpha * acc[i][j][0];
+      if (n + 1 < p.N) c[p.ldc] = accum ? fma(alpha, acc[i][j][1], c[p.ldc]) : alpha * acc[i][j][1];
     }
   }
 }
@@ -309,7 +313,8 @@ gemm_kernel_v2(const GemmProblem* __restrict__ probs, const GemmTile* __restrict
 template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 gemm_kernel_v3(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles,
-               const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase) {
+               const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase,
+            double alpha, int accum) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   using TileA = OpTile<BM, BK, TA>;
   using TileB = OpTile<BN, BK, !TB>;
@@ -420,15 +425,16 @@ gemm_kernel_v3(const GemmProblem* __restrict__ probs, const GemmTile* __restrict
     for (int j = 0; j < NI; j++) {
       int n = n0 + wn0 + j * 8 + 2 * lc;
       double* c = pC + (int64_t)n * p.ldc + m;
-      if (n < p.N) c[0] = acc[i][j][0];
-      if (n + 1 < p.N) c[p.ldc] = acc[i][j][1];
+      // C = alpha * A B (+ C): alpha = +-1 and the accumulate mode serve the planar complex products
+      if (n < p.N) c[0] = accum ? fma(alpha, acc[i][j][0], c[0]) : alpha * acc[i][j][0];
+      if (n + 1 < p.N) c[p.ldc] = accum ? fma(alpha, acc[i][j][1], c[p.ldc]) : alpha * acc[i][j][1];
     }
   }
 }
 
 template <int VER, int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
 static void launch_gemm_one(Ctx* ctx, const GemmProblem* probs, const GemmTile* tiles, int ntiles,
-                            const double* A, const double* B, double* C) {
+                            const double* A, const double* B, double* C, double alpha, int accum) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr size_t SMEM = sizeof(double) * STAGES * (OpTile<BM, BK, TA>::ELEMS + OpTile<BN, BK, !TB>::ELEMS);
   auto kern = VER == 3 ? gemm_kernel_v3<BM, BN, BK, WM, WN, TA, TB, STAGES>
@@ -438,7 +444,7 @@ static void launch_gemm_one(Ctx* ctx, const GemmProblem* probs, const GemmTile* 
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     configured = true;
   }
-  kern<<<ntiles, NT, SMEM, ctx->stream>>>(probs, tiles, A, B, C);
+  kern<<<ntiles, NT, SMEM, ctx->stream>>>(probs, tiles, A, B, C, alpha, accum);
   CUDA_OK(cudaGetLastError());
   ctx->cnt.launches++;
   ctx->cnt.gemm_launches++;
@@ -446,16 +452,17 @@ static void launch_gemm_one(Ctx* ctx, const GemmProblem* probs, const GemmTile* 
 
 template <int VER, int BM, int BN, int BK, int WM, int WN, int STAGES>
 static void launch_gemm_cfg(Ctx* ctx, bool ta, bool tb, const GemmProblem* probs, const GemmTile* tiles, int ntiles,
-                            const double* A, const double* B, double* C) {
+                            const double* A, const double* B, double* C, double alpha = 1.0, int accum = 0) {
   if (ntiles == 0) return;
-  if (!ta && !tb) launch_gemm_one<VER, BM, BN, BK, WM, WN, false, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
-  else if (!ta && tb) launch_gemm_one<VER, BM, BN, BK, WM, WN, false, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
-  else if (ta && !tb) launch_gemm_one<VER, BM, BN, BK, WM, WN, true, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
-  else launch_gemm_one<VER, BM, BN, BK, WM, WN, true, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C);
+  if (!ta && !tb) launch_gemm_one<VER, BM, BN, BK, WM, WN, false, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
+  else if (!ta && tb) launch_gemm_one<VER, BM, BN, BK, WM, WN, false, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
+  else if (ta && !tb) launch_gemm_one<VER, BM, BN, BK, WM, WN, true, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
+  else launch_gemm_one<VER, BM, BN, BK, WM, WN, true, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
 }
 
-void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C) {
-  for (auto& z : p.zero_fill) CUDA_OK(cudaMemsetAsync(C + z.first, 0, z.second * sizeof(double), ctx->stream));
+void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C, double alpha, bool accum) {
+  if (!accum)
+    for (auto& z : p.zero_fill) CUDA_OK(cudaMemsetAsync(C + z.first, 0, z.second * sizeof(double), ctx->stream));
   Ctx::ProfRec rec{};
   const bool prof = ctx->prof_gemm && !p.tiles_big.empty();
   if (prof) {
@@ -465,20 +472,20 @@ void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C
   }
   const int nb = (int)p.tiles_big.size();
   switch (ctx->gemm_variant) {
-    case 1: launch_gemm_cfg<1, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    case 4: launch_gemm_cfg<2, 128, 128, 16, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    case 5: launch_gemm_cfg<2, 128, 128, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    case 6: launch_gemm_cfg<2, 128, 128, 32, 32, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    case 7: launch_gemm_cfg<2, 128, 128, 32, 32, 64, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    case 8: launch_gemm_cfg<3, 128, 128, 32, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    case 11: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 6>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    case 2: launch_gemm_cfg<2, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    case 3: launch_gemm_cfg<2, 128, 128, 32, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    case 9: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 5>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    case 12: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
-    default: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C); break;
+    case 1: launch_gemm_cfg<1, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
+    case 4: launch_gemm_cfg<2, 128, 128, 16, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
+    case 5: launch_gemm_cfg<2, 128, 128, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
+    case 6: launch_gemm_cfg<2, 128, 128, 32, 32, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
+    case 7: launch_gemm_cfg<2, 128, 128, 32, 32, 64, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
+    case 8: launch_gemm_cfg<3, 128, 128, 32, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
+    case 11: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 6>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
+    case 2: launch_gemm_cfg<2, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
+    case 3: launch_gemm_cfg<2, 128, 128, 32, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
+    case 9: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 5>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
+    case 12: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
+    default: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
   }
-  launch_gemm_cfg<1, 64, 64, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_small, (int)p.tiles_small.size(), A, B, C);
+  launch_gemm_cfg<1, 64, 64, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_small, (int)p.tiles_small.size(), A, B, C, alpha, accum ? 1 : 0);
   if (prof) {
     CUDA_OK(cudaEventRecord(rec.b, ctx->stream));
     rec.flops = p.flops;
@@ -938,6 +945,160 @@ void vec_lincomb(Ctx* ctx, double* y, const double* const* xs, const double* coe
   ctx->cnt.launches++;
   ctx->cnt.vec_bytes += (k + 1.0) * n * 8.0;
 }
+// ---- planar complex vectors: [re plane | im plane], each `n` doubles -----------------------------
+// <x, y> = sum conj(x) y : out[0] = re, out[1] = im; same deterministic two-level reduction as dot_kernel
+__global__ void __launch_bounds__(VT)
+cdot_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n2, int64_t plane2,
+            double* __restrict__ partials, unsigned int* __restrict__ sync, double* __restrict__ out) {
+  const double2* xr = reinterpret_cast<const double2*>(x);
+  const double2* yr = reinterpret_cast<const double2*>(y);
+  const double2* xi = xr + plane2;
+  const double2* yi = yr + plane2;
+  double sr = 0.0, si = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * VT;
+  for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += stride) {
+    const double2 a = xr[i], b = xi[i], c = yr[i], d = yi[i];
+    sr = fma(a.x, c.x, sr); sr = fma(a.y, c.y, sr); sr = fma(b.x, d.x, sr); sr = fma(b.y, d.y, sr);
+    si = fma(a.x, d.x, si); si = fma(a.y, d.y, si); si = fma(-b.x, c.x, si); si = fma(-b.y, c.y, si);
+  }
+  sr = warp_sum(sr);
+  si = warp_sum(si);
+  __shared__ double ws[2][VT / 32];
+  __shared__ bool last;
+  if ((threadIdx.x & 31) == 0) { ws[0][threadIdx.x >> 5] = sr; ws[1][threadIdx.x >> 5] = si; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int w = 0; w < VT / 32; w++) { t0 += ws[0][w]; t1 += ws[1][w]; }
+    partials[2 * blockIdx.x] = t0;
+    partials[2 * blockIdx.x + 1] = t1;
+    __threadfence();
+    unsigned int done = atomicAdd(sync, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double t0 = 0.0, t1 = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += VT) { t0 += partials[2 * b]; t1 += partials[2 * b + 1]; }
+    t0 = warp_sum(t0);
+    t1 = warp_sum(t1);
+    if ((threadIdx.x & 31) == 0) { ws[0][threadIdx.x >> 5] = t0; ws[1][threadIdx.x >> 5] = t1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r0 = 0.0, r1 = 0.0;
+      for (int w = 0; w < VT / 32; w++) { r0 += ws[0][w]; r1 += ws[1][w]; }
+      out[0] = r0;
+      out[1] = r1;
+      *sync = 0u;
+    }
+  }
+}
+
+// y += s x with s = sign * (sdev[0] + i sdev[1]) or (ar + i ai)
+__global__ void __launch_bounds__(VT)
+caxpy_kernel(double* __restrict__ y, const double* __restrict__ x, int64_t n2, int64_t plane2,
+             const double* __restrict__ sdev, double ar, double ai) {
+  const double sr = sdev ? ar * sdev[0] : ar;
+  const double si = sdev ? ar * sdev[1] : ai;
+  double2* yr = reinterpret_cast<double2*>(y);
+  double2* yi = yr + plane2;
+  const double2* xr = reinterpret_cast<const double2*>(x);
+  const double2* xi = xr + plane2;
+  const int64_t stride = (int64_t)gridDim.x * VT;
+  for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += stride) {
+    const double2 a = xr[i], b = xi[i];
+    double2 c = yr[i], d = yi[i];
+    c.x = fma(sr, a.x, c.x); c.x = fma(-si, b.x, c.x); c.y = fma(sr, a.y, c.y); c.y = fma(-si, b.y, c.y);
+    d.x = fma(sr, b.x, d.x); d.x = fma(si, a.x, d.x); d.y = fma(sr, b.y, d.y); d.y = fma(si, a.y, d.y);
+    yr[i] = c;
+    yi[i] = d;
+  }
+}
+
+struct CLincombArgs { const double* x[LC_MAX]; double cr[LC_MAX]; double ci[LC_MAX]; int k; };
+__global__ void __launch_bounds__(VT)
+clincomb_kernel(double* __restrict__ y, CLincombArgs a, int64_t n2, int64_t plane2) {
+  double2* yr = reinterpret_cast<double2*>(y);
+  double2* yi = yr + plane2;
+  const int64_t stride = (int64_t)gridDim.x * VT;
+  for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += stride) {
+    double2 r = make_double2(0.0, 0.0), m = make_double2(0.0, 0.0);
+    for (int j = 0; j < a.k; j++) {
+      const double2 vr = reinterpret_cast<const double2*>(a.x[j])[i];
+      const double2 vi = reinterpret_cast<const double2*>(a.x[j])[i + plane2];
+      r.x = fma(a.cr[j], vr.x, r.x); r.x = fma(-a.ci[j], vi.x, r.x);
+      r.y = fma(a.cr[j], vr.y, r.y); r.y = fma(-a.ci[j], vi.y, r.y);
+      m.x = fma(a.cr[j], vi.x, m.x); m.x = fma(a.ci[j], vr.x, m.x);
+      m.y = fma(a.cr[j], vi.y, m.y); m.y = fma(a.ci[j], vr.y, m.y);
+    }
+    yr[i] = r;
+    yi[i] = m;
+  }
+}
+
+void vec_cdot(Ctx* ctx, const double* x, const double* y, int64_t n, int slot) {
+  Ctx::Scope prof_scope(ctx, 2);
+  TNL_CHECK(n % 2 == 0, "padded vector length must be even");
+  cdot_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(x, y, n / 2, n / 2, ctx->d_partials, ctx->d_sync, ctx->d_scalars + slot);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.vec_bytes += (x == y ? 1.0 : 2.0) * n * 16.0;
+}
+void vec_caxpy_dev(Ctx* ctx, double* y, const double* x, int64_t n, int slot, double sign) {
+  Ctx::Scope prof_scope(ctx, 2);
+  caxpy_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(y, x, n / 2, n / 2, ctx->d_scalars + slot, sign, 0.0);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.vec_bytes += 3.0 * n * 16.0;
+}
+void vec_caxpy(Ctx* ctx, double* y, const double* x, int64_t n, double ar, double ai) {
+  Ctx::Scope prof_scope(ctx, 2);
+  caxpy_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(y, x, n / 2, n / 2, nullptr, ar, ai);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.vec_bytes += 3.0 * n * 16.0;
+}
+void vec_clincomb(Ctx* ctx, double* y, const double* const* xs, const double* cr, const double* ci, int k, int64_t n) {
+  Ctx::Scope prof_scope(ctx, 2);
+  TNL_CHECK(k <= LC_MAX, "too many vectors in linear combination");
+  CLincombArgs a;
+  a.k = k;
+  for (int j = 0; j < k; j++) { a.x[j] = xs[j]; a.cr[j] = cr[j]; a.ci[j] = ci[j]; }
+  clincomb_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(y, a, n / 2, n / 2);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.vec_bytes += (k + 1.0) * n * 16.0;
+}
+
+// C = op(A) op(B) for any mix of real and planar-complex operands (Ai / Bi == nullptr: real operand);
+// conjA / conjB conjugate a complex operand.  Four (two, one) launches of the real grouped DGEMM:
+//   Cr = Ar Br - sA sB Ai Bi ,  Ci = sB Ar Bi + sA Ai Br      (sX = -1 if conjX)
+void cgemm(Ctx* ctx, GemmPlan& p, const double* Ar, const double* Ai, bool conjA, const double* Br, const double* Bi,
+           bool conjB, double* Cr, double* Ci) {
+  const double sA = conjA ? -1.0 : 1.0, sB = conjB ? -1.0 : 1.0;
+  run_gemm(ctx, p, Ar, Br, Cr, 1.0, false);
+  if (Ai && Bi) run_gemm(ctx, p, Ai, Bi, Cr, -sA * sB, true);
+  if (!Ci) { TNL_CHECK(!Ai && !Bi, "complex product needs a complex result"); return; }
+  bool first = true;
+  if (Bi) { run_gemm(ctx, p, Ar, Bi, Ci, sB, false); first = false; }
+  if (Ai) { run_gemm(ctx, p, Ai, Br, Ci, sA, !first); first = false; }
+  if (first) {   // both operands real: the imaginary plane of the result is zero on every problem
+    for (const GemmProblem& q : p.probs)
+      for (int n = 0; n < q.N; n++) CUDA_OK(cudaMemsetAsync(Ci + q.c + (int64_t)n * q.ldc, 0, (size_t)q.M * sizeof(double), ctx->stream));
+  }
+}
+void cgemm(Ctx* ctx, GemmPlan& p, const Tensor& A, bool conjA, const Tensor& B, bool conjB, Tensor& C) {
+  TNL_CHECK(C.cplx == (A.cplx || B.cplx), "result of a contraction is complex iff an operand is");
+  cgemm(ctx, p, A.d, A.cplx ? A.im() : nullptr, conjA, B.d, B.cplx ? B.im() : nullptr, conjB, C.d, C.cplx ? C.im() : nullptr);
+}
+// transform of both planes (W real)
+void run_transform_c(Ctx* ctx, TransformPlan& p, const Tensor& X, Tensor& Y, const double* W) {
+  TNL_CHECK(X.cplx == Y.cplx, "transform keeps the element type");
+  run_transform(ctx, p, X.d, Y.d, W);
+  if (X.cplx) run_transform(ctx, p, X.im(), Y.im(), W);
+}
+
 void fetch_scalars(Ctx* ctx, int n) {
   CUDA_OK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));

@@ -59,8 +59,11 @@ class HostTensor:
         self.inds = list(inds)
         self.blocks = {} if blocks is None else blocks
 
+    def is_complex(self) -> bool:
+        return any(np.iscomplexobj(b) for b in self.blocks.values())
+
     def to_dense(self):
-        out = np.zeros([ix.dim for ix in self.inds])
+        out = np.zeros([ix.dim for ix in self.inds], dtype=np.complex128 if self.is_complex() else np.float64)
         offs = [np.concatenate([[0], np.cumsum(ix.dims)]) for ix in self.inds]
         for c, b in self.blocks.items():
             out[tuple(slice(o[k], o[k + 1]) for o, k in zip(offs, c))] = b
@@ -83,8 +86,9 @@ def _index_array(inds):
     return arr, nq, keep
 
 
-def flatten_blocks(t):
-    """NDTensors flat layout: (coords[nb,rank] i32, offsets[nb] i64, data f64), blocks column-major."""
+def flatten_blocks(t, dtype=np.float64):
+    """NDTensors flat layout: (coords[nb,rank] i32, offsets[nb] i64, data), blocks column-major; `dtype`
+    complex128 gives the interleaved (re, im) ComplexF64 storage, offsets counting complex elements."""
     keys = list(t.blocks.keys())
     rank = len(t.inds)
     coords = np.zeros((max(len(keys), 1), rank), dtype=np.int32)
@@ -93,10 +97,10 @@ def flatten_blocks(t):
     for n, c in enumerate(keys):
         coords[n] = c
         offsets[n] = off
-        b = np.asarray(t.blocks[c], dtype=np.float64)
+        b = np.asarray(t.blocks[c], dtype=dtype)
         chunks.append(b.reshape(-1, order="F"))
         off += b.size
-    data = np.ascontiguousarray(np.concatenate(chunks)) if chunks else np.zeros(1)
+    data = np.ascontiguousarray(np.concatenate(chunks)) if chunks else np.zeros(1, dtype=dtype)
     return coords[:len(keys)] if keys else coords[:0], offsets[:len(keys)], data, len(keys)
 
 
@@ -190,10 +194,12 @@ class DeviceTensor:
     @staticmethod
     def from_host(ctx: Context, t, nrow: int = 1) -> "DeviceTensor":
         arr, nq, keep = _index_array(t.inds)
-        coords, offsets, data, nb = flatten_blocks(t)
+        cplx = any(np.iscomplexobj(b) for b in t.blocks.values())
+        coords, offsets, data, nb = flatten_blocks(t, np.complex128 if cplx else np.float64)
         h = C.c_void_p()
-        check(ctx.lib.tnl_tensor_import(ctx.h, len(t.inds), nq, arr, nb, coords.ctypes.data, offsets.ctypes.data,
-                                        data.ctypes.data, nrow, C.byref(h)), ctx.h)
+        fn = ctx.lib.tnl_tensor_import_c128 if cplx else ctx.lib.tnl_tensor_import
+        check(fn(ctx.h, len(t.inds), nq, arr, nb, coords.ctypes.data, offsets.ctypes.data, data.ctypes.data, nrow,
+                 C.byref(h)), ctx.h)
         return DeviceTensor(ctx, h, t.inds)
 
     @staticmethod
@@ -234,6 +240,16 @@ class DeviceTensor:
                 out.append(Index(qn, dims, dir=dr.value))
         return out
 
+    def is_complex(self) -> bool:
+        out = C.c_int32()
+        check(self.ctx.lib.tnl_tensor_is_complex(self.h, C.byref(out)), self.ctx.h)
+        return bool(out.value)
+
+    def promote_(self):
+        """real -> ComplexF64 (zero imaginary part), in place"""
+        check(self.ctx.lib.tnl_tensor_promote(self.h), self.ctx.h)
+        return self
+
     def to_host(self, drop_zero_blocks: bool = False) -> HostTensor:
         lib = self.ctx.lib
         nb, ne = C.c_int64(), C.c_int64()
@@ -242,7 +258,7 @@ class DeviceTensor:
         rank = len(inds)
         coords = np.zeros((max(nb.value, 1), rank), dtype=np.int32)
         offsets = np.zeros(max(nb.value, 1), dtype=np.int64)
-        data = np.zeros(max(ne.value, 1), dtype=np.float64)
+        data = np.zeros(max(ne.value, 1), dtype=np.complex128 if self.is_complex() else np.float64)
         check(lib.tnl_tensor_export(self.h, coords.ctypes.data, offsets.ctypes.data, data.ctypes.data), self.ctx.h)
         t = HostTensor(inds)
         for n in range(nb.value):
@@ -270,10 +286,11 @@ class DeviceTensor:
         check(self.ctx.lib.tnl_vec_norm(self.h, C.byref(out)), self.ctx.h)
         return out.value
 
-    def dot(self, other: "DeviceTensor") -> float:
-        out = C.c_double()
-        check(self.ctx.lib.tnl_vec_dot(self.h, other.h, C.byref(out)), self.ctx.h)
-        return out.value
+    def dot(self, other: "DeviceTensor"):
+        """<self, other> = sum conj(self) other; a complex number for complex tensors."""
+        re, im = C.c_double(), C.c_double()
+        check(self.ctx.lib.tnl_vec_dot_c(self.h, other.h, C.byref(re), C.byref(im)), self.ctx.h)
+        return complex(re.value, im.value) if self.is_complex() else re.value
 
     def scale_(self, a: float):
         check(self.ctx.lib.tnl_vec_scale(self.h, float(a)), self.ctx.h)

@@ -650,3 +650,159 @@ def test_dynamic_tdvp_and_penalty_on_coupling_model(ctx):
     assert abs(E0d - E0o) < 1e-10 * abs(E0o)
     assert abs(E1d - E1o) < 1e-8 * abs(E1o)
     assert abs(E1d - (-2.9822404877)) < 1e-6          # ED: first excited state of S=1/2 N=8 in the Sz=0 sector
+
+
+# ---------------------------------------------------------------------------------------------- ComplexF64 (planar)
+def _complexify(mps, seed):
+    """Random complex MPS with the block structure of a real one (same indices)."""
+    rng = np.random.default_rng(seed)
+    for j, A in enumerate(mps.t):
+        blocks = {c: b * (rng.standard_normal(b.shape) + 1j * rng.standard_normal(b.shape)) for c, b in A.blocks.items()}
+        mps.t[j] = type(A)(A.inds, blocks, np.complex128)
+    return mps
+
+
+def test_complex_tensor_roundtrip_and_vector_interface(ctx):
+    T, ob, od, ok, om, op = _imports()
+    _, _, mps = _setup(om, od, "S=1", 8, 24, 3, 1)
+    _complexify(mps, 5)
+    A, B = mps[4], mps[4].scale(0.5 - 0.25j)
+    for nrow in (1, 2, 3):
+        d = T.DeviceTensor.from_host(ctx, A, nrow=nrow)
+        assert d.is_complex()
+        assert np.array_equal(d.to_host().to_dense(), A.to_dense())
+    x, y = T.DeviceTensor.from_host(ctx, A, 1), T.DeviceTensor.from_host(ctx, B, 1)
+    ref = ob.inner(A, B)
+    assert abs(x.dot(y) - ref) < 1e-13 * abs(ref)
+    assert abs(x.norm() - A.norm()) < 1e-13 * A.norm()
+    y.axpy_(x, -0.3).scale_(2.0)
+    assert rel(y.to_host().to_dense(), B.add(A, -0.3).scale(2.0).to_dense()) < 1e-15
+    r = T.DeviceTensor.from_host(ctx, _setup(om, od, "S=1", 8, 24, 3, 1)[2][4], 1)
+    assert not r.is_complex() and r.promote_().is_complex()
+
+
+@pytest.mark.parametrize("model", ["mpo", "cm"])
+def test_complex_environments_and_apply_match_oracle(ctx, model):
+    """Complex MPS: environments L = L A W conj(A), H_eff apply for two-, one- and zero-site vectors, expectation."""
+    T, ob, od, ok, om, op = _imports()
+    from oracle import couplingmodel as oc
+    N = 8
+    sites, H, mps = _setup(om, od, "S=1", N, 16, 3, 1)
+    if model == "cm":
+        H = oc.heisenberg_coupling_model(sites, merge=True, j2=0.3)
+    _complexify(mps, 7)
+    od.orthogonalize(mps, 4)
+    env_o = od.StateEnvs(mps, H)
+    env_d = T.StateEnvs(ctx, mps.t, H, llim=3, rlim=5)
+    for nsite, pos in ((2, 4), (2, 1), (2, N - 1), (1, 4)):
+        od.orthogonalize(env_o.psi, pos)
+        env_d = T.StateEnvs(ctx, env_o.psi.t, H, llim=pos - 1, rlim=pos + 1)
+        env_o.PH.lpos, env_o.PH.rpos = 0, N + 1
+        env_o.set_nsite(nsite); env_o.position(pos)
+        env_d.set_nsite(nsite); env_d.position(pos)
+        phi_o = ob.contract(env_o.psi[pos], env_o.psi[pos + 1]) if nsite == 2 else env_o.psi[pos]
+        phi_d = env_d.make_phi(pos) if nsite == 2 else env_d.site_tensor(pos)
+        assert rel(phi_d.to_host().to_dense(), phi_o.to_dense()) < 1e-13
+        ref = env_o.product(phi_o).permute(phi_o.inds).to_dense()
+        assert rel(env_d.product(phi_d).to_host().to_dense(), ref) < 1e-12
+        e_ref = ob.inner(phi_o, env_o.product(phi_o))
+        assert abs(env_d.expectation(phi_d) - e_ref.real) < 1e-11 * abs(e_ref) and abs(e_ref.imag) < 1e-10 * abs(e_ref)
+    # zero-site
+    od.orthogonalize(env_o.psi, 4)
+    v4 = env_o.psi[4]
+    Lf, Rf, spec, u = ob.factorize(v4, v4.inds[:2], ortho="left", which_decomp="svd", cutoff=0.0)
+    env_o.psi[4] = Lf
+    env_o.PH.lpos, env_o.PH.rpos = 0, N + 1
+    env_d = T.StateEnvs(ctx, env_o.psi.t, H, llim=4, rlim=6)
+    env_o.set_nsite(0); env_o.position(5)
+    env_d.set_nsite(0); env_d.position(5)
+    Cd = T.DeviceTensor.from_host(ctx, Rf, 1)
+    assert rel(env_d.product(Cd).to_host().to_dense(), env_o.product(Rf).permute(Rf.inds).to_dense()) < 1e-12
+
+
+@pytest.mark.parametrize("nsite,t", [(2, -0.1j), (1, 0.05j), (2, -0.05 - 0.08j), (0, 0.07j)])
+def test_exp_solver_complex_time_matches_oracle(ctx, nsite, t):
+    """Real-time evolution exp(-i dt H_eff): a real vector is promoted to ComplexF64 on the device."""
+    T, ob, od, ok, om, op = _imports()
+    sites, H, mps = _setup(om, od, "S=1", 8, 24, 3, 4)
+    env_o = od.StateEnvs(mps, H)
+    pos = 4
+    if nsite == 0:
+        v_o = env_o.psi[4]
+        L, R, spec, u = ob.factorize(v_o, v_o.inds[:2], ortho="left", which_decomp="svd", cutoff=0.0)
+        env_o.psi[4] = L
+        phi_o, pos = R, 5
+        env_d = T.StateEnvs(ctx, env_o.psi.t, H, llim=4, rlim=6)
+    else:
+        env_d = T.StateEnvs(ctx, mps.t, H, llim=3, rlim=5)
+        phi_o = ob.contract(env_o.psi[4], env_o.psi[5]) if nsite == 2 else env_o.psi[4]
+    env_o.set_nsite(nsite); env_o.position(pos)
+    env_d.set_nsite(nsite); env_d.position(pos)
+    phi_d = T.DeviceTensor.from_host(ctx, phi_o, 1)
+    _, out_o = od.exp_solver(env_o, phi_o, t)
+    _, out_d = T.exp_solver(env_d, phi_d, t)
+    assert out_d.is_complex()
+    assert env_d.last_solver_info["converged"] == 1
+    assert abs(env_d.last_solver_info["numops"] - od.exp_solver.last_info["numops"]) <= 1
+    assert rel(out_d.to_host().to_dense(), out_o.permute(phi_o.inds).to_dense()) < 1e-10
+    if t.real == 0:
+        assert abs(out_d.norm() - phi_o.norm()) < 1e-11 * phi_o.norm()          # unitary
+
+
+@pytest.mark.parametrize("ortho", ["left", "right"])
+def test_complex_replacebond_matches_oracle(ctx, ortho):
+    """Truncation of a complex two-site tensor through the Hermitian eigenproblem of M M^+ / M^+ M: kept spectrum,
+    truncation error, new link sectors; the factors are compared through their product and isometry."""
+    T, ob, od, ok, om, op = _imports()
+    sites, H, mps = _setup(om, od, "S=1", 8, 24, 3, 4)
+    _complexify(mps, 11)
+    od.orthogonalize(mps, 4)
+    pos = 4 if ortho == "left" else 3
+    env_d = T.StateEnvs(ctx, mps.t, H, llim=3, rlim=5)
+    env_d.set_nsite(2)
+    phi_d = env_d.make_phi(pos)
+    phi_o = ob.contract(mps[pos], mps[pos + 1])
+    phi_o = phi_o.scale(1.0 / phi_o.norm())
+    phi_d.scale_(1.0 / phi_d.norm())
+    psi_o = mps.copy()
+    spec = od.replacebond(psi_o, pos, phi_o, maxdim=12, mindim=1, cutoff=1e-13, eigen_perturbation=None, ortho=ortho,
+                          normalize=True)
+    terr, eigs = env_d.replacebond(pos, phi_d, maxdim=12, mindim=1, cutoff=1e-13, noise=0.0, ortho=ortho, normalize=True)
+    assert len(eigs) == len(spec.eigs) and abs(terr - spec.truncerr) < 1e-12
+    assert np.allclose(eigs, spec.eigs, rtol=0, atol=1e-12)
+    Ad, Bd = env_d.site_tensor(pos).to_host(), env_d.site_tensor(pos + 1).to_host()
+    assert [ix.dims for ix in Ad.inds] == [ix.dims for ix in psi_o[pos].inds]
+    two_d = np.tensordot(Ad.to_dense(), Bd.to_dense(), axes=([2], [0]))
+    two_o = np.tensordot(psi_o[pos].to_dense(), psi_o[pos + 1].to_dense(), axes=([2], [0]))
+    assert rel(two_d, two_o) < 1e-10                                          # gauge-invariant product
+    iso = Ad.to_dense() if ortho == "left" else Bd.to_dense()
+    m = iso.reshape(-1, iso.shape[2]) if ortho == "left" else iso.reshape(iso.shape[0], -1).T
+    assert np.abs(m.conj().T @ m - np.eye(m.shape[1])).max() < 1e-12
+
+
+@pytest.mark.parametrize("nsite", [2, 1])
+def test_tdvp_real_time_matches_oracle_and_exact_evolution(ctx, nsite):
+    """tdvpsweep!(engine, -im*dt) (the reference's TDVP test step, test/test_MPS_TDVP.jl:50-56): energies per sweep
+    against the oracle, energy conservation, and the state against exp(-i t H)|Neel> from dense linear algebra."""
+    import scipy.linalg as sl
+    T, ob, od, ok, om, op = _imports()
+    N = 8
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites)
+    psi0 = od.MPS(om.neel_mps(sites))
+    eng_o, eng_d = od.TDVPEngine(psi0, H), T.TDVPEngine(ctx, psi0.t, H)
+    sched = [2, 2] + [nsite] * 3
+    dt = 0.05
+    for ns in sched:
+        od.tdvpsweep(eng_o, -1j * dt, ns, maxdim=16, cutoff=1e-13)
+        T.tdvpsweep(eng_d, -1j * dt, ns, maxdim=16, cutoff=1e-13, outputlevel=0)
+    assert eng_d.swdata.maxchi == eng_o.swdata.maxchi
+    assert np.allclose(eng_d.swdata.energy, eng_o.swdata.energy, rtol=1e-10, atol=0)
+    assert np.allclose(eng_d.swdata.maxtruncerr, eng_o.swdata.maxtruncerr, rtol=0, atol=1e-12)
+    assert max(abs(e - eng_d.swdata.energy[0]) for e in eng_d.swdata.energy) < 1e-8      # unitary evolution
+    Hd = om.mpo_to_dense(H)
+    v = sl.expm(-1j * dt * len(sched) * Hd) @ om.mps_to_dense(psi0.t)
+    w = om.mps_to_dense(eng_d.getpsi())
+    assert abs(abs(np.vdot(v, w)) - 1.0) < 1e-8
+    wo = om.mps_to_dense(eng_o.sysenv.psi.t)
+    assert abs(abs(np.vdot(wo, w)) - 1.0) < 1e-10
