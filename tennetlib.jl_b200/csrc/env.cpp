@@ -1574,6 +1574,20 @@ static const Env::CM::Op& cm_filler(Ctx* ctx, Env::CM& cm, const Index& site_ket
 
 static bool same_space_dag(const Index& a, const Index& b) { return a.dims == b.dims && a.qns == b.qns && a.dir == -b.dir; }
 
+// local_tensor += phidag (src/mps/projcouplingmodel.jl:170-189): same layout for every contribution; a real
+// accumulator meeting a complex contribution is promoted first
+static void add_local(Ctx* ctx, TensorP& local, const TensorP& t) {
+  if (!local) { local = t; return; }
+  TNL_CHECK(local->nelem == t->nelem, "local environment layouts differ");
+  if (t->cplx && !local->cplx) {
+    auto n = std::make_shared<Tensor>(ctx, local->inds, local->nrow, true, true);
+    vec_copy(ctx, n->d, local->d, local->nelem);
+    local = n;
+  }
+  vec_axpy(ctx, local->d, t->d, t->planes() * t->nelem, 1.0);
+  ctx->sync();
+}
+
 // ProjCouplingModel._makeL! (src/mps/projcouplingmodel.jl:123-196)
 void Env::cm_makeL(int k) {
   int ll = lpos;
@@ -1607,12 +1621,7 @@ void Env::cm_makeL(int k) {
       TensorP Ln = step_left(Lid, A[ll], *op->Wlr);
       if (!open) {
         TNL_CHECK(is_trivial_link(Ln->inds[1]), "CouplingModel: closed term with a non-trivial link");
-        if (!local) local = Ln;
-        else {
-          TNL_CHECK(local->nelem == Ln->nelem, "local environment layouts differ");
-          vec_axpy(ctx, local->d, Ln->d, Ln->nelem, 1.0);
-          ctx->sync();
-        }
+        add_local(ctx, local, Ln);
       } else {
         next[id] = CM::E{Ln, true};
       }
@@ -1658,12 +1667,7 @@ void Env::cm_makeR(int k) {
       TensorP Rn = step_right(Rid, A[j], *op->Wrl);
       if (!open) {
         TNL_CHECK(is_trivial_link(Rn->inds[1]), "CouplingModel: closed term with a non-trivial link");
-        if (!local) local = Rn;
-        else {
-          TNL_CHECK(local->nelem == Rn->nelem, "local environment layouts differ");
-          vec_axpy(ctx, local->d, Rn->d, Rn->nelem, 1.0);
-          ctx->sync();
-        }
+        add_local(ctx, local, Rn);
       } else {
         next[id] = CM::E{Rn, true};
       }

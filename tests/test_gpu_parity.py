@@ -412,7 +412,7 @@ def test_exp_solver_substeps_when_the_basis_is_full(ctx):
     assert rel(out_d.to_host().to_dense(), out_o.permute(phi_o.inds).to_dense()) < 1e-9
 
 
-def test_exp_solver_rejects_complex_steps_and_missing_step(ctx):
+def test_exp_solver_missing_step_and_promotion(ctx):
     T, ob, od, ok, om, op = _imports()
     sites, H, mps = _setup(om, od, "S=1", 6, 12, 5, 3)
     env_d = T.StateEnvs(ctx, mps.t, H, llim=2, rlim=4)
@@ -420,8 +420,10 @@ def test_exp_solver_rejects_complex_steps_and_missing_step(ctx):
     phi = env_d.make_phi(3)
     with pytest.raises(RuntimeError):
         T.exp_solver(env_d, phi, None)
-    with pytest.raises(T.TnlError, match="complex"):
-        T.exp_solver(env_d, phi, -0.05j)
+    assert not phi.is_complex()
+    n0 = phi.norm()
+    _, out = T.exp_solver(env_d, phi, -0.05j)            # real-time step: the vector is promoted to ComplexF64
+    assert out.is_complex() and abs(out.norm() - n0) < 1e-11 * n0
 
 
 @pytest.mark.parametrize("nsite", [2, 1])
