@@ -4,7 +4,7 @@
 # Usage:   using TenNetLib, TenNetLibB200;  TenNetLibB200.enable!(sysenv)   # then dmrg!(sysenv, params, 2) as usual
 #
 # The shim adds a MORE SPECIFIC method of TenNetLib._update_two_site! for StateEnvs{ProjMPO} whose state lives
-# on the device, so dmrg!/fullsweep!/update_position! source runs unchanged (src/mps/update_site.jl:27-90,231-277).
+# on the device, so dmrg!/fullsweep!/tdvpsweep!/update_position! source runs unchanged (src/mps/update_site.jl:27-90,231-277).
 module TenNetLibB200
 
 using ITensors, ITensorMPS, TenNetLib
@@ -113,6 +113,59 @@ function TenNetLib._update_two_site!(sysenv::StateEnvs{ProjMPO}, solver::typeof(
                       (ITensorMPS.setleftlim!(sysenv.psi, pos - 1); ITensorMPS.setrightlim!(sysenv.psi, pos + 1))
     return ev[], terr[], eigs[1:ne[]]                                                                          # :89
 end
+
+# ---- TDVP: the same local update with exp_solver and the backward one-site step (src/mps/update_site.jl:78-87) --
+function TenNetLib._update_two_site!(sysenv::StateEnvs{ProjMPO}, solver::typeof(TenNetLib.exp_solver), pos::Int,
+        ortho::String, time_step::Union{Float64,ComplexF64}, normalize::Bool, maxdim::Int, mindim::Int, cutoff::Float64,
+        svd_alg::String, noise::Float64, reverse_step::Bool; kwargs...)
+    d = DEVICES[sysenv]
+    expo(phi, t) = begin
+        conv = Ref{Int32}(); nops = Ref{Int32}(); nit = Ref{Int32}(); err = Ref{Float64}()
+        check(ccall((:tnl_exponentiate, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Float64, Int32, Int32, Int32, Ref{Int32}, Ref{Int32}, Ref{Int32}, Ref{Float64}),
+            d.env, phi, real(t), imag(t), get(kwargs, :solver_tol, 1E-12), get(kwargs, :solver_krylovdim, 30),
+            get(kwargs, :solver_maxiter, 100), get(kwargs, :solver_eager, true) ? 1 : 0, conv, nops, nit, err), d.ctx)
+        get(kwargs, :solver_check_convergence, false) && conv[] < 1 && error("`eig_solver()` not converged !!")
+    end
+    normed(phi) = begin
+        nrm = Ref{Float64}(); check(ccall((:tnl_vec_norm, LIB), Cint, (Ptr{Cvoid}, Ref{Float64}), phi, nrm), d.ctx)
+        normalize && check(ccall((:tnl_vec_scale, LIB), Cint, (Ptr{Cvoid}, Float64), phi, 1 / nrm[]), d.ctx)
+    end
+    energy(phi) = begin
+        e = Ref{Float64}(); check(ccall((:tnl_expectation, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Float64}), d.env, phi, e), d.ctx); e[]
+    end
+    check(ccall((:tnl_env_set_nsite, LIB), Cint, (Ptr{Cvoid}, Int32), d.env, 2), d.ctx)
+    phi = Ref{Ptr{Cvoid}}()
+    check(ccall((:tnl_env_make_phi, LIB), Cint, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), d.env, pos, phi), d.ctx)
+    check(ccall((:tnl_env_position, LIB), Cint, (Ptr{Cvoid}, Int32), d.env, pos), d.ctx)
+    expo(phi[], time_step); normed(phi[]); en = energy(phi[])                                                  # :48-57
+    eigs = Vector{Float64}(undef, 65536); terr = Ref{Float64}(); ne = Ref{Int64}()
+    check(ccall((:tnl_replacebond, LIB), Cint,
+        (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int32, Int64, Int64, Float64, Float64, Int32, Int32, Ref{Float64}, Ptr{Float64}, Int64, Ref{Int64}),
+        d.env, pos, phi[], ortho == "left" ? 1 : 0, maxdim == typemax(Int) ? 0 : maxdim, mindim, cutoff, 0.0,
+        normalize ? 1 : 0, 0, terr, eigs, length(eigs), ne), d.ctx)
+    ccall((:tnl_tensor_free, LIB), Cint, (Ptr{Cvoid},), phi[])
+    if reverse_step && !TenNetLib.halfsweep_done(length(sysenv), pos, 2, ortho)                                # :78-87
+        pos1 = ortho == "left" ? pos + 1 : pos
+        phi0 = Ref{Ptr{Cvoid}}(); cp = Ref{Ptr{Cvoid}}()
+        check(ccall((:tnl_env_get_state, LIB), Cint, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), d.env, pos1, phi0), d.ctx)
+        check(ccall((:tnl_tensor_copy, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), phi0[], cp), d.ctx)
+        check(ccall((:tnl_env_set_nsite, LIB), Cint, (Ptr{Cvoid}, Int32), d.env, 1), d.ctx)
+        check(ccall((:tnl_env_position, LIB), Cint, (Ptr{Cvoid}, Int32), d.env, pos1), d.ctx)
+        expo(cp[], -time_step); normed(cp[]); en = energy(cp[])
+        check(ccall((:tnl_env_set_state, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}), d.env, pos1, cp[]), d.ctx)
+        ccall((:tnl_tensor_free, LIB), Cint, (Ptr{Cvoid},), phi0[]); ccall((:tnl_tensor_free, LIB), Cint, (Ptr{Cvoid},), cp[])
+    end
+    return en, terr[], eigs[1:ne[]]
+end
+
+# ---- CouplingModel: one tnl_env_cm_set_term per (site, id) (src/base/couplingmodel.jl:14-17) ---------------------
+# for (n, terms) in enumerate(H.terms), (id, T) in terms:
+#     wl, wr = OpLink shared with the term's previous / next tensor (or nothing)
+#     W = permute(T * onehot(dummy) ..., (wl or dummy, s', s, wr or dummy));  flatten(W, nq)
+#     ccall((:tnl_env_cm_set_term, LIB), Cint, (Ptr{Cvoid}, Int32, Int64, Int32, Int32, Int32, Ptr{TnlIndex}, Int64,
+#           Ptr{Int32}, Ptr{Int64}, Ptr{Float64}), env, n, id, wl !== nothing, wr !== nothing, nq, idx, nb, coords, offs, data)
+# ComplexF64 ITensors go through tnl_tensor_import_c128 with `reinterpret(Float64, ITensors.data(T))`.
 
 "getpsi (src/mps/state_envs.jl:36): bring the MPS back as ITensors (tnl_env_get_state + tnl_tensor_export)."
 function download!(sysenv::StateEnvs{ProjMPO}) end   # marshalling mirror of `flatten`; omitted for brevity
