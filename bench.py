@@ -35,6 +35,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
+# load every kernel image at start-up: with lazy loading the first use of a cuSOLVER / cuBLAS / library kernel variant
+# inside a timed step costs tens of milliseconds once, and at N > 1 the other ranks wait for it inside a collective
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 FP64_PEAK_TFLOPS_FALLBACK = 35.46     # cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_peaks_fp64.json)
 SIGMA_SZ = 1.3
@@ -312,6 +315,15 @@ def run_ours(args):
     ms_per_step, tf_apply = agg["ms_per_step"], agg["tflops"]
     tf_e2e = aggregate(0.0, e2e_s, flops_per_apply * e2e_ops)["tflops"]
 
+    # per-rank device time by kernel class: a slow rank shows up as waiting time inside the collectives of the others
+    per_rank = None
+    if world > 1:
+        names = ("gemm", "transform", "vector", "collective")
+        mine = torch.tensor([prof["category_ms"].get(k, 0.0) / args.steps for k in names], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{k: float(v) for k, v in zip(names, t.tolist())} for t in allr]
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -354,6 +366,7 @@ def run_ours(args):
             "device_ms_per_step_by_kernel_class": {k: v / args.steps for k, v in prof["category_ms"].items()},
             "device_ms_per_step_by_phase_and_kernel_class": {ph: {k: v / args.steps for k, v in d.items()}
                                                              for ph, d in sysenv.phase_kernel_ms.items()},
+            "device_ms_per_step_by_rank": per_rank,
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": tf_e2e, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "call": "tnl_tensor_import -> tnl_eigsolve_lanczos -> tnl_tensor_export"},
