@@ -331,8 +331,15 @@ def run_ours(args):
 
     peak, peak_src = fp64_peak()
     gemm_tf = prof["flops"] / (prof["total_ms"] * 1e-3) / 1e12 if prof["total_ms"] > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "tnl::gemm_kernel<128,128,16,64,32> (FP64 DMMA grouped GEMM)",
-                "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": None,
+    traffic, traffic_src = None, None
+    try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(HERE, "profiles", "r01c_gemm_traffic.json")))
+        traffic, traffic_src = float(tj["dram_bytes_per_launch_mean"]), tj["source"]
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "tnl::gemm_kernel_v3<128,128,16,64,32> (FP64 DMMA grouped GEMM)",
+                "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": traffic,
+                "traffic_unit": "bytes per launch (DRAM read + write)", "traffic_source": traffic_src,
                 "peak_source": peak_src, "launches": prof["launches"],
                 "avg_launch_ms": prof["total_ms"] / max(1, prof["launches"]),
                 "algorithmic_gflop_per_launch": prof["flops"] / max(1, prof["launches"]) / 1e9,
