@@ -119,3 +119,131 @@ def test_shard_ranges_tile_every_sector_exactly():
                 if cnt.value:
                     owners.add(rank)
         assert len(owners) == world
+
+
+def test_coupling_model_ingestion_gives_canonical_rank4_terms():
+    """`canonical_terms` (host side of tnl_env_cm_set_term): every term tensor becomes W(wl, s', s, wr) with the
+    OpLink shared with the previous / next tensor of the same id, dim-1 charge-0 placeholders elsewhere, and the
+    dense operator of the canonical terms equals the model's."""
+    from oracle import couplingmodel as oc, models as om
+    from tennetlib.jl_b200.couplingmodel import canonical_terms, is_coupling_model
+    sites = om.siteinds("S=1", 6)
+    M = oc.heisenberg_coupling_model(sites, merge=True, field=0.3, j2=0.5)
+    assert is_coupling_model(M) and not is_coupling_model(om.heisenberg_mpo(sites))
+    ct = canonical_terms(M)
+    assert len(ct) == 6
+    support = {}
+    for j, terms in enumerate(ct):
+        assert set(terms) == set(M.terms[j])
+        for tid, W in terms.items():
+            assert len(W.inds) == 4 and W.inds[1].plev == 1 and W.inds[2].plev == 0
+            assert W.inds[0].dir == +1 and W.inds[3].dir == -1
+            for c, b in W.blocks.items():
+                assert b.shape == tuple(ix.dims[k] for ix, k in zip(W.inds, c))
+                q = sum(ix.dir * ix.qns[k][0] for ix, k in zip(W.inds, c))
+                assert q == 0                                   # flux 0 with the OpLinks carrying the charge
+            support.setdefault(tid, []).append((j, W))
+    # chain structure per id: first tensor has no left link, last no right link, inner links pair up
+    dense = np.zeros((3 ** 6, 3 ** 6))
+    for tid, lst in support.items():
+        assert not lst[0][1].has_wl and not lst[-1][1].has_wr
+        acc = np.ones((1, 1, 1))
+        pos = 0
+        for j, W in lst:
+            while pos < j:                                       # sites the term skips: identity
+                acc = np.einsum("rcw,xy->rxcyw", acc, np.eye(3)).reshape(acc.shape[0] * 3, acc.shape[1] * 3, acc.shape[2])
+                pos += 1
+            Wd = W.to_dense()
+            assert Wd.shape[0] == acc.shape[2]
+            acc = np.einsum("rcw,wxyv->rxcyv", acc, Wd).reshape(acc.shape[0] * 3, acc.shape[1] * 3, Wd.shape[3])
+            pos += 1
+        while pos < 6:
+            acc = np.einsum("rcw,xy->rxcyw", acc, np.eye(3)).reshape(acc.shape[0] * 3, acc.shape[1] * 3, acc.shape[2])
+            pos += 1
+        assert acc.shape[2] == 1
+        dense += acc[:, :, 0]
+    assert np.abs(dense - oc.coupling_model_to_dense(M)).max() < 1e-13
+
+
+def test_complex_host_tensors_flatten_to_interleaved_storage():
+    from tennetlib.jl_b200.tensor import HostTensor, Index, flatten_blocks
+    ix = [Index([(0,), (2,)], [2, 1], dir=+1), Index([(0,), (2,)], [2, 1], dir=-1)]
+    rng = np.random.default_rng(0)
+    t = HostTensor(ix, {(0, 0): rng.standard_normal((2, 2)) + 1j * rng.standard_normal((2, 2)), (1, 1): np.array([[0.5 - 2j]])})
+    assert t.is_complex() and t.to_dense().dtype == np.complex128
+    coords, offsets, data, nb = flatten_blocks(t, np.complex128)
+    assert nb == 2 and list(offsets) == [0, 4] and data.dtype == np.complex128
+    raw = data.view(np.float64)                                  # what tnl_tensor_import_c128 reads: (re, im) pairs
+    assert raw[0] == t.blocks[(0, 0)][0, 0].real and raw[1] == t.blocks[(0, 0)][0, 0].imag
+    assert raw[2] == t.blocks[(0, 0)][1, 0].real                  # column-major inside the block
+    assert raw[8] == 0.5 and raw[9] == -2.0
+
+
+class _FakeEnv:
+    """Stand-in for StateEnvs: records the (site, nsite, ortho) sequence a sweep driver issues."""
+
+    def __init__(self, N, lasteig, dims, kind="cm"):
+        self.N, self.calls, self._dims, self._lasteig = N, [], dims, lasteig
+        self.nterms, self.is_coupling_model, self.has_penalty = 1, kind == "cm", False
+        self.llim, self.rlim = 0, 2
+
+    def __len__(self):
+        return self.N
+
+    def isortho(self):
+        return True
+
+    def orthocenter(self):
+        return 1
+
+    def linkdim(self, bond):
+        return self._dims[bond - 1]
+
+    def linkdims(self):
+        return list(self._dims)
+
+
+def test_dynamic_fullsweep_picks_one_or_two_site_updates_like_the_reference(monkeypatch):
+    """src/mps/sweep.jl:302-336: per bond nsite = 1 if the last kept Schmidt weight of the previous half sweep is
+    below eigthreshold or the bond is saturated at maxdim, else 2; the site index of a one-site update on the way
+    back is bond+1; the edge sites get their extra one-site update."""
+    from tennetlib.jl_b200 import sweep as sw
+    N = 6
+    dims = [2, 4, 8, 4, 2]
+    env = _FakeEnv(N, None, dims)
+    data = sw.SweepData()
+    data.sweepcount = 1
+    data.energy, data.entropy, data.maxchi, data.maxtruncerr = [-0.5], [0.1], [4], [0.0]
+    data.lasteigs = [np.array([0.9, 1e-3]), np.array([0.9, 1e-14]), np.array([0.5, 0.1]), np.array([0.9, 1e-2]),
+                     np.array([0.9, 1e-13])]
+
+    def fake_update(sysenv, solver, pos, nsite, ortho, **kw):
+        sysenv.calls.append((pos, nsite, ortho))
+        return -1.0, 1e-9, np.array([0.7, 0.3])
+    monkeypatch.setattr(sw, "update_position", fake_update)
+    sw.dynamic_fullsweep(env, T.exp_solver, data, maxdim=8, outputlevel=0, time_step=-0.05)
+    left = [c for c in env.calls if c[2] == "left"]
+    right = [c for c in env.calls if c[2] == "right"]
+    # bond 2: tiny weight -> 1 site; bond 3: saturated (dim 8 >= maxdim) -> 1 site; bond 5: tiny -> 1 site + edge update
+    assert left == [(1, 2, "left"), (2, 1, "left"), (3, 1, "left"), (4, 2, "left"), (5, 1, "left"), (6, 1, "left")]
+    # on the way back the decisions use the eigs recorded on the way out (0.3 everywhere): only the saturated bond is 1-site
+    assert right == [(5, 2, "right"), (4, 2, "right"), (4, 1, "right"), (2, 2, "right"), (1, 2, "right")]
+    assert data.sweepcount == 2 and len(data.energy) == 2 and data.maxchi == [4, 8]
+    # first sweep on a single MPO needs the Global Subspace Expansion
+    with pytest.raises(NotImplementedError):
+        sw.dynamic_fullsweep(_FakeEnv(N, None, dims, kind="mpo"), T.exp_solver, sw.SweepData(), maxdim=8, outputlevel=0)
+
+
+def test_tdvpsweep_argument_checks():
+    from tennetlib.jl_b200 import tdvp
+
+    class E:
+        sysenv, swdata, abstime = None, None, 0.0
+    with pytest.raises(RuntimeError):
+        tdvp.tdvpsweep(E(), -0.1, 2, solver=T.eig_solver)
+    with pytest.raises(RuntimeError):
+        tdvp.tdvpsweep(E(), -0.1, 3)
+    with pytest.raises(RuntimeError):
+        tdvp.tdvpsweep(E(), -0.1, 2, extendat=5)
+    with pytest.raises(RuntimeError):
+        T.exp_solver(None, None, None)
