@@ -43,7 +43,14 @@ class CouplingModel:
         return self.terms[j - 1]
 
 
+_DENSE_OPS = {"X": np.array([[0.0, 1.0], [1.0, 0.0]]), "Z": np.array([[1.0, 0.0], [0.0, -1.0]]), "Id": np.eye(2),
+              "Sz": np.array([[0.5, 0.0], [0.0, -0.5]]), "Sx": np.array([[0.0, 0.5], [0.5, 0.0]]),
+              "S+": np.array([[0.0, 1.0], [0.0, 0.0]]), "S-": np.array([[0.0, 0.0], [1.0, 0.0]])}
+
+
 def _op_tensor(name: str, s: Index) -> BSTensor:
+    if s.nsect == 1:                                        # site without quantum numbers (d = 2): dense operator
+        return BSTensor.from_dense([s.prime().copy(dir=+1), s.copy(dir=-1)], _DENSE_OPS[name], keep_zero_blocks=True)
     ops = spin_ops(site_S2(s))
     dense = {"Sz": ops["Sz"], "S+": ops["Sp"], "S-": ops["Sm"], "Id": ops["Id"]}[name]
     step = s.qns[0][0] - s.qns[1][0]                       # charge carried by one spin flip (2 in 2Sz units)
@@ -136,6 +143,17 @@ def heisenberg_coupling_model(sites: Sequence[Index], Jz: float = 1.0, Jxy: floa
     for j in range(1, N + 1):
         if field:
             os += [(field, ("Sz", j))]
+    return coupling_model(os, sites, merge)
+
+
+def tfi_coupling_model(sites: Sequence[Index], h: float = 1.0, J: float = 1.0, merge: bool = True) -> CouplingModel:
+    """H = -J sum Z_j Z_{j+1} - h sum X_j on sites without quantum numbers (BASELINE.json configs[4])."""
+    os = []
+    N = len(sites)
+    for j in range(1, N):
+        os.append((-J, ("Z", j), ("Z", j + 1)))
+    for j in range(1, N + 1):
+        os.append((-h, ("X", j)))
     return coupling_model(os, sites, merge)
 
 

@@ -1,0 +1,583 @@
+"""Tree tensor networks on the CPU (oracle; test infrastructure only) -- SURVEY.md section 8 row a12.
+
+Restates the reference's in-tree TTN path for tensors WITHOUT quantum numbers (every index is one sector of
+charge 0, so the block-sparse oracle tensor is a dense tensor with named indices):
+  /root/reference/src/base/graph.jl:196-438                 bfs, nodes_from_bfs, shortest_path, central node
+  /root/reference/src/ttn/ttn_generators.jl:1-94,171-260     default_graph_sitenodes, randomTTN (non-QN branch)
+  /root/reference/src/ttn/ttn.jl:266-384                     moveisometry_to_next!, isometrize_full!, isometrize!
+  /root/reference/src/ttn/linktensors.jl:35-221,231-262      LinkTensorsTTN(psi, M), move_linktensors*, product
+  /root/reference/src/ttn/helper_internal_funcs.jl:22-47     _get_links
+  /root/reference/src/ttn/state_envs_ttn.jl:120-157          position!, product
+  /root/reference/src/ttn/update_site_ttn.jl:42-109          update_position!, subspace_expand!
+  /root/reference/src/ttn/sweep_ttn.jl:36-243                SweepDataTTN, default_sweeppath, fullsweep!
+  /root/reference/src/ttn/optimize_ttn.jl:47-218             OptimizeParamsTTN, optimize!
+This is the CPU statement the device path of the next round is to be checked against; nothing in the product
+package uses it.  Deviations that do not change any result: Julia iterates Sets / Dicts in hash order, here nodes and
+ids are visited in sorted order (sums over ids and tie-breaks between equally central nodes are order independent up
+to rounding / gauge); `qr` is done with the untruncated SVD (another gauge of the same isometry); the random padding
+of `subspace_expand!` draws from a NumPy generator.
+"""
+from __future__ import annotations
+
+import itertools
+from collections import deque
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+from .blocksparse import BSTensor, Index, commoninds, contract, factorize, inner, uniqueinds
+from .couplingmodel import CouplingModel, gen_id
+from .dmrg import FLOAT64_THRESHOLD, eig_solver
+
+Node = Tuple[int, int]
+
+
+# ------------------------------------------------------------------------------------------ graph
+class Graph:
+    def __init__(self):
+        self.adj: Dict[Node, set] = {}
+
+    @property
+    def nodes(self):
+        return set(self.adj)
+
+    def addedge(self, a: Node, b: Node):
+        self.adj.setdefault(a, set()).add(b)
+        self.adj.setdefault(b, set()).add(a)
+
+    def __getitem__(self, node):
+        return sorted(self.adj[node])
+
+    def isneighbor(self, a, b):
+        return b in self.adj.get(a, ())
+
+
+def bfs(graph: Graph, source: Node, destination: Node | None = None):
+    q = deque([source])
+    visited = {source}
+    parents: Dict[Node, Node] = {}
+    dist = {source: 0}
+    while q:
+        node = q.popleft()
+        for nb in graph[node]:
+            if nb not in visited:
+                q.append(nb)
+                visited.add(nb)
+                dist[nb] = dist[node] + 1
+                parents[nb] = node
+                if destination is not None and nb == destination:
+                    return dist, parents
+    return dist, parents
+
+
+def nodes_from_bfs(graph: Graph, source: Node, destinations=None, reverse: bool = False) -> List[Node]:
+    dist, parents = bfs(graph, source)
+    if destinations is None:
+        nodes = sorted(dist)
+    else:
+        res = set()
+        for d in destinations:
+            if d != source:
+                cur = d
+                res.add(cur)
+                while cur in parents:
+                    res.add(parents[cur])
+                    cur = parents[cur]
+            else:
+                res.add(source)
+        nodes = sorted(res)
+    return sorted(nodes, key=lambda x: dist[x], reverse=reverse)
+
+
+def shortest_path(graph: Graph, source: Node, destination: Node) -> List[Node]:
+    if source == destination:
+        return [source]
+    _, parents = bfs(graph, source, destination)
+    if destination not in parents:
+        raise RuntimeError(f"`shortest_path()`: `destination={destination}` is not reachable from `source={source}` !!")
+    out = [destination]
+    while destination in parents:
+        out.append(parents[destination])
+        destination = parents[destination]
+    return out[::-1]
+
+
+def nextnode_in_path(graph: Graph, source: Node, destination: Node, n: int = 1) -> Node:
+    return shortest_path(graph, source, destination)[n]
+
+
+def find_eccentric_central_node(graph: Graph, nodes=None) -> Node:
+    best, best_d = None, None
+    for node in sorted(graph.nodes):
+        dist, _ = bfs(graph, node)
+        if nodes is not None:
+            dist = {k: v for k, v in dist.items() if k in set(nodes)}
+        md = max(dist.values())
+        if best_d is None or md < best_d:
+            best, best_d = node, md
+    return best
+
+
+# --------------------------------------------------------------------------------- default binary tree
+def _minimum_power2_greater_than(n: int) -> int:
+    p = 1
+    while p < n:
+        p *= 2
+    return p
+
+
+def _distribute_site_positions(numsites: int, loc=None) -> List[int]:
+    """ttn_generators.jl:1-48."""
+    if not loc:
+        loc = [numsites // 2, numsites // 2 + numsites % 2]
+        numsites = _minimum_power2_greater_than(numsites)
+    else:
+        newloc = []
+        power = (len(loc) & -len(loc)).bit_length() - 1          # trailing_zeros
+        for m in loc:
+            rem = m % 2
+            newloc.append(m // 2 + rem if power % 2 == 1 else m // 2)
+            newloc.append(m // 2 if power % 2 == 1 else m // 2 + rem)
+        loc = newloc
+    numsites //= 2
+    power = (numsites & -numsites).bit_length() - 1
+    if power > 1:
+        return _distribute_site_positions(numsites, loc)
+    pos = []
+    for m in loc:
+        if m == 1:
+            pos += [1, 0]
+        elif m == 2:
+            pos += [1, 1]
+        else:
+            raise RuntimeError("`_distribute_site_positions()`: SOMETHING IS WRONG !!")
+    return pos
+
+
+def default_graph_sitenodes(numsites: int):
+    """ttn_generators.jl:69-94: hierarchical binary tree, two sites per bottom node, the two top nodes linked."""
+    site_positions = _distribute_site_positions(numsites)
+    pow2 = len(site_positions)
+    numlayers = (pow2 & -pow2).bit_length() - 1
+    sitenodes: Dict[int, Node] = {}
+    graph = Graph()
+    sitecount = 1
+    for ll in range(1, numlayers - 1):
+        for nn in range(1, (pow2 >> ll) + 1):
+            if ll == 1 and (site_positions[2 * nn - 2] == 0 or site_positions[2 * nn - 1] == 0):
+                sitenodes[sitecount] = (ll + 1, (nn + 1) // 2)
+                sitecount += 1
+                continue
+            elif ll == 1:
+                sitenodes[sitecount] = (ll, nn)
+                sitecount += 1
+                sitenodes[sitecount] = (ll, nn)
+                sitecount += 1
+            graph.addedge((ll, nn), (ll + 1, (nn + 1) // 2))
+    graph.addedge((numlayers - 1, 1), (numlayers - 1, 2))
+    return graph, sitenodes
+
+
+# ------------------------------------------------------------------------------------------- TTN
+def dense_index(dim: int, dir: int = +1, tags: str = "") -> Index:
+    return Index([(0,)], [dim], dir=dir, tags=tags)
+
+
+def dense_siteinds(N: int, d: int = 2) -> List[Index]:
+    return [dense_index(d, +1, f"Site,n={j + 1}") for j in range(N)]
+
+
+class TTN:
+    """ttn.jl:13-40."""
+
+    def __init__(self, sites, graph: Graph, tensors: Dict[Node, BSTensor], orthocenter=None):
+        self.sites = list(sites)
+        self.graph = graph
+        self.tensors = dict(tensors)
+        self.orthocenter = orthocenter
+
+    def __getitem__(self, node):
+        return self.tensors[node]
+
+    def __setitem__(self, node, t):
+        self.tensors[node] = t
+        if self.orthocenter != node:
+            self.orthocenter = None
+
+    def copy(self):
+        return TTN(self.sites, self.graph, {k: v.copy() for k, v in self.tensors.items()}, self.orthocenter)
+
+    def numsites(self):
+        return len(self.sites)
+
+    def findsites(self, t: BSTensor) -> List[int]:
+        ids = {ix.id for ix in t.inds}
+        return [n + 1 for n, s in enumerate(self.sites) if s.id in ids]
+
+    def find_sitenode(self, n: int) -> Node:
+        sid = self.sites[n - 1].id
+        for node in sorted(self.tensors):
+            if any(ix.id == sid for ix in self.tensors[node].inds):
+                return node
+        raise KeyError(n)
+
+    def maxlinkdim(self) -> int:
+        md = 1
+        for t in self.tensors.values():
+            for ix in t.inds:
+                if "Link" in ix.tags:
+                    md = max(md, ix.dim)
+        return md
+
+    def normalize(self):
+        t = self.tensors[self.orthocenter]
+        self.tensors[self.orthocenter] = t.scale(1.0 / t.norm())
+
+
+def random_ttn(sites, graph: Graph, sitenodes: Dict[int, Node], chi: int, rng: np.random.Generator) -> TTN:
+    """randomTTN, non-QN branch (ttn_generators.jl:171-246): link dims min(prod of the other dims, chi)."""
+    inds: Dict[Node, List[Index]] = {node: [] for node in graph.nodes}
+    for b, s in enumerate(sites):
+        inds[sitenodes[b + 1]].append(s)
+    center = find_eccentric_central_node(graph, list(sitenodes.values()))
+    for node in nodes_from_bfs(graph, center, reverse=True)[:-1]:
+        nxt = nextnode_in_path(graph, node, center)
+        dim = min(int(np.prod([ix.dim for ix in inds[node]])), chi)
+        link = dense_index(dim, +1, f"Link,{node}")
+        inds[node].append(link.copy(dir=-1))
+        inds[nxt].append(link)
+    tensors = {}
+    for node in sorted(graph.nodes):
+        t = BSTensor.random(inds[node], rng)
+        tensors[node] = t.scale(1.0 / t.norm())
+    ttn = TTN(sites, graph, tensors, None)
+    isometrize_full(ttn, center, normalize=True, cutoff=0.0, maxdim=chi)
+    return ttn
+
+
+def default_random_ttn(sites, chi: int, rng: np.random.Generator) -> TTN:
+    graph, sitenodes = default_graph_sitenodes(len(sites))
+    return random_ttn(sites, graph, sitenodes, chi, rng)
+
+
+def moveisometry_to_next(ttn: TTN, node1: Node, node2: Node, *, ignore_orthocenter=False, maxdim=None, mindim=1,
+                         cutoff=FLOAT64_THRESHOLD, svd_alg="divide_and_conquer", **_):
+    """ttn.jl:266-310: SVD when a truncation can happen (cutoff > 0 or the link exceeds maxdim), QR otherwise."""
+    if ttn.orthocenter != node1 and not ignore_orthocenter:
+        raise RuntimeError(f"`moveisometry_to_next!()`: `orthocenter` does not match with the input `node1 = {node1} !!")
+    if not ttn.graph.isneighbor(node1, node2):
+        raise RuntimeError("`moveisometry_to_next!()`: Input nodes are not neighbors !!")
+    A, B = ttn.tensors[node1], ttn.tensors[node2]
+    com = commoninds(A, B)[0]
+    uinds = uniqueinds(A, B)
+    big = (1 << 62) if maxdim is None else maxdim
+    if cutoff > 0.0 or com.dim > big:
+        U, R, spec, u = factorize(A, uinds, ortho="left", which_decomp="svd", maxdim=maxdim, mindim=mindim,
+                                  cutoff=cutoff, tags=com.tags)
+    else:
+        U, R, spec, u = factorize(A, uinds, ortho="left", which_decomp="svd", maxdim=None, mindim=1, cutoff=None,
+                                  tags=com.tags)
+    ttn.tensors[node1] = U
+    ttn.tensors[node2] = contract(B, R)
+    ttn.orthocenter = node2
+
+
+def isometrize_full(ttn: TTN, node: Node, normalize=True, **kw):
+    path = nodes_from_bfs(ttn.graph, node, reverse=True)
+    for n in path[:-1]:
+        nxt = nextnode_in_path(ttn.graph, n, node)
+        moveisometry_to_next(ttn, n, nxt, ignore_orthocenter=True, **kw)
+    ttn.orthocenter = node
+    if normalize:
+        ttn.normalize()
+
+
+def isometrize(ttn: TTN, node: Node, normalize=True, **kw):
+    if ttn.orthocenter is None:
+        isometrize_full(ttn, node, normalize=normalize, **kw)
+    if node != ttn.orthocenter:
+        path = shortest_path(ttn.graph, ttn.orthocenter, node)
+        for a, b in zip(path[:-1], path[1:]):
+            moveisometry_to_next(ttn, a, b, **kw)
+    if normalize:
+        ttn.normalize()
+
+
+def ttn_to_dense(ttn: TTN) -> np.ndarray:
+    """Full state vector (small N; KAT helper), site 1 = most significant digit."""
+    acc = None
+    for node in nodes_from_bfs(ttn.graph, ttn.orthocenter or sorted(ttn.graph.nodes)[0]):
+        acc = ttn.tensors[node] if acc is None else contract(acc, ttn.tensors[node])
+    order = [next(ix for ix in acc.inds if ix.id == s.id) for s in ttn.sites]
+    rest = [ix for ix in acc.inds if all(ix.id != s.id for s in ttn.sites)]
+    assert all(ix.dim == 1 for ix in rest)
+    return acc.permute(order + rest).to_dense().reshape(-1)
+
+
+# ---------------------------------------------------------------------------------- link environments
+def _link(a: Node, b: Node):
+    return frozenset((a, b))
+
+
+class LinkTensorsTTN(dict):
+    """Dict{LinkTypeTTN, IDTensors}: per link the environment tensors of every term id (linktensors.jl:1-20)."""
+
+
+def _get_links(psi: TTN, node: Node, nextnode: Node | None = None):
+    nbrs = [x for x in psi.graph[node] if x != nextnode]
+    nbrs += [(0, n) for n in psi.findsites(psi[node])]
+    links = [_link(node, x) for x in nbrs]
+    return (_link(node, nextnode), links) if nextnode is not None else links
+
+
+def _collect(env: LinkTensorsTTN, links) -> Dict[int, List[BSTensor]]:
+    idtens: Dict[int, List[BSTensor]] = {}
+    for link in links:
+        for tid, t in env.get(link, {}).items():
+            idtens.setdefault(tid, []).append(t)
+    return idtens
+
+
+def move_linktensors_to_next(env: LinkTensorsTTN, psi: TTN, node: Node, nextnode: Node):
+    """linktensors.jl:63-118: for every id on the other links of `node`, contract dag(prime(phi)) * tensors * phi; results
+    that still carry an OpLink (order > 2) stay separate, the others are summed into one local tensor."""
+    if not psi.graph.isneighbor(node, nextnode):
+        raise RuntimeError("`move_linktensors_to_next!()`: Input nodes are not neighbors !!")
+    next_link, prev_links = _get_links(psi, node, nextnode)
+    idtens = _collect(env, prev_links)
+    if not idtens:
+        return
+    env[next_link] = {}
+    phi = psi[node]
+    nextind = commoninds(phi, psi[nextnode])[0]
+    local = None
+    for tid in sorted(idtens):
+        to_prime = [commoninds(phi, x)[0] for x in idtens[tid]] + [nextind]
+        t = phi.prime(1, to_prime).dag()
+        for x in idtens[tid]:
+            t = contract(t, x)
+        t = contract(t, phi)
+        if t.rank > 2:
+            env[next_link][tid] = t
+        else:
+            local = t if local is None else local.add(t)
+    if local is not None:
+        env[next_link][gen_id()] = local
+
+
+def move_linktensors(env: LinkTensorsTTN, psi: TTN, source: Node, destination: Node, node_to_skip=None):
+    if source == destination:
+        return
+    path = shortest_path(psi.graph, source, destination)
+    for a, b in zip(path[:-1], path[1:]):
+        if a == node_to_skip:
+            continue
+        move_linktensors_to_next(env, psi, a, b)
+
+
+def link_tensors_from_model(psi: TTN, M: CouplingModel) -> LinkTensorsTTN:
+    """LinkTensorsTTN(psi, M) (linktensors.jl:231-262): site operators sit on the virtual links (0, n) -- node; the
+    environments are then pulled towards the orthogonality centre, farthest nodes first."""
+    if psi.orthocenter is None:
+        raise RuntimeError("`LinkTensorsTTN()`: TTN does not have a proper orthogonality center !!")
+    env = LinkTensorsTTN()
+    nodelist = set()
+    for n in range(1, psi.numsites() + 1):
+        node = psi.find_sitenode(n)
+        if M[n]:
+            env[_link((0, n), node)] = dict(M[n])
+            nodelist.add(node)
+    oc = psi.orthocenter
+    path = nodes_from_bfs(psi.graph, oc, nodelist, reverse=True)
+    for n1 in path[:-1]:
+        move_linktensors_to_next(env, psi, n1, nextnode_in_path(psi.graph, n1, oc))
+    return env
+
+
+def product(env: LinkTensorsTTN, psi: TTN, v: BSTensor) -> BSTensor:
+    """linktensors.jl:183-221: sum over ids of contract(v, link tensors of the id around the orthogonality centre)."""
+    idtens = _collect(env, _get_links(psi, psi.orthocenter))
+    out = None
+    for tid in sorted(idtens):
+        Hv = v
+        for x in idtens[tid]:
+            Hv = contract(Hv, x)
+        Hv = Hv.noprime()
+        out = Hv if out is None else out.add(Hv)
+    if out.rank != v.rank:
+        raise RuntimeError("The order of the LinkTensorsTTN-ITensor product P*v is not equal to the order of the ITensor v")
+    return out
+
+
+class StateEnvsTTN:
+    """state_envs_ttn.jl:13-45 (CouplingModel environment, no penalised states)."""
+
+    def __init__(self, psi: TTN, M: CouplingModel):
+        self.psi = psi.copy()
+        self.env = link_tensors_from_model(self.psi, M)
+
+    def position(self, node: Node, *, maxdim=None, mindim=1, cutoff=FLOAT64_THRESHOLD, svd_alg="divide_and_conquer",
+                 normalize=True, node_to_skip=None):
+        oc = self.psi.orthocenter
+        isometrize(self.psi, node, normalize=normalize, maxdim=maxdim, mindim=mindim, cutoff=cutoff, svd_alg=svd_alg)
+        move_linktensors(self.env, self.psi, oc, node, node_to_skip=node_to_skip)
+
+    def product(self, v: BSTensor) -> BSTensor:
+        return product(self.env, self.psi, v)
+
+    __call__ = product
+
+
+def update_position_ttn(sysenv: StateEnvsTTN, solver, node: Node, *, time_step=None, normalize=True, maxdim=None,
+                        mindim=1, cutoff=FLOAT64_THRESHOLD, svd_alg="divide_and_conquer", **kw):
+    """update_site_ttn.jl:42-63."""
+    sysenv.position(node, normalize=normalize, maxdim=maxdim, mindim=mindim, cutoff=cutoff, svd_alg=svd_alg)
+    phi = sysenv.psi[node]
+    energy, phi = solver(sysenv, phi, time_step, **kw)
+    sysenv.psi[node] = phi.permute(sysenv.psi[node].inds)
+    return energy
+
+
+def _directsum(A: BSTensor, ia: Index, P: BSTensor, ip: Index, tags: str):
+    """ITensors `directsum(A => ia, P => ip)` for dense tensors: concatenate along one index."""
+    oa = [ix for ix in A.inds if ix != ia]
+    Ad = A.permute(oa + [ia]).to_dense()
+    Pd = P.permute([next(jx for jx in P.inds if jx == ix) for ix in oa] + [ip]).to_dense()
+    new = dense_index(ia.dim + ip.dim, ia.dir, tags)
+    return BSTensor.from_dense(oa + [new], np.concatenate([Ad, Pd], axis=-1), keep_zero_blocks=True), new
+
+
+def subspace_expand(psi: TTN, node: Node, nextnode: Node, max_expand_dim: int, noise: float, rng: np.random.Generator):
+    """update_site_ttn.jl:75-109: pad the link between `node` and `nextnode` with random directions of relative size
+    `noise`; dense `indexintersection` = min(SUM of the dims on either side, max_expand_dim)
+    (src/base/helper_internal_funcs.jl:180-186)."""
+    A, B = psi.tensors[node], psi.tensors[nextnode]
+    ind_to_update = commoninds(B, A)[0]
+    indsA, indsB = uniqueinds(A, B), uniqueinds(B, A)
+    padd = min(sum(ix.dim for ix in indsB), sum(ix.dim for ix in indsA), max_expand_dim)
+    ind_padB = dense_index(padd, ind_to_update.dir, "pad")
+    padB = BSTensor.random([ind_padB] + list(indsB), rng)
+    padB = padB.scale(noise * B.norm() / padB.norm())
+    enlargedB, sumB = _directsum(B, ind_to_update, padB, ind_padB, ind_to_update.tags)
+    psi.tensors[nextnode] = enlargedB
+    ind_padA = ind_padB.copy(dir=-ind_padB.dir)
+    padA = BSTensor.random([ind_padA] + list(indsA), rng)
+    padA = padA.scale(noise * A.norm() / padA.norm())
+    ia = next(ix for ix in A.inds if ix == ind_to_update)
+    enlargedA, sumA = _directsum(A, ia, padA, ind_padA, ind_to_update.tags)
+    psi.tensors[node] = enlargedA.replaceinds([sumA], [sumB.copy(dir=-sumB.dir)])
+
+
+# ------------------------------------------------------------------------------------------ sweeps
+class SweepDataTTN:
+    def __init__(self):
+        self.sweepcount = 0
+        self.maxchi: List[int] = []
+        self.energy: List[float] = []
+
+
+def default_sweeppath(psi: TTN) -> List[Node]:
+    """sweep_ttn.jl:36-52."""
+    path = []
+    nsites = _minimum_power2_greater_than(psi.numsites())
+    nlayers = (nsites & -nsites).bit_length() - 1
+    for ll in range(nlayers - 1, 0, -1):
+        for nn in range(1, (nsites >> ll) + 1):
+            nnpos = nn if (nlayers - ll) % 2 == 1 else (nsites >> ll) - nn + 1
+            node = (ll, nnpos)
+            if ll == 1 and node not in psi.graph.nodes:
+                continue
+            path.append(node)
+    return path
+
+
+def fullsweep_ttn(sysenv: StateEnvsTTN, sweeppath: Sequence[Node], solver, swdata: SweepDataTTN, rng=None, **kw):
+    """sweep_ttn.jl:94-243: plain sweep (noise == 0: isometry moves by QR, truncating only links above maxdim) or the
+    subspace-expansion sweep (noise > 0: pad the link towards the centre, then alternate `expand_numiter` updates of the
+    two nodes with a shrinking maxdim)."""
+    assert set(sweeppath) == sysenv.psi.graph.nodes
+    kw = dict(kw)
+    kw.pop("outputlevel", None)
+    time_step = kw.pop("time_step", None)
+    maxdim = kw.pop("maxdim", None)
+    mindim = kw.pop("mindim", 1)
+    cutoff = kw.pop("cutoff", FLOAT64_THRESHOLD)
+    svd_alg = kw.pop("svd_alg", "divide_and_conquer")
+    normalize = kw.pop("normalize", True)
+    noise = kw.pop("noise", 0.0)
+    expand_dim = kw.pop("expand_dim", 0 if abs(noise) < 100 * FLOAT64_THRESHOLD else 20)
+    max_expand_dim = kw.pop("max_expand_dim", 2 * expand_dim)
+    expand_numiter = kw.pop("expand_numiter", 4)
+    linkwise_maxdim = kw.pop("linkwise_maxdim", None)
+    if expand_dim != 0 and expand_numiter < 2:
+        raise RuntimeError(f"`fullsweep!()`: `expand_numiter={expand_numiter}` cannot be less than 2 for `expand_dim={expand_dim}` !!")
+    energy = float("nan")
+    swdata.sweepcount += 1
+    common = dict(time_step=time_step, normalize=normalize, mindim=mindim, svd_alg=svd_alg)
+    if abs(noise) < 100 * FLOAT64_THRESHOLD:
+        for node in list(sweeppath) + list(sweeppath)[::-1]:
+            energy = update_position_ttn(sysenv, solver, node, maxdim=maxdim, cutoff=-1.0, **common, **kw)
+    else:
+        rng = rng or np.random.default_rng(0)
+        central = find_eccentric_central_node(sysenv.psi.graph)
+        big = (1 << 62) if maxdim is None else maxdim
+        for ii in list(range(len(sweeppath))) + list(range(len(sweeppath) - 1, -1, -1)):
+            node = sweeppath[ii]
+            if node == central:
+                energy = update_position_ttn(sysenv, solver, node, maxdim=maxdim, cutoff=-1.0, **common, **kw)
+                continue
+            nextnode = nextnode_in_path(sysenv.psi.graph, node, central)
+            sysenv.position(node, normalize=normalize, maxdim=maxdim, mindim=mindim, cutoff=-1.0, svd_alg=svd_alg,
+                            node_to_skip=nextnode)
+            subspace_expand(sysenv.psi, node, nextnode, max_expand_dim, noise, rng)
+            sysenv.psi.orthocenter = nextnode
+            link = _link(node, nextnode)
+            linkmax = linkwise_maxdim[link] if linkwise_maxdim and link in linkwise_maxdim else big
+            for dummy in range(1, expand_numiter + 1):
+                newmax = linkmax if dummy == expand_numiter else (linkmax + max_expand_dim if dummy == 1 else linkmax + expand_dim)
+                newnode = node if dummy % 2 == 1 else nextnode
+                energy = update_position_ttn(sysenv, solver, newnode, maxdim=newmax, cutoff=cutoff, **common, **kw)
+    swdata.maxchi.append(sysenv.psi.maxlinkdim())
+    swdata.energy.append(energy)
+    return swdata.energy[-1] - swdata.energy[-2] if swdata.sweepcount > 1 else float("nan")
+
+
+class OptimizeParamsTTN:
+    """optimize_ttn.jl:18-99."""
+
+    def __init__(self, *, maxdim, nsweeps, cutoff=FLOAT64_THRESHOLD, noise=0.0, noisedecay=1.0,
+                 disable_noise_after=(1 << 62)):
+        n = len(nsweeps)
+        vec = lambda x, T: [T(v) for v in x] if isinstance(x, (list, tuple)) else [T(x)] * n
+        self.maxdim, self.nsweeps = list(maxdim), list(nsweeps)
+        self.cutoff, self.noise = vec(cutoff, float), vec(noise, float)
+        self.noisedecay, self.disable_noise_after = vec(noisedecay, float), vec(disable_noise_after, int)
+        if not (len(self.maxdim) == n == len(self.cutoff) == len(self.noise) == len(self.noisedecay)
+                == len(self.disable_noise_after)):
+            raise ValueError("`OptimizeParamsTTN()`: Size mismatch in input vectors !!")
+
+
+def optimize_(sysenv: StateEnvsTTN, params: OptimizeParamsTTN, sweeppath: Sequence[Node], rng=None, **kw) -> SweepDataTTN:
+    """`optimize!` (optimize_ttn.jl:148-218): stage / sweep loop with the noise schedule of `dmrg!`."""
+    enerrgoal = kw.pop("energyErrGoal", None)
+    swdata = SweepDataTTN()
+    for ii in range(len(params.nsweeps)):
+        maxdim, cutoff, noise = params.maxdim[ii], params.cutoff[ii], params.noise[ii]
+        noisedecay, disable_after = params.noisedecay[ii], params.disable_noise_after[ii]
+        for jj in range(1, params.nsweeps[ii] + 1):
+            enerr = fullsweep_ttn(sysenv, sweeppath, eig_solver, swdata, rng=rng, maxdim=maxdim, cutoff=cutoff,
+                                  noise=noise, **kw)
+            if enerrgoal is not None and abs(enerr) < abs(enerrgoal) and abs(noise) < FLOAT64_THRESHOLD:
+                break
+            if jj == disable_after:
+                noise = 0.0
+            noise /= noisedecay
+            if noise < 100 * FLOAT64_THRESHOLD:
+                noise = 0.0
+    return swdata
+
+
+def optimize(psi0: TTN, H: CouplingModel, params: OptimizeParamsTTN, sweeppath: Sequence[Node], rng=None, **kw):
+    sysenv = StateEnvsTTN(psi0, H)
+    sw = optimize_(sysenv, params, sweeppath, rng=rng, **kw)
+    return sw.energy[-1], sysenv.psi, sw

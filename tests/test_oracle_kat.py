@@ -334,3 +334,61 @@ def test_coupling_model_dmrg_and_tdvp_kat():
     for ns in (2, 2, 1):
         od.tdvpsweep(eng, -0.05, ns, maxdim=16, cutoff=1e-12)
     assert eng.swdata.energy[0] > eng.swdata.energy[1] > eng.swdata.energy[2]
+
+
+# ---------------------------------------------------------------------------------------------- TTN (row a12, oracle only)
+def test_ttn_default_graph_and_sweeppath_follow_the_reference_docstring():
+    """default_graph_sitenodes (src/ttn/ttn_generators.jl:50-94): the documented site -> node map for N = 32, a tree
+    for sizes that are not a power of two, and a sweep path that visits every node once."""
+    from oracle import ttn as ot
+    graph, sitenodes = ot.default_graph_sitenodes(32)
+    assert sitenodes[1] == (1, 1) and sitenodes[2] == (1, 1) and sitenodes[3] == (1, 2) and sitenodes[4] == (1, 2)
+    assert sitenodes[31] == (1, 16) and sitenodes[32] == (1, 16)
+    assert len(graph.nodes) == 16 + 8 + 4 + 2 and graph.isneighbor((4, 1), (4, 2))
+    for N in (6, 8, 12, 20):
+        g, sn = ot.default_graph_sitenodes(N)
+        assert sorted(sn) == list(range(1, N + 1))
+        edges = sum(len(v) for v in g.adj.values()) // 2
+        assert edges == len(g.nodes) - 1                              # a tree
+        psi = ot.default_random_ttn(ot.dense_siteinds(N), 3, np.random.default_rng(N))
+        path = ot.default_sweeppath(psi)
+        assert sorted(path) == sorted(g.nodes) and len(set(path)) == len(path)
+        assert abs(np.linalg.norm(ot.ttn_to_dense(psi)) - 1.0) < 1e-12   # isometrised and normalised
+
+
+def test_ttn_environments_reproduce_the_dense_expectation_value():
+    """LinkTensorsTTN (src/ttn/linktensors.jl:63-262): <phi|H_eff|phi> at every node of the sweep path equals the
+    dense <psi|H|psi>, with the environments moved along the tree by `position!`."""
+    from oracle import blocksparse as ob, couplingmodel as oc, ttn as ot
+    N = 8
+    sites = ot.dense_siteinds(N)
+    M = oc.tfi_coupling_model(sites, h=0.7)
+    Hd = oc.coupling_model_to_dense(M)
+    psi = ot.default_random_ttn(sites, 4, np.random.default_rng(2))
+    env = ot.StateEnvsTTN(psi, M)
+    for node in ot.default_sweeppath(psi):
+        env.position(node, cutoff=-1.0)
+        phi = env.psi[node]
+        v = ot.ttn_to_dense(env.psi)
+        e = ob.inner(phi, env.product(phi).permute(phi.inds)) / ob.inner(phi, phi)
+        assert abs(e - v @ Hd @ v / (v @ v)) < 1e-12
+
+
+@pytest.mark.parametrize("N", [8, 12])
+def test_ttn_optimize_reaches_the_tfi_ground_state(N):
+    """optimize! (src/ttn/optimize_ttn.jl:148-218) with subspace expansion on the critical transverse-field Ising
+    chain (BASELINE.json configs[4] at CPU scale) against exact diagonalisation."""
+    from oracle import couplingmodel as oc, ttn as ot
+    sites = ot.dense_siteinds(N)
+    M = oc.tfi_coupling_model(sites, h=1.0)
+    E0 = np.linalg.eigvalsh(oc.coupling_model_to_dense(M))[0]
+    rng = np.random.default_rng(1)
+    psi0 = ot.default_random_ttn(sites, 4, rng)
+    prm = ot.OptimizeParamsTTN(maxdim=[8, 16], nsweeps=[4, 3], cutoff=1e-14, noise=[1e-2, 0.0], noisedecay=5,
+                               disable_noise_after=3)
+    E, psi, sw = ot.optimize(psi0, M, prm, ot.default_sweeppath(psi0), rng=rng)
+    assert abs(E - E0) < 1e-7 and sw.maxchi[-1] <= 16
+    assert all(b <= a + 1e-9 for a, b in zip(sw.energy[3:], sw.energy[4:]))      # monotone once the noise is off
+    v = ot.ttn_to_dense(psi)
+    Hd = oc.coupling_model_to_dense(M)
+    assert abs(v @ Hd @ v / (v @ v) - E) < 1e-10
