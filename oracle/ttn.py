@@ -1,9 +1,10 @@
 """Tree tensor networks on the CPU (oracle; test infrastructure only) -- SURVEY.md section 8 row a12.
 
-Restates the reference's in-tree TTN path for tensors WITHOUT quantum numbers (every index is one sector of
-charge 0, so the block-sparse oracle tensor is a dense tensor with named indices):
+Restates the reference's in-tree TTN path on the oracle's block-sparse tensors, for sites without quantum numbers
+(every index one sector of charge 0: a dense tensor with named indices; BASELINE.json configs[4]) and for
+QN-conserving sites with the dummy "QN" index at the centre node (the model of test/test_TTN.jl):
   /root/reference/src/base/graph.jl:196-438                 bfs, nodes_from_bfs, shortest_path, central node
-  /root/reference/src/ttn/ttn_generators.jl:1-94,171-260     default_graph_sitenodes, randomTTN (non-QN branch)
+  /root/reference/src/ttn/ttn_generators.jl:1-94,96-260      default_graph_sitenodes, randomTTN (both branches)
   /root/reference/src/ttn/ttn.jl:266-384                     moveisometry_to_next!, isometrize_full!, isometrize!
   /root/reference/src/ttn/linktensors.jl:35-221,231-262      LinkTensorsTTN(psi, M), move_linktensors*, product
   /root/reference/src/ttn/helper_internal_funcs.jl:22-47     _get_links
@@ -255,8 +256,100 @@ def random_ttn(sites, graph: Graph, sitenodes: Dict[int, Node], chi: int, rng: n
     return ttn
 
 
-def default_random_ttn(sites, chi: int, rng: np.random.Generator) -> TTN:
+def _sectors_of(ix: Index) -> Dict[tuple, int]:
+    out: Dict[tuple, int] = {}
+    for q, d in zip(ix.qns, ix.dims):
+        out[q] = out.get(q, 0) + d
+    return out
+
+
+def _fuse(a: Dict[tuple, int], b: Dict[tuple, int]) -> Dict[tuple, int]:
+    out: Dict[tuple, int] = {}
+    for qa, da in a.items():
+        for qb, db in b.items():
+            q = tuple(x + y for x, y in zip(qa, qb))
+            out[q] = min(out.get(q, 0) + da * db, 1 << 40)
+    return out
+
+
+def random_ttn_qn(sites, graph: Graph, sitenodes: Dict[int, Node], chi: int, total_qn, rng: np.random.Generator) -> TTN:
+    """randomTTN, QN branch (ttn_generators.jl:171-246): the centre node carries a dummy "QN" index with the global
+    charge; every link keeps only the charge sectors that the sites below it can produce AND that the rest of the tree
+    can complete to the global charge, with block dimensions reduced proportionally to a total of `chi`.  The
+    reference reaches the same fixed point by 100 rounds of `_ttn_ind_cleanup!` / `_ttn_ind_reducedim!`
+    (:96-170) with a gradually shrinking cap; here it is one bottom-up and one top-down pass (the start state is
+    random either way, only its sector structure matters)."""
+    nq = len(sites[0].qns[0])
+    total_qn = tuple(total_qn)
+    center = find_eccentric_central_node(graph, list(sitenodes.values()))
+    order_up = nodes_from_bfs(graph, center, reverse=True)            # leaves first
+    parent = {n: nextnode_in_path(graph, n, center) for n in order_up[:-1]}
+    children: Dict[Node, List[Node]] = {n: [] for n in graph.nodes}
+    for n, pnode in parent.items():
+        children[pnode].append(n)
+    site_of: Dict[Node, List[Index]] = {n: [] for n in graph.nodes}
+    for b, sidx in enumerate(sites):
+        site_of[sitenodes[b + 1]].append(sidx)
+    zero = {(0,) * nq: 1}
+    # bottom-up: charges (as seen by the parent, i.e. sum of dir*qn of everything below) each subtree can produce
+    below: Dict[Node, Dict[tuple, int]] = {}
+    for n in order_up:
+        acc = dict(zero)
+        for sidx in site_of[n]:
+            acc = _fuse(acc, {tuple(sidx.dir * x for x in q): d for q, d in _sectors_of(sidx).items()})
+        for c in sorted(children[n]):
+            acc = _fuse(acc, below[c])
+        below[n] = acc
+    # top-down: sectors of the link above each node that the rest of the tree can complete
+    link_sectors: Dict[Node, Dict[tuple, int]] = {}
+    above: Dict[Node, Dict[tuple, int]] = {center: {total_qn: 1}}       # charge the node as a whole must carry upwards
+    for n in nodes_from_bfs(graph, center):
+        parts = [(None, {tuple(sidx.dir * x for x in q): d for q, d in _sectors_of(sidx).items()}) for sidx in site_of[n]]
+        parts += [(c, below[c]) for c in sorted(children[n])]
+        for k, (c, sect) in enumerate(parts):
+            if c is None:
+                continue
+            others = dict(zero)
+            for kk, (_, s2) in enumerate(parts):
+                if kk != k:
+                    others = _fuse(others, link_sectors.get(parts[kk][0], s2) if parts[kk][0] is not None else s2)
+            allowed = {}
+            for q, d in sect.items():
+                comp = 0
+                for up, du in above[n].items():
+                    need = tuple(u - x for u, x in zip(up, q))
+                    comp += others.get(need, 0) * du
+                if comp > 0:
+                    allowed[q] = min(d, comp, chi)
+            qs = sorted(allowed)
+            dims = _cap_dims([allowed[q] for q in qs], chi)
+            link_sectors[c] = {q: d for q, d in zip(qs, dims) if d > 0}
+        for c in sorted(children[n]):
+            # what child c must deliver upwards = its link sectors
+            above[c] = dict(link_sectors[c])
+    inds: Dict[Node, List[Index]] = {n: list(site_of[n]) for n in graph.nodes}
+    for n in order_up[:-1]:
+        qs = sorted(link_sectors[n])
+        link = Index(qs, [link_sectors[n][q] for q in qs], dir=+1, tags=f"Link,{n}")
+        inds[n].append(link.copy(dir=-1))
+        inds[parent[n]].append(link)
+    inds[center].append(Index([total_qn], [1], dir=-1, tags="QN"))
+    tensors = {}
+    for n in sorted(graph.nodes):
+        t = BSTensor.random(inds[n], rng)
+        if not t.blocks:
+            raise RuntimeError(f"randomTTN: node {n} has no symmetry-allowed block")
+        tensors[n] = t.scale(1.0 / t.norm())
+    ttn = TTN(sites, graph, tensors, None)
+    isometrize_full(ttn, center, normalize=True, cutoff=0.0, maxdim=chi)
+    return ttn
+
+
+def default_random_ttn(sites, chi: int, rng: np.random.Generator, total_qn=None) -> TTN:
     graph, sitenodes = default_graph_sitenodes(len(sites))
+    if sites[0].nsect > 1:
+        nq = len(sites[0].qns[0])
+        return random_ttn_qn(sites, graph, sitenodes, chi, (0,) * nq if total_qn is None else total_qn, rng)
     return random_ttn(sites, graph, sitenodes, chi, rng)
 
 
@@ -438,24 +531,76 @@ def update_position_ttn(sysenv: StateEnvsTTN, solver, node: Node, *, time_step=N
     return energy
 
 
+def _fused_sectors(inds: Sequence[Index]) -> Dict[tuple, int]:
+    """charge -> dimension of the fused space of `inds`, charge = sum_i dir_i * qn_i."""
+    out: Dict[tuple, int] = {}
+    nq = len(inds[0].qns[0])
+    for combo in itertools.product(*[range(ix.nsect) for ix in inds]):
+        q = tuple(sum(ix.dir * ix.qns[k][a] for ix, k in zip(inds, combo)) for a in range(nq))
+        out[q] = out.get(q, 0) + int(np.prod([ix.dims[k] for ix, k in zip(inds, combo)]))
+    return out
+
+
+def _cap_dims(dims: List[int], maxdim: int) -> List[int]:
+    """proportional reduction of block dimensions to a total of `maxdim` (src/base/helper_internal_funcs.jl:228-244)."""
+    if sum(dims) <= maxdim:
+        return dims
+    tot = sum(dims)
+    # Julia `round` is round-half-to-even, like Python's
+    d = [max(1, int(round(maxdim * (x / tot)))) for x in dims]
+    diff = sum(d) - maxdim
+    if diff > 0:
+        order = sorted(range(len(d)), key=lambda i: -d[i])
+        for ii in range(min(diff, len(order))):
+            if d[order[ii]] > 1:
+                d[order[ii]] -= 1
+    return d
+
+
+def index_intersection_for_link(indsB: Sequence[Index], indsA: Sequence[Index], maxdim: int, dir: int, tags: str) -> Index:
+    """`indexintersection(indsB, dag.(indsA); maxdim, dir)` (src/base/helper_internal_funcs.jl:171-247) as used by
+    subspace_expand!: the sectors a new link between B(link, indsB...) and A(dag(link), indsA...) can carry.
+    Without QNs the reference takes min(SUM of the dims on either side, maxdim) (:180-186); with QNs the common
+    charges with the smaller of the two fused block dimensions, each capped at maxdim, then reduced proportionally."""
+    if all(ix.nsect == 1 for ix in list(indsB) + list(indsA)):
+        d = min(sum(ix.dim for ix in indsB), sum(ix.dim for ix in indsA), maxdim)
+        return Index([indsB[0].qns[0]], [d], dir=dir, tags=tags)
+    fb = {tuple(-dir * x for x in q): d for q, d in _fused_sectors(indsB).items()}     # flux 0 on B
+    fa = {tuple(dir * x for x in q): d for q, d in _fused_sectors(indsA).items()}      # flux 0 on A (link dagged)
+    qns, dims = [], []
+    for q in sorted(fb):
+        if q in fa:
+            qns.append(q)
+            dims.append(min(fb[q], fa[q], maxdim))
+    if not qns:
+        raise RuntimeError("`indexintersection()`: No common QN blocks present !!")
+    dims = _cap_dims(dims, maxdim)
+    keep = [(q, d) for q, d in zip(qns, dims) if d > 0]
+    return Index([q for q, _ in keep], [d for _, d in keep], dir=dir, tags=tags)
+
+
 def _directsum(A: BSTensor, ia: Index, P: BSTensor, ip: Index, tags: str):
-    """ITensors `directsum(A => ia, P => ip)` for dense tensors: concatenate along one index."""
+    """ITensors `directsum(A => ia, P => ip)`: the new index lists the sectors of `ia`, then those of `ip`; the other
+    indices are shared."""
     oa = [ix for ix in A.inds if ix != ia]
-    Ad = A.permute(oa + [ia]).to_dense()
-    Pd = P.permute([next(jx for jx in P.inds if jx == ix) for ix in oa] + [ip]).to_dense()
-    new = dense_index(ia.dim + ip.dim, ia.dir, tags)
-    return BSTensor.from_dense(oa + [new], np.concatenate([Ad, Pd], axis=-1), keep_zero_blocks=True), new
+    Ap = A.permute(oa + [ia])
+    Pp = P.permute([next(jx for jx in P.inds if jx == ix) for ix in oa] + [ip])
+    new = Index(list(ia.qns) + list(ip.qns), list(ia.dims) + list(ip.dims), dir=ia.dir, tags=tags)
+    out = BSTensor(oa + [new], dtype=np.result_type(A.dtype, P.dtype))
+    for c, blk in Ap.blocks.items():
+        out.blocks[c] = blk.copy()
+    for c, blk in Pp.blocks.items():
+        out.blocks[c[:-1] + (c[-1] + ia.nsect,)] = blk.copy()
+    return out, new
 
 
 def subspace_expand(psi: TTN, node: Node, nextnode: Node, max_expand_dim: int, noise: float, rng: np.random.Generator):
     """update_site_ttn.jl:75-109: pad the link between `node` and `nextnode` with random directions of relative size
-    `noise`; dense `indexintersection` = min(SUM of the dims on either side, max_expand_dim)
-    (src/base/helper_internal_funcs.jl:180-186)."""
+    `noise` on both tensors."""
     A, B = psi.tensors[node], psi.tensors[nextnode]
     ind_to_update = commoninds(B, A)[0]
     indsA, indsB = uniqueinds(A, B), uniqueinds(B, A)
-    padd = min(sum(ix.dim for ix in indsB), sum(ix.dim for ix in indsA), max_expand_dim)
-    ind_padB = dense_index(padd, ind_to_update.dir, "pad")
+    ind_padB = index_intersection_for_link(indsB, indsA, max_expand_dim, ind_to_update.dir, "pad")
     padB = BSTensor.random([ind_padB] + list(indsB), rng)
     padB = padB.scale(noise * B.norm() / padB.norm())
     enlargedB, sumB = _directsum(B, ind_to_update, padB, ind_padB, ind_to_update.tags)
@@ -466,6 +611,38 @@ def subspace_expand(psi: TTN, node: Node, nextnode: Node, max_expand_dim: int, n
     ia = next(ix for ix in A.inds if ix == ind_to_update)
     enlargedA, sumA = _directsum(A, ia, padA, ind_padA, ind_to_update.tags)
     psi.tensors[node] = enlargedA.replaceinds([sumA], [sumB.copy(dir=-sumB.dir)])
+
+
+def product_ttn(sites: Sequence[Index], states: Sequence[int], graph: Graph | None = None,
+                sitenodes: Dict[int, Node] | None = None) -> TTN:
+    """Product state on the (default) tree with QN-conserving sites: every link is one sector of dimension 1
+    carrying the charge of the sites below it; the centre node holds the dummy "QN" index with the total charge
+    (randomTTN attaches the same index, ttn_generators.jl:221-223).  states[n] = sector number of site n+1."""
+    if graph is None:
+        graph, sitenodes = default_graph_sitenodes(len(sites))
+    nq = len(sites[0].qns[0])
+    inds: Dict[Node, List[Index]] = {node: [] for node in graph.nodes}
+    coords: Dict[Node, List[int]] = {node: [] for node in graph.nodes}
+    charge: Dict[Node, tuple] = {node: (0,) * nq for node in graph.nodes}
+    for b, s in enumerate(sites):
+        node = sitenodes[b + 1]
+        inds[node].append(s)
+        coords[node].append(states[b])
+        charge[node] = tuple(a + s.dir * c for a, c in zip(charge[node], s.qns[states[b]]))
+    center = find_eccentric_central_node(graph, list(sitenodes.values()))
+    for node in nodes_from_bfs(graph, center, reverse=True)[:-1]:
+        nxt = nextnode_in_path(graph, node, center)
+        link = Index([charge[node]], [1], dir=+1, tags=f"Link,{node}")
+        inds[node].append(link.copy(dir=-1))
+        coords[node].append(0)
+        inds[nxt].append(link)
+        coords[nxt].append(0)
+        charge[nxt] = tuple(a + c for a, c in zip(charge[nxt], charge[node]))
+    qnindex = Index([charge[center]], [1], dir=-1, tags="QN")
+    inds[center].append(qnindex)
+    coords[center].append(0)
+    tensors = {node: BSTensor(inds[node], {tuple(coords[node]): np.ones([1] * len(inds[node]))}) for node in graph.nodes}
+    return TTN(sites, graph, tensors, center)
 
 
 # ------------------------------------------------------------------------------------------ sweeps

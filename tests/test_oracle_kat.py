@@ -392,3 +392,27 @@ def test_ttn_optimize_reaches_the_tfi_ground_state(N):
     v = ot.ttn_to_dense(psi)
     Hd = oc.coupling_model_to_dense(M)
     assert abs(v @ Hd @ v / (v @ v) - E) < 1e-10
+
+
+def test_ttn_with_quantum_numbers_heisenberg_ground_state():
+    """The model of the reference's TTN test (test/test_TTN.jl:7-38: S=1/2 Heisenberg CouplingModel, QN-conserving
+    sites, default_randomTTN in the Sz = 0 sector, optimize! with noise): the random tree state lives in the
+    right charge sector, and the optimisation reaches the ED energy up to the bond-dimension truncation."""
+    from oracle import couplingmodel as oc, models as om, ttn as ot
+    from tests import ed
+    N = 8
+    sites = om.siteinds("S=1/2", N)
+    M = oc.heisenberg_coupling_model(sites, merge=True)
+    rng = np.random.default_rng(3)
+    psi0 = ot.default_random_ttn(sites, 6, rng)
+    v = ot.ttn_to_dense(psi0)
+    nz = np.nonzero(np.abs(v) > 1e-14)[0]
+    assert abs(np.linalg.norm(v) - 1.0) < 1e-12 and all(bin(int(i)).count("1") == N // 2 for i in nz)
+    assert any(ix.tags == "QN" for ix in psi0[psi0.orthocenter].inds)
+    prm = ot.OptimizeParamsTTN(maxdim=[12, 24], nsweeps=[4, 3], cutoff=1e-14, noise=[1e-2, 0.0], noisedecay=3,
+                               disable_noise_after=3)
+    E, psi, sw = ot.optimize(psi0, M, prm, ot.default_sweeppath(psi0), rng=rng)
+    E0 = ed.lowest_energies(N, 1, 1)[0]
+    assert 0 <= E - E0 < 1e-5
+    w = ot.ttn_to_dense(psi)
+    assert all(bin(int(i)).count("1") == N // 2 for i in np.nonzero(np.abs(w) > 1e-12)[0])     # the sector is conserved
