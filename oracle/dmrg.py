@@ -363,14 +363,16 @@ def fullsweep(sysenv: StateEnvs, solver, nsite: int, swdata: SweepData, **kw):
 def dynamic_fullsweep(sysenv: StateEnvs, solver, swdata: SweepData, eigthreshold: float = 1e-12, extendat=None, **kw):
     """src/mps/sweep.jl:257-382: bond by bond one-site update where the smallest kept Schmidt weight of the
     previous half sweep is below `eigthreshold` or the bond is saturated at `maxdim`, two-site update otherwise.
-    The first sweep (and every `extendat`-th) is a plain two-site sweep for every PH but ProjMPO, which needs the
-    Global Subspace Expansion (`krylov_extend!`, not restated)."""
+    The first sweep (and every `extendat`-th) is a Global Subspace Expansion (oracle/gse.py) followed by a one-site
+    sweep for StateEnvs{ProjMPO}, a plain two-site sweep for every other PH."""
     from .projmpo import ProjMPO as _ProjMPO
     maxdim = kw.get("maxdim", None)
     first = swdata.sweepcount == 0 or (extendat is not None and (swdata.sweepcount + 1) % extendat == 0)
     if first:
         if type(sysenv.PH) is _ProjMPO:
-            raise NotImplementedError("dynamic_fullsweep! on StateEnvs{ProjMPO} starts with krylov_extend! (not restated)")
+            from .gse import krylov_extend
+            krylov_extend(sysenv, **kw)                       # Global Subspace Expansion, then a pure one-site sweep
+            return fullsweep(sysenv, solver, 1, swdata, **kw)
         return fullsweep(sysenv, solver, 2, swdata, **kw)
     psi = sysenv.psi
     if (not psi.isortho()) or psi.orthocenter() != 1:

@@ -416,3 +416,56 @@ def test_ttn_with_quantum_numbers_heisenberg_ground_state():
     assert 0 <= E - E0 < 1e-5
     w = ot.ttn_to_dense(psi)
     assert all(bin(int(i)).count("1") == N // 2 for i in np.nonzero(np.abs(w) > 1e-12)[0])     # the sector is conserved
+
+
+# ---------------------------------------------------------------------------------------------- GSE (section 8f rank 1, oracle only)
+def test_apply_mpo_and_global_subspace_expansion():
+    """apply(H, psi) restatement is exact without truncation and near-optimal with it; krylov_extend! leaves the state
+    untouched while enlarging the bonds with right-orthonormal bases (src/mps/sweep.jl:399-555)."""
+    from oracle import dmrg as od, gse, models as om
+    N = 8
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites)
+    Hd = om.mpo_to_dense(H)
+    qn, dm = om.gaussian_link_sectors(12, 1.3, 4, step=1)
+    mps = od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(2)))
+    od.orthogonalize(mps, 1)
+    v = om.mps_to_dense(mps.t)
+    w = om.mps_to_dense(gse.apply_mpo(H, mps, maxdim=None, cutoff=1e-15).t)
+    assert np.abs(w - Hd @ v).max() < 1e-12 * np.abs(Hd @ v).max()
+    phi = gse.apply_mpo(H, mps, maxdim=8, cutoff=1e-15)
+    assert max(A.inds[2].dim for A in phi.t[:-1]) == 8
+    w2 = om.mps_to_dense(phi.t)
+    assert abs(np.vdot(w2, Hd @ v)) / np.linalg.norm(w2) / np.linalg.norm(Hd @ v) > 0.99
+    psi = od.MPS(om.neel_mps(sites))
+    v0 = om.mps_to_dense(psi.t)
+    gse.krylov_extend_mps(psi, H, extension_krylovdim=3)
+    v1 = om.mps_to_dense(psi.t)
+    assert abs(abs(np.vdot(v0, v1)) - 1.0) < 1e-13 and abs(np.linalg.norm(v1) - 1.0) < 1e-13
+    assert max(A.inds[2].dim for A in psi.t[:-1]) > 1 and psi.isortho() and psi.orthocenter() == 1
+    for j in range(2, N + 1):
+        M = psi[j].to_dense().reshape(psi[j].inds[0].dim, -1)
+        assert np.abs(M @ M.conj().T - np.eye(M.shape[0])).max() < 1e-12
+
+
+@pytest.mark.parametrize("ts", [-0.02, -0.02j])
+def test_dynamic_tdvp_on_a_single_mpo_follows_exact_evolution(ts):
+    """The reference's TDVP test flow (test/test_MPS_TDVP.jl:50-66: tdvpsweep!(engine, -0.01im; nsite = "dynamic",
+    maxdim = 20, cutoff = 1E-12, extendat = 5) on an MPO): GSE + one-site sweep at sweeps 1, 5, 10, dynamic
+    one-/two-site sweeps in between, against exp(tH)|Neel>."""
+    import scipy.linalg as sl
+    from oracle import dmrg as od, models as om
+    N = 8
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites)
+    Hd = om.mpo_to_dense(H)
+    psi0 = od.MPS(om.neel_mps(sites))
+    v0 = om.mps_to_dense(psi0.t)
+    eng = od.TDVPEngine(psi0, H)
+    for _ in range(10):
+        od.tdvpsweep(eng, ts, "dynamic", maxdim=20, cutoff=1e-12, extendat=5)
+    v = sl.expm(10 * ts * Hd) @ v0
+    v /= np.linalg.norm(v)
+    w = om.mps_to_dense(eng.sysenv.psi.t)
+    assert abs(abs(np.vdot(v, w)) - 1.0) < 1e-9
+    assert abs(eng.swdata.energy[-1] - np.real(np.vdot(v, Hd @ v))) < 1e-5
