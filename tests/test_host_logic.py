@@ -247,3 +247,23 @@ def test_tdvpsweep_argument_checks():
         tdvp.tdvpsweep(E(), -0.1, 2, extendat=5)
     with pytest.raises(RuntimeError):
         T.exp_solver(None, None, None)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU arm of the driver: the oracle port timed on the host cores) prints one JSON line
+    with the same metric / unit / config as the GPU arm plus `impl`, `cpu_baseline` and a zero-copy `e2e`."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--chi", "128",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "heff_apply_fp64_tflops" and line["unit"] == "TFLOP/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1 and line["warmup"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and line["config"]["chi"] == 128
+    # the other ranks of a torchrun launch exit silently
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--chi", "128",
+                          "--steps", "1", "--warmup", "1", "--gpus", "2"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
