@@ -1,7 +1,8 @@
 """tnl_b200: B200-native hot path of TenNetLib.jl's DMRG sweeps behind the reference's own API names.
 
 Product code only: CUDA kernels + C ABI in `csrc/` (libtnl_b200.so) and the host-side mirror of the reference
-interface (`StateEnvs`, `eig_solver`, `update_position`, `fullsweep`, `DMRGParams`, `dmrg_`/`dmrg2`).
+interface (`StateEnvs` on an MPO / a vector of MPOs / a `CouplingModel`, `eig_solver`, `exp_solver`,
+`update_position`, `fullsweep`, `dynamic_fullsweep`, `DMRGParams`, `dmrg_`/`dmrg1`/`dmrg2`, `TDVPEngine`, `tdvpsweep`).
 Nothing here imports `oracle/`; there is no CPU fallback."""
 from ._lib import EXPORTED, TnlError, load, so_path
 from .couplingmodel import CouplingModel

@@ -31,7 +31,8 @@ def eig_solver(env, phi0, time_step=None, **kwargs):
 def exp_solver(env, phi0, time_step, **kwargs):
     """src/base/solver.jl:66-88: phi <- exp(time_step * H_eff) phi0 with KrylovKit.exponentiate's Lanczos
     integrator on the device (`tnl_exponentiate`).  Returns (NaN, phi) like the reference; the caller evaluates
-    the energy.  Complex time steps need complex tensors, which this build does not have: the C ABI rejects them."""
+    the energy.  A complex time step (real-time evolution, `time_step = -im*dt`) promotes a real `phi0` to a
+    ComplexF64 (planar) device tensor in place."""
     if time_step is None:
         raise RuntimeError(f"`exp_solver()` is not defined with `time_step={time_step}` !!")
     if not kwargs.get("ishermitian", True):
