@@ -62,6 +62,15 @@ def case_dmrg_model(kind, N, params, model, **model_kw):
                 maxtruncerr=sw.maxtruncerr)
 
 
+def case_config0(params):
+    """BASELINE.json configs[0]: S=1/2 Heisenberg chain N=20, two-site DMRG, maxdim 20 -> 64 (test_MPS_DMRG.jl scale)."""
+    sites = om.siteinds("S=1/2", 20)
+    H = om.heisenberg_mpo(sites)
+    e, psi, sw = od.dmrg2(od.MPS(om.neel_mps(sites)), H, od.DMRGParams(**params))
+    return dict(kind="S=1/2", N=20, params=params, energy=sw.energy, maxchi=sw.maxchi, maxtruncerr=sw.maxtruncerr,
+                entropy=sw.entropy, linkdims=[A.inds[2].dim for A in psi.t[:-1]], ed_literature=-8.682473334399)
+
+
 def case_ttn(N, h, chi0, seed, params):
     sites = ot.dense_siteinds(N)
     M = oc.tfi_coupling_model(sites, h=h)
@@ -84,6 +93,8 @@ def build():
         dmrg_models=[case_dmrg_model("S=1/2", 8, noisy, "cm", merge=True),
                      case_dmrg_model("S=1/2", 8, noisy, "cm", merge=False),
                      case_dmrg_model("S=1", 8, dict(maxdim=[10, 20], nsweeps=[2, 2], cutoff=1e-13, noise=[1e-4, 0.0]), "mposum")],
+        config0=[case_config0(dict(nsweeps=[5, 5], maxdim=[20, 64], cutoff=1e-14, noise=[1e-3, 0.0], noisedecay=2,
+                                   disable_noise_after=2))],
         ttn=[case_ttn(8, 1.0, 4, 1, dict(maxdim=[8, 16], nsweeps=[4, 3], cutoff=1e-14, noise=[1e-2, 0.0], noisedecay=5,
                                          disable_noise_after=3))],
     )

@@ -82,3 +82,15 @@ def test_oracle_reproduces_ttn_fixture():
     r = case_ttn(g["N"], g["h"], g["chi0"], g["seed"], g["params"])
     assert r["maxchi"] == g["maxchi"]
     assert abs(r["energy"][-1] - g["energy"][-1]) < 1e-9 and abs(g["energy"][-1] - g["ed"]) < 1e-7
+
+
+def test_oracle_reproduces_baseline_config0_fixture():
+    """BASELINE.json configs[0] (S=1/2 N=20, maxdim 20 -> 64): the reference's CPU-runnable case, against the fixture
+    and the literature ground-state energy."""
+    from tests.golden.make_golden_r01b import case_config0
+    g = G2["config0"][0]
+    r = case_config0(g["params"])
+    assert r["maxchi"] == g["maxchi"] and r["linkdims"] == g["linkdims"]
+    assert np.abs(np.array(r["energy"]) - np.array(g["energy"])).max() < 1e-7
+    assert abs(r["energy"][-1] - g["energy"][-1]) < 1e-11
+    assert abs(g["energy"][-1] - g["ed_literature"]) < 1e-10
