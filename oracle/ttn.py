@@ -8,7 +8,8 @@ QN-conserving sites with the dummy "QN" index at the centre node (the model of t
   /root/reference/src/ttn/ttn.jl:266-384                     moveisometry_to_next!, isometrize_full!, isometrize!
   /root/reference/src/ttn/linktensors.jl:35-221,231-262      LinkTensorsTTN(psi, M), move_linktensors*, product
   /root/reference/src/ttn/helper_internal_funcs.jl:22-47     _get_links
-  /root/reference/src/ttn/state_envs_ttn.jl:120-157          position!, product
+  /root/reference/src/ttn/linkproj.jl:14-224                 LinkProjTTN (excited states: weight * |M><M|)
+  /root/reference/src/ttn/state_envs_ttn.jl:13-157           StateEnvsTTN, position!, product
   /root/reference/src/ttn/update_site_ttn.jl:42-109          update_position!, subspace_expand!
   /root/reference/src/ttn/sweep_ttn.jl:36-243                SweepDataTTN, default_sweeppath, fullsweep!
   /root/reference/src/ttn/optimize_ttn.jl:47-218             OptimizeParamsTTN, optimize!
@@ -502,11 +503,77 @@ def product(env: LinkTensorsTTN, psi: TTN, v: BSTensor) -> BSTensor:
     return out
 
 
-class StateEnvsTTN:
-    """state_envs_ttn.jl:13-45 (CouplingModel environment, no penalised states)."""
+class LinkProjTTN:
+    """Projector environments for a fixed TTN `M` (src/ttn/linkproj.jl:14-224): tensors[link] = overlap of the part
+    of the tree behind the link, dag(prime(M[node]; tags = "Link")) * (tensors on the other links) * psi[node]."""
 
-    def __init__(self, psi: TTN, M: CouplingModel):
+    def __init__(self, psi: TTN, M: TTN):
+        assert [s.id for s in psi.sites] == [s.id for s in M.sites]
+        if psi.orthocenter is None:
+            raise RuntimeError("`LinkProjTTN()`: TTN does not have a proper orthogonality center !!")
+        self.M = M
+        self.tensors: Dict[frozenset, BSTensor] = {}
+        # both trees must share the dummy QN index (linkproj.jl:201-211)
+        for node, t in psi.tensors.items():
+            qi = [ix for ix in t.inds if ix.tags == "QN"]
+            if qi:
+                qm = next(ix for tm in M.tensors.values() for ix in tm.inds if ix.tags == "QN")
+                if not qm.same_space(qi[0]):
+                    raise RuntimeError("`LinkProjTTN()`: TTNs do have same global QN !!")
+                psi.tensors[node] = t.replaceinds([qi[0]], [qm])
+        oc = psi.orthocenter
+        path = nodes_from_bfs(psi.graph, oc, reverse=True)
+        for n1 in path[:-1]:
+            self.move_to_next(psi, n1, nextnode_in_path(psi.graph, n1, oc))
+
+    def _mdag(self, node: Node) -> BSTensor:
+        t = self.M[node]
+        return t.prime(1, [ix for ix in t.inds if "Link" in ix.tags]).dag()
+
+    def move_to_next(self, psi: TTN, node: Node, nextnode: Node):
+        next_link, prev_links = _get_links(psi, node, nextnode)
+        t = self._mdag(node)
+        for x in prev_links:
+            if x in self.tensors:
+                t = contract(t, self.tensors[x])
+        self.tensors[next_link] = contract(t, psi[node])
+
+    def move(self, psi: TTN, source: Node, destination: Node, node_to_skip=None):
+        if source == destination:
+            return
+        path = shortest_path(psi.graph, source, destination)
+        for a, b in zip(path[:-1], path[1:]):
+            if a == node_to_skip:
+                continue
+            self.move_to_next(psi, a, b)
+
+    def contract_v(self, psi: TTN, v: BSTensor | None) -> BSTensor:
+        oc = psi.orthocenter
+        t = self._mdag(oc)
+        for x in _get_links(psi, oc):
+            if x in self.tensors:
+                t = contract(t, self.tensors[x])
+        return t if v is None else contract(t, v)
+
+    def product(self, psi: TTN, v: BSTensor) -> BSTensor:
+        ov = self.contract_v(psi, v)                       # <M|v>, order 0
+        m = self.contract_v(psi, None).dag()               # |m> in the indices of the centre tensor
+        if ov.rank != 0 or m.rank != v.rank:
+            raise RuntimeError("The order of the LinkProjTTN-ITensor product P*v is not equal to the order of the ITensor v")
+        return m.scale(ov.scalar()).noprime()
+
+
+class StateEnvsTTN:
+    """state_envs_ttn.jl:13-66: StateEnvsTTN(psi, M::CouplingModel[, Ms::Vector{TTN}; weight])."""
+
+    def __init__(self, psi: TTN, M: CouplingModel, Ms: Sequence[TTN] | None = None, weight: float = -1.0):
         self.psi = psi.copy()
+        self.projs: List[LinkProjTTN] = []
+        self.weight = weight
+        if Ms:
+            if weight <= 0.0:
+                raise ValueError(f"`weight` parameter should be > 0.0 (value passed was `weight={weight}`)")
+            self.projs = [LinkProjTTN(self.psi, m) for m in Ms]
         self.env = link_tensors_from_model(self.psi, M)
 
     def position(self, node: Node, *, maxdim=None, mindim=1, cutoff=FLOAT64_THRESHOLD, svd_alg="divide_and_conquer",
@@ -514,9 +581,14 @@ class StateEnvsTTN:
         oc = self.psi.orthocenter
         isometrize(self.psi, node, normalize=normalize, maxdim=maxdim, mindim=mindim, cutoff=cutoff, svd_alg=svd_alg)
         move_linktensors(self.env, self.psi, oc, node, node_to_skip=node_to_skip)
+        for p in self.projs:
+            p.move(self.psi, oc, node, node_to_skip=node_to_skip)
 
     def product(self, v: BSTensor) -> BSTensor:
-        return product(self.env, self.psi, v)
+        Pv = product(self.env, self.psi, v)
+        for p in self.projs:                               # EnvCouplingModelProjTTN.product (environment.jl:95-101)
+            Pv = Pv.add(p.product(self.psi, v).permute(Pv.inds), self.weight)
+        return Pv
 
     __call__ = product
 
@@ -754,7 +826,8 @@ def optimize_(sysenv: StateEnvsTTN, params: OptimizeParamsTTN, sweeppath: Sequen
     return swdata
 
 
-def optimize(psi0: TTN, H: CouplingModel, params: OptimizeParamsTTN, sweeppath: Sequence[Node], rng=None, **kw):
-    sysenv = StateEnvsTTN(psi0, H)
+def optimize(psi0: TTN, H: CouplingModel, params: OptimizeParamsTTN, sweeppath: Sequence[Node], rng=None, Ms=None,
+             weight: float = -1.0, **kw):
+    sysenv = StateEnvsTTN(psi0, H, Ms, weight)
     sw = optimize_(sysenv, params, sweeppath, rng=rng, **kw)
     return sw.energy[-1], sysenv.psi, sw

@@ -469,3 +469,31 @@ def test_dynamic_tdvp_on_a_single_mpo_follows_exact_evolution(ts):
     w = om.mps_to_dense(eng.sysenv.psi.t)
     assert abs(abs(np.vdot(v, w)) - 1.0) < 1e-9
     assert abs(eng.swdata.energy[-1] - np.real(np.vdot(v, Hd @ v))) < 1e-5
+
+
+def test_ttn_excited_state_with_projector_penalty():
+    """StateEnvsTTN(psi, H, Ms; weight) (src/ttn/linkproj.jl, src/ttn/environment.jl:95-101; the second half of
+    test/test_TTN.jl): first excited state of the TFI chain (no QNs) and of the Heisenberg chain in the Sz = 0 sector
+    (QN tree) against exact diagonalisation."""
+    from oracle import couplingmodel as oc, models as om, ttn as ot
+    from tests import ed
+    N = 8
+    sites = ot.dense_siteinds(N)
+    M = oc.tfi_coupling_model(sites, h=1.5)
+    w = np.linalg.eigvalsh(oc.coupling_model_to_dense(M))
+    rng = np.random.default_rng(1)
+    psi0 = ot.default_random_ttn(sites, 4, rng)
+    prm = ot.OptimizeParamsTTN(maxdim=[16], nsweeps=[6], cutoff=1e-14, noise=1e-2, noisedecay=5, disable_noise_after=3)
+    E0, gs, _ = ot.optimize(psi0, M, prm, ot.default_sweeppath(psi0), rng=rng)
+    E1, ex, _ = ot.optimize(psi0, M, prm, ot.default_sweeppath(psi0), rng=rng, Ms=[gs], weight=10.0)
+    assert abs(E0 - w[0]) < 1e-9 and abs(E1 - w[1]) < 1e-8
+    assert abs(ot.ttn_to_dense(gs) @ ot.ttn_to_dense(ex)) < 1e-8
+    sites = om.siteinds("S=1/2", N)
+    M = oc.heisenberg_coupling_model(sites, merge=True)
+    rng = np.random.default_rng(3)
+    psi0 = ot.default_random_ttn(sites, 6, rng)
+    prm = ot.OptimizeParamsTTN(maxdim=[16], nsweeps=[6], cutoff=1e-14, noise=1e-2, noisedecay=3, disable_noise_after=3)
+    E0, gs, _ = ot.optimize(psi0, M, prm, ot.default_sweeppath(psi0), rng=rng)
+    E1, ex, _ = ot.optimize(psi0, M, prm, ot.default_sweeppath(psi0), rng=rng, Ms=[gs], weight=10.0)
+    e = ed.lowest_energies(N, 1, 2)
+    assert abs(E0 - e[0]) < 1e-9 and abs(E1 - e[1]) < 1e-7
