@@ -81,19 +81,31 @@ def _outer(a: BSTensor, b: BSTensor) -> BSTensor:
     return contract(a, b)                # no common indices: outer product
 
 
-def _directsum_pair(terms: List[List[BSTensor]]) -> List[BSTensor]:
-    """Exact direct sum of two-site terms over their single OpLink (ITensors `directsum`, sectors kept apart)."""
-    qns = [t[0].inds[-1].qns[0] for t in terms]
-    link = Index(qns, [1] * len(terms), dir=-1, tags="OpLink")
-    a0, b0 = terms[0]
-    A = BSTensor([a0.inds[0], a0.inds[1], link])
-    B = BSTensor([link.copy(dir=+1), b0.inds[1], b0.inds[2]])
-    for k, (a, b) in enumerate(terms):
-        for c, blk in a.blocks.items():
-            A.blocks[(c[0], c[1], k)] = blk.copy()
-        for c, blk in b.blocks.items():
-            B.blocks[(k, c[1], c[2])] = blk.copy()
-    return [A, B]
+def _directsum_chain(terms: List[List[BSTensor]]) -> List[BSTensor]:
+    """Exact direct sum of terms with the same support over their OpLinks (`_directsum`,
+    src/base/helper_internal_funcs.jl:73-110; ITensors `directsum` keeps the sectors of the summands apart): link b of
+    the sum has one dim-1 sector per term; tensor b of term k sits in sector (k, k) of its two links.
+    Index order from `_add_oplinks`: first (s', s, r), middle (l, s', s, r), last (l, s', s)."""
+    n = len(terms[0])
+    K = len(terms)
+    links = []
+    for bnd in range(n - 1):
+        qns = [t[bnd].inds[-1].qns[0] for t in terms]
+        links.append(Index(qns, [1] * K, dir=-1, tags="OpLink"))
+    out = []
+    for pos in range(n):
+        t0 = terms[0][pos]
+        sp = next(ix for ix in t0.inds if "OpLink" not in ix.tags and ix.plev == 1)
+        sk = next(ix for ix in t0.inds if "OpLink" not in ix.tags and ix.plev == 0)
+        inds = ([links[pos - 1].copy(dir=+1)] if pos > 0 else []) + [sp, sk] + ([links[pos]] if pos < n - 1 else [])
+        T = BSTensor(inds)
+        for k, term in enumerate(terms):
+            for c, blk in term[pos].blocks.items():
+                site_c = c[1:3] if pos > 0 else c[0:2]
+                cc = ((k,) if pos > 0 else ()) + tuple(site_c) + ((k,) if pos < n - 1 else ())
+                T.blocks[cc] = blk.copy()
+        out.append(T)
+    return out
 
 
 def coupling_model(os: Sequence, sites: Sequence[Index], merge: bool = True) -> CouplingModel:
@@ -120,8 +132,7 @@ def coupling_model(os: Sequence, sites: Sequence[Index], merge: bool = True) -> 
     terms: List[Dict[int, BSTensor]] = [dict() for _ in range(N)]
     for pos, lst in collected.items():
         if merge and len(lst) > 1:
-            assert len(pos) == 2, "oracle constructor merges two-site terms only"
-            lst = [_directsum_pair(lst)]
+            lst = [_directsum_chain(lst)]
         for tensors in lst:
             tid = gen_id()
             for p, t in zip(pos, tensors):

@@ -826,3 +826,33 @@ def test_baseline_config0_matches_fixture_and_literature(ctx):
     assert de.max() < 1e-6 * abs(g["energy"][-1])
     assert de[-3:].max() < 1e-9 * abs(g["energy"][-1])
     assert abs(e - g["ed_literature"]) < 1e-9
+
+
+def test_coupling_model_with_multi_site_terms_matches_oracle(ctx):
+    """CouplingModel terms with three and four operators (middle tensors with two open OpLinks), terms skipping
+    several sites, merged and unmerged: H_eff apply at several positions and a DMRG run against the oracle."""
+    T, ob, od, ok, om, op = _imports()
+    from oracle import couplingmodel as oc
+    from tests.test_oracle_kat import _multi_site_model
+    N = 8
+    sites, os_ = _multi_site_model(om, oc, N)
+    qn, dm = om.gaussian_link_sectors(8, 1.3, 4, step=1)
+    mps = od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(4)))
+    for merge in (True, False):
+        M = oc.coupling_model(os_, sites, merge=merge)
+        for nsite, pos in ((2, 3), (2, 1), (2, 7), (1, 4)):
+            od.orthogonalize(mps, pos)
+            env_o = od.StateEnvs(mps, M)
+            env_d = T.StateEnvs(ctx, mps.t, M, llim=pos - 1, rlim=pos + 1)
+            env_o.set_nsite(nsite); env_o.position(pos)
+            env_d.set_nsite(nsite); env_d.position(pos)
+            phi_o = ob.contract(env_o.psi[pos], env_o.psi[pos + 1]) if nsite == 2 else env_o.psi[pos]
+            phi_d = env_d.make_phi(pos) if nsite == 2 else env_d.site_tensor(pos)
+            ref = env_o.product(phi_o).permute(phi_o.inds).to_dense()
+            assert rel(env_d.product(phi_d).to_host().to_dense(), ref) < 1e-12
+    M = oc.coupling_model(os_, sites, merge=True)
+    prm = dict(maxdim=[16, 32], nsweeps=[3, 3], cutoff=1e-14, noise=[1e-3, 0.0])
+    Eo, _, swo = od.dmrg2(od.MPS(om.neel_mps(sites)), M, od.DMRGParams(**prm))
+    Ed, _, swd = T.dmrg2(ctx, om.neel_mps(sites), M, T.DMRGParams(**prm), outputlevel=0)
+    assert swd.maxchi[-1] == swo.maxchi[-1]
+    assert abs(Ed - Eo) < 1e-9 * abs(Eo)

@@ -497,3 +497,51 @@ def test_ttn_excited_state_with_projector_penalty():
     E1, ex, _ = ot.optimize(psi0, M, prm, ot.default_sweeppath(psi0), rng=rng, Ms=[gs], weight=10.0)
     e = ed.lowest_energies(N, 1, 2)
     assert abs(E0 - e[0]) < 1e-9 and abs(E1 - e[1]) < 1e-7
+
+
+def _multi_site_model(om, oc, N=8):
+    sites = om.siteinds("S=1/2", N)
+    os = []
+    for j in range(1, N):
+        os += [(1.0, ("Sz", j), ("Sz", j + 1)), (0.5, ("S+", j), ("S-", j + 1)), (0.5, ("S-", j), ("S+", j + 1))]
+    os += [(0.7, ("S+", 1), ("Sz", 3), ("S-", 4)), (0.7, ("S-", 1), ("Sz", 3), ("S+", 4)),
+           (-0.4, ("Sz", 2), ("Sz", 4), ("Sz", 5), ("Sz", 7)), (0.3, ("Sz", 3)),
+           (0.2, ("S+", 2), ("S-", 6)), (0.2, ("S-", 2), ("S+", 6))]
+    return sites, os
+
+
+def test_coupling_model_with_three_and_four_site_terms():
+    """Terms with more than two operators (middle tensors carry two OpLinks; merged terms are direct sums over both),
+    terms that skip several sites and a one-site term: dense operator, projected expectation values and DMRG energy."""
+    from oracle import blocksparse as ob, couplingmodel as oc, dmrg as od, models as om
+    N = 8
+    sites, os = _multi_site_model(om, oc, N)
+    S = {"Sz": np.diag([0.5, -0.5]), "S+": np.array([[0, 1.0], [0, 0]]), "S-": np.array([[0, 0], [1.0, 0]])}
+
+    def at(ops):
+        mats = [np.eye(2)] * N
+        for name, p in ops:
+            mats[p - 1] = S[name]
+        out = np.eye(1)
+        for m in mats:
+            out = np.kron(out, m)
+        return out
+    Hk = sum(t[0] * at(t[1:]) for t in os)
+    qn, dm = om.gaussian_link_sectors(8, 1.3, 4, step=1)
+    mps = od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(4)))
+    for merge in (True, False):
+        M = oc.coupling_model(os, sites, merge=merge)
+        assert sorted({t.rank for terms in M.terms for t in terms.values()}) == [2, 3, 4]
+        assert np.abs(oc.coupling_model_to_dense(M) - Hk).max() < 1e-14
+        for nsite, pos in ((2, 3), (2, 1), (2, 7), (1, 4), (1, 8)):
+            od.orthogonalize(mps, pos)
+            P = oc.ProjCouplingModel(M)
+            P.set_nsite(nsite); P.position(mps.t, pos)
+            phi = ob.contract(mps[pos], mps[pos + 1]) if nsite == 2 else mps[pos]
+            v = om.mps_to_dense(mps.t)
+            assert abs(ob.inner(phi, P.product(phi)) / ob.inner(phi, phi) - v @ Hk @ v / (v @ v)) < 1e-12
+    M = oc.coupling_model(os, sites, merge=True)
+    E, _, _ = od.dmrg2(od.MPS(om.neel_mps(sites)), M,
+                       od.DMRGParams(maxdim=[16, 32], nsweeps=[3, 3], cutoff=1e-14, noise=[1e-3, 0.0]))
+    sel = [i for i in range(2 ** N) if bin(i).count("1") == N // 2]
+    assert abs(E - np.linalg.eigvalsh(Hk[np.ix_(sel, sel)])[0]) < 1e-10
