@@ -48,9 +48,8 @@ int tnl_timer_start(tnl_ctx_t ctx, int32_t slot); /* slot 0..3 */
 int tnl_timer_stop(tnl_ctx_t ctx, int32_t slot, double* milliseconds);
 /* kernel self test / micro-benchmark: random C = op(A) op(B) with the grouped DGEMM kernel; returns the average
  * launch time and (verify != 0) the max abs deviation from a naive FP64 reference kernel */
-int tnl_gemm_selftest(tnl_ctx_t ctx, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB, int32_t variant,
-                      int32_t reps, int32_t verify, double* ms, double* maxerr);
-int tnl_set_gemm_variant(tnl_ctx_t ctx, int32_t variant); /* tuning knob: main-loop variant of the DGEMM kernel */
+int tnl_gemm_selftest(tnl_ctx_t ctx, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB, int32_t reps,
+                      int32_t verify, double* ms, double* maxerr);
 /* per-launch CUDA-event profile of the grouped DGEMM launches (those with 128x128 tiles): enable, run, read
  * (read synchronises, sums the launch durations and algorithmic flops, and clears the records) */
 int tnl_profile_gemm(tnl_ctx_t ctx, int32_t enable);
@@ -67,6 +66,9 @@ int tnl_profile_categories(tnl_ctx_t ctx, double* out8);
 int tnl_comm_unique_id(char* out128);
 int tnl_comm_init(tnl_ctx_t ctx, const char* uid128, int32_t rank, int32_t world);
 int tnl_comm_destroy(tnl_ctx_t ctx);
+/* enable = 0: every rank computes the whole replicated problem without collectives (the unsharded result the
+ * sharded path is checked against, bench.py `parity`); enable = 1 (default after tnl_comm_init): sharded. */
+int tnl_comm_set_sharding(tnl_ctx_t ctx, int32_t enable);
 int tnl_shard_range(int32_t dim, int32_t world, int32_t sector, int32_t rank, int32_t* start, int32_t* count);
 /* collective micro-benchmark on the library stream: kind 0 = all-reduce of n doubles, 1 = reduce-scatter
  * (n per rank), 2 = all-gather (n per rank); returns the average milliseconds per call */
@@ -96,6 +98,9 @@ int tnl_tensor_index(tnl_tensor_t t, int32_t which, int32_t* nsect, int32_t* dir
 int tnl_tensor_export_size(tnl_tensor_t t, int64_t* nblocks, int64_t* nelem);
 int tnl_tensor_export(tnl_tensor_t t, int32_t* coords, int64_t* offsets, double* data);
 int tnl_tensor_fill_random(tnl_tensor_t t, uint64_t seed); /* uniform [-1,1), counter based */
+/* T(..., i, ...) *= values[i] along index `which` (values: dim(index) doubles, sector after sector) -- ITensor
+ * contraction with a diagonal tensor, as the reference's `S * V` (src/mps/update_site.jl:172) */
+int tnl_tensor_scale_index(tnl_tensor_t t, int32_t which, const double* values);
 
 /* ---- Krylov vector interface (VectorInterface inner / norm / scale!! / add!! on ITensors) ---- */
 int tnl_vec_dot(tnl_tensor_t x, tnl_tensor_t y, double* out); /* complex tensors: the real part */

@@ -33,11 +33,11 @@ _SIGS = {
     "tnl_comm_unique_id": [C.c_char_p],
     "tnl_comm_init": [_P, C.c_char_p, C.c_int32, C.c_int32],
     "tnl_comm_destroy": [_P],
+    "tnl_comm_set_sharding": [_P, C.c_int32],
     "tnl_comm_bench": [_P, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_double)],
     "tnl_shard_range": [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
-    "tnl_gemm_selftest": [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+    "tnl_gemm_selftest": [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                           C.POINTER(C.c_double), C.POINTER(C.c_double)],
-    "tnl_set_gemm_variant": [_P, C.c_int32],
     "tnl_profile_gemm": [_P, C.c_int32],
     "tnl_profile_read": [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "tnl_profile_categories": [_P, C.POINTER(C.c_double)],
@@ -55,6 +55,7 @@ _SIGS = {
     "tnl_tensor_export_size": [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     "tnl_tensor_export": [_P, _P, _P, _P],
     "tnl_tensor_fill_random": [_P, C.c_uint64],
+    "tnl_tensor_scale_index": [_P, C.c_int32, _P],
     "tnl_vec_dot": [_P, _P, C.POINTER(C.c_double)],
     "tnl_vec_norm": [_P, C.POINTER(C.c_double)],
     "tnl_vec_scale": [_P, C.c_double],

@@ -77,6 +77,12 @@ def canonical_terms(model) -> List[Dict[int, HostTensor]]:
             blocks = {}
             for c, b in t.blocks.items():
                 cc = tuple(c[p] for p in perm)
+                b = np.asarray(b)
+                if np.iscomplexobj(b):
+                    if np.abs(b.imag).max(initial=0.0) > 0.0:
+                        raise NotImplementedError("complex CouplingModel tensors are not supported on the device: only "
+                                                  "the state and the environments may be ComplexF64")
+                    b = b.real
                 bb = np.transpose(np.asarray(b, dtype=np.float64), perm)
                 if wl is None:
                     cc, bb = (0,) + cc, bb[None]

@@ -130,6 +130,13 @@ int tnl_comm_init(tnl_ctx_t c, const char* uid128, int32_t rank, int32_t world) 
 int tnl_comm_destroy(tnl_ctx_t c) {
   return guard(&c->ctx, [&] { comm_destroy(&c->ctx); });
 }
+int tnl_comm_set_sharding(tnl_ctx_t c, int32_t enable) {
+  return guard(&c->ctx, [&] {
+    c->ctx.sync();
+    c->ctx.shard_enabled = enable != 0;
+    c->ctx.slot_epoch++;                       // every cached apply plan is rebuilt for the new mode
+  });
+}
 int tnl_comm_bench(tnl_ctx_t c, int64_t n, int32_t reps, int32_t kind, double* ms) {
   return guard(&c->ctx, [&] {
     Ctx* ctx = &c->ctx;
@@ -165,17 +172,9 @@ int tnl_shard_range(int32_t dim, int32_t world, int32_t sector, int32_t rank, in
     *start = s; *count = n;
   });
 }
-int tnl_gemm_selftest(tnl_ctx_t c, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB, int32_t variant,
-                      int32_t reps, int32_t verify, double* ms, double* maxerr) {
-  return guard(&c->ctx, [&] {
-    int old = c->ctx.gemm_variant;
-    if (variant > 0) c->ctx.gemm_variant = variant;
-    gemm_selftest(&c->ctx, M, N, K, transA != 0, transB != 0, reps, verify != 0, ms, maxerr);
-    c->ctx.gemm_variant = old;
-  });
-}
-int tnl_set_gemm_variant(tnl_ctx_t c, int32_t variant) {
-  return guard(&c->ctx, [&] { c->ctx.gemm_variant = variant; });
+int tnl_gemm_selftest(tnl_ctx_t c, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB, int32_t reps,
+                      int32_t verify, double* ms, double* maxerr) {
+  return guard(&c->ctx, [&] { gemm_selftest(&c->ctx, M, N, K, transA != 0, transB != 0, reps, verify != 0, ms, maxerr); });
 }
 int tnl_profile_gemm(tnl_ctx_t c, int32_t enable) {
   return guard(&c->ctx, [&] { c->ctx.prof_gemm = enable != 0; });
@@ -298,6 +297,17 @@ int tnl_tensor_export(tnl_tensor_t t, int32_t* coords, int64_t* offsets, double*
       ctx->sync();
       for (int64_t e = 0; e < n; e++) { data[2 * e] = re[e]; data[2 * e + 1] = im[e]; }
     }
+  });
+}
+int tnl_tensor_scale_index(tnl_tensor_t t, int32_t which, const double* values) {
+  return guard(t->t->ctx, [&] {
+    Ctx* ctx = t->t->ctx;
+    TNL_CHECK(which >= 0 && which < t->t->rank(), "index number out of range");
+    std::vector<double> w(values, values + t->t->inds[which].dim());
+    double* d = ctx->upload(w);
+    scale_index(ctx, *t->t, which, d);
+    ctx->sync();
+    ctx->free(d);
   });
 }
 int tnl_tensor_fill_random(tnl_tensor_t t, uint64_t seed) {
@@ -439,6 +449,7 @@ int tnl_eigsolve_lanczos(tnl_env_t e, tnl_tensor_t phi, double tol, int32_t kryl
                          double* eval, int32_t* converged, int32_t* numops, int32_t* numiter, double* normres) {
   return guard(e->env.ctx, [&] {
     if (phi->t->nrow != 1) phi->t = relayout(e->env.ctx, *phi->t, 1);
+    if (e->env.complex_at_position()) phi->t = promoted(phi->t);   // complex environments: complex Ritz vector
     LanczosResult r = e->env.eigsolve(*phi->t, tol, krylovdim, maxiter, eager != 0);
     *eval = r.eval; *converged = r.converged; *numops = r.numops; *numiter = r.numiter; *normres = r.normres;
   });

@@ -113,7 +113,7 @@ GemmPlan::~GemmPlan() {
   if (ctx) { ctx->free(d_probs); ctx->free(d_tiles_big); ctx->free(d_tiles_small); }
 }
 TransformPlan::~TransformPlan() {
-  if (ctx) { ctx->free(d_blocks); ctx->free(d_contribs); ctx->free(d_flats); }
+  if (ctx) { ctx->free(d_blocks); ctx->free(d_flats); }
 }
 
 // --------------------------------------------------------------------------------------- Tensor
@@ -420,7 +420,6 @@ void finalize_transform_plan(TransformPlan& p, bool has_w) {
   }
   p.pure_copy = !has_w;
   p.d_blocks = p.ctx->upload(p.blocks);
-  p.d_contribs = p.ctx->upload(p.contribs);
   p.d_flats = p.ctx->upload(p.flats);
 }
 

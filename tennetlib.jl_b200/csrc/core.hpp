@@ -186,7 +186,6 @@ struct TransformPlan {
   std::vector<XfContrib> contribs;
   std::vector<XfFlat> flats;
   XfBlock* d_blocks = nullptr;
-  XfContrib* d_contribs = nullptr;
   XfFlat* d_flats = nullptr;
   bool pure_copy = false;    // no W: every output column is a copy of one input column (or zero)
   int64_t ncols = 0;
@@ -220,7 +219,6 @@ class Ctx {
   unsigned int* d_sync = nullptr;   // "last block" counters
   double* d_partials = nullptr;
   int num_sms = 148;
-  int gemm_variant = 10;            // grouped DGEMM main-loop variant (10 = early-sync loop, BK=16, 4 stages; see kernels.cu)
   // optional per-launch CUDA-event profile of the grouped GEMM kernel (bench.py roofline)
   struct ProfRec { cudaEvent_t a, b; double flops; int tiles; int cat; };   // cat: 0 gemm, 1 transform, 2 vec, 3 comm
   bool prof_gemm = false;
@@ -240,6 +238,9 @@ class Ctx {
   // NCCL sharding (multi-GPU apply); rank 0 / world 1 when unused
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
+  bool shard_enabled = true;        // false: every rank computes the whole (replicated, no collectives) -- the
+                                    // reference path the sharded results are checked against (bench.py parity)
+  int shard_world() const { return shard_enabled ? world : 1; }
   // cuSOLVER (opaque here; factorize.cu owns the type)
   void* cusolver = nullptr;
   void* solver_work = nullptr; size_t solver_work_bytes = 0;
@@ -317,6 +318,10 @@ void run_transform(Ctx* ctx, TransformPlan& p, const double* X, double* Y, const
 void vec_dot(Ctx* ctx, const double* x, const double* y, int64_t n, int slot);       // d_scalars[slot] = <x,y>
 void vec_axpy_dev(Ctx* ctx, double* y, const double* x, int64_t n, int slot, double sign);  // y += sign*s[slot]*x
 void vec_axpy(Ctx* ctx, double* y, const double* x, int64_t n, double a);
+// fused MGS step: w += (slot_in >= 0 ? a * s[slot_in] : a) * x, then s[slot_out] = <y, w> (y may alias w), one pass
+void vec_axpy_dot(Ctx* ctx, double* w, const double* x, int64_t n, int slot_in, double a, const double* y, int slot_out);
+void vec_caxpy_cdot(Ctx* ctx, double* w, const double* x, int64_t n, int slot_in, double ar, double ai, const double* y,
+                    int slot_out);
 void vec_scale(Ctx* ctx, double* y, int64_t n, double a);
 void vec_scale_to(Ctx* ctx, double* y, const double* x, int64_t n, double a);         // y = a*x
 void vec_copy(Ctx* ctx, double* y, const double* x, int64_t n);
@@ -332,6 +337,7 @@ void cgemm(Ctx* ctx, GemmPlan& p, const Tensor& A, bool conjA, const Tensor& B, 
 void run_transform_c(Ctx* ctx, TransformPlan& p, const Tensor& X, Tensor& Y, const double* W);
 void fetch_scalars(Ctx* ctx, int n);                                                  // d_scalars -> h_scalars, sync
 void fill_random(Ctx* ctx, Tensor& t, uint64_t seed);
+void scale_index(Ctx* ctx, Tensor& t, int which, const double* w_dev);
 void scale_rows_or_cols(Ctx* ctx, double* A, int64_t ld, int64_t R, int64_t C, const double* s, bool rows);
 
 }  // namespace tnl

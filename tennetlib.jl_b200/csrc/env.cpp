@@ -540,7 +540,9 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
     p->W1 = W1p;
     p->W2 = W2p;
     const Tensor* vin = &v;
-    if (ctx->world > 1 && allow_shard && p->L && p->R && !cp) {
+    // bonds near the chain ends (right link smaller than 64 per rank) run replicated: every rank computes the
+    // identical full result, no collective
+    if (ctx->shard_world() > 1 && allow_shard && p->L && p->R && !cp && v.inds[3].dim() >= 64 * (int64_t)ctx->world) {
       // Sharded apply: every rank owns a contiguous share of each sector of the right
       // link r.  It contracts L with its slice of v, carries the slice through the site operators and contracts
       // with its slice of R over (w, r_local): a partial H_eff v of full size, summed by one NCCL all-reduce.
@@ -900,52 +902,77 @@ static void householder(const std::vector<double>& x, int i, double& beta, std::
   beta = -vi / nu;
 }
 
+// Krylov vectors of one solver call: acquired from the context's pool, released when the call ends -- also when it
+// ends with an exception (RAII)
+struct VecPool {
+  Ctx* c;
+  size_t n;
+  std::vector<double*> owned;
+  VecPool(Ctx* ctx, size_t len) : c(ctx), n(len) {}
+  double* get() { double* p = c->vec_acquire(n); owned.push_back(p); return p; }      // zero-filled
+  void give(double* p) {
+    auto it = std::find(owned.begin(), owned.end(), p);
+    if (it == owned.end()) return;
+    owned.erase(it);
+    c->vec_release(p, 0);
+  }
+  ~VecPool() { for (double* p : owned) c->vec_release(p, 0); }
+};
+
 // Restatement of KrylovKit.eigsolve(A, x0, 1, :SR, Lanczos(krylovdim, maxiter, tol, eager; orth = MGS2)).
-// The same algorithm is restated independently in oracle/krylov.py.
+// The same algorithm is restated independently in oracle/krylov.py.  Float64 and ComplexF64 (planar) vectors: H_eff is
+// Hermitian, so the tridiagonal matrix (alpha, beta) is real in both cases and only the MGS coefficients are complex;
+// they stay on the device as (re, im) scalar slot pairs.  Every MGS step is ONE fused pass (vec_axpy_dot).
 LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter, bool eager) {
-  TNL_CHECK(krylovdim >= 1 && krylovdim < 200, "krylovdim out of range");
-  TNL_CHECK(!phi.cplx, "eig_solver on complex tensors is not built (TDVP / exp_solver is)");
+  TNL_CHECK(krylovdim >= 1 && krylovdim < LC_MAX_HOST, "krylovdim out of range (1 .. 31)");
+  const bool cx = phi.cplx;
   ensure_plan(phi);
   const bool sh = ap->sharded;                       // Krylov vectors live as r-slices, one per rank
-  const int64_t n = sh ? ap->nloc : phi.nelem;
+  TNL_CHECK(!(sh && cx), "complex vectors are not sharded");
+  const int64_t n = sh ? ap->nloc : phi.nelem;       // plane size
+  const int64_t nv = cx ? 2 * n : n;                 // doubles per Krylov vector
   const int howmany = 1;
-  std::vector<double*> V;                  // Krylov basis (device buffers)
+  std::vector<double*> V;                            // Krylov basis (device buffers)
   // pads between charge groups must stay zero: the flat BLAS-1 kernels run over the padded buffer
-  auto newvec = [&]() { return ctx->vec_acquire((size_t)n); };
-  double* r = newvec();
+  VecPool pool(ctx, (size_t)nv);
   auto applyraw = [&](double* vin, double* vout) { if (sh) apply_local(vin, vout); else apply_ptr(phi, vin, vout); };
-  // inner products: local partial sum, then a one-double all-reduce on the stream (no host round trip)
-  auto vec_dot = [&](Ctx* c, const double* x, const double* y, int64_t len, int slot) {
-    tnl::vec_dot(c, x, y, len, slot);
-    if (sh) comm_allreduce_sum(c, c->d_scalars + slot, 1);
+  // scalar slot pair k = (2k, 2k+1) = (re, im); inner products are reduced over the ranks on the stream
+  auto reduce = [&](int k) { if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + 2 * k, 1); };
+  auto dot = [&](const double* x, const double* y, int k) {
+    if (cx) vec_cdot(ctx, x, y, n, 2 * k); else tnl::vec_dot(ctx, x, y, n, 2 * k);
+    reduce(k);
   };
-  double* phi_full = phi.d;
+  // fused MGS step: w += a * (kin >= 0 ? s[kin] : 1) * x ; s[kout] = <y, w>
+  auto step = [&](double* w, const double* x, int kin, double a, const double* y, int kout) {
+    if (cx) vec_caxpy_cdot(ctx, w, x, n, kin >= 0 ? 2 * kin : -1, a, 0.0, y, 2 * kout);
+    else vec_axpy_dot(ctx, w, x, n, kin >= 0 ? 2 * kin : -1, a, y, 2 * kout);
+    reduce(kout);
+  };
+  double* x0 = phi.d;
   double* phi_loc = nullptr;
   if (sh) {
-    phi_loc = newvec();
+    phi_loc = pool.get();
     run_transform(ctx, *ap->xs, phi.d, phi_loc, nullptr);
+    x0 = phi_loc;
   }
-  struct { double* d; } phiv{sh ? phi_loc : phi.d};
-#define phi phiv
   // ---- initialize
-  vec_dot(ctx, phi.d, phi.d, n, 0);
+  double* r = pool.get();
+  dot(x0, x0, 0);
   fetch_scalars(ctx, 1);
-  double beta0 = std::sqrt(ctx->h_scalars[0]);
+  const double beta0 = std::sqrt(ctx->h_scalars[0]);
   TNL_CHECK(beta0 > 0, "initial vector should not have norm zero");
-  applyraw(phi.d, r);                                   // Ax0
-  vec_dot(ctx, phi.d, r, n, 0);
+  applyraw(x0, r);                                      // A x0
+  dot(x0, r, 0);
   fetch_scalars(ctx, 1);
   double alpha = ctx->h_scalars[0] / (beta0 * beta0);
-  double* v0 = newvec();
-  vec_scale_to(ctx, v0, phi.d, n, 1.0 / beta0);
-  vec_scale(ctx, r, n, 1.0 / beta0);
-  vec_axpy(ctx, r, v0, n, -alpha);
-  vec_dot(ctx, v0, r, n, 0);                            // MGS2 correction
-  vec_axpy_dev(ctx, r, v0, n, 0, -1.0);
-  vec_dot(ctx, r, r, n, 1);
-  fetch_scalars(ctx, 2);
+  double* v0 = pool.get();
+  vec_scale_to(ctx, v0, x0, nv, 1.0 / beta0);
+  vec_scale(ctx, r, nv, 1.0 / beta0);
+  step(r, v0, -1, -alpha, v0, 0);                       // r -= alpha v0 ; s0 = <v0, r>   (MGS2 correction)
+  step(r, v0, 0, -1.0, r, 1);                           // r -= s0 v0    ; s1 = |r|^2
+  fetch_scalars(ctx, 4);
   alpha += ctx->h_scalars[0];
-  double beta = std::sqrt(ctx->h_scalars[1]);
+  double beta = std::sqrt(ctx->h_scalars[2]);
   V.push_back(v0);
   std::vector<double> alphas{alpha}, betas{beta};
   LanczosResult res;
@@ -976,25 +1003,26 @@ LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter,
     }
     if (K < krylovdim) {
       // expand! + lanczosrecurrence (ModifiedGramSchmidt2)
-      double bold = betas.back();
+      const double bold = betas.back();
       double* vnew = r;
-      vec_scale(ctx, vnew, n, 1.0 / bold);
+      vec_scale(ctx, vnew, nv, 1.0 / bold);
       V.push_back(vnew);
-      double* w = newvec();
+      double* w = pool.get();
       applyraw(vnew, w);
       res.numops++;
       const int m = (int)V.size();
-      vec_axpy(ctx, w, V[m - 2], n, -bold);
-      vec_dot(ctx, vnew, w, n, 0);
-      vec_axpy_dev(ctx, w, vnew, n, 0, -1.0);
-      for (int q = 0; q < m; q++) {
-        vec_dot(ctx, V[q], w, n, 1 + q);
-        vec_axpy_dev(ctx, w, V[q], n, 1 + q, -1.0);
+      step(w, V[m - 2], -1, -bold, vnew, 0);            // w -= beta v_prev ; s0 = <vnew, w>
+      const double* prev = vnew;
+      int slot = 0;
+      for (int q = 0; q < m; q++) {                     // w -= s prev ; s_{1+q} = <V[q], w>
+        step(w, prev, slot, -1.0, V[q], 1 + q);
+        prev = V[q];
+        slot = 1 + q;
       }
-      vec_dot(ctx, w, w, n, 1 + m);
-      fetch_scalars(ctx, 2 + m);
-      double a = ctx->h_scalars[0] + ctx->h_scalars[m];       // alpha + last correction (against vnew)
-      double b = std::sqrt(ctx->h_scalars[1 + m]);
+      step(w, prev, slot, -1.0, w, 1 + m);              // last correction ; |w|^2
+      fetch_scalars(ctx, 2 * (2 + m));
+      const double a = ctx->h_scalars[0] + ctx->h_scalars[2 * m];     // alpha + last correction (against vnew)
+      const double b = std::sqrt(ctx->h_scalars[2 * (1 + m)]);
       alphas.push_back(a);
       betas.push_back(b);
       r = w;
@@ -1015,37 +1043,37 @@ LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter,
         for (int c = 0; c < j; c++) h(j + 1, c) = 0.0;
         if (hb != 0.0) {
           for (int c = 0; c < keep; c++) {            // rows 0..j from the left
-            double s = 0;
-            for (int i = 0; i <= j; i++) s += hv[i] * h(i, c);
-            for (int i = 0; i <= j; i++) h(i, c) -= hb * hv[i] * s;
+            double sacc = 0;
+            for (int i = 0; i <= j; i++) sacc += hv[i] * h(i, c);
+            for (int i = 0; i <= j; i++) h(i, c) -= hb * hv[i] * sacc;
           }
           for (int i = 0; i <= j; i++) {              // columns 0..j of rows 0..j from the right
-            double s = 0;
-            for (int c = 0; c <= j; c++) s += h(i, c) * hv[c];
-            for (int c = 0; c <= j; c++) h(i, c) -= hb * s * hv[c];
+            double sacc = 0;
+            for (int c = 0; c <= j; c++) sacc += h(i, c) * hv[c];
+            for (int c = 0; c <= j; c++) h(i, c) -= hb * sacc * hv[c];
           }
           for (int i = 0; i < K; i++) {               // accumulate into U
-            double s = 0;
-            for (int c = 0; c <= j; c++) s += U2[(size_t)i * K + c] * hv[c];
-            for (int c = 0; c <= j; c++) U2[(size_t)i * K + c] -= hb * s * hv[c];
+            double sacc = 0;
+            for (int c = 0; c <= j; c++) sacc += U2[(size_t)i * K + c] * hv[c];
+            for (int c = 0; c <= j; c++) U2[(size_t)i * K + c] -= hb * sacc * hv[c];
           }
         }
       }
-      // basistransform!: B_new[j] = sum_i B[i] U2[i, j]
+      // basistransform!: B_new[j] = sum_i B[i] U2[i, j]   (real coefficients: one flat pass over both planes)
       std::vector<double*> newV;
       for (int j = 0; j < keep; j++) {
-        double* y = newvec();
+        double* y = pool.get();
         std::vector<double> coef(K);
         for (int i = 0; i < K; i++) coef[i] = U2[(size_t)i * K + j];
-        vec_lincomb(ctx, y, V.data(), coef.data(), K, n);
+        vec_lincomb(ctx, y, V.data(), coef.data(), K, nv);
         newV.push_back(y);
       }
-      for (double* p : V) ctx->vec_release(p, 0);
+      for (double* p : V) pool.give(p);
       V = newV;
       alphas.resize(keep);
       betas.resize(keep);
       for (int j = 0; j < keep; j++) { alphas[j] = h(j, j); betas[j] = h(j + 1, j); }
-      vec_scale(ctx, r, n, betas.back() / beta);      // B[keep+1] = r/beta ; shrink!: r <- that * normres
+      vec_scale(ctx, r, nv, betas.back() / beta);      // B[keep+1] = r/beta ; shrink!: r <- that * normres
       res.numiter++;
     }
   }
@@ -1055,18 +1083,14 @@ LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter,
     std::vector<double> coef(K);
     for (int i = 0; i < K; i++) coef[i] = U[(size_t)i * K + 0];
     TNL_CHECK((int)V.size() >= K, "Krylov basis bookkeeping");
-    vec_lincomb(ctx, phi.d, V.data(), coef.data(), K, n);
+    vec_lincomb(ctx, x0, V.data(), coef.data(), K, nv);
   }
-#undef phi
   if (sh) {
     comm_allgather(ctx, phi_loc, ap->packed, ap->nloc);
     for (int k = 0; k < ctx->world; k++)
-      run_transform(ctx, *ap->unpack[k], ap->packed + (int64_t)k * ap->nloc, phi_full, nullptr);
-    ctx->vec_release(phi_loc, 0);
+      run_transform(ctx, *ap->unpack[k], ap->packed + (int64_t)k * ap->nloc, phi.d, nullptr);
   }
   ctx->sync();
-  for (double* p : V) ctx->vec_release(p, 0);
-  if (std::find(V.begin(), V.end(), r) == V.end()) ctx->vec_release(r, 0);
   res.eval = D[0];
   res.converged = converged;
   res.normres = std::fabs(f[0]);
@@ -1107,8 +1131,15 @@ ExpResult Env::exponentiate(Tensor& phi, double t_re, double t_im, double tol, i
   const int64_t n = sh ? ap->nloc : phi.nelem;        // plane size
   const int64_t nv = cx ? 2 * n : n;                  // doubles per Krylov vector
   const cd sgn = t / tau;
-  auto newvec = [&]() { return ctx->vec_acquire((size_t)nv); };
+  VecPool pool(ctx, (size_t)nv);
+  auto newvec = [&]() { return pool.get(); };
   auto applyraw = [&](double* vin, double* vout) { if (sh) apply_local(vin, vout); else apply_ptr(phi, vin, vout); res.numops++; };
+  // fused MGS step: w += a * (kin >= 0 ? s[kin] : 1) * x ; s[kout] = <y, w>   (slot pairs (2k, 2k+1))
+  auto step = [&](double* w, const double* x, int kin, double a, const double* y, int kout) {
+    if (cx) vec_caxpy_cdot(ctx, w, x, n, kin >= 0 ? 2 * kin : -1, a, 0.0, y, 2 * kout);
+    else vec_axpy_dot(ctx, w, x, n, kin >= 0 ? 2 * kin : -1, a, y, 2 * kout);
+    if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + 2 * kout, 1);
+  };
   // <x, y> into scalar slots (2k, 2k+1) = (re, im); the imaginary part of a real product is left untouched
   auto dot = [&](const double* x, const double* y, int k) {
     if (cx) vec_cdot(ctx, x, y, n, 2 * k);
@@ -1120,10 +1151,6 @@ ExpResult Env::exponentiate(Tensor& phi, double t_re, double t_im, double tol, i
   auto norm2 = [&](const double* x, int k) {          // |x|^2: one flat pass over both planes
     tnl::vec_dot(ctx, x, x, nv, 2 * k);
     if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + 2 * k, 1);
-  };
-  auto axpy_slot = [&](double* y, const double* x, int k) {      // y -= s_k x
-    if (cx) vec_caxpy_dev(ctx, y, x, n, 2 * k, -1.0);
-    else vec_axpy_dev(ctx, y, x, n, 2 * k, -1.0);
   };
   double* w0 = phi.d;
   double* phi_loc = nullptr;
@@ -1138,9 +1165,9 @@ ExpResult Env::exponentiate(Tensor& phi, double t_re, double t_im, double tol, i
   double* w1 = newvec();
   double beta = 0.0;
   auto release_basis = [&]() {
-    for (double* p : V) ctx->vec_release(p, 0);
+    for (double* p : V) pool.give(p);
     V.clear();
-    if (r) ctx->vec_release(r, 0);
+    if (r) pool.give(r);
     r = nullptr;
   };
   // LanczosIterator initialize on x = w1 (not consumed)
@@ -1155,10 +1182,8 @@ ExpResult Env::exponentiate(Tensor& phi, double t_re, double t_im, double tol, i
     double* v0 = newvec();
     vec_scale_to(ctx, v0, w1, nv, 1.0 / beta);
     vec_scale(ctx, r, nv, 1.0 / beta);
-    vec_axpy(ctx, r, v0, nv, -alpha);
-    dot(v0, r, 0);
-    axpy_slot(r, v0, 0);
-    norm2(r, 1);
+    step(r, v0, -1, -alpha, v0, 0);
+    step(r, v0, 0, -1.0, r, 1);
     fetch_scalars(ctx, 4);
     alphas.push_back(alpha + ctx->h_scalars[0]);
     betas.push_back(std::sqrt(ctx->h_scalars[2]));
@@ -1207,7 +1232,7 @@ ExpResult Env::exponentiate(Tensor& phi, double t_re, double t_im, double tol, i
       vec_lincomb(ctx, y, xs.data(), cr.data(), K + 1, n);
       vec_axpy(ctx, w0, y, n, f.real());
     }
-    ctx->vec_release(y, 0);
+    pool.give(y);
   };
   const double gamma = 0.8;
   const double eta = tol / tau;
@@ -1253,14 +1278,15 @@ ExpResult Env::exponentiate(Tensor& phi, double t_re, double t_im, double tol, i
       r = nullptr;
       applyraw(vnew, w);
       const int m = (int)V.size();
-      vec_axpy(ctx, w, V[m - 2], nv, -bold);
-      dot(vnew, w, 0);
-      axpy_slot(w, vnew, 0);
+      step(w, V[m - 2], -1, -bold, vnew, 0);
+      const double* prev = vnew;
+      int slot = 0;
       for (int qi = 0; qi < m; qi++) {
-        dot(V[qi], w, 1 + qi);
-        axpy_slot(w, V[qi], 1 + qi);
+        step(w, prev, slot, -1.0, V[qi], 1 + qi);
+        prev = V[qi];
+        slot = 1 + qi;
       }
-      norm2(w, 1 + m);
+      step(w, prev, slot, -1.0, w, 1 + m);
       fetch_scalars(ctx, 2 * (2 + m));
       alphas.push_back(ctx->h_scalars[0] + ctx->h_scalars[2 * m]);       // alpha + last correction (against vnew)
       betas.push_back(std::sqrt(ctx->h_scalars[2 * (1 + m)]));
@@ -1274,12 +1300,10 @@ ExpResult Env::exponentiate(Tensor& phi, double t_re, double t_im, double tol, i
   }
   if (fixed_point) { res.converged = 1; totalerr = beta; }
   release_basis();
-  ctx->vec_release(w1, 0);
   if (sh) {
     comm_allgather(ctx, phi_loc, ap->packed, ap->nloc);
     for (int k = 0; k < ctx->world; k++)
       run_transform(ctx, *ap->unpack[k], ap->packed + (int64_t)k * ap->nloc, phi.d, nullptr);
-    ctx->vec_release(phi_loc, 0);
   }
   ctx->sync();
   res.err = totalerr;

@@ -458,7 +458,7 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
 
   // Multi-GPU: the per-charge-group decompositions are independent -- distribute them
   // over the ranks (longest-processing-time first on n^3), exchange the spectrum, and sum the two factors.
-  const int W = ctx->world;
+  const int W = ctx->shard_world();
   if (W > 1) {
     std::vector<size_t> ord(fg.size());
     std::iota(ord.begin(), ord.end(), 0);

@@ -76,90 +76,9 @@ struct OpTile {
   }
 };
 
-template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
-gemm_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles,
-            const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase,
-            double alpha, int accum) {
-  constexpr int NT = (BM / WM) * (BN / WN) * 32;
-  using TileA = OpTile<BM, BK, TA>;     // A is k-fast when transposed (stored [k, m])
-  using TileB = OpTile<BN, BK, !TB>;    // B is k-fast when NOT transposed (stored [k, n])
-  constexpr int STAGE_ELEMS = TileA::ELEMS + TileB::ELEMS;
-  extern __shared__ __align__(16) double smem[];
-
-  const GemmTile tile = tiles[blockIdx.x];
-  const GemmProblem p = probs[tile.prob];
-  const double* pA = Abase + p.a;
-  const double* pB = Bbase + p.b;
-  double* pC = Cbase + p.c;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm0 = (warp % (BM / WM)) * WM, wn0 = (warp / (BM / WM)) * WN;
-  const int m0 = tile.m0, n0 = tile.n0;
-  const int ktiles = (p.K + BK - 1) / BK;
-
-  double acc[WM / 8][WN / 8][2];
-#pragma unroll
-  for (int i = 0; i < WM / 8; i++)
-#pragma unroll
-    for (int j = 0; j < WN / 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  auto issue = [&](int kt) {
-    double* sa = smem + (kt % STAGES) * STAGE_ELEMS;
-    double* sb = sa + TileA::ELEMS;
-    TileA::template load<NT>(sa, pA, p.lda, m0, kt * BK, p.M, p.K, tid);
-    TileB::template load<NT>(sb, pB, p.ldb, n0, kt * BK, p.N, p.K, tid);
-  };
-
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; s++) {
-    if (s < ktiles) issue(s);
-    cp_async_commit();
-  }
-  const int lr = lane >> 2, lc = lane & 3;
-  for (int kt = 0; kt < ktiles; kt++) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    if (kt + STAGES - 1 < ktiles) issue(kt + STAGES - 1);
-    cp_async_commit();
-    const double* sa = smem + (kt % STAGES) * STAGE_ELEMS;
-    const double* sb = sa + TileA::ELEMS;
-#pragma unroll
-    for (int kk = 0; kk < BK / 4; kk++) {
-      double a[WM / 8], b[WN / 8];
-#pragma unroll
-      for (int i = 0; i < WM / 8; i++) a[i] = TileA::frag(sa, wm0 + i * 8 + lr, kk * 4 + lc);
-#pragma unroll
-      for (int j = 0; j < WN / 8; j++) b[j] = TileB::frag(sb, wn0 + j * 8 + lr, kk * 4 + lc);
-#pragma unroll
-      for (int i = 0; i < WM / 8; i++)
-#pragma unroll
-        for (int j = 0; j < WN / 8; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    }
-  }
-  cp_async_wait<0>();
-  // epilogue: C fragment = rows lane>>2, cols 2*(lane&3)+{0,1}
-#pragma unroll
-  for (int i = 0; i < WM / 8; i++) {
-    int m = m0 + wm0 + i * 8 + lr;
-    if (m >= p.M) continue;
-#pragma unroll
-    for (int j = 0; j < WN / 8; j++) {
-      int n = n0 + wn0 + j * 8 + 2 * lc;
-      double* c = pC + (int64_t)n * p.ldc + m;
-      // C = alpha * A B (+ C): alpha = +-1 and the accumulate mode serve the planar complex products
-      if (n < p.N) c[0] = accum ? fma(alpha, acc[i][j][0], c[0]) : alpha * acc[i][j][0];
-      if (n + 1 < p.N) c[p.ldc] = accum ? fma(alpha, acc[i][j][1], c[p.ldc]) : alpha * acc[i][j][1];
-    }
-  }
-}
-
-
 // -------------------------------------------------------------------------------------------------
-// v2 of the grouped DGEMM main loop.  Differences to gemm_kernel:
-//   * every thread precomputes, once per tile, the source offset / validity of its 16-byte chunks: inside the
-//     k loop a load is "offset += step" + one predicate (no 64-bit multiplies, no branches);
-//   * DMMA fragments are double buffered in registers: the LDS of k-step kk+1 are issued before the 32 DMMAs
-//     of k-step kk, and the cp.async of the next stage are issued after the first fragments are in flight.
+// Global -> shared loader: every thread precomputes, once per tile, the source offset / validity of its 16-byte
+// chunks, so that inside the k loop a load is "offset += step" + one predicate (no 64-bit multiplies, no branches).
 // -------------------------------------------------------------------------------------------------
 template <int BX, int BK, bool KFAST, int NT>
 struct Loader {
@@ -209,110 +128,11 @@ struct Loader {
   }
 };
 
+// Grouped DGEMM kernel: one CTA per (charge-sector problem, 128x128 or 64x64 tile); DMMA fragments double buffered
+// in registers (the LDS of k-step kk+1 are issued before the DMMAs of k-step kk).
 template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
-gemm_kernel_v2(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles,
-               const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase,
-            double alpha, int accum) {
-  constexpr int NT = (BM / WM) * (BN / WN) * 32;
-  using TileA = OpTile<BM, BK, TA>;
-  using TileB = OpTile<BN, BK, !TB>;
-  constexpr int STAGE_ELEMS = TileA::ELEMS + TileB::ELEMS;
-  constexpr int MI = WM / 8, NI = WN / 8, KK = BK / 4;
-  extern __shared__ __align__(16) double smem[];
-
-  const GemmTile tile = tiles[blockIdx.x];
-  const GemmProblem p = probs[tile.prob];
-  const double* pA = Abase + p.a;
-  const double* pB = Bbase + p.b;
-  double* pC = Cbase + p.c;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm0 = (warp % (BM / WM)) * WM, wn0 = (warp / (BM / WM)) * WN;
-  const int m0 = tile.m0, n0 = tile.n0;
-  const int ktiles = (p.K + BK - 1) / BK;
-  const int lr = lane >> 2, lc = lane & 3;
-
-  Loader<BM, BK, TA, NT> la;
-  Loader<BN, BK, !TB, NT> lb;
-  la.init(p.lda, m0, p.M, tid);
-  lb.init(p.ldb, n0, p.N, tid);
-
-  double acc[MI][NI][2];
-#pragma unroll
-  for (int i = 0; i < MI; i++)
-#pragma unroll
-    for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; s++) {
-    if (s < ktiles) {
-      double* sa = smem + s * STAGE_ELEMS;
-      la.issue(sa, pA, s, p.K);
-      lb.issue(sa + TileA::ELEMS, pB, s, p.K);
-    }
-    cp_async_commit();
-  }
-  // fragment element offsets of this lane inside a stage
-  const int fa = TA ? (wm0 + lr) * TileA::LD + lc : lc * TileA::LD + wm0 + lr;
-  const int fb = (!TB) ? (wn0 + lr) * TileB::LD + lc : lc * TileB::LD + wn0 + lr;
-  constexpr int FA_I = TA ? 8 * TileA::LD : 8;            // +8 rows of m
-  constexpr int FA_K = TA ? 4 : 4 * TileA::LD;            // +4 in k
-  constexpr int FB_J = (!TB) ? 8 * TileB::LD : 8;
-  constexpr int FB_K = (!TB) ? 4 : 4 * TileB::LD;
-
-  double a[2][MI], b[2][NI];
-  for (int kt = 0; kt < ktiles; kt++) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    const double* sa = smem + (kt % STAGES) * STAGE_ELEMS + fa;
-    const double* sb = smem + (kt % STAGES) * STAGE_ELEMS + TileA::ELEMS + fb;
-#pragma unroll
-    for (int i = 0; i < MI; i++) a[0][i] = sa[i * FA_I];
-#pragma unroll
-    for (int j = 0; j < NI; j++) b[0][j] = sb[j * FB_J];
-    {
-      const int nk = kt + STAGES - 1;
-      if (nk < ktiles) {
-        double* st = smem + (nk % STAGES) * STAGE_ELEMS;
-        la.issue(st, pA, nk, p.K);
-        lb.issue(st + TileA::ELEMS, pB, nk, p.K);
-      }
-      cp_async_commit();
-    }
-#pragma unroll
-    for (int kk = 0; kk < KK; kk++) {
-      const int cur = kk & 1, nxt = cur ^ 1;
-      if (kk + 1 < KK) {
-#pragma unroll
-        for (int i = 0; i < MI; i++) a[nxt][i] = sa[i * FA_I + (kk + 1) * FA_K];
-#pragma unroll
-        for (int j = 0; j < NI; j++) b[nxt][j] = sb[j * FB_J + (kk + 1) * FB_K];
-      }
-#pragma unroll
-      for (int i = 0; i < MI; i++)
-#pragma unroll
-        for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
-    }
-  }
-  cp_async_wait<0>();
-#pragma unroll
-  for (int i = 0; i < MI; i++) {
-    int m = m0 + wm0 + i * 8 + lr;
-    if (m >= p.M) continue;
-#pragma unroll
-    for (int j = 0; j < NI; j++) {
-      int n = n0 + wn0 + j * 8 + 2 * lc;
-      double* c = pC + (int64_t)n * p.ldc + m;
-      // C = alpha * A B (+ C): alpha = +-1 and the accumulate mode serve the planar complex products
-      if (n < p.N) c[0] = accum ? fma(alpha, acc[i][j][0], c[0]) : alpha * acc[i][j][0];
-      if (n + 1 < p.N) c[p.ldc] = accum ? fma(alpha, acc[i][j][1], c[p.ldc]) : alpha * acc[i][j][1];
-    }
-  }
-}
-
-template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
-gemm_kernel_v3(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles,
+gemm_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles,
                const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase,
             double alpha, int accum) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
@@ -432,13 +252,12 @@ gemm_kernel_v3(const GemmProblem* __restrict__ probs, const GemmTile* __restrict
   }
 }
 
-template <int VER, int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
+template <int BM, int BN, int BK, int WM, int WN, bool TA, bool TB, int STAGES>
 static void launch_gemm_one(Ctx* ctx, const GemmProblem* probs, const GemmTile* tiles, int ntiles,
                             const double* A, const double* B, double* C, double alpha, int accum) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr size_t SMEM = sizeof(double) * STAGES * (OpTile<BM, BK, TA>::ELEMS + OpTile<BN, BK, !TB>::ELEMS);
-  auto kern = VER == 3 ? gemm_kernel_v3<BM, BN, BK, WM, WN, TA, TB, STAGES>
-                       : (VER == 2 ? gemm_kernel_v2<BM, BN, BK, WM, WN, TA, TB, STAGES> : gemm_kernel<BM, BN, BK, WM, WN, TA, TB, STAGES>);
+  auto kern = gemm_kernel<BM, BN, BK, WM, WN, TA, TB, STAGES>;
   static bool configured = false;   // one static per template instantiation
   if (!configured) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -450,14 +269,14 @@ static void launch_gemm_one(Ctx* ctx, const GemmProblem* probs, const GemmTile* 
   ctx->cnt.gemm_launches++;
 }
 
-template <int VER, int BM, int BN, int BK, int WM, int WN, int STAGES>
+template <int BM, int BN, int BK, int WM, int WN, int STAGES>
 static void launch_gemm_cfg(Ctx* ctx, bool ta, bool tb, const GemmProblem* probs, const GemmTile* tiles, int ntiles,
                             const double* A, const double* B, double* C, double alpha = 1.0, int accum = 0) {
   if (ntiles == 0) return;
-  if (!ta && !tb) launch_gemm_one<VER, BM, BN, BK, WM, WN, false, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
-  else if (!ta && tb) launch_gemm_one<VER, BM, BN, BK, WM, WN, false, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
-  else if (ta && !tb) launch_gemm_one<VER, BM, BN, BK, WM, WN, true, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
-  else launch_gemm_one<VER, BM, BN, BK, WM, WN, true, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
+  if (!ta && !tb) launch_gemm_one<BM, BN, BK, WM, WN, false, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
+  else if (!ta && tb) launch_gemm_one<BM, BN, BK, WM, WN, false, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
+  else if (ta && !tb) launch_gemm_one<BM, BN, BK, WM, WN, true, false, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
+  else launch_gemm_one<BM, BN, BK, WM, WN, true, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
 }
 
 void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C, double alpha, bool accum) {
@@ -470,22 +289,10 @@ void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C
     CUDA_OK(cudaEventCreate(&rec.b));
     CUDA_OK(cudaEventRecord(rec.a, ctx->stream));
   }
-  const int nb = (int)p.tiles_big.size();
-  switch (ctx->gemm_variant) {
-    case 1: launch_gemm_cfg<1, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
-    case 4: launch_gemm_cfg<2, 128, 128, 16, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
-    case 5: launch_gemm_cfg<2, 128, 128, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
-    case 6: launch_gemm_cfg<2, 128, 128, 32, 32, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
-    case 7: launch_gemm_cfg<2, 128, 128, 32, 32, 64, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
-    case 8: launch_gemm_cfg<3, 128, 128, 32, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
-    case 11: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 6>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
-    case 2: launch_gemm_cfg<2, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
-    case 3: launch_gemm_cfg<2, 128, 128, 32, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
-    case 9: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 5>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
-    case 12: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 3>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
-    default: launch_gemm_cfg<3, 128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, nb, A, B, C, alpha, accum ? 1 : 0); break;
-  }
-  launch_gemm_cfg<1, 64, 64, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_small, (int)p.tiles_small.size(), A, B, C, alpha, accum ? 1 : 0);
+  // 128x128x16 tiles, 8 warps x (64x32), 4 cp.async stages for sectors larger than 64 in both extents;
+  // 64x64x16 tiles, 4 warps x (32x32) for the small ones
+  launch_gemm_cfg<128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, (int)p.tiles_big.size(), A, B, C, alpha, accum ? 1 : 0);
+  launch_gemm_cfg<64, 64, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_small, (int)p.tiles_small.size(), A, B, C, alpha, accum ? 1 : 0);
   if (prof) {
     CUDA_OK(cudaEventRecord(rec.b, ctx->stream));
     rec.flops = p.flops;
@@ -577,84 +384,12 @@ void gemm_selftest(Ctx* ctx, int M, int N, int K, bool ta, bool tb, int reps, bo
 // =================================================================================================
 // One warp per PASSIVE column of an output block: the X columns it needs are read once and all Na = nd0*nd1
 // new-index outputs are produced from registers (up to 4 at a time), lanes run along the stride-1 index i.
-__global__ void __launch_bounds__(256)
-transform_kernel(const XfBlock* __restrict__ blocks, int nblocks, const XfContrib* __restrict__ contribs,
-                 const double* __restrict__ X, double* __restrict__ Y, const double* __restrict__ W, int64_t ncols) {
-  const int lane = threadIdx.x & 31;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; col < ncols; col += nwarps) {
-    int lo = 0, hi = nblocks - 1;
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (blocks[mid].colstart <= col) lo = mid; else hi = mid - 1;
-    }
-    const XfBlock& b = blocks[lo];
-    int64_t t = col - b.colstart;
-    int64_t ybase = b.yoff;
-    int pidx[MAXP];
-#pragma unroll
-    for (int k = 0; k < MAXP; k++) {
-      pidx[k] = (int)(t % b.pd[k]); t /= b.pd[k];
-      ybase += pidx[k] * b.yps[k];
-    }
-    const int I = b.I, Na = b.nd0 * b.nd1;
-    for (int nc = 0; nc < Na; nc += 4) {
-      const int nn = min(4, Na - nc);
-      for (int i0 = 0; i0 < I; i0 += 128) {
-        double acc[4][4];
-#pragma unroll
-        for (int n = 0; n < 4; n++)
-#pragma unroll
-          for (int u = 0; u < 4; u++) acc[n][u] = 0.0;
-        for (int c = b.cbeg; c < b.cbeg + b.cnum; c++) {
-          const XfContrib& cc = contribs[c];
-          int64_t xb = cc.xoff;
-#pragma unroll
-          for (int k = 0; k < MAXP; k++) xb += pidx[k] * cc.xps[k];
-          const int Ka = cc.kd0 * cc.kd1;
-          for (int a1 = 0; a1 < cc.kd1; a1++)
-            for (int a0 = 0; a0 < cc.kd0; a0++) {
-              const double* xp = X + xb + a0 * cc.ks0 + a1 * cc.ks1;
-              double x[4];
-#pragma unroll
-              for (int u = 0; u < 4; u++) {
-                int i = i0 + lane + 32 * u;
-                x[u] = i < I ? xp[i] : 0.0;
-              }
-              const double* wp = W ? W + cc.woff + a0 + cc.kd0 * a1 + (int64_t)Ka * nc : nullptr;
-#pragma unroll
-              for (int n = 0; n < 4; n++) {
-                if (n < nn) {
-                  const double w = wp ? wp[(int64_t)Ka * n] : 1.0;
-#pragma unroll
-                  for (int u = 0; u < 4; u++) acc[n][u] = fma(x[u], w, acc[n][u]);
-                }
-              }
-            }
-        }
-#pragma unroll
-        for (int n = 0; n < 4; n++) {
-          if (n < nn) {
-            const int na = nc + n;
-            double* yp = Y + ybase + (na % b.nd0) * b.yns[0] + (na / b.nd0) * b.yns[1];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              int i = i0 + lane + 32 * u;
-              if (i < I) yp[i] = acc[n][u];
-            }
-          }
-        }
-      }
-    }
-  }
-}
-
-// v2: the contributions are flattened to one entry per contracted element, and the X columns of FB entries
-// (FB x 4 x 32 doubles per warp) are requested before the first FMA consumes one -- 4x the bytes in flight of the
-// first kernel, which was latency bound at ~50 % of the HBM roofline (profiles/r01b_ncu_hbm.md).
+// The contributions are flattened to one entry per contracted element, and the X columns of FB entries
+// (FB x 4 x 32 doubles per warp) are requested before the first FMA consumes one (a first kernel with one column in
+// flight per warp was latency bound at ~50 % of the HBM roofline, profiles/r01b_ncu_hbm.md).
 constexpr int XF_FB = 4;
 __global__ void __launch_bounds__(256)
-transform_kernel_v2(const XfBlock* __restrict__ blocks, int nblocks, const XfFlat* __restrict__ flats,
+transform_kernel(const XfBlock* __restrict__ blocks, int nblocks, const XfFlat* __restrict__ flats,
                     const double* __restrict__ X, double* __restrict__ Y, const double* __restrict__ W, int64_t ncols) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -783,13 +518,10 @@ void run_transform(Ctx* ctx, TransformPlan& p, const double* X, double* Y, const
   Ctx::Scope prof_scope(ctx, 1);
   int64_t warps_needed = p.ncols;
   int64_t blocks = std::min<int64_t>((warps_needed + 7) / 8, (int64_t)ctx->num_sms * 32);
-  static const int variant = [] { const char* e = getenv("TNL_XF"); return e ? atoi(e) : 2; }();
-  if (variant < 2 || p.flats.empty()) {
-    transform_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_contribs, X, Y, W, p.ncols);
-  } else if (!W) {
+  if (!W) {
     relayout_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_flats, X, Y, p.ncols);
   } else {
-    transform_kernel_v2<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_flats, X, Y, W, p.ncols);
+    transform_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_flats, X, Y, W, p.ncols);
   }
   CUDA_OK(cudaGetLastError());
   ctx->cnt.launches++;
@@ -868,6 +600,57 @@ axpy_kernel(double* __restrict__ y, const double* __restrict__ x, int64_t n2, co
   }
 }
 
+// Fused MGS step (KrylovKit ModifiedGramSchmidt2 keeps its sequential order: the coefficient of step q+1 is taken
+// AFTER the correction of step q): w += s x followed by out = <y, w_new> in ONE pass over w -- 4ne bytes instead of
+// the 5ne of axpy + dot (y == w: the norm^2 of the corrected vector, 3ne instead of 4ne).  s = a * (*sdev) or a.
+__global__ void __launch_bounds__(VT)
+axpy_dot_kernel(double* w, const double* __restrict__ x, const double* y, int64_t n2, const double* __restrict__ sdev,
+                double a, double* __restrict__ partials, unsigned int* __restrict__ sync, double* __restrict__ out) {
+  const double s = sdev ? a * (*sdev) : a;
+  double2* w2 = reinterpret_cast<double2*>(w);
+  const double2* x2 = reinterpret_cast<const double2*>(x);
+  const double2* y2 = reinterpret_cast<const double2*>(y);
+  const bool self = (y == w);
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * VT;
+  for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += stride) {
+    const double2 xv = x2[i];
+    double2 b = w2[i];
+    b.x = fma(s, xv.x, b.x); b.y = fma(s, xv.y, b.y);
+    w2[i] = b;
+    const double2 c = self ? b : y2[i];
+    acc = fma(c.x, b.x, acc); acc = fma(c.y, b.y, acc);
+  }
+  acc = warp_sum(acc);
+  __shared__ double ws[VT / 32];
+  __shared__ bool last;
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < VT / 32; k++) t += ws[k];
+    partials[blockIdx.x] = t;
+    __threadfence();
+    unsigned int done = atomicAdd(sync, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double t = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += VT) t += partials[b];
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r = 0.0;
+      for (int k = 0; k < VT / 32; k++) r += ws[k];
+      *out = r;
+      *sync = 0u;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(VT)
 scale_kernel(double* __restrict__ y, const double* __restrict__ x, int64_t n2, double a) {
   double2* y2 = reinterpret_cast<double2*>(y);
@@ -922,6 +705,16 @@ void vec_axpy(Ctx* ctx, double* y, const double* x, int64_t n, double a) {
   CUDA_OK(cudaGetLastError());
   ctx->cnt.launches++;
   ctx->cnt.vec_bytes += 3.0 * n * 8.0;
+}
+// w += (slot_in >= 0 ? a * s[slot_in] : a) * x ;  s[slot_out] = <y, w>   (y may be w)
+void vec_axpy_dot(Ctx* ctx, double* w, const double* x, int64_t n, int slot_in, double a, const double* y, int slot_out) {
+  Ctx::Scope prof_scope(ctx, 2);
+  TNL_CHECK(n % 2 == 0, "padded vector length must be even");
+  axpy_dot_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(w, x, y, n / 2, slot_in >= 0 ? ctx->d_scalars + slot_in : nullptr, a,
+                                                               ctx->d_partials, ctx->d_sync, ctx->d_scalars + slot_out);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.vec_bytes += (y == w ? 3.0 : 4.0) * n * 8.0;
 }
 void vec_scale(Ctx* ctx, double* y, int64_t n, double a) { vec_scale_to(ctx, y, y, n, a); }
 void vec_scale_to(Ctx* ctx, double* y, const double* x, int64_t n, double a) {
@@ -1016,6 +809,67 @@ caxpy_kernel(double* __restrict__ y, const double* __restrict__ x, int64_t n2, i
   }
 }
 
+// complex fused MGS step on planar vectors: w += s x, out = <y, w_new> = sum conj(y) w  (out[0] = re, out[1] = im)
+__global__ void __launch_bounds__(VT)
+caxpy_cdot_kernel(double* w, const double* __restrict__ x, const double* y, int64_t n2, int64_t plane2,
+                  const double* __restrict__ sdev, double ar, double ai, double* __restrict__ partials,
+                  unsigned int* __restrict__ sync, double* __restrict__ out) {
+  const double sr = sdev ? ar * sdev[0] : ar;
+  const double si = sdev ? ar * sdev[1] : ai;
+  double2* wr = reinterpret_cast<double2*>(w);
+  double2* wi = wr + plane2;
+  const double2* xr = reinterpret_cast<const double2*>(x);
+  const double2* xi = xr + plane2;
+  const double2* yr = reinterpret_cast<const double2*>(y);
+  const double2* yi = yr + plane2;
+  const bool self = (y == w);
+  double accr = 0.0, acci = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * VT;
+  for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += stride) {
+    const double2 a = xr[i], b = xi[i];
+    double2 c = wr[i], d = wi[i];
+    c.x = fma(sr, a.x, c.x); c.x = fma(-si, b.x, c.x); c.y = fma(sr, a.y, c.y); c.y = fma(-si, b.y, c.y);
+    d.x = fma(sr, b.x, d.x); d.x = fma(si, a.x, d.x); d.y = fma(sr, b.y, d.y); d.y = fma(si, a.y, d.y);
+    wr[i] = c;
+    wi[i] = d;
+    const double2 p = self ? c : yr[i], q = self ? d : yi[i];
+    accr = fma(p.x, c.x, accr); accr = fma(p.y, c.y, accr); accr = fma(q.x, d.x, accr); accr = fma(q.y, d.y, accr);
+    acci = fma(p.x, d.x, acci); acci = fma(p.y, d.y, acci); acci = fma(-q.x, c.x, acci); acci = fma(-q.y, c.y, acci);
+  }
+  accr = warp_sum(accr);
+  acci = warp_sum(acci);
+  __shared__ double ws[2][VT / 32];
+  __shared__ bool last;
+  if ((threadIdx.x & 31) == 0) { ws[0][threadIdx.x >> 5] = accr; ws[1][threadIdx.x >> 5] = acci; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int k = 0; k < VT / 32; k++) { t0 += ws[0][k]; t1 += ws[1][k]; }
+    partials[2 * blockIdx.x] = t0;
+    partials[2 * blockIdx.x + 1] = t1;
+    __threadfence();
+    unsigned int done = atomicAdd(sync, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double t0 = 0.0, t1 = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += VT) { t0 += partials[2 * b]; t1 += partials[2 * b + 1]; }
+    t0 = warp_sum(t0);
+    t1 = warp_sum(t1);
+    if ((threadIdx.x & 31) == 0) { ws[0][threadIdx.x >> 5] = t0; ws[1][threadIdx.x >> 5] = t1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r0 = 0.0, r1 = 0.0;
+      for (int k = 0; k < VT / 32; k++) { r0 += ws[0][k]; r1 += ws[1][k]; }
+      out[0] = r0;
+      out[1] = r1;
+      *sync = 0u;
+    }
+  }
+}
+
 struct CLincombArgs { const double* x[LC_MAX]; double cr[LC_MAX]; double ci[LC_MAX]; int k; };
 __global__ void __launch_bounds__(VT)
 clincomb_kernel(double* __restrict__ y, CLincombArgs a, int64_t n2, int64_t plane2) {
@@ -1058,6 +912,18 @@ void vec_caxpy(Ctx* ctx, double* y, const double* x, int64_t n, double ar, doubl
   CUDA_OK(cudaGetLastError());
   ctx->cnt.launches++;
   ctx->cnt.vec_bytes += 3.0 * n * 16.0;
+}
+// planar complex: w += (slot_in >= 0 ? ar * (s[slot_in] + i s[slot_in+1]) : ar + i ai) * x ; s[slot_out, +1] = <y, w>
+void vec_caxpy_cdot(Ctx* ctx, double* w, const double* x, int64_t n, int slot_in, double ar, double ai, const double* y,
+                    int slot_out) {
+  Ctx::Scope prof_scope(ctx, 2);
+  TNL_CHECK(n % 2 == 0, "padded vector length must be even");
+  caxpy_cdot_kernel<<<vec_grid(ctx, n / 2), VT, 0, ctx->stream>>>(w, x, y, n / 2, n / 2,
+                                                                 slot_in >= 0 ? ctx->d_scalars + slot_in : nullptr, ar, ai,
+                                                                 ctx->d_partials, ctx->d_sync, ctx->d_scalars + slot_out);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.vec_bytes += (y == w ? 3.0 : 4.0) * n * 16.0;
 }
 void vec_clincomb(Ctx* ctx, double* y, const double* const* xs, const double* cr, const double* ci, int k, int64_t n) {
   Ctx::Scope prof_scope(ctx, 2);
@@ -1118,6 +984,38 @@ void fill_random(Ctx* ctx, Tensor& t, uint64_t seed) {
     CUDA_OK(cudaGetLastError());
     ctx->cnt.launches++;
   }
+}
+
+// T(..., i_k, ...) *= w[i_k] on one block: `w` points at the values of the block's sector of index k
+__global__ void scale_index_kernel(double* __restrict__ data, BlkDesc b, int64_t n, int k, const double* __restrict__ w) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = e, addr = b.off;
+    int ik = 0;
+    for (int q = 0; q < b.r; q++) {
+      const int i = (int)(t % b.d[q]);
+      t /= b.d[q];
+      addr += i * b.st[q];
+      if (q == k) ik = i;
+    }
+    data[addr] *= w[ik];
+  }
+}
+// diag(w) applied on index `which` of every block (w: one value per element of the index, sector after sector)
+void scale_index(Ctx* ctx, Tensor& t, int which, const double* w_dev) {
+  std::vector<int64_t> soff(t.inds[which].nsect() + 1, 0);
+  for (int s = 0; s < t.inds[which].nsect(); s++) soff[s + 1] = soff[s] + t.inds[which].dims[s];
+  for (int pl = 0; pl < t.planes(); pl++)
+    for (auto& b : t.blocks) {
+      BlkDesc d;
+      d.off = b.off; d.r = t.rank(); d.key = 0;
+      int64_t n = 1;
+      for (int k = 0; k < t.rank(); k++) { d.st[k] = b.st[k]; d.d[k] = b.d[k]; n *= b.d[k]; }
+      if (n == 0) continue;
+      int grid = (int)std::min<int64_t>((n + 255) / 256, 1184);
+      scale_index_kernel<<<grid, 256, 0, ctx->stream>>>(t.d + pl * t.nelem, d, n, which, w_dev + soff[b.c[which]]);
+      CUDA_OK(cudaGetLastError());
+      ctx->cnt.launches++;
+    }
 }
 
 __global__ void scale_rc_kernel(double* __restrict__ A, int64_t ld, int64_t R, int64_t C, const double* __restrict__ s, bool rows) {

@@ -57,8 +57,11 @@ def dmrg_(sysenv: StateEnvs, params: DMRGParams, nsite: int, **kwargs) -> SweepD
 
 
 def dmrg(ctx, psi0, H, params: DMRGParams, nsite: int, Ms=None, **kwargs):
-    """dmrg(psi0, H, params, nsite) and dmrg(psi0, H, Ms, params, nsite; weight) (src/mps/dmrg.jl:231-246)."""
-    sysenv = StateEnvs(ctx, psi0, H, llim=kwargs.pop("llim", 0), rlim=kwargs.pop("rlim", 2), Ms=Ms,
+    """dmrg(psi0, H, params, nsite) and dmrg(psi0, H, Ms, params, nsite; weight) (src/mps/dmrg.jl:231-246).
+    Host tensors carry no gauge information, so unless the caller states the orthogonality limits (`llim`, `rlim`)
+    the gauge is taken as unknown and the first sweep right-canonicalises psi0 (`orthogonalize!(psi, 1)`,
+    src/mps/sweep.jl:100-102) -- the reference reads the limits from the MPS object itself."""
+    sysenv = StateEnvs(ctx, psi0, H, llim=kwargs.pop("llim", 0), rlim=kwargs.pop("rlim", None), Ms=Ms,
                        weight=kwargs.pop("weight", -1.0))
     swdata = dmrg_(sysenv, params, nsite, **kwargs)
     return swdata.energy[-1], sysenv, swdata

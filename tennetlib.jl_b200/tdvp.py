@@ -7,9 +7,10 @@ from .sweep import SweepData, dynamic_fullsweep, fullsweep
 
 
 class TDVPEngine:
-    """TDVPEngine(psi, H) / TDVPEngine(psi, H, Ms; weight): state + environments, sweep history, elapsed time."""
+    """TDVPEngine(psi, H) / TDVPEngine(psi, H, Ms; weight): state + environments, sweep history, elapsed time.
+    `rlim=None`: gauge of `psi` unknown, the first sweep orthogonalises it (pass llim / rlim for a canonical MPS)."""
 
-    def __init__(self, ctx, psi, H, Ms=None, weight: float = -1.0, llim: int = 0, rlim: int = 2):
+    def __init__(self, ctx, psi, H, Ms=None, weight: float = -1.0, llim: int = 0, rlim: int | None = None):
         self.sysenv = StateEnvs(ctx, psi, H, llim=llim, rlim=rlim, Ms=Ms, weight=weight)
         self.swdata = SweepData()
         self.abstime = 0.0

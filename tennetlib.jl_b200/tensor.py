@@ -97,7 +97,13 @@ def flatten_blocks(t, dtype=np.float64):
     for n, c in enumerate(keys):
         coords[n] = c
         offsets[n] = off
-        b = np.asarray(t.blocks[c], dtype=dtype)
+        b = np.asarray(t.blocks[c])
+        if np.iscomplexobj(b) and np.dtype(dtype).kind != "c":
+            if np.abs(b.imag).max(initial=0.0) > 0.0:
+                raise NotImplementedError("complex site operators (complex MPO / CouplingModel tensors) are not "
+                                          "supported on the device: only the state and the environments may be ComplexF64")
+            b = b.real
+        b = np.asarray(b, dtype=dtype)
         chunks.append(b.reshape(-1, order="F"))
         off += b.size
     data = np.ascontiguousarray(np.concatenate(chunks)) if chunks else np.zeros(1, dtype=dtype)
@@ -143,6 +149,10 @@ class Context:
     def comm_init(self, uid: bytes, rank: int, world: int):
         check(self.lib.tnl_comm_init(self.h, uid, rank, world), self.h)
 
+    def comm_set_sharding(self, enable: bool):
+        """False: replicated, collective-free computation on every rank (parity reference of the sharded path)."""
+        check(self.lib.tnl_comm_set_sharding(self.h, 1 if enable else 0), self.h)
+
     def comm_bench(self, n: int, reps: int, kind: int) -> float:
         ms = C.c_double()
         check(self.lib.tnl_comm_bench(self.h, n, reps, kind, C.byref(ms)), self.h)
@@ -151,14 +161,11 @@ class Context:
     def comm_destroy(self):
         check(self.lib.tnl_comm_destroy(self.h), self.h)
 
-    def gemm_selftest(self, M, N, K, transA=False, transB=False, variant=0, reps=1, verify=True):
+    def gemm_selftest(self, M, N, K, transA=False, transB=False, reps=1, verify=True):
         ms, err = C.c_double(), C.c_double()
-        check(self.lib.tnl_gemm_selftest(self.h, M, N, K, int(transA), int(transB), variant, reps, int(verify),
+        check(self.lib.tnl_gemm_selftest(self.h, M, N, K, int(transA), int(transB), reps, int(verify),
                                          C.byref(ms), C.byref(err)), self.h)
         return ms.value, err.value
-
-    def set_gemm_variant(self, v: int):
-        check(self.lib.tnl_set_gemm_variant(self.h, v), self.h)
 
     def profile_gemm(self, enable: bool):
         check(self.lib.tnl_profile_gemm(self.h, 1 if enable else 0), self.h)
@@ -278,6 +285,12 @@ class DeviceTensor:
 
     def fill_random(self, seed: int):
         check(self.ctx.lib.tnl_tensor_fill_random(self.h, C.c_uint64(seed)), self.ctx.h)
+        return self
+
+    def scale_index_(self, which: int, values):
+        """T(..., i, ...) *= values[i] along index `which` (contraction with a diagonal matrix), in place."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        check(self.ctx.lib.tnl_tensor_scale_index(self.h, int(which), v.ctypes.data), self.ctx.h)
         return self
 
     # ---- VectorInterface

@@ -336,14 +336,13 @@ def test_svd_drivers_agree(ctx, svd_alg):
         assert np.abs(M.T @ M - np.eye(M.shape[1])).max() < 1e-10
 
 
-@pytest.mark.parametrize("variant", [1, 3, 10])
-def test_grouped_dgemm_kernel_against_naive_reference(ctx, variant):
+def test_grouped_dgemm_kernel_against_naive_reference(ctx):
     """Kernel-level check: DMMA grouped GEMM vs a one-thread-per-element FP64 reference kernel, ragged sizes,
     all four operand layouts (tails in M, N and K, odd leading dimensions)."""
     for (M, N, K) in ((1, 1, 1), (7, 5, 3), (129, 65, 17), (255, 257, 33), (385, 254, 935)):
         for ta in (0, 1):
             for tb in (0, 1):
-                ms, err = ctx.gemm_selftest(M, N, K, ta, tb, variant, 1, True)
+                ms, err = ctx.gemm_selftest(M, N, K, ta, tb, 1, True)
                 assert 0.0 <= err < 1e-12 * K, (M, N, K, ta, tb, err)
 
 

@@ -1,5 +1,6 @@
-"""Cross-rank aggregation used by bench.py (replicas: no data-path collective): times are the MAX over
-ranks, work is the SUM over ranks."""
+"""Cross-rank aggregation used by bench.py: times are the MAX over ranks, work is the SUM over ranks.  In the default
+sharded mode every rank holds a slice of the same bond update (its own share of the apply flops); with
+`--multi replicas` the ranks run independent copies."""
 import torch
 import torch.distributed as dist
 
