@@ -379,6 +379,7 @@ def run_ours(args):
 
     sysenv.set_nsite(2)
     bond_e2e = bond
+    li = sysenv.site_tensor(bond_e2e).inds[0]          # left link of the e2e / cpu_baseline bond (before later legs)
     phi = sysenv.make_phi(bond_e2e)
     sysenv.position(bond_e2e)
     _ = sysenv.product(phi)
@@ -465,7 +466,7 @@ def run_ours(args):
         trunc_decay = {"decades": 24, "link_dim": int(nlink), "cutoff": args.cutoff, "maxdim": chi, "ms": {}, "kept": {},
                        "truncerr": {}}
         Qt = sysenv.site_tensor(b).copy()
-        for alg in ("gram", "polar"):
+        for alg in ("divide_and_conquer", "polar"):
             ms_l = []
             for rep in range(2):
                 Vw = Vt.copy().scale_index_(0, w)
@@ -549,7 +550,6 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline:
         # bounded sample: ONE oracle apply on a synthetic bond with the same sector profile
-        li = sysenv.site_tensor(bond_e2e).inds[0]
         times, fl, gen_s, cores = time_oracle_apply(list(li.qns), list(li.dims), 1)
         cpu = {"value": fl / times[0] / 1e12, "unit": "TFLOP/s", "cores": cores, "host_cores": host_cores(), "kind": "port",
                "sample": "one H_eff apply (%.1f GFLOP algorithmic) by the NumPy oracle on a synthetic bond with the "
@@ -600,11 +600,13 @@ def main():
     ap.add_argument("--nsites", type=int, default=100)
     ap.add_argument("--cutoff", type=float, default=1e-15)
     ap.add_argument("--decomp", default="auto", choices=["auto", "svd", "eigen"])
-    ap.add_argument("--svd-alg", dest="svd_alg", default="gram", choices=["divide_and_conquer", "qr_iteration", "polar", "gram"],
-                    help="SVD driver of the truncation: gesvd, gesvdp (polar) or Gram-eigh with accuracy guard + gesvdp fallback")
+    ap.add_argument("--svd-alg", dest="svd_alg", default="divide_and_conquer",
+                    choices=["divide_and_conquer", "qr_iteration", "polar", "gram"],
+                    help="SVD driver of the truncation: the product default `divide_and_conquer` (Gram eigenproblem on the "
+                         "grouped DGEMM + deflated refinement; `gram` is an alias), gesvd `qr_iteration`, gesvdp `polar`")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
                     help="N>1: shard the H_eff apply of ONE sweep over the GPUs (strong scaling) or run independent replicas")
-    ap.add_argument("--reserve-gb", dest="reserve_gb", type=float, default=12.0,
+    ap.add_argument("--reserve-gb", dest="reserve_gb", type=float, default=40.0,
                     help="device memory pool head-room reserved before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the measured full sweep (198 bond updates)")

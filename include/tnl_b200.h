@@ -158,7 +158,9 @@ int tnl_exponentiate(tnl_env_t env, tnl_tensor_t phi, double t_re, double t_im, 
 /* real(scalar(dag(phi) * PH(phi))) : src/mps/update_site.jl:51-57 */
 int tnl_expectation(tnl_env_t env, tnl_tensor_t phi, double* e);
 /* noiseterm + replacebond! : src/mps/update_site.jl:59-76.  which_decomp low 4 bits: 0 = reference rule,
- * 1 = svd, 2 = eigen; bits 4.. select the SVD driver (0 = gesvd `qr_iteration`, 1 = gesvdp polar).
+ * 1 = svd, 2 = eigen; bits 4.. select the SVD driver: 0 = `divide_and_conquer` (the reference's default,
+ * src/mps/update_site.jl:242) served by the Gram-matrix eigenproblem on the grouped DGEMM with deflated refinement of
+ * the small singular values, 1 = cusolverDnXgesvdp (polar), 2 = alias of 0, 3 = cusolverDnDgesvd `qr_iteration`.
  * eigs receives spec.eigs (kept spectrum, descending), at most `cap` values; *neigs = number kept. */
 int tnl_replacebond(tnl_env_t env, int32_t pos, tnl_tensor_t phi, int32_t ortho_left, int64_t maxdim, int64_t mindim,
                     double cutoff, double noise, int32_t normalize, int32_t which_decomp, double* truncerr,
@@ -166,7 +168,7 @@ int tnl_replacebond(tnl_env_t env, int32_t pos, tnl_tensor_t phi, int32_t ortho_
 
 /* one-site update tail, src/mps/update_site.jl:158-186: U,S,V = svd(phi, uinds; maxdim, mindim, cutoff);
  * normalize!(S); psi[pos] = U; psi[posnext] = (S*V)*psi[posnext]  (posnext = pos+1 for ortho left, pos-1 for right).
- * svd_alg: 0 = gesvd, 1 = gesvdp, 2 = guarded Gram-eigh.
+ * svd_alg: as in tnl_replacebond (0 = Gram + deflated refinement, 1 = gesvdp, 3 = gesvd).
  * carry == NULL: as above.  carry != NULL (TDVP, update_site.jl:172-186): only psi[pos] = U is stored and
  * *carry = S*V (ortho left) or U*S (ortho right) is returned; after the zero-site backward evolution the caller
  * hands it to tnl_env_absorb_bond, which performs psi[posnext] = carry * psi[posnext]. */

@@ -121,6 +121,27 @@ static void gather_cols(Ctx* ctx, double* dst, int64_t ldd, const double* src, i
   ctx->free(d_sc);
 }
 
+__global__ void scatter_cols_kernel(double* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds,
+                                    int64_t R, int nk, const int* __restrict__ idx) {
+  int64_t n = R * nk;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = e % R, c = e / R;
+    dst[(int64_t)idx[c] * ldd + r] = src[c * lds + r];
+  }
+}
+// dst[:, idx[c]] = src[:, c]
+static void scatter_cols(Ctx* ctx, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t R,
+                         const std::vector<int>& idx) {
+  int nk = (int)idx.size();
+  if (R * nk == 0) return;
+  int* d_idx = ctx->upload(idx);
+  int grid = (int)std::min<int64_t>((R * nk + 255) / 256, 1184);
+  scatter_cols_kernel<<<grid, 256, 0, ctx->stream>>>(dst, ldd, src, lds, R, nk, d_idx);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->free(d_idx);
+}
+
 struct FG {                     // one charge group of the factorisation
   Charge q;
   int64_t R = 0, C = 0;
@@ -135,7 +156,78 @@ struct FG {                     // one charge group of the factorisation
   std::vector<int> keep;                          // kept columns, descending weight
   bool mine = true;                               // multi-GPU: this rank decomposes the group
   int64_t nvals = 0;                              // number of spectrum values the group contributes
+  int64_t kmax = INT64_MAX;                       // Gram driver: only the min(R, C) largest eigenvalues of M M^T are
+                                                  // singular values, the rest is structurally zero and never kept
+  // weights (|value|) of the group's admissible spectrum entries, descending, with their positions in `vals`
+  std::vector<int> admissible() const {
+    std::vector<int> order(vals.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return std::fabs(vals[a]) > std::fabs(vals[b]); });
+    if ((int64_t)order.size() > kmax) order.resize((size_t)kmax);
+    return order;
+  }
 };
+
+// Hermitian eigendecompositions of independent dense matrices (one per charge group), spread over side streams and
+// host threads: cusolverDnDsyevd is largely host-driven (its calls block while panels are factorised), so each side
+// solver gets its own host thread and the decompositions of the large charge groups really run concurrently.
+struct EighJob { int64_t n; double* A; double* W; std::vector<double>* vals; int64_t lda; };   // A: in matrix / out eigenvectors
+static void syevd_batch(Ctx* ctx, std::vector<EighJob>& jobs) {
+  if (jobs.empty()) return;
+  ctx->sync();
+  std::vector<size_t> order(jobs.size());
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return jobs[a].n > jobs[b].n; });
+  auto& sides = side_solvers(ctx);
+  std::vector<int> slot_of(jobs.size());
+  std::vector<int> used(sides.size(), 0);
+  for (size_t k = 0; k < order.size(); k++) {
+    TNL_CHECK(used[k % sides.size()] < 64, "too many charge groups per side stream");
+    slot_of[order[k]] = used[k % sides.size()]++;
+  }
+  std::vector<std::string> errs(sides.size());
+  auto worker = [&](size_t si) {
+    try {
+      CUDA_OK(cudaSetDevice(ctx->device));
+      SideSolver& sv = sides[si];
+      for (size_t k = si; k < order.size(); k += sides.size()) {
+        EighJob& j = jobs[order[k]];
+        int lwork = 0;
+        CUSOLVER_OK(cusolverDnDsyevd_bufferSize(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)j.n, j.A, (int)j.lda,
+                                                j.W, &lwork));
+        if ((size_t)lwork * sizeof(double) > sv.bytes) {
+          CUDA_OK(cudaStreamSynchronize(sv.s));
+          if (sv.work) cudaFree(sv.work);
+          sv.bytes = (size_t)lwork * sizeof(double) * 5 / 4;
+          CUDA_OK(cudaMalloc(&sv.work, sv.bytes));
+        }
+        CUSOLVER_OK(cusolverDnDsyevd(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)j.n, j.A, (int)j.lda, j.W,
+                                     sv.work, lwork, sv.info + slot_of[order[k]]));
+      }
+      CUDA_OK(cudaStreamSynchronize(sv.s));
+    } catch (const std::exception& e) {
+      errs[si] = e.what();
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    const size_t nth = std::min(sides.size(), order.size());
+    for (size_t si = 1; si < nth; si++) th.emplace_back(worker, si);
+    if (nth > 0) worker(0);
+    for (auto& t : th) t.join();
+    for (auto& e : errs) TNL_CHECK(e.empty(), e);
+  }
+  for (auto& sv : sides) CUDA_OK(cudaStreamSynchronize(sv.s));
+  for (size_t k = 0; k < order.size(); k++) {
+    EighJob& j = jobs[order[k]];
+    SideSolver& sv = sides[k % sides.size()];
+    j.vals->resize(j.n);
+    CUDA_OK(cudaMemcpy(j.vals->data(), j.W, j.n * sizeof(double), cudaMemcpyDeviceToHost));
+    int info = 0;
+    CUDA_OK(cudaMemcpy(&info, sv.info + slot_of[order[k]], sizeof(int), cudaMemcpyDeviceToHost));
+    TNL_CHECK(info == 0, "cusolverDnDsyevd did not converge");
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // QR / LQ gauge move without truncation (ITensors `factorize(...; which_decomp = "qr")`, what
@@ -408,6 +500,130 @@ static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const Factor
   return res;
 }
 
+// Multi-GPU spectrum exchange: every rank fills the segments of its own groups, the rest is zero; one all-reduce.
+// Afterwards every rank holds the values of every group (f.nvals each).
+static void exchange_spectrum(Ctx* ctx, std::vector<FG>& fg) {
+  int64_t tot = 0;
+  for (FG& f : fg) tot += f.nvals;
+  std::vector<double> all((size_t)((tot + 1) & ~int64_t(1)), 0.0);
+  int64_t o = 0;
+  for (FG& f : fg) {
+    if (f.mine) for (int64_t i = 0; i < (int64_t)f.vals.size(); i++) all[o + i] = f.vals[i];
+    o += f.nvals;
+  }
+  if (tot > 0) {
+    double* d = ctx->upload(all);
+    comm_allreduce_sum(ctx, d, (int64_t)all.size());
+    CUDA_OK(cudaMemcpyAsync(all.data(), d, all.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    ctx->free(d);
+  }
+  o = 0;
+  for (FG& f : fg) {
+    f.vals.assign(all.begin() + o, all.begin() + o + f.nvals);
+    o += f.nvals;
+  }
+}
+
+// Deflated Gram refinement -- what makes the Gram-matrix SVD as accurate as a bidiagonalisation-based one.
+// The eigenvalues of rho = M M^T come out with an ABSOLUTE error eps * sigma_max^2, so weights below ~1e-10 of the
+// largest carry few correct digits (a converged DMRG state keeps weights down to the cutoff, 1e-15).  The eigenvectors
+// U, however, are orthonormal to eps and split the space cleanly: the span U_T of the unresolved ones contains the
+// small singular directions, and in that subspace the problem is well scaled again,
+//     B = U_T^T M   (|T| x C),   rho_2 = B B^T  with  ||rho_2|| <= tau * sigma_max^2,
+// so one more eigendecomposition of the |T| x |T| matrix resolves ten further orders of magnitude (leakage of the
+// resolved directions into rho_2 is O(eps^2)).  Repeating this at most three times covers the whole double range.
+// Only directions that can still matter for the truncation are refined: weights more than 1e3 below the smallest
+// kept weight stay as they are (they are discarded either way and enter only the truncation error).  Everything is
+// grouped DGEMMs on the DMMA kernel plus eigendecompositions of shrinking size.
+template <class TAlloc>
+static void refine_gram_spectrum(Ctx* ctx, std::vector<FG>& fg, bool left, const FactorizeParams& prm, TAlloc& talloc) {
+  const double tau = 1e-10;
+  auto off = [](const double* p) { return (int64_t)(reinterpret_cast<intptr_t>(p) / (intptr_t)sizeof(double)); };
+  auto ev = [](int64_t x) { return (x + 1) & ~int64_t(1); };
+  for (int level = 1; level <= 3; level++) {
+    if (ctx->shard_world() > 1) exchange_spectrum(ctx, fg);
+    std::vector<double> pooled;
+    for (FG& f : fg)
+      for (int i : f.admissible()) pooled.push_back(std::fabs(f.vals[i]));
+    if (pooled.empty()) return;
+    std::sort(pooled.begin(), pooled.end(), std::greater<double>());
+    const double wmax = pooled[0];
+    if (!(wmax > 0.0)) return;
+    std::vector<double> kept = pooled;
+    double te = 0, dc = 0;
+    truncate_spectrum(kept, prm.maxdim, prm.mindim, prm.cutoff, te, dc);
+    const double pcut = kept.empty() ? 0.0 : kept.back();
+    const double hi = std::pow(tau, level) * wmax;              // weights below `hi` are unresolved so far
+    if (pcut >= hi) return;                                     // every kept weight is resolved
+    const double noise_floor = 1e-16 * std::pow(tau, level - 1) * wmax;
+    const double lo = pcut > 1e3 * noise_floor ? 1e-3 * pcut : -1.0;
+    struct Sub { FG* f; std::vector<int> idx; int64_t n, t; double *Ut, *B, *G2, *W2, *Un; std::vector<double> mu; };
+    std::vector<Sub> subs;
+    for (FG& f : fg) {
+      if (!f.mine || !f.E || !f.M) continue;
+      Sub sb{};
+      sb.f = &f;
+      sb.n = left ? f.R : f.C;
+      for (int i : f.admissible()) {
+        const double w = std::fabs(f.vals[i]);
+        if (w < hi && w >= lo) sb.idx.push_back(i);
+      }
+      sb.t = (int64_t)sb.idx.size();
+      if (sb.t > 0) subs.push_back(std::move(sb));
+    }
+    // (no early return on an empty list: under sharding the other ranks may still have groups to refine and the
+    // loop head contains a collective)
+    std::vector<GemmProblem> p1, p2, p3;
+    for (Sub& sb : subs) {
+      FG& f = *sb.f;
+      const int64_t n = sb.n, t = sb.t, ldn = ev(n), ldt = ev(t);
+      sb.Ut = talloc(ldn * t);
+      gather_cols(ctx, sb.Ut, ldn, f.E, n, n, sb.idx, nullptr);
+      sb.G2 = talloc(ldt * t);
+      sb.W2 = talloc(t);
+      sb.Un = talloc(ldn * t);
+      GemmProblem a{}, b{}, c{};
+      if (left) {
+        // B[t x C] = U_T^T M ;  G2 = B B^T
+        sb.B = talloc(ldt * f.C);
+        a.M = (int)t; a.N = (int)f.C; a.K = (int)f.R; a.a = off(sb.Ut); a.lda = (int)ldn; a.b = off(f.M); a.ldb = (int)f.ldm;
+        a.c = off(sb.B); a.ldc = (int)ldt;
+        b.M = b.N = (int)t; b.K = (int)f.C; b.a = b.b = off(sb.B); b.lda = b.ldb = (int)ldt; b.c = off(sb.G2); b.ldc = (int)ldt;
+      } else {
+        // B[R x t] = M V_T ;  G2 = B^T B
+        const int64_t ldr = ev(f.R);
+        sb.B = talloc(ldr * t);
+        a.M = (int)f.R; a.N = (int)t; a.K = (int)f.C; a.a = off(f.M); a.lda = (int)f.ldm; a.b = off(sb.Ut); a.ldb = (int)ldn;
+        a.c = off(sb.B); a.ldc = (int)ldr;
+        b.M = b.N = (int)t; b.K = (int)f.R; b.a = b.b = off(sb.B); b.lda = b.ldb = (int)ldr; b.c = off(sb.G2); b.ldc = (int)ldt;
+      }
+      // refined vectors  U_T V2  [n x t]
+      c.M = (int)n; c.N = (int)t; c.K = (int)t; c.a = off(sb.Ut); c.lda = (int)ldn; c.b = off(sb.G2); c.ldb = (int)ldt;
+      c.c = off(sb.Un); c.ldc = (int)ldn;
+      p1.push_back(a); p2.push_back(b); p3.push_back(c);
+    }
+    if (!subs.empty()) {
+      auto g1 = plan_gemm_raw(ctx, left, false, p1);             // left: op(A) = U_T^T
+      run_gemm(ctx, *g1, nullptr, nullptr, nullptr);
+      auto g2 = plan_gemm_raw(ctx, !left, left, p2);             // left: B B^T ; right: B^T B
+      run_gemm(ctx, *g2, nullptr, nullptr, nullptr);
+      ctx->sync();
+      std::vector<EighJob> jobs;
+      for (Sub& sb : subs) jobs.push_back(EighJob{sb.t, sb.G2, sb.W2, &sb.mu, ev(sb.t)});
+      syevd_batch(ctx, jobs);
+      auto g3 = plan_gemm_raw(ctx, false, false, p3);
+      run_gemm(ctx, *g3, nullptr, nullptr, nullptr);
+      for (Sub& sb : subs) {
+        FG& f = *sb.f;
+        scatter_cols(ctx, f.E, sb.n, sb.Un, ev(sb.n), sb.n, sb.idx);
+        for (int64_t k = 0; k < sb.t; k++) f.vals[sb.idx[k]] = sb.mu[k];
+      }
+      ctx->sync();
+    }
+  }
+}
+
 FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm) {
   if (T.cplx) return factorize_complex(ctx, T, prm);
   const int split = T.nrow, rank = T.rank();
@@ -419,10 +635,11 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
   cusolverDnHandle_t H = solver(ctx);
   int svd_alg = prm.svd_alg;
   if (which == 3) return factorize_qr(ctx, T, left, prm.new_dir_on_L);
-  // svd_alg 2 ("gram"): singular vectors from the Hermitian eigenproblem of M M^T / M^T M (three DGEMM-rich
-  // steps instead of a latency-bound vendor SVD).  sigma^2 is then accurate to eps*sigma_max^2 ABSOLUTE, so the
-  // result is accepted only if every kept weight is >= 1e-10 of the largest; otherwise fall back to gesvdp.
-  const bool gram = (which == 1 && svd_alg == 2);
+  // SVD drivers: 0 ("divide_and_conquer", the reference's default) and 2 ("gram") = singular vectors from the
+  // Hermitian eigenproblem of M M^T / M^T M built with the grouped DGEMM, followed by the deflated refinement
+  // (refine_gram_spectrum) that restores the accuracy of a bidiagonalisation-based SVD for small singular values;
+  // 1 = cusolverDnXgesvdp (polar), 3 = cusolverDnDgesvd (QR iteration).
+  const bool gram = (which == 1 && (svd_alg == 0 || svd_alg == 2));
   if (gram) which = 2;
 
   // ---- collect charge groups (union of T's and, on the kept side, the noise operand's)
@@ -471,7 +688,10 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
       fg[i].mine = (r == ctx->rank);
     }
   }
-  for (FG& f : fg) f.nvals = which == 1 ? std::min(f.R, f.C) : (left ? f.R : f.C);
+  for (FG& f : fg) {
+    f.nvals = which == 1 ? std::min(f.R, f.C) : (left ? f.R : f.C);
+    if (gram) f.kmax = std::min(f.R, f.C);
+  }
 
   std::vector<void*> temps;                        // overflow allocations (arena too small this time)
   ctx->arena_reset();
@@ -498,7 +718,7 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
       double* S = talloc(n);
       double* Uw = talloc(m * n);
       double* Vw = talloc(n * n);
-      const int alg = (n >= 64) ? svd_alg : 0;
+      const int alg = (n >= 64) ? svd_alg : 3;
       if (alg == 1) {
         // polar-decomposition SVD (QDWH + syevd inside cuSOLVER): same absolute accuracy as gesvd, GEMM-rich
         static cusolverDnParams_t params = nullptr;
@@ -589,134 +809,42 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
         ctx->sync();                               // gn's device arrays die with this iteration
       }
     }
-    // Hermitian eigendecompositions, one per charge group, spread over side streams so that the
-    // host-latency-bound phases of cusolverDnDsyevd of different groups overlap
-    std::vector<FG*> todo;
-    std::vector<double*> Wvs;
+    // Hermitian eigendecompositions, one per charge group
+    std::vector<EighJob> jobs;
     for (FG& f : fg) {
       const int64_t n = left ? f.R : f.C;
       if (n == 0 || !f.mine) continue;
-      todo.push_back(&f);
-      Wvs.push_back(talloc(n));
+      jobs.push_back(EighJob{n, f.E, talloc(n), &f.vals, n});
     }
     ctx->sync();
     g.reset();
-    std::vector<size_t> order(todo.size());
-    std::iota(order.begin(), order.end(), 0);
-    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
-      return (left ? todo[a]->R : todo[a]->C) > (left ? todo[b]->R : todo[b]->C);
-    });
-    auto& sides = side_solvers(ctx);
-    std::vector<int> slot_of(todo.size());
-    std::vector<int> used(sides.size(), 0);
-    for (size_t k = 0; k < order.size(); k++) {
-      TNL_CHECK(used[k % sides.size()] < 64, "too many charge groups per side stream");
-      slot_of[order[k]] = used[k % sides.size()]++;
-    }
-    // cusolverDnDsyevd is largely host-driven (its calls block while panels are factorised), so each side
-    // solver gets its own host thread: the decompositions of the large charge groups really run concurrently
-    std::vector<std::string> errs(sides.size());
-    auto worker = [&](size_t si) {
-      try {
-        CUDA_OK(cudaSetDevice(ctx->device));
-        SideSolver& sv = sides[si];
-        for (size_t k = si; k < order.size(); k += sides.size()) {
-          FG& f = *todo[order[k]];
-          const int64_t n = left ? f.R : f.C;
-          int lwork = 0;
-          CUSOLVER_OK(cusolverDnDsyevd_bufferSize(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, f.E,
-                                                  (int)n, Wvs[order[k]], &lwork));
-          if ((size_t)lwork * sizeof(double) > sv.bytes) {
-            CUDA_OK(cudaStreamSynchronize(sv.s));
-            if (sv.work) cudaFree(sv.work);
-            sv.bytes = (size_t)lwork * sizeof(double) * 5 / 4;
-            CUDA_OK(cudaMalloc(&sv.work, sv.bytes));
-          }
-          CUSOLVER_OK(cusolverDnDsyevd(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, f.E, (int)n,
-                                       Wvs[order[k]], sv.work, lwork, sv.info + slot_of[order[k]]));
-        }
-        CUDA_OK(cudaStreamSynchronize(sv.s));
-      } catch (const std::exception& e) {
-        errs[si] = e.what();
-      }
-    };
-    {
-      std::vector<std::thread> th;
-      const size_t nth = std::min(sides.size(), order.size());
-      for (size_t si = 1; si < nth; si++) th.emplace_back(worker, si);
-      if (nth > 0) worker(0);
-      for (auto& t : th) t.join();
-      for (auto& e : errs) TNL_CHECK(e.empty(), e);
-    }
-    for (auto& sv : sides) CUDA_OK(cudaStreamSynchronize(sv.s));
-    for (size_t k = 0; k < order.size(); k++) {
-      FG& f = *todo[order[k]];
-      const int64_t n = left ? f.R : f.C;
-      SideSolver& sv = sides[k % sides.size()];
-      f.vals.resize(n);
-      CUDA_OK(cudaMemcpy(f.vals.data(), Wvs[order[k]], n * sizeof(double), cudaMemcpyDeviceToHost));
-      int info = 0;
-      CUDA_OK(cudaMemcpy(&info, sv.info + slot_of[order[k]], sizeof(int), cudaMemcpyDeviceToHost));
-      TNL_CHECK(info == 0, "cusolverDnDsyevd did not converge");
-    }
+    syevd_batch(ctx, jobs);
+    if (gram) refine_gram_spectrum(ctx, fg, left, prm, talloc);
     for (FG& f : fg)
-      for (double w : f.vals) pool.push_back(std::fabs(w));
+      for (int i : f.admissible()) pool.push_back(std::fabs(f.vals[i]));
   }
 
   if (W > 1) {
-    // spectrum exchange: every rank fills the segments of its own groups, the rest is zero; one all-reduce
-    int64_t tot = 0;
-    for (FG& f : fg) tot += f.nvals;
-    std::vector<double> all((size_t)((tot + 1) & ~int64_t(1)), 0.0);
-    int64_t o = 0;
-    for (FG& f : fg) {
-      if (f.mine) for (int64_t i = 0; i < (int64_t)f.vals.size(); i++) all[o + i] = f.vals[i];
-      o += f.nvals;
-    }
-    if (tot > 0) {
-      double* d = ctx->upload(all);
-      comm_allreduce_sum(ctx, d, (int64_t)all.size());
-      CUDA_OK(cudaMemcpyAsync(all.data(), d, all.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-      ctx->sync();
-      ctx->free(d);
-    }
-    o = 0;
+    exchange_spectrum(ctx, fg);
     pool.clear();
-    for (FG& f : fg) {
-      f.vals.assign(all.begin() + o, all.begin() + o + f.nvals);
-      o += f.nvals;
-      for (double v : f.vals) pool.push_back(which == 1 ? v * v : std::fabs(v));
-    }
+    for (FG& f : fg)
+      for (int i : f.admissible()) pool.push_back(which == 1 ? f.vals[i] * f.vals[i] : std::fabs(f.vals[i]));
   }
 
   // ---- pooled truncation
   std::sort(pool.begin(), pool.end(), std::greater<double>());
   FactorizeResult res;
-  res.path = which == 1 ? "svd" : (gram ? "svd(gram)" : "eigen");
+  res.path = which == 1 ? "svd" : (gram ? "svd(gram, deflated refinement)" : "eigen");
   double docut = 0.0;
-  const double wmax = pool.empty() ? 0.0 : pool[0];
   truncate_spectrum(pool, prm.maxdim, prm.mindim, prm.cutoff, res.truncerr, docut);
   res.eigs = pool;
-  if (gram && !pool.empty() && pool.back() < 1e-10 * wmax) {
-    ctx->sync();
-    for (void* p : temps) ctx->free(p);
-    FactorizeParams p2 = prm;
-    p2.which = 1;
-    p2.svd_alg = 1;
-    FactorizeResult r2 = factorize(ctx, T, p2);
-    r2.path = "svd(polar, gram guard tripped)";
-    return r2;
-  }
   Index m;
   m.nq = T.inds[0].nq;
   std::vector<FG*> kept;
   for (FG& f : fg) {
     if (f.vals.empty()) continue;
-    std::vector<int> order(f.vals.size());
-    std::iota(order.begin(), order.end(), 0);
     auto wt = [&](int i) { return which == 1 ? f.vals[i] * f.vals[i] : std::fabs(f.vals[i]); };
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return wt(a) > wt(b); });
-    for (int i : order)
+    for (int i : f.admissible())
       if (wt(i) > docut) f.keep.push_back(i);
     if (f.keep.empty()) continue;
     m.dims.push_back((int)f.keep.size());

@@ -153,7 +153,7 @@ class StateEnvs:
         neigs = C.c_int64()
         carry = C.c_void_p()
         md = 0 if maxdim is None or maxdim >= (1 << 62) else int(maxdim)
-        alg = {"divide_and_conquer": 0, "qr_iteration": 0, "recursive": 0, "polar": 1, "gram": 2}[svd_alg]
+        alg = {"divide_and_conquer": 0, "recursive": 0, "polar": 1, "gram": 2, "qr_iteration": 3}[svd_alg]
         check(self.ctx.lib.tnl_svd_split(self.h, pos, phi.h, 1 if ortho == "left" else 0, md, int(mindim), float(cutoff),
                                          1 if normalize else 0, alg, C.byref(truncerr), eigs.ctypes.data, cap,
                                          C.byref(neigs), None if absorb else C.byref(carry)), self.ctx.h)
@@ -222,7 +222,7 @@ class StateEnvs:
         truncerr = C.c_double()
         neigs = C.c_int64()
         which = {None: 0, "svd": 1, "eigen": 2}[which_decomp]
-        which |= {"divide_and_conquer": 0, "qr_iteration": 0, "recursive": 0, "polar": 1, "gram": 2}[svd_alg] << 4
+        which |= {"divide_and_conquer": 0, "recursive": 0, "polar": 1, "gram": 2, "qr_iteration": 3}[svd_alg] << 4
         md = 0 if maxdim is None or maxdim >= (1 << 62) else int(maxdim)
         check(self.ctx.lib.tnl_replacebond(self.h, pos, phi.h, 1 if ortho == "left" else 0, md, int(mindim),
                                            float(cutoff), float(noise), 1 if normalize else 0, which,
