@@ -22,6 +22,7 @@ extern "C" {
 typedef struct tnl_ctx_s* tnl_ctx_t;
 typedef struct tnl_tensor_s* tnl_tensor_t;
 typedef struct tnl_env_s* tnl_env_t;
+typedef struct tnl_sumop_s* tnl_sumop_t;
 
 /* One QN index: ITensors `Index{Vector{Pair{QN,Int}}}` -- sector dims, nq charges per sector, arrow. */
 typedef struct {
@@ -176,6 +177,42 @@ int tnl_svd_split(tnl_env_t env, int32_t pos, tnl_tensor_t phi, int32_t ortho_le
                   double cutoff, int32_t normalize, int32_t svd_alg, double* truncerr, double* eigs, int64_t cap,
                   int64_t* neigs, tnl_tensor_t* carry);
 int tnl_env_absorb_bond(tnl_env_t env, int32_t pos, int32_t ortho_left, tnl_tensor_t carry);
+
+/* ---- generic block-sparse tensor algebra: the ITensor operations of the tree-tensor-network path ------------------
+ * The TTN code of the reference is written as ITensor contractions over index identities
+ * (src/ttn/linktensors.jl:63-118,183-221, src/ttn/ttn.jl:266-310, src/ttn/linkproj.jl:56-179,
+ * src/ttn/update_site_ttn.jl:75-109); so are the Global Subspace Expansion (src/mps/sweep.jl:399-555) and the
+ * measurements (src/mps/measure.jl).  An index identity is an integer LABEL chosen by the caller (the shim uses the
+ * ITensor index id + prime level). */
+/* out(j_0..) = t(i_perm[0]..): index k of the result is index perm[k] of t; result laid out with `nrow` row indices */
+int tnl_tensor_permute(tnl_tensor_t t, const int32_t* perm, int32_t nrow, tnl_tensor_t* out);
+/* ITensor `A * B` (or dag(A) * B, ...): contracts every label the two tensors share; result indices = free indices of
+ * A then of B; labels_out must hold rank(A) + rank(B) entries.  At least one free index must remain. */
+int tnl_tensor_contract(tnl_tensor_t a, const int32_t* labels_a, int32_t dag_a, tnl_tensor_t b, const int32_t* labels_b,
+                        int32_t dag_b, tnl_tensor_t* out, int32_t* labels_out, int32_t* rank_out);
+/* ITensors `directsum(A => ia, B => ib)` with all other indices shared and in the same order (ia == ib) */
+int tnl_tensor_directsum(tnl_tensor_t a, int32_t ia, tnl_tensor_t b, int32_t ib, tnl_tensor_t* out);
+/* ITensors `factorize` / `svd` / `qr` of t[(first nleft indices) | rest]: L(left..., m), R(m, right...);
+ * which_decomp as in tnl_replacebond (low bits 0 = reference rule, 1 = svd, 2 = eigen, 3 = qr without truncation). */
+int tnl_tensor_factorize(tnl_tensor_t t, int32_t nleft, int32_t ortho_left, int64_t maxdim, int64_t mindim, double cutoff,
+                         int32_t which_decomp, tnl_tensor_t* L, tnl_tensor_t* R, double* truncerr, double* eigs, int64_t cap,
+                         int64_t* neigs);
+/* Effective Hamiltonian of a tree node: H v = sum_terms noprime(v * x_1 * ... * x_k) + weight * sum_m <m|v> |m>
+ * (product(::LinkTensorsTTN) src/ttn/linktensors.jl:183-221; EnvCouplingModelProjTTN src/ttn/environment.jl:95-101).
+ * vlabels: labels of v's indices; a term lists its operand tensors with their labels (concatenated in labels_flat);
+ * relabel maps the labels of the primed output indices back to v's (noprime).  eig_solver / exp_solver run the same
+ * device Krylov loops as for the MPS (src/ttn/update_site_ttn.jl:60 -> src/base/solver.jl:23-88). */
+int tnl_sumop_create(tnl_ctx_t ctx, int32_t rank, const int32_t* vlabels, tnl_sumop_t* out);
+int tnl_sumop_destroy(tnl_sumop_t op);
+int tnl_sumop_add_term(tnl_sumop_t op, int32_t nops, const tnl_tensor_t* tensors, const int32_t* labels_flat);
+int tnl_sumop_set_relabel(tnl_sumop_t op, int32_t n, const int32_t* from, const int32_t* to);
+int tnl_sumop_add_projector(tnl_sumop_t op, tnl_tensor_t m, double weight);
+int tnl_sumop_apply(tnl_sumop_t op, tnl_tensor_t v, tnl_tensor_t* out);
+int tnl_sumop_apply_flops(tnl_sumop_t op, double* flops); /* algorithmic GEMM flops of the last apply */
+int tnl_sumop_eigsolve(tnl_sumop_t op, tnl_tensor_t phi, double tol, int32_t krylovdim, int32_t maxiter, int32_t eager,
+                       double* eval, int32_t* converged, int32_t* numops, int32_t* numiter, double* normres);
+int tnl_sumop_exponentiate(tnl_sumop_t op, tnl_tensor_t phi, double t_re, double t_im, double tol, int32_t krylovdim,
+                           int32_t maxiter, int32_t eager, int32_t* converged, int32_t* numops, int32_t* numiter, double* err);
 
 #ifdef __cplusplus
 }

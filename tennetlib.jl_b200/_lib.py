@@ -83,6 +83,22 @@ _SIGS = {
     "tnl_env_absorb_bond": [_P, C.c_int32, C.c_int32, _P],
     "tnl_exponentiate": [_P, _P, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)],
+    "tnl_tensor_permute": [_P, _P, C.c_int32, C.POINTER(_P)],
+    "tnl_tensor_contract": [_P, _P, C.c_int32, _P, _P, C.c_int32, C.POINTER(_P), _P, C.POINTER(C.c_int32)],
+    "tnl_tensor_directsum": [_P, C.c_int32, _P, C.c_int32, C.POINTER(_P)],
+    "tnl_tensor_factorize": [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.POINTER(_P),
+                             C.POINTER(_P), C.POINTER(C.c_double), _P, C.c_int64, C.POINTER(C.c_int64)],
+    "tnl_sumop_create": [_P, C.c_int32, _P, C.POINTER(_P)],
+    "tnl_sumop_destroy": [_P],
+    "tnl_sumop_add_term": [_P, C.c_int32, C.POINTER(_P), _P],
+    "tnl_sumop_set_relabel": [_P, C.c_int32, _P, _P],
+    "tnl_sumop_add_projector": [_P, _P, C.c_double],
+    "tnl_sumop_apply": [_P, _P, C.POINTER(_P)],
+    "tnl_sumop_apply_flops": [_P, C.POINTER(C.c_double)],
+    "tnl_sumop_eigsolve": [_P, _P, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double),
+                           C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)],
+    "tnl_sumop_exponentiate": [_P, _P, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
+                               C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)],
     "tnl_replacebond": [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int32,
                         C.c_int32, C.POINTER(C.c_double), _P, C.c_int64, C.POINTER(C.c_int64)],
 }

@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libtnl_b200.so")
-SOURCES = ["kernels.cu", "core.cpp", "env.cpp", "factorize.cu", "comm.cpp", "capi.cpp"]
-HEADERS = ["core.hpp", "env.hpp", os.path.join("..", "..", "include", "tnl_b200.h")]
+SOURCES = ["kernels.cu", "core.cpp", "env.cpp", "factorize.cu", "algebra.cu", "comm.cpp", "capi.cpp"]
+HEADERS = ["core.hpp", "env.hpp", "krylov.hpp", "algebra.hpp", os.path.join("..", "..", "include", "tnl_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-x", "cu"]

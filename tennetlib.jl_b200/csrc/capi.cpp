@@ -5,13 +5,16 @@
 #include <cmath>
 #include <cstring>
 
+#include "algebra.hpp"
 #include "env.hpp"
+#include "krylov.hpp"
 
 using namespace tnl;
 
 struct tnl_ctx_s { Ctx ctx; cudaEvent_t ev[8] = {}; double cat_ms[8] = {}; explicit tnl_ctx_s(int dev) : ctx(dev) {} };
 struct tnl_tensor_s { TensorP t; };
 struct tnl_env_s { Env env; tnl_env_s(Ctx* c, int n) : env(c, n) {} };
+struct tnl_sumop_s { SumOp op; explicit tnl_sumop_s(Ctx* c) : op(c) {} };
 
 static thread_local std::string g_last_error;
 
@@ -508,6 +511,119 @@ int tnl_svd_split(tnl_env_t e, int32_t pos, tnl_tensor_t phi, int32_t ortho_left
     *truncerr = f.truncerr;
     *neigs = (int64_t)f.eigs.size();
     for (int64_t i = 0; i < std::min<int64_t>(cap, *neigs); i++) eigs[i] = f.eigs[i];
+  });
+}
+
+
+/* ---- generic tensor algebra (algebra.hpp) ---------------------------------------------------------------------- */
+int tnl_tensor_permute(tnl_tensor_t t, const int32_t* perm, int32_t nrow, tnl_tensor_t* out) {
+  return guard(t->t->ctx, [&] {
+    std::vector<int> p(perm, perm + t->t->rank());
+    *out = new tnl_tensor_s{permute(t->t->ctx, *t->t, p, nrow)};
+  });
+}
+int tnl_tensor_contract(tnl_tensor_t a, const int32_t* labels_a, int32_t dag_a, tnl_tensor_t b, const int32_t* labels_b,
+                        int32_t dag_b, tnl_tensor_t* out, int32_t* labels_out, int32_t* rank_out) {
+  return guard(a->t->ctx, [&] {
+    std::vector<int> la(labels_a, labels_a + a->t->rank()), lb(labels_b, labels_b + b->t->rank()), lc;
+    TensorP c = contract(a->t->ctx, *a->t, la, dag_a != 0, *b->t, lb, dag_b != 0, &lc);
+    a->t->ctx->sync();
+    for (size_t k = 0; k < lc.size(); k++) labels_out[k] = lc[k];
+    *rank_out = (int32_t)lc.size();
+    *out = new tnl_tensor_s{c};
+  });
+}
+int tnl_tensor_directsum(tnl_tensor_t a, int32_t ia, tnl_tensor_t b, int32_t ib, tnl_tensor_t* out) {
+  return guard(a->t->ctx, [&] {
+    *out = new tnl_tensor_s{directsum(a->t->ctx, *a->t, ia, *b->t, ib)};
+    a->t->ctx->sync();
+  });
+}
+int tnl_tensor_factorize(tnl_tensor_t t, int32_t nleft, int32_t ortho_left, int64_t maxdim, int64_t mindim, double cutoff,
+                         int32_t which_decomp, tnl_tensor_t* L, tnl_tensor_t* R, double* truncerr, double* eigs, int64_t cap,
+                         int64_t* neigs) {
+  return guard(t->t->ctx, [&] {
+    Ctx* ctx = t->t->ctx;
+    TNL_CHECK(nleft >= 1 && nleft < t->t->rank(), "factorize needs a proper bipartition");
+    FactorizeParams prm;
+    prm.ortho_left = ortho_left;
+    prm.maxdim = maxdim <= 0 ? INT64_MAX : maxdim;
+    prm.mindim = mindim;
+    prm.cutoff = cutoff;
+    prm.which = which_decomp & 15;
+    prm.svd_alg = which_decomp >> 4;
+    TensorP T = t->t->nrow == nleft ? t->t : relayout(ctx, *t->t, nleft);
+    FactorizeResult f = factorize(ctx, *T, prm);
+    ctx->sync();
+    *L = new tnl_tensor_s{f.L};
+    *R = new tnl_tensor_s{f.R};
+    if (truncerr) *truncerr = f.truncerr;
+    if (neigs) *neigs = (int64_t)f.eigs.size();
+    if (eigs) for (int64_t i = 0; i < std::min<int64_t>(cap, (int64_t)f.eigs.size()); i++) eigs[i] = f.eigs[i];
+  });
+}
+
+int tnl_sumop_create(tnl_ctx_t c, int32_t rank, const int32_t* vlabels, tnl_sumop_t* out) {
+  return guard(&c->ctx, [&] {
+    auto* h = new tnl_sumop_s(&c->ctx);
+    h->op.vlabels.assign(vlabels, vlabels + rank);
+    *out = h;
+  });
+}
+int tnl_sumop_destroy(tnl_sumop_t op) {
+  return guard(nullptr, [&] { delete op; });
+}
+int tnl_sumop_add_term(tnl_sumop_t op, int32_t nops, const tnl_tensor_t* tensors, const int32_t* labels_flat) {
+  return guard(op->op.ctx, [&] {
+    SumOp::Term term;
+    int at = 0;
+    for (int k = 0; k < nops; k++) {
+      SumOp::Operand o;
+      o.t = tensors[k]->t;
+      o.labels.assign(labels_flat + at, labels_flat + at + o.t->rank());
+      at += o.t->rank();
+      term.ops.push_back(std::move(o));
+    }
+    op->op.terms.push_back(std::move(term));
+  });
+}
+int tnl_sumop_set_relabel(tnl_sumop_t op, int32_t n, const int32_t* from, const int32_t* to) {
+  return guard(op->op.ctx, [&] {
+    op->op.relabel.clear();
+    for (int k = 0; k < n; k++) op->op.relabel.emplace_back(from[k], to[k]);
+  });
+}
+int tnl_sumop_add_projector(tnl_sumop_t op, tnl_tensor_t m, double weight) {
+  return guard(op->op.ctx, [&] {
+    TNL_CHECK(weight > 0.0, "`weight` parameter should be > 0.0");
+    op->op.projs.push_back(m->t);
+    op->op.weight = weight;
+  });
+}
+int tnl_sumop_apply(tnl_sumop_t op, tnl_tensor_t v, tnl_tensor_t* out) {
+  return guard(op->op.ctx, [&] {
+    auto o = std::make_shared<Tensor>(op->op.ctx, v->t->inds, v->t->nrow, true, v->t->cplx);
+    op->op.apply(*v->t, *o);
+    op->op.ctx->sync();
+    *out = new tnl_tensor_s{o};
+  });
+}
+int tnl_sumop_apply_flops(tnl_sumop_t op, double* flops) {
+  return guard(op->op.ctx, [&] { *flops = op->op.flops; });
+}
+int tnl_sumop_eigsolve(tnl_sumop_t op, tnl_tensor_t phi, double tol, int32_t krylovdim, int32_t maxiter, int32_t eager,
+                       double* eval, int32_t* converged, int32_t* numops, int32_t* numiter, double* normres) {
+  return guard(op->op.ctx, [&] {
+    LanczosResult r = krylov_eigsolve(op->op.ctx, op->op, *phi->t, tol, krylovdim, maxiter, eager != 0);
+    *eval = r.eval; *converged = r.converged; *numops = r.numops; *numiter = r.numiter; *normres = r.normres;
+  });
+}
+int tnl_sumop_exponentiate(tnl_sumop_t op, tnl_tensor_t phi, double t_re, double t_im, double tol, int32_t krylovdim,
+                           int32_t maxiter, int32_t eager, int32_t* converged, int32_t* numops, int32_t* numiter, double* err) {
+  return guard(op->op.ctx, [&] {
+    if (t_im != 0.0) phi->t = promoted(phi->t);
+    ExpResult r = krylov_exponentiate(op->op.ctx, op->op, *phi->t, t_re, t_im, tol, krylovdim, maxiter, eager != 0);
+    *converged = r.converged; *numops = r.numops; *numiter = r.numiter; *err = r.err;
   });
 }
 

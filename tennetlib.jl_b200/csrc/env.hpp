@@ -114,6 +114,11 @@ class Env {
   void apply_ptr(const Tensor& proto, const double* vin, double* vout);
   void apply_local(const double* vloc, double* outloc);   // sharded core (multi-GPU)
   void ensure_plan(const Tensor& proto);
+  // operator interface of the Krylov templates (krylov.hpp)
+  bool op_sharded() const;
+  int64_t op_nloc() const;
+  void op_to_local(const double* full, double* loc);
+  void op_gather(const double* loc, double* full);
   LanczosResult eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter, bool eager);
   // exp_solver: phi <- exp(t * H_eff) phi  (KrylovKit.exponentiate)
   ExpResult exponentiate(Tensor& phi, double t_re, double t_im, double tol, int krylovdim, int maxiter, bool eager);
