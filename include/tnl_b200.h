@@ -94,6 +94,7 @@ int tnl_tensor_create(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t
 int tnl_tensor_free(tnl_tensor_t t);
 int tnl_tensor_copy(tnl_tensor_t t, tnl_tensor_t* out);
 int tnl_tensor_rank(tnl_tensor_t t, int32_t* rank, int32_t* nq);
+int tnl_tensor_nrow(tnl_tensor_t t, int32_t* nrow); /* number of leading indices forming the row group of the layout */
 int tnl_tensor_index(tnl_tensor_t t, int32_t which, int32_t* nsect, int32_t* dir, int32_t* dims, int32_t* qns,
                      int32_t cap);
 int tnl_tensor_export_size(tnl_tensor_t t, int64_t* nblocks, int64_t* nelem);
@@ -186,6 +187,7 @@ int tnl_env_absorb_bond(tnl_env_t env, int32_t pos, int32_t ortho_left, tnl_tens
  * ITensor index id + prime level). */
 /* out(j_0..) = t(i_perm[0]..): index k of the result is index perm[k] of t; result laid out with `nrow` row indices */
 int tnl_tensor_permute(tnl_tensor_t t, const int32_t* perm, int32_t nrow, tnl_tensor_t* out);
+int tnl_tensor_dag(tnl_tensor_t t, tnl_tensor_t* out); /* ITensors `dag`: arrows reversed, ComplexF64 conjugated */
 /* ITensor `A * B` (or dag(A) * B, ...): contracts every label the two tensors share; result indices = free indices of
  * A then of B; labels_out must hold rank(A) + rank(B) entries.  At least one free index must remain. */
 int tnl_tensor_contract(tnl_tensor_t a, const int32_t* labels_a, int32_t dag_a, tnl_tensor_t b, const int32_t* labels_b,

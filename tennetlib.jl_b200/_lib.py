@@ -84,6 +84,8 @@ _SIGS = {
     "tnl_exponentiate": [_P, _P, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)],
     "tnl_tensor_permute": [_P, _P, C.c_int32, C.POINTER(_P)],
+    "tnl_tensor_dag": [_P, C.POINTER(_P)],
+    "tnl_tensor_nrow": [_P, C.POINTER(C.c_int32)],
     "tnl_tensor_contract": [_P, _P, C.c_int32, _P, _P, C.c_int32, C.POINTER(_P), _P, C.POINTER(C.c_int32)],
     "tnl_tensor_directsum": [_P, C.c_int32, _P, C.c_int32, C.POINTER(_P)],
     "tnl_tensor_factorize": [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.POINTER(_P),

@@ -145,6 +145,30 @@ TensorP permute(Ctx* ctx, const Tensor& X, const std::vector<int>& perm, int nro
   return Y;
 }
 
+// dag(X) as a tensor of its own: arrows reversed (the charge groups change their order, hence a copy), ComplexF64
+// conjugated
+TensorP dag_copy(Ctx* ctx, const Tensor& X) {
+  const int r = X.rank();
+  std::vector<Index> inds = X.inds;
+  for (Index& ix : inds) ix.dir = -ix.dir;
+  auto Y = std::make_shared<Tensor>(ctx, inds, X.nrow, true, X.cplx);
+  std::vector<int> ident(r);
+  std::iota(ident.begin(), ident.end(), 0);
+  std::vector<PermBlock> pbs;
+  for (const Block& yb : Y->blocks) {
+    const int bi = X.find(yb.c);
+    TNL_CHECK(bi >= 0, "dag: block missing in the source");
+    pbs.push_back(perm_block(X.blocks[bi], yb, ident));
+  }
+  run_perm_blocks(ctx, pbs, X.d, Y->d);
+  if (X.cplx) {
+    run_perm_blocks(ctx, pbs, X.im(), Y->im());
+    vec_scale(ctx, Y->im(), Y->nelem, -1.0);
+  }
+  Y->present = X.present;
+  return Y;
+}
+
 // =================================================================================================
 // contraction over shared labels
 // =================================================================================================

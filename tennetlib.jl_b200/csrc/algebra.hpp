@@ -21,6 +21,8 @@ namespace tnl {
 // Y(j_0, ..., j_{r-1}) = X(i_perm[0], ..., i_perm[r-1]): Y's index k is X's index perm[k]; result laid out with `nrow`
 TensorP permute(Ctx* ctx, const Tensor& X, const std::vector<int>& perm, int nrow);
 
+TensorP dag_copy(Ctx* ctx, const Tensor& X);   // dag(X) materialised: arrows reversed, ComplexF64 conjugated
+
 // C = A * B over all labels the two tensors share (ITensor `*`).  dagA / dagB: the operand enters as dag(.) -- arrows
 // reversed and, for ComplexF64, conjugated.  Result indices: free indices of A (in A's order) then those of B;
 // `lc` receives their labels.  nrow of the result = number of free indices of A (at least one free index in total).

@@ -256,6 +256,9 @@ int tnl_tensor_copy(tnl_tensor_t t, tnl_tensor_t* out) {
 int tnl_tensor_rank(tnl_tensor_t t, int32_t* rank, int32_t* nq) {
   return guard(t->t->ctx, [&] { *rank = t->t->rank(); *nq = t->t->inds[0].nq; });
 }
+int tnl_tensor_nrow(tnl_tensor_t t, int32_t* nrow) {
+  return guard(t->t->ctx, [&] { *nrow = t->t->nrow; });
+}
 int tnl_tensor_index(tnl_tensor_t t, int32_t which, int32_t* nsect, int32_t* dir, int32_t* dims, int32_t* qns, int32_t cap) {
   return guard(t->t->ctx, [&] {
     TNL_CHECK(which >= 0 && which < t->t->rank(), "index number out of range");
@@ -521,6 +524,9 @@ int tnl_tensor_permute(tnl_tensor_t t, const int32_t* perm, int32_t nrow, tnl_te
     std::vector<int> p(perm, perm + t->t->rank());
     *out = new tnl_tensor_s{permute(t->t->ctx, *t->t, p, nrow)};
   });
+}
+int tnl_tensor_dag(tnl_tensor_t t, tnl_tensor_t* out) {
+  return guard(t->t->ctx, [&] { *out = new tnl_tensor_s{dag_copy(t->t->ctx, *t->t)}; });
 }
 int tnl_tensor_contract(tnl_tensor_t a, const int32_t* labels_a, int32_t dag_a, tnl_tensor_t b, const int32_t* labels_b,
                         int32_t dag_b, tnl_tensor_t* out, int32_t* labels_out, int32_t* rank_out) {

@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 from ._lib import check, tnl_index_t
 
-_ids = itertools.count(1)
+_ids = itertools.count(1 << 20)      # apart from the ids of foreign (test oracle / caller) index objects
 
 
 class Index:

@@ -267,3 +267,15 @@ def test_bench_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--chi", "128",
                           "--steps", "1", "--warmup", "1", "--gpus", "2"], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_graph_and_sweeppath_match_oracle():
+    from tennetlib.jl_b200 import graph as dg
+    from oracle import ttn as ot
+    for N in (4, 6, 8, 11, 12, 16, 27, 32, 100, 128):
+        g_o, sn_o = ot.default_graph_sitenodes(N)
+        g_d, sn_d = dg.default_graph_sitenodes(N)
+        assert sn_o == sn_d and {k: set(v) for k, v in g_o.adj.items()} == g_d.adj
+        assert dg.find_eccentric_central_node(g_d) == ot.find_eccentric_central_node(g_o)
+        src = sorted(g_d.nodes)[0]
+        assert dg.nodes_from_bfs(g_d, src, reverse=True) == ot.nodes_from_bfs(g_o, src, reverse=True)
