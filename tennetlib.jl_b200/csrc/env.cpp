@@ -1014,8 +1014,7 @@ void Env::absorb_bond(int pos, bool left, const Tensor& carry) {
 // move_center(N, 1) right-canonicalises an arbitrary MPS (sweep.jl:100-102).
 void Env::move_center(int from, int to) {
   TNL_CHECK(from >= 1 && from <= N && to >= 1 && to <= N, "site out of range");
-  for (int j = std::min(from, to); j <= std::max(from, to); j++)
-    TNL_CHECK(!A[j - 1]->cplx, "QR gauge moves of complex tensors are not built");
+  // ComplexF64: the gauge move comes from the Hermitian eigenproblem (factorize_complex, which == 3)
   FactorizeParams prm;
   prm.which = 3;
   for (int j = from; j > to; j--) {                // right-orthonormalise site j, push the rest into j-1
@@ -1024,10 +1023,11 @@ void Env::move_center(int from, int to) {
     FactorizeResult f = factorize(ctx, *Aq, prm);  // L (l, m) ; R = Q (m, s, r)
     A[j - 1] = f.R;
     TensorP Ap = as_nrow(ctx, A[j - 2], 2);        // [(l0 s0) | l]
-    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{Ap->inds[0], Ap->inds[1], f.L->inds[1]}, 2);
     TensorP Cm = as_nrow(ctx, f.L, 1);
+    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{Ap->inds[0], Ap->inds[1], f.L->inds[1]}, 2, true,
+                                       Ap->cplx || Cm->cplx);
     auto g = plan_gemm(*Ap, false, *Cm, false, *An);
-    run_gemm(ctx, *g, Ap->d, Cm->d, An->d);
+    cgemm(ctx, *g, *Ap, false, *Cm, false, *An);
     ctx->sync();
     A[j - 2] = An;
   }
@@ -1037,9 +1037,10 @@ void Env::move_center(int from, int to) {
     FactorizeResult f = factorize(ctx, *As, prm);  // L = Q (l, s, m) ; R (m, r)
     A[j - 1] = f.L;
     TensorP An1 = as_nrow(ctx, A[j], 1);           // [r | s2 r2]
-    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{f.R->inds[0], An1->inds[1], An1->inds[2]}, 1);
+    auto An = std::make_shared<Tensor>(ctx, std::vector<Index>{f.R->inds[0], An1->inds[1], An1->inds[2]}, 1, true,
+                                       f.R->cplx || An1->cplx);
     auto g = plan_gemm(*f.R, false, *An1, false, *An);
-    run_gemm(ctx, *g, f.R->d, An1->d, An->d);
+    cgemm(ctx, *g, *f.R, false, *An1, false, *An);
     ctx->sync();
     A[j] = An;
   }

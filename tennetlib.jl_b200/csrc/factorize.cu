@@ -322,7 +322,10 @@ __global__ void deinterleave_kernel(double* __restrict__ re, double* __restrict_
 static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const FactorizeParams& prm) {
   const int split = T.nrow;
   TNL_CHECK(prm.noise == 0.0 || prm.noiseX == nullptr, "noise term on complex tensors is not built");
-  TNL_CHECK(prm.which != 3, "QR gauge moves of complex tensors are not built");
+  // which == 3 (the untruncated gauge move of `qr` / `orthogonalize!`): the isometry spans range(M) -- the leading
+  // min(R, C) eigenvectors of rho per charge group -- and the other factor is its projection; another gauge of the
+  // same factorisation a Householder QR would give
+  const bool gauge_only = prm.which == 3;
   const bool left = prm.ortho_left != 0;
   cusolverDnHandle_t H = solver(ctx);
   const int64_t tn = T.nelem;
@@ -411,7 +414,7 @@ static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const Factor
   FactorizeResult res;
   res.path = "eigen(complex)";
   double docut = 0.0;
-  truncate_spectrum(pool, prm.maxdim, prm.mindim, prm.cutoff, res.truncerr, docut);
+  if (!gauge_only) truncate_spectrum(pool, prm.maxdim, prm.mindim, prm.cutoff, res.truncerr, docut);
   res.eigs = pool;
   Index m;
   m.nq = T.inds[0].nq;
@@ -423,6 +426,10 @@ static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const Factor
     std::iota(order.begin(), order.end(), 0);
     auto wt = [&](int i) { return std::fabs(f.vals[i]); };
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return wt(a) > wt(b); });
+    if (gauge_only) {
+      const int64_t k = std::min(f.R, f.C);
+      for (int64_t i = 0; i < k; i++) f.keep.push_back(order[i]);
+    } else
     for (int i : order)
       if (wt(i) > docut) f.keep.push_back(i);
     if (f.keep.empty()) continue;

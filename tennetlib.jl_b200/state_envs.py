@@ -40,6 +40,7 @@ class StateEnvs:
         if any(len(Hk) != self.N for Hk in Hs):
             raise ValueError("MPS and MPO lengths differ")
         self.nterms = len(Hs)
+        self.H_host = Hs[0] if len(Hs) == 1 else None      # krylov_extend! works on the MPO itself (sweep.jl:446)
         h = C.c_void_p()
         check(ctx.lib.tnl_env_create(ctx.h, self.N, C.byref(h)), ctx.h)
         self.h = h

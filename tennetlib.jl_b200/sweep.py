@@ -75,16 +75,17 @@ def fullsweep(sysenv, solver, nsite: int, swdata: SweepData, **kwargs):
 def dynamic_fullsweep(sysenv, solver, swdata: SweepData, eigthreshold: float = 1e-12, extendat=None, **kwargs):
     """`dynamic_fullsweep!` (src/mps/sweep.jl:257-382): per bond a one-site update where the smallest kept Schmidt
     weight of the previous half sweep is below `eigthreshold` or the bond is saturated at `maxdim`, a two-site
-    update otherwise.  The first sweep and every `extendat`-th one are plain two-site sweeps; for StateEnvs{ProjMPO}
-    the reference does a Global Subspace Expansion + one-site sweep there instead (`krylov_extend!`, sweep.jl:399-555),
-    which is not built: that case raises."""
+    update otherwise.  The first sweep and every `extendat`-th one are plain two-site sweeps -- except for
+    StateEnvs{ProjMPO}, where the reference does a Global Subspace Expansion followed by a one-site sweep
+    (`krylov_extend!`, sweep.jl:266-282,399-555; here gse.py on the device)."""
     maxdim = kwargs.get("maxdim", None)
     outputlevel = kwargs.get("outputlevel", 1)
     noise = kwargs.get("noise", 0.0)
     if swdata.sweepcount == 0 or (extendat is not None and (swdata.sweepcount + 1) % extendat == 0):
         if sysenv.nterms == 1 and not sysenv.is_coupling_model and not sysenv.has_penalty:
-            raise NotImplementedError("`dynamic_fullsweep!` on StateEnvs{ProjMPO} needs `krylov_extend!` (Global Subspace "
-                                      "Expansion), which is not built; use nsite=2 / nsite=1 sweeps")
+            from .gse import krylov_extend
+            krylov_extend(sysenv, **kwargs)
+            return fullsweep(sysenv, solver, 1, swdata, **kwargs)
         return fullsweep(sysenv, solver, 2, swdata, **kwargs)
     kwargs.pop("outputlevel", None)
     if (not sysenv.isortho()) or sysenv.orthocenter() != 1:

@@ -42,8 +42,8 @@ def totalerror(engine: TDVPEngine) -> float:
 def tdvpsweep(engine: TDVPEngine, time_step, nsite=2, solver=exp_solver, **kwargs):
     """`tdvpsweep!`: psi' = exp(time_step * H) psi by one second-order sweep (half a step left-to-right, half a
     step right-to-left, backward evolutions of the centre in between).  `nsite="dynamic"` mixes one- and two-site
-    updates bond by bond (`dynamic_fullsweep!`); on a single MPO it would start with the Global Subspace Expansion
-    (`krylov_extend!`), which is not built and raises."""
+    updates bond by bond (`dynamic_fullsweep!`); on a single MPO it starts with the Global Subspace Expansion
+    (`krylov_extend!`, gse.py)."""
     if solver is not exp_solver:
         raise RuntimeError("`tdvpsweep!()`: `solver` must be `exp_solver` !!")
     if nsite == "dynamic":

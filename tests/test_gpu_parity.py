@@ -641,8 +641,6 @@ def test_dynamic_tdvp_and_penalty_on_coupling_model(ctx):
         T.tdvpsweep(eng_d, -0.1, "dynamic", maxdim=6, cutoff=1e-12, extendat=5, outputlevel=0)
     assert eng_d.swdata.maxchi == eng_o.swdata.maxchi
     assert np.allclose(eng_d.swdata.energy, eng_o.swdata.energy, rtol=1e-10, atol=0)
-    with pytest.raises(NotImplementedError):          # single MPO: needs krylov_extend!
-        T.tdvpsweep(T.TDVPEngine(ctx, psi0.t, om.heisenberg_mpo(sites)), -0.1, "dynamic", maxdim=6, outputlevel=0)
     prm = dict(maxdim=[16, 32], nsweeps=[3, 3], cutoff=1e-14, noise=[1e-3, 0.0])
     E0o, p0o, _ = od.dmrg2(psi0, M, od.DMRGParams(**prm))
     E1o, _, _ = od.dmrg2(psi0, M, od.DMRGParams(**prm), Ms=[p0o], weight=10.0)
