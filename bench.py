@@ -613,7 +613,14 @@ def main():
     ap.add_argument("--no-decaying", dest="decaying", action="store_false",
                     help="skip the truncation timing on a decaying Schmidt spectrum")
     ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu)")
+    ap.add_argument("--workload", default="heisenberg_s1", choices=["heisenberg_s1", "j1j2_cylinder", "hubbard_tdvp", "ttn_tfi"],
+                    help="heisenberg_s1 = the headline line (BASELINE.json configs[1]); the others are configs[2..4] on one "
+                         "GPU (tools/bench_workloads.py), own arm only")
     args = ap.parse_args()
+    if args.workload != "heisenberg_s1" and args.impl == "ours":
+        from tools import bench_workloads
+        bench_workloads.run(args, ClockSampler, fp64_peak)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -122,6 +122,12 @@ int tnl_env_set_site_op(tnl_env_t env, int32_t site, int32_t nq, const tnl_index
  * become sums over the terms; every term keeps its own environments over the shared state. */
 int tnl_env_set_site_op_term(tnl_env_t env, int32_t term, int32_t site, int32_t nq, const tnl_index_t* inds4,
                              int64_t nblocks, const int32_t* coords, const int64_t* offsets, const double* data);
+/* updateH!(sysenv::StateEnvs{ProjMPO}, H; recalcEnv = false) (src/mps/state_envs.jl:181-208): replace W_site and keep
+ * every cached environment (time-dependent Hamiltonians, docs/src/mps/example_tdvp.md:134-136).  The MPO links must
+ * keep their spaces and the left watermark must be 0 (orthogonality centre at site 1), as the reference asserts.
+ * recalcEnv = true is a fresh environment over the same state tensors (tnl_env_create + tnl_env_set_state). */
+int tnl_env_update_site_op(tnl_env_t env, int32_t site, int32_t nq, const tnl_index_t* inds4, int64_t nblocks,
+                           const int32_t* coords, const int64_t* offsets, const double* data);
 /* StateEnvs(psi, H::CouplingModel) = ProjCouplingModel (src/mps/state_envs.jl:73-79, src/mps/projcouplingmodel.jl,
  * src/base/couplingmodel.jl:14-17): tensor of term `id` (the key of the IDTensors dictionary, any non-negative
  * integer) on `site`, handed over as W(wl, s', s, wr) where wl / wr are the OpLinks shared with the term's previous

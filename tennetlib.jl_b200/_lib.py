@@ -63,6 +63,7 @@ _SIGS = {
     "tnl_env_create": [_P, C.c_int32, C.POINTER(_P)],
     "tnl_env_destroy": [_P],
     "tnl_env_set_site_op": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int64, _P, _P, _P],
+    "tnl_env_update_site_op": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int64, _P, _P, _P],
     "tnl_env_set_site_op_term": [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int64, _P, _P, _P],
     "tnl_env_cm_set_term": [_P, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int64,
                             _P, _P, _P],

@@ -396,6 +396,13 @@ int tnl_env_set_site_op_term(tnl_env_t e, int32_t term, int32_t site, int32_t nq
     e->env.term(term).set_site_op(site, hb);
   });
 }
+int tnl_env_update_site_op(tnl_env_t e, int32_t site, int32_t nq, const tnl_index_t* inds4, int64_t nblocks,
+                           const int32_t* coords, const int64_t* offsets, const double* data) {
+  return guard(e->env.ctx, [&] {
+    HostBlocks hb = make_host(4, nq, inds4, nblocks, coords, offsets, data);
+    e->env.update_site_op(site, hb);
+  });
+}
 int tnl_env_cm_set_term(tnl_env_t e, int32_t site, int64_t id, int32_t has_wl, int32_t has_wr, int32_t nq,
                         const tnl_index_t* inds4, int64_t nblocks, const int32_t* coords, const int64_t* offsets,
                         const double* data) {

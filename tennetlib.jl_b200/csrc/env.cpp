@@ -152,6 +152,19 @@ void Env::set_site_op(int site, const HostBlocks& hb) {
   lpos = 0; rpos = N + 1; ap.reset(); Ledge.reset(); Redge.reset();
 }
 
+// updateH!(sysenv, H; recalcEnv = false) (src/mps/state_envs.jl:181-208): the site operator changes, the cached
+// right environments are reused as they are; the MPO links must span the same spaces and the left watermark must be 0
+void Env::update_site_op(int site, const HostBlocks& hb) {
+  TNL_CHECK(site >= 1 && site <= N && Wlr[site - 1], "updateH!: no operator on this site yet");
+  TNL_CHECK(lpos == 0, "updateH!(recalcEnv = false) needs lpos == 0");
+  TNL_CHECK(hb.rank == 4 && hb.inds[0].same_space(Wl[site - 1]) && hb.inds[3].same_space(Wr[site - 1]),
+            "updateH!(recalcEnv = false): the MPO links must keep their spaces");
+  const int lp = lpos, rp = rpos;
+  TensorP le = Ledge, re = Redge;
+  set_site_op(site, hb);
+  lpos = lp; rpos = rp; Ledge = le; Redge = re;
+}
+
 Env& Env::term(int k) {
   TNL_CHECK(!parent, "terms are addressed through the top environment");
   TNL_CHECK(k >= 0 && k < 64, "MPO term index out of range");
@@ -363,7 +376,7 @@ void Env::add_penalty(const std::vector<TensorP>& M, double w) {
 
 void Env::position_penalty(Penalty& p, int pos) {
   if (p.dead) return;
-  for (auto& a : A) TNL_CHECK(!a || !a->cplx, "excited-state penalties on complex states are not built");
+  // ComplexF64 states / penalised states: every contraction below is the planar complex GEMM (dag = arrows + conj)
   if (!p.Ledge) {
     const Index &a0 = A[0]->inds[0], &m0 = p.M[0]->inds[0], &aN = A[N - 1]->inds[2], &mN = p.M[N - 1]->inds[2];
     p.Ledge = mk(ctx, {with_dir(a0, -a0.dir), with_dir(m0, m0.dir)}, 1);
@@ -382,15 +395,15 @@ void Env::position_penalty(Penalty& p, int pos) {
     while (ll < kl) {
       TensorP Aq = as_nrow(ctx, A[ll], 1);
       TensorP Ms = as_nrow(ctx, p.M[ll], 2);
-      auto X = mk(ctx, {L->inds[1], Aq->inds[1], Aq->inds[2]}, 1);                 // (lM, s, r)
+      auto X = mk(ctx, {L->inds[1], Aq->inds[1], Aq->inds[2]}, 1, L->cplx || Aq->cplx);   // (lM, s, r)
       auto g1 = plan_gemm(*L, true, *Aq, false, *X);
-      run_gemm(ctx, *g1, L->d, Aq->d, X->d);
+      cgemm(ctx, *g1, *L, false, *Aq, false, *X);
       ctx->sync();
       TensorP X2 = relayout(ctx, *X, 2);
       const Index& rm = Ms->inds[2];
-      auto Ln = mk(ctx, {X->inds[2], with_dir(rm, -rm.dir)}, 1);                   // (r, rM)
+      auto Ln = mk(ctx, {X->inds[2], with_dir(rm, -rm.dir)}, 1, X2->cplx || Ms->cplx);    // (r, rM)
       auto g2 = plan_gemm(*X2, true, *Ms, false, *Ln, false, /*dagB=*/true);
-      run_gemm(ctx, *g2, X2->d, Ms->d, Ln->d);
+      cgemm(ctx, *g2, *X2, false, *Ms, true, *Ln);
       ctx->sync();
       p.LR[ll] = Ln;
       L = Ln;
@@ -407,15 +420,15 @@ void Env::position_penalty(Penalty& p, int pos) {
       const int j = rl - 2;
       TensorP As = as_nrow(ctx, A[j], 2);
       TensorP Mq = as_nrow(ctx, p.M[j], 1);
-      auto Y = mk(ctx, {As->inds[0], As->inds[1], R->inds[1]}, 2);                 // (l, s, rM)
+      auto Y = mk(ctx, {As->inds[0], As->inds[1], R->inds[1]}, 2, As->cplx || R->cplx);   // (l, s, rM)
       auto g1 = plan_gemm(*As, false, *R, false, *Y);
-      run_gemm(ctx, *g1, As->d, R->d, Y->d);
+      cgemm(ctx, *g1, *As, false, *R, false, *Y);
       ctx->sync();
       TensorP Y1 = relayout(ctx, *Y, 1);
       const Index& lm = Mq->inds[0];
-      auto Rn = mk(ctx, {Y->inds[0], with_dir(lm, -lm.dir)}, 1);                   // (l, lM)
+      auto Rn = mk(ctx, {Y->inds[0], with_dir(lm, -lm.dir)}, 1, Y1->cplx || Mq->cplx);    // (l, lM)
       auto g2 = plan_gemm(*Y1, false, *Mq, true, *Rn, false, /*dagB=*/true);
-      run_gemm(ctx, *g2, Y1->d, Mq->d, Rn->d);
+      cgemm(ctx, *g2, *Y1, false, *Mq, true, *Rn);
       ctx->sync();
       p.LR[j] = Rn;
       R = Rn;
@@ -436,24 +449,25 @@ void Env::build_penalty_vector(Penalty& p, const Tensor& proto) {
   TensorP cur;           // running tensor with indices (l, sites..., link_M) , bipartition before the last index
   const int first = p.lpos + 1;
   if (nsite == 0) {
-    auto m = mk(ctx, {with_dir(L->inds[0], -L->inds[0].dir), with_dir(R->inds[0], -R->inds[0].dir)}, 1);
+    auto m = mk(ctx, {with_dir(L->inds[0], -L->inds[0].dir), with_dir(R->inds[0], -R->inds[0].dir)}, 1, proto.cplx);
     auto g = plan_gemm(*L, false, *R, true, *m, true, true);
-    run_gemm(ctx, *g, L->d, R->d, m->d);
+    if (proto.cplx) cgemm(ctx, *g, L->d, L->cplx ? L->im() : nullptr, true, R->d, R->cplx ? R->im() : nullptr, true, m->d, m->im());
+    else run_gemm(ctx, *g, L->d, R->d, m->d);
     ctx->sync();
     p.m = m;
   } else {
     TensorP M1 = as_nrow(ctx, p.M[first - 1], 1);
-    auto P1 = mk(ctx, {with_dir(L->inds[0], -L->inds[0].dir), M1->inds[1], M1->inds[2]}, 1);   // (l, s1, mM)
+    auto P1 = mk(ctx, {with_dir(L->inds[0], -L->inds[0].dir), M1->inds[1], M1->inds[2]}, 1, L->cplx || M1->cplx);   // (l, s1, mM)
     auto g1 = plan_gemm(*L, false, *M1, false, *P1, /*dagA=*/true);
-    run_gemm(ctx, *g1, L->d, M1->d, P1->d);
+    cgemm(ctx, *g1, *L, true, *M1, false, *P1);
     ctx->sync();
     cur = P1;
     if (nsite == 2) {
       TensorP P1s = relayout(ctx, *P1, 2);
       TensorP M2 = as_nrow(ctx, p.M[first], 1);
-      auto P2 = mk(ctx, {P1->inds[0], P1->inds[1], M2->inds[1], M2->inds[2]}, 2);              // (l, s1, s2, rM)
+      auto P2 = mk(ctx, {P1->inds[0], P1->inds[1], M2->inds[1], M2->inds[2]}, 2, P1s->cplx || M2->cplx);   // (l, s1, s2, rM)
       auto g2 = plan_gemm(*P1s, false, *M2, false, *P2);
-      run_gemm(ctx, *g2, P1s->d, M2->d, P2->d);
+      cgemm(ctx, *g2, *P1s, false, *M2, false, *P2);
       ctx->sync();
       cur = P2;
     }
@@ -461,9 +475,14 @@ void Env::build_penalty_vector(Penalty& p, const Tensor& proto) {
     TensorP C3 = relayout(ctx, *cur, r - 1);
     std::vector<Index> mi(cur->inds.begin(), cur->inds.end() - 1);
     mi.push_back(with_dir(R->inds[0], -R->inds[0].dir));
-    auto m = mk(ctx, mi, r - 1);
+    // a real |m> under a complex Krylov vector is stored complex (zero imaginary plane): one layout for cdot / caxpy
+    auto m = mk(ctx, mi, r - 1, proto.cplx);
     auto g3 = plan_gemm(*C3, false, *R, true, *m, false, /*dagB=*/true);
-    run_gemm(ctx, *g3, C3->d, R->d, m->d);
+    if (proto.cplx) cgemm(ctx, *g3, C3->d, C3->cplx ? C3->im() : nullptr, false, R->d, R->cplx ? R->im() : nullptr, true, m->d, m->im());
+    else {
+      TNL_CHECK(!C3->cplx && !R->cplx, "complex penalised state under a real Krylov vector: promote the state first");
+      run_gemm(ctx, *g3, C3->d, R->d, m->d);
+    }
     ctx->sync();
     p.m = relayout(ctx, *m, 1);
   }
@@ -815,12 +834,16 @@ void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
     ctx->vec_release(tmp, 0);
   }
   // + weight * sum_M <m|v> |m>   (ProjMPO_MPS2.product)
-  TNL_CHECK(!proto.cplx || pens.empty(), "excited-state penalties on complex vectors are not built");
   for (auto& pen : pens) {
     if (pen.dead) continue;
     build_penalty_vector(pen, proto);
-    vec_dot(ctx, pen.m->d, vin, proto.nelem, 200);
-    vec_axpy_dev(ctx, vout, pen.m->d, proto.nelem, 200, weight);
+    if (proto.cplx) {
+      vec_cdot(ctx, pen.m->d, vin, proto.nelem, 200);           // <m|v> = sum conj(m) v
+      vec_caxpy_dev(ctx, vout, pen.m->d, proto.nelem, 200, weight);
+    } else {
+      vec_dot(ctx, pen.m->d, vin, proto.nelem, 200);
+      vec_axpy_dev(ctx, vout, pen.m->d, proto.nelem, 200, weight);
+    }
   }
   if (!parent) ctx->cnt.apply_count += 1;
 }
@@ -870,25 +893,26 @@ TensorP Env::noise_tensor(const Tensor& phi, bool left, bool own_storage) {
 // (ITensorMPS noiseterm(::ProjMPO); per id in src/mps/projcouplingmodel.jl:391-492).  The first operand of a bond
 // may live in workspace slot T2; further operands (MPO sums, CouplingModel ids) own their memory.
 TensorP Env::noise_operand(const Tensor& phi, bool left, const Tensor* E, const Tensor& W, bool own_storage) {
+  const bool cx = phi.cplx || (E && E->cplx);      // ComplexF64: planar complex GEMMs, the (real) W transform per plane
   auto mk_x = [&](std::vector<Index> inds, int nrow) {
-    return own_storage ? mk(ctx, std::move(inds), nrow) : mk_ws(ctx, std::move(inds), nrow, Ctx::SLOT_T2);
+    return own_storage ? mk(ctx, std::move(inds), nrow, cx) : mk_ws(ctx, std::move(inds), nrow, Ctx::SLOT_T2, cx);
   };
-  TNL_CHECK(!phi.cplx && !(E && E->cplx), "noise term on complex tensors is not built");
   ap.reset();                                     // reuse the apply workspaces (the plan dies with the bond anyway)
   ctx->slot_epoch++;
   if (left) {
     TensorP T1;
     if (E) {
-      T1 = mk_ws(ctx, {E->inds[0], E->inds[1], phi.inds[1], phi.inds[2], phi.inds[3]}, 2, Ctx::SLOT_T1);
+      T1 = mk_ws(ctx, {E->inds[0], E->inds[1], phi.inds[1], phi.inds[2], phi.inds[3]}, 2, Ctx::SLOT_T1, cx);
       auto g1 = plan_gemm(*E, false, phi, false, *T1);
-      run_gemm(ctx, *g1, E->d, phi.d, T1->d);
+      cgemm(ctx, *g1, *E, false, phi, false, *T1);
     } else {
       TNL_CHECK(is_trivial_link(W.inds[0]), "term without a left environment must start with a trivial link");
       T1 = view_with_trivial(ctx, phi, 1, 2, trivial_like(W.inds[0], -W.inds[0].dir), phi.d);
     }
     auto X = mk_x({T1->inds[0], W.inds[2], W.inds[3], phi.inds[2], phi.inds[3]}, 2);
     auto x = plan_transform(*T1, *X, {0, -1, -1, 3, 4}, &W, {1, 2});
-    run_transform(ctx, *x, T1->d, X->d, W.d);
+    TNL_CHECK(T1->cplx == X->cplx, "noise operand element type");
+    run_transform_c(ctx, *x, *T1, *X, W.d);
     ctx->sync();
     return X;
   }
@@ -897,9 +921,9 @@ TensorP Env::noise_operand(const Tensor& phi, bool left, const Tensor* E, const 
   Index rout;
   if (E) {
     TensorP R = relayout(ctx, *E, 2);                           // [(r' w) | r]
-    Xa = mk_ws(ctx, {phi.inds[0], phi.inds[1], phi.inds[2], R->inds[0], R->inds[1]}, 3, Ctx::SLOT_T1);
+    Xa = mk_ws(ctx, {phi.inds[0], phi.inds[1], phi.inds[2], R->inds[0], R->inds[1]}, 3, Ctx::SLOT_T1, cx);
     auto g1 = plan_gemm(*P3, false, *R, true, *Xa);
-    run_gemm(ctx, *g1, P3->d, R->d, Xa->d);
+    cgemm(ctx, *g1, *P3, false, *R, false, *Xa);
     ctx->sync();
     rout = R->inds[0];
   } else {
@@ -909,7 +933,8 @@ TensorP Env::noise_operand(const Tensor& phi, bool left, const Tensor* E, const 
   }
   auto X = mk_x({phi.inds[0], phi.inds[1], W.inds[2], W.inds[3], rout}, 3);       // W = (s, wr | wl, s')
   auto x = plan_transform(*Xa, *X, {0, 1, -1, -1, 3}, &W, {2, 4});
-  run_transform(ctx, *x, Xa->d, X->d, W.d);
+  TNL_CHECK(Xa->cplx == X->cplx, "noise operand element type");
+  run_transform_c(ctx, *x, *Xa, *X, W.d);
   ctx->sync();
   return X;
 }

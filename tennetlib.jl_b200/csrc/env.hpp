@@ -106,7 +106,8 @@ class Env {
       : ctx(c), N(n), lpos(0), rpos(n + 1), Wlr(n), Wrl(n), Wnr(n), Wl(n), Wr(n), A_store(par ? 0 : n),
         A(par ? par->A_store : A_store), LR(n), parent(par) {}
 
-  void set_site_op(int site, const HostBlocks& hb);     // W(wl, s', s, wr), 1-based site
+  void set_site_op(int site, const HostBlocks& hb);
+  void update_site_op(int site, const HostBlocks& hb);   // updateH!(...; recalcEnv = false)     // W(wl, s', s, wr), 1-based site
   void set_state(int site, TensorP a);
   void position(int pos);                               // makeL!(pos-1), makeR!(pos+nsite)
   TensorP make_phi(int pos);                            // two-site tensor (l,s1,s2,r) in Krylov layout (nrow 1)

@@ -146,7 +146,7 @@ struct FG {                     // one charge group of the factorisation
   Charge q;
   int64_t R = 0, C = 0;
   const double* M = nullptr; int64_t ldm = 0;     // data of T (nullptr: group opened by the noise term only)
-  struct NoiseOp { const double* X = nullptr; int64_t ldx = 0, XK = 0; };
+  struct NoiseOp { const double* X = nullptr; int64_t ldx = 0, XK = 0; int64_t xn = 0; /* plane distance (complex X) */ };
   std::vector<NoiseOp> Xs;                        // noise operands, one slot per MPO term (X == nullptr: none)
   // results
   double* U = nullptr; int64_t ldu = 0;           // left vectors  [R x k]
@@ -321,7 +321,7 @@ __global__ void deinterleave_kernel(double* __restrict__ re, double* __restrict_
 
 static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const FactorizeParams& prm) {
   const int split = T.nrow;
-  TNL_CHECK(prm.noise == 0.0 || prm.noiseX == nullptr, "noise term on complex tensors is not built");
+  const bool noisy = prm.noise != 0.0 && prm.noiseX != nullptr && prm.which != 3;
   // which == 3 (the untruncated gauge move of `qr` / `orthogonalize!`): the isometry spans range(M) -- the leading
   // min(R, C) eigenvectors of rho per charge group -- and the other factor is its projection; another gauge of the
   // same factorisation a Householder QR would give
@@ -333,6 +333,31 @@ static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const Factor
   for (const Group& g : T.groups) {
     FG f; f.q = g.q; f.R = g.R; f.C = g.C; f.M = T.d + g.base; f.ldm = g.ld;
     fg.push_back(f);
+  }
+  // noise operands (noiseterm, update_site.jl:59-62): rho += noise * sum_t X_t X_t^+ (ortho left) / X_t^+ X_t (right);
+  // a sector the operands open on the kept side only exists on the factor that carries the eigenvectors
+  std::vector<const Tensor*> nops;
+  if (noisy) {
+    nops.push_back(prm.noiseX);
+    for (const Tensor* x : prm.noiseXmore) nops.push_back(x);
+    for (size_t t = 0; t < nops.size(); t++) {
+      const Tensor& X = *nops[t];
+      for (const Group& g : X.groups) {
+        auto it = std::find_if(fg.begin(), fg.end(), [&](const FG& f) { return f.q == g.q; });
+        if (it == fg.end()) {
+          FG f; f.q = g.q;
+          if (left) { f.R = g.R; f.C = 0; } else { f.R = 0; f.C = g.C; }
+          fg.push_back(f);
+          it = fg.end() - 1;
+        }
+        if (left) TNL_CHECK(it->R == g.R, "noise operand rows do not match");
+        else TNL_CHECK(it->C == g.C, "noise operand cols do not match");
+        it->Xs.resize(nops.size());
+        it->Xs[t].X = X.d + g.base; it->Xs[t].ldx = g.ld; it->Xs[t].XK = left ? g.C : g.R;
+        it->Xs[t].xn = X.cplx ? X.nelem : 0;
+      }
+    }
+    std::sort(fg.begin(), fg.end(), [](const FG& a, const FG& b) { return a.q < b.q; });
   }
   std::vector<void*> temps;
   auto talloc = [&](int64_t n) {
@@ -354,6 +379,7 @@ static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const Factor
       if (n == 0) continue;
       Er[gi] = talloc(n * n);
       Ei[gi] = talloc(n * n);
+      if (!f.M) continue;                        // opened by the noise term only: rho starts at zero
       GemmProblem p{};
       p.M = p.N = (int)n; p.ldc = (int)n; p.K = (int)(left ? f.C : f.R);
       p.a = p.b = off(f.M); p.lda = p.ldb = (int)f.ldm;
@@ -381,6 +407,38 @@ static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const Factor
       run_gemm(ctx, *gi2, Mi, Mr, nullptr, -1.0, true);
     }
     ctx->sync();
+    // rho += noise * X X^+ : the same four products per operand, accumulated with alpha = noise.  The plane distance
+    // differs per operand tensor, hence one plan per (operand, group).
+    for (size_t t = 0; t < nops.size(); t++) {
+      for (size_t gi = 0; gi < fg.size(); gi++) {
+        FG& f = fg[gi];
+        const int64_t n = left ? f.R : f.C;
+        if (n == 0 || f.Xs.size() <= t || !f.Xs[t].X || f.Xs[t].XK == 0) continue;
+        GemmProblem p{};
+        p.M = p.N = (int)n; p.ldc = (int)n; p.K = (int)f.Xs[t].XK;
+        p.a = p.b = off(f.Xs[t].X); p.lda = p.ldb = (int)f.Xs[t].ldx;
+        p.c = off(Er[gi]);
+        auto gx = plan_gemm_raw(ctx, !left, left, {p});
+        GemmProblem q = p;
+        q.c = off(Ei[gi]);
+        auto gy = plan_gemm_raw(ctx, !left, left, {q});
+        const double* Xr = nullptr;
+        const double* Xi = Xr + f.Xs[t].xn;
+        const double a = prm.noise;
+        run_gemm(ctx, *gx, Xr, Xr, nullptr, a, true);
+        if (f.Xs[t].xn) {
+          run_gemm(ctx, *gx, Xi, Xi, nullptr, a, true);
+          if (left) {
+            run_gemm(ctx, *gy, Xi, Xr, nullptr, a, true);
+            run_gemm(ctx, *gy, Xr, Xi, nullptr, -a, true);
+          } else {
+            run_gemm(ctx, *gy, Xr, Xi, nullptr, a, true);
+            run_gemm(ctx, *gy, Xi, Xr, nullptr, -a, true);
+          }
+        }
+        ctx->sync();
+      }
+    }
   }
   // ---- Hermitian eigendecompositions
   std::vector<double> pool;
@@ -446,19 +504,25 @@ static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const Factor
   res.R = std::make_shared<Tensor>(ctx, ri, 1, true, true);
   const int64_t ln = res.L->nelem, rn = res.R->nelem;
   std::vector<GemmProblem> proj;
+  std::vector<size_t> proj_group;             // (unused bookkeeping of skipped groups keeps proj aligned with `kept`)
   for (size_t gi : kept) {
     FG& f = fg[gi];
     const int nk = (int)f.keep.size();
     const int gl = res.L->find_group(f.q), gr = res.R->find_group(f.q);
-    TNL_CHECK(gl >= 0 && gr >= 0, "new link sector missing on a factor");
-    const Group &GL = res.L->groups[gl], &GR = res.R->groups[gr];
-    TNL_CHECK(GL.R == f.R && GL.C == nk && GR.R == nk && GR.C == f.C, "factor group shape");
-    double* Ld = res.L->d + GL.base;
-    double* Rd = res.R->d + GR.base;
+    // a sector opened by the noise term alone exists only on the factor that carries the eigenvectors
+    TNL_CHECK(left ? gl >= 0 : gr >= 0, "new link sector missing on the isometric factor");
+    TNL_CHECK((gl >= 0 && gr >= 0) || !f.M, "new link sector missing on a factor");
+    static const Group kNoGroup{};
+    const Group &GL = gl >= 0 ? res.L->groups[gl] : kNoGroup, &GR = gr >= 0 ? res.R->groups[gr] : kNoGroup;
+    if (gl >= 0) TNL_CHECK(GL.R == f.R && GL.C == nk, "factor group shape");
+    if (gr >= 0) TNL_CHECK(GR.R == nk && GR.C == f.C, "factor group shape");
+    double* Ld = gl >= 0 ? res.L->d + GL.base : nullptr;
+    double* Rd = gr >= 0 ? res.R->d + GR.base : nullptr;
     if (left) {
       // L = V_k ; R = V_k^+ M
       gather_cols(ctx, Ld, GL.ld, Er[gi], f.R, f.R, f.keep, nullptr);
       gather_cols(ctx, Ld + ln, GL.ld, Ei[gi], f.R, f.R, f.keep, nullptr);
+      if (!f.M || gr < 0) { proj_group.push_back(gi); proj.push_back(GemmProblem{}); proj.back().M = 0; continue; }
       GemmProblem p{};
       p.M = nk; p.N = (int)f.C; p.K = (int)f.R;
       p.a = off(Ld); p.lda = (int)GL.ld; p.b = off(f.M); p.ldb = (int)f.ldm;
@@ -476,6 +540,7 @@ static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const Factor
       double* dneg = ctx->upload(neg);
       scale_rows_or_cols(ctx, Rd + rn, GR.ld, nk, f.C, dneg, true);      // conjugate
       ctx->free(dneg);
+      if (!f.M || gl < 0) { proj_group.push_back(gi); proj.push_back(GemmProblem{}); proj.back().M = 0; continue; }
       GemmProblem p{};
       p.M = (int)f.R; p.N = nk; p.K = (int)f.C;
       p.a = off(f.M); p.lda = (int)f.ldm; p.b = off(Vk); p.ldb = (int)ldk;
@@ -488,12 +553,18 @@ static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const Factor
   if (!proj.empty()) {
     if (left) {
       // R = conj(L)^T M : planes of L are ln apart, of M tn apart, of R rn apart
-      auto g = plan_gemm_raw(ctx, true, false, proj);
-      const double* z = nullptr;
-      cgemm(ctx, *g, z, z + ln, true, z, z + tn, false, (double*)z, (double*)z + rn);
+      std::vector<GemmProblem> live;
+      for (const GemmProblem& q : proj) if (q.M > 0) live.push_back(q);
+      if (!live.empty()) {
+        auto g = plan_gemm_raw(ctx, true, false, live);
+        const double* z = nullptr;
+        cgemm(ctx, *g, z, z + ln, true, z, z + tn, false, (double*)z, (double*)z + rn);
+        ctx->sync();
+      }
     } else {
       // L = M V_k : the plane distance of Vk differs per group -> one launch set per group
       for (size_t k = 0; k < proj.size(); k++) {
+        if (proj[k].M == 0) continue;
         auto g = plan_gemm_raw(ctx, false, false, {proj[k]});
         const double* z = nullptr;
         cgemm(ctx, *g, z, z + tn, false, z, z + fg[kept[k]].ldu, false, (double*)z, (double*)z + ln);

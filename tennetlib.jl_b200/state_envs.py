@@ -79,6 +79,32 @@ class StateEnvs:
         self.rlim = self.N + 1 if rlim is None else rlim
         self._nsite = 2
 
+    def updateH(self, H, Ms: Sequence | None = None, weight: float = -1.0, recalcEnv: bool = True):
+        """`updateH!` (src/mps/state_envs.jl:181-330).  recalcEnv = True: a fresh projected Hamiltonian over the same
+        (shared, not copied) device state -- all environments are rebuilt on demand.  recalcEnv = False (single MPO
+        only, as in the reference): only the site operators are replaced, every cached environment is kept."""
+        if recalcEnv:
+            new = StateEnvs(self.ctx, [self.site_tensor(j) for j in range(1, self.N + 1)], H, llim=self.llim,
+                            rlim=self.rlim, copy=False, Ms=Ms, weight=weight)
+            new.set_nsite(self._nsite)
+            self.h, new.h = new.h, self.h                      # the old tnl_env_t goes away with `new`
+            for k in ("nterms", "H_host", "is_coupling_model", "has_penalty"):
+                setattr(self, k, getattr(new, k))
+            return self
+        if self.nterms != 1 or self.is_coupling_model or self.has_penalty or Ms:
+            raise RuntimeError(f"`updateH!()` :: Not implemented for `recalcEnv={recalcEnv}` with this `StateEnvs` !!")
+        if len(H) != self.N:
+            raise ValueError("MPS and MPO lengths differ")
+        if (not self.isortho()) or self.orthocenter() != 1:
+            self.orthogonalize1()
+        for j, W in enumerate(H):
+            arr, nq, keep = _index_array(W.inds)
+            coords, offsets, data, nb = flatten_blocks(W)
+            check(self.ctx.lib.tnl_env_update_site_op(self.h, j + 1, nq, arr, nb, coords.ctypes.data, offsets.ctypes.data,
+                                                      data.ctypes.data), self.ctx.h)
+        self.H_host = H
+        return self
+
     def __del__(self):
         try:
             if self.h and self.ctx.h:

@@ -615,3 +615,64 @@ def optimize(psi0: TTN, H, params: OptimizeParamsTTN, sweeppath: Sequence[Node],
     sysenv = StateEnvsTTN(psi0, H, Ms, weight)
     sw = optimize_(sysenv, params, sweeppath, **kw)
     return sw.energy[-1], sysenv.psi, sw
+
+
+# ------------------------------------------------------------------------- generators (bench / test workloads)
+def dense_index(dim: int, dir: int = +1, tags: str = "") -> Index:
+    return Index([(0,)], [dim], dir=dir, tags=tags)
+
+
+def dense_siteinds(N: int, d: int = 2) -> List[Index]:
+    """Site indices without quantum numbers (one charge-0 sector of dimension d)."""
+    return [dense_index(d, +1, f"Site,n={j + 1}") for j in range(N)]
+
+
+def tfi_coupling_model(sites: Sequence[Index], h: float = 1.0, J: float = 1.0):
+    """H = -J sum_j Z_j Z_{j+1} - h sum_j X_j as a `CouplingModel` (BASELINE.json configs[4]): one id per bond with a
+    dim-1 OpLink between its two tensors, one id per field term (src/base/couplingmodel.jl:120-230 builds the same
+    structure from OpStrings)."""
+    from .couplingmodel import CouplingModel
+    from .tensor import HostTensor
+    Z = np.array([[1.0, 0.0], [0.0, -1.0]])
+    X = np.array([[0.0, 1.0], [1.0, 0.0]])
+    N = len(sites)
+    terms: List[Dict[int, object]] = [dict() for _ in range(N)]
+    tid = itertools.count(1)
+    for j in range(N - 1):
+        k = next(tid)
+        link = Index([(0,)], [1], dir=-1, tags="OpLink")
+        sa, sb = sites[j], sites[j + 1]
+        terms[j][k] = HostTensor([sa.prime().copy(dir=+1), sa.copy(dir=-1), link], {(0, 0, 0): (-J * Z)[:, :, None].copy()})
+        terms[j + 1][k] = HostTensor([link.copy(dir=+1), sb.prime().copy(dir=+1), sb.copy(dir=-1)], {(0, 0, 0): Z[None].copy()})
+    for j in range(N):
+        s = sites[j]
+        terms[j][next(tid)] = HostTensor([s.prime().copy(dir=+1), s.copy(dir=-1)], {(0, 0): (-h * X).copy()})
+    return CouplingModel(sites, terms)
+
+
+def random_ttn(ctx: Context, sites, graph: Graph, sitenodes: Dict[int, Node], chi: int, seed: int = 0) -> TTN:
+    """randomTTN without quantum numbers (ttn_generators.jl:171-246): link dimensions min(product of the other
+    dimensions, chi), random tensors on the device, isometrised towards the most central node and normalised."""
+    inds: Dict[Node, List[Index]] = {node: [] for node in graph.nodes}
+    for b, s in enumerate(sites):
+        inds[sitenodes[b + 1]].append(s)
+    center = find_eccentric_central_node(graph, list(sitenodes.values()))
+    for node in nodes_from_bfs(graph, center, reverse=True)[:-1]:
+        nxt = nextnode_in_path(graph, node, center)
+        dim = min(int(np.prod([float(ix.dim) for ix in inds[node]])), chi)
+        link = dense_index(dim, +1, f"Link,{node}")
+        inds[node].append(link.dag())
+        inds[nxt].append(link)
+    tensors = {}
+    for k, node in enumerate(sorted(graph.nodes)):
+        t = ITensor.random(ctx, inds[node], seed * 100003 + k + 1)
+        tensors[node] = t.scale_(1.0 / t.norm())
+    psi = TTN(sites, graph, tensors, None)
+    isometrize_full(psi, center, normalize=True, cutoff=0.0, maxdim=chi)
+    return psi
+
+
+def default_random_ttn(ctx: Context, sites, chi: int, seed: int = 0) -> TTN:
+    """default_randomTTN (ttn_generators.jl:248-281) for sites without quantum numbers."""
+    graph, sitenodes = default_graph_sitenodes(len(sites))
+    return random_ttn(ctx, sites, graph, sitenodes, chi, seed)

@@ -204,3 +204,64 @@ def test_two_charges_hubbard_dmrg_energy_matches_ed(ctx):
     assert sw.maxchi == sw_o.maxchi
     assert abs(sw.energy[-1] - sw_o.energy[-1]) < 1e-10 * abs(e_ed)
     assert env.linkdims() == [A.inds[2].dim for A in psi_f.t[:-1]]
+
+
+# ------------------------------------------------------------------------------------------- ComplexF64 completion
+def _complexify(mps, seed):
+    rng = np.random.default_rng(seed)
+    for j, A in enumerate(mps.t):
+        blocks = {c: b * (rng.standard_normal(b.shape) + 1j * rng.standard_normal(b.shape)) for c, b in A.blocks.items()}
+        mps.t[j] = type(A)(A.inds, blocks, np.complex128)
+    return mps
+
+
+@pytest.mark.parametrize("model", ["mpo", "cm"])
+def test_complex_dmrg_with_noise_gauge_moves_and_penalty_match_oracle(ctx, model):
+    """ComplexF64 `eig_solver`, noise term, QR gauge moves (`orthogonalize!`) and excited-state
+    penalties.  A complex random MPS (real Hamiltonian) goes through two-site DMRG with noise, then the first excited
+    state is found with the complex ground state penalised; energies against the oracle and ED."""
+    T, pm, ob, od, ok, om, op = _imports()
+    from oracle import couplingmodel as oc
+    N = 8
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites) if model == "mpo" else oc.heisenberg_coupling_model(sites, merge=True)
+    qn, dm = om.gaussian_link_sectors(16, 1.3, 4, step=1)
+    psi0 = _complexify(od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(31))), 32)
+    # gauge moves of a complex state keep the state
+    env = T.StateEnvs(ctx, psi0.t, H)
+    v0 = om.mps_to_dense(psi0.t)
+    env.orthogonalize(1)
+    env.orthogonalize(5)
+    v1 = om.mps_to_dense([to_oracle(A) for A in env.getpsi()])
+    assert abs(abs(np.vdot(v0, v1)) / np.linalg.norm(v0) / np.linalg.norm(v1) - 1.0) < 1e-12
+    for j in (1, 2, 3):                                    # left-orthonormal sites
+        A = env.getpsi()[j - 1].to_dense()
+        M = A.reshape(-1, A.shape[2])
+        assert np.abs(M.conj().T @ M - np.eye(M.shape[1])).max() < 1e-12
+    prm = dict(maxdim=[16, 32], nsweeps=[3, 3], cutoff=1e-14, noise=[1e-3, 0.0])
+    E0o, p0o, sw_o = od.dmrg2(psi0, H, od.DMRGParams(**prm))
+    E0d, env0, sw_d = T.dmrg2(ctx, psi0.t, H, T.DMRGParams(**prm), outputlevel=0)
+    assert sw_d.maxchi == sw_o.maxchi
+    assert np.allclose(sw_d.energy[:3], sw_o.energy[:3], rtol=1e-7, atol=0)        # noisy sweeps
+    assert abs(E0d - E0o) < 1e-10 * abs(E0o)
+    assert abs(E0d - (-3.3749325987)) < 1e-8                                      # ED, S=1/2 N=8
+    assert any(np.iscomplexobj(b) and np.abs(b.imag).max() > 1e-6 for A in env0.getpsi() for b in A.blocks.values())
+    E1o, _, _ = od.dmrg2(psi0, H, od.DMRGParams(**prm), Ms=[p0o], weight=10.0)
+    E1d, _, _ = T.dmrg2(ctx, psi0.t, H, T.DMRGParams(**prm), Ms=[env0.getpsi()], weight=10.0, outputlevel=0)
+    assert abs(E1d - E1o) < 1e-8 * abs(E1o)
+    assert abs(E1d - (-2.9822404877)) < 1e-6
+
+
+def test_complex_one_site_dmrg_with_noise_matches_oracle(ctx):
+    """one-site update with the noise branch (two-site tensor + replacebond!, update_site.jl:135-156) on a complex state"""
+    T, pm, ob, od, ok, om, op = _imports()
+    N = 8
+    sites = om.siteinds("S=1/2", N)
+    H = om.heisenberg_mpo(sites)
+    qn, dm = om.gaussian_link_sectors(16, 1.3, 4, step=1)
+    psi0 = _complexify(od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(41))), 42)
+    prm = dict(maxdim=[16], nsweeps=[4], cutoff=1e-14, noise=[1e-3], noisedecay=[10.0])
+    Eo, _, sw_o = od.dmrg1(psi0, H, od.DMRGParams(**prm))
+    Ed, _, sw_d = T.dmrg1(ctx, psi0.t, H, T.DMRGParams(**prm), outputlevel=0)
+    assert sw_d.maxchi == sw_o.maxchi
+    assert np.allclose(sw_d.energy, sw_o.energy, rtol=1e-7, atol=0)
