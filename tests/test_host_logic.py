@@ -229,9 +229,12 @@ def test_dynamic_fullsweep_picks_one_or_two_site_updates_like_the_reference(monk
     # on the way back the decisions use the eigs recorded on the way out (0.3 everywhere): only the saturated bond is 1-site
     assert right == [(5, 2, "right"), (4, 2, "right"), (4, 1, "right"), (2, 2, "right"), (1, 2, "right")]
     assert data.sweepcount == 2 and len(data.energy) == 2 and data.maxchi == [4, 8]
-    # first sweep on a single MPO needs the Global Subspace Expansion
-    with pytest.raises(NotImplementedError):
-        sw.dynamic_fullsweep(_FakeEnv(N, None, dims, kind="mpo"), T.exp_solver, sw.SweepData(), maxdim=8, outputlevel=0)
+    # first sweep on a single MPO starts with the Global Subspace Expansion (src/mps/sweep.jl:266-282)
+    from tennetlib.jl_b200 import gse
+    seen = []
+    monkeypatch.setattr(gse, "krylov_extend", lambda sysenv, **kw: seen.append(sorted(kw)))
+    sw.dynamic_fullsweep(_FakeEnv(N, None, dims, kind="mpo"), T.exp_solver, sw.SweepData(), maxdim=8, outputlevel=0)
+    assert len(seen) == 1
 
 
 def test_tdvpsweep_argument_checks():

@@ -14,11 +14,11 @@ ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control no
     > $out/${tag}_ncu_list.log 2>&1
 # --set full of the kernels of two H_eff applies (the first 9 matching launches belong to make_phi / position)
 ncu --profile-from-start off --set full --clock-control none --import-source on \
-    -k regex:"gemm_kernel_v3|transform_kernel_v2|relayout_kernel" --launch-skip 9 -c 10 -f -o $out/${tag}_apply \
+    -k regex:"gemm_kernel|transform_kernel|relayout_kernel" --launch-skip 9 -c 10 -f -o $out/${tag}_apply \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile-region > $out/${tag}_ncu_apply.log 2>&1
 # Krylov vector kernels
 ncu --profile-from-start off --set full --clock-control none --import-source on \
-    -k regex:"dot_kernel|axpy_kernel|lincomb_kernel|scale_kernel" --launch-skip 4 -c 8 -f -o $out/${tag}_vec \
+    -k regex:"dot_kernel|axpy_kernel|axpy_dot_kernel|lincomb_kernel|scale_kernel" --launch-skip 4 -c 8 -f -o $out/${tag}_vec \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile-region > $out/${tag}_ncu_vec.log 2>&1
 ls -la $out
 # then, here:  python tools/summarize_launches.py gpurun_out/${tag}_launches.csv ; python tools/ncu_summary.py gpurun_out/${tag}_apply.ncu-rep
