@@ -539,7 +539,7 @@ def run_ours(args):
         traffic, traffic_src = float(tj["dram_bytes_per_launch_mean"]), tj["source"]
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "tnl::gemm_kernel_v3<128,128,16,64,32> (FP64 DMMA grouped GEMM)",
+    roofline = {"bound": "tensor", "kernel": "tnl::gemm_tma_ws_kernel (FP64 DMMA grouped GEMM: TMA producer warpgroup + 8 DMMA warps, 128x128x16 tiles, 6 stages; 64x64 cp.async kernel for small sectors)",
                 "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": traffic,
                 "traffic_unit": "bytes per launch (DRAM read + write)", "traffic_source": traffic_src,
                 "peak_source": peak_src, "peak_burst": peak_burst, "launches": prof["launches"],

@@ -27,6 +27,21 @@ Ctx::Ctx(int dev) : device(dev) {
   CUDA_OK(cudaMemset(d_sync, 0, sizeof(unsigned int)));
   CUDA_OK(cudaMalloc(&d_partials, 4096 * sizeof(double)));
   CUDA_OK(cudaMalloc(&d_info, 16 * sizeof(int)));
+  if (const char* e = getenv("TNL_GEMM_TMA")) use_tma = atoi(e) != 0;
+}
+// Pinned staging memory for cudaMemcpyAsync sources that the host fills and forgets: a ring; when it wraps the
+// stream is drained once so that no pending copy still reads the bytes about to be overwritten.
+void* Ctx::stage_pinned(size_t bytes) {
+  bytes = (bytes + 127) & ~size_t(127);
+  if (!pin_ring) {
+    pin_cap = size_t(4) << 20;
+    CUDA_OK(cudaMallocHost((void**)&pin_ring, pin_cap));
+  }
+  TNL_CHECK(bytes <= pin_cap, "staging request larger than the pinned ring");
+  if (pin_off + bytes > pin_cap) { sync(); pin_off = 0; }
+  void* p = pin_ring + pin_off;
+  pin_off += bytes;
+  return p;
 }
 Ctx::~Ctx() {
   cudaStreamSynchronize(stream);
@@ -36,6 +51,7 @@ Ctx::~Ctx() {
   for (auto& v : vec_pool) cudaFreeAsync(v.first, stream);
   cudaStreamSynchronize(stream);
   cudaFree(d_scalars);
+  if (pin_ring) cudaFreeHost(pin_ring);
   cudaFreeHost(h_scalars);
   cudaFree(d_sync);
   cudaFree(d_partials);
@@ -46,8 +62,9 @@ Ctx::~Ctx() {
 // the context stream are reused by later allocations of any size without touching the OS.
 void* Ctx::alloc(size_t bytes) {
   void* p = nullptr;
-  if (bytes == 0) bytes = 16;
-  CUDA_OK(cudaMallocAsync(&p, bytes, stream));
+  // + 128 bytes: the chunked TMA view of a ragged GEMM operand may read up to 15 doubles past its last row
+  // (kernels.cu, gemm_tma_ws_kernel); the slack keeps that over-read inside the allocation
+  CUDA_OK(cudaMallocAsync(&p, bytes + 128, stream));
   return p;
 }
 void Ctx::free(void* p) {
@@ -60,7 +77,7 @@ double* Ctx::scratch(int slot, size_t nelem, bool zero) {
   if (bytes > s.cap) {
     if (s.p) cudaFreeAsync(s.p, stream);
     slot_epoch++;
-    s.cap = bytes + bytes / 4;                       // headroom: sector sizes drift from bond to bond
+    s.cap = bytes + bytes / 4 + 128;                 // headroom: sector sizes drift from bond to bond (+ TMA over-read slack)
     CUDA_OK(cudaMallocAsync(&s.p, s.cap, stream));
   }
   if (zero) CUDA_OK(cudaMemsetAsync(s.p, 0, bytes, stream));
@@ -76,7 +93,7 @@ double* Ctx::vec_acquire(size_t nelem) {
       cudaFreeAsync(vec_pool.back().first, stream);
       vec_pool.pop_back();
     }
-    cap = nelem + nelem / 4;
+    cap = nelem + nelem / 4 + 16;
     CUDA_OK(cudaMallocAsync(&p, cap * sizeof(double), stream));
   }
   CUDA_OK(cudaMemsetAsync(p, 0, nelem * sizeof(double), stream));
@@ -110,7 +127,7 @@ double* Ctx::arena_alloc(size_t nelem, bool* from_arena) {
 }
 
 GemmPlan::~GemmPlan() {
-  if (ctx) { ctx->free(d_probs); ctx->free(d_tiles_big); ctx->free(d_tiles_small); }
+  if (ctx) { ctx->free(d_probs); ctx->free(d_tiles_big); ctx->free(d_tiles_small); ctx->free(d_tiles_tma); ctx->free(d_maps); }
 }
 TransformPlan::~TransformPlan() {
   if (ctx) { ctx->free(d_blocks); ctx->free(d_flats); }
@@ -224,9 +241,22 @@ static void make_tiles(GemmPlan& plan) {
     const auto &x = plan.probs[a], &y = plan.probs[b];
     return (double)x.M * x.N * x.K > (double)y.M * y.N * y.K;
   });
+  const bool tma = plan.ctx->use_tma;
   for (int pi : order) {
     const auto& p = plan.probs[pi];
     bool big = p.M > 64 && p.N > 64;
+    if (big && tma) {
+      // Persistent TMA kernel: CTA b works on tiles b, b + #SMs, ... so the tiles in flight are ~#SMs consecutive
+      // list entries.  Super-columns of GN n-tiles, m fastest across them: a wave covers a ~12 x 12 block of the
+      // output and touches 12 + 12 operand panels instead of all of A (L2 re-reads across waves).
+      const int mt = (p.M + 127) / 128, nt = (p.N + 127) / 128, kt = (p.K + 15) / 16;
+      const int GN = 12;
+      for (int nb = 0; nb < nt; nb += GN)
+        for (int mi = 0; mi < mt; mi++)
+          for (int ni = nb; ni < std::min(nt, nb + GN); ni++)
+            plan.tiles_tma.push_back(TmaTile{p.c, mi * 128, ni * 128, p.M, p.N, kt, p.ldc, pi, 0});
+      continue;
+    }
     int bm = big ? 128 : 64, bn = big ? 128 : 64;
     auto& tl = big ? plan.tiles_big : plan.tiles_small;
     for (int n0 = 0; n0 < p.N; n0 += bn)
@@ -235,6 +265,9 @@ static void make_tiles(GemmPlan& plan) {
   plan.d_probs = plan.ctx->upload(plan.probs);
   plan.d_tiles_big = plan.ctx->upload(plan.tiles_big);
   plan.d_tiles_small = plan.ctx->upload(plan.tiles_small);
+  plan.d_tiles_tma = plan.ctx->upload(plan.tiles_tma);
+  if (!plan.tiles_tma.empty())
+    plan.d_maps = plan.ctx->alloc((size_t)GemmPlan::MAPSETS_MAX * 2 * plan.probs.size() * 128);
 }
 
 std::unique_ptr<GemmPlan> plan_gemm_raw(Ctx* ctx, bool transA, bool transB, const std::vector<GemmProblem>& probs) {

@@ -140,14 +140,25 @@ struct GemmProblem {          // C[M x N] = op(A)[M x K] * op(B)[K x N], column-
   int lda, ldb, ldc;
 };
 struct GemmTile { int prob; int m0; int n0; };
+// 128x128 output tile of the persistent TMA kernel: everything a CTA needs without a second (dependent) load
+struct TmaTile { int64_t c; int m0, n0, M, N, ktiles, ldc, prob, pad; };
 
 struct GemmPlan {
   bool transA = false, transB = false;
   std::vector<GemmProblem> probs;
   std::vector<GemmTile> tiles_big, tiles_small;
+  std::vector<TmaTile> tiles_tma;       // tiles of the sectors larger than 64 in both extents (TMA kernel)
   GemmProblem* d_probs = nullptr;
   GemmTile* d_tiles_big = nullptr;
   GemmTile* d_tiles_small = nullptr;
+  TmaTile* d_tiles_tma = nullptr;
+  // TMA descriptors (CUtensorMap, 128 bytes each; A and B of every problem).  A descriptor holds the absolute
+  // global address, and the operands of a plan change from launch to launch (Krylov vectors), so the plan keeps
+  // one descriptor set per distinct (A, B) base pair it has been launched with.
+  static constexpr int MAPSETS_MAX = 24;
+  struct MapSet { const double* A; const double* B; };
+  std::vector<MapSet> mapsets;
+  void* d_maps = nullptr;               // MAPSETS_MAX x 2*probs.size() descriptors
   std::vector<std::pair<int64_t, int64_t>> zero_fill;   // (offset, count) of C ranges with no contribution
   double flops = 0;
   Ctx* ctx = nullptr;
@@ -267,6 +278,10 @@ class Ctx {
   size_t arena_off = 0, arena_want = 0;
   void arena_reset();
   double* arena_alloc(size_t nelem, bool* from_arena);
+  // pinned staging ring for small host->device uploads that must not block the host (TMA descriptor sets)
+  unsigned char* pin_ring = nullptr; size_t pin_cap = 0, pin_off = 0;
+  void* stage_pinned(size_t bytes);
+  bool use_tma = true;              // grouped GEMM through the TMA kernel (TNL_GEMM_TMA=0 selects the cp.async kernel)
   void sync() { CUDA_OK(cudaStreamSynchronize(stream)); }
   template <class T> T* upload(const std::vector<T>& v) {
     if (v.empty()) return nullptr;

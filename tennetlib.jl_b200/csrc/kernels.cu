@@ -12,6 +12,8 @@
 //                       KrylovKit.eigsolve from src/base/solver.jl:36) with warp-shuffle reductions.
 #include "core.hpp"
 
+#include <cuda.h>
+
 #include <algorithm>
 
 namespace tnl {
@@ -279,25 +281,303 @@ static void launch_gemm_cfg(Ctx* ctx, bool ta, bool tb, const GemmProblem* probs
   else launch_gemm_one<BM, BN, BK, WM, WN, true, true, STAGES>(ctx, probs, tiles, ntiles, A, B, C, alpha, accum);
 }
 
+
+// =================================================================================================
+// grouped DGEMM, TMA-staged persistent warp-specialised kernel (128x128 tiles of every charge sector larger than 64x64)
+// =================================================================================================
+// One CTA per SM walks the tile list with stride gridDim.x.  Warpgroup 0 is the TMA producer: one elected thread issues
+// cp.async.bulk.tensor (UTMALDG) for the two operand tiles (128 x 16 doubles each) of a stage and the group gives its
+// registers away with setmaxnreg; warpgroups 1-2 are the eight DMMA warps (64 x 32 register tiles, 232 registers).
+// Stages are handed over with a full / empty mbarrier pair per stage, so there is no CTA-wide barrier in the k loop:
+// the DMMA warps wait only for data, never for each other, and the producer runs up to STAGES k-tiles ahead ACROSS
+// tile boundaries -- while the 64 accumulators of tile t are stored the first k-tiles of tile t+1 are already in
+// shared memory and its first fragments in registers, so the DMMA pipe does not drain between tiles.  Out-of-range
+// rows / columns / k are zero-filled by the TMA unit: no predication in the kernel.  Measured on B200
+// (profiles/r02e_gemm.txt): 36.3 TFLOP/s at 8192^3 (cuBLAS DGEMM: 35.5), 34.4 at the `L v` shape of the chi = 4096
+// apply, against 33.4 / 31.6 for the cp.async kernel above (which paid a prologue per tile and a barrier per k-tile).
+//
+// Shared-memory layouts written by the TMA (SWIZZLE_128B: 16-byte chunk index ^= 128-byte row index mod 8):
+//   k contiguous in global (KF): one box {16 k, 128 x}: row x = 128 bytes = the 16 k values
+//   x contiguous in global     : one 3-d box {16 x, 16 k, 8 chunks} of the operand seen as (x mod 16, k, x div 16):
+//                                chunk b holds x in [16b, 16b+16), row k = 128 bytes.  (The inner box extent is capped
+//                                at the 128-byte swizzle span, hence the chunked view.)  The last chunk of a ragged
+//                                extent reads up to 15 doubles past the row end -- values that only reach accumulator
+//                                rows / columns outside the matrix, which are never stored; Ctx::alloc pads every
+//                                allocation so that the over-read stays inside mapped memory.
+// The DMMA fragment of k-step s takes the k values  kbase(lc) ^ 2s,  kbase = (0, 3, 12, 15)[lc]  (the same
+// permutation for A and B, so the product is unchanged): with it the 8 x 4 fragment loads of a half-warp fall into
+// 16 distinct 8-byte bank pairs for BOTH layouts (checked exhaustively in tests/test_host_logic.py).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TNL_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TNL_DONE;\n"
+      "bra TNL_WAIT;\n"
+      "TNL_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+               "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(dst),
+               "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+struct alignas(128) TmaDesc { unsigned char b[128]; };   // CUtensorMap (opaque on the device side)
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+
+template <bool KFA, bool KFB, int STAGES>
+__global__ void __launch_bounds__(384, 1)
+gemm_tma_ws_kernel(const TmaTile* __restrict__ tiles, int ntiles, const TmaDesc* __restrict__ maps, double* __restrict__ Cbase,
+                   double alpha, int accum) {
+  constexpr int MI = 8, NI = 4;
+  constexpr int TILE_ELEMS = 128 * 16;
+  constexpr int STAGE_ELEMS = 2 * TILE_ELEMS;
+  constexpr uint32_t STAGE_BYTES = STAGE_ELEMS * 8;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base_u32 = (raw_u32 + 1023u) & ~1023u;
+  const double* smem = reinterpret_cast<const double*>(smem_raw + (base_u32 - raw_u32));
+  const uint32_t full0 = base_u32 + STAGES * STAGE_BYTES;
+  const uint32_t empty0 = full0 + 8 * STAGES;
+  const int tid = threadIdx.x;
+  const int G = gridDim.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid < 128) {
+    // ---------------------------------------------------------------- producer warpgroup
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    if (tid == 0) {
+      int stage = 0;
+      uint32_t phase = 1;                          // a fresh mbarrier passes a wait on parity 1
+      for (int ti = blockIdx.x; ti < ntiles; ti += G) {
+        const int m0 = tiles[ti].m0, n0 = tiles[ti].n0, ktiles = tiles[ti].ktiles;
+        const TmaDesc* ma = maps + 2 * tiles[ti].prob;
+        for (int kt = 0; kt < ktiles; kt++) {
+          mbar_wait(empty0 + 8 * stage, phase);
+          const uint32_t bar = full0 + 8 * stage;
+          const uint32_t dA = base_u32 + stage * STAGE_BYTES, dB = dA + TILE_ELEMS * 8;
+          mbar_arrive_expect_tx(bar, STAGE_BYTES);
+          if (KFA) tma_load_2d(dA, ma, bar, kt * 16, m0);
+          else tma_load_3d(dA, ma, bar, 0, kt * 16, m0 >> 4);
+          if (KFB) tma_load_2d(dB, ma + 1, bar, kt * 16, n0);
+          else tma_load_3d(dB, ma + 1, bar, 0, kt * 16, n0 >> 4);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+  // ------------------------------------------------------------------ DMMA warpgroups
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+  const int lane = tid & 31, warp = (tid >> 5) - 4;
+  const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int kb = (lc & 1) * 3 + (lc >> 1) * 12;
+  int ea[4], eb[4];
+  const int da = KFA ? 0 : ((lc >> 1) ? -8 : 8);
+  const int db = KFB ? 0 : ((lc >> 1) ? -8 : 8);
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const int k = kb ^ (2 * s);
+    if (KFA) ea[s] = (wm0 + lr) * 16 + ((((k >> 1) ^ lr)) << 1) + (k & 1);
+    else     ea[s] = (wm0 >> 4) * 256 + k * 16 + 2 * ((lr >> 1) ^ (k & 3)) + (lr & 1) + 8 * ((k >> 2) & 1);
+    if (KFB) eb[s] = (wn0 + lr) * 16 + ((((k >> 1) ^ lr)) << 1) + (k & 1);
+    else     eb[s] = (wn0 >> 4) * 256 + k * 16 + 2 * ((lr >> 1) ^ (k & 3)) + (lr & 1) + 8 * ((k >> 2) & 1);
+  }
+#define TNL_FRAG_A(st, s, i) ((st)[ea[s] + (KFA ? (i) * 128 : ((i) >> 1) * 256 + ((i) & 1) * ((s) < 2 ? da : -da))])
+#define TNL_FRAG_B(st, s, j) ((st)[TILE_ELEMS + eb[s] + (KFB ? (j) * 128 : ((j) >> 1) * 256 + ((j) & 1) * ((s) < 2 ? db : -db))])
+
+  double acc[MI][NI][2];
+  double a[2][MI], b[2][NI];
+  int c_stage = 0;
+  uint32_t c_phase = 0;
+  mbar_wait(full0, 0);
+#pragma unroll
+  for (int i = 0; i < MI; i++) a[0][i] = TNL_FRAG_A(smem, 0, i);
+#pragma unroll
+  for (int j = 0; j < NI; j++) b[0][j] = TNL_FRAG_B(smem, 0, j);
+
+  TmaTile cur = tiles[blockIdx.x];
+  for (int ti = blockIdx.x; ti < ntiles; ti += G) {
+    const int tn = ti + G;
+    TmaTile nxt = cur;
+    if (tn < ntiles) nxt = tiles[tn];
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+      for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kt = 0; kt < cur.ktiles; kt++) {
+      const double* st = smem + c_stage * STAGE_ELEMS;
+      const int n_stage = (c_stage + 1 == STAGES) ? 0 : c_stage + 1;
+      const uint32_t n_phase = (c_stage + 1 == STAGES) ? (c_phase ^ 1u) : c_phase;
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        const int cb = s & 1, nb = cb ^ 1;
+        if (s < 3) {
+#pragma unroll
+          for (int i = 0; i < MI; i++) a[nb][i] = TNL_FRAG_A(st, s + 1, i);
+#pragma unroll
+          for (int j = 0; j < NI; j++) b[nb][j] = TNL_FRAG_B(st, s + 1, j);
+        } else if ((kt + 1 < cur.ktiles) || (tn < ntiles)) {
+          // first fragments of the next k-tile of this CTA's sequence (possibly of the next output tile)
+          mbar_wait(full0 + 8 * n_stage, n_phase);
+          const double* ns = smem + n_stage * STAGE_ELEMS;
+#pragma unroll
+          for (int i = 0; i < MI; i++) a[nb][i] = TNL_FRAG_A(ns, 0, i);
+#pragma unroll
+          for (int j = 0; j < NI; j++) b[nb][j] = TNL_FRAG_B(ns, 0, j);
+        }
+#pragma unroll
+        for (int i = 0; i < MI; i++)
+#pragma unroll
+          for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], a[cb][i], b[cb][j]);
+      }
+      // every fragment of this stage has been consumed by an issued DMMA: hand the stage back to the producer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * c_stage);
+      c_stage = n_stage;
+      c_phase = n_phase;
+    }
+    double* pC = Cbase + cur.c;
+#pragma unroll
+    for (int i = 0; i < MI; i++) {
+      const int m = cur.m0 + wm0 + i * 8 + lr;
+      if (m >= cur.M) continue;
+#pragma unroll
+      for (int j = 0; j < NI; j++) {
+        const int n = cur.n0 + wn0 + j * 8 + 2 * lc;
+        double* c = pC + (int64_t)n * cur.ldc + m;
+        if (n < cur.N) c[0] = accum ? fma(alpha, acc[i][j][0], c[0]) : alpha * acc[i][j][0];
+        if (n + 1 < cur.N) c[cur.ldc] = accum ? fma(alpha, acc[i][j][1], c[cur.ldc]) : alpha * acc[i][j][1];
+      }
+    }
+    cur = nxt;
+  }
+#undef TNL_FRAG_A
+#undef TNL_FRAG_B
+}
+
+// ---- host side: descriptor sets ----------------------------------------------------------------
+typedef CUresult (*TnlEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TnlEncodeTiledFn tma_encoder() {
+  static TnlEncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    TNL_CHECK(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+    return (TnlEncodeTiledFn)p;
+  }();
+  return fn;
+}
+// operand of extent X (rows of op(.)) x K stored with leading dimension ld; kfast: element (x, k) at x*ld + k
+static void encode_operand(CUtensorMap* m, const double* base, int X, int K, int ld, bool kfast) {
+  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)X, 1};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * sizeof(double), 0};
+  cuuint32_t box[3] = {16u, 128u, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  if (!kfast) {                                    // (x mod 16, k, x div 16)
+    gdim[0] = 16; gdim[1] = (cuuint64_t)K; gdim[2] = (cuuint64_t)(X + 15) / 16;
+    gstr[1] = 16 * sizeof(double);
+    box[1] = 16u; box[2] = 8u;
+  }
+  TNL_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld & 1) == 0, "GEMM operand is not 16-byte aligned");
+  CUresult r = tma_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, kfast ? 2 : 3, const_cast<double*>(base), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TNL_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+}
+static const TmaDesc* tma_maps_for(Ctx* ctx, GemmPlan& p, const double* A, const double* B) {
+  const size_t per_set = 2 * p.probs.size();
+  for (size_t i = 0; i < p.mapsets.size(); i++)
+    if (p.mapsets[i].A == A && p.mapsets[i].B == B) return (const TmaDesc*)p.d_maps + i * per_set;
+  if ((int)p.mapsets.size() == GemmPlan::MAPSETS_MAX) p.mapsets.clear();   // stream order keeps in-flight launches safe
+  const size_t slot = p.mapsets.size();
+  static_assert(sizeof(CUtensorMap) == 128 && sizeof(TmaDesc) == 128, "descriptor size");
+  CUtensorMap* h = (CUtensorMap*)ctx->stage_pinned(per_set * sizeof(CUtensorMap));
+  for (size_t i = 0; i < p.probs.size(); i++) {
+    const GemmProblem& g = p.probs[i];
+    encode_operand(&h[2 * i], A + g.a, g.M, g.K, g.lda, p.transA);
+    encode_operand(&h[2 * i + 1], B + g.b, g.N, g.K, g.ldb, !p.transB);
+  }
+  TmaDesc* d = (TmaDesc*)p.d_maps + slot * per_set;
+  CUDA_OK(cudaMemcpyAsync(d, h, per_set * sizeof(CUtensorMap), cudaMemcpyHostToDevice, ctx->stream));
+  p.mapsets.push_back(GemmPlan::MapSet{A, B});
+  return d;
+}
+
+template <bool KFA, bool KFB>
+static void launch_gemm_tma_one(Ctx* ctx, GemmPlan& p, const TmaDesc* maps, double* C, double alpha, int accum) {
+  constexpr int STAGES = 6;
+  constexpr size_t SMEM = (size_t)STAGES * 2 * 128 * 16 * sizeof(double) + 2 * STAGES * 8 + 1024;
+  auto kern = gemm_tma_ws_kernel<KFA, KFB, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    configured = true;
+  }
+  const int ntiles = (int)p.tiles_tma.size();
+  const int grid = std::min(ntiles, ctx->num_sms);
+  kern<<<grid, 384, SMEM, ctx->stream>>>(p.d_tiles_tma, ntiles, maps, C, alpha, accum);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+  ctx->cnt.gemm_launches++;
+}
+static void launch_gemm_tma(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C, double alpha, int accum) {
+  if (p.tiles_tma.empty()) return;
+  const TmaDesc* maps = tma_maps_for(ctx, p, A, B);
+  const bool kfa = p.transA, kfb = !p.transB;
+  if (kfa && kfb) launch_gemm_tma_one<true, true>(ctx, p, maps, C, alpha, accum);
+  else if (kfa && !kfb) launch_gemm_tma_one<true, false>(ctx, p, maps, C, alpha, accum);
+  else if (!kfa && kfb) launch_gemm_tma_one<false, true>(ctx, p, maps, C, alpha, accum);
+  else launch_gemm_tma_one<false, false>(ctx, p, maps, C, alpha, accum);
+}
+
 void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C, double alpha, bool accum) {
   if (!accum)
     for (auto& z : p.zero_fill) CUDA_OK(cudaMemsetAsync(C + z.first, 0, z.second * sizeof(double), ctx->stream));
   Ctx::ProfRec rec{};
-  const bool prof = ctx->prof_gemm && !p.tiles_big.empty();
+  const bool prof = ctx->prof_gemm && !(p.tiles_big.empty() && p.tiles_tma.empty());
   if (prof) {
     CUDA_OK(cudaEventCreate(&rec.a));
     CUDA_OK(cudaEventCreate(&rec.b));
     CUDA_OK(cudaEventRecord(rec.a, ctx->stream));
   }
-  // 128x128x16 tiles, 8 warps x (64x32), 4 cp.async stages for sectors larger than 64 in both extents;
-  // 64x64x16 tiles, 4 warps x (32x32) for the small ones
+  // sectors larger than 64 in both extents: persistent TMA kernel (or, with TNL_GEMM_TMA=0, 128x128x16 tiles fed by
+  // 4 cp.async stages); 64x64x16 tiles, 4 warps x (32x32), for the small ones
+  launch_gemm_tma(ctx, p, A, B, C, alpha, accum ? 1 : 0);
   launch_gemm_cfg<128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, (int)p.tiles_big.size(), A, B, C, alpha, accum ? 1 : 0);
   launch_gemm_cfg<64, 64, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_small, (int)p.tiles_small.size(), A, B, C, alpha, accum ? 1 : 0);
   if (prof) {
     CUDA_OK(cudaEventRecord(rec.b, ctx->stream));
     rec.flops = p.flops;
     rec.cat = 0;
-    rec.tiles = (int)(p.tiles_big.size() + p.tiles_small.size());
+    rec.tiles = (int)(p.tiles_big.size() + p.tiles_small.size() + p.tiles_tma.size());
     ctx->prof_recs.push_back(rec);
   }
   ctx->cnt.gemm_flops += p.flops;

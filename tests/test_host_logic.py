@@ -73,6 +73,55 @@ def test_sass_contains_fp64_tensor_ops_and_async_copies():
     assert "DMMA" in out and "LDGSTS" in out
 
 
+def test_sass_contains_tma_loads():
+    """The 128x128 tiles of the grouped GEMM are staged by the TMA unit (UTMALDG) with mbarrier completion."""
+    out = subprocess.run(["cuobjdump", "-sass", T.so_path()], capture_output=True, text=True).stdout
+    assert "UTMALDG.2D" in out and "SYNCS.ARRIVE.TRANS64" in out
+
+
+def test_tma_swizzled_fragment_loads_are_bank_conflict_free():
+    """csrc/kernels.cu gemm_tma_ws_kernel: with the k permutation  k = (0,3,12,15)[lc] ^ 2s  the 8x4 DMMA fragment
+    loads of every half-warp hit 16 distinct 8-byte bank pairs in both SWIZZLE_128B tile layouts, and the four
+    k-steps cover k = 0..15 exactly once."""
+    ksets = [[((lc & 1) * 3 + (lc >> 1) * 12) ^ (2 * s) for lc in range(4)] for s in range(4)]
+    assert sorted(k for ks in ksets for k in ks) == list(range(16))
+
+    def pair_kfast(x, k):      # one box {16 k, 128 x}: row x = 128 bytes
+        return ((x * 128 + (((k >> 1) ^ (x & 7)) << 4) + (k & 1) * 8) // 8) % 16
+
+    def pair_xfast(x, k):      # boxes {16 x, 16 k}: box x>>4, row k = 128 bytes
+        xx = x & 15
+        return (((x >> 4) * 2048 + k * 128 + (((xx >> 1) ^ (k & 7)) << 4) + (xx & 1) * 8) // 8) % 16
+
+    for f in (pair_kfast, pair_xfast):
+        for ks in ksets:
+            for w0 in range(0, 128, 8):
+                for half in (0, 1):
+                    hit = {f(w0 + lr, ks[lc]) for lr in range(4 * half, 4 * half + 4) for lc in range(4)}
+                    assert len(hit) == 16
+
+    # the kernel's closed-form fragment offsets equal the layout functions above
+    def off_kfast(x, k):
+        return x * 16 + (((k >> 1) ^ (x & 7)) << 1) + (k & 1)
+
+    def off_xfast(x, k):
+        xx = x & 15
+        return (x >> 4) * 256 + k * 16 + (((xx >> 1) ^ (k & 7)) << 1) + (xx & 1)
+
+    for w0 in (0, 32, 64, 96):
+        for lr in range(8):
+            for lc in range(4):
+                kb = (lc & 1) * 3 + (lc >> 1) * 12
+                d = -8 if (lc >> 1) else 8
+                for s in range(4):
+                    k = kb ^ (2 * s)
+                    e_kf = (w0 + lr) * 16 + (((k >> 1) ^ lr) << 1) + (k & 1)
+                    e_xf = (w0 >> 4) * 256 + k * 16 + 2 * ((lr >> 1) ^ (k & 3)) + (lr & 1) + 8 * ((k >> 2) & 1)
+                    for i in range(4):
+                        assert e_kf + i * 128 == off_kfast(w0 + 8 * i + lr, k)
+                        assert e_xf + (i >> 1) * 256 + (i & 1) * (d if s < 2 else -d) == off_xfast(w0 + 8 * i + lr, k)
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():

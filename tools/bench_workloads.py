@@ -152,7 +152,7 @@ def run(args, ClockSampler, fp64_peak):
     extra = {"energies": energies[-2:], "setup_s": setup_s,
              "timed_bond_sectors": {"bond": bond - args.steps, "nsect": li.nsect, "dim": li.dim, "largest": max(li.dims)},
              "device_ms_per_step_by_kernel_class": {k: v / args.steps for k, v in cat.items()},
-             "roofline": {"bound": "tensor", "kernel": "tnl::gemm_kernel (FP64 DMMA grouped GEMM)", "achieved": gemm_tf,
+             "roofline": {"bound": "tensor", "kernel": "tnl::gemm_tma_ws_kernel (FP64 DMMA grouped GEMM)", "achieved": gemm_tf,
                           "peak": peak, "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": None, "peak_source": peak_src,
                           "launches": prof["launches"]},
              "roofline_krylov_vectors": {"bound": "hbm", "kernel": "Krylov vector kernels (dot / axpy / MGS / lincomb)",
@@ -220,7 +220,7 @@ def run_ttn(args, ctx, T, ClockSampler, fp64_peak):
             "energies": energies[-2:], "solver_ms_per_step": solver_ms / args.steps,
             "apply_gflop": fl / max(1, nops) / 1e9, "applies_per_step": nops / args.steps, "setup_s": setup_s,
             "device_ms_per_step_by_kernel_class": {k2: v / args.steps for k2, v in pr["category_ms"].items()},
-            "roofline": {"bound": "tensor", "kernel": "tnl::gemm_kernel (FP64 DMMA grouped GEMM)", "achieved": gemm_tf,
+            "roofline": {"bound": "tensor", "kernel": "tnl::gemm_tma_ws_kernel (FP64 DMMA grouped GEMM)", "achieved": gemm_tf,
                          "peak": peak, "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": None, "peak_source": peak_src,
                          "launches": pr["launches"]},
             "gpu_launches": int(cnt["launches"]), "clocks": clocks}

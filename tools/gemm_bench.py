@@ -6,7 +6,8 @@ import tennetlib.jl_b200 as T
 ctx = T.Context()
 print("== correctness (odd sizes, all transposes)")
 worst = 0.0
-for (M, N, K) in ((1, 1, 1), (7, 5, 3), (129, 65, 17), (255, 257, 33), (385, 1254, 935), (130, 300, 1000)):
+for (M, N, K) in ((1, 1, 1), (7, 5, 3), (129, 65, 17), (255, 257, 33), (385, 1254, 935), (130, 300, 1000), (128, 128, 16),
+                  (129, 200, 64), (300, 257, 100), (1000, 1000, 1001), (66, 4000, 15), (2000, 70, 333)):
     for ta in (0, 1):
         for tb in (0, 1):
             ms, err = ctx.gemm_selftest(M, N, K, ta, tb, 1, True)

@@ -14,7 +14,7 @@ ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control no
     > $out/${tag}_ncu_list.log 2>&1
 # --set full of the kernels of two H_eff applies (the first 9 matching launches belong to make_phi / position)
 ncu --profile-from-start off --set full --clock-control none --import-source on \
-    -k regex:"gemm_kernel|transform_kernel|relayout_kernel" --launch-skip 9 -c 10 -f -o $out/${tag}_apply \
+    -k regex:"gemm_tma_ws_kernel|gemm_kernel|transform_kernel|relayout_kernel" --launch-skip 9 -c 10 -f -o $out/${tag}_apply \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile-region > $out/${tag}_ncu_apply.log 2>&1
 # Krylov vector kernels
 ncu --profile-from-start off --set full --clock-control none --import-source on \

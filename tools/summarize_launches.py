@@ -30,7 +30,7 @@ def main():
     for k in sorted(t, key=t.get, reverse=True)[:top]:
         print(f"| {t[k]:.3f} | {100 * t[k] / total:.1f}% | {n[k]} | `{k}` |")
     ours = sum(v for k, v in t.items() if "tnl::" in k)
-    gemm = sum(v for k, v in t.items() if "tnl::gemm_kernel" in k)
+    gemm = sum(v for k, v in t.items() if "tnl::gemm_" in k)
     print(f"\nkernels of this library (tnl::*): {ours:.1f} ms = {100 * ours / total:.1f}% ; grouped DGEMM: {gemm:.1f} ms = "
           f"{100 * gemm / total:.1f}%")
 
