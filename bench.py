@@ -348,6 +348,7 @@ def run_ours(args):
     sysenv.phase_ms = {}
     sysenv.phase_log = []
     sysenv.phase_kernel_ms = {}
+    sysenv.collective_detail = {}
     ctx.profile_gemm(True)
     ctx.profile_read()
     apply_flops_total, numops_total = 0.0, 0
@@ -581,6 +582,8 @@ def run_ours(args):
             "device_ms_per_step_by_phase_and_kernel_class": {ph: {k: v / args.steps for k, v in d.items()}
                                                              for ph, d in sysenv.phase_kernel_ms.items()},
             "device_ms_per_step_by_rank": per_rank,
+            "collectives_rank0_per_step": {ph: {k: {"ms": v[0] / args.steps, "calls": v[1] / args.steps} for k, v in d.items()}
+                                           for ph, d in sysenv.collective_detail.items() if d},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": tf_e2e, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "call": e2e_path, "result_norm": e2e_norm},

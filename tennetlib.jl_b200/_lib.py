@@ -41,6 +41,7 @@ _SIGS = {
     "tnl_profile_gemm": [_P, C.c_int32],
     "tnl_profile_read": [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "tnl_profile_categories": [_P, C.POINTER(C.c_double)],
+    "tnl_profile_collectives": [_P, C.POINTER(C.c_double)],
     "tnl_tensor_import": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int64, _P, _P, _P, C.c_int32, C.POINTER(_P)],
     "tnl_tensor_import_c128": [_P, C.c_int32, C.c_int32, C.POINTER(tnl_index_t), C.c_int64, _P, _P, _P, C.c_int32,
                                C.POINTER(_P)],

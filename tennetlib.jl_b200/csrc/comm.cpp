@@ -85,6 +85,7 @@ void comm_destroy(Ctx* ctx) {
 
 void comm_allreduce_sum(Ctx* ctx, double* buf, int64_t n) {
   Ctx::Scope prof_scope(ctx, 3);
+  prof_scope.r.tiles = n <= 64 ? 0 : 3;            // kind (tnl_profile_collectives)
   TNL_CHECK(ctx->nccl_comm, "communicator not initialised");
   NCCL_OK(nccl().AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
   ctx->cnt.allreduce_bytes += 8.0 * n;
@@ -93,6 +94,7 @@ void comm_allreduce_sum(Ctx* ctx, double* buf, int64_t n) {
 // recv[0..n) = sum over ranks of send[rank*n .. rank*n+n)
 void comm_reduce_scatter_sum(Ctx* ctx, const double* send, double* recv, int64_t n) {
   Ctx::Scope prof_scope(ctx, 3);
+  prof_scope.r.tiles = 1;
   TNL_CHECK(ctx->nccl_comm, "communicator not initialised");
   NCCL_OK(nccl().ReduceScatter(send, recv, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
   ctx->cnt.allreduce_bytes += 8.0 * n * ctx->world;
@@ -100,6 +102,7 @@ void comm_reduce_scatter_sum(Ctx* ctx, const double* send, double* recv, int64_t
 // recv[k*n .. k*n+n) = send of rank k
 void comm_allgather(Ctx* ctx, const double* send, double* recv, int64_t n) {
   Ctx::Scope prof_scope(ctx, 3);
+  prof_scope.r.tiles = 2;
   TNL_CHECK(ctx->nccl_comm, "communicator not initialised");
   NCCL_OK(nccl().AllGather(send, recv, (size_t)n, ncclFloat64, (ncclComm_t)ctx->nccl_comm, ctx->stream));
   ctx->cnt.allreduce_bytes += 8.0 * n * ctx->world;

@@ -752,12 +752,15 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
   }
 
   // Multi-GPU: the per-charge-group decompositions are independent -- distribute them
-  // over the ranks (longest-processing-time first on n^3), exchange the spectrum, and sum the two factors.
+  // over the ranks (longest-processing-time first on the measured cost of a decomposition), exchange the spectrum, and sum the two factors.
   const int W = ctx->shard_world();
   if (W > 1) {
     std::vector<size_t> ord(fg.size());
     std::iota(ord.begin(), ord.end(), 0);
-    auto cost = [&](const FG& f) { double n = (double)std::max(f.R, f.C); return n * n * n; };
+    // cost model of one decomposition = cusolverDnDsyevd measured on B200 (profiles/r02c_eigh_bench.json):
+    // t[ms] ~ 0.0109 n + 6.4e-10 n^3 -- the tridiagonalisation is latency bound (about 11 us per column), so the
+    // linear term dominates below n ~ 4000 and an n^3 model would overload the rank that gets the mid-sized groups
+    auto cost = [&](const FG& f) { double n = (double)(which == 1 ? std::max(f.R, f.C) : (left ? f.R : f.C)); return 0.0109 * n + 6.4e-10 * n * n * n; };
     std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cost(fg[a]) > cost(fg[b]); });
     std::vector<double> load(W, 0.0);
     for (size_t i : ord) {

@@ -25,6 +25,7 @@ class StateEnvs:
         self.phase_log = []            # (phase, ms) in call order: shows one-off hiccups that an average hides
         self.profile_kernels = False   # additionally split the device time of each phase by kernel class
         self.phase_kernel_ms = {}
+        self.collective_detail = {}     # phase -> kind -> [device ms, calls] (multi-GPU, when profile_kernels)
         self.gemm_prof = dict(total_ms=0.0, launches=0, flops=0.0, max_tflops=0.0)
         self.last_solver_info = {}
         self.N = len(psi)
@@ -135,6 +136,11 @@ class StateEnvs:
                         acc = env.phase_kernel_ms.setdefault(name, {})
                         for k, v in pr["category_ms"].items():
                             acc[k] = acc.get(k, 0.0) + v
+                        cd = env.collective_detail.setdefault(name, {})
+                        for k, v in pr["collective_ms"].items():
+                            if pr["collective_calls"][k]:
+                                e = cd.setdefault(k, [0.0, 0])
+                                e[0] += v; e[1] += pr["collective_calls"][k]
                         g = env.gemm_prof
                         g["total_ms"] += pr["total_ms"]; g["launches"] += pr["launches"]; g["flops"] += pr["flops"]
                         g["max_tflops"] = max(g["max_tflops"], pr["max_tflops"])
