@@ -66,7 +66,8 @@ int tnl_profile_collectives(tnl_ctx_t ctx, double* out8);
 /* ---- multi-GPU: one process per GPU, sharded H_eff apply ----------------
  * rank 0 calls tnl_comm_unique_id, the 128 bytes are broadcast by the host (torch.distributed / MPI), every rank
  * calls tnl_comm_init.  Afterwards tnl_heff_apply / tnl_eigsolve_lanczos shard the two-site apply over the right
- * link (each rank owns tnl_shard_range of every sector) and combine the partial results with ncclAllReduce.
+ * link (each rank owns tnl_shard_range of every sector) and combine the partial results with ncclReduceScatter
+ * (Krylov vectors stay sharded; inner products are scalar all-reduces, the result vector one all-gather).
  * All ranks must hold identical replicated state and issue the same calls. */
 int tnl_comm_unique_id(char* out128);
 int tnl_comm_init(tnl_ctx_t ctx, const char* uid128, int32_t rank, int32_t world);
@@ -87,7 +88,8 @@ int tnl_tensor_import(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t
  * NDTensors' interleaved (re, im) storage (offsets count complex elements); on the device the tensor is PLANAR --
  * two real planes in the same charge-fused layout -- so every contraction stays on the FP64 DMMA kernels.
  * tnl_tensor_export writes 2 * nelem doubles for a complex tensor.  Site operators (MPO / CouplingModel tensors)
- * are real.  Not built for complex tensors: eig_solver, QR gauge moves, the noise term, penalties, sharding. */
+ * are real.  eig_solver, exp_solver, the noise term, penalties and the gauge moves accept complex states; only the
+ * multi-GPU sharding is Float64-only (complex vectors run replicated). */
 int tnl_tensor_import_c128(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t* inds, int64_t nblocks,
                            const int32_t* coords, const int64_t* offsets, const double* data_re_im, int32_t nrow,
                            tnl_tensor_t* out);

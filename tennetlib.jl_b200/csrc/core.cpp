@@ -390,7 +390,8 @@ std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const 
     for (size_t k = 0; k < passY.size(); k++) xc[xmap[passY[k]]] = yb.c[passY[k]];
     int64_t slice_start = 0;
     if (slice) {
-      TNL_CHECK(slice->ypos > 0 && xmap[slice->ypos] >= 0, "sliced index must be passive and non-leading");
+      // the sliced index is passive, or the shared leading index (then the local rows are a sub-range of the source rows)
+      TNL_CHECK(slice->ypos >= 0 && xmap[slice->ypos] >= 0, "sliced index must not be contracted");
       xc[xmap[slice->ypos]] = slice->orig[yb.c[slice->ypos]];
       slice_start = slice->start[yb.c[slice->ypos]];
     }
@@ -460,7 +461,7 @@ std::unique_ptr<TransformPlan> plan_scatter(const Tensor& X, Tensor& Y, const Sl
   auto plan = std::make_unique<TransformPlan>();
   plan->ctx = Y.ctx;
   const int r = X.rank(), pos = slice.ypos;
-  TNL_CHECK(r == Y.rank() && pos > 0 && pos < r && r - 1 <= MAXP, "plan_scatter: bad ranks / slice position");
+  TNL_CHECK(r == Y.rank() && pos >= 0 && pos < r && r - 1 <= MAXP, "plan_scatter: bad ranks / slice position");
   int64_t col = 0;
   for (const Block& xb : X.blocks) {
     int yc[MAXR];

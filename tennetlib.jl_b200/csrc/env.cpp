@@ -250,6 +250,63 @@ static TensorP view_with_trivial(Ctx* ctx, const Tensor& src, int at, int nrow, 
   return v;
 }
 
+// ---- multi-GPU environment update ---------------------------------------------------------------------------------
+// Every rank computes the part of the new environment that belongs to its share of one link index (the same
+// tnl_shard_range partition the sharded apply uses) and the parts are exchanged with one all-gather: both GEMMs of
+// the update shrink by the world size, the result is replicated again (and bitwise identical on every rank).
+struct ShardIx { std::vector<SliceMap> sm; std::vector<Index> loc; };
+static ShardIx shard_index(Ctx* ctx, const Index& ix, int ypos) {
+  ShardIx sh;
+  sh.sm.resize(ctx->world);
+  sh.loc.resize(ctx->world);
+  for (int k = 0; k < ctx->world; k++) {
+    Index l = ix;
+    l.dims.clear(); l.qns.clear();
+    sh.sm[k].ypos = ypos;
+    for (int s = 0; s < ix.nsect(); s++) {
+      int st, cnt;
+      shard_range(ix.dims[s], ctx->world, s, k, &st, &cnt);
+      if (cnt > 0) { l.dims.push_back(cnt); l.qns.push_back(ix.qns[s]); sh.sm[k].orig.push_back(s); sh.sm[k].start.push_back(st); }
+    }
+    sh.loc[k] = l;
+  }
+  return sh;
+}
+static bool env_update_shardable(Ctx* ctx, const Tensor* E, const TensorP& Asite, const Index& ix) {
+  return ctx->shard_world() > 1 && E && !E->cplx && !Asite->cplx && ix.dim() >= 64 * (int64_t)ctx->world;
+}
+// `part` = this rank's slice (index `pos` local, any row grouping); returns the full tensor with `nrow` row indices
+static TensorP allgather_slices(Ctx* ctx, const Tensor& part, const Index& full_ix, int pos, int nrow, const ShardIx& sh) {
+  std::vector<Index> inds = part.inds;
+  std::vector<std::shared_ptr<Tensor>> loc(ctx->world);
+  int64_t nloc = 0;
+  for (int k = 0; k < ctx->world; k++) {
+    inds[pos] = with_dir(sh.loc[k], part.inds[pos].dir);
+    loc[k] = std::make_shared<Tensor>(ctx, inds, nrow, false);
+    nloc = std::max(nloc, loc[k]->nelem);
+  }
+  nloc = (nloc + 1) & ~int64_t(1);
+  double* send = ctx->scratch(Ctx::SLOT_LOCOUT, (size_t)nloc, true);
+  double* recv = ctx->scratch(Ctx::SLOT_PACKED, (size_t)nloc * ctx->world, false);
+  Tensor& mine = *loc[ctx->rank];
+  std::vector<int> id(part.rank());
+  std::iota(id.begin(), id.end(), 0);
+  auto xr = plan_transform(part, mine, id, nullptr, {});
+  run_transform(ctx, *xr, part.d, send, nullptr);
+  comm_allgather(ctx, send, recv, nloc);
+  inds[pos] = with_dir(full_ix, part.inds[pos].dir);
+  auto full = mk(ctx, inds, nrow);
+  std::vector<std::unique_ptr<TransformPlan>> keep;
+  for (int k = 0; k < ctx->world; k++) {
+    SliceMap sm = sh.sm[k];
+    sm.ypos = pos;
+    keep.push_back(plan_scatter(*loc[k], *full, sm));
+    run_transform(ctx, *keep.back(), recv + (int64_t)k * nloc, full->d, nullptr);
+  }
+  ctx->sync();
+  return full;
+}
+
 // L_j = L_{j-1} * A_j * W_j * dag(prime(A_j))      (ITensorMPS ProjMPO._makeL!; the same three contractions per id
 // in ProjCouplingModel._makeL!, src/mps/projcouplingmodel.jl:123-196).  L == nullptr: the term starts at this
 // site (src/mps/projcouplingmodel.jl:151-165, "uncommon tensor" branch with the site operator) -- L is the
@@ -259,6 +316,18 @@ TensorP Env::step_left(const Tensor* L, const TensorP& Asite, const Tensor& W) {
   TensorP As = as_nrow(ctx, Asite, 2);            // [l s | r]
   ap.reset();                                     // the apply workspaces are reused below
   ctx->slot_epoch++;
+  // multi-GPU: this rank takes its share of the KET's right link (the column group of the new environment)
+  const bool shard = env_update_shardable(ctx, L, Asite, Asite->inds[2]);
+  ShardIx sh;
+  const Index rfull = Aq->inds[2];
+  if (shard) {
+    sh = shard_index(ctx, rfull, 2);
+    auto Aloc = mk(ctx, {Aq->inds[0], Aq->inds[1], sh.loc[ctx->rank]}, 1);
+    auto xa = plan_transform(*Aq, *Aloc, {0, 1, 2}, nullptr, {}, &sh.sm[ctx->rank]);
+    run_transform(ctx, *xa, Aq->d, Aloc->d, nullptr);
+    ctx->sync();
+    Aq = Aloc;
+  }
   TensorP X1;
   if (L) {
     X1 = mk_ws(ctx, {L->inds[0], L->inds[1], Aq->inds[1], Aq->inds[2]}, 2, Ctx::SLOT_T1, L->cplx || Aq->cplx);
@@ -276,6 +345,7 @@ TensorP Env::step_left(const Tensor* L, const TensorP& Asite, const Tensor& W) {
   auto g2 = plan_gemm(*As, true, *Y1, false, *Ln, /*dagA=*/true);
   cgemm(ctx, *g2, *As, /*conj: the bra*/true, *Y1, false, *Ln);
   ctx->sync();
+  if (shard) return allgather_slices(ctx, *Ln, rfull, 2, 2, sh);
   return relayout(ctx, *Ln, 2);
 }
 
@@ -284,9 +354,21 @@ TensorP Env::step_left(const Tensor* L, const TensorP& Asite, const Tensor& W) {
 TensorP Env::step_right(const Tensor* R, const TensorP& Asite, const Tensor& W) {
   TensorP Aq = as_nrow(ctx, Asite, 1);
   TensorP As = as_nrow(ctx, Asite, 2);
-  const Index &l = As->inds[0], &s = As->inds[1], &r = As->inds[2];
   ap.reset();
   ctx->slot_epoch++;
+  // multi-GPU: this rank takes its share of the BRA's left link (the row group of the new environment)
+  const bool shard = env_update_shardable(ctx, R, Asite, Asite->inds[0]);
+  ShardIx sh;
+  const Index lfull = As->inds[0];
+  if (shard) {
+    sh = shard_index(ctx, lfull, 0);
+    auto Aloc = mk(ctx, {sh.loc[ctx->rank], As->inds[1], As->inds[2]}, 2);
+    auto xa = plan_transform(*As, *Aloc, {0, 1, 2}, nullptr, {}, &sh.sm[ctx->rank]);
+    run_transform(ctx, *xa, As->d, Aloc->d, nullptr);
+    ctx->sync();
+    As = Aloc;
+  }
+  const Index &l = As->inds[0], &s = As->inds[1], &r = As->inds[2];
   TensorP Z, conj_keep;
   if (R) {
     Z = mk_ws(ctx, {with_dir(l, -l.dir), with_dir(s, -s.dir), R->inds[1], R->inds[2]}, 2, Ctx::SLOT_T1, As->cplx || R->cplx);
@@ -314,6 +396,7 @@ TensorP Env::step_right(const Tensor* R, const TensorP& Asite, const Tensor& W) 
   auto g2 = plan_gemm(*Z2, false, *Aq, true, *Rn);
   cgemm(ctx, *g2, *Z2, false, *Aq, false, *Rn);
   ctx->sync();
+  if (shard) return allgather_slices(ctx, *Rn, with_dir(lfull, Rn->inds[0].dir), 0, 1, sh);
   return relayout(ctx, *Rn, 1);
 }
 

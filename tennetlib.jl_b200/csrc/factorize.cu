@@ -9,6 +9,7 @@
 //             grouped DGEMM kernel, cusolverDnDsyevd, other factor by projection (factorize_eigen).
 // Truncation: pooled spectrum sorted descending -> NDTensors `truncate!` (relative cumulative cutoff,
 // maxdim/mindim, degeneracy-aware docut) -> per-group keep `value > docut`; groups keeping nothing drop.
+#include <cuda.h>
 #include <cusolverDn.h>
 
 #include <algorithm>
@@ -36,23 +37,118 @@ static cusolverDnHandle_t solver(Ctx* ctx) {
   }
   return (cusolverDnHandle_t)ctx->cusolver;
 }
-struct SideSolver { cudaStream_t s = nullptr; cusolverDnHandle_t h = nullptr; double* work = nullptr; size_t bytes = 0; int* info = nullptr; };
-static std::vector<SideSolver>& side_solvers(Ctx* ctx) {
-  static std::map<Ctx*, std::vector<SideSolver>> all;
-  auto& v = all[ctx];
-  if (v.empty()) {
-    int ns = 4;
-    if (const char* e = getenv("TNL_SIDE_STREAMS")) ns = std::max(1, atoi(e));
-    v.resize(ns);
-    for (auto& sv : v) {
-      CUDA_OK(cudaStreamCreateWithFlags(&sv.s, cudaStreamNonBlocking));
-      CUSOLVER_OK(cusolverDnCreate(&sv.h));
-      CUSOLVER_OK(cusolverDnSetStream(sv.h, sv.s));
-      CUDA_OK(cudaMalloc(&sv.info, 64 * sizeof(int)));
-    }
-  }
-  return v;
+// ---------------------------------------------------------------------------------------------------
+// SM partitions for the per-charge-group eigendecompositions.
+// cusolverDnDsyevd is a latency chain -- its tridiagonalisation costs ~11 us per COLUMN whatever the machine size,
+// plus a bandwidth term ~ n^3 / #SMs (measured on B200, profiles/r02g_eigh_green.json:  t[ms] ~ 0.0112 n + 9.2e-8 n^3 / S)
+// -- and its persistent kernel sizes itself to the SMs it sees, so decompositions on plain side streams do not
+// overlap (profiles/r02c_eigh_bench.json).  Inside GREEN CONTEXTS (disjoint SM partitions, CUDA driver API) they do:
+// the 11 charge groups of the chi = 4096 bench bond take 196 ms one after the other and ~100 ms on three partitions.
+// A partition set is a tuple of sizes in units of 16 SMs (on B200 the driver hands out nine 16-SM groups + 4 SMs; with 8-SM
+// groups it only places fifteen, profiles/r02g_eigh_green.json); the batch driver
+// below picks, per call, the set with the smallest modelled makespan out of a short candidate list.
+struct PartSolver {
+  cudaStream_t s = nullptr; cusolverDnHandle_t h = nullptr; double* work = nullptr; size_t bytes = 0; int* info = nullptr;
+  int sms = 0;
+};
+constexpr int kPartUnitSMs = 16;
+struct PartSet { std::vector<int> units; std::vector<PartSolver> parts; bool ok = false; };
+
+struct GreenApi {
+  CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+  CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*DevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+  CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*GreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*GreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  bool ok = false;
+};
+static GreenApi& green_api() {
+  static GreenApi api = [] {
+    GreenApi a;
+    auto get = [](const char* name) -> void* {
+      void* p = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+      return p;
+    };
+    a.DeviceGet = (decltype(a.DeviceGet))get("cuDeviceGet");
+    a.DeviceGetDevResource = (decltype(a.DeviceGetDevResource))get("cuDeviceGetDevResource");
+    a.DevSmResourceSplitByCount = (decltype(a.DevSmResourceSplitByCount))get("cuDevSmResourceSplitByCount");
+    a.DevResourceGenerateDesc = (decltype(a.DevResourceGenerateDesc))get("cuDevResourceGenerateDesc");
+    a.GreenCtxCreate = (decltype(a.GreenCtxCreate))get("cuGreenCtxCreate");
+    a.GreenCtxStreamCreate = (decltype(a.GreenCtxStreamCreate))get("cuGreenCtxStreamCreate");
+    a.ok = a.DeviceGet && a.DeviceGetDevResource && a.DevSmResourceSplitByCount && a.DevResourceGenerateDesc && a.GreenCtxCreate &&
+           a.GreenCtxStreamCreate;
+    cudaGetLastError();
+    return a;
+  }();
+  return api;
 }
+
+// partition set `units` (sizes in units of 16 SMs) on `device`; one unit tuple {0} = the whole device on a plain stream.
+// Sets are created once per (device, tuple) and shared by every context on that device.
+static PartSet& part_set(int device, const std::vector<int>& units) {
+  static std::map<std::pair<int, std::vector<int>>, PartSet> all;
+  auto key = std::make_pair(device, units);
+  auto it = all.find(key);
+  if (it != all.end()) return it->second;
+  PartSet& ps = all[key];
+  ps.units = units;
+  auto finish = [&](PartSolver& sv) {
+    CUSOLVER_OK(cusolverDnCreate(&sv.h));
+    CUSOLVER_OK(cusolverDnSetStream(sv.h, sv.s));
+    CUDA_OK(cudaMalloc(&sv.info, 64 * sizeof(int)));
+  };
+  if (units.size() == 1) {                         // whole device
+    ps.parts.resize(1);
+    CUDA_OK(cudaStreamCreateWithFlags(&ps.parts[0].s, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    ps.parts[0].sms = prop.multiProcessorCount;
+    finish(ps.parts[0]);
+    ps.ok = true;
+    return ps;
+  }
+  GreenApi& api = green_api();
+  static const bool dbg = getenv("TNL_EIGH_DEBUG") != nullptr;
+  auto fail = [&](const char* what, int rc) -> PartSet& {
+    if (dbg) fprintf(stderr, "[tnl] SM partition set unavailable: %s (rc %d)\n", what, rc);
+    return ps;
+  };
+  if (!api.ok) return fail("green-context driver entry points missing", 0);
+  CUdevice dev;
+  CUdevResource all_sm, rem;
+  CUresult rc;
+  if ((rc = api.DeviceGet(&dev, device)) != CUDA_SUCCESS) return fail("cuDeviceGet", rc);
+  if ((rc = api.DeviceGetDevResource(dev, &all_sm, CU_DEV_RESOURCE_TYPE_SM)) != CUDA_SUCCESS) return fail("cuDeviceGetDevResource", rc);
+  int total_units = 0;
+  for (int u : units) total_units += u;
+  std::vector<CUdevResource> res((size_t)total_units);
+  unsigned int ng = (unsigned int)total_units;
+  rc = api.DevSmResourceSplitByCount(res.data(), &ng, &all_sm, &rem, 0, kPartUnitSMs);
+  if (rc != CUDA_SUCCESS || (int)ng < total_units) return fail("cuDevSmResourceSplitByCount (16-SM units)", rc != CUDA_SUCCESS ? (int)rc : -(int)ng);
+  ps.parts.resize(units.size());
+  int at = 0;
+  for (size_t p = 0; p < units.size(); p++) {
+    CUdevResourceDesc desc;
+    CUgreenCtx g;
+    CUstream st;
+    if ((rc = api.DevResourceGenerateDesc(&desc, &res[at], (unsigned int)units[p])) != CUDA_SUCCESS) return fail("cuDevResourceGenerateDesc", rc);
+    if ((rc = api.GreenCtxCreate(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) return fail("cuGreenCtxCreate", rc);
+    if ((rc = api.GreenCtxStreamCreate(&st, g, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS) return fail("cuGreenCtxStreamCreate", rc);
+    ps.parts[p].s = (cudaStream_t)st;
+    ps.parts[p].sms = 0;
+    for (int u = 0; u < units[p]; u++) ps.parts[p].sms += (int)res[at + u].sm.smCount;
+    at += units[p];
+    finish(ps.parts[p]);
+  }
+  ps.ok = true;
+  return ps;
+}
+// modelled milliseconds of one cusolverDn{D,Z}syevd / heevd of order n on S SMs (fit of profiles/r02g_eigh_green.json)
+static double eigh_cost_ms(double n, double S, bool cplx) { return (0.0112 * n + 9.2e-8 * n * n * n / S) * (cplx ? 2.0 : 1.0); }
+
 static double* solver_ws(Ctx* ctx, size_t doubles) {
   size_t bytes = doubles * sizeof(double);
   if (bytes > ctx->solver_work_bytes) {
@@ -168,41 +264,102 @@ struct FG {                     // one charge group of the factorisation
   }
 };
 
-// Hermitian eigendecompositions of independent dense matrices (one per charge group), spread over side streams and
-// host threads: cusolverDnDsyevd is largely host-driven (its calls block while panels are factorised), so each side
-// solver gets its own host thread and the decompositions of the large charge groups really run concurrently.
-struct EighJob { int64_t n; double* A; double* W; std::vector<double>* vals; int64_t lda; };   // A: in matrix / out eigenvectors
+// Hermitian eigendecompositions of independent dense matrices (one per charge group), spread over SM partitions
+// (green contexts, see part_set) and host threads: cusolverDnDsyevd is host-driven (its calls block while panels are
+// factorised), so each partition gets its own host thread.  Jobs go, largest first, to the partition on which they
+// would finish earliest under the cost model; the partition set is the candidate with the smallest modelled makespan.
+struct EighJob { int64_t n; double* A; double* W; std::vector<double>* vals; int64_t lda; bool cplx = false; };   // A: in matrix / out eigenvectors (cplx: interleaved)
 static void syevd_batch(Ctx* ctx, std::vector<EighJob>& jobs) {
   if (jobs.empty()) return;
   ctx->sync();
   std::vector<size_t> order(jobs.size());
   std::iota(order.begin(), order.end(), 0);
   std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return jobs[a].n > jobs[b].n; });
-  auto& sides = side_solvers(ctx);
+  // ---- choose the partition set
+  static const std::vector<std::vector<int>> kCandidates = {{0}, {8, 1}, {7, 2}, {5, 4}, {4, 3, 2}, {3, 3, 3}, {4, 2, 2, 1}, {2, 2, 2, 2, 1}};
+  std::vector<std::vector<int>> cands;
+  if (const char* e = getenv("TNL_EIGH_PARTS")) {            // "0" = whole device only, "4,2,2,1" = this set, unset = auto
+    std::vector<int> u;
+    for (const char* q = e; *q;) { u.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q == ',') q++; }
+    cands.push_back(u.empty() ? std::vector<int>{0} : u);
+  } else {
+    cands = kCandidates;
+  }
+  auto assign = [&](const std::vector<int>& sms, std::vector<int>& where) {
+    std::vector<double> fin(sms.size(), 0.0);
+    where.assign(jobs.size(), 0);
+    for (size_t k : order) {
+      size_t best = 0;
+      double bt = 1e300;
+      for (size_t p = 0; p < sms.size(); p++) {
+        const double t = fin[p] + eigh_cost_ms((double)jobs[k].n, sms[p], jobs[k].cplx);
+        if (t < bt) { bt = t; best = p; }
+      }
+      fin[best] = bt;
+      where[k] = (int)best;
+    }
+    return *std::max_element(fin.begin(), fin.end());
+  };
+  PartSet* ps = nullptr;
+  std::vector<int> where;
+  {
+    double best = 1e300;
+    for (auto& u : cands) {
+      std::vector<int> sms;
+      if (u.size() == 1) sms = {ctx->num_sms}; else for (int x : u) sms.push_back(kPartUnitSMs * x);
+      std::vector<int> w;
+      const double t = assign(sms, w);
+      if (t < best * 0.97) {                       // a partitioned set must win by a margin: it costs extra launches
+        PartSet& cand = part_set(ctx->device, u.size() == 1 ? std::vector<int>{0} : u);
+        if (!cand.ok) continue;
+        best = t; ps = &cand; where = w;
+      }
+    }
+    if (!ps) {
+      ps = &part_set(ctx->device, {0});
+      assign({ctx->num_sms}, where);
+    }
+  }
+  if (getenv("TNL_EIGH_DEBUG")) {
+    fprintf(stderr, "[tnl] syevd_batch: %zu jobs (largest n = %lld) on partition set {", jobs.size(), (long long)jobs[order[0]].n);
+    for (auto& sv : ps->parts) fprintf(stderr, " %d", sv.sms);
+    fprintf(stderr, " } SMs\n");
+  }
+  auto& sides = ps->parts;
   std::vector<int> slot_of(jobs.size());
   std::vector<int> used(sides.size(), 0);
-  for (size_t k = 0; k < order.size(); k++) {
-    TNL_CHECK(used[k % sides.size()] < 64, "too many charge groups per side stream");
-    slot_of[order[k]] = used[k % sides.size()]++;
+  for (size_t k : order) {
+    TNL_CHECK(used[where[k]] < 64, "too many charge groups per partition");
+    slot_of[k] = used[where[k]]++;
   }
   std::vector<std::string> errs(sides.size());
   auto worker = [&](size_t si) {
     try {
       CUDA_OK(cudaSetDevice(ctx->device));
-      SideSolver& sv = sides[si];
-      for (size_t k = si; k < order.size(); k += sides.size()) {
-        EighJob& j = jobs[order[k]];
+      PartSolver& sv = sides[si];
+      for (size_t k : order) {
+        if ((size_t)where[k] != si) continue;
+        EighJob& j = jobs[k];
         int lwork = 0;
-        CUSOLVER_OK(cusolverDnDsyevd_bufferSize(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)j.n, j.A, (int)j.lda,
-                                                j.W, &lwork));
-        if ((size_t)lwork * sizeof(double) > sv.bytes) {
+        if (j.cplx)
+          CUSOLVER_OK(cusolverDnZheevd_bufferSize(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)j.n, (cuDoubleComplex*)j.A,
+                                                  (int)j.lda, j.W, &lwork));
+        else
+          CUSOLVER_OK(cusolverDnDsyevd_bufferSize(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)j.n, j.A, (int)j.lda,
+                                                  j.W, &lwork));
+        const size_t need = (size_t)lwork * sizeof(double) * (j.cplx ? 2 : 1);
+        if (need > sv.bytes) {
           CUDA_OK(cudaStreamSynchronize(sv.s));
           if (sv.work) cudaFree(sv.work);
-          sv.bytes = (size_t)lwork * sizeof(double) * 5 / 4;
+          sv.bytes = need * 5 / 4;
           CUDA_OK(cudaMalloc(&sv.work, sv.bytes));
         }
-        CUSOLVER_OK(cusolverDnDsyevd(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)j.n, j.A, (int)j.lda, j.W,
-                                     sv.work, lwork, sv.info + slot_of[order[k]]));
+        if (j.cplx)
+          CUSOLVER_OK(cusolverDnZheevd(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)j.n, (cuDoubleComplex*)j.A, (int)j.lda,
+                                       j.W, (cuDoubleComplex*)sv.work, lwork, sv.info + slot_of[k]));
+        else
+          CUSOLVER_OK(cusolverDnDsyevd(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)j.n, j.A, (int)j.lda, j.W,
+                                       sv.work, lwork, sv.info + slot_of[k]));
       }
       CUDA_OK(cudaStreamSynchronize(sv.s));
     } catch (const std::exception& e) {
@@ -211,21 +368,21 @@ static void syevd_batch(Ctx* ctx, std::vector<EighJob>& jobs) {
   };
   {
     std::vector<std::thread> th;
-    const size_t nth = std::min(sides.size(), order.size());
-    for (size_t si = 1; si < nth; si++) th.emplace_back(worker, si);
-    if (nth > 0) worker(0);
+    for (size_t si = 1; si < sides.size(); si++)
+      if (used[si] > 0) th.emplace_back(worker, si);
+    worker(0);
     for (auto& t : th) t.join();
     for (auto& e : errs) TNL_CHECK(e.empty(), e);
   }
   for (auto& sv : sides) CUDA_OK(cudaStreamSynchronize(sv.s));
-  for (size_t k = 0; k < order.size(); k++) {
-    EighJob& j = jobs[order[k]];
-    SideSolver& sv = sides[k % sides.size()];
+  for (size_t k : order) {
+    EighJob& j = jobs[k];
+    PartSolver& sv = sides[where[k]];
     j.vals->resize(j.n);
     CUDA_OK(cudaMemcpy(j.vals->data(), j.W, j.n * sizeof(double), cudaMemcpyDeviceToHost));
     int info = 0;
-    CUDA_OK(cudaMemcpy(&info, sv.info + slot_of[order[k]], sizeof(int), cudaMemcpyDeviceToHost));
-    TNL_CHECK(info == 0, "cusolverDnDsyevd did not converge");
+    CUDA_OK(cudaMemcpy(&info, sv.info + slot_of[k], sizeof(int), cudaMemcpyDeviceToHost));
+    TNL_CHECK(info == 0, "cuSOLVER syevd / heevd did not converge");
   }
 }
 
@@ -440,32 +597,38 @@ static FactorizeResult factorize_complex(Ctx* ctx, const Tensor& T, const Factor
       }
     }
   }
-  // ---- Hermitian eigendecompositions
+  // ---- Hermitian eigendecompositions: planar -> interleaved, cusolverDnZheevd per charge group on the SM
+  // partitions (syevd_batch), eigenvectors back to planes
   std::vector<double> pool;
-  for (size_t gi = 0; gi < fg.size(); gi++) {
-    FG& f = fg[gi];
-    const int64_t n = left ? f.R : f.C;
-    if (n == 0) continue;
-    double2* Z = (double2*)talloc(2 * n * n);
-    double* Wv = talloc(n);
-    const int grid = (int)std::min<int64_t>((n * n + 255) / 256, 1184);
-    interleave_kernel<<<grid, 256, 0, ctx->stream>>>(Z, Er[gi], Ei[gi], n * n);
-    CUDA_OK(cudaGetLastError());
-    int lwork = 0;
-    CUSOLVER_OK(cusolverDnZheevd_bufferSize(H, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n,
-                                            (cuDoubleComplex*)Z, (int)n, Wv, &lwork));
-    double* work = solver_ws(ctx, (size_t)lwork * 2);
-    CUSOLVER_OK(cusolverDnZheevd(H, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, (cuDoubleComplex*)Z, (int)n,
-                                 Wv, (cuDoubleComplex*)work, lwork, ctx->d_info));
-    deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>(Er[gi], Ei[gi], Z, n * n);     // eigenvectors, planar
-    CUDA_OK(cudaGetLastError());
-    f.vals.resize(n);
-    int info = 0;
-    CUDA_OK(cudaMemcpyAsync(f.vals.data(), Wv, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_OK(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  {
+    std::vector<EighJob> jobs;
+    std::vector<size_t> job_group;
+    std::vector<double2*> Zs;
+    for (size_t gi = 0; gi < fg.size(); gi++) {
+      FG& f = fg[gi];
+      const int64_t n = left ? f.R : f.C;
+      if (n == 0) continue;
+      double2* Z = (double2*)talloc(2 * n * n);
+      double* Wv = talloc(n);
+      const int grid = (int)std::min<int64_t>((n * n + 255) / 256, 1184);
+      interleave_kernel<<<grid, 256, 0, ctx->stream>>>(Z, Er[gi], Ei[gi], n * n);
+      CUDA_OK(cudaGetLastError());
+      EighJob j{n, (double*)Z, Wv, &f.vals, n};
+      j.cplx = true;
+      jobs.push_back(j);
+      job_group.push_back(gi);
+      Zs.push_back(Z);
+    }
+    syevd_batch(ctx, jobs);
+    for (size_t k = 0; k < jobs.size(); k++) {
+      const size_t gi = job_group[k];
+      const int64_t n = jobs[k].n;
+      const int grid = (int)std::min<int64_t>((n * n + 255) / 256, 1184);
+      deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>(Er[gi], Ei[gi], Zs[k], n * n);     // eigenvectors, planar
+      CUDA_OK(cudaGetLastError());
+      for (double w : fg[gi].vals) pool.push_back(std::fabs(w));
+    }
     ctx->sync();
-    TNL_CHECK(info == 0, "cusolverDnZheevd did not converge");
-    for (double w : f.vals) pool.push_back(std::fabs(w));
   }
   // ---- pooled truncation (identical to the real path)
   std::sort(pool.begin(), pool.end(), std::greater<double>());
