@@ -264,6 +264,37 @@ struct FG {                     // one charge group of the factorisation
   }
 };
 
+static const std::vector<std::vector<int>> kPartCandidates = {{0}, {8, 1}, {7, 2}, {5, 4}, {4, 3, 2}, {3, 3, 3}, {4, 2, 2, 1}, {2, 2, 2, 2, 1}};
+// modelled makespan of a list of decompositions (orders n) on the partition set `units`: largest first, each job to
+// the partition on which it would finish earliest; `where` (optional) receives the partition of every job
+static double eigh_makespan(const std::vector<int64_t>& n, const std::vector<char>& cplx, const std::vector<int>& units, int device_sms,
+                            std::vector<int>* where) {
+  std::vector<int> sms;
+  if (units.size() == 1) sms = {device_sms}; else for (int x : units) sms.push_back(kPartUnitSMs * x);
+  std::vector<size_t> order(n.size());
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return n[a] > n[b]; });
+  std::vector<double> fin(sms.size(), 0.0);
+  if (where) where->assign(n.size(), 0);
+  for (size_t k : order) {
+    size_t best = 0;
+    double bt = 1e300;
+    for (size_t p = 0; p < sms.size(); p++) {
+      const double t = fin[p] + eigh_cost_ms((double)n[k], sms[p], cplx.empty() ? false : cplx[k] != 0);
+      if (t < bt) { bt = t; best = p; }
+    }
+    fin[best] = bt;
+    if (where) (*where)[k] = (int)best;
+  }
+  return fin.empty() ? 0.0 : *std::max_element(fin.begin(), fin.end());
+}
+// smallest modelled makespan over the candidate partition sets (what syevd_batch will achieve for these jobs)
+static double eigh_best_makespan(const std::vector<int64_t>& n, int device_sms) {
+  double best = 1e300;
+  for (auto& u : kPartCandidates) best = std::min(best, eigh_makespan(n, {}, u, device_sms, nullptr));
+  return n.empty() ? 0.0 : best;
+}
+
 // Hermitian eigendecompositions of independent dense matrices (one per charge group), spread over SM partitions
 // (green contexts, see part_set) and host threads: cusolverDnDsyevd is host-driven (its calls block while panels are
 // factorised), so each partition gets its own host thread.  Jobs go, largest first, to the partition on which they
@@ -276,39 +307,24 @@ static void syevd_batch(Ctx* ctx, std::vector<EighJob>& jobs) {
   std::iota(order.begin(), order.end(), 0);
   std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return jobs[a].n > jobs[b].n; });
   // ---- choose the partition set
-  static const std::vector<std::vector<int>> kCandidates = {{0}, {8, 1}, {7, 2}, {5, 4}, {4, 3, 2}, {3, 3, 3}, {4, 2, 2, 1}, {2, 2, 2, 2, 1}};
   std::vector<std::vector<int>> cands;
   if (const char* e = getenv("TNL_EIGH_PARTS")) {            // "0" = whole device only, "4,2,2,1" = this set, unset = auto
     std::vector<int> u;
     for (const char* q = e; *q;) { u.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q == ',') q++; }
     cands.push_back(u.empty() ? std::vector<int>{0} : u);
   } else {
-    cands = kCandidates;
+    cands = kPartCandidates;
   }
-  auto assign = [&](const std::vector<int>& sms, std::vector<int>& where) {
-    std::vector<double> fin(sms.size(), 0.0);
-    where.assign(jobs.size(), 0);
-    for (size_t k : order) {
-      size_t best = 0;
-      double bt = 1e300;
-      for (size_t p = 0; p < sms.size(); p++) {
-        const double t = fin[p] + eigh_cost_ms((double)jobs[k].n, sms[p], jobs[k].cplx);
-        if (t < bt) { bt = t; best = p; }
-      }
-      fin[best] = bt;
-      where[k] = (int)best;
-    }
-    return *std::max_element(fin.begin(), fin.end());
-  };
+  std::vector<int64_t> jn;
+  std::vector<char> jc;
+  for (auto& j : jobs) { jn.push_back(j.n); jc.push_back(j.cplx ? 1 : 0); }
   PartSet* ps = nullptr;
   std::vector<int> where;
   {
     double best = 1e300;
     for (auto& u : cands) {
-      std::vector<int> sms;
-      if (u.size() == 1) sms = {ctx->num_sms}; else for (int x : u) sms.push_back(kPartUnitSMs * x);
       std::vector<int> w;
-      const double t = assign(sms, w);
+      const double t = eigh_makespan(jn, jc, u, ctx->num_sms, &w);
       if (t < best * 0.97) {                       // a partitioned set must win by a margin: it costs extra launches
         PartSet& cand = part_set(ctx->device, u.size() == 1 ? std::vector<int>{0} : u);
         if (!cand.ok) continue;
@@ -317,7 +333,7 @@ static void syevd_batch(Ctx* ctx, std::vector<EighJob>& jobs) {
     }
     if (!ps) {
       ps = &part_set(ctx->device, {0});
-      assign({ctx->num_sms}, where);
+      eigh_makespan(jn, jc, {0}, ctx->num_sms, &where);
     }
   }
   if (getenv("TNL_EIGH_DEBUG")) {
@@ -920,16 +936,25 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
   if (W > 1) {
     std::vector<size_t> ord(fg.size());
     std::iota(ord.begin(), ord.end(), 0);
-    // cost model of one decomposition = cusolverDnDsyevd measured on B200 (profiles/r02c_eigh_bench.json):
-    // t[ms] ~ 0.0109 n + 6.4e-10 n^3 -- the tridiagonalisation is latency bound (about 11 us per column), so the
-    // linear term dominates below n ~ 4000 and an n^3 model would overload the rank that gets the mid-sized groups
-    auto cost = [&](const FG& f) { double n = (double)(which == 1 ? std::max(f.R, f.C) : (left ? f.R : f.C)); return 0.0109 * n + 6.4e-10 * n * n * n; };
-    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cost(fg[a]) > cost(fg[b]); });
+    // a rank runs its decompositions concurrently on SM partitions (syevd_batch), so its load is the modelled
+    // makespan of its job list, not the sum of the costs; groups go, largest first, to the rank whose makespan
+    // grows the least
+    auto order_of = [&](const FG& f) { return (int64_t)(which == 1 ? std::max(f.R, f.C) : (left ? f.R : f.C)); };
+    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return order_of(fg[a]) > order_of(fg[b]); });
+    std::vector<std::vector<int64_t>> jobs_of(W);
     std::vector<double> load(W, 0.0);
     for (size_t i : ord) {
-      int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-      load[r] += cost(fg[i]);
-      fg[i].mine = (r == ctx->rank);
+      int best = 0;
+      double bt = 1e300;
+      for (int r = 0; r < W; r++) {
+        jobs_of[r].push_back(order_of(fg[i]));
+        const double t = eigh_best_makespan(jobs_of[r], ctx->num_sms);
+        jobs_of[r].pop_back();
+        if (t < bt - 1e-9) { bt = t; best = r; }
+      }
+      jobs_of[best].push_back(order_of(fg[i]));
+      load[best] = bt;
+      fg[i].mine = (best == ctx->rank);
     }
   }
   for (FG& f : fg) {
