@@ -574,6 +574,7 @@ def run_ours(args):
             "sweep_time_s_est": 198 * ms_per_step * 1e-3,
             "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
             "phase_ms_max_over_steps": {k: max(v for n, v in sysenv.phase_log if n == k) for k in phases},
+            "step_ms_list": [round(sum(v for _, v in sysenv.phase_log[4 * i:4 * i + 4]), 2) for i in range(len(sysenv.phase_log) // 4)],
             "apply_gflop": apply_flops_total / max(1, numops_total) / 1e9, "applies_per_step": numops_total / args.steps,
             "setup_s": t_setup,
             "krylov_vec": {"algorithmic_gb_per_step": cnt["vec_bytes"] / args.steps / 1e9},

@@ -58,10 +58,11 @@ int tnl_profile_read(tnl_ctx_t ctx, double* total_ms, int64_t* launches, double*
 /* by-category device time of the records consumed by the last tnl_profile_read: out[0..3] = ms of grouped DGEMM,
  * transform, Krylov-vector and collective launches, out[4..7] = their launch counts */
 int tnl_profile_categories(tnl_ctx_t ctx, double* out8);
-/* collectives consumed by the last tnl_profile_read, by kind: out[0..3] = ms of scalar all-reduces (Krylov inner
- * products), reduce-scatters (H_eff partial sums), all-gathers (result vectors), large all-reduces (truncation
- * factors); out[4..7] = their call counts */
-int tnl_profile_collectives(tnl_ctx_t ctx, double* out8);
+/* collectives consumed by the last tnl_profile_read, by kind: out[0..5] = ms of scalar all-reduces (Krylov inner
+ * products), NCCL reduce-scatters (H_eff partial sums), all-gathers (result vectors, environment slices), large
+ * all-reduces (truncation factors), and -- fused GEMM -> reduce-scatter over peer memory -- the wait for "staging slots
+ * consumed" and the ordered sum over the slots (which includes the wait for the peers' tiles); out[6..11] = call counts */
+int tnl_profile_collectives(tnl_ctx_t ctx, double* out12);
 
 /* ---- multi-GPU: one process per GPU, sharded H_eff apply ----------------
  * rank 0 calls tnl_comm_unique_id, the 128 bytes are broadcast by the host (torch.distributed / MPI), every rank

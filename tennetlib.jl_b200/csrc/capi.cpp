@@ -11,7 +11,7 @@
 
 using namespace tnl;
 
-struct tnl_ctx_s { Ctx ctx; cudaEvent_t ev[8] = {}; double cat_ms[8] = {}; double coll_ms[8] = {}; explicit tnl_ctx_s(int dev) : ctx(dev) {} };
+struct tnl_ctx_s { Ctx ctx; cudaEvent_t ev[8] = {}; double cat_ms[8] = {}; double coll_ms[12] = {}; explicit tnl_ctx_s(int dev) : ctx(dev) {} };
 struct tnl_tensor_s { TensorP t; };
 struct tnl_env_s { Env env; tnl_env_s(Ctx* c, int n) : env(c, n) {} };
 struct tnl_sumop_s { SumOp op; explicit tnl_sumop_s(Ctx* c) : op(c) {} };
@@ -186,7 +186,8 @@ int tnl_profile_read(tnl_ctx_t c, double* total_ms, int64_t* launches, double* f
   return guard(&c->ctx, [&] {
     c->ctx.sync();
     *total_ms = 0; *launches = 0; *flops = 0; *max_tflops = 0;
-    for (int k = 0; k < 8; k++) c->cat_ms[k] = c->coll_ms[k] = 0;
+    for (int k = 0; k < 8; k++) c->cat_ms[k] = 0;
+    for (int k = 0; k < 12; k++) c->coll_ms[k] = 0;
     for (auto& r : c->ctx.prof_recs) {
       float ms = 0;
       CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
@@ -195,7 +196,7 @@ int tnl_profile_read(tnl_ctx_t c, double* total_ms, int64_t* launches, double* f
         if (ms > 0 && r.flops > 1e9) *max_tflops = std::max(*max_tflops, r.flops / (ms * 1e-3) / 1e12);
       }
       if (r.cat >= 0 && r.cat < 4) { c->cat_ms[r.cat] += ms; c->cat_ms[4 + r.cat] += 1; }
-      if (r.cat == 3 && r.tiles >= 0 && r.tiles < 4) { c->coll_ms[r.tiles] += ms; c->coll_ms[4 + r.tiles] += 1; }
+      if (r.cat == 3 && r.tiles >= 0 && r.tiles < 6) { c->coll_ms[r.tiles] += ms; c->coll_ms[6 + r.tiles] += 1; }
       cudaEventDestroy(r.a); cudaEventDestroy(r.b);
     }
     c->ctx.prof_recs.clear();
@@ -207,10 +208,12 @@ int tnl_profile_categories(tnl_ctx_t c, double* out8) {
   return guard(&c->ctx, [&] { for (int k = 0; k < 8; k++) out8[k] = c->cat_ms[k]; out8[7] = c->ctx.cnt.host_plan_ms; });
 }
 
-/* collectives of the last tnl_profile_read by kind: out[0..3] = ms of scalar all-reduces (inner products), reduce-scatters
- * (H_eff partial sums), all-gathers (result vectors), large all-reduces (truncation factors); out[4..7] = call counts */
-int tnl_profile_collectives(tnl_ctx_t c, double* out8) {
-  return guard(&c->ctx, [&] { for (int k = 0; k < 8; k++) out8[k] = c->coll_ms[k]; });
+/* collectives of the last tnl_profile_read by kind: out[0..5] = ms of scalar all-reduces (inner products), NCCL
+ * reduce-scatters (H_eff partial sums), all-gathers, large all-reduces (truncation factors), and of the fused path the
+ * "slots consumed" wait and the ordered sum over the staging slots (includes the wait for the peers' data);
+ * out[6..11] = call counts */
+int tnl_profile_collectives(tnl_ctx_t c, double* out12) {
+  return guard(&c->ctx, [&] { for (int k = 0; k < 12; k++) out12[k] = c->coll_ms[k]; });
 }
 
 int tnl_tensor_import(tnl_ctx_t c, int32_t rank, int32_t nq, const tnl_index_t* inds, int64_t nblocks,

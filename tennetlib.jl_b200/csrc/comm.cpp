@@ -3,7 +3,9 @@
 // same soname resolves to it.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "env.hpp"
 
@@ -73,9 +75,100 @@ void comm_init(Ctx* ctx, const char* uid128, int rank, int world) {
   ctx->world = world;
 }
 
+static void stage_release(Ctx* ctx) {
+  Ctx::PeerStage& ps = ctx->pstage;
+  for (int k = 0; k < (int)ps.peer_base.size(); k++)
+    if (k != ctx->rank && ps.peer_base[k]) cudaIpcCloseMemHandle(ps.peer_base[k]);
+  ps.peer_base.clear();
+  if (ps.base) cudaFree(ps.base);
+  if (ps.d_peer_slots) cudaFree(ps.d_peer_slots);
+  if (ps.d_peer_flags) cudaFree(ps.d_peer_flags);
+  if (ps.d_done) cudaFree(ps.d_done);
+  ps.base = nullptr; ps.d_peer_slots = nullptr; ps.d_peer_flags = nullptr; ps.d_done = nullptr;
+  ps.slot_cap = 0;
+  ps.ok = false;
+}
+
+// Collective: (re)allocates the staging area when a slot of `slot_doubles` does not fit, exchanges the CUDA-IPC handles
+// through the NCCL communicator and maps the peers' areas.  Every rank takes the same decisions (sizes derive from
+// the replicated plan), and a failure on any rank switches the fused path off on all of them.
+constexpr size_t kStageFlagBytes = 2 * 64 * sizeof(unsigned long long);
+bool comm_stage_ensure(Ctx* ctx, size_t slot_doubles) {
+  Ctx::PeerStage& ps = ctx->pstage;
+  if (ctx->world <= 1 || !ctx->nccl_comm) return false;
+  if (ps.tried && !ps.ok) return false;
+  if (ps.ok && slot_doubles <= ps.slot_cap) return true;
+  if (const char* e = getenv("TNL_FUSED_RS")) if (atoi(e) == 0) { ps.tried = true; ps.ok = false; return false; }
+  TNL_CHECK(ctx->world <= 64, "staging flags are laid out for at most 64 ranks");
+  ps.tried = true;
+  ctx->sync();
+  // quiesce: nobody may still be writing into an area that is about to be unmapped
+  double* dflag = (double*)ctx->alloc(8 * sizeof(double));
+  CUDA_OK(cudaMemsetAsync(dflag, 0, 8 * sizeof(double), ctx->stream));
+  comm_allreduce_sum(ctx, dflag, 1);
+  ctx->sync();
+  stage_release(ctx);
+  const size_t cap = (std::max<size_t>(slot_doubles + slot_doubles / 2, size_t(1) << 20) + 1) & ~size_t(1);
+  const size_t bytes = kStageFlagBytes + cap * ctx->world * sizeof(double);
+  int good = 1;
+  cudaIpcMemHandle_t mine{};
+  if (cudaMalloc(&ps.base, bytes) != cudaSuccess) { good = 0; ps.base = nullptr; cudaGetLastError(); }
+  if (good) {
+    CUDA_OK(cudaMemset(ps.base, 0, bytes));
+    if (cudaIpcGetMemHandle(&mine, ps.base) != cudaSuccess) { good = 0; cudaGetLastError(); }
+  }
+  // all-gather of the 64-byte handles (+ one word "good") through NCCL: 9 doubles per rank
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  std::vector<double> sendh(9, 0.0), recvh((size_t)9 * ctx->world, 0.0);
+  std::memcpy(sendh.data(), &mine, 64);
+  sendh[8] = good ? 1.0 : 0.0;
+  double* dsend = (double*)ctx->alloc(9 * sizeof(double));
+  double* drecv = (double*)ctx->alloc((size_t)9 * ctx->world * sizeof(double));
+  CUDA_OK(cudaMemcpyAsync(dsend, sendh.data(), 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  comm_allgather(ctx, dsend, drecv, 9);
+  CUDA_OK(cudaMemcpyAsync(recvh.data(), drecv, recvh.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+  for (int k = 0; k < ctx->world; k++) good = good && recvh[(size_t)9 * k + 8] == 1.0;
+  ps.peer_base.assign(ctx->world, nullptr);
+  if (good) {
+    for (int k = 0; k < ctx->world && good; k++) {
+      if (k == ctx->rank) { ps.peer_base[k] = ps.base; continue; }
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, &recvh[(size_t)9 * k], 64);
+      if (cudaIpcOpenMemHandle(&ps.peer_base[k], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { good = 0; ps.peer_base[k] = nullptr; cudaGetLastError(); }
+    }
+  }
+  // agree on the outcome
+  double g = good ? 0.0 : 1.0;
+  CUDA_OK(cudaMemcpyAsync(dflag, &g, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  comm_allreduce_sum(ctx, dflag, 1);
+  CUDA_OK(cudaMemcpyAsync(&g, dflag, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+  ctx->free(dflag); ctx->free(dsend); ctx->free(drecv);
+  if (g != 0.0) { stage_release(ctx); return false; }
+  ps.slot_cap = cap;
+  std::vector<double*> slots(ctx->world);
+  std::vector<unsigned long long*> flags(ctx->world);
+  for (int k = 0; k < ctx->world; k++) {
+    flags[k] = (unsigned long long*)ps.peer_base[k];
+    slots[k] = (double*)((char*)ps.peer_base[k] + kStageFlagBytes) + (size_t)ctx->rank * cap;   // MY slot on rank k
+  }
+  CUDA_OK(cudaMalloc(&ps.d_peer_slots, ctx->world * sizeof(double*)));
+  CUDA_OK(cudaMalloc(&ps.d_peer_flags, ctx->world * sizeof(unsigned long long*)));
+  CUDA_OK(cudaMalloc(&ps.d_done, sizeof(unsigned int)));
+  CUDA_OK(cudaMemcpy(ps.d_peer_slots, slots.data(), ctx->world * sizeof(double*), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(ps.d_peer_flags, flags.data(), ctx->world * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemset(ps.d_done, 0, sizeof(unsigned int)));
+  ps.epoch = 0;                        // flags were zeroed with the new area
+  ps.ok = true;
+  return true;
+}
+
 void comm_destroy(Ctx* ctx) {
   if (ctx->nccl_comm) {
     ctx->sync();
+    stage_release(ctx);
+    ctx->pstage.tried = false;
     nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
     ctx->rank = 0;

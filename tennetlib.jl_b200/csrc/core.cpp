@@ -270,6 +270,29 @@ static void make_tiles(GemmPlan& plan) {
     plan.d_maps = plan.ctx->alloc((size_t)GemmPlan::MAPSETS_MAX * 2 * plan.probs.size() * 128);
 }
 
+// Re-tile a plan so that EVERY problem runs on the persistent TMA kernel (the fused GEMM -> reduce-scatter needs a
+// single kernel with the scatter epilogue; small sectors become partially filled 128x128 tiles, zero-filled by the TMA)
+void gemm_plan_force_tma(GemmPlan& plan) {
+  if (plan.tiles_big.empty() && plan.tiles_small.empty()) return;
+  Ctx* ctx = plan.ctx;
+  std::vector<char> have(plan.probs.size(), 0);
+  for (auto& t : plan.tiles_tma) have[t.prob] = 1;
+  for (size_t pi = 0; pi < plan.probs.size(); pi++) {
+    if (have[pi]) continue;
+    const auto& p = plan.probs[pi];
+    const int kt = (p.K + 15) / 16;
+    for (int n0 = 0; n0 < p.N; n0 += 128)
+      for (int m0 = 0; m0 < p.M; m0 += 128) plan.tiles_tma.push_back(TmaTile{p.c, m0, n0, p.M, p.N, kt, p.ldc, (int)pi, 0});
+  }
+  plan.tiles_big.clear();
+  plan.tiles_small.clear();
+  ctx->free(plan.d_tiles_big); ctx->free(plan.d_tiles_small); ctx->free(plan.d_tiles_tma);
+  plan.d_tiles_big = nullptr; plan.d_tiles_small = nullptr;
+  plan.d_tiles_tma = ctx->upload(plan.tiles_tma);
+  if (!plan.d_maps) plan.d_maps = ctx->alloc((size_t)GemmPlan::MAPSETS_MAX * 2 * plan.probs.size() * 128);
+  plan.mapsets.clear();
+}
+
 std::unique_ptr<GemmPlan> plan_gemm_raw(Ctx* ctx, bool transA, bool transB, const std::vector<GemmProblem>& probs) {
   auto plan = std::make_unique<GemmPlan>();
   plan->ctx = ctx;

@@ -165,6 +165,25 @@ struct GemmPlan {
   ~GemmPlan();
 };
 
+// Scatter epilogue of the grouped DGEMM (multi-GPU, fused reduce-scatter): element (m, n) of problem `prob` goes to
+// rank `rank(n)`, into the slot this rank owns there, at   T[rb(m) * nseg + seg(n)] + roff(m) + jj(n) * cstride[rb(m)]
+// -- the position of the element in the destination rank's local Krylov-vector layout.
+struct ScatterProb {
+  const int2* rowinfo;       // [M]: (row block rb, offset of the row inside a destination block)
+  const int2* colinfo;       // [N]: (segment | destination rank << 16, column inside the destination rank's share)
+  const int64_t* T;          // [nrb * nseg]: offset of the destination block
+  const int* cstride;        // [nrb]: stride between consecutive columns of the destination block
+  int nseg, pad;
+};
+struct ScatterArgs {
+  const ScatterProb* probs = nullptr;
+  double* const* peer_slots = nullptr;          // [world]: my slot inside every rank's staging area
+  unsigned long long* const* peer_flags = nullptr;
+  unsigned int* done = nullptr;                 // last-CTA counter
+  unsigned long long epoch = 0;
+  int rank = 0, world = 1;
+};
+
 // transform: Y(i, n..., p...) = sum_contrib sum_k X(i, k..., p...) * W(k, n)
 constexpr int MAXP = 4;
 struct XfContrib {
@@ -252,6 +271,19 @@ class Ctx {
   bool shard_enabled = true;        // false: every rank computes the whole (replicated, no collectives) -- the
                                     // reference path the sharded results are checked against (bench.py parity)
   int shard_world() const { return shard_enabled ? world : 1; }
+  // Fused GEMM -> reduce-scatter over peer memory (comm.cpp, kernels.cu): every rank owns a staging area of `world`
+  // slots (one per source rank) that its peers write straight from the epilogue of the `T3 R^T` GEMM through
+  // CUDA-IPC mappings, plus two flag words per source rank ("data of epoch e complete" / "slot consumed up to e").
+  struct PeerStage {
+    bool tried = false, ok = false;
+    void* base = nullptr;               // cudaMalloc: [flags: 2 * 64 words][world slots of slot_cap doubles]
+    size_t slot_cap = 0;                // doubles per slot
+    std::vector<void*> peer_base;       // the peers' bases mapped into this process (own base for rank == me)
+    double** d_peer_slots = nullptr;    // device array [world]: address of MY slot inside every peer's staging area
+    unsigned long long** d_peer_flags = nullptr;   // device array [world]: the peers' flag blocks
+    unsigned int* d_done = nullptr;     // "last CTA" counter of the scattering GEMM
+    unsigned long long epoch = 0;       // number of fused reduce-scatters issued (identical on every rank)
+  } pstage;
   // cuSOLVER (opaque here; factorize.cu owns the type)
   void* cusolver = nullptr;
   void* solver_work = nullptr; size_t solver_work_bytes = 0;
@@ -301,12 +333,21 @@ std::unique_ptr<GemmPlan> plan_gemm(const Tensor& A, bool transA, const Tensor& 
                                     bool dagA = false, bool dagB = false);
 // C = alpha * op(A) op(B)  (accum: += ; alpha = +-1 and accumulate serve the planar complex products)
 void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C, double alpha = 1.0, bool accum = false);
+// Fused GEMM -> reduce-scatter over peer memory: C tiles are stored straight into the destination ranks' staging slots
+// (scatter epilogue), completion is flagged to every peer, and `out` (nloc doubles) receives the sum over the source
+// ranks of this rank's slots, in rank order.  The plan must consist of 128x128 tiles only (plan_all_tma).
+void run_gemm_reduce_scatter(Ctx* ctx, GemmPlan& p, const double* A, const double* B, const ScatterProb* d_scatter, double* out,
+                             int64_t nloc);
+bool plan_all_tma(const GemmPlan& p);
+void gemm_plan_force_tma(GemmPlan& plan);   // every problem on the TMA kernel (also the small sectors)
 // ad-hoc problems (factorisation internals); builds tiles and uploads
 std::unique_ptr<GemmPlan> plan_gemm_raw(Ctx* ctx, bool transA, bool transB, const std::vector<GemmProblem>& probs);
 void gemm_selftest(Ctx* ctx, int M, int N, int K, bool ta, bool tb, int reps, bool verify, double* ms, double* maxerr);
 void comm_unique_id(char* out128);
 void comm_init(Ctx* ctx, const char* uid128, int rank, int world);
 void comm_destroy(Ctx* ctx);
+// staging area with at least `slot_doubles` per slot, mapped on every rank (collective call); false: fused path off
+bool comm_stage_ensure(Ctx* ctx, size_t slot_doubles);
 void comm_allreduce_sum(Ctx* ctx, double* buf, int64_t n);
 void comm_reduce_scatter_sum(Ctx* ctx, const double* send, double* recv, int64_t n);
 void comm_allgather(Ctx* ctx, const double* send, double* recv, int64_t n);

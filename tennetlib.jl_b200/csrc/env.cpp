@@ -600,6 +600,10 @@ struct Env::ApplyPlan {
   std::vector<SliceMap> pack_maps;
   std::vector<TensorP> qloc;
   Ctx* ctx = nullptr;
+  // fused `T3 R^T` -> reduce-scatter over peer memory: scatter tables of the GEMM epilogue (device) and their owner
+  ScatterProb* d_scatter = nullptr;
+  std::vector<void*> dev_allocs;
+  ~ApplyPlan() { if (ctx) for (void* q : dev_allocs) ctx->free(q); }
 
   TensorP L, R, W1, W2;
   TensorP T1, T2, T3, P;
@@ -718,9 +722,11 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
     Tensor Q(ctx, p->P->inds, 1, false);
     TNL_CHECK(Q.nelem == vfull.nelem, "H_eff output layout differs from the input layout (index mismatch)");
     p->x5 = plan_transform(*p->P, Q, {0, 1, 2, 3}, nullptr, {});
-    if (p->sharded)
+    if (p->sharded) {
       for (int k = 0; k < ctx->world; k++)
         p->pack.push_back(plan_transform(*p->P, *p->qloc[k], {0, 1, 2, 3}, nullptr, {}, &p->pack_maps[k]));
+      build_scatter_tables(*p);
+    }
     p->flops = (p->g1 ? p->g1->flops : 0.0) + p->x2->flops + p->x3->flops + (p->g4 ? p->g4->flops : 0.0);
   } else if (nsite == 1) {
     TNL_CHECK(v.rank() == 3, "one-site apply needs a (l,s,r) vector");
@@ -790,6 +796,88 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
   return p;
 }
 
+// Scatter tables of the fused reduce-scatter: for every charge-sector problem of `T3 R^T` (a group of
+// P[(l' s1' s2') | r']) where each output element lives in the local Krylov layout [l | (s1 s2 r_k)] of the rank k
+// that owns its column.  Row side: the row block (l' sector, s1', s2') and the offset inside the destination block;
+// column side: owner rank and column inside its share.  Falls back to pack + ncclReduceScatter when the staging
+// area cannot be set up or the plan has tiles the TMA kernel does not serve.
+void Env::build_scatter_tables(ApplyPlan& p) {
+  if (!p.g4 || !ctx->use_tma || p.g4->probs.empty()) return;
+  if (!comm_stage_ensure(ctx, (size_t)p.nloc)) return;
+  gemm_plan_force_tma(*p.g4);
+  const Tensor& P = *p.P;
+  const int W = ctx->world;
+  std::vector<int2> rowinfo, colinfo;
+  std::vector<int64_t> Tt;
+  std::vector<int> cstride;
+  struct Offs { size_t row, col, t, cs; int nseg; };
+  std::vector<Offs> offs;
+  for (const GemmProblem& gp : p.g4->probs) {
+    int gi = -1;
+    for (size_t g = 0; g < P.groups.size(); g++) if (P.groups[g].base == gp.c) gi = (int)g;
+    TNL_CHECK(gi >= 0, "scatter tables: GEMM problem without an output group");
+    const Group& G = P.groups[gi];
+    TNL_CHECK(G.R == gp.M && G.C == gp.N, "scatter tables: group shape");
+    const int nrb = (int)G.rows.size();
+    const int nseg = (int)G.cols.size() * W;
+    TNL_CHECK(nseg < 65536 && W < 32768, "scatter tables: too many column segments");
+    Offs o{rowinfo.size(), colinfo.size(), Tt.size(), cstride.size(), nseg};
+    rowinfo.resize(o.row + (size_t)G.R);
+    colinfo.resize(o.col + (size_t)G.C);
+    Tt.resize(o.t + (size_t)nrb * nseg, -1);
+    cstride.resize(o.cs + (size_t)nrb, 0);
+    // destination blocks: (row combo, column sector, rank)
+    std::vector<int64_t> st1(nrb, -1), st2(nrb, -1);
+    for (int rb = 0; rb < nrb; rb++) {
+      const Combo& rc = G.rows[rb];
+      for (size_t cc = 0; cc < G.cols.size(); cc++) {
+        const int bsec = G.cols[cc].c[0];
+        for (int k = 0; k < W; k++) {
+          const SliceMap& sm = p.pack_maps[k];
+          int bloc = -1;
+          for (size_t q = 0; q < sm.orig.size(); q++) if (sm.orig[q] == bsec) bloc = (int)q;
+          if (bloc < 0) continue;                  // rank k holds nothing of this sector
+          int co[MAXR] = {rc.c[0], rc.c[1], rc.c[2], bloc};
+          const int bi = p.qloc[k]->find(co);
+          TNL_CHECK(bi >= 0, "scatter tables: destination block missing");
+          const Block& db = p.qloc[k]->blocks[bi];
+          Tt[o.t + (size_t)rb * nseg + cc * W + k] = db.off;
+          TNL_CHECK(db.st[0] == 1, "scatter tables: destination rows must be contiguous");
+          if (st1[rb] < 0) { st1[rb] = db.st[1]; st2[rb] = db.st[2]; cstride[o.cs + rb] = (int)db.st[3]; }
+          TNL_CHECK(st1[rb] == db.st[1] && st2[rb] == db.st[2] && cstride[o.cs + rb] == (int)db.st[3],
+                    "scatter tables: destination strides differ between ranks");
+        }
+      }
+      for (int64_t e = 0; e < rc.dim; e++) {
+        const int64_t i0 = e % rc.d[0], i1 = (e / rc.d[0]) % rc.d[1], i2 = e / ((int64_t)rc.d[0] * rc.d[1]);
+        const int64_t roff = i0 + i1 * std::max<int64_t>(st1[rb], 0) + i2 * std::max<int64_t>(st2[rb], 0);
+        TNL_CHECK(roff < INT32_MAX, "scatter tables: row offset overflow");
+        rowinfo[o.row + (size_t)(rc.off + e)] = make_int2(rb, (int)roff);
+      }
+    }
+    for (size_t cc = 0; cc < G.cols.size(); cc++) {
+      const Combo& c = G.cols[cc];
+      const int bsec = c.c[0];
+      for (int k = 0; k < W; k++) {
+        int st, cnt;
+        shard_range((int)c.dim, W, bsec, k, &st, &cnt);
+        for (int j = 0; j < cnt; j++) colinfo[o.col + (size_t)(c.off + st + j)] = make_int2((int)(cc * W + k) | (k << 16), j);
+      }
+    }
+    offs.push_back(o);
+  }
+  p.ctx = ctx;
+  int2* d_row = ctx->upload(rowinfo);
+  int2* d_col = ctx->upload(colinfo);
+  int64_t* d_T = ctx->upload(Tt);
+  int* d_cs = ctx->upload(cstride);
+  std::vector<ScatterProb> sp(offs.size());
+  for (size_t i = 0; i < offs.size(); i++)
+    sp[i] = ScatterProb{d_row + offs[i].row, d_col + offs[i].col, d_T + offs[i].t, d_cs + offs[i].cs, offs[i].nseg, 0};
+  p.d_scatter = ctx->upload(sp);
+  p.dev_allocs = {d_row, d_col, d_T, d_cs, p.d_scatter};
+}
+
 double Env::apply_flops() const {
   if (cm) return cm_apply_flops();
   double f = ap ? ap->flops : 0.0;
@@ -808,9 +896,14 @@ void Env::apply_local(const double* vloc, double* outloc) {
   run_gemm(ctx, *p.g1, p.L->d, vloc, p.T1->d);
   run_transform(ctx, *p.x2, p.T1->d, p.T2->d, p.W1->d);
   run_transform(ctx, *p.x3, p.T2->d, p.T3->d, p.W2->d);
-  run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
-  for (int k = 0; k < ctx->world; k++) run_transform(ctx, *p.pack[k], p.P->d, p.packed + (int64_t)k * p.nloc, nullptr);
-  comm_reduce_scatter_sum(ctx, p.packed, outloc, p.nloc);
+  if (p.d_scatter) {
+    // one kernel does the GEMM and the exchange: tiles go straight into the owners' staging slots over NVLink
+    run_gemm_reduce_scatter(ctx, *p.g4, p.T3->d, p.R->d, p.d_scatter, outloc, p.nloc);
+  } else {
+    run_gemm(ctx, *p.g4, p.T3->d, p.R->d, p.P->d);
+    for (int k = 0; k < ctx->world; k++) run_transform(ctx, *p.pack[k], p.P->d, p.packed + (int64_t)k * p.nloc, nullptr);
+    comm_reduce_scatter_sum(ctx, p.packed, outloc, p.nloc);
+  }
   if (!more.empty()) {
     double* tmp = ctx->vec_acquire((size_t)p.nloc);
     for (auto& m : more) {

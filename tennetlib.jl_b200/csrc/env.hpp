@@ -136,6 +136,7 @@ class Env {
   struct ApplyPlan;
   std::shared_ptr<ApplyPlan> ap;
   void build_apply_plan(const Tensor& v);
+  void build_scatter_tables(ApplyPlan& p);   // multi-GPU: epilogue tables of the fused GEMM -> reduce-scatter
   std::shared_ptr<ApplyPlan> make_plan(const Tensor& v, TensorP L, TensorP W1, TensorP W2, TensorP R, bool allow_shard);
   void run_plan(ApplyPlan& p, const double* vin, double* vout);
   TensorP step_left(const Tensor* L, const TensorP& Asite, const Tensor& W);

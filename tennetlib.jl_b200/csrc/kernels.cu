@@ -344,10 +344,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
 
-template <bool KFA, bool KFB, int STAGES>
+// EPI = 0: C = alpha * A B (+ C) in place.  EPI = 1 (multi-GPU): scatter epilogue -- every element is stored into the
+// staging slot of the rank that owns its column (peer memory over NVLink), and the last CTA to finish flags "epoch
+// complete" to every peer (see run_gemm_reduce_scatter).
+template <bool KFA, bool KFB, int STAGES, int EPI>
 __global__ void __launch_bounds__(384, 1)
 gemm_tma_ws_kernel(const TmaTile* __restrict__ tiles, int ntiles, const TmaDesc* __restrict__ maps, double* __restrict__ Cbase,
-                   double alpha, int accum) {
+                   double alpha, int accum, ScatterArgs sargs) {
   constexpr int MI = 8, NI = 4;
   constexpr int TILE_ELEMS = 128 * 16;
   constexpr int STAGE_ELEMS = 2 * TILE_ELEMS;
@@ -462,23 +465,123 @@ gemm_tma_ws_kernel(const TmaTile* __restrict__ tiles, int ntiles, const TmaDesc*
       c_stage = n_stage;
       c_phase = n_phase;
     }
-    double* pC = Cbase + cur.c;
+    if (EPI == 0) {
+      double* pC = Cbase + cur.c;
 #pragma unroll
-    for (int i = 0; i < MI; i++) {
-      const int m = cur.m0 + wm0 + i * 8 + lr;
-      if (m >= cur.M) continue;
+      for (int i = 0; i < MI; i++) {
+        const int m = cur.m0 + wm0 + i * 8 + lr;
+        if (m >= cur.M) continue;
+#pragma unroll
+        for (int j = 0; j < NI; j++) {
+          const int n = cur.n0 + wn0 + j * 8 + 2 * lc;
+          double* c = pC + (int64_t)n * cur.ldc + m;
+          if (n < cur.N) c[0] = accum ? fma(alpha, acc[i][j][0], c[0]) : alpha * acc[i][j][0];
+          if (n + 1 < cur.N) c[cur.ldc] = accum ? fma(alpha, acc[i][j][1], c[cur.ldc]) : alpha * acc[i][j][1];
+        }
+      }
+    } else {
+      const ScatterProb sp = sargs.probs[cur.prob];
+      int2 ri[MI];
+#pragma unroll
+      for (int i = 0; i < MI; i++) {
+        const int m = cur.m0 + wm0 + i * 8 + lr;
+        ri[i] = m < cur.M ? sp.rowinfo[m] : make_int2(-1, 0);
+      }
 #pragma unroll
       for (int j = 0; j < NI; j++) {
-        const int n = cur.n0 + wn0 + j * 8 + 2 * lc;
-        double* c = pC + (int64_t)n * cur.ldc + m;
-        if (n < cur.N) c[0] = accum ? fma(alpha, acc[i][j][0], c[0]) : alpha * acc[i][j][0];
-        if (n + 1 < cur.N) c[cur.ldc] = accum ? fma(alpha, acc[i][j][1], c[cur.ldc]) : alpha * acc[i][j][1];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int n = cur.n0 + wn0 + j * 8 + 2 * lc + e;
+          if (n >= cur.N) continue;
+          const int2 ci = sp.colinfo[n];
+          const int seg = ci.x & 0xffff;
+          double* dst = sargs.peer_slots[ci.x >> 16];
+#pragma unroll
+          for (int i = 0; i < MI; i++) {
+            if (ri[i].x < 0) continue;
+            dst[sp.T[ri[i].x * sp.nseg + seg] + ri[i].y + (int64_t)ci.y * sp.cstride[ri[i].x]] = alpha * acc[i][j][e];
+          }
+        }
       }
     }
     cur = nxt;
   }
 #undef TNL_FRAG_A
 #undef TNL_FRAG_B
+  if (EPI == 1) {
+    // every DMMA thread fences its own remote stores, the 256 of them meet on a named barrier (the producer
+    // warpgroup has exited), and the last CTA of the grid publishes the epoch to every peer
+    __threadfence_system();
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    if (tid == 128) {
+      const unsigned int prev = atomicAdd(sargs.done, 1u);
+      if (prev == gridDim.x - 1) {
+        *sargs.done = 0;
+        __threadfence_system();
+        for (int k = 0; k < sargs.world; k++) {
+          volatile unsigned long long* f = sargs.peer_flags[k] + sargs.rank;       // "ready" word of source `rank` on peer k
+          *f = sargs.epoch;
+        }
+        __threadfence_system();
+      }
+    }
+  }
+}
+
+// ---- fused reduce-scatter: flag waits and the ordered sum over the source slots -----------------------------------
+// flags of one rank: words [0, 64) "ready": source s has delivered epoch e;  words [64, 128) "consumed": destination d
+// has summed (and cleared) what this rank sent it in epoch e
+__global__ void stage_wait_consumed_kernel(const volatile unsigned long long* my_flags, int world, unsigned long long need) {
+  const int k = threadIdx.x;
+  if (k < world) {
+    const long long t0 = clock64();
+    while (my_flags[64 + k] < need) {
+      __nanosleep(100);
+      if (clock64() - t0 > 8000000000ll) __trap();       // a peer died: fail instead of hanging the GPU
+    }
+  }
+}
+// out[i] = sum_s slot_s[i] (s ascending: the same order on every rank and in every run), slots cleared for the next epoch
+__global__ void __launch_bounds__(256)
+stage_reduce_kernel(double* __restrict__ out, double* slots, int64_t slot_cap, int64_t n, int world, volatile unsigned long long* my_flags,
+                    unsigned long long* const* peer_flags, int rank, unsigned long long epoch, unsigned int* done) {
+  if (threadIdx.x < world) {
+    const long long t0 = clock64();
+    while (my_flags[threadIdx.x] < epoch) {
+      __nanosleep(100);
+      if (clock64() - t0 > 8000000000ll) __trap();
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += (int64_t)gridDim.x * blockDim.x * 2) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int s0 = 0; s0 < world; s0 += 8) {          // all loads of up to eight slots in flight before the first add
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        v[u] = s0 + u < world ? __ldcv(reinterpret_cast<const double2*>(slots + (int64_t)(s0 + u) * slot_cap + i)) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        acc.x += v[u].x; acc.y += v[u].y;
+        if (s0 + u < world) *reinterpret_cast<double2*>(slots + (int64_t)(s0 + u) * slot_cap + i) = make_double2(0.0, 0.0);
+      }
+    }
+    *reinterpret_cast<double2*>(out + i) = acc;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {
+      *done = 0;
+      __threadfence_system();
+      for (int k = 0; k < world; k++) {
+        volatile unsigned long long* f = peer_flags[k] + 64 + rank;                // "consumed" word of destination `rank` on peer k
+        *f = epoch;
+      }
+    }
+  }
 }
 
 // ---- host side: descriptor sets ----------------------------------------------------------------
@@ -531,11 +634,12 @@ static const TmaDesc* tma_maps_for(Ctx* ctx, GemmPlan& p, const double* A, const
   return d;
 }
 
-template <bool KFA, bool KFB>
-static void launch_gemm_tma_one(Ctx* ctx, GemmPlan& p, const TmaDesc* maps, double* C, double alpha, int accum) {
+template <bool KFA, bool KFB, int EPI = 0>
+static void launch_gemm_tma_one(Ctx* ctx, GemmPlan& p, const TmaDesc* maps, double* C, double alpha, int accum,
+                                const ScatterArgs& sargs = ScatterArgs()) {
   constexpr int STAGES = 6;
   constexpr size_t SMEM = (size_t)STAGES * 2 * 128 * 16 * sizeof(double) + 2 * STAGES * 8 + 1024;
-  auto kern = gemm_tma_ws_kernel<KFA, KFB, STAGES>;
+  auto kern = gemm_tma_ws_kernel<KFA, KFB, STAGES, EPI>;
   static bool configured = false;
   if (!configured) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -543,7 +647,7 @@ static void launch_gemm_tma_one(Ctx* ctx, GemmPlan& p, const TmaDesc* maps, doub
   }
   const int ntiles = (int)p.tiles_tma.size();
   const int grid = std::min(ntiles, ctx->num_sms);
-  kern<<<grid, 384, SMEM, ctx->stream>>>(p.d_tiles_tma, ntiles, maps, C, alpha, accum);
+  kern<<<grid, 384, SMEM, ctx->stream>>>(p.d_tiles_tma, ntiles, maps, C, alpha, accum, sargs);
   CUDA_OK(cudaGetLastError());
   ctx->cnt.launches++;
   ctx->cnt.gemm_launches++;
@@ -556,6 +660,60 @@ static void launch_gemm_tma(Ctx* ctx, GemmPlan& p, const double* A, const double
   else if (kfa && !kfb) launch_gemm_tma_one<true, false>(ctx, p, maps, C, alpha, accum);
   else if (!kfa && kfb) launch_gemm_tma_one<false, true>(ctx, p, maps, C, alpha, accum);
   else launch_gemm_tma_one<false, false>(ctx, p, maps, C, alpha, accum);
+}
+
+// (output ranges without a contribution -- zero_fill -- need no store in the fused path: the staging slots are zero)
+bool plan_all_tma(const GemmPlan& p) { return !p.tiles_tma.empty() && p.tiles_big.empty() && p.tiles_small.empty(); }
+
+void run_gemm_reduce_scatter(Ctx* ctx, GemmPlan& p, const double* A, const double* B, const ScatterProb* d_scatter, double* out,
+                             int64_t nloc) {
+  Ctx::PeerStage& ps = ctx->pstage;
+  TNL_CHECK(ps.ok && (size_t)nloc <= ps.slot_cap && (nloc & 1) == 0, "staging area not set up for this vector length");
+  TNL_CHECK(plan_all_tma(p) && !p.transA && p.transB, "the fused reduce-scatter needs a plan of 128x128 tiles of A B^T");
+  unsigned long long* my_flags = (unsigned long long*)ps.base;
+  double* my_slots = (double*)((char*)ps.base + 2 * 64 * sizeof(unsigned long long));
+  ps.epoch++;
+  Ctx::ProfRec rec{};
+  const bool prof = ctx->prof_gemm;
+  // nobody may still hold unsummed data of the previous epoch in the slots this rank is about to overwrite
+  {
+    Ctx::Scope prof_scope(ctx, 3);
+    prof_scope.r.tiles = 4;
+    stage_wait_consumed_kernel<<<1, 64, 0, ctx->stream>>>(my_flags, ctx->world, ps.epoch - 1);
+  }
+  if (prof) {
+    CUDA_OK(cudaEventCreate(&rec.a));
+    CUDA_OK(cudaEventCreate(&rec.b));
+    CUDA_OK(cudaEventRecord(rec.a, ctx->stream));
+  }
+  ScatterArgs sa;
+  sa.probs = d_scatter;
+  sa.peer_slots = ps.d_peer_slots;
+  sa.peer_flags = ps.d_peer_flags;
+  sa.done = ps.d_done;
+  sa.epoch = ps.epoch;
+  sa.rank = ctx->rank;
+  sa.world = ctx->world;
+  const TmaDesc* maps = tma_maps_for(ctx, p, A, B);
+  launch_gemm_tma_one<false, false, 1>(ctx, p, maps, nullptr, 1.0, 0, sa);
+  if (prof) {
+    CUDA_OK(cudaEventRecord(rec.b, ctx->stream));
+    rec.flops = p.flops;
+    rec.cat = 0;
+    rec.tiles = (int)p.tiles_tma.size();
+    ctx->prof_recs.push_back(rec);
+  }
+  ctx->cnt.gemm_flops += p.flops;
+  {
+    Ctx::Scope prof_scope(ctx, 3);
+    prof_scope.r.tiles = 5;
+    const int grid = (int)std::min<int64_t>((nloc / 2 + 255) / 256, (int64_t)ctx->num_sms * 8);
+    stage_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(out, my_slots, (int64_t)ps.slot_cap, nloc, ctx->world, my_flags, ps.d_peer_flags,
+                                                        ctx->rank, ps.epoch, ps.d_done);
+    CUDA_OK(cudaGetLastError());
+    ctx->cnt.launches += 2;
+    ctx->cnt.allreduce_bytes += 8.0 * nloc * ctx->world;
+  }
 }
 
 void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C, double alpha, bool accum) {

@@ -176,12 +176,12 @@ class Context:
         cat = (C.c_double * 8)()
         check(self.lib.tnl_profile_categories(self.h, cat), self.h)
         names = ("gemm", "transform", "vector", "collective")
-        coll = (C.c_double * 8)()
+        coll = (C.c_double * 12)()
         check(self.lib.tnl_profile_collectives(self.h, coll), self.h)
-        kinds = ("allreduce_scalar", "reduce_scatter", "allgather", "allreduce_big")
+        kinds = ("allreduce_scalar", "reduce_scatter", "allgather", "allreduce_big", "fused_wait_consumed", "fused_slot_sum")
         return dict(total_ms=ms.value, launches=n.value, flops=fl.value, max_tflops=mx.value,
                     collective_ms={k: coll[i] for i, k in enumerate(kinds)},
-                    collective_calls={k: int(coll[4 + i]) for i, k in enumerate(kinds)},
+                    collective_calls={k: int(coll[6 + i]) for i, k in enumerate(kinds)},
                     category_ms={k: cat[i] for i, k in enumerate(names)},
                     category_launches={k: int(cat[4 + i]) for i, k in enumerate(names[:3])},
                     host_plan_ms_total=cat[7])
