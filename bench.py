@@ -88,6 +88,7 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.first = 0
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -105,12 +106,18 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def mark(self):
+        """Start of the timed region: only samples from here on count.  The process itself is started during the
+        warm-up -- the first nvidia-smi query initialises NVML and can hold the driver for hundreds of milliseconds,
+        which must not land inside the first timed step."""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -334,14 +341,15 @@ def run_ours(args):
 
     energies = []
     bond = b0
+    sampler = ClockSampler(local)
+    sampler.start()                  # NVML start-up happens during the warm-up; samples count from mark() on
     for _ in range(args.warmup):
         e, err, eigs = T.update_position(sysenv, T.eig_solver, bond, 2, "left", **kw)
         bond += 1
     barrier()
     li0 = sysenv.site_tensor(bond).inds[0]
     timed_sectors = {"bond": bond, "qns": [list(q) for q in li0.qns], "dims": list(li0.dims)}
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     ctx.reset_counters()
     sysenv.profile = True
     sysenv.profile_kernels = True

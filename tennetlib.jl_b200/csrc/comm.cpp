@@ -92,13 +92,17 @@ static void stage_release(Ctx* ctx) {
 // Collective: (re)allocates the staging area when a slot of `slot_doubles` does not fit, exchanges the CUDA-IPC handles
 // through the NCCL communicator and maps the peers' areas.  Every rank takes the same decisions (sizes derive from
 // the replicated plan), and a failure on any rank switches the fused path off on all of them.
-constexpr size_t kStageFlagBytes = 2 * 64 * sizeof(unsigned long long);
+// header of a staging area (bytes): [0, 512) "ready" words, [512, 1024) "consumed" words (fused reduce-scatter);
+// [1024, 2048) sequence words [2 parities][64 sources] and [2048, 10240) mailboxes [2][64][8 doubles] of the scalar
+// all-reduce; slots start at 16 KB
+constexpr size_t kStageFlagBytes = 16384;
 bool comm_stage_ensure(Ctx* ctx, size_t slot_doubles) {
   Ctx::PeerStage& ps = ctx->pstage;
   if (ctx->world <= 1 || !ctx->nccl_comm) return false;
   if (ps.tried && !ps.ok) return false;
   if (ps.ok && slot_doubles <= ps.slot_cap) return true;
   if (const char* e = getenv("TNL_FUSED_RS")) if (atoi(e) == 0) { ps.tried = true; ps.ok = false; return false; }
+  if (const char* e = getenv("TNL_PEER_SCALAR_AR")) ps.small_ar = atoi(e) != 0;
   TNL_CHECK(ctx->world <= 64, "staging flags are laid out for at most 64 ranks");
   ps.tried = true;
   ctx->sync();
@@ -160,6 +164,7 @@ bool comm_stage_ensure(Ctx* ctx, size_t slot_doubles) {
   CUDA_OK(cudaMemcpy(ps.d_peer_flags, flags.data(), ctx->world * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemset(ps.d_done, 0, sizeof(unsigned int)));
   ps.epoch = 0;                        // flags were zeroed with the new area
+  ps.ar_epoch = 0;
   ps.ok = true;
   return true;
 }
@@ -176,10 +181,19 @@ void comm_destroy(Ctx* ctx) {
   }
 }
 
+void peer_allreduce_small(Ctx* ctx, double* buf, int n);   // kernels.cu
+
 void comm_allreduce_sum(Ctx* ctx, double* buf, int64_t n) {
   Ctx::Scope prof_scope(ctx, 3);
   prof_scope.r.tiles = n <= 64 ? 0 : 3;            // kind (tnl_profile_collectives)
   TNL_CHECK(ctx->nccl_comm, "communicator not initialised");
+  if (n <= 8 && ctx->pstage.ok && ctx->pstage.small_ar) {
+    // Krylov inner products: a few doubles, latency only -- mailboxes in the peers' staging headers instead of an
+    // NCCL kernel (every rank sums the W contributions in rank order: identical result everywhere)
+    peer_allreduce_small(ctx, buf, (int)n);
+    ctx->cnt.allreduce_bytes += 8.0 * n;
+    return;
+  }
   NCCL_OK(nccl().AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
   ctx->cnt.allreduce_bytes += 8.0 * n;
 }

@@ -64,7 +64,14 @@ void* Ctx::alloc(size_t bytes) {
   void* p = nullptr;
   // + 128 bytes: the chunked TMA view of a ragged GEMM operand may read up to 15 doubles past its last row
   // (kernels.cu, gemm_tma_ws_kernel); the slack keeps that over-read inside the allocation
-  CUDA_OK(cudaMallocAsync(&p, bytes + 128, stream));
+  // Size classes: tensors of neighbouring bonds differ by a few per cent in size; with exact sizes a freed block is
+  // slightly too small for its successor, the pool fragments and every so often has to map fresh physical memory in
+  // the middle of a sweep (one-off 200 ms stalls in make_phi / position, profiles/r02m_*: step_ms_list).  Rounding
+  // large requests up to 16 MB (2 MB for medium ones) lets the successor reuse the block.
+  bytes += 128;
+  const size_t g = bytes >= (size_t(64) << 20) ? (size_t(16) << 20) : bytes >= (size_t(2) << 20) ? (size_t(2) << 20) : 256;
+  bytes = (bytes + g - 1) / g * g;
+  CUDA_OK(cudaMallocAsync(&p, bytes, stream));
   return p;
 }
 void Ctx::free(void* p) {
@@ -130,7 +137,7 @@ GemmPlan::~GemmPlan() {
   if (ctx) { ctx->free(d_probs); ctx->free(d_tiles_big); ctx->free(d_tiles_small); ctx->free(d_tiles_tma); ctx->free(d_maps); }
 }
 TransformPlan::~TransformPlan() {
-  if (ctx) { ctx->free(d_blocks); ctx->free(d_flats); }
+  if (ctx) { ctx->free(d_blocks); ctx->free(d_flats); ctx->free(d_groups); }
 }
 
 // --------------------------------------------------------------------------------------- Tensor
@@ -390,7 +397,13 @@ std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const 
   if (W) TNL_CHECK(W->rank() == nk + nn && W->nrow == W->rank(), "W must be (contracted..., new...) in natural layout");
   // W blocks grouped by their new-sector coordinates
   int64_t col = 0;
+  std::vector<std::vector<int>> keys;              // (leading sector, passive sectors) of every output block
   for (const Block& yb : Y.blocks) {
+    {
+      std::vector<int> key{yb.c[0]};
+      for (int j : passY) key.push_back(yb.c[j]);
+      keys.push_back(std::move(key));
+    }
     XfBlock xb{};
     xb.yoff = yb.off;
     xb.I = yb.d[0];
@@ -452,6 +465,27 @@ std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const 
   }
   plan->ncols = col;
   plan->bytes = 8.0 * ((double)X.logical_elems() + (double)Y.logical_elems());
+  if (W) {
+    // groups of blocks with a common source: stable sort by key, consecutive runs become groups
+    std::vector<size_t> ord(plan->blocks.size());
+    for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+    std::vector<XfBlock> sorted;
+    int64_t c0 = 0;
+    for (size_t k = 0; k < ord.size(); k++) {
+      XfBlock b = plan->blocks[ord[k]];
+      int64_t P = 1;
+      for (int q = 0; q < MAXP; q++) P *= b.pd[q];
+      const bool same = k > 0 && keys[ord[k]] == keys[ord[k - 1]] && plan->groups.back().P == P;
+      if (!same) plan->groups.push_back(XfGroup{c0, P, (int)sorted.size(), 0});
+      plan->groups.back().nb++;
+      b.colstart = c0;
+      c0 += P;
+      sorted.push_back(b);
+    }
+    plan->blocks.swap(sorted);
+    TNL_CHECK(c0 == plan->ncols, "transform groups do not cover the columns");
+  }
   finalize_transform_plan(*plan, W != nullptr);
   return plan;
 }
@@ -476,6 +510,7 @@ void finalize_transform_plan(TransformPlan& p, bool has_w) {
     b.fnum = (int)p.flats.size() - b.fbeg;
   }
   p.pure_copy = !has_w;
+  p.d_groups = p.ctx->upload(p.groups);
   p.d_blocks = p.ctx->upload(p.blocks);
   p.d_flats = p.ctx->upload(p.flats);
 }

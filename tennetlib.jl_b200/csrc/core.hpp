@@ -211,7 +211,13 @@ struct XfFlat {
   int64_t woff;              // W element offset of (this k, n=0)
   int wst;                   // W stride between consecutive n (= Ka of the contribution)
 };
+// Output blocks that read the SAME X columns (same leading and passive sectors, different new-index sectors): the
+// kernel walks a group column-major over (passive column, block), so the warps of a CTA that need one X column run
+// next to each other and the column comes from DRAM once (site operators feed 2-3 output blocks from each column).
+struct XfGroup { int64_t colstart; int64_t P; int first; int nb; };
 struct TransformPlan {
+  std::vector<XfGroup> groups;
+  XfGroup* d_groups = nullptr;
   std::vector<XfBlock> blocks;
   std::vector<XfContrib> contribs;
   std::vector<XfFlat> flats;
@@ -283,6 +289,8 @@ class Ctx {
     unsigned long long** d_peer_flags = nullptr;   // device array [world]: the peers' flag blocks
     unsigned int* d_done = nullptr;     // "last CTA" counter of the scattering GEMM
     unsigned long long epoch = 0;       // number of fused reduce-scatters issued (identical on every rank)
+    unsigned long long ar_epoch = 0;    // number of scalar all-reduces issued through the mailboxes
+    bool small_ar = true;               // scalar all-reduces over the mailboxes (TNL_PEER_SCALAR_AR=0: NCCL)
   } pstage;
   // cuSOLVER (opaque here; factorize.cu owns the type)
   void* cusolver = nullptr;

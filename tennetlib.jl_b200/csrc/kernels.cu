@@ -663,6 +663,44 @@ static void launch_gemm_tma(Ctx* ctx, GemmPlan& p, const double* A, const double
 }
 
 // (output ranges without a contribution -- zero_fill -- need no store in the fused path: the staging slots are zero)
+// Scalar all-reduce over the peers' staging headers (see comm.cpp for the layout): every rank drops its n <= 8 values
+// into mailbox [epoch parity][rank] of every peer, bumps the sequence word, waits for the W sequence words of its own
+// header and sums the mailboxes in rank order.  Two parities are enough: a rank can only be one all-reduce ahead of the
+// slowest one, because completing epoch e needs everybody's contribution to e.
+__global__ void peer_allreduce_small_kernel(double* vals, int n, unsigned long long* const* peer_hdr, unsigned long long* my_hdr,
+                                            int rank, int world, unsigned long long epoch) {
+  const int k = threadIdx.x;
+  const int par = (int)(epoch & 1);
+  if (k < world) {
+    volatile double* mail = reinterpret_cast<volatile double*>(reinterpret_cast<char*>(peer_hdr[k]) + 2048) + (par * 64 + rank) * 8;
+    for (int j = 0; j < n; j++) mail[j] = vals[j];
+    __threadfence_system();
+    volatile unsigned long long* seq = peer_hdr[k] + 128 + par * 64 + rank;
+    *seq = epoch;
+    volatile unsigned long long* mine = my_hdr + 128 + par * 64 + k;
+    const long long t0 = clock64();
+    while (*mine < epoch) {
+      if (clock64() - t0 > 8000000000ll) __trap();
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  if (k < n) {
+    const double* mail = reinterpret_cast<const double*>(reinterpret_cast<const char*>(my_hdr) + 2048) + par * 64 * 8;
+    double s = 0.0;
+    for (int src = 0; src < world; src++) s += __ldcv(mail + src * 8 + k);
+    vals[k] = s;
+  }
+}
+void peer_allreduce_small(Ctx* ctx, double* buf, int n) {
+  Ctx::PeerStage& ps = ctx->pstage;
+  ps.ar_epoch++;
+  peer_allreduce_small_kernel<<<1, 64, 0, ctx->stream>>>(buf, n, ps.d_peer_flags, (unsigned long long*)ps.base, ctx->rank, ctx->world,
+                                                          ps.ar_epoch);
+  CUDA_OK(cudaGetLastError());
+  ctx->cnt.launches++;
+}
+
 bool plan_all_tma(const GemmPlan& p) { return !p.tiles_tma.empty() && p.tiles_big.empty() && p.tiles_small.empty(); }
 
 void run_gemm_reduce_scatter(Ctx* ctx, GemmPlan& p, const double* A, const double* B, const ScatterProb* d_scatter, double* out,
@@ -671,7 +709,7 @@ void run_gemm_reduce_scatter(Ctx* ctx, GemmPlan& p, const double* A, const doubl
   TNL_CHECK(ps.ok && (size_t)nloc <= ps.slot_cap && (nloc & 1) == 0, "staging area not set up for this vector length");
   TNL_CHECK(plan_all_tma(p) && !p.transA && p.transB, "the fused reduce-scatter needs a plan of 128x128 tiles of A B^T");
   unsigned long long* my_flags = (unsigned long long*)ps.base;
-  double* my_slots = (double*)((char*)ps.base + 2 * 64 * sizeof(unsigned long long));
+  double* my_slots = (double*)((char*)ps.base + 16384);        // kStageFlagBytes (comm.cpp)
   ps.epoch++;
   Ctx::ProfRec rec{};
   const bool prof = ctx->prof_gemm;
@@ -827,18 +865,21 @@ void gemm_selftest(Ctx* ctx, int M, int N, int K, bool ta, bool tb, int reps, bo
 // flight per warp was latency bound at ~50 % of the HBM roofline, profiles/r01b_ncu_hbm.md).
 constexpr int XF_FB = 4;
 __global__ void __launch_bounds__(256)
-transform_kernel(const XfBlock* __restrict__ blocks, int nblocks, const XfFlat* __restrict__ flats,
+transform_kernel(const XfGroup* __restrict__ groups, int ngroups, const XfBlock* __restrict__ blocks, const XfFlat* __restrict__ flats,
                     const double* __restrict__ X, double* __restrict__ Y, const double* __restrict__ W, int64_t ncols) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; col < ncols; col += nwarps) {
-    int lo = 0, hi = nblocks - 1;
+    // work item = (group, passive column, block of the group), block fastest: neighbouring warps share their X columns
+    int lo = 0, hi = ngroups - 1;
     while (lo < hi) {
       int mid = (lo + hi + 1) >> 1;
-      if (blocks[mid].colstart <= col) lo = mid; else hi = mid - 1;
+      if (groups[mid].colstart <= col) lo = mid; else hi = mid - 1;
     }
-    const XfBlock& b = blocks[lo];
-    int64_t t = col - b.colstart;
+    const XfGroup g = groups[lo];
+    const int64_t tg = col - g.colstart;
+    const XfBlock& b = blocks[g.first + (int)(tg % g.nb)];
+    int64_t t = tg / g.nb;
     int64_t ybase = b.yoff;
     int pidx[MAXP];
 #pragma unroll
@@ -959,7 +1000,7 @@ void run_transform(Ctx* ctx, TransformPlan& p, const double* X, double* Y, const
   if (!W) {
     relayout_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_flats, X, Y, p.ncols);
   } else {
-    transform_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_flats, X, Y, W, p.ncols);
+    transform_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_groups, (int)p.groups.size(), p.d_blocks, p.d_flats, X, Y, W, p.ncols);
   }
   CUDA_OK(cudaGetLastError());
   ctx->cnt.launches++;
