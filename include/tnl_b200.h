@@ -67,8 +67,11 @@ int tnl_profile_collectives(tnl_ctx_t ctx, double* out12);
 /* ---- multi-GPU: one process per GPU, sharded H_eff apply ----------------
  * rank 0 calls tnl_comm_unique_id, the 128 bytes are broadcast by the host (torch.distributed / MPI), every rank
  * calls tnl_comm_init.  Afterwards tnl_heff_apply / tnl_eigsolve_lanczos shard the two-site apply over the right
- * link (each rank owns tnl_shard_range of every sector) and combine the partial results with ncclReduceScatter
- * (Krylov vectors stay sharded; inner products are scalar all-reduces, the result vector one all-gather).
+ * link (each rank owns tnl_shard_range of every sector).  The partial results are combined inside the last GEMM of the
+ * apply: its epilogue stores every tile into the owner rank's staging slot over NVLink (CUDA-IPC peer memory) and a
+ * small kernel sums the slots in rank order; if peer memory cannot be set up (or TNL_FUSED_RS=0) the same exchange is a
+ * pack pass + ncclReduceScatter.  Krylov vectors stay sharded; inner products are scalar all-reduces, the result
+ * vector one all-gather; the environment update shards over a link index and all-gathers the slices.
  * All ranks must hold identical replicated state and issue the same calls. */
 int tnl_comm_unique_id(char* out128);
 int tnl_comm_init(tnl_ctx_t ctx, const char* uid128, int32_t rank, int32_t world);
