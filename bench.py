@@ -573,8 +573,10 @@ def run_ours(args):
             "data": "synthetic",
             "config": dict(workload_config(args),
                            parallelism=("H_eff apply + Krylov vectors sharded over the right link across %d GPUs "
-                                        "(NCCL reduce-scatter per apply, scalar all-reduces, one all-gather per "
-                                        "eig_solver); truncation groups distributed; env update replicated" % world)
+                                        "(T3 R^T GEMM fused with the reduce-scatter over peer memory -- NCCL "
+                                        "reduce-scatter if peer memory is unavailable --, scalar all-reduces, one "
+                                        "all-gather per eig_solver); truncation groups distributed; env update sharded "
+                                        "over a link index + all-gather" % world)
                            if sharded else ("replicas x%d" % world if world > 1 else "single GPU"),
                            first_timed_bond=b0 + args.warmup),
             "sweep": sweep, "truncation_decaying_spectrum": trunc_decay, "timed_bond_sectors": timed_sectors,

@@ -791,6 +791,13 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
   } else {
     throw Error(2, "nsite must be 0, 1 or 2");
   }
+  if (cp) {
+    // planar complex arithmetic: a (complex environment) x (complex tensor) product is four real GEMM launches (8mnk),
+    // a real environment two (4mnk); the site-operator passes run once per plane
+    const double fl = p->L && p->L->cplx ? 4.0 : 2.0, fr = p->R && p->R->cplx ? 4.0 : 2.0;
+    const double xf = p->flops - (p->g1 ? p->g1->flops : 0.0) - (p->g4 ? p->g4->flops : 0.0);
+    p->flops = fl * (p->g1 ? p->g1->flops : 0.0) + fr * (p->g4 ? p->g4->flops : 0.0) + 2.0 * xf;
+  }
   p->nelem = vfull.nelem;
   p->epoch = ctx->slot_epoch;
   return p;

@@ -23,9 +23,18 @@ def eig_solver(env, phi0, time_step=None, **kwargs):
           env.ctx.h)
     env.last_solver_info = dict(converged=conv.value, numops=nops.value, numiter=nit.value, normres=nres.value,
                                 apply_flops=env.apply_flops())
+    _accumulate(env)
     if kwargs.get("solver_check_convergence", False) and conv.value < 1:
         raise RuntimeError("`eig_solver()` not converged !!")
     return ev.value, phi0
+
+
+def _accumulate(env):
+    """running totals over every solver call on this environment (a TDVP update makes up to three: two-site forward,
+    one-site / zero-site backward) -- what the workload benches divide by the solver time"""
+    info = env.last_solver_info
+    env.solver_numops_total = getattr(env, "solver_numops_total", 0) + info["numops"]
+    env.solver_flops_total = getattr(env, "solver_flops_total", 0.0) + info["apply_flops"] * info["numops"]
 
 
 def exp_solver(env, phi0, time_step, **kwargs):
@@ -48,6 +57,7 @@ def exp_solver(env, phi0, time_step, **kwargs):
           env.ctx.h)
     env.last_solver_info = dict(converged=conv.value, numops=nops.value, numiter=nit.value, normres=err.value,
                                 apply_flops=env.apply_flops())
+    _accumulate(env)
     if kwargs.get("solver_check_convergence", False) and conv.value < 1:
         raise RuntimeError("`eig_solver()` not converged !!")      # message as in the reference (solver.jl:84)
     return float("nan"), phi0

@@ -120,15 +120,15 @@ def run(args, ClockSampler, fp64_peak):
     ctx.profile_gemm(True)
     ctx.profile_read()
     fl, nops, steps_ms, energies = 0.0, 0, [], []
+    fl0, nops0 = getattr(sysenv, "solver_flops_total", 0.0), getattr(sysenv, "solver_numops_total", 0)
     for _ in range(args.steps):
         ctx.timer_start(1)
         e, err, eigs = T.update_position(sysenv, solver, bond, 2, "left", **kw)
         steps_ms.append(ctx.timer_stop(1))
         energies.append(e)
-        info = sysenv.last_solver_info
-        nops += info["numops"]
-        fl += info["apply_flops"] * info["numops"]
         bond += 1
+    # every solver call of the update counts (TDVP: two-site forward + one-site backward), not only the last one
+    fl, nops = sysenv.solver_flops_total - fl0, sysenv.solver_numops_total - nops0
     clocks = sampler.stop()
     cnt = ctx.counters()
     ctx.profile_read()
