@@ -134,7 +134,10 @@ double* Ctx::arena_alloc(size_t nelem, bool* from_arena) {
 }
 
 GemmPlan::~GemmPlan() {
-  if (ctx) { ctx->free(d_probs); ctx->free(d_tiles_big); ctx->free(d_tiles_small); ctx->free(d_tiles_tma); ctx->free(d_maps); }
+  if (ctx) {
+    ctx->free(d_probs); ctx->free(d_tiles_big); ctx->free(d_tiles_small); ctx->free(d_tiles_tma); ctx->free(d_maps);
+    ctx->free(d_splits); ctx->free(d_splitws);
+  }
 }
 TransformPlan::~TransformPlan() {
   if (ctx) { ctx->free(d_blocks); ctx->free(d_flats); ctx->free(d_groups); }
@@ -261,13 +264,57 @@ static void make_tiles(GemmPlan& plan) {
       for (int nb = 0; nb < nt; nb += GN)
         for (int mi = 0; mi < mt; mi++)
           for (int ni = nb; ni < std::min(nt, nb + GN); ni++)
-            plan.tiles_tma.push_back(TmaTile{p.c, mi * 128, ni * 128, p.M, p.N, kt, p.ldc, pi, 0});
+            plan.tiles_tma.push_back(TmaTile{p.c, mi * 128, ni * 128, p.M, p.N, kt, p.ldc, pi, 0, 0, 0});
       continue;
     }
     int bm = big ? 128 : 64, bn = big ? 128 : 64;
     auto& tl = big ? plan.tiles_big : plan.tiles_small;
     for (int n0 = 0; n0 < p.N; n0 += bn)
       for (int m0 = 0; m0 < p.M; m0 += bm) tl.push_back(GemmTile{pi, m0, n0});
+  }
+  // Split-K: a plan that cannot fill the machine with output tiles but has a long contracted range (environment
+  // updates of tree nodes: M = N = chi, K = chi^2; Gram matrices of skinny blocks) runs at tiles / #SMs of the DMMA
+  // rate -- 1 TFLOP/s for 256 x 256 x 65536.  Every 128x128 tile is cut into S parts along K (at least 32 k-tiles
+  // each) so that about two waves of tiles exist; the parts go to a workspace and are summed in order afterwards.
+  const int sms = plan.ctx->num_sms;
+  if (!plan.tiles_tma.empty() && (int)plan.tiles_tma.size() < sms) {
+    int ktmax = 0;
+    for (auto& t : plan.tiles_tma) ktmax = std::max(ktmax, t.ktiles);
+    const int S0 = (2 * sms + (int)plan.tiles_tma.size() - 1) / (int)plan.tiles_tma.size();
+    if (ktmax >= 64 && S0 >= 2) {
+      std::vector<TmaTile> cut;
+      std::map<int, int> split_of;                   // problem -> index in plan.splits
+      int64_t ws = 0;
+      for (const TmaTile& t : plan.tiles_tma) {
+        const int S = std::max(1, std::min(S0, t.ktiles / 32));
+        if (S < 2) { cut.push_back(t); continue; }
+        const auto& p = plan.probs[t.prob];
+        auto it = split_of.find(t.prob);
+        if (it == split_of.end()) {
+          const int ldw = (p.M + 1) & ~1;
+          plan.splits.push_back(SplitDesc{p.c, ws, p.M, p.N, p.ldc, ldw, S, 0});
+          it = split_of.emplace(t.prob, (int)plan.splits.size() - 1).first;
+          ws += (int64_t)S * ldw * p.N;
+        }
+        const SplitDesc& sd = plan.splits[it->second];
+        const int per = (t.ktiles + sd.S - 1) / sd.S;
+        for (int s = 0; s < sd.S; s++) {
+          TmaTile u = t;
+          u.kt0 = s * per;
+          u.ktiles = std::max(0, std::min(per, t.ktiles - u.kt0));
+          u.c = sd.ws + (int64_t)s * sd.ldw * p.N;
+          u.ldc = sd.ldw;
+          u.split = 1;
+          if (u.ktiles == 0) { u.ktiles = 1; u.kt0 = t.ktiles; }   // beyond K: the TMA zero-fills, the part is zero
+          cut.push_back(u);
+        }
+      }
+      if (!plan.splits.empty()) {
+        plan.tiles_tma.swap(cut);
+        plan.d_splitws = (double*)plan.ctx->alloc((size_t)ws * sizeof(double));
+        plan.d_splits = plan.ctx->upload(plan.splits);
+      }
+    }
   }
   plan.d_probs = plan.ctx->upload(plan.probs);
   plan.d_tiles_big = plan.ctx->upload(plan.tiles_big);
@@ -280,6 +327,7 @@ static void make_tiles(GemmPlan& plan) {
 // Re-tile a plan so that EVERY problem runs on the persistent TMA kernel (the fused GEMM -> reduce-scatter needs a
 // single kernel with the scatter epilogue; small sectors become partially filled 128x128 tiles, zero-filled by the TMA)
 void gemm_plan_force_tma(GemmPlan& plan) {
+  TNL_CHECK(plan.splits.empty(), "a split-K plan cannot take the scatter epilogue");
   if (plan.tiles_big.empty() && plan.tiles_small.empty()) return;
   Ctx* ctx = plan.ctx;
   std::vector<char> have(plan.probs.size(), 0);
@@ -289,7 +337,7 @@ void gemm_plan_force_tma(GemmPlan& plan) {
     const auto& p = plan.probs[pi];
     const int kt = (p.K + 15) / 16;
     for (int n0 = 0; n0 < p.N; n0 += 128)
-      for (int m0 = 0; m0 < p.M; m0 += 128) plan.tiles_tma.push_back(TmaTile{p.c, m0, n0, p.M, p.N, kt, p.ldc, (int)pi, 0});
+      for (int m0 = 0; m0 < p.M; m0 += 128) plan.tiles_tma.push_back(TmaTile{p.c, m0, n0, p.M, p.N, kt, p.ldc, (int)pi, 0, 0, 0});
   }
   plan.tiles_big.clear();
   plan.tiles_small.clear();

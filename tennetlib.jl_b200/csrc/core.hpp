@@ -141,7 +141,12 @@ struct GemmProblem {          // C[M x N] = op(A)[M x K] * op(B)[K x N], column-
 };
 struct GemmTile { int prob; int m0; int n0; };
 // 128x128 output tile of the persistent TMA kernel: everything a CTA needs without a second (dependent) load
-struct TmaTile { int64_t c; int m0, n0, M, N, ktiles, ldc, prob, pad; };
+// `kt0` / `ktiles`: the tile's range of 16-wide k-tiles.  Split-K tiles (`split` != 0) cover a part of K and store their
+// partial result into the plan's workspace (c = offset there, ldc = its leading dimension); a reduction kernel sums
+// the parts in order afterwards.
+struct TmaTile { int64_t c; int m0, n0, M, N, ktiles, ldc, prob, kt0, split, pad; };
+// one split problem: C[M x N] (+)= alpha * sum_s ws[s]   with ws[s] = workspace + ws + s * ldw * N
+struct SplitDesc { int64_t c, ws; int M, N, ldc, ldw, S, pad; };
 
 struct GemmPlan {
   bool transA = false, transB = false;
@@ -159,6 +164,10 @@ struct GemmPlan {
   struct MapSet { const double* A; const double* B; };
   std::vector<MapSet> mapsets;
   void* d_maps = nullptr;               // MAPSETS_MAX x 2*probs.size() descriptors
+  // split-K (few output tiles, long K: environment updates of tree nodes, Gram matrices of skinny blocks)
+  std::vector<SplitDesc> splits;
+  SplitDesc* d_splits = nullptr;
+  double* d_splitws = nullptr;
   std::vector<std::pair<int64_t, int64_t>> zero_fill;   // (offset, count) of C ranges with no contribution
   double flops = 0;
   Ctx* ctx = nullptr;

@@ -350,7 +350,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 template <bool KFA, bool KFB, int STAGES, int EPI>
 __global__ void __launch_bounds__(384, 1)
 gemm_tma_ws_kernel(const TmaTile* __restrict__ tiles, int ntiles, const TmaDesc* __restrict__ maps, double* __restrict__ Cbase,
-                   double alpha, int accum, ScatterArgs sargs) {
+                   double* __restrict__ Wbase, double alpha, int accum, ScatterArgs sargs) {
   constexpr int MI = 8, NI = 4;
   constexpr int TILE_ELEMS = 128 * 16;
   constexpr int STAGE_ELEMS = 2 * TILE_ELEMS;
@@ -377,9 +377,9 @@ gemm_tma_ws_kernel(const TmaTile* __restrict__ tiles, int ntiles, const TmaDesc*
       int stage = 0;
       uint32_t phase = 1;                          // a fresh mbarrier passes a wait on parity 1
       for (int ti = blockIdx.x; ti < ntiles; ti += G) {
-        const int m0 = tiles[ti].m0, n0 = tiles[ti].n0, ktiles = tiles[ti].ktiles;
+        const int m0 = tiles[ti].m0, n0 = tiles[ti].n0, kt1 = tiles[ti].kt0 + tiles[ti].ktiles;
         const TmaDesc* ma = maps + 2 * tiles[ti].prob;
-        for (int kt = 0; kt < ktiles; kt++) {
+        for (int kt = tiles[ti].kt0; kt < kt1; kt++) {
           mbar_wait(empty0 + 8 * stage, phase);
           const uint32_t bar = full0 + 8 * stage;
           const uint32_t dA = base_u32 + stage * STAGE_BYTES, dB = dA + TILE_ELEMS * 8;
@@ -466,7 +466,10 @@ gemm_tma_ws_kernel(const TmaTile* __restrict__ tiles, int ntiles, const TmaDesc*
       c_phase = n_phase;
     }
     if (EPI == 0) {
-      double* pC = Cbase + cur.c;
+      // split-K part: raw partial product into the workspace (alpha and the accumulate mode are applied by the reduction)
+      double* pC = (cur.split ? Wbase : Cbase) + cur.c;
+      const double al = cur.split ? 1.0 : alpha;
+      const int ac = cur.split ? 0 : accum;
 #pragma unroll
       for (int i = 0; i < MI; i++) {
         const int m = cur.m0 + wm0 + i * 8 + lr;
@@ -475,8 +478,8 @@ gemm_tma_ws_kernel(const TmaTile* __restrict__ tiles, int ntiles, const TmaDesc*
         for (int j = 0; j < NI; j++) {
           const int n = cur.n0 + wn0 + j * 8 + 2 * lc;
           double* c = pC + (int64_t)n * cur.ldc + m;
-          if (n < cur.N) c[0] = accum ? fma(alpha, acc[i][j][0], c[0]) : alpha * acc[i][j][0];
-          if (n + 1 < cur.N) c[cur.ldc] = accum ? fma(alpha, acc[i][j][1], c[cur.ldc]) : alpha * acc[i][j][1];
+          if (n < cur.N) c[0] = ac ? fma(al, acc[i][j][0], c[0]) : al * acc[i][j][0];
+          if (n + 1 < cur.N) c[cur.ldc] = ac ? fma(al, acc[i][j][1], c[cur.ldc]) : al * acc[i][j][1];
         }
       }
     } else {
@@ -634,6 +637,24 @@ static const TmaDesc* tma_maps_for(Ctx* ctx, GemmPlan& p, const double* A, const
   return d;
 }
 
+// C (+)= alpha * sum_s ws[s], parts added in order (deterministic)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const SplitDesc* __restrict__ sd, int nsplit, double* __restrict__ C, const double* __restrict__ W, double alpha, int accum) {
+  for (int q = blockIdx.y; q < nsplit; q += gridDim.y) {
+    const SplitDesc d = sd[q];
+    const int64_t tot = (int64_t)d.M * d.N, part = (int64_t)d.ldw * d.N;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+      const int m = (int)(e % d.M);
+      const int64_t n = e / d.M;
+      const double* w = W + d.ws + n * d.ldw + m;
+      double s = 0.0;
+      for (int k = 0; k < d.S; k++) s += w[(int64_t)k * part];
+      double* c = C + d.c + n * d.ldc + m;
+      *c = accum ? fma(alpha, s, *c) : alpha * s;
+    }
+  }
+}
+
 template <bool KFA, bool KFB, int EPI = 0>
 static void launch_gemm_tma_one(Ctx* ctx, GemmPlan& p, const TmaDesc* maps, double* C, double alpha, int accum,
                                 const ScatterArgs& sargs = ScatterArgs()) {
@@ -647,7 +668,15 @@ static void launch_gemm_tma_one(Ctx* ctx, GemmPlan& p, const TmaDesc* maps, doub
   }
   const int ntiles = (int)p.tiles_tma.size();
   const int grid = std::min(ntiles, ctx->num_sms);
-  kern<<<grid, 384, SMEM, ctx->stream>>>(p.d_tiles_tma, ntiles, maps, C, alpha, accum, sargs);
+  kern<<<grid, 384, SMEM, ctx->stream>>>(p.d_tiles_tma, ntiles, maps, C, p.d_splitws, alpha, accum, sargs);
+  if (!p.splits.empty()) {
+    TNL_CHECK(EPI == 0, "split-K parts cannot be scattered");
+    int64_t big = 0;
+    for (auto& d : p.splits) big = std::max<int64_t>(big, (int64_t)d.M * d.N);
+    dim3 rg((unsigned)std::min<int64_t>((big + 255) / 256, 1184), (unsigned)std::min<size_t>(p.splits.size(), 64));
+    splitk_reduce_kernel<<<rg, 256, 0, ctx->stream>>>(p.d_splits, (int)p.splits.size(), C, p.d_splitws, alpha, accum);
+    ctx->cnt.launches++;
+  }
   CUDA_OK(cudaGetLastError());
   ctx->cnt.launches++;
   ctx->cnt.gemm_launches++;

@@ -265,3 +265,47 @@ def test_complex_one_site_dmrg_with_noise_matches_oracle(ctx):
     Ed, _, sw_d = T.dmrg1(ctx, psi0.t, H, T.DMRGParams(**prm), outputlevel=0)
     assert sw_d.maxchi == sw_o.maxchi
     assert np.allclose(sw_d.energy, sw_o.energy, rtol=1e-7, atol=0)
+
+
+# ------------------------------------------------------------------- SM partitions of the truncation, split-K GEMM
+@pytest.mark.parametrize("parts", ["4,2,2,1", "3,3,3", "5,4"])
+def test_sm_partitions_do_not_change_the_truncation(ctx, monkeypatch, parts):
+    """The per-charge-group eigendecompositions run on SM partitions (green contexts, csrc/factorize.cu syevd_batch);
+    whatever the partition set, `replacebond!` must give the spectrum / truncation error / link sectors of the
+    whole-device run (TNL_EIGH_PARTS=0) and the same two-site tensor."""
+    T, pm, ob, od, ok, om, op = _imports()
+    N, chi, pos = 8, 300, 4
+    sites = om.siteinds("S=1", N)
+    H = om.heisenberg_mpo(sites)
+    qn, dm = om.gaussian_link_sectors(chi, 1.3, 5)
+    mps = od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(31)))
+    od.orthogonalize(mps, pos)
+    phi_o = ob.contract(mps[pos], mps[pos + 1])
+    phi_o = phi_o.scale(1 / phi_o.norm())
+    out = {}
+    for setting in ("0", parts):
+        monkeypatch.setenv("TNL_EIGH_PARTS", setting)
+        env_d = T.StateEnvs(ctx, mps.t, H, llim=pos - 1, rlim=pos + 1)
+        env_d.set_nsite(2)
+        env_d.position(pos)
+        phi_d = T.DeviceTensor.from_host(ctx, phi_o, nrow=1)
+        terr, eigs = env_d.replacebond(pos, phi_d, maxdim=200, mindim=1, cutoff=1e-14, noise=0.0, ortho="left",
+                                       normalize=True, which_decomp="svd")
+        A1 = env_d.site_tensor(pos).to_host().to_dense(); A2 = env_d.site_tensor(pos + 1).to_host().to_dense()
+        link = env_d.site_tensor(pos).inds[2]
+        out[setting] = (terr, np.array(eigs), np.tensordot(A1, A2, axes=([2], [0])), (link.qns, link.dims))
+    a, b = out["0"], out[parts]
+    assert a[3] == b[3]
+    assert abs(a[0] - b[0]) < 1e-13 and np.abs(a[1] - b[1]).max() < 1e-13
+    assert rel(b[2], a[2]) < 1e-10
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 20000), (129, 300, 5000), (100, 100, 4097), (400, 130, 1030), (256, 64, 30000)])
+def test_split_k_gemm_matches_the_reference_kernel(ctx, shape):
+    """Plans with fewer output tiles than SMs and a long contracted range are cut along K (csrc/core.cpp make_tiles,
+    splitk_reduce_kernel): same result as the scalar reference kernel for every transpose combination."""
+    M, N, K = shape
+    for ta in (0, 1):
+        for tb in (0, 1):
+            ms, err = ctx.gemm_selftest(M, N, K, ta, tb, 1, True)
+            assert err < 1e-13 * K, (shape, ta, tb, err)

@@ -1,12 +1,15 @@
 mkdir -p gpurun_out
-for n in 4 8; do
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n bench.py --gpus $n --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02o_bench_n$n.json 2> gpurun_out/r02o_bench_n$n.err
-tail -2 gpurun_out/r02o_bench_n$n.err
-python - <<PY
+timeout 300 python tools/gemm_bench.py 2>&1 | tail -9
+timeout 300 python tools/_gemm_shapes.py 2>&1 | grep "65536)\|, 256, 0, 0)\|, 512, 0, 0)" | head -8
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+timeout 600 python bench.py --workload ttn_tfi --chi 256 --steps 4 --warmup 3 > gpurun_out/r02p_ttn_chi256.json 2> gpurun_out/r02p_ttn.err
+timeout 900 python bench.py --workload hubbard_tdvp --chi 2048 --steps 3 --warmup 3 > gpurun_out/r02p_hubbard_chi2048.json 2> gpurun_out/r02p_hubbard.err
+python - <<'PY'
 import json
-d=json.loads([l for l in open('gpurun_out/r02o_bench_n$n.json').read().splitlines() if l.startswith('{')][-1])
-print("N=$n", {k:d.get(k) for k in ('value','ms_per_step','phase_ms_per_step','energies','parity','sweep_time_s','step_ms_list')})
-print(d.get('collectives_rank0_per_step'))
-print(d.get('device_ms_per_step_by_phase_and_kernel_class',{}).get('solver'))
+for f in ('ttn_chi256','hubbard_chi2048'):
+    try:
+        d=json.loads([l for l in open('gpurun_out/r02p_%s.json'%f).read().splitlines() if l.startswith('{')][-1])
+        print(f, d.get('value'), d.get('ms_per_step'), d.get('phase_ms_per_step'), d['roofline']['frac'], d.get('device_ms_per_step_by_kernel_class'), d.get('apply_gflop'), d.get('applies_per_step'))
+    except Exception as e:
+        print(f, 'failed', e)
 PY
-done

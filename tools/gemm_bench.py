@@ -7,7 +7,8 @@ ctx = T.Context()
 print("== correctness (odd sizes, all transposes)")
 worst = 0.0
 for (M, N, K) in ((1, 1, 1), (7, 5, 3), (129, 65, 17), (255, 257, 33), (385, 1254, 935), (130, 300, 1000), (128, 128, 16),
-                  (129, 200, 64), (300, 257, 100), (1000, 1000, 1001), (66, 4000, 15), (2000, 70, 333)):
+                  (129, 200, 64), (300, 257, 100), (1000, 1000, 1001), (66, 4000, 15), (2000, 70, 333),
+                  (256, 256, 20000), (129, 300, 5000), (100, 100, 4097), (400, 130, 1030)):
     for ta in (0, 1):
         for tb in (0, 1):
             ms, err = ctx.gemm_selftest(M, N, K, ta, tb, 1, True)
