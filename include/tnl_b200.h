@@ -92,8 +92,8 @@ int tnl_tensor_import(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t
  * NDTensors' interleaved (re, im) storage (offsets count complex elements); on the device the tensor is PLANAR --
  * two real planes in the same charge-fused layout -- so every contraction stays on the FP64 DMMA kernels.
  * tnl_tensor_export writes 2 * nelem doubles for a complex tensor.  Site operators (MPO / CouplingModel tensors)
- * are real.  eig_solver, exp_solver, the noise term, penalties and the gauge moves accept complex states; only the
- * multi-GPU sharding is Float64-only (complex vectors run replicated). */
+ * are real.  eig_solver, exp_solver, the noise term, penalties and the gauge moves accept complex states.  Complex
+ * vectors shard plane by plane (pack + ncclReduceScatter per plane; the fused GEMM epilogue serves Float64). */
 int tnl_tensor_import_c128(tnl_ctx_t ctx, int32_t rank, int32_t nq, const tnl_index_t* inds, int64_t nblocks,
                            const int32_t* coords, const int64_t* offsets, const double* data_re_im, int32_t nrow,
                            tnl_tensor_t* out);

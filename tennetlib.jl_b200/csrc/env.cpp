@@ -649,7 +649,8 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
     const Tensor* vin = &v;
     // bonds near the chain ends (right link smaller than 64 per rank) run replicated: every rank computes the
     // identical full result, no collective
-    if (ctx->shard_world() > 1 && allow_shard && p->L && p->R && !cp && v.inds[3].dim() >= 64 * (int64_t)ctx->world) {
+    // (complex vectors shard plane by plane; penalised complex states stay replicated)
+    if (ctx->shard_world() > 1 && allow_shard && p->L && p->R && !(cp && !pens.empty()) && v.inds[3].dim() >= 64 * (int64_t)ctx->world) {
       // Sharded apply: every rank owns a contiguous share of each sector of the right
       // link r.  It contracts L with its slice of v, carries the slice through the site operators and contracts
       // with its slice of R over (w, r_local): a partial H_eff v of full size, summed by one NCCL all-reduce.
@@ -669,15 +670,16 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
           shard_range(r.dims[s], ctx->world, s, k, &st, &cnt);
           if (cnt > 0) { rl.dims.push_back(cnt); rl.qns.push_back(r.qns[s]); sms[k].orig.push_back(s); sms[k].start.push_back(st); }
         }
-        qloc[k] = std::make_shared<Tensor>(ctx, std::vector<Index>{v.inds[0], v.inds[1], v.inds[2], rl}, 1, false);
+        qloc[k] = std::make_shared<Tensor>(ctx, std::vector<Index>{v.inds[0], v.inds[1], v.inds[2], rl}, 1, false, cp);
         p->nloc = std::max(p->nloc, qloc[k]->nelem);
       }
       const SliceMap& sm = sms[ctx->rank];
       p->vloc = qloc[ctx->rank];
       p->xs = plan_transform(v, *p->vloc, {0, 1, 2, 3}, nullptr, {}, &sm);
-      p->packed = ctx->scratch(Ctx::SLOT_PACKED, (size_t)p->nloc * ctx->world, true);
-      p->loc_in = ctx->scratch(Ctx::SLOT_LOCIN, (size_t)p->nloc, true);
-      p->loc_out = ctx->scratch(Ctx::SLOT_LOCOUT, (size_t)p->nloc, true);
+      const size_t npl = cp ? 2 : 1;                               // planes of a (planar) complex vector
+      p->packed = ctx->scratch(Ctx::SLOT_PACKED, (size_t)p->nloc * ctx->world * npl, true);
+      p->loc_in = ctx->scratch(Ctx::SLOT_LOCIN, (size_t)p->nloc * npl, true);
+      p->loc_out = ctx->scratch(Ctx::SLOT_LOCOUT, (size_t)p->nloc * npl, true);
       for (int k = 0; k < ctx->world; k++) p->unpack.push_back(plan_scatter(*qloc[k], Qfull, sms[k]));
       // pack plans need P: built below once P exists (same slice maps on P's last index)
       p->pack_maps = sms;
@@ -686,9 +688,9 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
       rlR.dir = Rf.inds[2].dir;
       SliceMap sr = sm;
       sr.ypos = 2;
-      auto Rloc = mk(ctx, {Rf.inds[0], Rf.inds[1], rlR}, 1);
+      auto Rloc = mk(ctx, {Rf.inds[0], Rf.inds[1], rlR}, 1, Rf.cplx);
       auto xr = plan_transform(Rf, *Rloc, {0, 1, 2}, nullptr, {}, &sr);
-      run_transform(ctx, *xr, Rf.d, Rloc->d, nullptr);
+      run_transform_c(ctx, *xr, Rf, *Rloc, nullptr);
       ctx->sync();
       p->R = Rloc;
       vin = p->vloc.get();
@@ -809,7 +811,7 @@ std::shared_ptr<Env::ApplyPlan> Env::make_plan(const Tensor& vfull, TensorP Lp, 
 // column side: owner rank and column inside its share.  Falls back to pack + ncclReduceScatter when the staging
 // area cannot be set up or the plan has tiles the TMA kernel does not serve.
 void Env::build_scatter_tables(ApplyPlan& p) {
-  if (!p.g4 || !ctx->use_tma || p.g4->probs.empty()) return;
+  if (!p.g4 || !ctx->use_tma || p.g4->probs.empty() || p.cplx) return;   // complex: four accumulating launches, NCCL path
   if (!comm_stage_ensure(ctx, (size_t)p.nloc)) return;
   gemm_plan_force_tma(*p.g4);
   const Tensor& P = *p.P;
@@ -900,6 +902,32 @@ void Env::apply(const Tensor& v, Tensor& out) {
 // Sharded core: local slice in, local slice of H_eff v out (sum over ranks by reduce-scatter).
 void Env::apply_local(const double* vloc, double* outloc) {
   ApplyPlan& p = *ap;
+  if (p.cplx) {
+    // planar complex vectors: local planes at distance nloc; every contraction is 2-4 launches of the real kernels,
+    // each plane is packed and reduce-scattered on its own
+    const int64_t nl = p.nloc, W = ctx->world;
+    auto imc = [&](const TensorP& t) -> const double* { return t->cplx ? t->im() : nullptr; };
+    cgemm(ctx, *p.g1, p.L->d, imc(p.L), false, vloc, vloc + nl, false, p.T1->d, p.T1->im());
+    run_transform_c(ctx, *p.x2, *p.T1, *p.T2, p.W1->d);
+    run_transform_c(ctx, *p.x3, *p.T2, *p.T3, p.W2->d);
+    cgemm(ctx, *p.g4, p.T3->d, p.T3->im(), false, p.R->d, imc(p.R), false, p.P->d, p.P->im());
+    for (int pl = 0; pl < 2; pl++) {
+      const double* src = pl ? p.P->im() : p.P->d;
+      double* pk = p.packed + pl * W * nl;
+      for (int k = 0; k < W; k++) run_transform(ctx, *p.pack[k], src, pk + (int64_t)k * nl, nullptr);
+      comm_reduce_scatter_sum(ctx, pk, outloc + pl * nl, nl);
+    }
+    if (!more.empty()) {
+      double* tmp = ctx->vec_acquire((size_t)(2 * nl));
+      for (auto& m : more) {
+        m->apply_local(vloc, tmp);
+        vec_axpy(ctx, outloc, tmp, 2 * nl, 1.0);
+      }
+      ctx->vec_release(tmp, 0);
+    }
+    if (!parent) ctx->cnt.apply_count += 1;
+    return;
+  }
   run_gemm(ctx, *p.g1, p.L->d, vloc, p.T1->d);
   run_transform(ctx, *p.x2, p.T1->d, p.T2->d, p.W1->d);
   run_transform(ctx, *p.x3, p.T2->d, p.T3->d, p.W2->d);
@@ -998,10 +1026,9 @@ void Env::apply_ptr(const Tensor& proto, const double* vin, double* vout) {
   if (!parent) ensure_plan(proto);
   ApplyPlan& p = *ap;
   if (p.sharded) {
-    run_transform(ctx, *p.xs, vin, p.loc_in, nullptr);
+    op_to_local(vin, p.loc_in);
     apply_local(p.loc_in, p.loc_out);
-    comm_allgather(ctx, p.loc_out, p.packed, p.nloc);
-    for (int k = 0; k < ctx->world; k++) run_transform(ctx, *p.unpack[k], p.packed + (int64_t)k * p.nloc, vout, nullptr);
+    op_gather(p.loc_out, vout);
     return;
   }
   if (cm) cm_apply(proto, vin, vout);
@@ -1043,11 +1070,19 @@ double Env::expectation(const Tensor& phi) {
 // (templates in krylov.hpp; the sharded Krylov vectors are r-slices, one per rank)
 int64_t Env::op_nloc() const { return ap->nloc; }
 bool Env::op_sharded() const { return ap && ap->sharded; }
-void Env::op_to_local(const double* full, double* loc) { run_transform(ctx, *ap->xs, full, loc, nullptr); }
+// full Krylov vector <-> this rank's r-slice (planar complex: plane by plane; full planes at distance nelem, local
+// planes at distance nloc)
+void Env::op_to_local(const double* full, double* loc) {
+  for (int pl = 0; pl < (ap->cplx ? 2 : 1); pl++)
+    run_transform(ctx, *ap->xs, full + pl * ap->nelem, loc + pl * ap->nloc, nullptr);
+}
 void Env::op_gather(const double* loc, double* full) {
-  comm_allgather(ctx, loc, ap->packed, ap->nloc);
-  for (int k = 0; k < ctx->world; k++)
-    run_transform(ctx, *ap->unpack[k], ap->packed + (int64_t)k * ap->nloc, full, nullptr);
+  const int64_t nl = ap->nloc, W = ctx->world;
+  for (int pl = 0; pl < (ap->cplx ? 2 : 1); pl++) {
+    double* pk = ap->packed + pl * W * nl;
+    comm_allgather(ctx, loc + pl * nl, pk, nl);
+    for (int k = 0; k < W; k++) run_transform(ctx, *ap->unpack[k], pk + (int64_t)k * nl, full + pl * ap->nelem, nullptr);
+  }
 }
 LanczosResult Env::eigsolve(Tensor& phi, double tol, int krylovdim, int maxiter, bool eager) {
   return krylov_eigsolve(ctx, *this, phi, tol, krylovdim, maxiter, eager);

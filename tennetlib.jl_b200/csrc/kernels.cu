@@ -540,7 +540,7 @@ __global__ void stage_wait_consumed_kernel(const volatile unsigned long long* my
     const long long t0 = clock64();
     while (my_flags[64 + k] < need) {
       __nanosleep(100);
-      if (clock64() - t0 > 8000000000ll) __trap();       // a peer died: fail instead of hanging the GPU
+      if (clock64() - t0 > 120000000000ll) __trap();       // a peer died: fail instead of hanging the GPU
     }
   }
 }
@@ -552,7 +552,7 @@ stage_reduce_kernel(double* __restrict__ out, double* slots, int64_t slot_cap, i
     const long long t0 = clock64();
     while (my_flags[threadIdx.x] < epoch) {
       __nanosleep(100);
-      if (clock64() - t0 > 8000000000ll) __trap();
+      if (clock64() - t0 > 120000000000ll) __trap();
     }
   }
   __syncthreads();
@@ -709,7 +709,7 @@ __global__ void peer_allreduce_small_kernel(double* vals, int n, unsigned long l
     volatile unsigned long long* mine = my_hdr + 128 + par * 64 + k;
     const long long t0 = clock64();
     while (*mine < epoch) {
-      if (clock64() - t0 > 8000000000ll) __trap();
+      if (clock64() - t0 > 120000000000ll) __trap();
     }
   }
   __syncthreads();

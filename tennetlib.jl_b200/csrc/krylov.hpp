@@ -111,7 +111,6 @@ LanczosResult krylov_eigsolve(Ctx* ctx, Op& op, Tensor& phi, double tol, int kry
   const bool cx = phi.cplx;
   op.ensure_plan(phi);
   const bool sh = op.op_sharded();                       // Krylov vectors live as r-slices, one per rank
-  TNL_CHECK(!(sh && cx), "complex vectors are not sharded");
   const int64_t n = sh ? op.op_nloc() : phi.nelem;       // plane size
   const int64_t nv = cx ? 2 * n : n;                 // doubles per Krylov vector
   const int howmany = 1;
@@ -120,7 +119,7 @@ LanczosResult krylov_eigsolve(Ctx* ctx, Op& op, Tensor& phi, double tol, int kry
   VecPool pool(ctx, (size_t)nv);
   auto applyraw = [&](double* vin, double* vout) { if (sh) op.apply_local(vin, vout); else op.apply_ptr(phi, vin, vout); };
   // scalar slot pair k = (2k, 2k+1) = (re, im); inner products are reduced over the ranks on the stream
-  auto reduce = [&](int k) { if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + 2 * k, 1); };
+  auto reduce = [&](int k) { if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + 2 * k, cx ? 2 : 1); };
   auto dot = [&](const double* x, const double* y, int k) {
     if (cx) vec_cdot(ctx, x, y, n, 2 * k); else tnl::vec_dot(ctx, x, y, n, 2 * k);
     reduce(k);
@@ -308,7 +307,6 @@ ExpResult krylov_exponentiate(Ctx* ctx, Op& op, Tensor& phi, double t_re, double
   if (tau == 0.0) { res.converged = 1; return res; }
   op.ensure_plan(phi);
   const bool sh = op.op_sharded();
-  TNL_CHECK(!(sh && cx), "complex vectors are not sharded");
   const int64_t n = sh ? op.op_nloc() : phi.nelem;        // plane size
   const int64_t nv = cx ? 2 * n : n;                  // doubles per Krylov vector
   const cd sgn = t / tau;
@@ -319,15 +317,12 @@ ExpResult krylov_exponentiate(Ctx* ctx, Op& op, Tensor& phi, double t_re, double
   auto step = [&](double* w, const double* x, int kin, double a, const double* y, int kout) {
     if (cx) vec_caxpy_cdot(ctx, w, x, n, kin >= 0 ? 2 * kin : -1, a, 0.0, y, 2 * kout);
     else vec_axpy_dot(ctx, w, x, n, kin >= 0 ? 2 * kin : -1, a, y, 2 * kout);
-    if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + 2 * kout, 1);
+    if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + 2 * kout, cx ? 2 : 1);
   };
   // <x, y> into scalar slots (2k, 2k+1) = (re, im); the imaginary part of a real product is left untouched
   auto dot = [&](const double* x, const double* y, int k) {
-    if (cx) vec_cdot(ctx, x, y, n, 2 * k);
-    else {
-      tnl::vec_dot(ctx, x, y, n, 2 * k);
-      if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + 2 * k, 1);
-    }
+    if (cx) vec_cdot(ctx, x, y, n, 2 * k); else tnl::vec_dot(ctx, x, y, n, 2 * k);
+    if (sh) comm_allreduce_sum(ctx, ctx->d_scalars + 2 * k, cx ? 2 : 1);
   };
   auto norm2 = [&](const double* x, int k) {          // |x|^2: one flat pass over both planes
     tnl::vec_dot(ctx, x, x, nv, 2 * k);

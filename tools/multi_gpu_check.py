@@ -63,6 +63,35 @@ for g in (G["dmrg"][0], G["dmrg"][2]):
     ok_all &= good
     print(f"rank {rank}/{world} dmrg {g['name']}: E {sw.energy[-1]:.12f} fixture {g['energy'][-1]:.12f} max dE {de:.2e} "
           f"maxchi {sw.maxchi == g['maxchi']} {'OK' if good else 'FAIL'}", flush=True)
+# ComplexF64 (planar) vectors: sharded vs replicated on the same data -- real-time exponentiate, then the apply and the
+# Lanczos eigensolver on the complex result (plane-by-plane pack / reduce-scatter, two-word scalar all-reduces)
+cpos = 7
+sites = om.siteinds("S=1", 14)
+H = om.heisenberg_mpo(sites)
+qn, dm = om.gaussian_link_sectors(200, 1.3, 4, step=2)
+mps = od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(5)))
+od.orthogonalize(mps, cpos)
+res = {}
+for mode in (True, False):
+    ctx.comm_set_sharding(mode)
+    env_d = T.StateEnvs(ctx, mps.t, H, llim=cpos - 1, rlim=cpos + 1)
+    env_d.set_nsite(2)
+    phi_d = env_d.make_phi(cpos); env_d.position(cpos)
+    phi_d.scale_(1 / phi_d.norm())
+    ctx.reset_counters()
+    _, psi_t = T.exp_solver(env_d, phi_d, -0.2j, solver_krylovdim=12)
+    nops = env_d.last_solver_info["numops"]
+    Hpsi = env_d.product(psi_t)
+    e_c, gs = T.eig_solver(env_d, psi_t.copy())
+    res[mode] = (psi_t.to_host().to_dense(), Hpsi.to_host().to_dense(), e_c, nops, env_d.apply_flops())
+ctx.comm_set_sharding(True)
+(a_t, a_h, a_e, a_n, a_c), (b_t, b_h, b_e, b_n, b_c) = res[True], res[False]
+err_t = np.abs(a_t - b_t).max() / np.abs(b_t).max()
+err_h = np.abs(a_h - b_h).max() / np.abs(b_h).max()
+good = a_c < 0.75 * b_c and err_t < 1e-12 and err_h < 1e-12 and abs(a_e - b_e) < 1e-10 * abs(b_e) and a_n == b_n and np.iscomplexobj(a_t) and np.abs(a_t.imag).max() > 1e-3
+ok_all &= good
+print(f"rank {rank}/{world} complex sharded vs replicated: exp err {err_t:.2e} apply err {err_h:.2e} E {a_e:.12f} / {b_e:.12f} "
+      f"numops {a_n}/{b_n} local apply flops {a_c:.0f} / {b_c:.0f} {'OK' if good else 'FAIL'}", flush=True)
 t = torch.tensor([1.0 if ok_all else 0.0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
