@@ -6,6 +6,8 @@
 // Contraction order follows the reference (L first, then the site operators, then R); in the
 // charge-fused layout each big step is a grouped DGEMM over charge sectors and each site-operator
 // step is one transform pass.
+#include <functional>
+
 #include "env.hpp"
 #include "krylov.hpp"
 
@@ -1565,22 +1567,50 @@ void Env::cm_ensure_plans(const Tensor& proto) {
 }
 
 // ProjCouplingModel.product (src/mps/projcouplingmodel.jl:315-383): sum over ids of contract(v, tensors of the id)
+// Multi-GPU: the sum over term ids (src/mps/projcouplingmodel.jl:340-352) is the natural axis -- every rank applies
+// the ids it owns (longest-processing-time first on the plans' flops, the same assignment on every rank) to the whole
+// replicated vector and the partial results are summed with one all-reduce.
+static std::vector<char> cm_my_plans(Ctx* ctx, size_t nplans, const std::function<double(size_t)>& flops) {
+  const int W = ctx->shard_world();
+  std::vector<char> mine(nplans, 1);
+  if (W <= 1 || nplans < 2) return mine;
+  std::vector<size_t> ord(nplans);
+  std::iota(ord.begin(), ord.end(), 0);
+  std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return flops(a) > flops(b); });
+  std::vector<double> load(W, 0.0);
+  for (size_t i : ord) {
+    const int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+    load[r] += flops(i);
+    mine[i] = r == ctx->rank;
+  }
+  return mine;
+}
+
 void Env::cm_apply(const Tensor& proto, const double* vin, double* vout) {
+  const int64_t nv = proto.planes() * proto.nelem;
+  const std::vector<char> mine = cm_my_plans(ctx, cm->plans.size(), [&](size_t i) { return cm->plans[i].second->flops; });
+  const bool spread = ctx->shard_world() > 1 && cm->plans.size() >= 2;
   double* tmp = nullptr;
   bool first = true;
-  for (auto& pl : cm->plans) {
+  for (size_t i = 0; i < cm->plans.size(); i++) {
+    if (!mine[i]) continue;
+    auto& pl = cm->plans[i];
     if (first) { run_plan(*pl.second, vin, vout); first = false; continue; }
-    const int64_t nv = proto.planes() * proto.nelem;
     if (!tmp) tmp = ctx->vec_acquire((size_t)nv);
     run_plan(*pl.second, vin, tmp);
     vec_axpy(ctx, vout, tmp, nv, 1.0);
   }
   if (tmp) ctx->vec_release(tmp, 0);
+  if (spread) {
+    if (first) CUDA_OK(cudaMemsetAsync(vout, 0, (size_t)nv * sizeof(double), ctx->stream));   // this rank owns no id here
+    comm_allreduce_sum(ctx, vout, nv);
+  }
 }
 
 double Env::cm_apply_flops() const {
+  const std::vector<char> mine = cm_my_plans(ctx, cm->plans.size(), [&](size_t i) { return cm->plans[i].second->flops; });
   double f = 0.0;
-  for (auto& pl : cm->plans) f += pl.second->flops;
+  for (size_t i = 0; i < cm->plans.size(); i++) if (mine[i]) f += cm->plans[i].second->flops;
   return f;
 }
 

@@ -92,6 +92,38 @@ good = a_c < 0.75 * b_c and err_t < 1e-12 and err_h < 1e-12 and abs(a_e - b_e) <
 ok_all &= good
 print(f"rank {rank}/{world} complex sharded vs replicated: exp err {err_t:.2e} apply err {err_h:.2e} E {a_e:.12f} / {b_e:.12f} "
       f"numops {a_n}/{b_n} local apply flops {a_c:.0f} / {b_c:.0f} {'OK' if good else 'FAIL'}", flush=True)
+# CouplingModel: the term ids are distributed over the ranks (one all-reduce per apply) -- product, eig_solver and a
+# DMRG run against the oracle
+from oracle import couplingmodel as oc
+sites = om.siteinds("S=1", 8)
+M = oc.heisenberg_coupling_model(sites, merge=False, field=0.3, j2=0.5)
+qn, dm = om.gaussian_link_sectors(24, 1.3, 4, step=2)
+mps = od.MPS(om.random_mps(sites, qn, dm, np.random.default_rng(3)))
+od.orthogonalize(mps, 4)
+env_o = od.StateEnvs(mps, M)
+env_o.set_nsite(2); env_o.position(4)
+phi_o = ob.contract(env_o.psi[4], env_o.psi[5])
+phi_o = phi_o.scale(1 / phi_o.norm())
+ref = env_o.product(phi_o).permute(phi_o.inds).to_dense()
+e_o, v_o, _ = ok.eigsolve_lanczos(env_o, phi_o)
+env_d = T.StateEnvs(ctx, mps.t, M, llim=3, rlim=5)
+env_d.set_nsite(2)
+phi_d = env_d.make_phi(4); env_d.position(4)
+phi_d.scale_(1 / phi_d.norm())
+err = np.abs(env_d.product(phi_d).to_host().to_dense() - ref).max() / np.abs(ref).max()
+full = None
+ctx.comm_set_sharding(False)
+env_r = T.StateEnvs(ctx, mps.t, M, llim=3, rlim=5)
+env_r.set_nsite(2); env_r.make_phi(4); env_r.position(4)
+env_r.product(phi_d)
+full = env_r.apply_flops()
+ctx.comm_set_sharding(True)
+env_d.product(phi_d)
+e_d, _ = T.eig_solver(env_d, phi_d)
+good = err < 1e-12 and abs(e_d - e_o) < 1e-10 * abs(e_o) and env_d.apply_flops() < 0.8 * full
+ok_all &= good
+print(f"rank {rank}/{world} CouplingModel ids over ranks: apply err {err:.2e} E dev {e_d:.12f} oracle {e_o:.12f} "
+      f"local flops {env_d.apply_flops():.0f} of {full:.0f} {'OK' if good else 'FAIL'}", flush=True)
 t = torch.tensor([1.0 if ok_all else 0.0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
