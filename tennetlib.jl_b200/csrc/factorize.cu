@@ -13,6 +13,7 @@
 #include <cusolverDn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <numeric>
 #include <thread>
@@ -349,6 +350,7 @@ static void syevd_batch(Ctx* ctx, std::vector<EighJob>& jobs) {
     slot_of[k] = used[where[k]]++;
   }
   std::vector<std::string> errs(sides.size());
+  const auto t_batch0 = std::chrono::steady_clock::now();
   auto worker = [&](size_t si) {
     try {
       CUDA_OK(cudaSetDevice(ctx->device));
@@ -391,6 +393,9 @@ static void syevd_batch(Ctx* ctx, std::vector<EighJob>& jobs) {
     for (auto& e : errs) TNL_CHECK(e.empty(), e);
   }
   for (auto& sv : sides) CUDA_OK(cudaStreamSynchronize(sv.s));
+  if (getenv("TNL_EIGH_DEBUG"))
+    fprintf(stderr, "[tnl] syevd_batch: %.2f ms wall\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_batch0).count());
   for (size_t k : order) {
     EighJob& j = jobs[k];
     PartSolver& sv = sides[where[k]];

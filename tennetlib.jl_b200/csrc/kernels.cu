@@ -1,11 +1,16 @@
 // Hand-written sm_100a kernels of the tnl_b200 hot path.
 //
-//  * gemm_kernel      : grouped FP64 GEMM over charge sectors.  Blackwell has no tcgen05/UMMA kind for
-//                       FP64; the FP64 tensor op is the warp-level DMMA.8x8x4 (mma.sync.m8n8k4.f64).
-//                       128x128x16 CTA tiles, 8 warps x (64x32) register tiles, 4-stage cp.async (LDGSTS.128)
-//                       pipeline into bank-conflict-free padded shared memory.  Replaces the per-block-pair
-//                       `permutedims + BLAS.gemm!` loop NDTensors runs for every ITensor `*` on the reference
-//                       hot path (src/mps/projcouplingmodel.jl:145-147,342-343; ITensorMPS ProjMPO.product).
+//  * gemm_tma_ws_kernel: grouped FP64 GEMM over charge sectors (all sectors larger than 64 x 64).  Blackwell has no
+//                       tcgen05/UMMA kind for FP64; the FP64 tensor op is the warp-level DMMA.8x8x4
+//                       (mma.sync.m8n8k4.f64).  Persistent, warp-specialised: a TMA producer warpgroup
+//                       (cp.async.bulk.tensor + mbarriers, 128B-swizzled 128x16 operand tiles, 6 stages) feeds eight
+//                       DMMA warps with 64x32 register tiles; split-K for plans that cannot fill the machine; an
+//                       optional scatter epilogue stores the tiles straight into peer GPUs' staging slots (fused
+//                       reduce-scatter of the sharded apply).  Replaces the per-block-pair `permutedims + BLAS.gemm!`
+//                       loop NDTensors runs for every ITensor `*` on the reference hot path
+//                       (src/mps/projcouplingmodel.jl:145-147,342-343; ITensorMPS ProjMPO.product).
+//  * gemm_kernel      : the same product with cp.async (LDGSTS.128) staging into padded shared memory: 64x64 tiles for
+//                       the small sectors (and 128x128 tiles when TNL_GEMM_TMA=0 selects the round-1 path).
 //  * transform_kernel : HBM-bound regrouping pass that also applies the skinny MPO site operators
 //                       (the `* W_j` steps of ProjMPO.product / `_makeL!`), one warp per output column.
 //  * vec kernels      : flat Krylov-vector kernels (VectorInterface inner/add!!/scale!!/norm as used by

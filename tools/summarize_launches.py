@@ -29,8 +29,10 @@ def main():
     print("| ms | share | launches | kernel |\n|---|---|---|---|")
     for k in sorted(t, key=t.get, reverse=True)[:top]:
         print(f"| {t[k]:.3f} | {100 * t[k] / total:.1f}% | {n[k]} | `{k}` |")
-    ours = sum(v for k, v in t.items() if "tnl::" in k)
-    gemm = sum(v for k, v in t.items() if "tnl::gemm_" in k)
+    own = ("gemm_tma_ws_kernel", "gemm_kernel", "transform_kernel", "relayout_kernel", "permute_kernel", "dot_kernel", "axpy",
+           "scale_kernel", "lincomb_kernel", "splitk_reduce", "stage_", "peer_allreduce", "gather_cols", "scatter_cols", "tnl::")
+    ours = sum(v for k, v in t.items() if any(o in k for o in own))
+    gemm = sum(v for k, v in t.items() if "gemm_tma_ws_kernel" in k or "gemm_kernel" in k)
     print(f"\nkernels of this library (tnl::*): {ours:.1f} ms = {100 * ours / total:.1f}% ; grouped DGEMM: {gemm:.1f} ms = "
           f"{100 * gemm / total:.1f}%")
 
