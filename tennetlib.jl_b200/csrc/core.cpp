@@ -263,14 +263,25 @@ static void make_tiles(GemmPlan& plan) {
       const int GN = 12;
       for (int nb = 0; nb < nt; nb += GN)
         for (int mi = 0; mi < mt; mi++)
-          for (int ni = nb; ni < std::min(nt, nb + GN); ni++)
+          for (int ni = nb; ni < std::min(nt, nb + GN); ni++) {
+            if (plan.lower_only && ni > mi) {        // tile strictly above the diagonal of a symmetric product
+              plan.flops -= 2.0 * std::min(128, p.M - mi * 128) * (double)std::min(128, p.N - ni * 128) * p.K;
+              continue;
+            }
             plan.tiles_tma.push_back(TmaTile{p.c, mi * 128, ni * 128, p.M, p.N, kt, p.ldc, pi, 0, 0, 0});
+          }
       continue;
     }
     int bm = big ? 128 : 64, bn = big ? 128 : 64;
     auto& tl = big ? plan.tiles_big : plan.tiles_small;
     for (int n0 = 0; n0 < p.N; n0 += bn)
-      for (int m0 = 0; m0 < p.M; m0 += bm) tl.push_back(GemmTile{pi, m0, n0});
+      for (int m0 = 0; m0 < p.M; m0 += bm) {
+        if (plan.lower_only && n0 >= m0 + bm) {
+          plan.flops -= 2.0 * std::min(bm, p.M - m0) * (double)std::min(bn, p.N - n0) * p.K;
+          continue;
+        }
+        tl.push_back(GemmTile{pi, m0, n0});
+      }
   }
   // Split-K: a plan that cannot fill the machine with output tiles but has a long contracted range (environment
   // updates of tree nodes: M = N = chi, K = chi^2; Gram matrices of skinny blocks) runs at tiles / #SMs of the DMMA
@@ -312,6 +323,8 @@ static void make_tiles(GemmPlan& plan) {
       if (!plan.splits.empty()) {
         plan.tiles_tma.swap(cut);
         plan.d_splitws = (double*)plan.ctx->alloc((size_t)ws * sizeof(double));
+        // (parts of tiles that are not computed -- lower_only -- must not feed garbage into the reduction)
+        if (plan.lower_only) CUDA_OK(cudaMemsetAsync(plan.d_splitws, 0, (size_t)ws * sizeof(double), plan.ctx->stream));
         plan.d_splits = plan.ctx->upload(plan.splits);
       }
     }
@@ -348,9 +361,11 @@ void gemm_plan_force_tma(GemmPlan& plan) {
   plan.mapsets.clear();
 }
 
-std::unique_ptr<GemmPlan> plan_gemm_raw(Ctx* ctx, bool transA, bool transB, const std::vector<GemmProblem>& probs) {
+std::unique_ptr<GemmPlan> plan_gemm_raw(Ctx* ctx, bool transA, bool transB, const std::vector<GemmProblem>& probs, bool lower_only) {
   auto plan = std::make_unique<GemmPlan>();
   plan->ctx = ctx;
+  plan->lower_only = lower_only;
+  if (lower_only) for (auto& p : probs) TNL_CHECK(p.M == p.N, "lower_only needs square (symmetric) products");
   plan->transA = transA;
   plan->transB = transB;
   for (auto& p : probs) {

@@ -150,6 +150,7 @@ struct SplitDesc { int64_t c, ws; int M, N, ldc, ldw, S, pad; };
 
 struct GemmPlan {
   bool transA = false, transB = false;
+  bool lower_only = false;              // symmetric result (Gram matrices): only tiles that touch the lower triangle
   std::vector<GemmProblem> probs;
   std::vector<GemmTile> tiles_big, tiles_small;
   std::vector<TmaTile> tiles_tma;       // tiles of the sectors larger than 64 in both extents (TMA kernel)
@@ -358,7 +359,10 @@ void run_gemm_reduce_scatter(Ctx* ctx, GemmPlan& p, const double* A, const doubl
 bool plan_all_tma(const GemmPlan& p);
 void gemm_plan_force_tma(GemmPlan& plan);   // every problem on the TMA kernel (also the small sectors)
 // ad-hoc problems (factorisation internals); builds tiles and uploads
-std::unique_ptr<GemmPlan> plan_gemm_raw(Ctx* ctx, bool transA, bool transB, const std::vector<GemmProblem>& probs);
+// lower_only: the products are symmetric (M M^T, M^T M) and the consumer reads the lower triangle only (cuSOLVER
+// CUBLAS_FILL_MODE_LOWER): tiles strictly above the diagonal are not computed
+std::unique_ptr<GemmPlan> plan_gemm_raw(Ctx* ctx, bool transA, bool transB, const std::vector<GemmProblem>& probs,
+                                        bool lower_only = false);
 void gemm_selftest(Ctx* ctx, int M, int N, int K, bool ta, bool tb, int reps, bool verify, double* ms, double* maxerr);
 void comm_unique_id(char* out128);
 void comm_init(Ctx* ctx, const char* uid128, int rank, int world);

@@ -868,7 +868,7 @@ static void refine_gram_spectrum(Ctx* ctx, std::vector<FG>& fg, bool left, const
     if (!subs.empty()) {
       auto g1 = plan_gemm_raw(ctx, left, false, p1);             // left: op(A) = U_T^T
       run_gemm(ctx, *g1, nullptr, nullptr, nullptr);
-      auto g2 = plan_gemm_raw(ctx, !left, left, p2);             // left: B B^T ; right: B^T B
+      auto g2 = plan_gemm_raw(ctx, !left, left, p2, true);       // left: B B^T ; right: B^T B (lower triangle)
       run_gemm(ctx, *g2, nullptr, nullptr, nullptr);
       ctx->sync();
       std::vector<EighJob> jobs;
@@ -1050,7 +1050,7 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
       pr.push_back(p);
     }
     // left: rho = M M^T  (A = M, B^T = M);  right: rho = M^T M (A^T = M, B = M)
-    auto g = plan_gemm_raw(ctx, !left, left, pr);
+    auto g = plan_gemm_raw(ctx, !left, left, pr, /*lower_only: syevd reads the lower triangle*/ true);
     run_gemm(ctx, *g, nullptr, nullptr, nullptr);
     if (noisy) {
       // rho += noise * sum_t X_t X_t^T (one grouped DGEMM + axpy per MPO term; the D buffers are reused)
@@ -1071,7 +1071,7 @@ FactorizeResult factorize(Ctx* ctx, const Tensor& T, const FactorizeParams& prm)
           prn.push_back(p);
         }
         if (prn.empty()) continue;
-        auto gn = plan_gemm_raw(ctx, !left, left, prn);
+        auto gn = plan_gemm_raw(ctx, !left, left, prn, true);
         run_gemm(ctx, *gn, nullptr, nullptr, nullptr);
         i = 0;
         for (FG& f : fg) {
