@@ -540,7 +540,9 @@ std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const 
       int64_t P = 1;
       for (int q = 0; q < MAXP; q++) P *= b.pd[q];
       const bool same = k > 0 && keys[ord[k]] == keys[ord[k - 1]] && plan->groups.back().P == P;
-      if (!same) plan->groups.push_back(XfGroup{c0, P, (int)sorted.size(), 0});
+      if (!same) {
+        plan->groups.push_back(XfGroup{0, P, (int)sorted.size(), 0, 1, 32});
+      }
       plan->groups.back().nb++;
       b.colstart = c0;
       c0 += P;
@@ -548,6 +550,12 @@ std::unique_ptr<TransformPlan> plan_transform(const Tensor& X, Tensor& Y, const 
     }
     plan->blocks.swap(sorted);
     TNL_CHECK(c0 == plan->ncols, "transform groups do not cover the columns");
+    int64_t it = 0;
+    for (XfGroup& g : plan->groups) {
+      g.colstart = it;
+      it += (int64_t)g.nb * ((g.P + g.cpw - 1) / g.cpw);
+    }
+    plan->nitems = it;
   }
   finalize_transform_plan(*plan, W != nullptr);
   return plan;

@@ -224,7 +224,9 @@ struct XfFlat {
 // Output blocks that read the SAME X columns (same leading and passive sectors, different new-index sectors): the
 // kernel walks a group column-major over (passive column, block), so the warps of a CTA that need one X column run
 // next to each other and the column comes from DRAM once (site operators feed 2-3 output blocks from each column).
-struct XfGroup { int64_t colstart; int64_t P; int first; int nb; };
+// `colstart` counts work items: nb * P per group (cpw = 1: one passive column per warp; packing several columns of a
+// tiny leading sector into one warp was tried and changed nothing -- the kernel was bound by per-item bookkeeping).
+struct XfGroup { int64_t colstart; int64_t P; int first; int nb; int cpw; int I2; };
 struct TransformPlan {
   std::vector<XfGroup> groups;
   XfGroup* d_groups = nullptr;
@@ -235,6 +237,7 @@ struct TransformPlan {
   XfFlat* d_flats = nullptr;
   bool pure_copy = false;    // no W: every output column is a copy of one input column (or zero)
   int64_t ncols = 0;
+  int64_t nitems = 0;        // work items of the grouped kernel (plans with W)
   double bytes = 0;          // algorithmic bytes moved (read X once + write Y once)
   double flops = 0;
   Ctx* ctx = nullptr;

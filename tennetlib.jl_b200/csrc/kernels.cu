@@ -897,21 +897,28 @@ void gemm_selftest(Ctx* ctx, int M, int N, int K, bool ta, bool tb, int reps, bo
 // The contributions are flattened to one entry per contracted element, and the X columns of FB entries
 // (FB x 4 x 32 doubles per warp) are requested before the first FMA consumes one (a first kernel with one column in
 // flight per warp was latency bound at ~50 % of the HBM roofline, profiles/r01b_ncu_hbm.md).
-constexpr int XF_FB = 4;
+// The per-contribution bookkeeping is staged once per work item in shared memory: lane f computes the base offset of
+// X column f (64-bit strides x passive coordinates) and fetches its W row, so the streaming loop over the rows is one
+// broadcast LDS for the offset, nn for the weights, four coalesced loads and 4 nn FMAs per contribution.  (ncu of the
+// round-1 kernel, profiles/r02q_ncu_apply.md: 375 M warp instructions and 36 M load requests for 4.1 M data loads --
+// the XfFlat records, the passive-offset arithmetic and the W loads were redone for every 128-row chunk.)
+constexpr int XF_FMAX = 32;                 // contributions staged per pass
 __global__ void __launch_bounds__(256)
 transform_kernel(const XfGroup* __restrict__ groups, int ngroups, const XfBlock* __restrict__ blocks, const XfFlat* __restrict__ flats,
-                    const double* __restrict__ X, double* __restrict__ Y, const double* __restrict__ W, int64_t ncols) {
-  const int lane = threadIdx.x & 31;
+                    const double* __restrict__ X, double* __restrict__ Y, const double* __restrict__ W, int64_t nitems) {
+  __shared__ int64_t s_x[8][XF_FMAX];       // per warp: X offset of (i = 0) of every staged contribution
+  __shared__ double s_w[8][XF_FMAX][4];     // per warp: W(k_f, nc .. nc+3)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; col < ncols; col += nwarps) {
+  for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < nitems; item += nwarps) {
     // work item = (group, passive column, block of the group), block fastest: neighbouring warps share their X columns
     int lo = 0, hi = ngroups - 1;
     while (lo < hi) {
       int mid = (lo + hi + 1) >> 1;
-      if (groups[mid].colstart <= col) lo = mid; else hi = mid - 1;
+      if (groups[mid].colstart <= item) lo = mid; else hi = mid - 1;
     }
     const XfGroup g = groups[lo];
-    const int64_t tg = col - g.colstart;
+    const int64_t tg = item - g.colstart;
     const XfBlock& b = blocks[g.first + (int)(tg % g.nb)];
     int64_t t = tg / g.nb;
     int64_t ybase = b.yoff;
@@ -922,62 +929,84 @@ transform_kernel(const XfGroup* __restrict__ groups, int ngroups, const XfBlock*
       ybase += pidx[k] * b.yps[k];
     }
     const int I = b.I, Na = b.nd0 * b.nd1;
-    const int fend = b.fbeg + b.fnum;
+    const int fbeg = b.fbeg, fnum = b.fnum;
     for (int nc = 0; nc < Na; nc += 4) {
       const int nn = min(4, Na - nc);
+      double* yp[4];
+#pragma unroll
+      for (int n = 0; n < 4; n++) {
+        const int na = nc + (n < nn ? n : 0);
+        yp[n] = Y + ybase + (na % b.nd0) * b.yns[0] + (na / b.nd0) * b.yns[1];
+      }
       for (int i0 = 0; i0 < I; i0 += 128) {
         double acc[4][4];
 #pragma unroll
         for (int n = 0; n < 4; n++)
 #pragma unroll
           for (int u = 0; u < 4; u++) acc[n][u] = 0.0;
-        for (int f0 = b.fbeg; f0 < fend; f0 += XF_FB) {
-          double x[XF_FB][4];
-          const double* wp[XF_FB];
-          int wst[XF_FB];
+        for (int fb = 0; fb < fnum; fb += XF_FMAX) {
+          const int fcnt = min(XF_FMAX, fnum - fb);
+          // (re)stage when the pass changes; with fnum <= XF_FMAX (the rule) once per nc chunk
+          if (i0 == 0 || fnum > XF_FMAX) {
+            __syncwarp();
+            if (lane < fcnt) {
+              const XfFlat& ff = flats[fbeg + fb + lane];
+              int64_t xb = ff.xoff;
 #pragma unroll
-          for (int k = 0; k < XF_FB; k++) {
-            const bool on = f0 + k < fend;
-            const XfFlat& ff = flats[on ? f0 + k : f0];
-            int64_t xb = ff.xoff;
+              for (int q = 0; q < MAXP; q++) xb += pidx[q] * ff.xps[q];
+              s_x[wid][lane] = xb;
+              const double* wr = W + ff.woff + (int64_t)ff.wst * nc;
 #pragma unroll
-            for (int q = 0; q < MAXP; q++) xb += pidx[q] * ff.xps[q];
-            const double* xp = X + xb;
+              for (int n = 0; n < 4; n++) s_w[wid][lane][n] = n < nn ? wr[(int64_t)ff.wst * n] : 0.0;
+            }
+            __syncwarp();
+          }
+          int f = 0;
+          for (; f + 2 <= fcnt; f += 2) {              // two contributions = eight independent loads in flight
+            const double* xa = X + s_x[wid][f];
+            const double* xc = X + s_x[wid][f + 1];
+            double va[4], vc[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
               const int i = i0 + lane + 32 * u;
-              x[k][u] = (on && i < I) ? xp[i] : 0.0;
+              va[u] = i < I ? xa[i] : 0.0;
+              vc[u] = i < I ? xc[i] : 0.0;
             }
-            wp[k] = on ? W + ff.woff + (int64_t)ff.wst * nc : nullptr;
-            wst[k] = ff.wst;
+#pragma unroll
+            for (int n = 0; n < 4; n++) {
+              const double wa = s_w[wid][f][n], wc = s_w[wid][f + 1][n];
+#pragma unroll
+              for (int u = 0; u < 4; u++) acc[n][u] = fma(vc[u], wc, fma(va[u], wa, acc[n][u]));
+            }
           }
+          if (f < fcnt) {
+            const double* xa = X + s_x[wid][f];
+            double va[4];
 #pragma unroll
-          for (int k = 0; k < XF_FB; k++) {
-            if (wp[k]) {
+            for (int u = 0; u < 4; u++) {
+              const int i = i0 + lane + 32 * u;
+              va[u] = i < I ? xa[i] : 0.0;
+            }
 #pragma unroll
-              for (int n = 0; n < 4; n++) {
-                if (n < nn) {
-                  const double w = wp[k][(int64_t)wst[k] * n];
+            for (int n = 0; n < 4; n++) {
+              const double wa = s_w[wid][f][n];
 #pragma unroll
-                  for (int u = 0; u < 4; u++) acc[n][u] = fma(x[k][u], w, acc[n][u]);
-                }
-              }
+              for (int u = 0; u < 4; u++) acc[n][u] = fma(va[u], wa, acc[n][u]);
             }
           }
         }
 #pragma unroll
         for (int n = 0; n < 4; n++) {
           if (n < nn) {
-            const int na = nc + n;
-            double* yp = Y + ybase + (na % b.nd0) * b.yns[0] + (na / b.nd0) * b.yns[1];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
               const int i = i0 + lane + 32 * u;
-              if (i < I) yp[i] = acc[n][u];
+              if (i < I) yp[n][i] = acc[n][u];
             }
           }
         }
       }
+      __syncwarp();                                    // the staging area is rewritten for the next nc chunk / item
     }
   }
 }
@@ -1029,12 +1058,12 @@ relayout_kernel(const XfBlock* __restrict__ blocks, int nblocks, const XfFlat* _
 void run_transform(Ctx* ctx, TransformPlan& p, const double* X, double* Y, const double* W) {
   if (p.ncols == 0) return;
   Ctx::Scope prof_scope(ctx, 1);
-  int64_t warps_needed = p.ncols;
+  int64_t warps_needed = W ? p.nitems : p.ncols;
   int64_t blocks = std::min<int64_t>((warps_needed + 7) / 8, (int64_t)ctx->num_sms * 32);
   if (!W) {
     relayout_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_blocks, (int)p.blocks.size(), p.d_flats, X, Y, p.ncols);
   } else {
-    transform_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_groups, (int)p.groups.size(), p.d_blocks, p.d_flats, X, Y, W, p.ncols);
+    transform_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(p.d_groups, (int)p.groups.size(), p.d_blocks, p.d_flats, X, Y, W, p.nitems);
   }
   CUDA_OK(cudaGetLastError());
   ctx->cnt.launches++;
