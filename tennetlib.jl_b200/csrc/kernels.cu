@@ -899,7 +899,8 @@ void gemm_selftest(Ctx* ctx, int M, int N, int K, bool ta, bool tb, int reps, bo
 // flight per warp was latency bound at ~50 % of the HBM roofline, profiles/r01b_ncu_hbm.md).
 // The per-contribution bookkeeping is staged once per work item in shared memory: lane f computes the base offset of
 // X column f (64-bit strides x passive coordinates) and fetches its W row, so the streaming loop over the rows is one
-// broadcast LDS for the offset, nn for the weights, four coalesced loads and 4 nn FMAs per contribution.  (ncu of the
+// broadcast LDS for the offset, nn for the weights, four coalesced loads and 4 nn FMAs per contribution, four
+// contributions (sixteen loads) in flight.  (ncu of the
 // round-1 kernel, profiles/r02q_ncu_apply.md: 375 M warp instructions and 36 M load requests for 4.1 M data loads --
 // the XfFlat records, the passive-offset arithmetic and the W loads were redone for every 128-row chunk.)
 constexpr int XF_FMAX = 32;                 // contributions staged per pass
@@ -961,37 +962,28 @@ transform_kernel(const XfGroup* __restrict__ groups, int ngroups, const XfBlock*
             }
             __syncwarp();
           }
-          int f = 0;
-          for (; f + 2 <= fcnt; f += 2) {              // two contributions = eight independent loads in flight
-            const double* xa = X + s_x[wid][f];
-            const double* xc = X + s_x[wid][f + 1];
-            double va[4], vc[4];
+          for (int f = 0; f < fcnt; f += 4) {           // four contributions = sixteen independent loads in flight
+            double v[4][4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const int i = i0 + lane + 32 * u;
-              va[u] = i < I ? xa[i] : 0.0;
-              vc[u] = i < I ? xc[i] : 0.0;
+            for (int k = 0; k < 4; k++) {
+              const bool on = f + k < fcnt;
+              const double* xp = X + s_x[wid][on ? f + k : f];
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const int i = i0 + lane + 32 * u;
+                v[k][u] = (on && i < I) ? xp[i] : 0.0;
+              }
             }
 #pragma unroll
-            for (int n = 0; n < 4; n++) {
-              const double wa = s_w[wid][f][n], wc = s_w[wid][f + 1][n];
+            for (int k = 0; k < 4; k++) {
+              if (f + k < fcnt) {
 #pragma unroll
-              for (int u = 0; u < 4; u++) acc[n][u] = fma(vc[u], wc, fma(va[u], wa, acc[n][u]));
-            }
-          }
-          if (f < fcnt) {
-            const double* xa = X + s_x[wid][f];
-            double va[4];
+                for (int n = 0; n < 4; n++) {
+                  const double w = s_w[wid][f + k][n];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const int i = i0 + lane + 32 * u;
-              va[u] = i < I ? xa[i] : 0.0;
-            }
-#pragma unroll
-            for (int n = 0; n < 4; n++) {
-              const double wa = s_w[wid][f][n];
-#pragma unroll
-              for (int u = 0; u < 4; u++) acc[n][u] = fma(va[u], wa, acc[n][u]);
+                  for (int u = 0; u < 4; u++) acc[n][u] = fma(v[k][u], w, acc[n][u]);
+                }
+              }
             }
           }
         }
