@@ -100,6 +100,21 @@ static PartSet& part_set(int device, const std::vector<int>& units) {
     CUSOLVER_OK(cusolverDnCreate(&sv.h));
     CUSOLVER_OK(cusolverDnSetStream(sv.h, sv.s));
     CUDA_OK(cudaMalloc(&sv.info, 64 * sizeof(int)));
+    // first call on a handle pays its lazy initialisation (internal buffers, kernel loading): do it here, on a 96 x 96
+    // identity, instead of inside the first real decomposition
+    const int n = 96;
+    double *A = nullptr, *Wv = nullptr, *wk = nullptr;
+    int lw = 0;
+    CUDA_OK(cudaMalloc(&A, sizeof(double) * n * n));
+    CUDA_OK(cudaMalloc(&Wv, sizeof(double) * n));
+    std::vector<double> eye((size_t)n * n, 0.0);
+    for (int i = 0; i < n; i++) eye[(size_t)i * n + i] = 1.0 + i;
+    CUDA_OK(cudaMemcpy(A, eye.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    CUSOLVER_OK(cusolverDnDsyevd_bufferSize(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, A, n, Wv, &lw));
+    CUDA_OK(cudaMalloc(&wk, sizeof(double) * std::max(lw, 1)));
+    CUSOLVER_OK(cusolverDnDsyevd(sv.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, A, n, Wv, wk, lw, sv.info));
+    CUDA_OK(cudaStreamSynchronize(sv.s));
+    cudaFree(A); cudaFree(Wv); cudaFree(wk);
   };
   if (units.size() == 1) {                         // whole device
     ps.parts.resize(1);
@@ -319,6 +334,16 @@ static void syevd_batch(Ctx* ctx, std::vector<EighJob>& jobs) {
   std::vector<int64_t> jn;
   std::vector<char> jc;
   for (auto& j : jobs) { jn.push_back(j.n); jc.push_back(j.cplx ? 1 : 0); }
+  {
+    // create every candidate set (green contexts, streams, cuSOLVER handles) the first time a batch with a large
+    // decomposition arrives: the set changes from bond to bond, and a lazily created one would put its one-off cost
+    // (hundreds of milliseconds) into the middle of a sweep
+    static std::map<int, bool> warmed;
+    if (!warmed[ctx->device] && jobs[order[0]].n >= 512 && !getenv("TNL_EIGH_PARTS")) {
+      warmed[ctx->device] = true;
+      for (auto& u : kPartCandidates) part_set(ctx->device, u);
+    }
+  }
   PartSet* ps = nullptr;
   std::vector<int> where;
   {
