@@ -132,6 +132,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def hbm_rooflines(cnt, prof, steps):
+    """HBM-bound kernel classes of the step (this rank): algorithmic bytes (read + written once)
+    over the CUDA-event time of the class, against the measured copy bandwidth of MEASURED_PEAKS.json (driver-written;
+    fallback: 6548 GB/s measured on this pool in round 1, profiles/r01_peaks_fp64.json)."""
+    peak, src = 6547.8, "profiles/r01_peaks_fp64.json (copy, measured on this pool)"
+    try:
+        mp = json.load(open(os.path.join(HERE, "MEASURED_PEAKS.json")))
+        peak, src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    out = {"peak": peak, "unit": "GB/s", "peak_source": src}
+    for name, key, cat in (("transform", "transform_bytes", "transform"), ("krylov_vectors", "vec_bytes", "vector")):
+        ms = prof["category_ms"].get(cat, 0.0)
+        gbs = cnt[key] / 1e9 / (ms * 1e-3) if ms > 0 else 0.0
+        out[name] = {"bound": "hbm", "achieved": gbs, "frac": gbs / peak, "algorithmic_gb_per_step": cnt[key] / steps / 1e9,
+                     "device_ms_per_step": ms / steps}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def workload_config(args):
     return {"workload": "S=1 Heisenberg chain N=%d U(1) QN two-site DMRG chi=%d (BASELINE.json configs[1])" % (args.nsites, args.chi),
@@ -589,6 +608,7 @@ def run_ours(args):
             "setup_s": t_setup,
             "krylov_vec": {"algorithmic_gb_per_step": cnt["vec_bytes"] / args.steps / 1e9},
             "transform": {"algorithmic_gb_per_step": cnt["transform_bytes"] / args.steps / 1e9},
+            "roofline_hbm": hbm_rooflines(cnt, prof, args.steps),
             "device_ms_per_step_by_kernel_class": {k: v / args.steps for k, v in prof["category_ms"].items()},
             "device_ms_per_step_by_phase_and_kernel_class": {ph: {k: v / args.steps for k, v in d.items()}
                                                              for ph, d in sysenv.phase_kernel_ms.items()},
