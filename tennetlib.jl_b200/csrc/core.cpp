@@ -28,6 +28,7 @@ Ctx::Ctx(int dev) : device(dev) {
   CUDA_OK(cudaMalloc(&d_partials, 4096 * sizeof(double)));
   CUDA_OK(cudaMalloc(&d_info, 16 * sizeof(int)));
   if (const char* e = getenv("TNL_GEMM_TMA")) use_tma = atoi(e) != 0;
+  if (const char* e = getenv("TNL_GEMM_DUAL")) dual_gemm = atoi(e) != 0;
 }
 // Pinned staging memory for cudaMemcpyAsync sources that the host fills and forgets: a ring; when it wraps the
 // stream is drained once so that no pending copy still reads the bytes about to be overwritten.

@@ -335,6 +335,7 @@ class Ctx {
   unsigned char* pin_ring = nullptr; size_t pin_cap = 0, pin_off = 0;
   void* stage_pinned(size_t bytes);
   bool use_tma = true;              // grouped GEMM through the TMA kernel (TNL_GEMM_TMA=0 selects the cp.async kernel)
+  bool dual_gemm = true;            // complex x complex products: one dual-source launch per plane (TNL_GEMM_DUAL=0: four launches)
   void sync() { CUDA_OK(cudaStreamSynchronize(stream)); }
   template <class T> T* upload(const std::vector<T>& v) {
     if (v.empty()) return nullptr;

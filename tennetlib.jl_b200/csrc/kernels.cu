@@ -349,13 +349,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
 
+// EPI = 2 (planar complex products): two operand pairs share the accumulators, C = alpha * (A1 B1 +- A2 B2) -- the k loop
+// runs over the first pair's k-tiles and then over the second pair's; for "-" the accumulators are negated at the
+// boundary and once more at the end.  One launch per plane of a complex x complex product instead of two, no
+// read-modify-write of C, twice the k range per tile.
 // EPI = 0: C = alpha * A B (+ C) in place.  EPI = 1 (multi-GPU): scatter epilogue -- every element is stored into the
 // staging slot of the rank that owns its column (peer memory over NVLink), and the last CTA to finish flags "epoch
 // complete" to every peer (see run_gemm_reduce_scatter).
 template <bool KFA, bool KFB, int STAGES, int EPI>
 __global__ void __launch_bounds__(384, 1)
 gemm_tma_ws_kernel(const TmaTile* __restrict__ tiles, int ntiles, const TmaDesc* __restrict__ maps, double* __restrict__ Cbase,
-                   double* __restrict__ Wbase, double alpha, int accum, ScatterArgs sargs) {
+                   double* __restrict__ Wbase, double alpha, int accum, ScatterArgs sargs, const TmaDesc* __restrict__ maps2,
+                   int negate2) {
   constexpr int MI = 8, NI = 4;
   constexpr int TILE_ELEMS = 128 * 16;
   constexpr int STAGE_ELEMS = 2 * TILE_ELEMS;
@@ -383,17 +388,19 @@ gemm_tma_ws_kernel(const TmaTile* __restrict__ tiles, int ntiles, const TmaDesc*
       uint32_t phase = 1;                          // a fresh mbarrier passes a wait on parity 1
       for (int ti = blockIdx.x; ti < ntiles; ti += G) {
         const int m0 = tiles[ti].m0, n0 = tiles[ti].n0, kt1 = tiles[ti].kt0 + tiles[ti].ktiles;
-        const TmaDesc* ma = maps + 2 * tiles[ti].prob;
-        for (int kt = tiles[ti].kt0; kt < kt1; kt++) {
-          mbar_wait(empty0 + 8 * stage, phase);
-          const uint32_t bar = full0 + 8 * stage;
-          const uint32_t dA = base_u32 + stage * STAGE_BYTES, dB = dA + TILE_ELEMS * 8;
-          mbar_arrive_expect_tx(bar, STAGE_BYTES);
-          if (KFA) tma_load_2d(dA, ma, bar, kt * 16, m0);
-          else tma_load_3d(dA, ma, bar, 0, kt * 16, m0 >> 4);
-          if (KFB) tma_load_2d(dB, ma + 1, bar, kt * 16, n0);
-          else tma_load_3d(dB, ma + 1, bar, 0, kt * 16, n0 >> 4);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        for (int half = 0; half < (EPI == 2 ? 2 : 1); half++) {
+          const TmaDesc* ma = (half ? maps2 : maps) + 2 * tiles[ti].prob;
+          for (int kt = tiles[ti].kt0; kt < kt1; kt++) {
+            mbar_wait(empty0 + 8 * stage, phase);
+            const uint32_t bar = full0 + 8 * stage;
+            const uint32_t dA = base_u32 + stage * STAGE_BYTES, dB = dA + TILE_ELEMS * 8;
+            mbar_arrive_expect_tx(bar, STAGE_BYTES);
+            if (KFA) tma_load_2d(dA, ma, bar, kt * 16, m0);
+            else tma_load_3d(dA, ma, bar, 0, kt * 16, m0 >> 4);
+            if (KFB) tma_load_2d(dB, ma + 1, bar, kt * 16, n0);
+            else tma_load_3d(dB, ma + 1, bar, 0, kt * 16, n0 >> 4);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -438,7 +445,14 @@ gemm_tma_ws_kernel(const TmaTile* __restrict__ tiles, int ntiles, const TmaDesc*
     for (int i = 0; i < MI; i++)
 #pragma unroll
       for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    for (int kt = 0; kt < cur.ktiles; kt++) {
+    const int nkt = EPI == 2 ? 2 * cur.ktiles : cur.ktiles;
+    for (int kt = 0; kt < nkt; kt++) {
+      if (EPI == 2 && negate2 && kt == cur.ktiles) {     // second operand pair enters with the opposite sign
+#pragma unroll
+        for (int i = 0; i < MI; i++)
+#pragma unroll
+          for (int j = 0; j < NI; j++) { acc[i][j][0] = -acc[i][j][0]; acc[i][j][1] = -acc[i][j][1]; }
+      }
       const double* st = smem + c_stage * STAGE_ELEMS;
       const int n_stage = (c_stage + 1 == STAGES) ? 0 : c_stage + 1;
       const uint32_t n_phase = (c_stage + 1 == STAGES) ? (c_phase ^ 1u) : c_phase;
@@ -450,7 +464,7 @@ gemm_tma_ws_kernel(const TmaTile* __restrict__ tiles, int ntiles, const TmaDesc*
           for (int i = 0; i < MI; i++) a[nb][i] = TNL_FRAG_A(st, s + 1, i);
 #pragma unroll
           for (int j = 0; j < NI; j++) b[nb][j] = TNL_FRAG_B(st, s + 1, j);
-        } else if ((kt + 1 < cur.ktiles) || (tn < ntiles)) {
+        } else if ((kt + 1 < nkt) || (tn < ntiles)) {
           // first fragments of the next k-tile of this CTA's sequence (possibly of the next output tile)
           mbar_wait(full0 + 8 * n_stage, n_phase);
           const double* ns = smem + n_stage * STAGE_ELEMS;
@@ -470,7 +484,13 @@ gemm_tma_ws_kernel(const TmaTile* __restrict__ tiles, int ntiles, const TmaDesc*
       c_stage = n_stage;
       c_phase = n_phase;
     }
-    if (EPI == 0) {
+    if (EPI == 2 && negate2) {
+#pragma unroll
+      for (int i = 0; i < MI; i++)
+#pragma unroll
+        for (int j = 0; j < NI; j++) { acc[i][j][0] = -acc[i][j][0]; acc[i][j][1] = -acc[i][j][1]; }
+    }
+    if (EPI == 0 || EPI == 2) {
       // split-K part: raw partial product into the workspace (alpha and the accumulate mode are applied by the reduction)
       double* pC = (cur.split ? Wbase : Cbase) + cur.c;
       const double al = cur.split ? 1.0 : alpha;
@@ -662,7 +682,7 @@ splitk_reduce_kernel(const SplitDesc* __restrict__ sd, int nsplit, double* __res
 
 template <bool KFA, bool KFB, int EPI = 0>
 static void launch_gemm_tma_one(Ctx* ctx, GemmPlan& p, const TmaDesc* maps, double* C, double alpha, int accum,
-                                const ScatterArgs& sargs = ScatterArgs()) {
+                                const ScatterArgs& sargs = ScatterArgs(), const TmaDesc* maps2 = nullptr, int negate2 = 0) {
   constexpr int STAGES = 6;
   constexpr size_t SMEM = (size_t)STAGES * 2 * 128 * 16 * sizeof(double) + 2 * STAGES * 8 + 1024;
   auto kern = gemm_tma_ws_kernel<KFA, KFB, STAGES, EPI>;
@@ -673,7 +693,7 @@ static void launch_gemm_tma_one(Ctx* ctx, GemmPlan& p, const TmaDesc* maps, doub
   }
   const int ntiles = (int)p.tiles_tma.size();
   const int grid = std::min(ntiles, ctx->num_sms);
-  kern<<<grid, 384, SMEM, ctx->stream>>>(p.d_tiles_tma, ntiles, maps, C, p.d_splitws, alpha, accum, sargs);
+  kern<<<grid, 384, SMEM, ctx->stream>>>(p.d_tiles_tma, ntiles, maps, C, p.d_splitws, alpha, accum, sargs, maps2, negate2);
   if (!p.splits.empty()) {
     TNL_CHECK(EPI == 0, "split-K parts cannot be scattered");
     int64_t big = 0;
@@ -786,6 +806,48 @@ void run_gemm_reduce_scatter(Ctx* ctx, GemmPlan& p, const double* A, const doubl
     ctx->cnt.launches += 2;
     ctx->cnt.allreduce_bytes += 8.0 * nloc * ctx->world;
   }
+}
+
+// C = s1 * A1 B1 + s2 * A2 B2   (s1, s2 = +-1): the two halves of one plane of a complex x complex product.  The
+// 128x128 tiles take both operand pairs in one launch (EPI = 2); small tiles and split-K plans fall back to two
+// accumulating launches.
+void run_gemm_dual(Ctx* ctx, GemmPlan& p, const double* A1, const double* B1, double s1, const double* A2, const double* B2, double s2,
+                   double* C) {
+  if (p.tiles_tma.empty() || !p.splits.empty()) {
+    run_gemm(ctx, p, A1, B1, C, s1, false);
+    run_gemm(ctx, p, A2, B2, C, s2, true);
+    return;
+  }
+  for (auto& z : p.zero_fill) CUDA_OK(cudaMemsetAsync(C + z.first, 0, z.second * sizeof(double), ctx->stream));
+  Ctx::ProfRec rec{};
+  const bool prof = ctx->prof_gemm;
+  if (prof) {
+    CUDA_OK(cudaEventCreate(&rec.a));
+    CUDA_OK(cudaEventCreate(&rec.b));
+    CUDA_OK(cudaEventRecord(rec.a, ctx->stream));
+  }
+  tma_maps_for(ctx, p, A1, B1);
+  const TmaDesc* m2 = tma_maps_for(ctx, p, A2, B2);
+  const TmaDesc* m1 = tma_maps_for(ctx, p, A1, B1);      // (again: the second request may have recycled the cache)
+  const int neg = (s2 * s1 < 0) ? 1 : 0;
+  const bool kfa = p.transA, kfb = !p.transB;
+  if (kfa && kfb) launch_gemm_tma_one<true, true, 2>(ctx, p, m1, C, s1, 0, ScatterArgs(), m2, neg);
+  else if (kfa && !kfb) launch_gemm_tma_one<true, false, 2>(ctx, p, m1, C, s1, 0, ScatterArgs(), m2, neg);
+  else if (!kfa && kfb) launch_gemm_tma_one<false, true, 2>(ctx, p, m1, C, s1, 0, ScatterArgs(), m2, neg);
+  else launch_gemm_tma_one<false, false, 2>(ctx, p, m1, C, s1, 0, ScatterArgs(), m2, neg);
+  // sectors below 64 in an extent: the cp.async kernel, two accumulating launches
+  launch_gemm_cfg<128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, (int)p.tiles_big.size(), A1, B1, C, s1, 0);
+  launch_gemm_cfg<128, 128, 16, 64, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_big, (int)p.tiles_big.size(), A2, B2, C, s2, 1);
+  launch_gemm_cfg<64, 64, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_small, (int)p.tiles_small.size(), A1, B1, C, s1, 0);
+  launch_gemm_cfg<64, 64, 16, 32, 32, 4>(ctx, p.transA, p.transB, p.d_probs, p.d_tiles_small, (int)p.tiles_small.size(), A2, B2, C, s2, 1);
+  if (prof) {
+    CUDA_OK(cudaEventRecord(rec.b, ctx->stream));
+    rec.flops = 2.0 * p.flops;
+    rec.cat = 0;
+    rec.tiles = (int)(p.tiles_big.size() + p.tiles_small.size() + p.tiles_tma.size());
+    ctx->prof_recs.push_back(rec);
+  }
+  ctx->cnt.gemm_flops += 2.0 * p.flops;
 }
 
 void run_gemm(Ctx* ctx, GemmPlan& p, const double* A, const double* B, double* C, double alpha, bool accum) {
@@ -1477,6 +1539,12 @@ void vec_clincomb(Ctx* ctx, double* y, const double* const* xs, const double* cr
 void cgemm(Ctx* ctx, GemmPlan& p, const double* Ar, const double* Ai, bool conjA, const double* Br, const double* Bi,
            bool conjB, double* Cr, double* Ci) {
   const double sA = conjA ? -1.0 : 1.0, sB = conjB ? -1.0 : 1.0;
+  if (Ai && Bi && Ci && ctx->use_tma && ctx->dual_gemm) {
+    // complex x complex: one dual-source launch per plane
+    run_gemm_dual(ctx, p, Ar, Br, 1.0, Ai, Bi, -sA * sB, Cr);
+    run_gemm_dual(ctx, p, Ar, Bi, sB, Ai, Br, sA, Ci);
+    return;
+  }
   run_gemm(ctx, p, Ar, Br, Cr, 1.0, false);
   if (Ai && Bi) run_gemm(ctx, p, Ai, Bi, Cr, -sA * sB, true);
   if (!Ci) { TNL_CHECK(!Ai && !Bi, "complex product needs a complex result"); return; }
